@@ -1,0 +1,381 @@
+"""Synthetic benchmark / parity systems and writers for the
+GOMC input files (PDB / PSF / Mie parameter file / in.conf) that let the
+reference itself (oracle/_ref probe) read exactly the same system.
+
+Pure numpy host code: no CUDA, no oracle.  Coordinates are rounded to the
+three decimals a PDB file carries so that the arrays here and what the
+reference parses are bit-identical.
+
+Force-field derivation follows Forcefield::Init (src/Forcefield.cpp:77-84) and
+FFParticle::Blend (src/FFParticle.cpp:155-199).
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+VDW_STD, VDW_SHIFT, VDW_SWITCH = 0, 1, 2
+_POT_NAME = {VDW_STD: "VDW", VDW_SHIFT: "SHIFT", VDW_SWITCH: "SWITCH"}
+
+
+@dataclass
+class MolKind:
+    name: str                 # residue name (<= 4 chars)
+    atom_names: list          # per atom
+    atom_types: list          # per atom, FF type name
+    charges: list             # per atom (e)
+    masses: list
+    bonds: list = field(default_factory=list)    # (i, j) local indices
+    angles: list = field(default_factory=list)   # (i, j, k)
+    local_xyz: np.ndarray | None = None           # rigid template, (natoms, 3)
+
+
+@dataclass
+class ForceField:
+    type_names: list          # FF atom types, order == kind index
+    epsilon: np.ndarray       # K, per type
+    sigma: np.ndarray         # Angstrom, per type
+    n: np.ndarray             # Mie exponent, per type
+    vdw_kind: int = VDW_STD
+    r_cut: float = 10.0
+    r_cut_low: float = 1.0
+    r_switch: float = 0.0
+    r_cut_coulomb: float = 10.0
+    tolerance: float = 1e-5
+    ewald: bool = True
+    electrostatic: bool = True
+    lrc: bool = True
+    bond_params: list = field(default_factory=list)   # (t1, t2, b0)
+    angle_params: list = field(default_factory=list)  # (t1, t2, t3, theta0)
+
+    # ---- derived exactly as the reference derives them -------------------
+    @property
+    def alpha(self) -> float:           # src/Forcefield.cpp:80
+        return math.sqrt(-math.log(self.tolerance)) / self.r_cut_coulomb
+
+    @property
+    def recip_rcut(self) -> float:      # src/Forcefield.cpp:82
+        return -2.0 * math.log(self.tolerance) / self.r_cut_coulomb
+
+    def tables(self):
+        """sigmaSq, epsilon_cn, n as [K*K] tables, index k1 + k2*K
+        (src/FFParticle.cpp:155-199, arithmetic-mean sigma, geometric epsilon,
+        arithmetic n)."""
+        K = len(self.type_names)
+        sig = np.zeros(K * K)
+        eps_cn = np.zeros(K * K)
+        nn = np.zeros(K * K)
+        for i in range(K):
+            for j in range(K):
+                idx = i + j * K
+                n_ij = (self.n[i] + self.n[j]) * 0.5
+                cn = n_ij / (n_ij - 6.0) * math.pow(n_ij / 6.0, 6.0 / (n_ij - 6.0))
+                s = (self.sigma[i] + self.sigma[j]) * 0.5
+                e = math.sqrt(self.epsilon[i] * self.epsilon[j])
+                sig[idx] = s * s
+                eps_cn[idx] = cn * e
+                nn[idx] = n_ij
+        return sig, eps_cn, nn
+
+
+@dataclass
+class System:
+    name: str
+    ff: ForceField
+    mol_kinds: list           # [MolKind]
+    axis: np.ndarray          # (3,) orthogonal box
+    x: np.ndarray
+    y: np.ndarray
+    z: np.ndarray
+    kind: np.ndarray          # int32 per atom: FF type index
+    mol: np.ndarray           # int32 per atom: molecule index
+    charge: np.ndarray        # per atom
+    mol_start: np.ndarray     # int32 [nMols+1]
+    mol_kind: np.ndarray      # int32 per molecule
+
+    @property
+    def n_atoms(self) -> int:
+        return int(self.x.shape[0])
+
+    @property
+    def n_mols(self) -> int:
+        return int(self.mol_kind.shape[0])
+
+    def com(self):
+        """Geometric centre of every molecule after unwrapping about its first
+        atom, wrapped back into the box (what COM::CalcCOM does with
+        uniform weights; used only as the torque reference point)."""
+        L = self.axis
+        cx = np.zeros(self.n_mols)
+        cy = np.zeros(self.n_mols)
+        cz = np.zeros(self.n_mols)
+        for arr, out, ax in ((self.x, cx, L[0]), (self.y, cy, L[1]), (self.z, cz, L[2])):
+            ref = arr[self.mol_start[:-1]]
+            lens = np.diff(self.mol_start)
+            refa = np.repeat(ref, lens)
+            d = arr - refa
+            d -= ax * np.round(d / ax)
+            s = np.add.reduceat(d, self.mol_start[:-1])
+            c = ref + s / lens
+            out[:] = np.mod(c, ax)
+        return cx, cy, cz
+
+
+# --------------------------------------------------------------------------
+def _rand_rotations(rng, n):
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    R = np.empty((n, 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z)
+    R[:, 0, 1] = 2 * (x * y - z * w)
+    R[:, 0, 2] = 2 * (x * z + y * w)
+    R[:, 1, 0] = 2 * (x * y + z * w)
+    R[:, 1, 1] = 1 - 2 * (x * x + z * z)
+    R[:, 1, 2] = 2 * (y * z - x * w)
+    R[:, 2, 0] = 2 * (x * z - y * w)
+    R[:, 2, 1] = 2 * (y * z + x * w)
+    R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def _lattice(n, L, rng, jitter):
+    m = int(math.ceil(n ** (1.0 / 3.0) - 1e-9))
+    a = L / m
+    g = np.arange(m)
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    sel = rng.permutation(pts.shape[0])[:n]
+    sel.sort()
+    pos = (pts[sel] + 0.5) * a
+    pos += rng.uniform(-jitter, jitter, size=pos.shape)
+    return pos
+
+
+def _assemble(name, ff, mol_kinds, counts, L, seed, jitter=0.3):
+    rng = np.random.default_rng(seed)
+    n_mols = int(sum(counts))
+    centres = _lattice(n_mols, L, rng, jitter)
+    order = rng.permutation(n_mols)          # mix kinds over lattice sites
+    type_index = {t: i for i, t in enumerate(ff.type_names)}
+    xs, kinds, mols, charges, starts, mkind = [], [], [], [], [0], []
+    site = 0
+    m = 0
+    for k, (mk, cnt) in enumerate(zip(mol_kinds, counts)):
+        na = len(mk.atom_names)
+        tmpl = mk.local_xyz if mk.local_xyz is not None else np.zeros((na, 3))
+        tmpl = tmpl - tmpl.mean(axis=0)
+        R = _rand_rotations(rng, cnt) if na > 1 else np.tile(np.eye(3), (cnt, 1, 1))
+        c = centres[order[site:site + cnt]]
+        site += cnt
+        pos = np.einsum("mij,aj->mai", R, tmpl) + c[:, None, :]
+        xs.append(pos.reshape(-1, 3))
+        kinds.append(np.tile([type_index[t] for t in mk.atom_types], cnt))
+        charges.append(np.tile(np.asarray(mk.charges, dtype=np.float64), cnt))
+        mols.append(np.repeat(np.arange(m, m + cnt), na))
+        starts.extend(starts[-1] + na * (np.arange(cnt) + 1))
+        mkind.extend([k] * cnt)
+        m += cnt
+    pos = np.concatenate(xs)
+    pos = np.mod(pos, L)
+    pos = np.round(pos, 3)
+    pos[pos >= L] -= L     # rounding may land exactly on L
+    pos = np.round(pos, 3)
+    return System(
+        name=name, ff=ff, mol_kinds=list(mol_kinds),
+        axis=np.array([L, L, L], dtype=np.float64),
+        x=np.ascontiguousarray(pos[:, 0]), y=np.ascontiguousarray(pos[:, 1]),
+        z=np.ascontiguousarray(pos[:, 2]),
+        kind=np.concatenate(kinds).astype(np.int32),
+        mol=np.concatenate(mols).astype(np.int32),
+        charge=np.concatenate(charges),
+        mol_start=np.asarray(starts, dtype=np.int32),
+        mol_kind=np.asarray(mkind, dtype=np.int32))
+
+
+def _spce_kind():
+    r, ang = 1.0, math.radians(109.47)
+    h = np.array([[0.0, 0.0, 0.0],
+                  [r * math.sin(ang / 2), r * math.cos(ang / 2), 0.0],
+                  [-r * math.sin(ang / 2), r * math.cos(ang / 2), 0.0]])
+    return MolKind("SPCE", ["O1", "H1", "H2"], ["OW", "HW", "HW"],
+                   [-0.8476, 0.4238, 0.4238], [15.9994, 1.008, 1.008],
+                   bonds=[(0, 1), (0, 2)], angles=[(1, 0, 2)], local_xyz=h)
+
+
+def make_argon(n_atoms=4000, density=0.0213, seed=123, r_cut=10.0, vdw_kind=VDW_STD,
+               r_switch=0.0):
+    """Config 1: LJ argon, sigma 3.4 A, eps/k 119.8 K, no electrostatics."""
+    L = round((n_atoms / density) ** (1.0 / 3.0), 3)
+    ff = ForceField(["AR"], np.array([119.8]), np.array([3.4]), np.array([12.0]),
+                    vdw_kind=vdw_kind, r_cut=r_cut, r_cut_coulomb=r_cut,
+                    r_switch=r_switch, ewald=False, electrostatic=False,
+                    lrc=(vdw_kind == VDW_STD))
+    mk = MolKind("AR", ["AR"], ["AR"], [0.0], [39.948])
+    return _assemble(f"argon{n_atoms}", ff, [mk], [n_atoms], L, seed)
+
+
+def make_spce(n_mols=10000, density=0.0334, seed=123, r_cut=10.0, r_cut_coulomb=None,
+              tolerance=1e-5, vdw_kind=VDW_STD, r_switch=0.0, ewald=True):
+    """Configs 2 and 4: rigid SPC/E water, Ewald on."""
+    rcc = r_cut if r_cut_coulomb is None else r_cut_coulomb
+    L = round((n_mols / density) ** (1.0 / 3.0), 3)
+    ff = ForceField(["OW", "HW"], np.array([78.2, 0.0]), np.array([3.166, 0.0]),
+                    np.array([12.0, 12.0]), vdw_kind=vdw_kind, r_cut=r_cut,
+                    r_cut_coulomb=rcc, tolerance=tolerance, r_switch=r_switch,
+                    ewald=ewald, electrostatic=True, lrc=(vdw_kind == VDW_STD),
+                    bond_params=[("OW", "HW", 1.0)],
+                    angle_params=[("HW", "OW", "HW", 109.47)])
+    return _assemble(f"spce{n_mols}", ff, [_spce_kind()], [n_mols], L, seed,
+                     jitter=0.15)
+
+
+def make_electrolyte(n_water=330000, n_pairs=5000, seed=123, r_cut=10.0,
+                     tolerance=1e-5):
+    """Config 5: SPC/E + Na+ + Cl- (1:1), 1 000 002 atoms at the default size."""
+    n_mols = n_water + 2 * n_pairs
+    L = round((n_mols / 0.0334) ** (1.0 / 3.0), 3)
+    ff = ForceField(["OW", "HW", "NA", "CL"], np.array([78.2, 0.0, 65.4, 50.3]),
+                    np.array([3.166, 0.0, 2.35, 4.40]), np.array([12.0] * 4),
+                    r_cut=r_cut, r_cut_coulomb=r_cut, tolerance=tolerance,
+                    bond_params=[("OW", "HW", 1.0)],
+                    angle_params=[("HW", "OW", "HW", 109.47)])
+    na = MolKind("NA", ["NA"], ["NA"], [1.0], [22.99])
+    cl = MolKind("CL", ["CL"], ["CL"], [-1.0], [35.45])
+    return _assemble(f"electrolyte{n_water}_{n_pairs}", ff, [_spce_kind(), na, cl],
+                     [n_water, n_pairs, n_pairs], L, seed, jitter=0.15)
+
+
+def make_mixture(n_a=150, n_b=100, seed=5, L=26.0, r_cut=8.0, vdw_kind=VDW_STD,
+                 r_switch=0.0, n_b_exp=14.0):
+    """Small two-kind Mie mixture with charged dimers: exercises the kind table
+    (non-integer n/2 via n=13 cross terms), charged + neutral atoms in one
+    molecule and multi-kind LRC."""
+    ff = ForceField(["CA", "CB", "DU"], np.array([98.0, 46.0, 0.0]),
+                    np.array([3.75, 3.0, 0.0]), np.array([12.0, n_b_exp, 12.0]),
+                    vdw_kind=vdw_kind, r_cut=r_cut, r_cut_coulomb=r_cut,
+                    r_switch=r_switch, tolerance=1e-5,
+                    lrc=(vdw_kind == VDW_STD),
+                    bond_params=[("CB", "CB", 1.5), ("CB", "DU", 0.8)],
+                    angle_params=[("CB", "CB", "DU", 120.0)])
+    a = MolKind("AAA", ["C1"], ["CA"], [0.0], [16.0])
+    tb = np.array([[0.0, 0.0, 0.0], [1.5, 0.0, 0.0], [1.9, 0.693, 0.0]])
+    b = MolKind("BBB", ["B1", "B2", "D1"], ["CB", "CB", "DU"], [0.35, -0.6, 0.25],
+                [14.0, 14.0, 1.0], bonds=[(0, 1), (1, 2)], angles=[(0, 1, 2)],
+                local_xyz=tb)
+    return _assemble(f"mixture{n_a}_{n_b}", ff, [a, b], [n_a, n_b], L, seed,
+                     jitter=0.2)
+
+
+# --------------------------------------------------------------------------
+# GOMC input writers (consumed by oracle/_ref/gomc_probe_*)
+
+def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
+                      cached_fourier=False, run_steps=0, pressure_calc=False):
+    os.makedirs(out_dir, exist_ok=True)
+    ff = sys.ff
+    # ---- parameter file (Mie / "EXOTIC" style, epsilon in K) --------------
+    with open(os.path.join(out_dir, "par.inp"), "w") as f:
+        f.write("* synthetic Mie parameter file written by gomc_b200.synth\n*\n\n")
+        f.write("BONDS\n")
+        for t1, t2, b0 in ff.bond_params:
+            f.write(f"{t1}\t{t2}\t999999999999\t{b0}\n")
+        f.write("\nANGLES\n")
+        for t1, t2, t3, th in ff.angle_params:
+            f.write(f"{t1}\t{t2}\t{t3}\t999999999999\t{th}\n")
+        f.write("\nDIHEDRALS\n\nNONBONDED_MIE\n")
+        for t, e, s, n in zip(ff.type_names, ff.epsilon, ff.sigma, ff.n):
+            f.write(f"{t}\t{float(e)!r}\t{float(s)!r}\t{float(n)!r}\n")
+        f.write("\nEND\n")
+    # ---- PDB + PSF -------------------------------------------------------
+    n = sys.n_atoms
+    with open(os.path.join(out_dir, "box0.pdb"), "w") as f:
+        f.write("CRYST1%9.3f%9.3f%9.3f  90.00  90.00  90.00 P 1           1\n"
+                % tuple(sys.axis))
+        for a in range(n):
+            m = int(sys.mol[a])
+            mk = sys.mol_kinds[int(sys.mol_kind[m])]
+            la = a - int(sys.mol_start[m])
+            f.write("ATOM  %5d %-4s %-4s%1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n" % (
+                (a + 1) % 100000, mk.atom_names[la], mk.name, "A",
+                (m + 1) % 10000, sys.x[a], sys.y[a], sys.z[a], 1.0, 0.0))
+        f.write("END\n")
+    bonds, angles = [], []
+    for m in range(sys.n_mols):
+        mk = sys.mol_kinds[int(sys.mol_kind[m])]
+        s = int(sys.mol_start[m]) + 1
+        bonds.extend((s + i, s + j) for i, j in mk.bonds)
+        angles.extend((s + i, s + j, s + k) for i, j, k in mk.angles)
+    with open(os.path.join(out_dir, "box0.psf"), "w") as f:
+        f.write("PSF\n\n       1 !NTITLE\n REMARKS synthetic system written by gomc_b200.synth\n\n")
+        f.write("%8d !NATOM\n" % n)
+        for a in range(n):
+            m = int(sys.mol[a])
+            mk = sys.mol_kinds[int(sys.mol_kind[m])]
+            la = a - int(sys.mol_start[m])
+            f.write("%8d %-4s %-4d %-4s %-4s %-4s %10.6f %13.4f %11d\n" % (
+                a + 1, "S", m + 1, mk.name, mk.atom_names[la], mk.atom_types[la],
+                mk.charges[la], mk.masses[la], 0))
+        f.write("\n%8d !NBOND: bonds\n" % len(bonds))
+        for i in range(0, len(bonds), 4):
+            f.write("".join("%8d%8d" % b for b in bonds[i:i + 4]) + "\n")
+        f.write("\n%8d !NTHETA: angles\n" % len(angles))
+        for i in range(0, len(angles), 3):
+            f.write("".join("%8d%8d%8d" % t for t in angles[i:i + 3]) + "\n")
+        f.write("\n%8d !NPHI: dihedrals\n\n\n%8d !NIMPHI: impropers\n\n\n" % (0, 0))
+        f.write("%8d !NDON: donors\n\n\n%8d !NACC: acceptors\n\n\n" % (0, 0))
+    # ---- in.conf ---------------------------------------------------------
+    L = sys.axis
+    conf = f"""ExpertMode True
+Restart false
+PRNG INTSEED
+Random_Seed 123
+ParaTypeMie on
+Parameters par.inp
+Coordinates 0 box0.pdb
+Structure 0 box0.psf
+Temperature 298.0
+Potential {_POT_NAME[ff.vdw_kind]}
+{('Rswitch ' + repr(float(ff.r_switch))) if ff.vdw_kind == VDW_SWITCH else ''}
+LRC {'true' if ff.lrc else 'false'}
+Rcut {float(ff.r_cut)!r}
+RcutLow {float(ff.r_cut_low)!r}
+Exclude 1-4
+Ewald {'true' if ff.ewald else 'false'}
+ElectroStatic {'true' if ff.electrostatic else 'false'}
+CachedFourier {'true' if cached_fourier else 'false'}
+Tolerance {ff.tolerance!r}
+1-4scaling false
+RcutCoulomb 0 {float(ff.r_cut_coulomb)!r}
+PressureCalc {'true 1000' if pressure_calc else 'false'}
+RunSteps {max(run_steps, 10)}
+EqSteps 5
+AdjSteps 5
+DisFreq {0.40 if multiparticle else 0.60}
+RotFreq {0.40 if multiparticle and any(len(k.atom_names) > 1 for k in sys.mol_kinds) else (0.40 if not multiparticle else 0.0)}
+{('MultiParticleFreq ' + ('0.20' if any(len(k.atom_names) > 1 for k in sys.mol_kinds) else '0.60')) if multiparticle else ''}
+CellBasisVector1 0 {float(L[0])!r} 0.0 0.0
+CellBasisVector2 0 0.0 {float(L[1])!r} 0.0
+CellBasisVector3 0 0.0 0.0 {float(L[2])!r}
+CBMC_First 10
+CBMC_Nth 8
+CBMC_Ang 50
+CBMC_Dih 50
+OutputName out
+RestartFreq false 1000
+CheckpointFreq false 1000
+CoordinatesFreq false 1000
+DCDFreq false 1000
+ConsoleFreq true 1000
+BlockAverageFreq false 1000
+OutEnergy true true
+OutPressure false false
+OutMolNum true true
+OutDensity false false
+OutSurfaceTension false false
+"""
+    with open(os.path.join(out_dir, "in.conf"), "w") as f:
+        f.write(conf)
+    return os.path.join(out_dir, "in.conf")

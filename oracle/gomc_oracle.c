@@ -1,0 +1,877 @@
+/*
+ * gomc_oracle.c -- TEST INFRASTRUCTURE ONLY (see gomc_oracle.h).
+ *
+ * CPU restatement, in plain C99, of the GOMC v2.80 energy/force hot path.
+ * Loop order follows the reference's CPU branch so that a single-thread run
+ * reproduces the reference's +p1 summation order.  Build:
+ *   gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC gomc_oracle.c -lm
+ * (-ffp-contract=off: the reference x86-64 build has no FMA contraction).
+ */
+#include "gomc_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+#ifndef M_2_SQRTPI
+#define M_2_SQRTPI 1.12837916709551257390
+#endif
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+/* ------------------------------------------------------------------------ */
+/* PBC: BoxDimensions::MinImageSigned, src/BoxDimensions.h:169-175           */
+static inline double min_image_signed(double raw, double ax, double halfAx) {
+  if (raw > halfAx)
+    raw -= ax;
+  else if (raw < -halfAx)
+    raw += ax;
+  return raw;
+}
+
+/* BoxDimensions::InRcut, src/BoxDimensions.h:231-237; rCutSq[b] is the square
+ * of max(rCut, rCutCoulomb[b]) (src/BoxDimensions.cpp:17-18). */
+static inline double box_rcut(const orc_params *p) {
+  return p->rCut > p->rCutCoulomb ? p->rCut : p->rCutCoulomb;
+}
+static inline int in_rcut(const orc_params *p, double boxRcutSq, double xi,
+                          double yi, double zi, double xj, double yj,
+                          double zj, double *distSq, double d[3]) {
+  d[0] = min_image_signed(xi - xj, p->axis[0], p->axis[0] * 0.5);
+  d[1] = min_image_signed(yi - yj, p->axis[1], p->axis[1] * 0.5);
+  d[2] = min_image_signed(zi - zj, p->axis[2], p->axis[2] * 0.5);
+  *distSq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  return boxRcutSq > *distSq;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Pair functors (lambda == 1 branch)                                        */
+
+/* FFParticle::CalcEn(distSq,index) src/FFParticle.cpp:317-325 */
+static inline double mie_en(const orc_params *p, double distSq, int idx) {
+  double rRat2 = p->sigmaSq[idx] / distSq;
+  double rRat4 = rRat2 * rRat2;
+  double attract = rRat4 * rRat2;
+  double repulse = pow(rRat2, p->n[idx] * 0.5);
+  return p->epsilon_cn[idx] * (repulse - attract);
+}
+/* FFParticle::CalcVir(distSq,index) src/FFParticle.cpp:350-359 */
+static inline double mie_vir(const orc_params *p, double distSq, int idx) {
+  double rNeg2 = 1.0 / distSq;
+  double rRat2 = rNeg2 * p->sigmaSq[idx];
+  double rRat4 = rRat2 * rRat2;
+  double attract = rRat4 * rRat2;
+  double repulse = pow(rRat2, p->n[idx] * 0.5);
+  double epsilon_cn_6 = p->epsilon_cn[idx] * 6; /* FFParticle.cpp:191 */
+  double nOver6 = p->n[idx] / 6;                /* FFParticle.cpp:193 */
+  return epsilon_cn_6 * (nOver6 * repulse - attract) * rNeg2;
+}
+/* FF_SHIFT::Init shiftConst, src/FFShift.h:100-116 */
+static inline double shift_const(const orc_params *p, int idx) {
+  double rCutSq = p->rCut * p->rCut;
+  double rRat2 = p->sigmaSq[idx] / rCutSq;
+  double rRat4 = rRat2 * rRat2;
+  double attract = rRat4 * rRat2;
+  double repulse = pow(sqrt(rRat2), p->n[idx]);
+  return p->epsilon_cn[idx] * (repulse - attract);
+}
+
+double orc_calc_en(const orc_params *p, double distSq, int kind1, int kind2) {
+  double rCutSq = p->rCut * p->rCut;
+  if (rCutSq < distSq) return 0.0; /* FFParticle.cpp:297 */
+  int idx = kind1 + kind2 * p->kindCount; /* FFParticle.h:111 */
+  switch (p->vdwKind) {
+  case ORC_VDW_SHIFT: { /* FFShift.h:167-175 */
+    double rRat2 = p->sigmaSq[idx] / distSq;
+    double rRat4 = rRat2 * rRat2;
+    double attract = rRat4 * rRat2;
+    double repulse = pow(rRat2, p->n[idx] * 0.5);
+    return p->epsilon_cn[idx] * (repulse - attract) - shift_const(p, idx);
+  }
+  case ORC_VDW_SWITCH: { /* FFSwitch.h:163-174, factors :101-105 */
+    double rOnSq = p->rOn * p->rOn;
+    double factor1 = rCutSq - 3 * rOnSq;
+    double factor2 =
+        1.0 / ((rCutSq - rOnSq) * (rCutSq - rOnSq) * (rCutSq - rOnSq));
+    double rCutSq_rijSq = rCutSq - distSq;
+    double rCutSq_rijSq_Sq = rCutSq_rijSq * rCutSq_rijSq;
+    double rRat2 = p->sigmaSq[idx] / distSq;
+    double attract = rRat2 * rRat2 * rRat2;
+    double repulse = pow(rRat2, p->n[idx] * 0.5);
+    double fE = rCutSq_rijSq_Sq * factor2 * (factor1 + 2.0 * distSq);
+    double factE = (distSq > rOnSq ? fE : 1.0);
+    return (p->epsilon_cn[idx] * (repulse - attract)) * factE;
+  }
+  default:
+    return mie_en(p, distSq, idx);
+  }
+}
+
+double orc_calc_vir(const orc_params *p, double distSq, int kind1, int kind2) {
+  double rCutSq = p->rCut * p->rCut;
+  if (rCutSq < distSq) return 0.0;
+  int idx = kind1 + kind2 * p->kindCount;
+  if (p->vdwKind == ORC_VDW_SWITCH) { /* FFSwitch.h:199-218 */
+    double rOnSq = p->rOn * p->rOn;
+    double factor1 = rCutSq - 3 * rOnSq;
+    double factor2 =
+        1.0 / ((rCutSq - rOnSq) * (rCutSq - rOnSq) * (rCutSq - rOnSq));
+    double rCutSq_rijSq = rCutSq - distSq;
+    double rCutSq_rijSq_Sq = rCutSq_rijSq * rCutSq_rijSq;
+    double rNeg2 = 1.0 / distSq;
+    double rRat2 = rNeg2 * p->sigmaSq[idx];
+    double attract = rRat2 * rRat2 * rRat2;
+    double repulse = pow(rRat2, p->n[idx] * 0.5);
+    double fE = rCutSq_rijSq_Sq * factor2 * (factor1 + 2.0 * distSq);
+    double fW = 12.0 * factor2 * rCutSq_rijSq * (rOnSq - distSq);
+    double factE = (distSq > rOnSq ? fE : 1.0);
+    double factW = (distSq > rOnSq ? fW : 0.0);
+    double Wij = (p->epsilon_cn[idx] * 6) *
+                 ((p->n[idx] / 6) * repulse - attract) * rNeg2;
+    double Eij = p->epsilon_cn[idx] * (repulse - attract);
+    return Wij * factE - Eij * factW;
+  }
+  /* STD and SHIFT share the virial (FFShift.h:200-210) */
+  return mie_vir(p, distSq, idx);
+}
+
+double orc_calc_coulomb(const orc_params *p, double distSq,
+                        double qi_qj_fact) {
+  double rcc2 = p->rCutCoulomb * p->rCutCoulomb;
+  if (rcc2 < distSq) return 0.0; /* FFParticle.cpp:364 */
+  double dist = sqrt(distSq);
+  if (p->ewald) { /* FFParticle.cpp:388-394, FFShift.h:239-244, FFSwitch.h:247-252 */
+    double val = p->alpha * dist;
+    return qi_qj_fact * erfc(val) / dist;
+  }
+  switch (p->vdwKind) {
+  case ORC_VDW_SHIFT: /* FFShift.h:245-249 */
+    return qi_qj_fact * (1.0 / dist - 1.0 / p->rCut);
+  case ORC_VDW_SWITCH: { /* FFSwitch.h:253-259 */
+    double switchVal = distSq / (p->rCut * p->rCut) - 1.0;
+    switchVal *= switchVal;
+    return qi_qj_fact * switchVal / dist;
+  }
+  default: /* FFParticle.cpp:395-398 */
+    return qi_qj_fact / dist;
+  }
+}
+
+double orc_calc_coulomb_vir(const orc_params *p, double distSq, double qi_qj) {
+  double rcc2 = p->rCutCoulomb * p->rCutCoulomb;
+  if (rcc2 < distSq) return 0.0;
+  double dist = sqrt(distSq);
+  if (p->ewald) {
+    double constValue = p->alpha * M_2_SQRTPI;
+    double expConstValue = exp(-1.0 * (p->alpha * p->alpha) * distSq);
+    double temp;
+    if (p->vdwKind == ORC_VDW_STD)
+      temp = 1.0 - erf(p->alpha * dist); /* FFParticle.cpp:439 */
+    else
+      temp = erfc(p->alpha * dist); /* FFShift.h:289, FFSwitch.h:299 */
+    return qi_qj * (temp / dist + constValue * expConstValue) / distSq;
+  }
+  if (p->vdwKind == ORC_VDW_SWITCH) { /* FFSwitch.h:302-307 */
+    double rCutSq = p->rCut * p->rCut;
+    double switchVal = distSq / rCutSq - 1.0;
+    switchVal *= switchVal;
+    double dSwitchVal = 2.0 * (distSq / rCutSq - 1.0) * 2.0 * dist / rCutSq;
+    return -qi_qj * (dSwitchVal / distSq - switchVal / (distSq * dist));
+  }
+  return qi_qj / (distSq * dist);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Cell list                                                                 */
+
+int orc_cell_edges(const orc_params *p, int edge[3]) {
+  double cutoff = box_rcut(p); /* CellList::SetCutoff, CellList.cpp:61-65 */
+  for (int d = 0; d < 3; ++d) { /* CellList::ResizeGrid, CellList.cpp:138-163 */
+    int e = (int)floor(p->axis[d] / cutoff);
+    edge[d] = e > 3 ? e : 3;
+  }
+  return edge[0] * edge[1] * edge[2];
+}
+
+/* CellList::PositionToCell, src/CellList.h:88-101 (orthogonal: unslant = id) */
+static inline int position_to_cell(const double cellSize[3], const int edge[3],
+                                   double px, double py, double pz) {
+  int cx = (int)(px / cellSize[0]);
+  int cy = (int)(py / cellSize[1]);
+  int cz = (int)(pz / cellSize[2]);
+  cx -= (cx == edge[0] ? 1 : 0);
+  cy -= (cy == edge[1] ? 1 : 0);
+  cz -= (cz == edge[2] ? 1 : 0);
+  return cx * edge[1] * edge[2] + cy * edge[2] + cz;
+}
+
+/* CellList::RebuildNeighbors, src/CellList.cpp:191-218 */
+static void build_neighbors(const int edge[3], int *neighborList) {
+  for (int cx = 0; cx < edge[0]; ++cx)
+    for (int cy = 0; cy < edge[1]; ++cy)
+      for (int cz = 0; cz < edge[2]; ++cz) {
+        int cell = cx * edge[2] * edge[1] + cy * edge[2] + cz;
+        int k = 0;
+        for (int dx = -1; dx <= 1; ++dx)
+          for (int dy = -1; dy <= 1; ++dy)
+            for (int dz = -1; dz <= 1; ++dz)
+              neighborList[cell * 27 + k++] =
+                  ((cx + dx + edge[0]) % edge[0]) * edge[2] * edge[1] +
+                  ((cy + dy + edge[1]) % edge[1]) * edge[2] +
+                  ((cz + dz + edge[2]) % edge[2]);
+      }
+}
+
+int orc_cell_list_build(const orc_params *p, int nAtomsTotal, const double *x,
+                        const double *y, const double *z, const int *boxAtoms,
+                        int nBox, int *cellVector, int *cellStart,
+                        int *mapParticleToCell, int *neighborList) {
+  int edge[3];
+  int nCells = orc_cell_edges(p, edge);
+  double cellSize[3] = {p->axis[0] / edge[0], p->axis[1] / edge[1],
+                        p->axis[2] / edge[2]};
+  /* counting sort by cell, scanning atoms in ascending index order: gives
+   * the ascending-within-cell order of GetCellListNeighbor's std::sort
+   * (CellList.cpp:258-285) whatever the linked-list insertion order was. */
+  int *sorted = (int *)malloc(sizeof(int) * (size_t)(nBox > 0 ? nBox : 1));
+  memcpy(sorted, boxAtoms, sizeof(int) * (size_t)nBox);
+  /* boxAtoms need not be sorted: sort ascending (insertion into CSR) */
+  for (int i = 1; i < nBox; ++i) { /* usually already sorted: O(n) */
+    int v = sorted[i], j = i - 1;
+    while (j >= 0 && sorted[j] > v) {
+      sorted[j + 1] = sorted[j];
+      --j;
+    }
+    sorted[j + 1] = v;
+  }
+  for (int i = 0; i < nAtomsTotal; ++i) mapParticleToCell[i] = -1;
+  for (int c = 0; c <= nCells; ++c) cellStart[c] = 0;
+  for (int i = 0; i < nBox; ++i) {
+    int a = sorted[i];
+    int c = position_to_cell(cellSize, edge, x[a], y[a], z[a]);
+    mapParticleToCell[a] = c;
+    cellStart[c + 1]++;
+  }
+  for (int c = 0; c < nCells; ++c) cellStart[c + 1] += cellStart[c];
+  int *fill = (int *)calloc((size_t)nCells, sizeof(int));
+  for (int i = 0; i < nBox; ++i) {
+    int a = sorted[i];
+    int c = mapParticleToCell[a];
+    cellVector[cellStart[c] + fill[c]++] = a;
+  }
+  free(fill);
+  free(sorted);
+  build_neighbors(edge, neighborList);
+  return nCells;
+}
+
+typedef struct {
+  int nCells;
+  int *cellVector, *cellStart, *map, *nbr;
+} cell_csr;
+
+static cell_csr csr_make(const orc_params *p, int nAtomsTotal, const double *x,
+                         const double *y, const double *z, const int *boxAtoms,
+                         int nBox) {
+  cell_csr c;
+  int edge[3];
+  int nCells = orc_cell_edges(p, edge);
+  c.cellVector = (int *)malloc(sizeof(int) * (size_t)(nBox + 1));
+  c.cellStart = (int *)malloc(sizeof(int) * (size_t)(nCells + 1));
+  c.map = (int *)malloc(sizeof(int) * (size_t)(nAtomsTotal + 1));
+  c.nbr = (int *)malloc(sizeof(int) * (size_t)nCells * 27);
+  c.nCells = orc_cell_list_build(p, nAtomsTotal, x, y, z, boxAtoms, nBox,
+                                 c.cellVector, c.cellStart, c.map, c.nbr);
+  return c;
+}
+static void csr_free(cell_csr *c) {
+  free(c->cellVector);
+  free(c->cellStart);
+  free(c->map);
+  free(c->nbr);
+}
+
+/* ------------------------------------------------------------------------ */
+/* BoxInter                                                                  */
+
+int orc_box_inter(const orc_params *p, int nAtomsTotal, const double *x,
+                  const double *y, const double *z, const int *kind,
+                  const int *mol, const double *charge, const int *boxAtoms,
+                  int nBox, double *ljEn, double *realEn) {
+  cell_csr c = csr_make(p, nAtomsTotal, x, y, z, boxAtoms, nBox);
+  double boxRcutSq = box_rcut(p) * box_rcut(p);
+  double tempREn = 0.0, tempLJEn = 0.0;
+  /* src/CalculateEnergy.cpp:199-250 */
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : tempREn, tempLJEn) schedule(static)
+#endif
+  for (int ci = 0; ci < nBox; ++ci) {
+    int cur = c.cellVector[ci];
+    int curCell = c.map[cur];
+    for (int nc = 0; nc < 27; ++nc) {
+      int nbrCell = c.nbr[curCell * 27 + nc];
+      int end = c.cellStart[nbrCell + 1];
+      for (int ni = c.cellStart[nbrCell]; ni < end; ++ni) {
+        int nb = c.cellVector[ni];
+        if (cur < nb && mol[cur] != mol[nb]) {
+          double distSq, d[3];
+          if (in_rcut(p, boxRcutSq, x[cur], y[cur], z[cur], x[nb], y[nb],
+                      z[nb], &distSq, d)) {
+            if (p->electrostatic) {
+              double qi_qj_fact = charge[cur] * charge[nb] * ORC_QQFACT;
+              if (qi_qj_fact != 0.0)
+                tempREn += orc_calc_coulomb(p, distSq, qi_qj_fact);
+            }
+            tempLJEn += orc_calc_en(p, distSq, kind[cur], kind[nb]);
+          }
+        }
+      }
+    }
+  }
+  *ljEn = tempLJEn;
+  *realEn = tempREn;
+  csr_free(&c);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* BoxForce                                                                  */
+
+int orc_box_force(const orc_params *p, int nAtomsTotal, int nMols,
+                  const double *x, const double *y, const double *z,
+                  const int *kind, const int *mol, const double *charge,
+                  const int *boxAtoms, int nBox, double *ljEn, double *realEn,
+                  double *aFx, double *aFy, double *aFz, double *mFx,
+                  double *mFy, double *mFz) {
+  (void)nMols;
+  cell_csr c = csr_make(p, nAtomsTotal, x, y, z, boxAtoms, nBox);
+  double boxRcutSq = box_rcut(p) * box_rcut(p);
+  double tempREn = 0.0, tempLJEn = 0.0;
+  /* ResetForce, src/CalculateEnergy.cpp:1408-1428 */
+  for (int i = 0; i < nBox; ++i) {
+    int a = boxAtoms[i];
+    aFx[a] = aFy[a] = aFz[a] = 0.0;
+    mFx[mol[a]] = mFy[mol[a]] = mFz[mol[a]] = 0.0;
+  }
+  /* src/CalculateEnergy.cpp:336-394; serial so that the force accumulation
+   * order is the reference's +p1 order. */
+  for (int ci = 0; ci < nBox; ++ci) {
+    int cur = c.cellVector[ci];
+    int curCell = c.map[cur];
+    for (int nc = 0; nc < 27; ++nc) {
+      int nbrCell = c.nbr[curCell * 27 + nc];
+      int end = c.cellStart[nbrCell + 1];
+      for (int ni = c.cellStart[nbrCell]; ni < end; ++ni) {
+        int nb = c.cellVector[ni];
+        if (cur < nb && mol[cur] != mol[nb]) {
+          double distSq, d[3];
+          if (in_rcut(p, boxRcutSq, x[cur], y[cur], z[cur], x[nb], y[nb],
+                      z[nb], &distSq, d)) {
+            double fR[3] = {0.0, 0.0, 0.0}, fL[3];
+            if (p->electrostatic) {
+              double qi_qj_fact = charge[cur] * charge[nb] * ORC_QQFACT;
+              if (qi_qj_fact != 0.0) {
+                tempREn += orc_calc_coulomb(p, distSq, qi_qj_fact);
+                double v = orc_calc_coulomb_vir(p, distSq, qi_qj_fact);
+                fR[0] = d[0] * v;
+                fR[1] = d[1] * v;
+                fR[2] = d[2] * v;
+              }
+            }
+            tempLJEn += orc_calc_en(p, distSq, kind[cur], kind[nb]);
+            double w = orc_calc_vir(p, distSq, kind[cur], kind[nb]);
+            fL[0] = d[0] * w;
+            fL[1] = d[1] * w;
+            fL[2] = d[2] * w;
+            aFx[cur] += fL[0] + fR[0];
+            aFy[cur] += fL[1] + fR[1];
+            aFz[cur] += fL[2] + fR[2];
+            aFx[nb] += -(fL[0] + fR[0]);
+            aFy[nb] += -(fL[1] + fR[1]);
+            aFz[nb] += -(fL[2] + fR[2]);
+            mFx[mol[cur]] += (fL[0] + fR[0]);
+            mFy[mol[cur]] += (fL[1] + fR[1]);
+            mFz[mol[cur]] += (fL[2] + fR[2]);
+            mFx[mol[nb]] += -(fL[0] + fR[0]);
+            mFy[mol[nb]] += -(fL[1] + fR[1]);
+            mFz[mol[nb]] += -(fL[2] + fR[2]);
+          }
+        }
+      }
+    }
+  }
+  *ljEn = tempLJEn;
+  *realEn = tempREn;
+  csr_free(&c);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* MoleculeInter / ParticleInter                                             */
+
+/* energy of one probe position against the 27 cells around it; sign = -1 for
+ * the "subtract old" sweep.  Mirrors one EnumerateLocal sweep of
+ * src/CalculateEnergy.cpp:593-678 (sum order: neighbour-cell order, ascending
+ * atom index inside a cell -- the reference walks its linked list instead,
+ * which is the same set in a history-dependent order). */
+static void probe_sweep(const orc_params *p, const cell_csr *c,
+                        const double cellSize[3], const int edge[3],
+                        const double *x, const double *y, const double *z,
+                        const int *kind, const double *charge, double px,
+                        double py, double pz, int kindI, double qI,
+                        double sign, int checkOverlap, double *lj,
+                        double *real, int *overlap) {
+  double boxRcutSq = box_rcut(p) * box_rcut(p);
+  double rCutLowSq = p->rCutLow * p->rCutLow;
+  int cell = position_to_cell(cellSize, edge, px, py, pz);
+  for (int nc = 0; nc < 27; ++nc) {
+    int nbrCell = c->nbr[cell * 27 + nc];
+    for (int ni = c->cellStart[nbrCell]; ni < c->cellStart[nbrCell + 1];
+         ++ni) {
+      int nb = c->cellVector[ni];
+      double distSq, d[3];
+      if (in_rcut(p, boxRcutSq, px, py, pz, x[nb], y[nb], z[nb], &distSq, d)) {
+        if (checkOverlap && distSq < rCutLowSq) *overlap |= 1;
+        if (p->electrostatic) {
+          double qi_qj_fact = qI * charge[nb] * ORC_QQFACT;
+          if (qi_qj_fact != 0.0)
+            *real += sign * orc_calc_coulomb(p, distSq, qi_qj_fact);
+        }
+        *lj += sign * orc_calc_en(p, distSq, kindI, kind[nb]);
+      }
+    }
+  }
+}
+
+int orc_molecule_inter(const orc_params *p, int nAtomsTotal, const double *x,
+                       const double *y, const double *z, const int *kind,
+                       const int *mol, const double *charge,
+                       const int *boxAtoms, int nBox, int molIndex,
+                       int molStart, int molLen, const double *newX,
+                       const double *newY, const double *newZ, double *dLJ,
+                       double *dReal) {
+  (void)mol;
+  (void)molIndex;
+  cell_csr c = csr_make(p, nAtomsTotal, x, y, z, boxAtoms, nBox);
+  int edge[3];
+  orc_cell_edges(p, edge);
+  double cellSize[3] = {p->axis[0] / edge[0], p->axis[1] / edge[1],
+                        p->axis[2] / edge[2]};
+  double lj = 0.0, real = 0.0;
+  int overlap = 0;
+  for (int a = 0; a < molLen; ++a) {
+    int atom = molStart + a;
+    /* subtract old energy, src/CalculateEnergy.cpp:593-634 */
+    probe_sweep(p, &c, cellSize, edge, x, y, z, kind, charge, x[atom], y[atom],
+                z[atom], kind[atom], charge[atom], -1.0, 0, &lj, &real,
+                &overlap);
+    /* add new energy, :637-678 */
+    probe_sweep(p, &c, cellSize, edge, x, y, z, kind, charge, newX[a], newY[a],
+                newZ[a], kind[atom], charge[atom], 1.0, 1, &lj, &real,
+                &overlap);
+  }
+  *dLJ = lj;
+  *dReal = real;
+  csr_free(&c);
+  return overlap;
+}
+
+int orc_particle_inter(const orc_params *p, int nAtomsTotal, const double *x,
+                       const double *y, const double *z, const int *kind,
+                       const int *mol, const double *charge,
+                       const int *boxAtoms, int nBox, int molIndex, int kindI,
+                       double qI, int trials, const double *tx,
+                       const double *ty, const double *tz, double *en,
+                       double *real, int *overlap) {
+  (void)mol;
+  (void)molIndex;
+  cell_csr c = csr_make(p, nAtomsTotal, x, y, z, boxAtoms, nBox);
+  int edge[3];
+  orc_cell_edges(p, edge);
+  double cellSize[3] = {p->axis[0] / edge[0], p->axis[1] / edge[1],
+                        p->axis[2] / edge[2]};
+  for (int t = 0; t < trials; ++t) { /* src/CalculateEnergy.cpp:741-782 */
+    double lj = 0.0, re = 0.0;
+    int ov = 0;
+    probe_sweep(p, &c, cellSize, edge, x, y, z, kind, charge, tx[t], ty[t],
+                tz[t], kindI, qI, 1.0, 1, &lj, &re, &ov);
+    en[t] += lj;
+    real[t] += re;
+    overlap[t] |= ov;
+  }
+  csr_free(&c);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Torque                                                                    */
+
+int orc_calculate_torque(const orc_params *p, int nBoxMols, const int *boxMols,
+                         const int *molStart, const double *x, const double *y,
+                         const double *z, const double *comX,
+                         const double *comY, const double *comZ,
+                         const double *aFx, const double *aFy,
+                         const double *aFz, const double *rFx,
+                         const double *rFy, const double *rFz, double *tx,
+                         double *ty, double *tz) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (int mi = 0; mi < nBoxMols; ++mi) { /* CalculateEnergy.cpp:1384-1403 */
+    int m = boxMols[mi];
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int a = molStart[m]; a < molStart[m + 1]; ++a) {
+      double dx = min_image_signed(x[a] - comX[m], p->axis[0], p->axis[0] * 0.5);
+      double dy = min_image_signed(y[a] - comY[m], p->axis[1], p->axis[1] * 0.5);
+      double dz = min_image_signed(z[a] - comZ[m], p->axis[2], p->axis[2] * 0.5);
+      double fx = aFx[a] + rFx[a], fy = aFy[a] + rFy[a], fz = aFz[a] + rFz[a];
+      /* geom::Cross, lib/GeomLib.h */
+      sx += dy * fz - dz * fy;
+      sy += dz * fx - dx * fz;
+      sz += dx * fy - dy * fx;
+    }
+    tx[m] = sx;
+    ty[m] = sy;
+    tz[m] = sz;
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* LRC                                                                       */
+
+static double energy_lrc_pair(const orc_params *p, int kind1, int kind2) {
+  /* FFParticle::EnergyLRC, src/FFParticle.cpp:96-116 */
+  int idx = kind1 + kind2 * p->kindCount;
+  double tc = 1.0;
+  double sigma = sqrt(p->sigmaSq[idx]);
+  double rRat = sigma / p->rCut;
+  double N = p->n[idx];
+  tc *= sigma * p->sigmaSq[idx];
+  tc *= 2.0 * M_PI * p->epsilon_cn[idx] / (N - 3.0);
+  tc *= (pow(rRat, p->n[idx] - 3.0) - ((N - 3.0) / 3.0) * rRat * rRat * rRat);
+  return tc;
+}
+
+double orc_energy_lrc(const orc_params *p, int nMolKinds,
+                      const int *molKindStart, const int *molKindAtomKinds,
+                      const int *numKindInBox) {
+  /* SHIFT/SWITCH have zero LRC (FFShift.h / FFSwitch.h EnergyLRC return 0) */
+  if (p->vdwKind != ORC_VDW_STD) return 0.0;
+  double volInv = 1.0 / (p->axis[0] * p->axis[1] * p->axis[2]);
+  double en = 0.0;
+  /* pairEnCorrections, src/Molecules.cpp (sum over atom pairs of the two
+   * molecule kinds), then CalculateEnergy::EnergyCorrection :1261-1269 */
+  for (int i = 0; i < nMolKinds; ++i)
+    for (int j = 0; j < nMolKinds; ++j) {
+      double pairCorr = 0.0;
+      for (int pI = molKindStart[i]; pI < molKindStart[i + 1]; ++pI)
+        for (int pJ = molKindStart[j]; pJ < molKindStart[j + 1]; ++pJ)
+          pairCorr +=
+              energy_lrc_pair(p, molKindAtomKinds[pI], molKindAtomKinds[pJ]);
+      en += pairCorr * numKindInBox[i] * numKindInBox[j] * volInv;
+    }
+  return en;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Reciprocal space                                                          */
+
+int orc_recip_init_orth(const orc_params *p, double *kx, double *ky,
+                        double *kz, double *hsqr, double *prefact,
+                        int *kmaxOut) {
+  /* src/Ewald.cpp:847-903 */
+  int counter = 0;
+  double alpsqr4 = 1.0 / (4.0 * (p->alpha * p->alpha));
+  double cv[3] = {2.0 * M_PI * (1.0 / p->axis[0]),
+                  2.0 * M_PI * (1.0 / p->axis[1]),
+                  2.0 * M_PI * (1.0 / p->axis[2])};
+  /* XYZ::Inverse then *= 2pi (lib/BasicTypes.h): x = 1.0/x; x *= 2pi */
+  cv[0] = (1.0 / p->axis[0]) * (2.0 * M_PI);
+  cv[1] = (1.0 / p->axis[1]) * (2.0 * M_PI);
+  cv[2] = (1.0 / p->axis[2]) * (2.0 * M_PI);
+  double volume = p->axis[0] * p->axis[1] * p->axis[2];
+  double vol = volume / (4.0 * M_PI);
+  double rr2 = p->recip_rcut * p->recip_rcut;
+  int nkx_max = (int)(p->recip_rcut * p->axis[0] / (2.0 * M_PI)) + 1;
+  int nky_max = (int)(p->recip_rcut * p->axis[1] / (2.0 * M_PI)) + 1;
+  int nkz_max = (int)(p->recip_rcut * p->axis[2] / (2.0 * M_PI)) + 1;
+  if (kmaxOut) {
+    int m = nkx_max > nky_max ? nkx_max : nky_max;
+    *kmaxOut = m > nkz_max ? m : nkz_max;
+  }
+  for (int ix = 0; ix <= nkx_max; ix++) {
+    int nky_min = (ix == 0) ? 0 : -nky_max;
+    for (int iy = nky_min; iy <= nky_max; iy++) {
+      int nkz_min = (ix == 0 && iy == 0) ? 1 : -nkz_max;
+      for (int iz = nkz_min; iz <= nkz_max; iz++) {
+        double kX = cv[0] * ix;
+        double kY = cv[1] * iy;
+        double kZ = cv[2] * iz;
+        double ksqr = kX * kX + kY * kY + kZ * kZ;
+        if (ksqr < rr2) {
+          if (kx) {
+            kx[counter] = kX;
+            ky[counter] = kY;
+            kz[counter] = kZ;
+            hsqr[counter] = ksqr;
+            prefact[counter] =
+                ORC_QQFACT * exp(-ksqr * alpsqr4) / (ksqr * vol);
+          }
+          counter++;
+        }
+      }
+    }
+  }
+  return counter;
+}
+
+int orc_box_recip_sums_slab(int nBoxMols, const int *boxMols,
+                            const int *molStart, const double *x,
+                            const double *y, const double *z,
+                            const double *charge, int k0, int k1,
+                            const double *kx, const double *ky,
+                            const double *kz, double *sumR, double *sumI) {
+  /* src/Ewald.cpp:222-269: memset, then molecule-outer / k-inner */
+  for (int i = k0; i < k1; ++i) sumR[i] = sumI[i] = 0.0;
+  /* k is the parallel axis in the reference too (omp for over i inside the
+   * molecule loop); hoisting the parallel region keeps each sumR[i]'s
+   * accumulation order (molecule order) unchanged. */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (int i = k0; i < k1; ++i) {
+    double accR = 0.0, accI = 0.0;
+    for (int mi = 0; mi < nBoxMols; ++mi) {
+      int m = boxMols[mi];
+      double sumReal = 0.0, sumImaginary = 0.0;
+      for (int a = molStart[m]; a < molStart[m + 1]; ++a) {
+        if (fabs(charge[a]) < 0.000000001) continue; /* Ewald.cpp:107-111 */
+        /* geom::Dot, lib/GeomLib.h:73-76 */
+        double dot = x[a] * kx[i] + y[a] * ky[i] + z[a] * kz[i];
+        sumReal += charge[a] * cos(dot);
+        sumImaginary += charge[a] * sin(dot);
+      }
+      accR += 1.0 * sumReal; /* lambdaCoef == 1 */
+      accI += 1.0 * sumImaginary;
+    }
+    sumR[i] = accR;
+    sumI[i] = accI;
+  }
+  return 0;
+}
+
+int orc_box_recip_sums(int nBoxMols, const int *boxMols, const int *molStart,
+                       const double *x, const double *y, const double *z,
+                       const double *charge, int nk, const double *kx,
+                       const double *ky, const double *kz, double *sumR,
+                       double *sumI) {
+  return orc_box_recip_sums_slab(nBoxMols, boxMols, molStart, x, y, z, charge,
+                                 0, nk, kx, ky, kz, sumR, sumI);
+}
+
+double orc_box_reciprocal(int nk, const double *sumR, const double *sumI,
+                          const double *prefact) {
+  double e = 0.0; /* src/Ewald.cpp:396-400 */
+  for (int i = 0; i < nk; ++i)
+    e += (sumR[i] * sumR[i] + sumI[i] * sumI[i]) * prefact[i];
+  return e;
+}
+
+double orc_mol_reciprocal(int molLen, const double *q, const double *oldX,
+                          const double *oldY, const double *oldZ,
+                          const double *newX, const double *newY,
+                          const double *newZ, int nk, const double *kx,
+                          const double *ky, const double *kz,
+                          const double *prefact, const double *sumRref,
+                          const double *sumIref, double *sumRnew,
+                          double *sumInew) {
+  double eNew = 0.0; /* src/Ewald.cpp:434-466 */
+  for (int i = 0; i < nk; ++i) {
+    double sRn = 0.0, sIn = 0.0, sRo = 0.0, sIo = 0.0;
+    for (int a = 0; a < molLen; ++a) {
+      if (fabs(q[a]) < 0.000000001) continue;
+      double dotNew = newX[a] * kx[i] + newY[a] * ky[i] + newZ[a] * kz[i];
+      double dotOld = oldX[a] * kx[i] + oldY[a] * ky[i] + oldZ[a] * kz[i];
+      sRn += q[a] * cos(dotNew);
+      sIn += q[a] * sin(dotNew);
+      sRo += q[a] * cos(dotOld);
+      sIo += q[a] * sin(dotOld);
+    }
+    sumRnew[i] = sumRref[i] + 1.0 * (sRn - sRo);
+    sumInew[i] = sumIref[i] + 1.0 * (sIn - sIo);
+    eNew += (sumRnew[i] * sumRnew[i] + sumInew[i] * sumInew[i]) * prefact[i];
+  }
+  return eNew;
+}
+
+double orc_swap_recip(int insert, int molLen, const double *q,
+                      const double *mx, const double *my, const double *mz,
+                      int nk, const double *kx, const double *ky,
+                      const double *kz, const double *prefact,
+                      const double *sumRref, const double *sumIref,
+                      double *sumRnew, double *sumInew) {
+  double eNew = 0.0; /* src/Ewald.cpp:501-524 / :681-703 */
+  for (int i = 0; i < nk; ++i) {
+    double sR = 0.0, sI = 0.0;
+    for (int a = 0; a < molLen; ++a) {
+      if (fabs(q[a]) < 0.000000001) continue;
+      double dot = mx[a] * kx[i] + my[a] * ky[i] + mz[a] * kz[i];
+      sR += q[a] * cos(dot);
+      sI += q[a] * sin(dot);
+    }
+    if (insert) {
+      sumRnew[i] = sumRref[i] + sR;
+      sumInew[i] = sumIref[i] + sI;
+    } else {
+      sumRnew[i] = sumRref[i] - sR;
+      sumInew[i] = sumIref[i] - sI;
+    }
+    eNew += (sumRnew[i] * sumRnew[i] + sumInew[i] * sumInew[i]) * prefact[i];
+  }
+  return eNew;
+}
+
+int orc_box_force_reciprocal(const orc_params *p, int nBoxMols,
+                             const int *boxMols, const int *molStart,
+                             const double *x, const double *y, const double *z,
+                             const double *charge, int nk, const double *kx,
+                             const double *ky, const double *kz,
+                             const double *prefact, const double *sumR,
+                             const double *sumI, double *rFx, double *rFy,
+                             double *rFz, double *mFx, double *mFy,
+                             double *mFz) {
+  double constValue = p->alpha * M_2_SQRTPI; /* src/Ewald.cpp:1502 */
+  double alphaSq = p->alpha * p->alpha;
+  double boxRcutSq = box_rcut(p) * box_rcut(p);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+  for (int mi = 0; mi < nBoxMols; ++mi) { /* :1541-1592 */
+    int m = boxMols[mi];
+    double msx = 0.0, msy = 0.0, msz = 0.0;
+    for (int a = molStart[m]; a < molStart[m + 1]; ++a) {
+      double X = 0.0, Y = 0.0, Z = 0.0;
+      if (!(fabs(charge[a]) < 0.000000001)) {
+        for (int j = molStart[m]; j < molStart[m + 1]; ++j) {
+          if (a != j) { /* intra (correction) force, :1556-1569 */
+            double distSq, d[3];
+            in_rcut(p, boxRcutSq, x[a], y[a], z[a], x[j], y[j], z[j], &distSq,
+                    d);
+            double dist = sqrt(distSq);
+            double expConstValue = exp(-1.0 * alphaSq * distSq);
+            double qiqj = charge[a] * charge[j] * ORC_QQFACT;
+            double intraForce = qiqj * 1.0 * 1.0 / distSq;
+            intraForce *=
+                ((erf(p->alpha * dist) / dist) - constValue * expConstValue);
+            X -= intraForce * d[0];
+            Y -= intraForce * d[1];
+            Z -= intraForce * d[2];
+          }
+        }
+        for (int i = 0; i < nk; ++i) { /* :1575-1586 */
+          double dot = x[a] * kx[i] + y[a] * ky[i] + z[a] * kz[i];
+          double factor = 2.0 * charge[a] * prefact[i] * 1.0 *
+                          (sin(dot) * sumR[i] - cos(dot) * sumI[i]);
+          X += factor * kx[i];
+          Y += factor * ky[i];
+          Z += factor * kz[i];
+        }
+      }
+      rFx[a] = X;
+      rFy[a] = Y;
+      rFz[a] = Z;
+      msx += X;
+      msy += Y;
+      msz += Z;
+    }
+    /* molForceRec.Set(0) then Add per atom (:1547, :1589) */
+    mFx[m] = msx;
+    mFy[m] = msy;
+    mFz[m] = msz;
+  }
+  return 0;
+}
+
+static double mol_correction(const orc_params *p, int len, const double *q,
+                             const double *mx, const double *my,
+                             const double *mz, int skipUncharged) {
+  double boxRcutSq = box_rcut(p) * box_rcut(p);
+  double correction = 0.0;
+  for (int i = 0; i < len; ++i) {
+    if (skipUncharged && fabs(q[i]) < 0.000000001) continue;
+    for (int j = i + 1; j < len; ++j) {
+      double distSq, d[3];
+      in_rcut(p, boxRcutSq, mx[i], my[i], mz[i], mx[j], my[j], mz[j], &distSq,
+              d);
+      double dist = sqrt(distSq);
+      correction += (q[i] * q[j] * erf(p->alpha * dist) / dist);
+    }
+  }
+  return correction;
+}
+
+double orc_box_correction(const orc_params *p, int nBoxMols,
+                          const int *boxMols, const int *molStart,
+                          const double *x, const double *y, const double *z,
+                          const double *charge) {
+  double total = 0.0; /* summed as src/CalculateEnergy.cpp:102-113 */
+  for (int mi = 0; mi < nBoxMols; ++mi) {
+    int m = boxMols[mi];
+    int s = molStart[m], len = molStart[m + 1] - s;
+    /* Ewald::MolCorrection, src/Ewald.cpp:1056-1085 */
+    double c = mol_correction(p, len, charge + s, x + s, y + s, z + s, 1);
+    total += -1.0 * ORC_QQFACT * c * 1.0 * 1.0;
+  }
+  return total;
+}
+
+double orc_box_self(const orc_params *p, int nBoxMols, const int *boxMols,
+                    const int *molStart, const double *charge) {
+  /* src/Ewald.cpp:1125-1163 groups by molecule kind (molSelfEnergy * molNum);
+   * here every molecule is summed individually, which is the same value up
+   * to rounding. */
+  double self = 0.0;
+  for (int mi = 0; mi < nBoxMols; ++mi) {
+    int m = boxMols[mi];
+    double molSelf = 0.0;
+    for (int a = molStart[m]; a < molStart[m + 1]; ++a)
+      molSelf += charge[a] * charge[a];
+    self += molSelf;
+  }
+  self *= -1.0 * p->alpha * ORC_QQFACT * M_2_SQRTPI * 0.5;
+  return self;
+}
+
+double orc_swap_correction(const orc_params *p, int molLen, const double *q,
+                           const double *mx, const double *my,
+                           const double *mz) {
+  /* src/Ewald.cpp:1311-1335: correction -= ...; return qqFact*correction */
+  double c = mol_correction(p, molLen, q, mx, my, mz, 0);
+  return ORC_QQFACT * (-c);
+}
+
+double orc_swap_self(const orc_params *p, int molLen, const double *q) {
+  double en_self = 0.0; /* src/Ewald.cpp:1375-1391 */
+  for (int i = 0; i < molLen; ++i) en_self -= q[i] * q[i];
+  return en_self * p->alpha * ORC_QQFACT * M_2_SQRTPI * 0.5;
+}

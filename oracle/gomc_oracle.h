@@ -1,0 +1,211 @@
+/*
+ * gomc_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C CPU restatement of the GOMC (v2.80) energy/force hot path.  It is
+ * the parity checker for the CUDA engine in gomc_b200/csrc and the "port"
+ * CPU baseline of bench.py.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it; the product
+ * path (libgomc_b200.so) never links or calls anything in oracle/.
+ *
+ * Pinning: the reference's own tests hold NO golden energies for this path
+ * (SURVEY.md section 8c).  The restatement is pinned instead against outputs
+ * of the reference itself, compiled unmodified from /root/reference by
+ * oracle/ref_build.mk and driven by oracle/ref_probe.cpp; the dumps are
+ * committed under tests/golden/ with the generating script
+ * (oracle/make_golden.py).
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * the GOMC tree).  lambda == 1 everywhere (no free-energy / NeMTMC fractional
+ * molecule), which is the case for all five BASELINE configs.
+ */
+#ifndef GOMC_ORACLE_H
+#define GOMC_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* lib/NumLib.h:22 */
+#define ORC_QQFACT 167103.208067979
+
+enum { ORC_VDW_STD = 0, ORC_VDW_SHIFT = 1, ORC_VDW_SWITCH = 2 };
+
+/* Force-field + per-box constants.  Mirrors what Forcefield::Init
+ * (src/Forcefield.cpp:29-84), FFParticle::Blend (src/FFParticle.cpp:155-199)
+ * and BoxDimensions::Init (src/BoxDimensions.cpp:17-18) derive. */
+typedef struct {
+  int vdwKind;       /* ORC_VDW_*                       (Forcefield.cpp:94-108) */
+  int ewald;         /* forcefield.ewald                                        */
+  int electrostatic; /* forcefield.electrostatic                                */
+  int kindCount;     /* FFParticle::count                                       */
+  double rCut;       /* forcefield.rCut (LJ cut-off)                            */
+  double rCutLow;    /* forcefield.rCutLow                                      */
+  double rOn;        /* forcefield.rswitch (SWITCH only)                        */
+  double rCutCoulomb; /* forcefield.rCutCoulomb[box]                            */
+  double alpha;       /* forcefield.alpha[box]      (Forcefield.cpp:80)         */
+  double recip_rcut;  /* forcefield.recip_rcut[box] (Forcefield.cpp:82)         */
+  double axis[3];     /* BoxDimensions::axis (orthogonal box)                   */
+  const double *sigmaSq;    /* [kindCount^2], index kind1 + kind2*count         */
+  const double *epsilon_cn; /* [kindCount^2]                                    */
+  const double *n;          /* [kindCount^2]                                    */
+} orc_params;
+
+/* ---- cell list (src/CellList.cpp:138-285, src/CellList.h:88-101) ---------- */
+/* edge[d] = max(floor(axis[d]/cutoff),3); returns number of cells. */
+int orc_cell_edges(const orc_params *p, int edge[3]);
+/* CSR of the atoms listed in boxAtoms[nBox] (sorted ascending inside each
+ * cell, as GetCellListNeighbor does).  cellVector[nBox], cellStart[nCells+1],
+ * mapParticleToCell[nAtomsTotal] (-1 for atoms not in the box),
+ * neighborList[nCells*27]. */
+int orc_cell_list_build(const orc_params *p, int nAtomsTotal, const double *x,
+                        const double *y, const double *z, const int *boxAtoms,
+                        int nBox, int *cellVector, int *cellStart,
+                        int *mapParticleToCell, int *neighborList);
+
+/* ---- pair path ---------------------------------------------------------- */
+/* CalculateEnergy::BoxInter, src/CalculateEnergy.cpp:157-266 (CPU branch). */
+int orc_box_inter(const orc_params *p, int nAtomsTotal, const double *x,
+                  const double *y, const double *z, const int *kind,
+                  const int *mol, const double *charge, const int *boxAtoms,
+                  int nBox, double *ljEn, double *realEn);
+
+/* CalculateEnergy::BoxForce, src/CalculateEnergy.cpp:268-406.  Force arrays
+ * are indexed by global atom / molecule index and are zeroed for the atoms
+ * and molecules of the box first (ResetForce, :1408-1428). */
+int orc_box_force(const orc_params *p, int nAtomsTotal, int nMols,
+                  const double *x, const double *y, const double *z,
+                  const int *kind, const int *mol, const double *charge,
+                  const int *boxAtoms, int nBox, double *ljEn, double *realEn,
+                  double *aFx, double *aFy, double *aFz, double *mFx,
+                  double *mFy, double *mFz);
+
+/* CalculateEnergy::MoleculeInter, src/CalculateEnergy.cpp:581-686.  The moved
+ * molecule (atoms molStart..molStart+len) must NOT be in boxAtoms (the caller
+ * does CellList::RemoveMol first, src/moves/Translate.h:84-89).  Returns the
+ * overlap flag. */
+int orc_molecule_inter(const orc_params *p, int nAtomsTotal, const double *x,
+                       const double *y, const double *z, const int *kind,
+                       const int *mol, const double *charge,
+                       const int *boxAtoms, int nBox, int molIndex,
+                       int molStart, int molLen, const double *newX,
+                       const double *newY, const double *newZ, double *dLJ,
+                       double *dReal);
+
+/* CalculateEnergy::ParticleInter, src/CalculateEnergy.cpp:727-785: energies of
+ * `trials` candidate positions of one atom of kind kindI / charge qI that
+ * belongs to molecule molIndex (which is not in boxAtoms).  en/real are
+ * incremented, overlap or-ed, as in the reference. */
+int orc_particle_inter(const orc_params *p, int nAtomsTotal, const double *x,
+                       const double *y, const double *z, const int *kind,
+                       const int *mol, const double *charge,
+                       const int *boxAtoms, int nBox, int molIndex, int kindI,
+                       double qI, int trials, const double *tx,
+                       const double *ty, const double *tz, double *en,
+                       double *real, int *overlap);
+
+/* CalculateEnergy::CalculateTorque, src/CalculateEnergy.cpp:1365-1406. */
+int orc_calculate_torque(const orc_params *p, int nBoxMols, const int *boxMols,
+                         const int *molStart, const double *x, const double *y,
+                         const double *z, const double *comX,
+                         const double *comY, const double *comZ,
+                         const double *aFx, const double *aFy,
+                         const double *aFz, const double *rFx,
+                         const double *rFy, const double *rFz, double *tx,
+                         double *ty, double *tz);
+
+/* FFParticle::EnergyLRC (src/FFParticle.cpp:96-116) summed as
+ * CalculateEnergy::EnergyCorrection (src/CalculateEnergy.cpp:1254-1270).
+ * molKindAtomKinds: CSR of atom kinds per molecule kind. */
+double orc_energy_lrc(const orc_params *p, int nMolKinds,
+                      const int *molKindStart, const int *molKindAtomKinds,
+                      const int *numKindInBox);
+
+/* pair functors exposed for unit tests (src/FFParticle.cpp:295-446,
+ * src/FFShift.h, src/FFSwitch.h) */
+double orc_calc_en(const orc_params *p, double distSq, int kind1, int kind2);
+double orc_calc_vir(const orc_params *p, double distSq, int kind1, int kind2);
+double orc_calc_coulomb(const orc_params *p, double distSq, double qi_qj_fact);
+double orc_calc_coulomb_vir(const orc_params *p, double distSq,
+                            double qi_qj_fact);
+
+/* ---- Ewald reciprocal path ---------------------------------------------- */
+/* Ewald::RecipInitOrth, src/Ewald.cpp:847-903.  Arrays sized >= the return
+ * value of a first call with kx == NULL (count only).  kmaxOut optional. */
+int orc_recip_init_orth(const orc_params *p, double *kx, double *ky,
+                        double *kz, double *hsqr, double *prefact,
+                        int *kmaxOut);
+
+/* Ewald::BoxReciprocalSetup / BoxReciprocalSums, src/Ewald.cpp:193-361:
+ * molecule-outer, k-inner, skipping |q|<1e-9 atoms (src/Ewald.cpp:107-111). */
+int orc_box_recip_sums(int nBoxMols, const int *boxMols, const int *molStart,
+                       const double *x, const double *y, const double *z,
+                       const double *charge, int nk, const double *kx,
+                       const double *ky, const double *kz, double *sumR,
+                       double *sumI);
+/* Same values for a k-slab [k0,k1) only (bounded CPU-baseline sample). */
+int orc_box_recip_sums_slab(int nBoxMols, const int *boxMols,
+                            const int *molStart, const double *x,
+                            const double *y, const double *z,
+                            const double *charge, int k0, int k1,
+                            const double *kx, const double *ky,
+                            const double *kz, double *sumR, double *sumI);
+
+/* Ewald::BoxReciprocal, src/Ewald.cpp:375-406. */
+double orc_box_reciprocal(int nk, const double *sumR, const double *sumI,
+                          const double *prefact);
+
+/* Ewald::MolReciprocal, src/Ewald.cpp:409-473 (non-cached; the cached variant
+ * src/EwaldCached.cpp:245-295 returns the same value up to rounding).  Writes
+ * sumRnew/sumInew, returns E_new (the caller subtracts sysPotRef recip). */
+double orc_mol_reciprocal(int molLen, const double *q, const double *oldX,
+                          const double *oldY, const double *oldZ,
+                          const double *newX, const double *newY,
+                          const double *newZ, int nk, const double *kx,
+                          const double *ky, const double *kz,
+                          const double *prefact, const double *sumRref,
+                          const double *sumIref, double *sumRnew,
+                          double *sumInew);
+
+/* Ewald::SwapDestRecip (insert=1, src/Ewald.cpp:478-531) and SwapSourceRecip
+ * (insert=0, :657-710).  Returns E_new. */
+double orc_swap_recip(int insert, int molLen, const double *q,
+                      const double *mx, const double *my, const double *mz,
+                      int nk, const double *kx, const double *ky,
+                      const double *kz, const double *prefact,
+                      const double *sumRref, const double *sumIref,
+                      double *sumRnew, double *sumInew);
+
+/* Ewald::BoxForceReciprocal, src/Ewald.cpp:1496-1596 (CPU branch), including
+ * the intramolecular erf-correction force (:1556-1569). */
+int orc_box_force_reciprocal(const orc_params *p, int nBoxMols,
+                             const int *boxMols, const int *molStart,
+                             const double *x, const double *y, const double *z,
+                             const double *charge, int nk, const double *kx,
+                             const double *ky, const double *kz,
+                             const double *prefact, const double *sumR,
+                             const double *sumI, double *rFx, double *rFy,
+                             double *rFz, double *mFx, double *mFy,
+                             double *mFz);
+
+/* Ewald::MolCorrection (src/Ewald.cpp:1056-1085), summed over boxMols. */
+double orc_box_correction(const orc_params *p, int nBoxMols,
+                          const int *boxMols, const int *molStart,
+                          const double *x, const double *y, const double *z,
+                          const double *charge);
+/* Ewald::BoxSelf, src/Ewald.cpp:1125-1163. */
+double orc_box_self(const orc_params *p, int nBoxMols, const int *boxMols,
+                    const int *molStart, const double *charge);
+/* Ewald::SwapCorrection(trialMol), src/Ewald.cpp:1311-1335. */
+double orc_swap_correction(const orc_params *p, int molLen, const double *q,
+                           const double *mx, const double *my,
+                           const double *mz);
+/* Ewald::SwapSelf, src/Ewald.cpp:1375-1391. */
+double orc_swap_self(const orc_params *p, int molLen, const double *q);
+
+int orc_max_threads(void);
+void orc_set_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

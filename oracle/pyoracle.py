@@ -1,0 +1,307 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes loader for oracle/libgomc_oracle.so (the
+plain-C CPU restatement of the reference hot path) and a reader for the dumps
+written by the reference probe (oracle/ref_probe.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module; nothing under gomc_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_LIB = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("vdwKind", C.c_int), ("ewald", C.c_int), ("electrostatic", C.c_int),
+                ("kindCount", C.c_int), ("rCut", C.c_double), ("rCutLow", C.c_double),
+                ("rOn", C.c_double), ("rCutCoulomb", C.c_double), ("alpha", C.c_double),
+                ("recip_rcut", C.c_double), ("axis", C.c_double * 3),
+                ("sigmaSq", _dp), ("epsilon_cn", _dp), ("n", _dp)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libgomc_oracle.so")
+    src = os.path.join(_HERE, "gomc_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-f", "oracle/Makefile"], cwd=_ROOT)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.orc_calc_en.restype = C.c_double
+        L.orc_calc_vir.restype = C.c_double
+        L.orc_calc_coulomb.restype = C.c_double
+        L.orc_calc_coulomb_vir.restype = C.c_double
+        L.orc_energy_lrc.restype = C.c_double
+        L.orc_box_reciprocal.restype = C.c_double
+        L.orc_mol_reciprocal.restype = C.c_double
+        L.orc_swap_recip.restype = C.c_double
+        L.orc_box_correction.restype = C.c_double
+        L.orc_box_self.restype = C.c_double
+        L.orc_swap_correction.restype = C.c_double
+        L.orc_swap_self.restype = C.c_double
+        L.orc_calc_en.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
+        L.orc_calc_vir.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
+        L.orc_calc_coulomb.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.orc_calc_coulomb_vir.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    return _LIB
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_ip)
+
+
+class Oracle:
+    """Stateless reference calculator bound to one (force field, box)."""
+
+    def __init__(self, *, vdw_kind, ewald, electrostatic, kind_count, r_cut, r_cut_low,
+                 r_switch, r_cut_coulomb, alpha, recip_rcut, axis, sigma_sq, epsilon_cn, n):
+        self.L = lib()
+        self._keep = [_d(sigma_sq), _d(epsilon_cn), _d(n)]
+        p = OrcParams()
+        p.vdwKind, p.ewald, p.electrostatic = int(vdw_kind), int(ewald), int(electrostatic)
+        p.kindCount = int(kind_count)
+        p.rCut, p.rCutLow, p.rOn = float(r_cut), float(r_cut_low), float(r_switch)
+        p.rCutCoulomb, p.alpha, p.recip_rcut = float(r_cut_coulomb), float(alpha), float(recip_rcut)
+        p.axis[0], p.axis[1], p.axis[2] = (float(v) for v in axis)
+        p.sigmaSq, p.epsilon_cn, p.n = (k[1] for k in self._keep)
+        self.p = p
+        self.pp = C.byref(p)
+
+    @classmethod
+    def from_system(cls, s):
+        sig, eps, nn = s.ff.tables()
+        ff = s.ff
+        return cls(vdw_kind=ff.vdw_kind, ewald=ff.ewald, electrostatic=ff.electrostatic,
+                   kind_count=len(ff.type_names), r_cut=ff.r_cut, r_cut_low=ff.r_cut_low,
+                   r_switch=ff.r_switch, r_cut_coulomb=ff.r_cut_coulomb, alpha=ff.alpha,
+                   recip_rcut=ff.recip_rcut, axis=s.axis, sigma_sq=sig, epsilon_cn=eps, n=nn)
+
+    @classmethod
+    def from_dump(cls, d, box=0):
+        return cls(vdw_kind=sc(d, "ff.vdwKind"), ewald=sc(d, "ff.ewald"),
+                   electrostatic=sc(d, "ff.electrostatic"), kind_count=sc(d, "ff.kindCount"),
+                   r_cut=sc(d, "ff.rCut"), r_cut_low=sc(d, "ff.rCutLow"),
+                   r_switch=sc(d, "ff.rswitch"),
+                   r_cut_coulomb=d["ff.rCutCoulomb"][box], alpha=d["ff.alpha"][box],
+                   recip_rcut=d["ff.recip_rcut"][box], axis=d[f"box{box}.axis"],
+                   sigma_sq=d["ff.sigmaSq"], epsilon_cn=d["ff.epsilon_cn"], n=d["ff.n"])
+
+    # ---- pair functors ---------------------------------------------------
+    def calc_en(self, r2, k1, k2):
+        return self.L.orc_calc_en(self.pp, r2, k1, k2)
+
+    def calc_vir(self, r2, k1, k2):
+        return self.L.orc_calc_vir(self.pp, r2, k1, k2)
+
+    def calc_coulomb(self, r2, qq):
+        return self.L.orc_calc_coulomb(self.pp, r2, qq)
+
+    def calc_coulomb_vir(self, r2, qq):
+        return self.L.orc_calc_coulomb_vir(self.pp, r2, qq)
+
+    # ---- cell list -------------------------------------------------------
+    def cell_list(self, x, y, z, box_atoms):
+        n = len(x)
+        edge = (C.c_int * 3)()
+        ncell = self.L.orc_cell_edges(self.pp, edge)
+        (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        ba, pba = _i(box_atoms)
+        cv = np.zeros(len(ba), np.int32)
+        cs = np.zeros(ncell + 1, np.int32)
+        mp = np.zeros(n, np.int32)
+        nb = np.zeros(ncell * 27, np.int32)
+        self.L.orc_cell_list_build(self.pp, n, px, py, pz, pba, len(ba),
+                                   cv.ctypes.data_as(_ip), cs.ctypes.data_as(_ip),
+                                   mp.ctypes.data_as(_ip), nb.ctypes.data_as(_ip))
+        return cv, cs, mp, nb.reshape(ncell, 27), tuple(edge)
+
+    # ---- pair path -------------------------------------------------------
+    def box_inter(self, x, y, z, kind, mol, charge, box_atoms):
+        (x, px), (y, py), (z, pz), (q, pq) = _d(x), _d(y), _d(z), _d(charge)
+        (k, pk), (m, pm), (ba, pba) = _i(kind), _i(mol), _i(box_atoms)
+        lj, re = C.c_double(), C.c_double()
+        self.L.orc_box_inter(self.pp, len(x), px, py, pz, pk, pm, pq, pba, len(ba),
+                             C.byref(lj), C.byref(re))
+        return lj.value, re.value
+
+    def box_force(self, x, y, z, kind, mol, charge, box_atoms, n_mols):
+        (x, px), (y, py), (z, pz), (q, pq) = _d(x), _d(y), _d(z), _d(charge)
+        (k, pk), (m, pm), (ba, pba) = _i(kind), _i(mol), _i(box_atoms)
+        lj, re = C.c_double(), C.c_double()
+        aF = [np.zeros(len(x)) for _ in range(3)]
+        mF = [np.zeros(n_mols) for _ in range(3)]
+        self.L.orc_box_force(self.pp, len(x), n_mols, px, py, pz, pk, pm, pq, pba, len(ba),
+                             C.byref(lj), C.byref(re),
+                             *[a.ctypes.data_as(_dp) for a in aF],
+                             *[a.ctypes.data_as(_dp) for a in mF])
+        return lj.value, re.value, aF, mF
+
+    def molecule_inter(self, x, y, z, kind, mol, charge, box_atoms, mol_index, mol_start,
+                       mol_len, nx, ny, nz):
+        (x, px), (y, py), (z, pz), (q, pq) = _d(x), _d(y), _d(z), _d(charge)
+        (k, pk), (m, pm), (ba, pba) = _i(kind), _i(mol), _i(box_atoms)
+        (nx, pnx), (ny, pny), (nz, pnz) = _d(nx), _d(ny), _d(nz)
+        lj, re = C.c_double(), C.c_double()
+        ov = self.L.orc_molecule_inter(self.pp, len(x), px, py, pz, pk, pm, pq, pba, len(ba),
+                                       int(mol_index), int(mol_start), int(mol_len),
+                                       pnx, pny, pnz, C.byref(lj), C.byref(re))
+        return lj.value, re.value, bool(ov)
+
+    def particle_inter(self, x, y, z, kind, mol, charge, box_atoms, mol_index, kind_i, q_i,
+                       tx, ty, tz):
+        (x, px), (y, py), (z, pz), (q, pq) = _d(x), _d(y), _d(z), _d(charge)
+        (k, pk), (m, pm), (ba, pba) = _i(kind), _i(mol), _i(box_atoms)
+        (tx, ptx), (ty, pty), (tz, ptz) = _d(tx), _d(ty), _d(tz)
+        t = len(tx)
+        en, re, ov = np.zeros(t), np.zeros(t), np.zeros(t, np.int32)
+        self.L.orc_particle_inter(self.pp, len(x), px, py, pz, pk, pm, pq, pba, len(ba),
+                                  int(mol_index), int(kind_i), C.c_double(q_i), t, ptx, pty,
+                                  ptz, en.ctypes.data_as(_dp), re.ctypes.data_as(_dp),
+                                  ov.ctypes.data_as(_ip))
+        return en, re, ov.astype(bool)
+
+    def calculate_torque(self, box_mols, mol_start, x, y, z, com, aF, rF, n_mols):
+        (bm, pbm), (ms, pms) = _i(box_mols), _i(mol_start)
+        arrs = [_d(a) for a in (x, y, z, *com, *aF, *rF)]
+        t = [np.zeros(n_mols) for _ in range(3)]
+        self.L.orc_calculate_torque(self.pp, len(bm), pbm, pms, *[a[1] for a in arrs],
+                                    *[a.ctypes.data_as(_dp) for a in t])
+        return t
+
+    def energy_lrc(self, mol_kind_start, mol_kind_atom_kinds, num_kind_in_box):
+        (a, pa), (b, pb), (c, pc) = _i(mol_kind_start), _i(mol_kind_atom_kinds), _i(num_kind_in_box)
+        return self.L.orc_energy_lrc(self.pp, len(a) - 1, pa, pb, pc)
+
+    # ---- reciprocal path -------------------------------------------------
+    def recip_init_orth(self):
+        kmax = C.c_int()
+        nk = self.L.orc_recip_init_orth(self.pp, None, None, None, None, None, C.byref(kmax))
+        arr = [np.zeros(nk) for _ in range(5)]
+        self.L.orc_recip_init_orth(self.pp, *[a.ctypes.data_as(_dp) for a in arr], C.byref(kmax))
+        return (*arr, kmax.value)   # kx, ky, kz, hsqr, prefact, kmax
+
+    def box_recip_sums(self, box_mols, mol_start, x, y, z, charge, kx, ky, kz, k0=0, k1=None):
+        (bm, pbm), (ms, pms) = _i(box_mols), _i(mol_start)
+        (x, px), (y, py), (z, pz), (q, pq) = _d(x), _d(y), _d(z), _d(charge)
+        (kx, pkx), (ky, pky), (kz, pkz) = _d(kx), _d(ky), _d(kz)
+        nk = len(kx)
+        k1 = nk if k1 is None else k1
+        sR, sI = np.zeros(nk), np.zeros(nk)
+        self.L.orc_box_recip_sums_slab(len(bm), pbm, pms, px, py, pz, pq, int(k0), int(k1),
+                                       pkx, pky, pkz, sR.ctypes.data_as(_dp),
+                                       sI.ctypes.data_as(_dp))
+        return sR, sI
+
+    def box_reciprocal(self, sR, sI, prefact):
+        (sR, a), (sI, b), (pf, c) = _d(sR), _d(sI), _d(prefact)
+        return self.L.orc_box_reciprocal(len(sR), a, b, c)
+
+    def mol_reciprocal(self, q, old, new, kx, ky, kz, prefact, sRref, sIref):
+        (q, pq) = _d(q)
+        o = [_d(a) for a in old]
+        nw = [_d(a) for a in new]
+        ks = [_d(a) for a in (kx, ky, kz, prefact, sRref, sIref)]
+        nk = len(ks[0][0])
+        sRn, sIn = np.zeros(nk), np.zeros(nk)
+        e = self.L.orc_mol_reciprocal(len(q), pq, *[a[1] for a in o], *[a[1] for a in nw], nk,
+                                      *[a[1] for a in ks], sRn.ctypes.data_as(_dp),
+                                      sIn.ctypes.data_as(_dp))
+        return e, sRn, sIn
+
+    def swap_recip(self, insert, q, mxyz, kx, ky, kz, prefact, sRref, sIref):
+        (q, pq) = _d(q)
+        m = [_d(a) for a in mxyz]
+        ks = [_d(a) for a in (kx, ky, kz, prefact, sRref, sIref)]
+        nk = len(ks[0][0])
+        sRn, sIn = np.zeros(nk), np.zeros(nk)
+        e = self.L.orc_swap_recip(int(insert), len(q), pq, *[a[1] for a in m], nk,
+                                  *[a[1] for a in ks], sRn.ctypes.data_as(_dp),
+                                  sIn.ctypes.data_as(_dp))
+        return e, sRn, sIn
+
+    def box_force_reciprocal(self, box_mols, mol_start, x, y, z, charge, kx, ky, kz, prefact,
+                             sR, sI, n_mols):
+        (bm, pbm), (ms, pms) = _i(box_mols), _i(mol_start)
+        arrs = [_d(a) for a in (x, y, z, charge)]
+        ks = [_d(a) for a in (kx, ky, kz, prefact, sR, sI)]
+        rF = [np.zeros(len(arrs[0][0])) for _ in range(3)]
+        mF = [np.zeros(n_mols) for _ in range(3)]
+        self.L.orc_box_force_reciprocal(self.pp, len(bm), pbm, pms, *[a[1] for a in arrs],
+                                        len(ks[0][0]), *[a[1] for a in ks],
+                                        *[a.ctypes.data_as(_dp) for a in rF],
+                                        *[a.ctypes.data_as(_dp) for a in mF])
+        return rF, mF
+
+    def box_correction(self, box_mols, mol_start, x, y, z, charge):
+        (bm, pbm), (ms, pms) = _i(box_mols), _i(mol_start)
+        arrs = [_d(a) for a in (x, y, z, charge)]
+        return self.L.orc_box_correction(self.pp, len(bm), pbm, pms, *[a[1] for a in arrs])
+
+    def box_self(self, box_mols, mol_start, charge):
+        (bm, pbm), (ms, pms), (q, pq) = _i(box_mols), _i(mol_start), _d(charge)
+        return self.L.orc_box_self(self.pp, len(bm), pbm, pms, pq)
+
+    def swap_correction(self, q, mxyz):
+        (q, pq) = _d(q)
+        m = [_d(a) for a in mxyz]
+        return self.L.orc_swap_correction(self.pp, len(q), pq, *[a[1] for a in m])
+
+    def swap_self(self, q):
+        (q, pq) = _d(q)
+        return self.L.orc_swap_self(self.pp, len(q), pq)
+
+
+def max_threads():
+    return lib().orc_max_threads()
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))
+
+
+# --------------------------------------------------------------------------
+def read_dump(path):
+    """Read a GOMCDUMP file written by oracle/ref_probe.cpp -> dict of arrays
+    (scalars are unwrapped to python numbers)."""
+    out = {}
+    with open(path, "rb") as f:
+        assert f.read(8) == b"GOMCDUMP", "bad magic"
+        while True:
+            h = f.read(4)
+            if not h:
+                break
+            (nl,) = struct.unpack("<I", h)
+            name = f.read(nl).decode()
+            (dt,) = struct.unpack("<B", f.read(1))
+            (cnt,) = struct.unpack("<Q", f.read(8))
+            dtype = np.float64 if dt == 0 else np.int32
+            a = np.frombuffer(f.read(cnt * np.dtype(dtype).itemsize), dtype=dtype).copy()
+            out[name] = a
+    return out
+
+
+def sc(d, key):
+    """Scalar entry of a dump."""
+    return d[key].reshape(-1)[0].item()

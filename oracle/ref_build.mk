@@ -1,0 +1,52 @@
+# Test infrastructure only (see oracle/README.md).
+# Compiles the UNMODIFIED reference CPU sources where they lie under $(REF)
+# (default /root/reference) with g++ directly -- the reference's own CMake
+# build is not run -- and links them with oracle/ref_probe.cpp into
+# oracle/_ref/gomc_probe_<ensemble>.  Flags follow the reference's GNU release
+# flags (-O3 -m64 -fopenmp, CMakeLists.txt:34) and per-ensemble -DENSEMBLE=n
+# (CMake/GOMCCPUSetup.cmake:4-17).  Nothing is copied out of $(REF); all
+# outputs land in oracle/_ref/ (git-ignored, travels to the GPU box).
+#
+#   make -f oracle/ref_build.mk -j8            # NVT + GEMC probes
+#   make -f oracle/ref_build.mk ENS=NVT -j8
+REF      ?= /root/reference
+OUT      ?= oracle/_ref
+CXX      := /usr/bin/g++
+CXXFLAGS := -O3 -m64 -fopenmp -std=c++17 -w
+ENS_LIST ?= NVT GEMC NPT
+ENSNUM_NVT  := 1
+ENSNUM_GEMC := 2
+ENSNUM_GCMC := 3
+ENSNUM_NPT  := 4
+
+INC := -I$(OUT)/include -I$(REF)/lib -I$(REF)/src -I$(REF)/src/cbmc -I$(REF)/src/moves \
+       -I$(REF)/src/GPU
+
+SRC := $(filter-out $(REF)/src/Main.cpp,$(wildcard $(REF)/src/*.cpp)) \
+       $(wildcard $(REF)/src/cbmc/*.cpp) $(wildcard $(REF)/lib/*.cpp)
+
+all: $(foreach e,$(ENS_LIST),$(OUT)/gomc_probe_$(e))
+
+$(OUT)/include/GOMC_Config.h:
+	@mkdir -p $(OUT)/include
+	@printf '%s\n' '#define GOMC_VERSION_MAJOR 2' '#define GOMC_VERSION_MINOR 80' \
+	  '#define GOMC_GTEST 0' '#define GOMC_GTEST_MPI 0' '#define GOMC_LIB_MPI 0' \
+	  '#define GOMC_THREAD_MPI 0' '#define GOMC_MPI (GOMC_LIB_MPI || GOMC_THREAD_MPI)' \
+	  '#define MPI_IN_PLACE_EXISTS 0' > $@
+
+define ENS_RULES
+OBJ_$(1) := $$(patsubst $(REF)/%.cpp,$(OUT)/obj_$(1)/%.o,$(SRC))
+$(OUT)/obj_$(1)/%.o: $(REF)/%.cpp $(OUT)/include/GOMC_Config.h
+	@mkdir -p $$(dir $$@)
+	$(CXX) $(CXXFLAGS) -DENSEMBLE=$(ENSNUM_$(1)) $(INC) -c $$< -o $$@
+$(OUT)/obj_$(1)/ref_probe.o: oracle/ref_probe.cpp $(OUT)/include/GOMC_Config.h
+	@mkdir -p $$(dir $$@)
+	$(CXX) $(CXXFLAGS) -DENSEMBLE=$(ENSNUM_$(1)) $(INC) -c $$< -o $$@
+$(OUT)/gomc_probe_$(1): $$(OBJ_$(1)) $(OUT)/obj_$(1)/ref_probe.o
+	$(CXX) $(CXXFLAGS) $$^ -o $$@
+endef
+$(foreach e,NVT GEMC GCMC NPT,$(eval $(call ENS_RULES,$(e))))
+
+clean:
+	rm -rf $(OUT)
+.PHONY: all clean

@@ -1,0 +1,548 @@
+/*
+ * ref_probe.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Harness that drives the UNMODIFIED GOMC reference (compiled from
+ * /root/reference by oracle/ref_build.mk) through its own L4 interfaces
+ * (CalculateEnergy / Ewald) and dumps inputs and outputs
+ * as named binary arrays.  The dumps pin oracle/gomc_oracle.c and become the
+ * golden vectors in tests/golden/ (see oracle/make_golden.py).
+ *
+ *   gomc_probe_<ENS> golden <in.conf> <out.bin> [nMoves] [seed]
+ *       full Simulation construction; every function of the hot path.
+ *   gomc_probe_<ENS> time <in.conf> <out.bin> <kFraction> <reps> [force]
+ *       light initialisation (no full structure-factor build, no virial) and
+ *       wall-clock timing of BoxInter + BoxReciprocalSums(k-slab) +
+ *       BoxReciprocal; with "force" also BoxForce + BoxForceReciprocal.
+ *
+ * Thread count comes from OMP_NUM_THREADS (the reference's "+pN").
+ * Private members are reached with the usual "#define private public" trick;
+ * no reference source is modified or copied.
+ */
+#include <algorithm>
+#include <array>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+#define private public
+#define protected public
+#include "Simulation.h"
+#include "Setup.h"
+#include "CalculateEnergy.h"
+#include "Ewald.h"
+#include "EwaldCached.h"
+#include "NoEwald.h"
+#include "FFParticle.h"
+#include "TrialMol.h"
+#undef private
+#undef protected
+
+namespace {
+
+struct Dump {
+  FILE *f;
+  explicit Dump(const char *path) {
+    f = fopen(path, "wb");
+    if (!f) {
+      perror(path);
+      exit(2);
+    }
+    fwrite("GOMCDUMP", 1, 8, f);
+  }
+  ~Dump() { fclose(f); }
+  void raw(const std::string &name, unsigned char dtype, uint64_t count,
+           const void *data, size_t elem) {
+    uint32_t nl = (uint32_t)name.size();
+    fwrite(&nl, 4, 1, f);
+    fwrite(name.data(), 1, nl, f);
+    fwrite(&dtype, 1, 1, f);
+    fwrite(&count, 8, 1, f);
+    fwrite(data, elem, count, f);
+  }
+  void f64(const std::string &n, const double *d, size_t c) {
+    raw(n, 0, c, d, 8);
+  }
+  void f64(const std::string &n, const std::vector<double> &v) {
+    raw(n, 0, v.size(), v.data(), 8);
+  }
+  void f64(const std::string &n, double v) { raw(n, 0, 1, &v, 8); }
+  void i32(const std::string &n, const std::vector<int> &v) {
+    raw(n, 1, v.size(), v.data(), 4);
+  }
+  void i32(const std::string &n, int v) { raw(n, 1, 1, &v, 4); }
+  void xyz(const std::string &n, const XYZArray &a) {
+    f64(n + ".x", a.x, a.Count());
+    f64(n + ".y", a.y, a.Count());
+    f64(n + ".z", a.z, a.Count());
+  }
+};
+
+double now() {
+  return std::chrono::duration<double>(
+             std::chrono::steady_clock::now().time_since_epoch())
+      .count();
+}
+
+std::string bname(const char *s, uint b) {
+  return std::string("box") + std::to_string(b) + "." + s;
+}
+
+void dump_static(Dump &out, StaticVals &sv, System &sys) {
+  Forcefield &ff = sv.forcefield;
+  FFParticle &fp = *ff.particles;
+  Molecules &mols = sv.mol;
+  uint nAtoms = sys.coordinates.Count();
+  out.i32("nAtoms", (int)nAtoms);
+  out.i32("nMols", (int)mols.count);
+  out.i32("boxTotal", (int)BOX_TOTAL);
+  out.i32("boxesWithU", (int)BOXES_WITH_U_NB);
+  out.i32("ff.vdwKind", (int)ff.vdwKind);
+  out.i32("ff.isMartini", (int)ff.isMartini);
+  out.i32("ff.exp6", (int)ff.exp6);
+  out.i32("ff.ewald", (int)ff.ewald);
+  out.i32("ff.electrostatic", (int)ff.electrostatic);
+  out.i32("ff.useLRC", (int)ff.useLRC);
+  out.i32("ff.kindCount", (int)fp.count);
+  out.f64("ff.rCut", ff.rCut);
+  out.f64("ff.rCutLow", ff.rCutLow);
+  out.f64("ff.rswitch", ff.rswitch);
+  out.f64("ff.tolerance", ff.tolerance);
+  out.f64("ff.rCutCoulomb", ff.rCutCoulomb, BOX_TOTAL);
+  out.f64("ff.alpha", ff.alpha, BOX_TOTAL);
+  out.f64("ff.recip_rcut", ff.recip_rcut, BOX_TOTAL);
+  out.f64("ff.sigmaSq", fp.sigmaSq, fp.count * fp.count);
+  out.f64("ff.epsilon_cn", fp.epsilon_cn, fp.count * fp.count);
+  out.f64("ff.n", fp.n, fp.count * fp.count);
+  out.xyz("coords", sys.coordinates);
+  out.xyz("com", sys.com);
+  out.i32("particleKind", sys.calcEnergy.particleKind);
+  out.i32("particleMol", sys.calcEnergy.particleMol);
+  out.f64("particleCharge", sys.calcEnergy.particleCharge);
+  std::vector<int> start(mols.count + 1), kidx(mols.count);
+  for (uint m = 0; m <= mols.count; ++m) start[m] = (int)mols.start[m];
+  for (uint m = 0; m < mols.count; ++m) kidx[m] = (int)mols.kIndex[m];
+  out.i32("molStart", start);
+  out.i32("molKindIndex", kidx);
+  out.i32("nMolKinds", (int)mols.kindsCount);
+  std::vector<int> mkStart(1, 0), mkAtomKinds;
+  for (uint k = 0; k < mols.kindsCount; ++k) {
+    for (uint a = 0; a < mols.kinds[k].NumAtoms(); ++a)
+      mkAtomKinds.push_back((int)mols.kinds[k].AtomKind(a));
+    mkStart.push_back((int)mkAtomKinds.size());
+  }
+  out.i32("molKindStart", mkStart);
+  out.i32("molKindAtomKinds", mkAtomKinds);
+  out.f64("pairEnCorrections", mols.pairEnCorrections,
+          mols.kindsCount * mols.kindsCount);
+  for (uint b = 0; b < BOX_TOTAL; ++b) {
+    XYZ ax = sys.boxDimRef.axis.Get(b);
+    double a3[3] = {ax.x, ax.y, ax.z};
+    out.f64(bname("axis", b), a3, 3);
+    out.i32(bname("orthogonal", b), (int)sys.boxDimRef.orthogonal[b]);
+    out.f64(bname("boxRcut", b), sys.boxDimRef.rCut[b]);
+    std::vector<int> molsInBox, numKind;
+    MoleculeLookup::box_iterator it = sys.molLookupRef.BoxBegin(b),
+                                 end = sys.molLookupRef.BoxEnd(b);
+    while (it != end) {
+      molsInBox.push_back((int)*it);
+      ++it;
+    }
+    for (uint k = 0; k < mols.kindsCount; ++k)
+      numKind.push_back((int)sys.molLookupRef.NumKindInBox(k, b));
+    out.i32(bname("mols", b), molsInBox);
+    out.i32(bname("numKindInBox", b), numKind);
+  }
+}
+
+void dump_kvectors(Dump &out, Ewald &ew, uint b, bool sums) {
+  uint nk = ew.imageSizeRef[b];
+  out.i32(bname("nk", b), (int)nk);
+  out.i32(bname("kmax", b), (int)ew.kmax[b]);
+  out.i32(bname("imageTotal", b), (int)ew.imageTotal);
+  out.f64(bname("kx", b), ew.kxRef[b], nk);
+  out.f64(bname("ky", b), ew.kyRef[b], nk);
+  out.f64(bname("kz", b), ew.kzRef[b], nk);
+  out.f64(bname("hsqr", b), ew.hsqrRef[b], nk);
+  out.f64(bname("prefact", b), ew.prefactRef[b], nk);
+  if (sums) {
+    out.f64(bname("sumRref", b), ew.sumRref[b], nk);
+    out.f64(bname("sumIref", b), ew.sumIref[b], nk);
+  }
+}
+
+int run_golden(int argc, char **argv) {
+  const char *conf = argv[2];
+  const char *outPath = argv[3];
+  int nMoves = argc > 4 ? atoi(argv[4]) : 4;
+  unsigned seed = argc > 5 ? (unsigned)atoi(argv[5]) : 7u;
+  Simulation sim(conf);
+  System &sys = *sim.system;
+  StaticVals &sv = *sim.staticValues;
+  Forcefield &ff = sv.forcefield;
+  Molecules &mols = sv.mol;
+  Ewald &ew = *sys.calcEwald;
+  CalculateEnergy &ce = sys.calcEnergy;
+  Dump out(outPath);
+  out.i32("threads", omp_get_max_threads());
+  dump_static(out, sv, sys);
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+
+  for (uint b = 0; b < BOXES_WITH_U_NB; ++b) {
+    MoleculeLookup::box_iterator it = sys.molLookupRef.BoxBegin(b),
+                                 end = sys.molLookupRef.BoxEnd(b);
+    std::vector<uint> molsInBox;
+    while (it != end) {
+      molsInBox.push_back(*it);
+      ++it;
+    }
+    if (molsInBox.empty()) continue;
+    // ---- SystemTotal pieces as computed by System::Init ------------------
+    const Energy &e0 = sys.potential.boxEnergy[b];
+    double sysEn[8] = {e0.inter, e0.real,       e0.recip,      e0.self,
+                       e0.correction, e0.tailCorrection, e0.intraBond,
+                       e0.intraNonbond};
+    out.f64(bname("systemTotal", b), sysEn, 8);
+    // ---- BoxInter --------------------------------------------------------
+    SystemPotential pot =
+        ce.BoxInter(SystemPotential(), sys.coordinates, sys.boxDimRef, b);
+    out.f64(bname("BoxInter.inter", b), pot.boxEnergy[b].inter);
+    out.f64(bname("BoxInter.real", b), pot.boxEnergy[b].real);
+    out.f64(bname("BoxInter.tailCorrection", b),
+            pot.boxEnergy[b].tailCorrection);
+    // ---- BoxForce (needs multiParticleEnabled for ResetForce) -------------
+    {
+      XYZArray aF(sys.coordinates.Count()), mF(mols.count);
+      aF.Reset();
+      mF.Reset();
+      SystemPotential pf = ce.BoxForce(SystemPotential(), sys.coordinates, aF,
+                                       mF, sys.boxDimRef, b);
+      out.f64(bname("BoxForce.inter", b), pf.boxEnergy[b].inter);
+      out.f64(bname("BoxForce.real", b), pf.boxEnergy[b].real);
+      out.xyz(bname("BoxForce.atomForce", b), aF);
+      out.xyz(bname("BoxForce.molForce", b), mF);
+      if (ff.ewald) {
+        // ---- reciprocal force + torque -------------------------------------
+        XYZArray aR(sys.coordinates.Count()), mR(mols.count), tq(mols.count);
+        aR.Reset();
+        mR.Reset();
+        tq.Reset();
+        ew.CopyRecip(b);
+        ew.BoxForceReciprocal(sys.coordinates, aR, mR, b);
+        out.xyz(bname("BoxForceReciprocal.atomForceRec", b), aR);
+        out.xyz(bname("BoxForceReciprocal.molForceRec", b), mR);
+        ce.CalculateTorque(molsInBox, sys.coordinates, sys.com, aF, aR, tq, b);
+        out.xyz(bname("CalculateTorque.molTorque", b), tq);
+      }
+    }
+    // ---- Ewald terms -------------------------------------------------------
+    if (ff.ewald) {
+      dump_kvectors(out, ew, b, true);
+      ew.CopyRecip(b);
+      out.f64(bname("BoxReciprocal", b), ew.BoxReciprocal(b, false));
+      double corr = 0.0;
+      for (uint m : molsInBox) corr += ew.MolCorrection(m, b);
+      out.f64(bname("MolCorrection.sum", b), corr);
+      out.f64(bname("BoxSelf", b), ew.BoxSelf(b));
+      // BoxReciprocalSums on the current coordinates must reproduce sumRref
+      ew.BoxReciprocalSums(b, sys.coordinates);
+      out.f64(bname("BoxReciprocalSums.sumRnew", b), ew.sumRnew[b],
+              ew.imageSizeRef[b]);
+      out.f64(bname("BoxReciprocalSums.sumInew", b), ew.sumInew[b],
+              ew.imageSizeRef[b]);
+    }
+    // ---- single-molecule moves: MoleculeInter + MolReciprocal -------------
+    XYZ ax = sys.boxDimRef.axis.Get(b);
+    std::vector<int> mvMol;
+    std::vector<double> mvX, mvY, mvZ, mvLJ, mvReal, mvRecip;
+    std::vector<int> mvOverlap, mvStart;
+    for (int t = 0; t < nMoves; ++t) {
+      uint m = molsInBox[(size_t)(rng() % molsInBox.size())];
+      uint start = mols.MolStart(m), len = mols.GetKind(m).NumAtoms();
+      XYZArray nc(len);
+      // rigid displacement, large for odd t (tests PBC wrap), small otherwise;
+      // every 4th move also puts the molecule on top of a neighbour to
+      // exercise the overlap flag.
+      double amp = (t % 2) ? 0.45 * std::min(ax.x, std::min(ax.y, ax.z)) : 0.4;
+      XYZ shift(U(rng) * amp, U(rng) * amp, U(rng) * amp);
+      if (t % 4 == 3 && molsInBox.size() > 1) {
+        uint other = molsInBox[(size_t)(rng() % molsInBox.size())];
+        if (other != m) {
+          XYZ d = sys.coordinates.Get(mols.MolStart(other)) -
+                  sys.coordinates.Get(start);
+          shift = d + XYZ(0.3, 0.2, 0.1);
+        }
+      }
+      for (uint a = 0; a < len; ++a) {
+        XYZ p = sys.coordinates.Get(start + a) + shift;
+        p = sys.boxDimRef.WrapPBC(p, b);
+        nc.Set(a, p);
+      }
+      Intermolecular iLJ, iReal;
+      sys.cellList.RemoveMol(m, b, sys.coordinates);
+      bool overlap = ce.MoleculeInter(iLJ, iReal, nc, m, b);
+      double dRecip = 0.0;
+      if (ff.ewald) dRecip = ew.MolReciprocal(nc, m, b);
+      if (ff.ewald && t == 0) {
+        out.f64(bname("MolReciprocal0.sumRnew", b), ew.sumRnew[b],
+                ew.imageSizeRef[b]);
+        out.f64(bname("MolReciprocal0.sumInew", b), ew.sumInew[b],
+                ew.imageSizeRef[b]);
+      }
+      // reject: state stays as it was (non-cached: nothing; cached: RestoreMol)
+      ew.RestoreMol(m);
+      sys.cellList.AddMol(m, b, sys.coordinates);
+      mvMol.push_back((int)m);
+      mvStart.push_back((int)mvX.size());
+      for (uint a = 0; a < len; ++a) {
+        mvX.push_back(nc.x[a]);
+        mvY.push_back(nc.y[a]);
+        mvZ.push_back(nc.z[a]);
+      }
+      mvLJ.push_back(iLJ.energy);
+      mvReal.push_back(iReal.energy);
+      mvRecip.push_back(dRecip);
+      mvOverlap.push_back((int)overlap);
+    }
+    mvStart.push_back((int)mvX.size());
+    out.i32(bname("move.mol", b), mvMol);
+    out.i32(bname("move.start", b), mvStart);
+    out.f64(bname("move.x", b), mvX);
+    out.f64(bname("move.y", b), mvY);
+    out.f64(bname("move.z", b), mvZ);
+    out.f64(bname("move.dLJ", b), mvLJ);
+    out.f64(bname("move.dReal", b), mvReal);
+    out.f64(bname("move.dRecip", b), mvRecip);
+    out.i32(bname("move.overlap", b), mvOverlap);
+    out.f64(bname("sysPotRef.recip", b), sys.potential.boxEnergy[b].recip);
+
+    // ---- swap-type deltas: SwapDestRecip / SwapSourceRecip / corrections ---
+    {
+      uint m = molsInBox[(size_t)(rng() % molsInBox.size())];
+      uint start = mols.MolStart(m), len = mols.GetKind(m).NumAtoms();
+      cbmc::TrialMol newMol(mols.GetKind(m), sys.boxDimRef, b);
+      cbmc::TrialMol oldMol(mols.GetKind(m), sys.boxDimRef, b);
+      XYZArray nc(len);
+      XYZ shift(U(rng) * 3.0, U(rng) * 3.0, U(rng) * 3.0);
+      for (uint a = 0; a < len; ++a) {
+        XYZ p = sys.coordinates.Get(start + a) + shift;
+        nc.Set(a, sys.boxDimRef.WrapPBC(p, b));
+      }
+      newMol.SetCoords(nc, 0);
+      oldMol.SetCoords(sys.coordinates, start);
+      out.i32(bname("swap.mol", b), (int)m);
+      out.xyz(bname("swap.newCoords", b), nc);
+      if (ff.ewald) {
+        double dDest = ew.SwapDestRecip(newMol, b, m);
+        out.f64(bname("SwapDestRecip", b), dDest);
+        out.f64(bname("SwapDestRecip.sumRnew", b), ew.sumRnew[b],
+                ew.imageSizeRef[b]);
+        ew.RestoreMol(m);
+        double dSrc = ew.SwapSourceRecip(oldMol, b, m);
+        out.f64(bname("SwapSourceRecip", b), dSrc);
+        out.f64(bname("SwapSourceRecip.sumInew", b), ew.sumInew[b],
+                ew.imageSizeRef[b]);
+        out.f64(bname("SwapCorrection.new", b), ew.SwapCorrection(newMol));
+        out.f64(bname("SwapCorrection.old", b), ew.SwapCorrection(oldMol));
+        out.f64(bname("SwapSelf", b), ew.SwapSelf(newMol));
+      }
+      // ---- ParticleInter: trial positions of the first atom of molecule m --
+      const uint trials = 6;
+      XYZArray tp(trials);
+      std::vector<double> en(trials, 0.0), re(trials, 0.0);
+      bool *ov = new bool[trials];
+      for (uint t = 0; t < trials; ++t) {
+        ov[t] = false;
+        XYZ p(0.5 * (U(rng) + 1.0) * ax.x, 0.5 * (U(rng) + 1.0) * ax.y,
+              0.5 * (U(rng) + 1.0) * ax.z);
+        if (t == trials - 1) // on top of another atom: overlap
+          p = sys.boxDimRef.WrapPBC(
+              sys.coordinates.Get(
+                  mols.MolStart(molsInBox[(m == molsInBox[0]) ? 1 : 0])) +
+                  XYZ(0.2, 0.1, 0.05),
+              b);
+        tp.Set(t, p);
+      }
+      sys.cellList.RemoveMol(m, b, sys.coordinates);
+      ce.ParticleInter(en.data(), re.data(), tp, ov, 0, m, b, trials);
+      sys.cellList.AddMol(m, b, sys.coordinates);
+      std::vector<int> ovi(trials);
+      for (uint t = 0; t < trials; ++t) ovi[t] = ov[t];
+      delete[] ov;
+      out.xyz(bname("ParticleInter.trialPos", b), tp);
+      out.f64(bname("ParticleInter.en", b), en);
+      out.f64(bname("ParticleInter.real", b), re);
+      out.i32(bname("ParticleInter.overlap", b), ovi);
+    }
+  }
+  return 0;
+}
+
+// Light initialisation: the statements of Simulation::Simulation
+// (src/Simulation.cpp:19-40) and System::Init (src/System.cpp:106-160) except
+// the two O(N*nk) start-up sweeps (BoxReciprocalSetup inside Ewald::Init and
+// SystemTotal's virial), which a bounded timing run cannot afford.
+int run_time(int argc, char **argv) {
+  const char *conf = argv[2];
+  const char *outPath = argv[3];
+  int kFrac = argc > 4 ? atoi(argv[4]) : 1;
+  int reps = argc > 5 ? atoi(argv[5]) : 3;
+  bool doForce = argc > 6 && std::string(argv[6]) == "force";
+  static Setup set;
+  set.Init(conf, NULL);
+  ulong startStep = 0;
+  StaticVals *sv = new StaticVals(set);
+  static MultiSim const *msNull = NULL;
+  System *sysp = new System(*sv, set, startStep, msNull);
+  System &sys = *sysp;
+  sv->Init(set, sys);
+  // ---- System::Init, minus SystemTotal and the k-space start-up sweep ----
+#ifdef VARIABLE_PARTICLE_NUMBER
+  sys.molLookup.Init(sv->mol, set.pdb.atoms, sv->forcefield,
+                     set.config.in.restart.restartFromCheckpoint);
+#endif
+  sys.moveSettings.Init(*sv, set.pdb.remarks, sys.molLookupRef.GetNumKind(),
+                        set.config.in.restart.restartFromCheckpoint);
+  sys.vel.Init(set.pdb.atoms, set.config.in);
+  sys.xsc.Init(set.pdb, sys.vel, set.config.in, sys.molLookupRef, sv->mol);
+  sys.boxDimensions->Init(set.config.in.restart, set.config.sys.volume,
+                          set.pdb.cryst, sv->forcefield);
+  sys.coordinates.InitFromPDB(set.pdb.atoms);
+  sys.com.CalcCOM();
+  sys.atomForceRef.Init(set.pdb.atoms.beta.size());
+  sys.molForceRef.Init(sys.com.Count());
+  sys.atomForceRecRef.Init(set.pdb.atoms.beta.size());
+  sys.molForceRecRef.Init(sys.com.Count());
+  sys.cellList.SetCutoff();
+  sys.cellList.GridAll(sys.boxDimRef, sys.coordinates, sys.molLookupRef);
+  bool ewaldOn = set.config.sys.elect.ewald;
+  if (ewaldOn)
+    sys.calcEwald = new Ewald(*sv, sys);
+  else
+    sys.calcEwald = new NoEwald(*sv, sys);
+  sys.InitLambda();
+  sys.calcEnergy.Init(sys);
+  Ewald &ew = *sys.calcEwald;
+  Molecules &mols = sv->mol;
+  if (ewaldOn) {
+    // Ewald::Init (src/Ewald.cpp:100-127) without BoxReciprocalSetup
+    for (uint m = 0; m < mols.count; ++m) {
+      const MoleculeKind &molKind = mols.GetKind(m);
+      for (uint a = 0; a < molKind.NumAtoms(); ++a) {
+        ew.particleKind.push_back(molKind.AtomKind(a));
+        ew.particleMol.push_back(m);
+        ew.particleCharge.push_back(molKind.AtomCharge(a));
+        ew.particleHasNoCharge.push_back(std::abs(molKind.AtomCharge(a)) <
+                                         0.000000001);
+      }
+    }
+    ew.startMol.resize(sys.coordinates.Count());
+    ew.lengthMol.resize(sys.coordinates.Count());
+    for (int atom = 0; atom < (int)sys.coordinates.Count(); atom++) {
+      ew.startMol[atom] = mols.MolStart(ew.particleMol[atom]);
+      ew.lengthMol[atom] = mols.MolLength(ew.particleMol[atom]);
+    }
+    ew.AllocMem();
+    for (uint b = 0; b < BOXES_WITH_U_NB; ++b) {
+      ew.RecipInit(b, sys.boxDimRef);
+      std::memset(ew.sumRnew[b], 0, sizeof(double) * ew.imageSize[b]);
+      std::memset(ew.sumInew[b], 0, sizeof(double) * ew.imageSize[b]);
+      ew.SetRecipRef(b);
+    }
+  }
+  Dump out(outPath);
+  out.i32("threads", omp_get_max_threads());
+  dump_static(out, *sv, sys);
+  const uint b = 0;
+  uint nkFull = ewaldOn ? ew.imageSizeRef[b] : 0;
+  uint nkSlab = ewaldOn ? std::max(1u, nkFull / (uint)std::max(1, kFrac)) : 0;
+  if (ewaldOn) dump_kvectors(out, ew, b, false);
+  out.i32("time.nkFull", (int)nkFull);
+  out.i32("time.nkSlab", (int)nkSlab);
+  std::vector<double> tInter, tSums, tRecip, tForce, tForceRec;
+  double lj = 0, real = 0, recip = 0;
+  for (int r = 0; r < reps + 1; ++r) { // first repetition is the warm-up
+    double t0 = now();
+    SystemPotential pot = sys.calcEnergy.BoxInter(
+        SystemPotential(), sys.coordinates, sys.boxDimRef, b);
+    double t1 = now();
+    if (ewaldOn) {
+      ew.imageSizeRef[b] = nkSlab; // bounded k-slab sample
+      ew.BoxReciprocalSums(b, sys.coordinates);
+    }
+    double t2 = now();
+    if (ewaldOn) recip = ew.BoxReciprocal(b, false);
+    double t3 = now();
+    if (ewaldOn) ew.imageSizeRef[b] = nkFull;
+    lj = pot.boxEnergy[b].inter;
+    real = pot.boxEnergy[b].real;
+    if (r > 0) {
+      tInter.push_back(t1 - t0);
+      tSums.push_back(t2 - t1);
+      tRecip.push_back(t3 - t2);
+    }
+    if (doForce) {
+      double f0 = now();
+      sys.calcEnergy.BoxForce(SystemPotential(), sys.coordinates,
+                              sys.atomForceRef, sys.molForceRef, sys.boxDimRef,
+                              b);
+      double f1 = now();
+      if (ewaldOn) {
+        ew.imageSizeRef[b] = std::max(1u, nkSlab / 8);
+        // BoxForceReciprocal opens one parallel region per atom; sample the
+        // first molecules only by shrinking nothing else -- cost is linear in
+        // the slab size, reported as such.
+        ew.BoxForceReciprocal(sys.coordinates, sys.atomForceRecRef,
+                              sys.molForceRecRef, b);
+        ew.imageSizeRef[b] = nkFull;
+      }
+      double f2 = now();
+      if (r > 0) {
+        tForce.push_back(f1 - f0);
+        tForceRec.push_back(f2 - f1);
+      }
+    }
+  }
+  out.f64("time.BoxInter", tInter);
+  out.f64("time.BoxReciprocalSums.slab", tSums);
+  out.f64("time.BoxReciprocal.slab", tRecip);
+  out.f64("time.BoxForce", tForce);
+  out.f64("time.BoxForceReciprocal.slab8", tForceRec);
+  out.f64("time.lj", lj);
+  out.f64("time.real", real);
+  out.f64("time.recipSlab", recip);
+  if (ewaldOn) {
+    out.f64("time.sumRnew.slab", ew.sumRnew[b], nkSlab);
+    out.f64("time.sumInew.slab", ew.sumInew[b], nkSlab);
+  }
+  return 0;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+  if (argc < 4) {
+    fprintf(stderr,
+            "usage: %s golden <in.conf> <out.bin> [nMoves] [seed]\n"
+            "       %s time   <in.conf> <out.bin> <kFraction> <reps> [force]\n",
+            argv[0], argv[0]);
+    return 1;
+  }
+  std::string mode = argv[1];
+  if (mode == "golden") return run_golden(argc, argv);
+  if (mode == "time") return run_time(argc, argv);
+  fprintf(stderr, "unknown mode %s\n", argv[1]);
+  return 1;
+}
