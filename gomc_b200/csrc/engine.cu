@@ -1,0 +1,1415 @@
+// engine.cu -- device-resident state + the C ABI of include/gomc_b200.h.
+//
+// Host side of the B200 engine: owns device memory, bins atoms into cells,
+// plans the reciprocal-space tiling, launches the kernels of pair.cuh and
+// recip.cuh on one stream and returns scalars through pinned memory.
+// No CPU fallback: every entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "../../include/gomc_b200.h"
+#include "common.cuh"
+#include "pair.cuh"
+#include "recip.cuh"
+
+using namespace gb;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_lastError = buf;
+  return code;
+}
+
+#define CK(call)                                                              \
+  do {                                                                        \
+    cudaError_t _e = (call);                                                  \
+    if (_e != cudaSuccess)                                                    \
+      return fail(GOMCB200_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,  \
+                  cudaGetErrorString(_e));                                    \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 16;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct KSet {
+  DevBuf<double> kx, ky, kz, hsqr, prefact;
+  std::vector<double> hkx, hky, hkz, hhsqr, hprefact;
+  int n = 0, kmax = 0;
+  int nmax[3] = {0, 0, 0};
+  double cv[3] = {0, 0, 0};
+  // factorised-sum plan
+  DevBuf<int4> rows, tiles;
+  int nTiles = 0, maxRows = 0;
+  bool planValid = false;
+};
+
+struct BoxState {
+  double axis[3] = {0, 0, 0};
+  bool haveAxes = false;
+  std::vector<int> hMols, hAtoms, hCharged;
+  DevBuf<int> molList, atomList, chargedList;
+  int nMols = 0, nAtoms = 0, nCharged = 0;
+  // cell-sorted copy
+  bool cellsDirty = true;
+  CellGrid grid;
+  DevBuf<int> keys, keysSorted, vals, sortedAtoms, cellStart;
+  DevBuf<double> sx, sy, sz, sq;
+  DevBuf<int2> skm;
+  // reciprocal space
+  KSet kset[2];  // index with cur / 1-cur
+  int cur = 0;   // kset[cur] = "new" k set (kx[]), kset[1-cur] = Ref
+  DevBuf<double> sum[4];  // Rnew, Inew, Rref, Iref through the idx below
+  int iRnew = 0, iInew = 1, iRref = 2, iIref = 3;
+  DevBuf<double4> packed;
+  bool packedDirty = true;
+};
+
+}  // namespace
+
+struct gomcb200_engine {
+  int device = 0, numSMs = 148, nBoxes = 1;
+  size_t smemOptin = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  // force field
+  bool haveFF = false;
+  int vdwKind = 0, ewald = 0, electrostatic = 0, kindCount = 0;
+  double rCut = 0, rCutLow = 0, rOn = 0;
+  std::vector<double> rCutCoulomb, alpha, recipRcut;
+  DevBuf<double> sigmaSq, epsilon_cn, nTab, shiftConst;
+  DevBuf<int> nHalf;
+  // topology
+  bool haveTopo = false;
+  int nAtoms = 0, nMols = 0, maxMolLen = 0;
+  std::vector<int> hKind, hMol, hMolStart;
+  std::vector<double> hCharge;
+  DevBuf<int> kind, mol, molStart;
+  DevBuf<double> x, y, z, q, comx, comy, comz;
+  DevBuf<double> force[5][3];
+  std::vector<BoxState> box;
+  int imageTotal = 0;
+  int recipAlgo = 1;
+  // scratch
+  DevBuf<double> part, blockA, blockB, result, molBuf, probeOut;
+  DevBuf<Probe> probes;
+  DevBuf<unsigned char> cubTemp;
+  double *hRes = nullptr;       // pinned, 64 doubles
+  double *hStage = nullptr;     // pinned staging for small uploads
+  size_t hStageCap = 0;
+  // timing
+  bool timing = false;
+  cudaEvent_t ev[8];
+  float lastTotalMs = 0, lastDominantMs = 0;
+};
+
+namespace {
+
+BoxParams make_params(const gomcb200_engine *e, int b) {
+  const BoxState &bx = e->box[b];
+  BoxParams p;
+  for (int d = 0; d < 3; ++d) {
+    p.ax[d] = bx.axis[d];
+    p.half[d] = bx.axis[d] * 0.5;  // BoxDimensions halfAx
+  }
+  p.rCut = e->rCut;
+  p.rCutSq = e->rCut * e->rCut;
+  p.rCutLowSq = e->rCutLow * e->rCutLow;
+  double rcc = e->rCutCoulomb[b];
+  p.rCutCoulombSq = rcc * rcc;
+  double br = std::max(e->rCut, rcc);  // src/BoxDimensions.cpp:17-18
+  p.boxRcutSq = br * br;
+  p.alpha = e->alpha[b];
+  p.alphaSq = p.alpha * p.alpha;
+  p.rOnSq = e->rOn * e->rOn;
+  p.factor1 = p.rCutSq - 3 * p.rOnSq;  // src/FFSwitch.h:103-105
+  double d3 = (p.rCutSq - p.rOnSq);
+  p.factor2 = 1.0 / (d3 * d3 * d3);
+  p.kindCount = e->kindCount;
+  p.vdwKind = e->vdwKind;
+  p.ewald = e->ewald;
+  p.electrostatic = e->electrostatic;
+  p.sigmaSq = e->sigmaSq.p;
+  p.epsilon_cn = e->epsilon_cn.p;
+  p.n = e->nTab.p;
+  p.shiftConst = e->shiftConst.p;
+  p.nHalf = e->nHalf.p;
+  return p;
+}
+
+int check_box(const gomcb200_engine *e, int b, bool needAxes = true) {
+  if (!e) return fail(GOMCB200_EINVAL, "null engine");
+  if (b < 0 || b >= e->nBoxes) return fail(GOMCB200_EINVAL, "box %d out of range", b);
+  if (!e->haveFF) return fail(GOMCB200_EINVAL, "gomcb200_init_forcefield not called");
+  if (!e->haveTopo) return fail(GOMCB200_EINVAL, "gomcb200_init_topology not called");
+  if (needAxes && !e->box[b].haveAxes)
+    return fail(GOMCB200_EINVAL, "gomcb200_set_box_axes not called for box %d", b);
+  return 0;
+}
+
+int stage_reserve(gomcb200_engine *e, size_t bytes) {
+  if (bytes <= e->hStageCap) return 0;
+  if (e->hStage) cudaFreeHost(e->hStage);
+  e->hStage = nullptr;
+  e->hStageCap = 0;
+  CK(cudaHostAlloc(&e->hStage, bytes * 2, cudaHostAllocDefault));
+  e->hStageCap = bytes * 2;
+  return 0;
+}
+
+// ---- cell binning ---------------------------------------------------------
+int ensure_cells(gomcb200_engine *e, int b) {
+  BoxState &bx = e->box[b];
+  if (!bx.cellsDirty) return 0;
+  const int n = bx.nAtoms;
+  double br = std::max(e->rCut, e->rCutCoulomb[b]);
+  CellGrid g;
+  for (int d = 0; d < 3; ++d) {  // CellList::ResizeGrid, src/CellList.cpp:138-163
+    int ed = (int)std::floor(bx.axis[d] / br);
+    g.edge[d] = std::max(ed, 3);
+    g.cellSize[d] = bx.axis[d] / g.edge[d];
+    g.generic[d] = g.edge[d] < 4;
+  }
+  g.nCells = g.edge[0] * g.edge[1] * g.edge[2];
+  bx.grid = g;
+  CK(bx.keys.reserve(n + 1));
+  CK(bx.keysSorted.reserve(n + 1));
+  CK(bx.vals.reserve(n + 1));
+  CK(bx.sortedAtoms.reserve(n + 1));
+  CK(bx.cellStart.reserve(g.nCells + 2));
+  CK(bx.sx.reserve(n + 1));
+  CK(bx.sy.reserve(n + 1));
+  CK(bx.sz.reserve(n + 1));
+  CK(bx.sq.reserve(n + 1));
+  CK(bx.skm.reserve(n + 1));
+  if (n > 0) {
+    int blocks = (n + 255) / 256;
+    k_cell_keys<<<blocks, 256, 0, e->stream>>>(g, n, bx.atomList.p, e->x.p, e->y.p,
+                                              e->z.p, bx.keys.p, bx.vals.p);
+    int bits = 1;
+    while ((1 << bits) < g.nCells + 1) ++bits;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, bx.keys.p, bx.keysSorted.p,
+                                    bx.vals.p, bx.sortedAtoms.p, n, 0, bits,
+                                    e->stream);
+    CK(e->cubTemp.reserve(tmp + 16));
+    CK(cub::DeviceRadixSort::SortPairs(e->cubTemp.p, tmp, bx.keys.p, bx.keysSorted.p,
+                                       bx.vals.p, bx.sortedAtoms.p, n, 0, bits,
+                                       e->stream));
+    k_gather_sorted<<<blocks, 256, 0, e->stream>>>(n, bx.sortedAtoms.p, e->x.p, e->y.p,
+                                                  e->z.p, e->q.p, e->kind.p, e->mol.p,
+                                                  bx.sx.p, bx.sy.p, bx.sz.p, bx.sq.p,
+                                                  bx.skm.p);
+    e->launches += 4;
+  }
+  k_cell_bounds<<<(g.nCells + 1 + 255) / 256, 256, 0, e->stream>>>(
+      g.nCells, n, bx.keysSorted.p, bx.cellStart.p);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  bx.cellsDirty = false;
+  return 0;
+}
+
+int fetch_result(gomcb200_engine *e, int n) {
+  CK(cudaMemcpyAsync(e->hRes, e->result.p, sizeof(double) * n, cudaMemcpyDeviceToHost,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+template <bool FORCE>
+void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int useSmem,
+                 int smemAtoms, size_t smemBytes, int grid) {
+  BoxState &bx = e->box[b];
+  double *fx = e->force[GOMCB200_ATOM_FORCE][0].p;
+  double *fy = e->force[GOMCB200_ATOM_FORCE][1].p;
+  double *fz = e->force[GOMCB200_ATOM_FORCE][2].p;
+#define LAUNCH(V)                                                                   \
+  do {                                                                              \
+    cudaFuncSetAttribute(k_pair_box<V, FORCE>,                                      \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); \
+    k_pair_box<V, FORCE><<<grid, kPairThreads, smemBytes, e->stream>>>(             \
+        p, bx.grid, slices, useSmem, smemAtoms, bx.cellStart.p, bx.sx.p, bx.sy.p,  \
+        bx.sz.p, bx.sq.p, bx.skm.p, bx.sortedAtoms.p, e->blockA.p, e->blockB.p, fx, \
+        fy, fz);                                                                    \
+  } while (0)
+  if (e->vdwKind == VDW_SHIFT)
+    LAUNCH(VDW_SHIFT);
+  else if (e->vdwKind == VDW_SWITCH)
+    LAUNCH(VDW_SWITCH);
+  else
+    LAUNCH(VDW_STD);
+#undef LAUNCH
+  e->launches += 1;
+}
+
+// pair sweep; results (LJ, real) land in e->result[0..1]
+int run_pair(gomcb200_engine *e, int b, bool force) {
+  int rc = ensure_cells(e, b);
+  if (rc) return rc;
+  BoxState &bx = e->box[b];
+  BoxParams p = make_params(e, b);
+  const int nCells = bx.grid.nCells;
+  int slices = (4 * e->numSMs + nCells - 1) / nCells;
+  slices = std::max(1, std::min(slices, 16));
+  int grid = nCells * slices;
+  // shared-memory staging of the neighbour cells (40 B per atom)
+  size_t staticSmem = 20 * 1024;
+  size_t capAtoms = (e->smemOptin > staticSmem ? (e->smemOptin - staticSmem) : 0) / 40;
+  double avg = (double)bx.nAtoms / nCells;
+  size_t want = (size_t)(27.0 * avg * 1.4) + 96;
+  int smemAtoms = (int)std::min(capAtoms, want);
+  smemAtoms &= ~1;
+  int useSmem = smemAtoms >= 64;
+  size_t smemBytes = useSmem ? (size_t)smemAtoms * 40 : 0;
+  CK(e->blockA.reserve(grid + 1024));
+  CK(e->blockB.reserve(grid + 1024));
+  if (force) {
+    // ResetForce (src/CalculateEnergy.cpp:1408-1428) is implicit: every atom
+    // and molecule of the box is overwritten below.
+    launch_pair<true>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid);
+  } else {
+    launch_pair<false>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid);
+  }
+  CK(cudaGetLastError());
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(grid, 2, e->blockA.p, e->blockB.p, nullptr,
+                                           nullptr, e->result.p);
+  e->launches += 1;
+  if (force && bx.nMols > 0) {
+    k_mol_force<<<(bx.nMols + 255) / 256, 256, 0, e->stream>>>(
+        bx.nMols, bx.molList.p, e->molStart.p, e->force[GOMCB200_ATOM_FORCE][0].p,
+        e->force[GOMCB200_ATOM_FORCE][1].p, e->force[GOMCB200_ATOM_FORCE][2].p,
+        e->force[GOMCB200_MOL_FORCE][0].p, e->force[GOMCB200_MOL_FORCE][1].p,
+        e->force[GOMCB200_MOL_FORCE][2].p);
+    e->launches += 1;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- reciprocal space -------------------------------------------------------
+// Ewald::RecipInitOrth (src/Ewald.cpp:847-903): same loop nest, same order,
+// same floating-point expressions, so the k list is index-compatible with the
+// host arrays of an unmodified GOMC.  Also derives the (a,b)-row table the
+// factorised kernel needs.
+struct RowRec {
+  int a, b, cmax, start;
+};
+
+// Enumerates the half-space k list.  ks == nullptr: count only.
+int recip_enumerate(const gomcb200_engine *e, int b, const double ax[3], KSet *ks,
+                    std::vector<RowRec> *rowsOut) {
+  const double alpha = e->alpha[b];
+  const double recip_rcut = e->recipRcut[b];
+  const double rr2 = recip_rcut * recip_rcut;
+  const double alpsqr4 = 1.0 / (4.0 * (alpha * alpha));
+  double cv[3];
+  for (int d = 0; d < 3; ++d) cv[d] = (1.0 / ax[d]) * (2.0 * M_PI);
+  const double vol = (ax[0] * ax[1] * ax[2]) / (4.0 * M_PI);
+  int nmax[3];
+  for (int d = 0; d < 3; ++d) nmax[d] = int(recip_rcut * ax[d] / (2.0 * M_PI)) + 1;
+  if (ks) {
+    ks->hkx.clear(); ks->hky.clear(); ks->hkz.clear(); ks->hhsqr.clear();
+    ks->hprefact.clear();
+    for (int d = 0; d < 3; ++d) { ks->nmax[d] = nmax[d]; ks->cv[d] = cv[d]; }
+    ks->kmax = std::max(std::max(nmax[0], nmax[1]), std::max(nmax[1], nmax[2]));
+  }
+  int counter = 0;
+  for (int ix = 0; ix <= nmax[0]; ix++) {
+    int nky_min = (ix == 0) ? 0 : -nmax[1];
+    for (int iy = nky_min; iy <= nmax[1]; iy++) {
+      int nkz_min = (ix == 0 && iy == 0) ? 1 : -nmax[2];
+      int first = -1, zlo = 0, zhi = 0, cnt = 0;
+      for (int iz = nkz_min; iz <= nmax[2]; iz++) {
+        double kX = cv[0] * ix, kY = cv[1] * iy, kZ = cv[2] * iz;
+        double ksqr = kX * kX + kY * kY + kZ * kZ;
+        if (ksqr < rr2) {
+          if (ks) {
+            ks->hkx.push_back(kX);
+            ks->hky.push_back(kY);
+            ks->hkz.push_back(kZ);
+            ks->hhsqr.push_back(ksqr);
+            ks->hprefact.push_back(kQQFact * exp(-ksqr * alpsqr4) / (ksqr * vol));
+          }
+          if (first < 0) { first = counter; zlo = iz; }
+          zhi = iz;
+          ++cnt;
+          counter++;
+        }
+      }
+      if (rowsOut && cnt > 0) {
+        // valid c form one run symmetric about 0 (ksqr is even and monotone
+        // in |c|); anything else would break the factorised indexing.
+        bool origin = (ix == 0 && iy == 0);
+        bool ok = origin ? (zlo == 1 && cnt == zhi) : (zlo == -zhi && cnt == 2 * zhi + 1);
+        if (!ok) return -1;
+        rowsOut->push_back({ix, iy, zhi, first});
+      }
+    }
+  }
+  return counter;
+}
+
+int build_plan(gomcb200_engine *e, KSet &ks, std::vector<RowRec> &rows) {
+  std::stable_sort(rows.begin(), rows.end(),
+                   [](const RowRec &x, const RowRec &y) { return x.cmax > y.cmax; });
+  std::vector<int4> hrows, htiles;
+  size_t i = 0;
+  int maxRows = 0;
+  while (i < rows.size()) {
+    int cmaxT = rows[i].cmax;
+    int CG = (cmaxT + 1 + kTC - 1) / kTC;
+    int RG = std::min(kFactThreads / CG, kMaxRG);
+    int R = RG * kTR;
+    int4 t = make_int4((int)hrows.size(), RG, CG, cmaxT);
+    for (int r = 0; r < R; ++r) {
+      if (i + r < rows.size()) {
+        const RowRec &rw = rows[i + r];
+        hrows.push_back(make_int4(rw.a, rw.b, rw.cmax, rw.start));
+      } else {
+        hrows.push_back(make_int4(0, 0, -1, 0));
+      }
+    }
+    htiles.push_back(t);
+    maxRows = std::max(maxRows, R);
+    i += R;
+  }
+  ks.nTiles = (int)htiles.size();
+  ks.maxRows = maxRows;
+  CK(ks.rows.reserve(hrows.size() + 1));
+  CK(ks.tiles.reserve(htiles.size() + 1));
+  if (!hrows.empty()) {
+    CK(cudaMemcpyAsync(ks.rows.p, hrows.data(), hrows.size() * sizeof(int4),
+                       cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(ks.tiles.p, htiles.data(), htiles.size() * sizeof(int4),
+                       cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  ks.planValid = true;
+  return 0;
+}
+
+int upload_kset(gomcb200_engine *e, KSet &ks) {
+  size_t n = ks.hkx.size();
+  size_t cap = std::max<size_t>(n, (size_t)e->imageTotal) + 1;
+  CK(ks.kx.reserve(cap));
+  CK(ks.ky.reserve(cap));
+  CK(ks.kz.reserve(cap));
+  CK(ks.hsqr.reserve(cap));
+  CK(ks.prefact.reserve(cap));
+  if (n) {
+    size_t bytes = n * sizeof(double);
+    CK(cudaMemcpyAsync(ks.kx.p, ks.hkx.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(ks.ky.p, ks.hky.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(ks.kz.p, ks.hkz.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(ks.hsqr.p, ks.hhsqr.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(ks.prefact.p, ks.hprefact.data(), bytes, cudaMemcpyHostToDevice,
+                       e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  ks.n = (int)n;
+  return 0;
+}
+
+int ensure_sums(gomcb200_engine *e, BoxState &bx, size_t n) {
+  size_t cap = std::max<size_t>(n, (size_t)e->imageTotal) + 1;
+  for (int i = 0; i < 4; ++i) {
+    if (bx.sum[i].cap < cap) {
+      CK(bx.sum[i].reserve(cap));
+      CK(cudaMemsetAsync(bx.sum[i].p, 0, bx.sum[i].cap * sizeof(double), e->stream));
+    }
+  }
+  return 0;
+}
+
+int ensure_packed(gomcb200_engine *e, int b) {
+  BoxState &bx = e->box[b];
+  if (!bx.packedDirty) return 0;
+  CK(bx.packed.reserve(bx.nCharged + 1));
+  if (bx.nCharged > 0) {
+    k_pack_charged<<<(bx.nCharged + 255) / 256, 256, 0, e->stream>>>(
+        bx.nCharged, bx.chargedList.p, e->x.p, e->y.p, e->z.p, e->q.p, bx.packed.p);
+    e->launches += 1;
+  }
+  bx.packedDirty = false;
+  return 0;
+}
+
+// Structure factor of box b on k set `ks` into sumRnew/sumInew; energy into
+// result[0].  (BoxReciprocalSetup: ks = new set; BoxReciprocalSums: Ref set.)
+int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
+  BoxState &bx = e->box[b];
+  const int nk = ks.n;
+  int rc = ensure_sums(e, bx, nk);
+  if (rc) return rc;
+  rc = ensure_packed(e, b);
+  if (rc) return rc;
+  const int nkStride = (nk + 31) & ~31;
+  const int nBlocks = (nk + 255) / 256;
+  CK(e->blockA.reserve(nBlocks + 1024));
+  if (nk == 0) {
+    CK(cudaMemsetAsync(e->result.p, 0, 8 * sizeof(double), e->stream));
+    return 0;
+  }
+  const int nAt = bx.nCharged;
+  int nSlabs = 1;
+  if (e->timing) cudaEventRecord(e->ev[2], e->stream);
+  if (e->recipAlgo == 1 && ks.planValid && ks.nTiles > 0 && nAt > 0) {
+    FactArgs fa;
+    fa.rows = ks.rows.p;
+    fa.tiles = ks.tiles.p;
+    fa.KX1 = ks.nmax[0] + 1;
+    fa.KY1 = ks.nmax[1] + 1;
+    fa.KZ1 = ks.nmax[2] + 1;
+    fa.ZS = ((fa.KZ1 + kTC - 1) / kTC) * kTC;
+    fa.RS = ks.maxRows;
+    size_t perAtom = (size_t)(fa.KX1 + fa.KY1 + fa.ZS + fa.RS) * sizeof(double2);
+    size_t budget = e->smemOptin > 8192 ? e->smemOptin - 4096 : 0;
+    int AT = (int)std::min<size_t>(32, budget / perAtom);
+    if (AT < 1)
+      return fail(GOMCB200_EINVAL, "k range too large for the factorised kernel");
+    fa.AT = AT;
+    nSlabs = std::max(1, (e->numSMs + ks.nTiles / 2) / ks.nTiles);
+    nSlabs = std::min(nSlabs, std::max(1, nAt / (2 * AT)));
+    int per = (nAt + nSlabs - 1) / nSlabs;
+    per = ((per + AT - 1) / AT) * AT;
+    nSlabs = (nAt + per - 1) / per;
+    fa.nAtoms = nAt;
+    fa.atomsPerSlab = per;
+    fa.nkStride = nkStride;
+    fa.cvx = ks.cv[0];
+    fa.cvy = ks.cv[1];
+    fa.cvz = ks.cv[2];
+    CK(e->part.reserve((size_t)nSlabs * 2 * nkStride + 64));
+    size_t smem = perAtom * AT;
+    CK(cudaFuncSetAttribute(k_recip_fact, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)smem));
+    dim3 grid(ks.nTiles, nSlabs);
+    k_recip_fact<<<grid, kFactThreads, smem, e->stream>>>(fa, bx.packed.p, e->part.p);
+    e->launches += 1;
+  } else {
+    nSlabs = std::max(1, std::min(64, (4 * e->numSMs + nBlocks - 1) / nBlocks));
+    nSlabs = std::min(nSlabs, std::max(1, nAt / 64));
+    int per = nAt > 0 ? (nAt + nSlabs - 1) / nSlabs : 1;
+    nSlabs = nAt > 0 ? (nAt + per - 1) / per : 1;
+    CK(e->part.reserve((size_t)nSlabs * 2 * nkStride + 64));
+    dim3 grid(nBlocks, nSlabs);
+    k_recip_direct<<<grid, 256, 0, e->stream>>>(nk, nkStride, nAt, per, bx.packed.p,
+                                               ks.kx.p, ks.ky.p, ks.kz.p, e->part.p);
+    e->launches += 1;
+  }
+  CK(cudaGetLastError());
+  if (e->timing) cudaEventRecord(e->ev[3], e->stream);
+  k_recip_finish<<<nBlocks, 256, 0, e->stream>>>(nk, nkStride, nSlabs, e->part.p,
+                                                ks.prefact.p, bx.sum[bx.iRnew].p,
+                                                bx.sum[bx.iInew].p, e->blockA.p);
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(nBlocks, 1, e->blockA.p, nullptr, nullptr,
+                                           nullptr, e->result.p);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
+                  const double *ny, const double *nz, int mode, double *out) {
+  BoxState &bx = e->box[b];
+  KSet &ks = bx.kset[1 - bx.cur];  // Ref set
+  const int nk = ks.n;
+  if (nk == 0) {
+    *out = 0.0;
+    return 0;
+  }
+  int rc = ensure_sums(e, bx, nk);
+  if (rc) return rc;
+  const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  size_t nd = 1 + 7 * (size_t)len;
+  rc = stage_reserve(e, nd * sizeof(double));
+  if (rc) return rc;
+  CK(e->molBuf.reserve(nd + 8));
+  double *h = e->hStage;
+  h[0] = (double)len;
+  for (int a = 0; a < len; ++a) {
+    double *m = h + 1 + 7 * a;
+    m[0] = e->hCharge[s + a];
+    m[1] = nx[a];
+    m[2] = ny[a];
+    m[3] = nz[a];
+    m[4] = m[5] = m[6] = 0.0;
+  }
+  CK(cudaMemcpyAsync(e->molBuf.p, h, nd * sizeof(double), cudaMemcpyHostToDevice,
+                     e->stream));
+  if (mode == 0) {  // old coordinates are resident: strided device copies
+    CK(cudaMemcpy2DAsync(e->molBuf.p + 1 + 4, 7 * sizeof(double), e->x.p + s,
+                         sizeof(double), sizeof(double), len, cudaMemcpyDeviceToDevice,
+                         e->stream));
+    CK(cudaMemcpy2DAsync(e->molBuf.p + 1 + 5, 7 * sizeof(double), e->y.p + s,
+                         sizeof(double), sizeof(double), len, cudaMemcpyDeviceToDevice,
+                         e->stream));
+    CK(cudaMemcpy2DAsync(e->molBuf.p + 1 + 6, 7 * sizeof(double), e->z.p + s,
+                         sizeof(double), sizeof(double), len, cudaMemcpyDeviceToDevice,
+                         e->stream));
+  }
+  const int nBlocks = (nk + 255) / 256;
+  CK(e->blockA.reserve(nBlocks + 1024));
+  k_mol_recip<<<nBlocks, 256, 7 * len * sizeof(double), e->stream>>>(
+      nk, mode, e->molBuf.p, ks.kx.p, ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRref].p,
+      bx.sum[bx.iIref].p, bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p, e->blockA.p);
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(nBlocks, 1, e->blockA.p, nullptr, nullptr,
+                                           nullptr, e->result.p);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  rc = fetch_result(e, 1);
+  if (rc) return rc;
+  *out = e->hRes[0];
+  return 0;
+}
+
+int upload3(gomcb200_engine *e, DevBuf<double> &dx, DevBuf<double> &dy, DevBuf<double> &dz,
+            const double *x, const double *y, const double *z, int first, int count,
+            int limit) {
+  if (first < 0 || count < 0 || first + count > limit)
+    return fail(GOMCB200_EINVAL, "range [%d,%d) outside [0,%d)", first, first + count, limit);
+  if (count == 0) return 0;
+  size_t bytes = sizeof(double) * (size_t)count;
+  CK(cudaMemcpyAsync(dx.p + first, x, bytes, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(dy.p + first, y, bytes, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(dz.p + first, z, bytes, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));  // caller may reuse pageable buffers
+  return 0;
+}
+
+void mark_coords_dirty(gomcb200_engine *e) {
+  for (auto &bx : e->box) {
+    bx.cellsDirty = true;
+    bx.packedDirty = true;
+  }
+}
+
+template <int VDW>
+void launch_probe(gomcb200_engine *e, int b, const BoxParams &p, int excludeMol, int n) {
+  BoxState &bx = e->box[b];
+  k_probe<VDW><<<n, kPairThreads, 0, e->stream>>>(p, bx.grid, excludeMol, e->probes.p,
+                                                 bx.cellStart.p, bx.sx.p, bx.sy.p, bx.sz.p,
+                                                 bx.sq.p, bx.skm.p, e->probeOut.p);
+}
+
+// probes staged in e->hStage as Probe[n]; results in e->hStage after the call
+int run_probes(gomcb200_engine *e, int b, int excludeMol, int n, std::vector<double> &out) {
+  int rc = ensure_cells(e, b);
+  if (rc) return rc;
+  BoxParams p = make_params(e, b);
+  CK(e->probes.reserve(n + 1));
+  CK(e->probeOut.reserve(3 * (size_t)n + 8));
+  CK(cudaMemcpyAsync(e->probes.p, e->hStage, sizeof(Probe) * (size_t)n,
+                     cudaMemcpyHostToDevice, e->stream));
+  if (e->vdwKind == VDW_SHIFT)
+    launch_probe<VDW_SHIFT>(e, b, p, excludeMol, n);
+  else if (e->vdwKind == VDW_SWITCH)
+    launch_probe<VDW_SWITCH>(e, b, p, excludeMol, n);
+  else
+    launch_probe<VDW_STD>(e, b, p, excludeMol, n);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  out.resize(3 * (size_t)n);
+  CK(cudaMemcpyAsync(out.data(), e->probeOut.p, sizeof(double) * 3 * n,
+                     cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+void timing_begin(gomcb200_engine *e) {
+  if (e->timing) cudaEventRecord(e->ev[0], e->stream);
+}
+void timing_end(gomcb200_engine *e, bool recip) {
+  if (!e->timing) return;
+  cudaEventRecord(e->ev[1], e->stream);
+  cudaEventSynchronize(e->ev[1]);
+  cudaEventElapsedTime(&e->lastTotalMs, e->ev[0], e->ev[1]);
+  e->lastDominantMs = 0;
+  if (recip) cudaEventElapsedTime(&e->lastDominantMs, e->ev[2], e->ev[3]);
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+const char *gomcb200_last_error(void) { return g_lastError.c_str(); }
+int gomcb200_version(void) { return 100; }
+
+int gomcb200_create(gomcb200_engine **out, int device, int nBoxes) {
+  if (!out || nBoxes < 1 || nBoxes > 2) return fail(GOMCB200_EINVAL, "bad arguments");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(GOMCB200_ENODEV, "no CUDA device: %s (this engine has no CPU fallback)",
+                ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+  if (device < 0) {
+    CK(cudaGetDevice(&device));
+  }
+  if (device >= count) return fail(GOMCB200_ENODEV, "device %d of %d", device, count);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(GOMCB200_ENODEV, "device %d is sm_%d%d; this build is sm_100a only", device,
+                prop.major, prop.minor);
+  gomcb200_engine *e = new gomcb200_engine();
+  e->device = device;
+  e->numSMs = prop.multiProcessorCount;
+  e->smemOptin = prop.sharedMemPerBlockOptin;
+  e->nBoxes = nBoxes;
+  e->box.resize(nBoxes);
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CK(cudaHostAlloc(&e->hRes, 64 * sizeof(double), cudaHostAllocDefault));
+  CK(e->result.reserve(64));
+  for (auto &ev : e->ev) CK(cudaEventCreate(&ev));
+  *out = e;
+  return 0;
+}
+
+int gomcb200_destroy(gomcb200_engine *e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  e->sigmaSq.release(); e->epsilon_cn.release(); e->nTab.release();
+  e->shiftConst.release(); e->nHalf.release();
+  e->kind.release(); e->mol.release(); e->molStart.release();
+  e->x.release(); e->y.release(); e->z.release(); e->q.release();
+  e->comx.release(); e->comy.release(); e->comz.release();
+  for (auto &f : e->force) for (auto &c : f) c.release();
+  for (auto &bx : e->box) {
+    bx.molList.release(); bx.atomList.release(); bx.chargedList.release();
+    bx.keys.release(); bx.keysSorted.release(); bx.vals.release();
+    bx.sortedAtoms.release(); bx.cellStart.release();
+    bx.sx.release(); bx.sy.release(); bx.sz.release(); bx.sq.release(); bx.skm.release();
+    for (auto &ks : bx.kset) {
+      ks.kx.release(); ks.ky.release(); ks.kz.release(); ks.hsqr.release();
+      ks.prefact.release(); ks.rows.release(); ks.tiles.release();
+    }
+    for (auto &s : bx.sum) s.release();
+    bx.packed.release();
+  }
+  e->part.release(); e->blockA.release(); e->blockB.release(); e->result.release();
+  e->molBuf.release(); e->probeOut.release(); e->probes.release(); e->cubTemp.release();
+  if (e->hRes) cudaFreeHost(e->hRes);
+  if (e->hStage) cudaFreeHost(e->hStage);
+  for (auto &ev : e->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return 0;
+}
+
+long long gomcb200_launch_count(const gomcb200_engine *e) { return e ? e->launches : 0; }
+
+int gomcb200_init_forcefield(gomcb200_engine *e, const double *sigmaSq,
+                             const double *epsilon_cn, const double *n, int vdwKind,
+                             int isMartini, int count, double rCut,
+                             const double *rCutCoulomb, double rCutLow, double rOn,
+                             const double *alpha, int ewald, int electrostatic,
+                             double diElectric_1) {
+  (void)diElectric_1;
+  if (!e || !sigmaSq || !epsilon_cn || !n || count < 1)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  if (isMartini) return fail(GOMCB200_EINVAL, "Martini switch potential not supported yet");
+  if (vdwKind < 0 || vdwKind > 2)
+    return fail(GOMCB200_EINVAL, "vdwKind %d not supported (EXP6 is a next-round row)", vdwKind);
+  CK(cudaSetDevice(e->device));
+  e->vdwKind = vdwKind;
+  e->ewald = ewald;
+  e->electrostatic = electrostatic;
+  e->kindCount = count;
+  e->rCut = rCut;
+  e->rCutLow = rCutLow;
+  e->rOn = rOn;
+  e->rCutCoulomb.assign(e->nBoxes, rCut);
+  e->alpha.assign(e->nBoxes, 0.0);
+  e->recipRcut.assign(e->nBoxes, 0.0);
+  for (int b = 0; b < e->nBoxes; ++b) {
+    if (rCutCoulomb) e->rCutCoulomb[b] = rCutCoulomb[b];
+    if (alpha) e->alpha[b] = alpha[b];
+  }
+  size_t sz = (size_t)count * count;
+  std::vector<double> shift(sz, 0.0);
+  std::vector<int> nHalf(sz, 0);
+  for (size_t i = 0; i < sz; ++i) {
+    double h = n[i] * 0.5;
+    if (h == std::floor(h) && h >= 1.0 && h <= 64.0) nHalf[i] = (int)h;
+    if (vdwKind == VDW_SHIFT) {  // FF_SHIFT::Init, src/FFShift.h:100-116
+      double rRat2 = sigmaSq[i] / (rCut * rCut);
+      double rRat4 = rRat2 * rRat2;
+      double attract = rRat4 * rRat2;
+      double repulse = pow(sqrt(rRat2), n[i]);
+      shift[i] = epsilon_cn[i] * (repulse - attract);
+    }
+  }
+  CK(e->sigmaSq.reserve(sz)); CK(e->epsilon_cn.reserve(sz)); CK(e->nTab.reserve(sz));
+  CK(e->shiftConst.reserve(sz)); CK(e->nHalf.reserve(sz));
+  CK(cudaMemcpy(e->sigmaSq.p, sigmaSq, sz * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->epsilon_cn.p, epsilon_cn, sz * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->nTab.p, n, sz * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->shiftConst.p, shift.data(), sz * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->nHalf.p, nHalf.data(), sz * sizeof(int), cudaMemcpyHostToDevice));
+  e->haveFF = true;
+  return 0;
+}
+
+int gomcb200_init_topology(gomcb200_engine *e, int nAtoms, int nMols, const int *particleKind,
+                           const int *particleMol, const double *particleCharge,
+                           const int *molStart) {
+  if (!e || nAtoms < 0 || nMols < 0 || !particleKind || !particleMol || !particleCharge ||
+      !molStart)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  e->nAtoms = nAtoms;
+  e->nMols = nMols;
+  e->hKind.assign(particleKind, particleKind + nAtoms);
+  e->hMol.assign(particleMol, particleMol + nAtoms);
+  e->hCharge.assign(particleCharge, particleCharge + nAtoms);
+  e->hMolStart.assign(molStart, molStart + nMols + 1);
+  e->maxMolLen = 0;
+  for (int m = 0; m < nMols; ++m)
+    e->maxMolLen = std::max(e->maxMolLen, molStart[m + 1] - molStart[m]);
+  size_t na = (size_t)nAtoms + 1, nm = (size_t)nMols + 1;
+  CK(e->kind.reserve(na)); CK(e->mol.reserve(na)); CK(e->q.reserve(na));
+  CK(e->molStart.reserve(nm + 1));
+  CK(e->x.reserve(na)); CK(e->y.reserve(na)); CK(e->z.reserve(na));
+  CK(e->comx.reserve(nm)); CK(e->comy.reserve(nm)); CK(e->comz.reserve(nm));
+  for (int w = 0; w < 5; ++w) {
+    size_t n = (w == GOMCB200_ATOM_FORCE || w == GOMCB200_ATOM_FORCE_REC) ? na : nm;
+    for (int c = 0; c < 3; ++c) {
+      CK(e->force[w][c].reserve(n));
+      CK(cudaMemset(e->force[w][c].p, 0, e->force[w][c].cap * sizeof(double)));
+    }
+  }
+  CK(cudaMemcpy(e->kind.p, particleKind, nAtoms * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->mol.p, particleMol, nAtoms * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->q.p, particleCharge, nAtoms * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->molStart.p, molStart, (nMols + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemset(e->comx.p, 0, e->comx.cap * sizeof(double)));
+  CK(cudaMemset(e->comy.p, 0, e->comy.cap * sizeof(double)));
+  CK(cudaMemset(e->comz.p, 0, e->comz.cap * sizeof(double)));
+  e->haveTopo = true;
+  return 0;
+}
+
+int gomcb200_set_box_molecules(gomcb200_engine *e, int box, const int *molIndices,
+                               int nMolsInBox) {
+  if (!e || box < 0 || box >= e->nBoxes || nMolsInBox < 0 || (!molIndices && nMolsInBox))
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!e->haveTopo) return fail(GOMCB200_EINVAL, "gomcb200_init_topology not called");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  bx.hMols.assign(molIndices, molIndices + nMolsInBox);
+  bx.hAtoms.clear();
+  bx.hCharged.clear();
+  for (int m : bx.hMols) {
+    if (m < 0 || m >= e->nMols) return fail(GOMCB200_EINVAL, "molecule index %d out of range", m);
+    for (int a = e->hMolStart[m]; a < e->hMolStart[m + 1]; ++a) {
+      bx.hAtoms.push_back(a);
+      // Ewald::Init particleHasNoCharge, src/Ewald.cpp:107-111
+      if (!(std::fabs(e->hCharge[a]) < 0.000000001)) bx.hCharged.push_back(a);
+    }
+  }
+  // ascending atom order: stable radix sort then yields ascending-within-cell
+  // order, the order GetCellListNeighbor sorts to (src/CellList.cpp:276)
+  std::sort(bx.hAtoms.begin(), bx.hAtoms.end());
+  bx.nMols = nMolsInBox;
+  bx.nAtoms = (int)bx.hAtoms.size();
+  bx.nCharged = (int)bx.hCharged.size();
+  CK(bx.molList.reserve(bx.nMols + 1));
+  CK(bx.atomList.reserve(bx.nAtoms + 1));
+  CK(bx.chargedList.reserve(bx.nCharged + 1));
+  if (bx.nMols)
+    CK(cudaMemcpy(bx.molList.p, bx.hMols.data(), bx.nMols * sizeof(int), cudaMemcpyHostToDevice));
+  if (bx.nAtoms)
+    CK(cudaMemcpy(bx.atomList.p, bx.hAtoms.data(), bx.nAtoms * sizeof(int),
+                  cudaMemcpyHostToDevice));
+  if (bx.nCharged)
+    CK(cudaMemcpy(bx.chargedList.p, bx.hCharged.data(), bx.nCharged * sizeof(int),
+                  cudaMemcpyHostToDevice));
+  bx.cellsDirty = true;
+  bx.packedDirty = true;
+  return 0;
+}
+
+int gomcb200_set_box_axes(gomcb200_engine *e, int box, const double axis[3]) {
+  if (!e || box < 0 || box >= e->nBoxes || !axis) return fail(GOMCB200_EINVAL, "bad arguments");
+  for (int d = 0; d < 3; ++d) {
+    if (!(axis[d] > 0.0)) return fail(GOMCB200_EINVAL, "axis %d is not positive", d);
+    e->box[box].axis[d] = axis[d];
+  }
+  e->box[box].haveAxes = true;
+  e->box[box].cellsDirty = true;
+  return 0;
+}
+
+int gomcb200_set_coords(gomcb200_engine *e, const double *x, const double *y, const double *z,
+                        int first, int count) {
+  if (!e || !e->haveTopo) return fail(GOMCB200_EINVAL, "topology not initialised");
+  CK(cudaSetDevice(e->device));
+  int rc = upload3(e, e->x, e->y, e->z, x, y, z, first, count, e->nAtoms);
+  if (rc) return rc;
+  mark_coords_dirty(e);
+  return 0;
+}
+
+int gomcb200_get_coords(gomcb200_engine *e, double *x, double *y, double *z, int first,
+                        int count) {
+  if (!e || !e->haveTopo || first < 0 || count < 0 || first + count > e->nAtoms)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  size_t bytes = sizeof(double) * (size_t)count;
+  CK(cudaMemcpy(x, e->x.p + first, bytes, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(y, e->y.p + first, bytes, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(z, e->z.p + first, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gomcb200_set_com(gomcb200_engine *e, const double *x, const double *y, const double *z,
+                     int first, int count) {
+  if (!e || !e->haveTopo) return fail(GOMCB200_EINVAL, "topology not initialised");
+  CK(cudaSetDevice(e->device));
+  return upload3(e, e->comx, e->comy, e->comz, x, y, z, first, count, e->nMols);
+}
+
+int gomcb200_set_molecule_coords(gomcb200_engine *e, int molIndex, const double *x,
+                                 const double *y, const double *z, const double com[3]) {
+  if (!e || !e->haveTopo || molIndex < 0 || molIndex >= e->nMols)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  int rc = gomcb200_set_coords(e, x, y, z, s, len);
+  if (rc) return rc;
+  if (com) rc = gomcb200_set_com(e, com, com + 1, com + 2, molIndex, 1);
+  return rc;
+}
+
+// ---- pair path --------------------------------------------------------------
+int gomcb200_box_inter(gomcb200_engine *e, int box, double *LJEn, double *REn) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  timing_begin(e);
+  rc = run_pair(e, box, false);
+  if (rc) return rc;
+  rc = fetch_result(e, 2);
+  if (rc) return rc;
+  timing_end(e, false);
+  if (LJEn) *LJEn = e->hRes[0];
+  if (REn) *REn = e->hRes[1];
+  return 0;
+}
+
+int gomcb200_box_force(gomcb200_engine *e, int box, double *LJEn, double *REn) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  timing_begin(e);
+  rc = run_pair(e, box, true);
+  if (rc) return rc;
+  rc = fetch_result(e, 2);
+  if (rc) return rc;
+  timing_end(e, false);
+  if (LJEn) *LJEn = e->hRes[0];
+  if (REn) *REn = e->hRes[1];
+  return 0;
+}
+
+int gomcb200_molecule_inter(gomcb200_engine *e, int box, int molIndex, const double *newX,
+                            const double *newY, const double *newZ, double *dLJ,
+                            double *dReal, int *overlap) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (molIndex < 0 || molIndex >= e->nMols || !newX || !newY || !newZ)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  rc = stage_reserve(e, sizeof(Probe) * 2 * (size_t)len + 6 * sizeof(double) * len);
+  if (rc) return rc;
+  // old coordinates of the molecule: host mirror is not kept, read them back
+  std::vector<double> ox(len), oy(len), oz(len);
+  rc = gomcb200_get_coords(e, ox.data(), oy.data(), oz.data(), s, len);
+  if (rc) return rc;
+  Probe *pr = reinterpret_cast<Probe *>(e->hStage);
+  for (int a = 0; a < len; ++a) {  // order of src/CalculateEnergy.cpp:590-678
+    Probe o = {ox[a], oy[a], oz[a], e->hCharge[s + a], -1.0, e->hKind[s + a], 0, 0};
+    Probe n = {newX[a], newY[a], newZ[a], e->hCharge[s + a], 1.0, e->hKind[s + a], 1, 0};
+    pr[2 * a] = o;
+    pr[2 * a + 1] = n;
+  }
+  std::vector<double> out;
+  rc = run_probes(e, box, molIndex, 2 * len, out);
+  if (rc) return rc;
+  double lj = 0.0, re = 0.0;
+  int ov = 0;
+  for (int t = 0; t < 2 * len; ++t) {
+    lj += out[3 * t];
+    re += out[3 * t + 1];
+    if (out[3 * t + 2] != 0.0) ov = 1;
+  }
+  if (dLJ) *dLJ = lj;
+  if (dReal) *dReal = re;
+  if (overlap) *overlap = ov;
+  return 0;
+}
+
+int gomcb200_particle_inter(gomcb200_engine *e, int box, int molIndex, int partIndex,
+                            int trials, const double *tx, const double *ty, const double *tz,
+                            double *en, double *real, int *overlap) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (molIndex < 0 || molIndex >= e->nMols || trials < 0 || !tx || !ty || !tz)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  if (trials == 0) return 0;
+  CK(cudaSetDevice(e->device));
+  const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  if (partIndex < 0 || partIndex >= len) return fail(GOMCB200_EINVAL, "partIndex out of range");
+  rc = stage_reserve(e, sizeof(Probe) * (size_t)trials);
+  if (rc) return rc;
+  Probe *pr = reinterpret_cast<Probe *>(e->hStage);
+  for (int t = 0; t < trials; ++t) {
+    Probe n = {tx[t], ty[t], tz[t], e->hCharge[s + partIndex], 1.0, e->hKind[s + partIndex],
+               1, 0};
+    pr[t] = n;
+  }
+  std::vector<double> out;
+  rc = run_probes(e, box, molIndex, trials, out);
+  if (rc) return rc;
+  for (int t = 0; t < trials; ++t) {
+    if (en) en[t] += out[3 * t];
+    if (real) real[t] += out[3 * t + 1];
+    if (overlap && out[3 * t + 2] != 0.0) overlap[t] |= 1;
+  }
+  return 0;
+}
+
+int gomcb200_calculate_torque(gomcb200_engine *e, int box) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  if (bx.nMols == 0) return 0;
+  BoxParams p = make_params(e, box);
+  k_torque<<<(bx.nMols + 255) / 256, 256, 0, e->stream>>>(
+      p, bx.nMols, bx.molList.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->comx.p,
+      e->comy.p, e->comz.p, e->force[0][0].p, e->force[0][1].p, e->force[0][2].p,
+      e->force[2][0].p, e->force[2][1].p, e->force[2][2].p, e->force[4][0].p,
+      e->force[4][1].p, e->force[4][2].p);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int gomcb200_get_forces(gomcb200_engine *e, int which, double *x, double *y, double *z,
+                        int first, int count) {
+  if (!e || !e->haveTopo || which < 0 || which > 4) return fail(GOMCB200_EINVAL, "bad arguments");
+  int limit = (which == GOMCB200_ATOM_FORCE || which == GOMCB200_ATOM_FORCE_REC) ? e->nAtoms
+                                                                                 : e->nMols;
+  if (first < 0 || count < 0 || first + count > limit)
+    return fail(GOMCB200_EINVAL, "range out of bounds");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  size_t bytes = sizeof(double) * (size_t)count;
+  if (x) CK(cudaMemcpy(x, e->force[which][0].p + first, bytes, cudaMemcpyDeviceToHost));
+  if (y) CK(cudaMemcpy(y, e->force[which][1].p + first, bytes, cudaMemcpyDeviceToHost));
+  if (z) CK(cudaMemcpy(z, e->force[which][2].p + first, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- reciprocal path --------------------------------------------------------
+int gomcb200_init_ewald(gomcb200_engine *e, int imageTotal, const double *recip_rcut) {
+  if (!e || imageTotal < 0 || !recip_rcut) return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!e->haveFF) return fail(GOMCB200_EINVAL, "gomcb200_init_forcefield not called");
+  e->imageTotal = imageTotal;
+  for (int b = 0; b < e->nBoxes; ++b) e->recipRcut[b] = recip_rcut[b];
+  return 0;
+}
+
+int gomcb200_recip_count(gomcb200_engine *e, int box, const double axis[3], double excess,
+                         int *imageSize) {
+  if (!e || box < 0 || box >= e->nBoxes || !axis || !imageSize || !e->haveFF)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  double ax[3] = {axis[0] * excess, axis[1] * excess, axis[2] * excess};
+  *imageSize = recip_enumerate(e, box, ax, nullptr, nullptr);
+  return 0;
+}
+
+int gomcb200_recip_init(gomcb200_engine *e, int box, const double axis[3], int *imageSize,
+                        int *kmax) {
+  if (!e || box < 0 || box >= e->nBoxes || !axis || !e->haveFF)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[bx.cur];
+  std::vector<RowRec> rows;
+  int n = recip_enumerate(e, box, axis, &ks, &rows);
+  ks.planValid = false;
+  if (n < 0) {  // cannot happen for an orthogonal box; keep the direct kernel usable
+    rows.clear();
+    n = recip_enumerate(e, box, axis, &ks, nullptr);
+  }
+  if (e->imageTotal > 0 && n > e->imageTotal)
+    return fail(GOMCB200_EKMAX,
+                "Kmax exceeded due to large change in system volume (%d > imageTotal %d)", n,
+                e->imageTotal);
+  int rc = upload_kset(e, ks);
+  if (rc) return rc;
+  if (!rows.empty()) {
+    rc = build_plan(e, ks, rows);
+    if (rc) return rc;
+  }
+  if (imageSize) *imageSize = n;
+  if (kmax) *kmax = ks.kmax;
+  return 0;
+}
+
+int gomcb200_get_kvectors(gomcb200_engine *e, int box, int which, double *kx, double *ky,
+                          double *kz, double *hsqr, double *prefact, int n) {
+  if (!e || box < 0 || box >= e->nBoxes) return fail(GOMCB200_EINVAL, "bad arguments");
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[which == GOMCB200_K_NEW ? bx.cur : 1 - bx.cur];
+  if (n > ks.n) return fail(GOMCB200_EINVAL, "n %d > imageSize %d", n, ks.n);
+  size_t bytes = sizeof(double) * (size_t)n;
+  if (kx) memcpy(kx, ks.hkx.data(), bytes);
+  if (ky) memcpy(ky, ks.hky.data(), bytes);
+  if (kz) memcpy(kz, ks.hkz.data(), bytes);
+  if (hsqr) memcpy(hsqr, ks.hhsqr.data(), bytes);
+  if (prefact) memcpy(prefact, ks.hprefact.data(), bytes);
+  return 0;
+}
+
+static int recip_sums_common(gomcb200_engine *e, int box, bool newSet, double *energyRecip) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  timing_begin(e);
+  rc = run_recip_sums(e, box, bx.kset[newSet ? bx.cur : 1 - bx.cur]);
+  if (rc) return rc;
+  rc = fetch_result(e, 1);
+  if (rc) return rc;
+  timing_end(e, true);
+  if (energyRecip) *energyRecip = e->hRes[0];
+  return 0;
+}
+
+int gomcb200_box_reciprocal_setup(gomcb200_engine *e, int box, double *energyRecip) {
+  return recip_sums_common(e, box, true, energyRecip);
+}
+
+int gomcb200_box_reciprocal_sums(gomcb200_engine *e, int box, double *energyRecip) {
+  return recip_sums_common(e, box, false, energyRecip);
+}
+
+int gomcb200_box_reciprocal(gomcb200_engine *e, int box, int isNewVolume, double *energyRecip) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[isNewVolume ? bx.cur : 1 - bx.cur];
+  if (ks.n == 0) {
+    if (energyRecip) *energyRecip = 0.0;
+    return 0;
+  }
+  rc = ensure_sums(e, bx, ks.n);
+  if (rc) return rc;
+  int nBlocks = (ks.n + 255) / 256;
+  CK(e->blockA.reserve(nBlocks + 1024));
+  k_recip_energy<<<nBlocks, 256, 0, e->stream>>>(ks.n, bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p,
+                                                ks.prefact.p, e->blockA.p);
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(nBlocks, 1, e->blockA.p, nullptr, nullptr, nullptr,
+                                           e->result.p);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  rc = fetch_result(e, 1);
+  if (rc) return rc;
+  if (energyRecip) *energyRecip = e->hRes[0];
+  return 0;
+}
+
+int gomcb200_mol_reciprocal(gomcb200_engine *e, int box, int molIndex, const double *newX,
+                            const double *newY, const double *newZ, double *energyRecipNew) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (molIndex < 0 || molIndex >= e->nMols || !newX || !newY || !newZ || !energyRecipNew)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  return run_mol_recip(e, box, molIndex, newX, newY, newZ, 0, energyRecipNew);
+}
+
+int gomcb200_swap_reciprocal(gomcb200_engine *e, int box, int molIndex, const double *x,
+                             const double *y, const double *z, int insert,
+                             double *energyRecipNew) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (molIndex < 0 || molIndex >= e->nMols || !x || !y || !z || !energyRecipNew)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  return run_mol_recip(e, box, molIndex, x, y, z, insert ? 1 : 2, energyRecipNew);
+}
+
+int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[1 - bx.cur];
+  rc = ensure_sums(e, bx, ks.n);
+  if (rc) return rc;
+  if (bx.nAtoms == 0) return 0;
+  BoxParams p = make_params(e, box);
+  k_force_recip_direct<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
+      p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->q.p,
+      ks.n, ks.kx.p, ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p,
+      e->force[2][0].p, e->force[2][1].p, e->force[2][2].p);
+  k_mol_force<<<(bx.nMols + 255) / 256, 256, 0, e->stream>>>(
+      bx.nMols, bx.molList.p, e->molStart.p, e->force[2][0].p, e->force[2][1].p,
+      e->force[2][2].p, e->force[3][0].p, e->force[3][1].p, e->force[3][2].p);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int gomcb200_get_recip_sums(gomcb200_engine *e, int box, int which, double *sumR, double *sumI,
+                            int n) {
+  if (!e || box < 0 || box >= e->nBoxes || n < 0) return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  if ((size_t)n > bx.sum[0].cap) return fail(GOMCB200_EINVAL, "n exceeds allocated sums");
+  CK(cudaStreamSynchronize(e->stream));
+  int ir = which == GOMCB200_SUM_NEW ? bx.iRnew : bx.iRref;
+  int ii = which == GOMCB200_SUM_NEW ? bx.iInew : bx.iIref;
+  if (sumR) CK(cudaMemcpy(sumR, bx.sum[ir].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  if (sumI) CK(cudaMemcpy(sumI, bx.sum[ii].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gomcb200_set_recip_ref(gomcb200_engine *e, int box) {
+  // Ewald::SetRecipRef, src/Ewald.cpp:1021-1053: sums new -> ref, k new -> Ref
+  if (!e || box < 0 || box >= e->nBoxes) return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &src = bx.kset[bx.cur], &dst = bx.kset[1 - bx.cur];
+  int rc = ensure_sums(e, bx, src.n);
+  if (rc) return rc;
+  size_t bytes = sizeof(double) * (size_t)src.n;
+  if (src.n) {
+    CK(cudaMemcpyAsync(bx.sum[bx.iRref].p, bx.sum[bx.iRnew].p, bytes, cudaMemcpyDeviceToDevice,
+                       e->stream));
+    CK(cudaMemcpyAsync(bx.sum[bx.iIref].p, bx.sum[bx.iInew].p, bytes, cudaMemcpyDeviceToDevice,
+                       e->stream));
+  }
+  dst.hkx = src.hkx; dst.hky = src.hky; dst.hkz = src.hkz; dst.hhsqr = src.hhsqr;
+  dst.hprefact = src.hprefact;
+  for (int d = 0; d < 3; ++d) { dst.nmax[d] = src.nmax[d]; dst.cv[d] = src.cv[d]; }
+  dst.kmax = src.kmax;
+  rc = upload_kset(e, dst);
+  if (rc) return rc;
+  // duplicate the plan (small)
+  dst.planValid = false;
+  if (src.planValid) {
+    size_t nr = src.rows.cap, nt = src.tiles.cap;
+    CK(dst.rows.reserve(nr));
+    CK(dst.tiles.reserve(nt));
+    CK(cudaMemcpyAsync(dst.rows.p, src.rows.p, std::min(nr, dst.rows.cap) * sizeof(int4),
+                       cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(dst.tiles.p, src.tiles.p, std::min(nt, dst.tiles.cap) * sizeof(int4),
+                       cudaMemcpyDeviceToDevice, e->stream));
+    dst.nTiles = src.nTiles;
+    dst.maxRows = src.maxRows;
+    dst.planValid = true;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int gomcb200_copy_recip(gomcb200_engine *e, int box) {
+  // Ewald::CopyRecip, src/Ewald.cpp:1441-1460: ref -> new
+  if (!e || box < 0 || box >= e->nBoxes) return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  int n = bx.kset[1 - bx.cur].n;
+  int rc = ensure_sums(e, bx, n);
+  if (rc) return rc;
+  if (n) {
+    size_t bytes = sizeof(double) * (size_t)n;
+    CK(cudaMemcpyAsync(bx.sum[bx.iRnew].p, bx.sum[bx.iRref].p, bytes, cudaMemcpyDeviceToDevice,
+                       e->stream));
+    CK(cudaMemcpyAsync(bx.sum[bx.iInew].p, bx.sum[bx.iIref].p, bytes, cudaMemcpyDeviceToDevice,
+                       e->stream));
+  }
+  return 0;
+}
+
+int gomcb200_update_recip(gomcb200_engine *e, int box) {
+  // Ewald::UpdateRecip, src/Ewald.cpp:1420-1434: O(1) swap new <-> ref
+  if (!e || box < 0 || box >= e->nBoxes) return fail(GOMCB200_EINVAL, "bad arguments");
+  BoxState &bx = e->box[box];
+  std::swap(bx.iRnew, bx.iRref);
+  std::swap(bx.iInew, bx.iIref);
+  return 0;
+}
+
+int gomcb200_update_recip_vec(gomcb200_engine *e, int box) {
+  // Ewald::UpdateRecipVec, src/Ewald.cpp:1462-1487: O(1) swap k <-> kRef
+  if (!e || box < 0 || box >= e->nBoxes) return fail(GOMCB200_EINVAL, "bad arguments");
+  e->box[box].cur = 1 - e->box[box].cur;
+  return 0;
+}
+
+int gomcb200_box_self_correction(gomcb200_engine *e, int box, double *self, double *correction) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  if (bx.nMols == 0) {
+    if (self) *self = 0.0;
+    if (correction) *correction = 0.0;
+    return 0;
+  }
+  BoxParams p = make_params(e, box);
+  int nBlocks = (bx.nMols + 255) / 256;
+  CK(e->blockA.reserve(nBlocks + 1024));
+  CK(e->blockB.reserve(nBlocks + 1024));
+  k_self_correction<<<nBlocks, 256, 0, e->stream>>>(p, bx.nMols, bx.molList.p, e->molStart.p,
+                                                   e->x.p, e->y.p, e->z.p, e->q.p, e->blockA.p,
+                                                   e->blockB.p);
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(nBlocks, 2, e->blockA.p, e->blockB.p, nullptr,
+                                           nullptr, e->result.p);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  rc = fetch_result(e, 2);
+  if (rc) return rc;
+  // src/Ewald.cpp:1159 and :1084
+  if (self) *self = e->hRes[0] * (-1.0 * p.alpha * kQQFact * kTwoOverSqrtPi * 0.5);
+  if (correction) *correction = -1.0 * kQQFact * e->hRes[1];
+  return 0;
+}
+
+// ---- literal drop-ins --------------------------------------------------------
+int gomcb200_call_box_inter(gomcb200_engine *e, int box, const double *x, const double *y,
+                            const double *z, const double axis[3], double *REn, double *LJEn) {
+  int rc = 0;
+  if (axis) rc = gomcb200_set_box_axes(e, box, axis);
+  if (rc) return rc;
+  rc = gomcb200_set_coords(e, x, y, z, 0, e ? e->nAtoms : 0);
+  if (rc) return rc;
+  return gomcb200_box_inter(e, box, LJEn, REn);
+}
+
+int gomcb200_call_box_reciprocal_sums(gomcb200_engine *e, int box, const double *x,
+                                      const double *y, const double *z, double *energyRecip) {
+  int rc = gomcb200_set_coords(e, x, y, z, 0, e ? e->nAtoms : 0);
+  if (rc) return rc;
+  return gomcb200_box_reciprocal_sums(e, box, energyRecip);
+}
+
+int gomcb200_call_box_force(gomcb200_engine *e, int box, const double *x, const double *y,
+                            const double *z, const double axis[3], double *REn, double *LJEn,
+                            double *aForcex, double *aForcey, double *aForcez,
+                            double *mForcex, double *mForcey, double *mForcez) {
+  int rc = 0;
+  if (axis) rc = gomcb200_set_box_axes(e, box, axis);
+  if (rc) return rc;
+  rc = gomcb200_set_coords(e, x, y, z, 0, e ? e->nAtoms : 0);
+  if (rc) return rc;
+  rc = gomcb200_box_force(e, box, LJEn, REn);
+  if (rc) return rc;
+  if (aForcex || aForcey || aForcez)
+    rc = gomcb200_get_forces(e, GOMCB200_ATOM_FORCE, aForcex, aForcey, aForcez, 0, e->nAtoms);
+  if (rc) return rc;
+  if (mForcex || mForcey || mForcez)
+    rc = gomcb200_get_forces(e, GOMCB200_MOL_FORCE, mForcex, mForcey, mForcez, 0, e->nMols);
+  return rc;
+}
+
+int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
+                                  const double *y, const double *z, double *LJEn, double *REn,
+                                  double *energyRecip) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  if (x) {
+    rc = gomcb200_set_coords(e, x, y, z, 0, e->nAtoms);
+    if (rc) return rc;
+  }
+  timing_begin(e);
+  rc = run_pair(e, box, false);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->hRes + 8, e->result.p, 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                     e->stream));
+  BoxState &bx = e->box[box];
+  double recip = 0.0;
+  if (e->ewald && e->electrostatic) {
+    rc = run_recip_sums(e, box, bx.kset[1 - bx.cur]);
+    if (rc) return rc;
+    rc = fetch_result(e, 1);
+    if (rc) return rc;
+    recip = e->hRes[0];
+  } else {
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  timing_end(e, e->ewald && e->electrostatic);
+  if (LJEn) *LJEn = e->hRes[8];
+  if (REn) *REn = e->hRes[9];
+  if (energyRecip) *energyRecip = recip;
+  return 0;
+}
+
+int gomcb200_set_recip_algo(gomcb200_engine *e, int algo) {
+  if (!e || algo < 0 || algo > 1) return fail(GOMCB200_EINVAL, "bad arguments");
+  e->recipAlgo = algo;
+  return 0;
+}
+
+int gomcb200_enable_timing(gomcb200_engine *e, int on) {
+  if (!e) return fail(GOMCB200_EINVAL, "null engine");
+  e->timing = on != 0;
+  return 0;
+}
+
+int gomcb200_last_timing(const gomcb200_engine *e, float *totalMs, float *dominantMs) {
+  if (!e) return fail(GOMCB200_EINVAL, "null engine");
+  if (totalMs) *totalMs = e->lastTotalMs;
+  if (dominantMs) *dominantMs = e->lastDominantMs;
+  return 0;
+}
+
+}  // extern "C"

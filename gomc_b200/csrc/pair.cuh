@@ -1,0 +1,494 @@
+// pair.cuh -- cell-list Lennard-Jones/Mie + real-space Coulomb kernels.
+//
+// Replaces BoxInterGPU / BoxForceGPU (src/GPU/CalculateEnergyCUDAKernel.cu:149,
+// src/GPU/CalculateForceCUDAKernel.cu:601) and gives device versions of
+// CalculateEnergy::MoleculeInter / ParticleInter (host-only in the reference).
+//
+// Design (B200): atoms are kept in cell-sorted SoA (x,y,z,q double; kind,mol
+// packed int2).  One CTA owns a slice of the i-atoms of one cell and first
+// stages the atoms of all 27 neighbour cells into shared memory (~150 KB for a
+// water box at rc = 10 A, read once from L2 with coalesced 8-byte loads).  Each
+// warp then owns one i-atom at a time: its 32 lanes test 32 different j-atoms
+// per round (cheap distance test), hits are compacted with ballot/popc into a
+// per-warp ring buffer, and whenever 32 hits are queued every lane evaluates
+// one full pair (erfc, Mie) -- so the expensive path always runs with full
+// lanes instead of the ~15 % in-range fraction.  Per-atom forces are summed in
+// registers and reduced with a fixed shuffle tree: no atomics, bit-reproducible.
+#pragma once
+#include "common.cuh"
+
+namespace gb {
+
+struct CellGrid {
+  int edge[3];
+  int nCells;
+  double cellSize[3];
+  int generic[3];  // 1: fewer than 4 cells on that axis -> per-pair min-image
+};
+
+// CellList::PositionToCell, src/CellList.h:88-101 (orthogonal box).
+__device__ __forceinline__ int position_to_cell(const CellGrid &g, double x,
+                                                double y, double z) {
+  int cx = (int)(x / g.cellSize[0]);
+  int cy = (int)(y / g.cellSize[1]);
+  int cz = (int)(z / g.cellSize[2]);
+  cx -= (cx == g.edge[0] ? 1 : 0);
+  cy -= (cy == g.edge[1] ? 1 : 0);
+  cz -= (cz == g.edge[2] ? 1 : 0);
+  return cx * g.edge[1] * g.edge[2] + cy * g.edge[2] + cz;
+}
+
+__global__ void k_cell_keys(CellGrid g, int n, const int *__restrict__ atomList,
+                            const double *__restrict__ x,
+                            const double *__restrict__ y,
+                            const double *__restrict__ z, int *keys,
+                            int *vals) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int a = atomList[t];
+  keys[t] = position_to_cell(g, x[a], y[a], z[a]);
+  vals[t] = a;
+}
+
+// cellStart[c] = first sorted position whose key >= c (lower bound).
+__global__ void k_cell_bounds(int nCells, int n,
+                              const int *__restrict__ sortedKeys,
+                              int *cellStart) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nCells) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (sortedKeys[mid] < c)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  cellStart[c] = lo;
+}
+
+__global__ void k_gather_sorted(int n, const int *__restrict__ sortedAtoms,
+                                const double *__restrict__ x,
+                                const double *__restrict__ y,
+                                const double *__restrict__ z,
+                                const double *__restrict__ q,
+                                const int *__restrict__ kind,
+                                const int *__restrict__ mol, double *sx,
+                                double *sy, double *sz, double *sq, int2 *skm) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int a = sortedAtoms[t];
+  sx[t] = x[a];
+  sy[t] = y[a];
+  sz[t] = z[a];
+  sq[t] = q[a];
+  skm[t] = make_int2(kind[a], mol[a]);
+}
+
+// ---------------------------------------------------------------------------
+// A neighbour "range": j-atoms [begin,end) in the j arrays (global sorted
+// arrays or their shared-memory staging), the global sorted index of `begin`,
+// and the periodic shift to add to (xi - xj) -- exactly what MinImageSigned
+// would add when the axis has >= 4 cells; 0 plus a per-pair test otherwise.
+struct JRange {
+  int begin, end, gbase, isSelf;
+  double sx, sy, sz;
+};
+
+constexpr int kQueue = 64;  // per-warp ring buffer entries (power of two)
+
+struct WarpQueue {
+  int j[kQueue];
+  double dx[kQueue], dy[kQueue], dz[kQueue];
+};
+
+struct PairAcc {
+  double lj, real, fx, fy, fz;
+  int overlap;
+};
+
+enum { SWEEP_PROBE = 0, SWEEP_HALF = 1, SWEEP_FULL = 2 };
+
+template <int VDW, bool FORCE>
+__device__ __forceinline__ void eval_pair(const BoxParams &p, int ki, double qi,
+                                          int excludeMol, bool countEnergy,
+                                          double sign, bool checkOverlap,
+                                          double dx, double dy, double dz,
+                                          double qj, int2 kmj, PairAcc &acc) {
+  if (kmj.y == excludeMol) return;
+  double r2 = dist_sq(dx, dy, dz);
+  if (checkOverlap && r2 < p.rCutLowSq) acc.overlap = 1;
+  int idx = ki + kmj.x * p.kindCount;
+  if (FORCE) {
+    double eL, wL, eC = 0.0, wC = 0.0;
+    calc_en_vir<VDW>(p, r2, idx, eL, wL);
+    if (p.electrostatic) {
+      double qq = qi * qj * kQQFact;
+      if (qq != 0.0) calc_coulomb_en_vir<VDW>(p, r2, qq, eC, wC);
+    }
+    if (countEnergy) {
+      acc.lj += eL;
+      acc.real += eC;
+    }
+    double w = wL + wC;
+    acc.fx += dx * w;
+    acc.fy += dy * w;
+    acc.fz += dz * w;
+  } else {
+    if (p.electrostatic) {
+      double qq = qi * qj * kQQFact;
+      if (qq != 0.0) acc.real += sign * calc_coulomb<VDW>(p, r2, qq);
+    }
+    acc.lj += sign * calc_en<VDW>(p, r2, idx);
+  }
+}
+
+// One warp, one position (xi,yi,zi), ranges[rangeFirst::rangeStride].
+//  SWEEP_PROBE: position is not part of the j set; every in-range j counts.
+//  SWEEP_HALF : energy-only half shell; in the self range only j > selfIndex.
+//  SWEEP_FULL : all neighbours, own force; energy counted for jGlobal > iGlobal.
+// selfIndex is in the index space of the self range; iGlobal the global sorted
+// index of the atom.
+template <int VDW, bool FORCE, int SWEEP>
+__device__ __forceinline__ void warp_probe(
+    const BoxParams &p, const int generic[3], double xi, double yi, double zi,
+    int ki, double qi, int excludeMol, int selfIndex, int iGlobal, double sign,
+    bool checkOverlap, const JRange *ranges, int nRanges, int rangeStride,
+    int rangeFirst, const double *__restrict__ jx,
+    const double *__restrict__ jy, const double *__restrict__ jz,
+    const double *__restrict__ jq, const int2 *__restrict__ jkm, WarpQueue &wq,
+    PairAcc &acc) {
+  const int lane = threadIdx.x & 31;
+  const unsigned ltMask = (1u << lane) - 1u;
+  int head = 0, count = 0;
+  for (int r = rangeFirst; r < nRanges; r += rangeStride) {
+    const JRange rg = ranges[r];
+    for (int base = rg.begin; base < rg.end; base += 32) {
+      int j = base + lane;
+      bool in = false;
+      int jEnc = j;
+      double dx = 0.0, dy = 0.0, dz = 0.0;
+      bool valid = j < rg.end;
+      if (SWEEP == SWEEP_HALF) valid = valid && !(rg.isSelf && j <= selfIndex);
+      if (SWEEP == SWEEP_FULL) valid = valid && !(rg.isSelf && j == selfIndex);
+      if (valid) {
+        dx = (xi - jx[j]) + rg.sx;
+        dy = (yi - jy[j]) + rg.sy;
+        dz = (zi - jz[j]) + rg.sz;
+        if (generic[0]) dx = min_image(dx, p.ax[0], p.half[0]);
+        if (generic[1]) dy = min_image(dy, p.ax[1], p.half[1]);
+        if (generic[2]) dz = min_image(dz, p.ax[2], p.half[2]);
+        double r2 = dist_sq(dx, dy, dz);
+        in = p.boxRcutSq > r2;  // BoxDimensions::InRcut, strict
+        if (SWEEP == SWEEP_FULL && (rg.gbase + (j - rg.begin)) > iGlobal)
+          jEnc |= 0x40000000;  // this side of the pair owns the energy
+      }
+      unsigned m = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        int pos = (head + count + __popc(m & ltMask)) & (kQueue - 1);
+        wq.j[pos] = jEnc;
+        wq.dx[pos] = dx;
+        wq.dy[pos] = dy;
+        wq.dz[pos] = dz;
+      }
+      count += __popc(m);
+      __syncwarp();
+      if (count >= 32) {
+        int pos = (head + lane) & (kQueue - 1);
+        int je = wq.j[pos];
+        int jj = je & 0x3fffffff;
+        double ddx = wq.dx[pos], ddy = wq.dy[pos], ddz = wq.dz[pos];
+        eval_pair<VDW, FORCE>(p, ki, qi, excludeMol,
+                              SWEEP != SWEEP_FULL || (je & 0x40000000), sign,
+                              checkOverlap, ddx, ddy, ddz, jq[jj], jkm[jj], acc);
+        head = (head + 32) & (kQueue - 1);
+        count -= 32;
+        __syncwarp();
+      }
+    }
+  }
+  if (lane < count) {
+    int pos = (head + lane) & (kQueue - 1);
+    int je = wq.j[pos];
+    int jj = je & 0x3fffffff;
+    eval_pair<VDW, FORCE>(p, ki, qi, excludeMol,
+                          SWEEP != SWEEP_FULL || (je & 0x40000000), sign,
+                          checkOverlap, wq.dx[pos], wq.dy[pos], wq.dz[pos],
+                          jq[jj], jkm[jj], acc);
+  }
+  __syncwarp();
+}
+
+// Neighbour ranges of a cell.  halfShell: own cell + the 13 "forward" cells
+// (each unordered cell pair exactly once; needs >= 3 cells per axis, which
+// CellList::ResizeGrid guarantees).
+__device__ __forceinline__ int build_ranges(const CellGrid &g,
+                                            const BoxParams &p, int cell,
+                                            bool halfShell,
+                                            const int *__restrict__ cellStart,
+                                            JRange *ranges) {
+  int cz = cell % g.edge[2];
+  int cy = (cell / g.edge[2]) % g.edge[1];
+  int cx = cell / (g.edge[2] * g.edge[1]);
+  int n = 0;
+  for (int d = (halfShell ? 13 : 0); d < 27; ++d) {
+    int dx = d / 9 - 1, dy = (d / 3) % 3 - 1, dz = d % 3 - 1;
+    int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+    JRange r;
+    r.sx = r.sy = r.sz = 0.0;
+    r.isSelf = (d == 13);
+    // raw = xi - xj; a j in a wrapped-below cell sits near +L: raw ~ -L -> +ax
+    if (nx < 0) { nx += g.edge[0]; if (!g.generic[0]) r.sx = p.ax[0]; }
+    else if (nx >= g.edge[0]) { nx -= g.edge[0]; if (!g.generic[0]) r.sx = -p.ax[0]; }
+    if (ny < 0) { ny += g.edge[1]; if (!g.generic[1]) r.sy = p.ax[1]; }
+    else if (ny >= g.edge[1]) { ny -= g.edge[1]; if (!g.generic[1]) r.sy = -p.ax[1]; }
+    if (nz < 0) { nz += g.edge[2]; if (!g.generic[2]) r.sz = p.ax[2]; }
+    else if (nz >= g.edge[2]) { nz -= g.edge[2]; if (!g.generic[2]) r.sz = -p.ax[2]; }
+    int nc = nx * g.edge[1] * g.edge[2] + ny * g.edge[2] + nz;
+    r.begin = cellStart[nc];
+    r.end = cellStart[nc + 1];
+    r.gbase = r.begin;
+    ranges[n++] = r;
+  }
+  return n;
+}
+
+constexpr int kPairThreads = 256;
+constexpr int kPairWarps = kPairThreads / 32;
+
+// Full-box pair sweep.  grid = nCells * slices.  FORCE: all 27 neighbour
+// cells, every atom accumulates its own force, energy counted for j > i.
+// !FORCE: half shell (own cell with j > i plus 13 forward cells).
+// Dynamic shared memory: staged j atoms (40 B each) when useSmem, else the j
+// arrays are read from global memory (cells too full to stage).
+template <int VDW, bool FORCE>
+__global__ void __launch_bounds__(kPairThreads)
+    k_pair_box(BoxParams p, CellGrid g, int slices, int useSmem, int smemAtoms,
+               const int *__restrict__ cellStart, const double *__restrict__ sx,
+               const double *__restrict__ sy, const double *__restrict__ sz,
+               const double *__restrict__ sq, const int2 *__restrict__ skm,
+               const int *__restrict__ sortedAtoms, double *__restrict__ partLJ,
+               double *__restrict__ partReal, double *__restrict__ fx,
+               double *__restrict__ fy, double *__restrict__ fz) {
+  extern __shared__ __align__(16) unsigned char dynSmem[];
+  __shared__ JRange ranges[27];
+  __shared__ JRange stagedRanges[27];
+  __shared__ WarpQueue queues[kPairWarps];
+  __shared__ double red[2][kPairWarps];
+  __shared__ int nRangesSh;
+
+  const int cell = blockIdx.x / slices, slice = blockIdx.x % slices;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int iBegin0 = cellStart[cell], iEnd0 = cellStart[cell + 1];
+  const int nI = iEnd0 - iBegin0;
+  const int iBegin = iBegin0 + (int)(((long long)nI * slice) / slices);
+  const int iEnd = iBegin0 + (int)(((long long)nI * (slice + 1)) / slices);
+
+  if (threadIdx.x == 0)
+    nRangesSh = build_ranges(g, p, cell, !FORCE, cellStart, ranges);
+  __syncthreads();
+  const int nRanges = nRangesSh;
+
+  const double *jx = sx, *jy = sy, *jz = sz, *jq = sq;
+  const int2 *jkm = skm;
+  int selfOffset = 0;  // self-range index = global sorted index + selfOffset
+  const JRange *useRanges = ranges;
+  if (useSmem && iEnd > iBegin) {
+    double *smx = reinterpret_cast<double *>(dynSmem);
+    double *smy = smx + smemAtoms;
+    double *smz = smy + smemAtoms;
+    double *smq = smz + smemAtoms;
+    int2 *smkm = reinterpret_cast<int2 *>(smq + smemAtoms);
+    int off = 0;
+    for (int r = 0; r < nRanges; ++r) {
+      const JRange rg = ranges[r];
+      int len = rg.end - rg.begin;
+      for (int t = threadIdx.x; t < len; t += blockDim.x) {
+        smx[off + t] = sx[rg.begin + t];
+        smy[off + t] = sy[rg.begin + t];
+        smz[off + t] = sz[rg.begin + t];
+        smq[off + t] = sq[rg.begin + t];
+        smkm[off + t] = skm[rg.begin + t];
+      }
+      if (threadIdx.x == 0) {
+        JRange s = rg;
+        s.begin = off;
+        s.end = off + len;
+        stagedRanges[r] = s;
+      }
+      if (rg.isSelf) selfOffset = off - rg.begin;
+      off += len;
+    }
+    jx = smx; jy = smy; jz = smz; jq = smq; jkm = smkm;
+    useRanges = stagedRanges;
+  }
+  __syncthreads();
+
+  double eLJ = 0.0, eReal = 0.0;
+  for (int i = iBegin + warp; i < iEnd; i += kPairWarps) {
+    PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
+    double xi = sx[i], yi = sy[i], zi = sz[i], qi = sq[i];
+    int2 kmi = skm[i];
+    warp_probe<VDW, FORCE, FORCE ? SWEEP_FULL : SWEEP_HALF>(
+        p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y, i + selfOffset, i, 1.0,
+        false, useRanges, nRanges, 1, 0, jx, jy, jz, jq, jkm, queues[warp],
+        acc);
+    eLJ += acc.lj;
+    eReal += acc.real;
+    if (FORCE) {
+      double f0 = warp_sum(acc.fx), f1 = warp_sum(acc.fy), f2 = warp_sum(acc.fz);
+      if (lane == 0) {
+        int a = sortedAtoms[i];
+        fx[a] = f0;
+        fy[a] = f1;
+        fz[a] = f2;
+      }
+    }
+  }
+  eLJ = warp_sum(eLJ);
+  eReal = warp_sum(eReal);
+  if (lane == 0) {
+    red[0][warp] = eLJ;
+    red[1][warp] = eReal;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < kPairWarps; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
+    partLJ[blockIdx.x] = a;
+    partReal[blockIdx.x] = b;
+  }
+}
+
+// Deterministic final reduction of up to 4 partial arrays of length n into
+// out[0..nArr).  One block.
+__global__ void k_final_reduce(int n, int nArr, const double *a0,
+                               const double *a1, const double *a2,
+                               const double *a3, double *out) {
+  __shared__ double scratch[32];
+  const double *arr[4] = {a0, a1, a2, a3};
+  for (int k = 0; k < nArr; ++k) {
+    double v = 0.0;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) v += arr[k][t];
+    double s = block_sum(v, scratch);
+    if (threadIdx.x == 0) out[k] = s;
+    __syncthreads();
+  }
+}
+
+// molForce[m] = sum of atomForce over the atoms of m (fixed order).
+__global__ void k_mol_force(int nMolsBox, const int *__restrict__ molList,
+                            const int *__restrict__ molStart,
+                            const double *__restrict__ fx,
+                            const double *__restrict__ fy,
+                            const double *__restrict__ fz, double *mx,
+                            double *my, double *mz) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nMolsBox) return;
+  int m = molList[t];
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int i = molStart[m]; i < molStart[m + 1]; ++i) {
+    a += fx[i];
+    b += fy[i];
+    c += fz[i];
+  }
+  mx[m] = a;
+  my[m] = b;
+  mz[m] = c;
+}
+
+// CalculateEnergy::CalculateTorque, src/CalculateEnergy.cpp:1365-1406.
+__global__ void k_torque(BoxParams p, int nMolsBox,
+                         const int *__restrict__ molList,
+                         const int *__restrict__ molStart,
+                         const double *__restrict__ x,
+                         const double *__restrict__ y,
+                         const double *__restrict__ z,
+                         const double *__restrict__ cx,
+                         const double *__restrict__ cy,
+                         const double *__restrict__ cz,
+                         const double *__restrict__ afx,
+                         const double *__restrict__ afy,
+                         const double *__restrict__ afz,
+                         const double *__restrict__ rfx,
+                         const double *__restrict__ rfy,
+                         const double *__restrict__ rfz, double *tx, double *ty,
+                         double *tz) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nMolsBox) return;
+  int m = molList[t];
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int i = molStart[m]; i < molStart[m + 1]; ++i) {
+    double dx = min_image(x[i] - cx[m], p.ax[0], p.half[0]);
+    double dy = min_image(y[i] - cy[m], p.ax[1], p.half[1]);
+    double dz = min_image(z[i] - cz[m], p.ax[2], p.half[2]);
+    double fx = afx[i] + rfx[i], fy = afy[i] + rfy[i], fz = afz[i] + rfz[i];
+    a += dy * fz - dz * fy;
+    b += dz * fx - dx * fz;
+    c += dx * fy - dy * fx;
+  }
+  tx[m] = a;
+  ty[m] = b;
+  tz[m] = c;
+}
+
+// ---------------------------------------------------------------------------
+// Probe kernel: energies of a few probe positions against the box, excluding
+// one molecule.  Used by MoleculeInter (2*len probes: old with sign -1, new
+// with sign +1 and overlap check) and ParticleInter (one probe per trial).
+// grid = nProbes, block = 256.  out[probe] = {lj, real, overlap}.
+struct Probe {
+  double x, y, z, q, sign;
+  int kind, checkOverlap, pad;
+};
+
+template <int VDW>
+__global__ void __launch_bounds__(kPairThreads)
+    k_probe(BoxParams p, CellGrid g, int excludeMol,
+            const Probe *__restrict__ probes, const int *__restrict__ cellStart,
+            const double *__restrict__ sx, const double *__restrict__ sy,
+            const double *__restrict__ sz, const double *__restrict__ sq,
+            const int2 *__restrict__ skm, double *__restrict__ out) {
+  __shared__ JRange ranges[27];
+  __shared__ WarpQueue queues[kPairWarps];
+  __shared__ double red[2][kPairWarps];
+  __shared__ int ovl[kPairWarps];
+  __shared__ int nRangesSh;
+  const Probe pr = probes[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    int cell = position_to_cell(g, pr.x, pr.y, pr.z);
+    nRangesSh = build_ranges(g, p, cell, false, cellStart, ranges);
+  }
+  __syncthreads();
+  PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
+  warp_probe<VDW, false, SWEEP_PROBE>(
+      p, g.generic, pr.x, pr.y, pr.z, pr.kind, pr.q, excludeMol, -1, -1,
+      pr.sign, pr.checkOverlap != 0, ranges, nRangesSh, kPairWarps, warp, sx,
+      sy, sz, sq, skm, queues[warp], acc);
+  double a = warp_sum(acc.lj), b = warp_sum(acc.real);
+  int ov = __any_sync(0xffffffffu, acc.overlap);
+  if (lane == 0) {
+    red[0][warp] = a;
+    red[1][warp] = b;
+    ovl[warp] = ov;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    int o = 0;
+    for (int w = 0; w < kPairWarps; ++w) {
+      s0 += red[0][w];
+      s1 += red[1][w];
+      o |= ovl[w];
+    }
+    out[3 * blockIdx.x + 0] = s0;
+    out[3 * blockIdx.x + 1] = s1;
+    out[3 * blockIdx.x + 2] = (double)o;
+  }
+}
+
+}  // namespace gb

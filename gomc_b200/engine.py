@@ -1,0 +1,371 @@
+"""ctypes binding of the C ABI in include/gomc_b200.h (libgomc_b200.so).
+
+This is the Python face of the product path: it only marshals numpy arrays to
+the C entry points.  There is no CPU fallback -- if the CUDA library has not
+been built, or no B200 is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgomc_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_vp = C.c_void_p
+
+ATOM_FORCE, MOL_FORCE, ATOM_FORCE_REC, MOL_FORCE_REC, MOL_TORQUE = range(5)
+K_NEW, K_REF = 0, 1
+SUM_NEW, SUM_REF = 0, 1
+
+# name -> (restype, argtypes); mirrors include/gomc_b200.h one to one
+_SIGS = {
+    "gomcb200_last_error": (C.c_char_p, []),
+    "gomcb200_version": (C.c_int, []),
+    "gomcb200_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int]),
+    "gomcb200_destroy": (C.c_int, [_vp]),
+    "gomcb200_launch_count": (C.c_longlong, [_vp]),
+    "gomcb200_init_forcefield": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int,
+                                           C.c_double, _dp, C.c_double, C.c_double, _dp,
+                                           C.c_int, C.c_int, C.c_double]),
+    "gomcb200_init_topology": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _dp, _ip]),
+    "gomcb200_set_box_molecules": (C.c_int, [_vp, C.c_int, _ip, C.c_int]),
+    "gomcb200_set_box_axes": (C.c_int, [_vp, C.c_int, _dp]),
+    "gomcb200_set_coords": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
+    "gomcb200_get_coords": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
+    "gomcb200_set_com": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
+    "gomcb200_set_molecule_coords": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp]),
+    "gomcb200_box_inter": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "gomcb200_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "gomcb200_molecule_inter": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "gomcb200_particle_inter": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
+                                          _dp, _dp, _dp, _ip]),
+    "gomcb200_calculate_torque": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_get_forces": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int]),
+    "gomcb200_init_ewald": (C.c_int, [_vp, C.c_int, _dp]),
+    "gomcb200_recip_init": (C.c_int, [_vp, C.c_int, _dp, _ip, _ip]),
+    "gomcb200_recip_count": (C.c_int, [_vp, C.c_int, _dp, C.c_double, _ip]),
+    "gomcb200_get_kvectors": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int]),
+    "gomcb200_box_reciprocal_setup": (C.c_int, [_vp, C.c_int, _dp]),
+    "gomcb200_box_reciprocal_sums": (C.c_int, [_vp, C.c_int, _dp]),
+    "gomcb200_box_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
+    "gomcb200_mol_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
+    "gomcb200_swap_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp]),
+    "gomcb200_box_force_reciprocal": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_get_recip_sums": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int]),
+    "gomcb200_set_recip_ref": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_copy_recip": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_update_recip": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_update_recip_vec": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_box_self_correction": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "gomcb200_call_box_inter": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "gomcb200_call_box_reciprocal_sums": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp]),
+    "gomcb200_call_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
+                                         _dp, _dp, _dp, _dp, _dp, _dp]),
+    "gomcb200_call_full_box_energy": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "gomcb200_set_recip_algo": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "gomcb200_enable_timing": (C.c_int, [_vp, C.c_int]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+_lib = None
+
+
+def load_library():
+    """dlopen libgomc_b200.so and type every symbol of include/gomc_b200.h."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ "
+                "as g; g.build()'` (nvcc, sm_100a).  gomc_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)     # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_ip)
+
+
+class Engine:
+    """Thin object wrapper over the opaque gomcb200_engine handle."""
+
+    def __init__(self, n_boxes=1, device=-1):
+        self.L = load_library()
+        h = _vp()
+        rc = self.L.gomcb200_create(C.byref(h), device, n_boxes)
+        if rc != 0:
+            raise EngineError(f"gomcb200_create failed ({rc}): "
+                              f"{self.L.gomcb200_last_error().decode()}")
+        self.h = h
+        self.n_boxes = n_boxes
+        self.n_atoms = 0
+        self.n_mols = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gomcb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(f"gomc_b200 error {rc}: {self.L.gomcb200_last_error().decode()}")
+
+    # ---- setup -----------------------------------------------------------
+    def init_forcefield(self, sigma_sq, epsilon_cn, n, vdw_kind, count, r_cut, r_cut_coulomb,
+                        r_cut_low, r_switch, alpha, ewald, electrostatic, is_martini=0):
+        (a, pa), (b, pb), (c, pc) = _d(sigma_sq), _d(epsilon_cn), _d(n)
+        (rc_, prc), (al, pal) = _d(np.atleast_1d(r_cut_coulomb)), _d(np.atleast_1d(alpha))
+        self._ck(self.L.gomcb200_init_forcefield(self.h, pa, pb, pc, int(vdw_kind),
+                                                 int(is_martini), int(count), float(r_cut), prc,
+                                                 float(r_cut_low), float(r_switch), pal,
+                                                 int(ewald), int(electrostatic), 1.0))
+
+    def init_topology(self, kind, mol, charge, mol_start):
+        (k, pk), (m, pm), (q, pq), (s, ps) = _i(kind), _i(mol), _d(charge), _i(mol_start)
+        self.n_atoms, self.n_mols = len(k), len(s) - 1
+        self.mol_start = s.copy()
+        self._ck(self.L.gomcb200_init_topology(self.h, len(k), len(s) - 1, pk, pm, pq, ps))
+
+    def set_box_molecules(self, box, mols):
+        m, pm = _i(mols)
+        self._ck(self.L.gomcb200_set_box_molecules(self.h, box, pm, len(m)))
+
+    def set_box_axes(self, box, axis):
+        a, pa = _d(axis)
+        self._ck(self.L.gomcb200_set_box_axes(self.h, box, pa))
+
+    def set_coords(self, x, y, z, first=0):
+        (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        self._ck(self.L.gomcb200_set_coords(self.h, px, py, pz, first, len(x)))
+
+    def get_coords(self, first=0, count=None):
+        count = self.n_atoms - first if count is None else count
+        out = [np.zeros(count) for _ in range(3)]
+        self._ck(self.L.gomcb200_get_coords(self.h, *[o.ctypes.data_as(_dp) for o in out],
+                                            first, count))
+        return out
+
+    def set_com(self, x, y, z, first=0):
+        (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        self._ck(self.L.gomcb200_set_com(self.h, px, py, pz, first, len(x)))
+
+    def set_molecule_coords(self, mol_index, x, y, z, com=None):
+        (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        pc = None
+        if com is not None:
+            com, pc = _d(com)
+        self._ck(self.L.gomcb200_set_molecule_coords(self.h, mol_index, px, py, pz, pc))
+
+    # ---- pair path -------------------------------------------------------
+    def box_inter(self, box=0):
+        lj, re = C.c_double(), C.c_double()
+        self._ck(self.L.gomcb200_box_inter(self.h, box, C.byref(lj), C.byref(re)))
+        return lj.value, re.value
+
+    def box_force(self, box=0):
+        lj, re = C.c_double(), C.c_double()
+        self._ck(self.L.gomcb200_box_force(self.h, box, C.byref(lj), C.byref(re)))
+        return lj.value, re.value
+
+    def molecule_inter(self, box, mol_index, nx, ny, nz):
+        (nx, px), (ny, py), (nz, pz) = _d(nx), _d(ny), _d(nz)
+        lj, re, ov = C.c_double(), C.c_double(), C.c_int()
+        self._ck(self.L.gomcb200_molecule_inter(self.h, box, mol_index, px, py, pz,
+                                                C.byref(lj), C.byref(re), C.byref(ov)))
+        return lj.value, re.value, bool(ov.value)
+
+    def particle_inter(self, box, mol_index, part_index, tx, ty, tz):
+        (tx, px), (ty, py), (tz, pz) = _d(tx), _d(ty), _d(tz)
+        t = len(tx)
+        en, re, ov = np.zeros(t), np.zeros(t), np.zeros(t, np.int32)
+        self._ck(self.L.gomcb200_particle_inter(self.h, box, mol_index, part_index, t, px, py,
+                                                pz, en.ctypes.data_as(_dp),
+                                                re.ctypes.data_as(_dp), ov.ctypes.data_as(_ip)))
+        return en, re, ov.astype(bool)
+
+    def calculate_torque(self, box=0):
+        self._ck(self.L.gomcb200_calculate_torque(self.h, box))
+
+    def get_forces(self, which, first=0, count=None):
+        limit = self.n_atoms if which in (ATOM_FORCE, ATOM_FORCE_REC) else self.n_mols
+        count = limit - first if count is None else count
+        out = [np.zeros(count) for _ in range(3)]
+        self._ck(self.L.gomcb200_get_forces(self.h, which, *[o.ctypes.data_as(_dp) for o in out],
+                                            first, count))
+        return out
+
+    # ---- reciprocal path -------------------------------------------------
+    def init_ewald(self, image_total, recip_rcut):
+        r, pr = _d(np.atleast_1d(recip_rcut))
+        self._ck(self.L.gomcb200_init_ewald(self.h, int(image_total), pr))
+
+    def recip_init(self, box, axis):
+        a, pa = _d(axis)
+        n, kmax = C.c_int(), C.c_int()
+        self._ck(self.L.gomcb200_recip_init(self.h, box, pa, C.byref(n), C.byref(kmax)))
+        return n.value, kmax.value
+
+    def recip_count(self, box, axis, excess=1.0):
+        a, pa = _d(axis)
+        n = C.c_int()
+        self._ck(self.L.gomcb200_recip_count(self.h, box, pa, float(excess), C.byref(n)))
+        return n.value
+
+    def get_kvectors(self, box, which, n):
+        out = [np.zeros(n) for _ in range(5)]
+        self._ck(self.L.gomcb200_get_kvectors(self.h, box, which,
+                                              *[o.ctypes.data_as(_dp) for o in out], n))
+        return out  # kx, ky, kz, hsqr, prefact
+
+    def box_reciprocal_setup(self, box=0):
+        e = C.c_double()
+        self._ck(self.L.gomcb200_box_reciprocal_setup(self.h, box, C.byref(e)))
+        return e.value
+
+    def box_reciprocal_sums(self, box=0):
+        e = C.c_double()
+        self._ck(self.L.gomcb200_box_reciprocal_sums(self.h, box, C.byref(e)))
+        return e.value
+
+    def box_reciprocal(self, box=0, is_new_volume=False):
+        e = C.c_double()
+        self._ck(self.L.gomcb200_box_reciprocal(self.h, box, int(is_new_volume), C.byref(e)))
+        return e.value
+
+    def mol_reciprocal(self, box, mol_index, nx, ny, nz):
+        (nx, px), (ny, py), (nz, pz) = _d(nx), _d(ny), _d(nz)
+        e = C.c_double()
+        self._ck(self.L.gomcb200_mol_reciprocal(self.h, box, mol_index, px, py, pz, C.byref(e)))
+        return e.value
+
+    def swap_reciprocal(self, box, mol_index, x, y, z, insert):
+        (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        e = C.c_double()
+        self._ck(self.L.gomcb200_swap_reciprocal(self.h, box, mol_index, px, py, pz,
+                                                 int(insert), C.byref(e)))
+        return e.value
+
+    def box_force_reciprocal(self, box=0):
+        self._ck(self.L.gomcb200_box_force_reciprocal(self.h, box))
+
+    def get_recip_sums(self, box, which, n):
+        r, i = np.zeros(n), np.zeros(n)
+        self._ck(self.L.gomcb200_get_recip_sums(self.h, box, which, r.ctypes.data_as(_dp),
+                                                i.ctypes.data_as(_dp), n))
+        return r, i
+
+    def set_recip_ref(self, box=0):
+        self._ck(self.L.gomcb200_set_recip_ref(self.h, box))
+
+    def copy_recip(self, box=0):
+        self._ck(self.L.gomcb200_copy_recip(self.h, box))
+
+    def update_recip(self, box=0):
+        self._ck(self.L.gomcb200_update_recip(self.h, box))
+
+    def update_recip_vec(self, box=0):
+        self._ck(self.L.gomcb200_update_recip_vec(self.h, box))
+
+    def box_self_correction(self, box=0):
+        s, c = C.c_double(), C.c_double()
+        self._ck(self.L.gomcb200_box_self_correction(self.h, box, C.byref(s), C.byref(c)))
+        return s.value, c.value
+
+    # ---- host-buffer drop-ins -------------------------------------------
+    def call_box_inter(self, box, x, y, z, axis):
+        (x, px), (y, py), (z, pz), (a, pa) = _d(x), _d(y), _d(z), _d(axis)
+        lj, re = C.c_double(), C.c_double()
+        self._ck(self.L.gomcb200_call_box_inter(self.h, box, px, py, pz, pa, C.byref(re),
+                                                C.byref(lj)))
+        return lj.value, re.value
+
+    def call_full_box_energy(self, box=0, x=None, y=None, z=None):
+        """E1: BoxInter + BoxReciprocalSums + BoxReciprocal.  x/y/z host arrays
+        (uploaded inside the call) or None to use the resident coordinates."""
+        if x is None:
+            px = py = pz = None
+        else:
+            (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        lj, re, rc = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.gomcb200_call_full_box_energy(self.h, box, px, py, pz, C.byref(lj),
+                                                      C.byref(re), C.byref(rc)))
+        return lj.value, re.value, rc.value
+
+    def call_full_box_energy_ptr(self, box, px, py, pz, out):
+        """Same with pre-extracted pointers (bench inner loop)."""
+        return self.L.gomcb200_call_full_box_energy(self.h, box, px, py, pz, out[0], out[1],
+                                                    out[2])
+
+    # ---- misc --------------------------------------------------------------
+    def set_recip_algo(self, algo):
+        self._ck(self.L.gomcb200_set_recip_algo(self.h, int(algo)))
+
+    def enable_timing(self, on=True):
+        self._ck(self.L.gomcb200_enable_timing(self.h, int(on)))
+
+    def last_timing(self):
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.L.gomcb200_last_timing(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def launch_count(self):
+        return int(self.L.gomcb200_launch_count(self.h))
+
+    # ---- convenience: bring up an engine for a synth.System ----------------
+    @classmethod
+    def from_system(cls, s, device=-1, recip=True):
+        ff = s.ff
+        sig, eps, nn = ff.tables()
+        e = cls(1, device)
+        e.init_forcefield(sig, eps, nn, ff.vdw_kind, len(ff.type_names), ff.r_cut,
+                          [ff.r_cut_coulomb], ff.r_cut_low, ff.r_switch, [ff.alpha],
+                          ff.ewald, ff.electrostatic)
+        e.init_topology(s.kind, s.mol, s.charge, s.mol_start)
+        e.set_box_molecules(0, np.arange(s.n_mols, dtype=np.int32))
+        e.set_box_axes(0, s.axis)
+        e.set_coords(s.x, s.y, s.z)
+        e.set_com(*s.com())
+        if recip and ff.ewald and ff.electrostatic:
+            n = e.setup_ewald(s.axis, [ff.recip_rcut])
+            e.nk = n
+        else:
+            e.nk = 0
+        return e
+
+    def setup_ewald(self, axis, recip_rcut, excess=1.0):
+        """Ewald::Init sequence (src/Ewald.cpp:100-139): AllocMem, RecipInit,
+        BoxReciprocalSetup, SetRecipRef."""
+        self.init_ewald(0, recip_rcut)
+        total = self.recip_count(0, axis, excess)
+        self.init_ewald(total, recip_rcut)
+        n, _ = self.recip_init(0, axis)
+        self.box_reciprocal_setup(0)
+        self.set_recip_ref(0)
+        return n

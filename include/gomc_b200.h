@@ -1,0 +1,252 @@
+/*
+ * gomc_b200.h -- C ABI of the B200-native GOMC energy/force engine.
+ *
+ * GOMC has no plugin API: its GPU seam is the set of free C++ functions
+ * Call*GPU(VariablesCUDA*, ...) declared in src/GPU/*.cuh and called from the
+ * `#ifdef GOMC_CUDA` blocks of CalculateEnergy.cpp / Ewald.cpp (SURVEY.md
+ * section 8b).  This header is the flattened, C-linkage replacement of that seam:
+ * plain pointers and sizes only.  Every entry point names the reference
+ * declaration it replaces.  INTEGRATION.md shows the glue a GOMC maintainer
+ * adds under `#ifdef GOMC_CUDA`.
+ *
+ * Differences from the reference seam, all deliberate:
+ *  - STATEFUL: topology, charges, kinds, force-field tables, k-vectors and
+ *    the structure-factor sums live on the device; coordinates are uploaded
+ *    with gomcb200_set_coords / gomcb200_set_molecule_coords and stay
+ *    resident.  The gomcb200_call_* entry points keep the reference's
+ *    "host buffers in, scalars out" convention for a literal drop-in.
+ *  - The engine bins atoms into cells on the device; the host CSR cell list
+ *    of the reference (cellVector / cellStartIndex / neighborList arguments
+ *    of CallBoxInterGPU) is not needed.  Box membership is given once per
+ *    change with gomcb200_set_box_molecules.
+ *  - All reductions are fixed-order: two calls on the same state return
+ *    bit-identical results (the reference uses atomicAdd).
+ *  - Errors: every function returns 0 on success or a negative GOMCB200_E*
+ *    code; gomcb200_last_error() returns the message.  (The reference prints
+ *    and exit()s, src/GPU/VariablesCUDA.cuh:20-39; the C++ host mirror in
+ *    gomc_b200/host keeps that behaviour.)  There is no CPU fallback: with no
+ *    usable CUDA device gomcb200_create fails.
+ *
+ * Arithmetic is IEEE double throughout; lambda == 1 (no fractional molecule).
+ * Orthogonal boxes only in this revision (gomcb200_set_box_axes).
+ * Threading: one host thread per engine, like the reference.
+ */
+#ifndef GOMC_B200_H
+#define GOMC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gomcb200_engine gomcb200_engine;
+
+enum {
+  GOMCB200_OK = 0,
+  GOMCB200_EINVAL = -1,  /* bad argument / call order */
+  GOMCB200_ECUDA = -2,   /* CUDA runtime error (message has the details) */
+  GOMCB200_ENODEV = -3,  /* no usable sm_100 device */
+  GOMCB200_ENOMEM = -4,
+  GOMCB200_EKMAX = -5    /* more k-vectors than imageTotal
+                            (src/Ewald.cpp:898-902 "Kmax exceeded") */
+};
+
+/* src/GPU/ConstantDefinitionsCUDAKernel.cuh:18-20 */
+enum { GOMCB200_VDW_STD = 0, GOMCB200_VDW_SHIFT = 1, GOMCB200_VDW_SWITCH = 2 };
+
+/* which force / k-vector buffer */
+enum {
+  GOMCB200_ATOM_FORCE = 0,     /* System::atomForceRef    */
+  GOMCB200_MOL_FORCE = 1,      /* System::molForceRef     */
+  GOMCB200_ATOM_FORCE_REC = 2, /* System::atomForceRecRef */
+  GOMCB200_MOL_FORCE_REC = 3,  /* System::molForceRecRef  */
+  GOMCB200_MOL_TORQUE = 4      /* MultiParticle molTorque */
+};
+enum { GOMCB200_K_NEW = 0, GOMCB200_K_REF = 1 };       /* kx[]  vs kxRef[]   */
+enum { GOMCB200_SUM_NEW = 0, GOMCB200_SUM_REF = 1 };   /* sumRnew vs sumRref */
+
+const char *gomcb200_last_error(void);
+int gomcb200_version(void);
+
+/* ---- lifecycle --------------------------------------------------------- */
+/* Replaces `new VariablesCUDA()` (src/FFParticle.cpp:56) and the device pick
+ * in src/Main.cpp:286-327.  device < 0 -> current device.  nBoxes = BOX_TOTAL
+ * (1 or 2). */
+int gomcb200_create(gomcb200_engine **out, int device, int nBoxes);
+/* DestroyCUDAVars / DestroyEwaldCUDAVars,
+ * src/GPU/ConstantDefinitionsCUDAKernel.cuh:43-46 */
+int gomcb200_destroy(gomcb200_engine *e);
+/* Number of kernels this engine has launched so far (bench.py gpu_launches). */
+long long gomcb200_launch_count(const gomcb200_engine *e);
+
+/* InitGPUForceField, src/GPU/ConstantDefinitionsCUDAKernel.cuh:24-30.
+ * Tables are [count*count], index kind1 + kind2*count (src/FFParticle.h:111).
+ * rCutCoulomb / alpha are per box [nBoxes]. */
+int gomcb200_init_forcefield(gomcb200_engine *e, const double *sigmaSq,
+                             const double *epsilon_cn, const double *n,
+                             int vdwKind, int isMartini, int count,
+                             double rCut, const double *rCutCoulomb,
+                             double rCutLow, double rOn, const double *alpha,
+                             int ewald, int electrostatic,
+                             double diElectric_1);
+
+/* InitCoordinatesCUDA (ConstantDefinitionsCUDAKernel.cuh:31-32) plus the
+ * per-atom vectors CalculateEnergy::Init / Ewald::Init build
+ * (src/CalculateEnergy.cpp:60-81, src/Ewald.cpp:100-127).
+ * molStart has nMols+1 entries (src/Molecules.h:46-51). */
+int gomcb200_init_topology(gomcb200_engine *e, int nAtoms, int nMols,
+                           const int *particleKind, const int *particleMol,
+                           const double *particleCharge, const int *molStart);
+
+/* MoleculeLookup box list (molLookup.BoxBegin(box)..BoxEnd(box)); call again
+ * after an accepted molecule transfer. */
+int gomcb200_set_box_molecules(gomcb200_engine *e, int box,
+                               const int *molIndices, int nMolsInBox);
+
+/* UpdateCellBasisCUDA (ConstantDefinitionsCUDAKernel.cuh:38-39) for an
+ * orthogonal cell: axis = BoxDimensions::axis.Get(box). */
+int gomcb200_set_box_axes(gomcb200_engine *e, int box, const double axis[3]);
+
+/* Coordinates / centres of mass (System::coordinates, System::com), global
+ * atom / molecule indexing; [first, first+count). */
+int gomcb200_set_coords(gomcb200_engine *e, const double *x, const double *y,
+                        const double *z, int first, int count);
+int gomcb200_get_coords(gomcb200_engine *e, double *x, double *y, double *z,
+                        int first, int count);
+int gomcb200_set_com(gomcb200_engine *e, const double *x, const double *y,
+                     const double *z, int first, int count);
+/* Accepted single-molecule move: new coordinates + COM of one molecule
+ * (what Translate::Accept copies, src/moves/Translate.h:106-113). */
+int gomcb200_set_molecule_coords(gomcb200_engine *e, int molIndex,
+                                 const double *x, const double *y,
+                                 const double *z, const double com[3]);
+
+/* ---- pair path (CalculateEnergy) --------------------------------------- */
+/* CallBoxInterGPU, src/GPU/CalculateEnergyCUDAKernel.cuh:17-26 ==
+ * CalculateEnergy::BoxInter pair sums, src/CalculateEnergy.cpp:157-266. */
+int gomcb200_box_inter(gomcb200_engine *e, int box, double *LJEn,
+                       double *REn);
+/* CallBoxForceGPU, src/GPU/CalculateForceCUDAKernel.cuh:17-30 ==
+ * CalculateEnergy::BoxForce, src/CalculateEnergy.cpp:268-406.  Writes the
+ * resident ATOM_FORCE / MOL_FORCE buffers (reset for this box first, as
+ * ResetForce does); read them with gomcb200_get_forces. */
+int gomcb200_box_force(gomcb200_engine *e, int box, double *LJEn,
+                       double *REn);
+/* CalculateEnergy::MoleculeInter, src/CalculateEnergy.cpp:581-686 (host-only
+ * in the reference GPU build).  The molecule is excluded from its own
+ * neighbourhood, which is what CellList::RemoveMol achieves. */
+int gomcb200_molecule_inter(gomcb200_engine *e, int box, int molIndex,
+                            const double *newX, const double *newY,
+                            const double *newZ, double *dLJ, double *dReal,
+                            int *overlap);
+/* CalculateEnergy::ParticleInter, src/CalculateEnergy.cpp:727-785: en[] and
+ * real[] are incremented, overlap[] or-ed. */
+int gomcb200_particle_inter(gomcb200_engine *e, int box, int molIndex,
+                            int partIndex, int trials, const double *tx,
+                            const double *ty, const double *tz, double *en,
+                            double *real, int *overlap);
+/* CalculateEnergy::CalculateTorque, src/CalculateEnergy.cpp:1365-1406, from
+ * the resident ATOM_FORCE + ATOM_FORCE_REC buffers and COM. */
+int gomcb200_calculate_torque(gomcb200_engine *e, int box);
+int gomcb200_get_forces(gomcb200_engine *e, int which, double *x, double *y,
+                        double *z, int first, int count);
+
+/* ---- Ewald reciprocal path --------------------------------------------- */
+/* InitEwaldVariablesCUDA, ConstantDefinitionsCUDAKernel.cuh:33 (capacity of
+ * the per-box k arrays, Ewald::AllocMem src/Ewald.cpp:141-188).
+ * recip_rcut[nBoxes] = Forcefield::recip_rcut (src/Forcefield.cpp:82); it is
+ * passed explicitly so that the k-vector membership test is bit-identical to
+ * the host's. */
+int gomcb200_init_ewald(gomcb200_engine *e, int imageTotal,
+                        const double *recip_rcut);
+/* Ewald::RecipInit (RecipInitOrth, src/Ewald.cpp:847-903) for the given
+ * axes into the NEW k set (kx[box]...); returns imageSize[box] and kmax. */
+int gomcb200_recip_init(gomcb200_engine *e, int box, const double axis[3],
+                        int *imageSize, int *kmax);
+/* Ewald::RecipCountInit, src/Ewald.cpp:968-1018 (count only; excess = the
+ * ensemble head-room factor 1.0 / 1.25 / 1.5). */
+int gomcb200_recip_count(gomcb200_engine *e, int box, const double axis[3],
+                         double excess, int *imageSize);
+int gomcb200_get_kvectors(gomcb200_engine *e, int box, int which, double *kx,
+                          double *ky, double *kz, double *hsqr,
+                          double *prefact, int n);
+/* CallBoxReciprocalSetupGPU (CalculateEwaldCUDAKernel.cuh:27-33) ==
+ * Ewald::BoxReciprocalSetup, src/Ewald.cpp:193-274: NEW k set. */
+int gomcb200_box_reciprocal_setup(gomcb200_engine *e, int box,
+                                  double *energyRecip);
+/* CallBoxReciprocalSumsGPU (CalculateEwaldCUDAKernel.cuh:35-38) ==
+ * Ewald::BoxReciprocalSums, src/Ewald.cpp:281-361: REF k set. */
+int gomcb200_box_reciprocal_sums(gomcb200_engine *e, int box,
+                                 double *energyRecip);
+/* Ewald::BoxReciprocal, src/Ewald.cpp:375-406. */
+int gomcb200_box_reciprocal(gomcb200_engine *e, int box, int isNewVolume,
+                            double *energyRecip);
+/* CallMolReciprocalGPU (CalculateEwaldCUDAKernel.cuh:40-44) ==
+ * Ewald::MolReciprocal, src/Ewald.cpp:409-473; old coordinates are the
+ * resident ones.  Returns E_new (caller subtracts sysPotRef recip). */
+int gomcb200_mol_reciprocal(gomcb200_engine *e, int box, int molIndex,
+                            const double *newX, const double *newY,
+                            const double *newZ, double *energyRecipNew);
+/* CallSwapReciprocalGPU (CalculateEwaldCUDAKernel.cuh:54-57) ==
+ * Ewald::SwapDestRecip (insert=1, src/Ewald.cpp:478-531) /
+ * SwapSourceRecip (insert=0, :657-710).  Charges are those of molIndex. */
+int gomcb200_swap_reciprocal(gomcb200_engine *e, int box, int molIndex,
+                             const double *x, const double *y,
+                             const double *z, int insert,
+                             double *energyRecipNew);
+/* CallBoxForceReciprocalGPU (CalculateEwaldCUDAKernel.cuh:16-25) ==
+ * Ewald::BoxForceReciprocal, src/Ewald.cpp:1496-1596 incl. the
+ * intramolecular correction force; writes ATOM_FORCE_REC / MOL_FORCE_REC. */
+int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box);
+/* Lazy D2H of the structure-factor sums for host-only reference callers
+ * (MolExchangeReciprocal src/Ewald.cpp:794-806, ChangeRecip :626-630). */
+int gomcb200_get_recip_sums(gomcb200_engine *e, int box, int which,
+                            double *sumR, double *sumI, int n);
+/* state machine, src/Ewald.cpp:1021-1053, :1420-1487 */
+int gomcb200_set_recip_ref(gomcb200_engine *e, int box);    /* SetRecipRef / CopyCurrentToRefCUDA */
+int gomcb200_copy_recip(gomcb200_engine *e, int box);       /* CopyRecip / CopyRefToNewCUDA       */
+int gomcb200_update_recip(gomcb200_engine *e, int box);     /* UpdateRecip / UpdateRecipCUDA      */
+int gomcb200_update_recip_vec(gomcb200_engine *e, int box); /* UpdateRecipVec / UpdateRecipVecCUDA */
+/* Ewald::BoxSelf (src/Ewald.cpp:1125-1163) and the box sum of
+ * Ewald::MolCorrection (src/Ewald.cpp:1056-1085). */
+int gomcb200_box_self_correction(gomcb200_engine *e, int box, double *self,
+                                 double *correction);
+
+/* ---- literal drop-ins: host buffers in, scalars out -------------------- */
+/* CallBoxInterGPU with the reference's argument meaning: x/y/z are the full
+ * System::coordinates arrays (nAtoms each), axis the current box axes. */
+int gomcb200_call_box_inter(gomcb200_engine *e, int box, const double *x,
+                            const double *y, const double *z,
+                            const double axis[3], double *REn, double *LJEn);
+/* CallBoxReciprocalSumsGPU + BoxReciprocal */
+int gomcb200_call_box_reciprocal_sums(gomcb200_engine *e, int box,
+                                      const double *x, const double *y,
+                                      const double *z, double *energyRecip);
+/* CallBoxForceGPU: also downloads atom and molecule forces (may be NULL). */
+int gomcb200_call_box_force(gomcb200_engine *e, int box, const double *x,
+                            const double *y, const double *z,
+                            const double axis[3], double *REn, double *LJEn,
+                            double *aForcex, double *aForcey, double *aForcez,
+                            double *mForcex, double *mForcey,
+                            double *mForcez);
+/* One full-box evaluation = BoxInter + BoxReciprocalSums + BoxReciprocal
+ * (the E1 metric of SURVEY.md section 8d) with host coordinates in. */
+int gomcb200_call_full_box_energy(gomcb200_engine *e, int box,
+                                  const double *x, const double *y,
+                                  const double *z, double *LJEn, double *REn,
+                                  double *energyRecip);
+
+/* ---- tuning / introspection (tests and bench only) ---------------------- */
+/* algorithm for the structure-factor build: 0 = direct sincos per (atom,k)
+ * (reference algorithm), 1 = factorised per-axis phases (default). */
+int gomcb200_set_recip_algo(gomcb200_engine *e, int algo);
+/* CUDA-event time (ms) of the kernels launched by the last call, and the
+ * device time of its dominant kernel. */
+int gomcb200_last_timing(const gomcb200_engine *e, float *totalMs,
+                         float *dominantMs);
+/* enable/disable per-call event timing (off by default) */
+int gomcb200_enable_timing(gomcb200_engine *e, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOMC_B200_H */

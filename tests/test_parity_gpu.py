@@ -1,0 +1,216 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle
+on the same seeded inputs.  Tolerance: relative 1e-9 (BASELINE.json north_star),
+written as TOL below; integer/flag outputs must match exactly."""
+import numpy as np
+import pytest
+
+from gomc_b200 import synth
+from gomc_b200 import engine as eng
+from tests.helpers import (SMALL_SYSTEMS, box_atoms, box_mols, oracle_for, random_move,
+                           rel_err)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+NAMES = [k for k, v in SMALL_SYSTEMS.items() if v is not None]
+
+
+@pytest.fixture(scope="module", params=NAMES)
+def case(request):
+    s = SMALL_SYSTEMS[request.param]()
+    e = eng.Engine.from_system(s)
+    o = oracle_for(s)
+    yield s, e, o
+    e.close()
+
+
+def test_box_inter(case):
+    s, e, o = case
+    lj, re = e.box_inter(0)
+    olj, ore = o.box_inter(s.x, s.y, s.z, s.kind, s.mol, s.charge, box_atoms(s))
+    assert abs(lj - olj) <= TOL * abs(olj)
+    assert abs(re - ore) <= TOL * max(abs(ore), 1e-300)
+    # determinism: two calls, identical bits
+    assert e.box_inter(0) == (lj, re)
+
+
+def test_box_force(case):
+    s, e, o = case
+    lj, re = e.box_force(0)
+    olj, ore, aF, mF = o.box_force(s.x, s.y, s.z, s.kind, s.mol, s.charge, box_atoms(s),
+                                   s.n_mols)
+    assert abs(lj - olj) <= TOL * abs(olj)
+    assert abs(re - ore) <= TOL * max(abs(ore), 1e-300)
+    gF = e.get_forces(eng.ATOM_FORCE)
+    gM = e.get_forces(eng.MOL_FORCE)
+    for c in range(3):
+        assert rel_err(gF[c], aF[c]) <= TOL
+        assert rel_err(gM[c], mF[c]) <= TOL
+    # Newton's third law: total force vanishes (to rounding of the sum)
+    tot = max(abs(float(np.sum(gF[c]))) for c in range(3))
+    assert tot <= 1e-9 * max(float(np.max(np.abs(gF[0]))), 1.0) * s.n_atoms ** 0.5
+
+
+def test_molecule_inter(case):
+    s, e, o = case
+    rng = np.random.default_rng(11)
+    for t in range(6):
+        m = int(rng.integers(s.n_mols))
+        amp = 0.4 if t % 2 == 0 else 0.45 * float(min(s.axis))
+        nx, ny, nz = random_move(s, rng, m, amp)
+        if t == 5:  # forced overlap: land on another molecule's first atom
+            other = (m + 1) % s.n_mols
+            a0 = s.mol_start[other]
+            sl = slice(s.mol_start[m], s.mol_start[m + 1])
+            nx = np.mod(s.x[sl] - s.x[sl][0] + s.x[a0] + 0.3, s.axis[0])
+            ny = np.mod(s.y[sl] - s.y[sl][0] + s.y[a0] + 0.2, s.axis[1])
+            nz = np.mod(s.z[sl] - s.z[sl][0] + s.z[a0] + 0.1, s.axis[2])
+        lj, re, ov = e.molecule_inter(0, m, nx, ny, nz)
+        ba = box_atoms(s)
+        ba = ba[(ba < s.mol_start[m]) | (ba >= s.mol_start[m + 1])]
+        olj, ore, oov = o.molecule_inter(s.x, s.y, s.z, s.kind, s.mol, s.charge, ba, m,
+                                         s.mol_start[m], s.mol_start[m + 1] - s.mol_start[m],
+                                         nx, ny, nz)
+        assert ov == oov
+        assert abs(lj - olj) <= TOL * max(abs(olj), 1.0)
+        assert abs(re - ore) <= TOL * max(abs(ore), 1.0)
+    assert ov  # the forced-overlap move must have been flagged
+
+
+def test_particle_inter(case):
+    s, e, o = case
+    rng = np.random.default_rng(5)
+    m = int(rng.integers(s.n_mols))
+    trials = 7
+    tx, ty, tz = (rng.uniform(0, s.axis[d], trials) for d in range(3))
+    en, re, ov = e.particle_inter(0, m, 0, tx, ty, tz)
+    ba = box_atoms(s)
+    ba = ba[(ba < s.mol_start[m]) | (ba >= s.mol_start[m + 1])]
+    a0 = s.mol_start[m]
+    oen, ore, oov = o.particle_inter(s.x, s.y, s.z, s.kind, s.mol, s.charge, ba, m,
+                                     s.kind[a0], s.charge[a0], tx, ty, tz)
+    assert np.array_equal(ov, oov)
+    assert rel_err(en, oen) <= TOL
+    if np.any(ore != 0):
+        assert rel_err(re, ore) <= TOL
+
+
+def _ewald(s):
+    return s.ff.ewald and s.ff.electrostatic
+
+
+def test_kvectors_bit_exact(case):
+    s, e, o = case
+    if not _ewald(s):
+        pytest.skip("no Ewald")
+    kx, ky, kz, hs, pf, kmax = o.recip_init_orth()
+    assert e.nk == len(kx)
+    g = e.get_kvectors(0, eng.K_REF, e.nk)
+    for a, b in zip(g, (kx, ky, kz, hs, pf)):
+        assert np.array_equal(a, b)          # index-compatible with the host list
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_box_reciprocal_sums(case, algo):
+    s, e, o = case
+    if not _ewald(s):
+        pytest.skip("no Ewald")
+    kx, ky, kz, hs, pf, kmax = o.recip_init_orth()
+    sR, sI = o.box_recip_sums(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge, kx, ky, kz)
+    eo = o.box_reciprocal(sR, sI, pf)
+    e.set_recip_algo(algo)
+    en = e.box_reciprocal_sums(0)
+    gR, gI = e.get_recip_sums(0, eng.SUM_NEW, e.nk)
+    e.set_recip_algo(1)
+    scale = max(np.max(np.abs(sR)), np.max(np.abs(sI)))
+    assert np.max(np.abs(gR - sR)) <= TOL * scale
+    assert np.max(np.abs(gI - sI)) <= TOL * scale
+    assert abs(en - eo) <= TOL * abs(eo)
+    assert abs(e.box_reciprocal(0, False) - eo) <= TOL * abs(eo)
+
+
+def test_mol_and_swap_reciprocal(case):
+    s, e, o = case
+    if not _ewald(s):
+        pytest.skip("no Ewald")
+    kx, ky, kz, hs, pf, kmax = o.recip_init_orth()
+    sR, sI = o.box_recip_sums(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge, kx, ky, kz)
+    rng = np.random.default_rng(3)
+    for t in range(3):
+        m = int(rng.integers(s.n_mols))
+        sl = slice(s.mol_start[m], s.mol_start[m + 1])
+        nx, ny, nz = random_move(s, rng, m, 1.5)
+        en = e.mol_reciprocal(0, m, nx, ny, nz)
+        oe, oR, oI = o.mol_reciprocal(s.charge[sl], (s.x[sl], s.y[sl], s.z[sl]), (nx, ny, nz),
+                                      kx, ky, kz, pf, sR, sI)
+        assert abs(en - oe) <= TOL * abs(oe)
+        gR, gI = e.get_recip_sums(0, eng.SUM_NEW, e.nk)
+        assert rel_err(gR, oR) <= TOL and rel_err(gI, oI) <= TOL
+        for insert in (1, 0):
+            en = e.swap_reciprocal(0, m, nx, ny, nz, insert)
+            oe, oR, oI = o.swap_recip(insert, s.charge[sl], (nx, ny, nz), kx, ky, kz, pf, sR, sI)
+            assert abs(en - oe) <= TOL * abs(oe)
+    # the reference sums must be untouched by trial moves (state machine rule 1)
+    rR, rI = e.get_recip_sums(0, eng.SUM_REF, e.nk)
+    assert rel_err(rR, sR) <= TOL and rel_err(rI, sI) <= TOL
+
+
+def test_force_reciprocal_and_torque(case):
+    s, e, o = case
+    if not _ewald(s):
+        pytest.skip("no Ewald")
+    kx, ky, kz, hs, pf, kmax = o.recip_init_orth()
+    sR, sI = o.box_recip_sums(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge, kx, ky, kz)
+    e.copy_recip(0)
+    e.box_force(0)
+    e.box_force_reciprocal(0)
+    e.calculate_torque(0)
+    rF, mR = o.box_force_reciprocal(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge, kx, ky,
+                                    kz, pf, sR, sI, s.n_mols)
+    _, _, aF, _ = o.box_force(s.x, s.y, s.z, s.kind, s.mol, s.charge, box_atoms(s), s.n_mols)
+    tq = o.calculate_torque(box_mols(s), s.mol_start, s.x, s.y, s.z, s.com(), aF, rF, s.n_mols)
+    gR = e.get_forces(eng.ATOM_FORCE_REC)
+    gM = e.get_forces(eng.MOL_FORCE_REC)
+    gT = e.get_forces(eng.MOL_TORQUE)
+    for c in range(3):
+        assert rel_err(gR[c], rF[c]) <= TOL
+        assert rel_err(gM[c], mR[c]) <= TOL
+        assert rel_err(gT[c], tq[c]) <= TOL
+
+
+def test_self_correction(case):
+    s, e, o = case
+    if not _ewald(s):
+        pytest.skip("no Ewald")
+    sf, co = e.box_self_correction(0)
+    osf = o.box_self(box_mols(s), s.mol_start, s.charge)
+    oco = o.box_correction(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge)
+    assert abs(sf - osf) <= TOL * abs(osf)
+    assert abs(co - oco) <= TOL * max(abs(oco), 1e-300)
+
+
+def test_accept_state_machine(case):
+    """Accepted move: set_molecule_coords + UpdateRecip must leave the engine in
+    the state a full recomputation gives (SURVEY.md section 8b contract)."""
+    s, e, o = case
+    if not _ewald(s):
+        pytest.skip("no Ewald")
+    rng = np.random.default_rng(21)
+    m = int(rng.integers(s.n_mols))
+    sl = slice(s.mol_start[m], s.mol_start[m + 1])
+    nx, ny, nz = random_move(s, rng, m, 0.8)
+    e_new = e.mol_reciprocal(0, m, nx, ny, nz)
+    old = (s.x[sl].copy(), s.y[sl].copy(), s.z[sl].copy())
+    e.set_molecule_coords(m, nx, ny, nz)
+    e.update_recip(0)
+    full = e.box_reciprocal_sums(0)        # recompute from scratch into "new"
+    assert abs(full - e_new) <= 1e-9 * abs(full)
+    x2, y2, z2 = s.x.copy(), s.y.copy(), s.z.copy()
+    x2[sl], y2[sl], z2[sl] = nx, ny, nz
+    olj, ore = o.box_inter(x2, y2, z2, s.kind, s.mol, s.charge, box_atoms(s))
+    lj, re = e.box_inter(0)
+    assert abs(lj - olj) <= TOL * abs(olj) and abs(re - ore) <= TOL * abs(ore)
+    # undo for the other tests of this module
+    e.set_molecule_coords(m, *old)
+    e.box_reciprocal_sums(0)
+    e.update_recip(0)
