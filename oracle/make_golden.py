@@ -1,0 +1,60 @@
+"""TEST INFRASTRUCTURE: regenerates tests/golden/*.npz by running the UNMODIFIED
+reference (oracle/_ref/gomc_probe_NVT, built by oracle/ref_build.mk from
+/root/reference) on small synthetic systems written by gomc_b200.synth.
+
+Run in the build container only (needs /root/reference):
+    python oracle/make_golden.py
+The probe runs with OMP_NUM_THREADS=1 so the reference's summation order is
+deterministic.  Each .npz holds the inputs as the reference parsed them
+(coordinates, kinds, charges, tables, k-vectors) and the outputs of every
+hot-path function.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gomc_b200 import synth  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+CASES = {
+    # name: (system factory, nMoves, seed)
+    "spce100_rc7": (lambda: synth.make_spce(100, r_cut=7.0), 6, 7),
+    "spce343_rc8": (lambda: synth.make_spce(343, r_cut=8.0, r_cut_coulomb=8.0), 6, 11),
+    "argon256": (lambda: synth.make_argon(256, r_cut=7.0), 4, 3),
+    "mixture_std": (lambda: synth.make_mixture(), 6, 5),
+    "mixture_shift": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SHIFT), 4, 5),
+    "mixture_switch": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.5), 4, 5),
+    "mixture_n13": (lambda: synth.make_mixture(n_b_exp=13.0, seed=9), 4, 5),
+}
+
+
+def main():
+    probe = os.path.join(ROOT, "oracle", "_ref", "gomc_probe_NVT")
+    if not os.path.exists(probe):
+        subprocess.check_call(["make", "-s", "-f", "oracle/ref_build.mk", "ENS_LIST=NVT", "-j8"],
+                              cwd=ROOT)
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for name, (make, n_moves, seed) in CASES.items():
+        s = make()
+        with tempfile.TemporaryDirectory() as d:
+            synth.write_gomc_inputs(s, d)
+            log = subprocess.run([probe, "golden", "in.conf", "dump.bin", str(n_moves), str(seed)],
+                                 cwd=d, env=env, capture_output=True, text=True)
+            if log.returncode != 0:
+                print(log.stdout[-3000:], log.stderr[-2000:])
+                raise SystemExit(f"probe failed on {name}")
+            dump = po.read_dump(os.path.join(d, "dump.bin"))
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **dump)
+        print(f"{name}: {s.n_atoms} atoms, {len(dump)} arrays, "
+              f"nk={int(dump['box0.nk'][0]) if 'box0.nk' in dump else 0}")
+
+
+if __name__ == "__main__":
+    main()

@@ -41,5 +41,4 @@ SMALL_SYSTEMS = {
     "mixture_std": lambda: synth.make_mixture(),
     "mixture_shift": lambda: synth.make_mixture(vdw_kind=synth.VDW_SHIFT),
     "mixture_switch": lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.5),
-    "mixture_noewald": None,
 }

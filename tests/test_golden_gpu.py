@@ -1,0 +1,116 @@
+"""GPU parity against the reference ITSELF: the CUDA engine (through the C ABI)
+versus tests/golden/*.npz, i.e. outputs of the unmodified GOMC CPU build on the
+same inputs.  Tolerance 1e-9 relative (north_star); flags exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from gomc_b200 import engine as eng
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _xyz(d, key):
+    return [d[f"{key}.{c}"] for c in "xyz"]
+
+
+@pytest.fixture(scope="module", params=GOLDEN, ids=[os.path.basename(g)[:-4] for g in GOLDEN])
+def gold(request):
+    d = dict(np.load(request.param))
+    e = eng.Engine(1)
+    e.init_forcefield(d["ff.sigmaSq"], d["ff.epsilon_cn"], d["ff.n"], int(d["ff.vdwKind"][0]),
+                      int(d["ff.kindCount"][0]), float(d["ff.rCut"][0]), d["ff.rCutCoulomb"][:1],
+                      float(d["ff.rCutLow"][0]), float(d["ff.rswitch"][0]), d["ff.alpha"][:1],
+                      int(d["ff.ewald"][0]), int(d["ff.electrostatic"][0]))
+    e.init_topology(d["particleKind"], d["particleMol"], d["particleCharge"], d["molStart"])
+    e.set_box_molecules(0, d["box0.mols"])
+    e.set_box_axes(0, d["box0.axis"])
+    e.set_coords(*_xyz(d, "coords"))
+    e.set_com(*_xyz(d, "com"))
+    e.nk = 0
+    if d["ff.ewald"][0]:
+        e.nk = e.setup_ewald(d["box0.axis"], d["ff.recip_rcut"][:1])
+    yield d, e
+    e.close()
+
+
+def test_pair_energies_and_forces(gold):
+    d, e = gold
+    lj, re = e.box_inter(0)
+    assert abs(lj - d["box0.BoxInter.inter"][0]) <= TOL * abs(lj)
+    assert abs(re - d["box0.BoxInter.real"][0]) <= TOL * max(abs(re), 1e-300)
+    lj, re = e.box_force(0)
+    assert abs(lj - d["box0.BoxForce.inter"][0]) <= TOL * abs(lj)
+    gF, gM = e.get_forces(eng.ATOM_FORCE), e.get_forces(eng.MOL_FORCE)
+    for i, c in enumerate("xyz"):
+        assert rel_err(gF[i], d[f"box0.BoxForce.atomForce.{c}"]) <= TOL
+        assert rel_err(gM[i], d[f"box0.BoxForce.molForce.{c}"]) <= TOL
+
+
+def test_moves_and_trials(gold):
+    d, e = gold
+    st = d["box0.move.start"]
+    for t, m in enumerate(d["box0.move.mol"]):
+        nx, ny, nz = (d[f"box0.move.{c}"][st[t]:st[t + 1]] for c in "xyz")
+        lj, re, ov = e.molecule_inter(0, int(m), nx, ny, nz)
+        assert ov == bool(d["box0.move.overlap"][t])
+        assert abs(lj - d["box0.move.dLJ"][t]) <= TOL * max(abs(lj), 1.0)
+        assert abs(re - d["box0.move.dReal"][t]) <= TOL * max(abs(re), 1.0)
+        if d["ff.ewald"][0]:
+            en = e.mol_reciprocal(0, int(m), nx, ny, nz)
+            ref = d["box0.move.dRecip"][t] + d["box0.sysPotRef.recip"][0]
+            assert abs(en - ref) <= TOL * abs(ref)
+    m = int(d["box0.swap.mol"][0])
+    en, re, ov = e.particle_inter(0, m, 0, *_xyz(d, "box0.ParticleInter.trialPos"))
+    assert np.array_equal(ov.astype(np.int32), d["box0.ParticleInter.overlap"])
+    assert rel_err(en, d["box0.ParticleInter.en"]) <= TOL
+
+
+def test_reciprocal(gold):
+    d, e = gold
+    if not d["ff.ewald"][0]:
+        pytest.skip("no Ewald")
+    nk = int(d["box0.nk"][0])
+    assert e.nk == nk
+    for a, name in zip(e.get_kvectors(0, eng.K_REF, nk), ("kx", "ky", "kz", "hsqr", "prefact")):
+        assert np.array_equal(a, d["box0." + name]), name
+    for algo in (0, 1):
+        e.set_recip_algo(algo)
+        en = e.box_reciprocal_sums(0)
+        gR, gI = e.get_recip_sums(0, eng.SUM_NEW, nk)
+        scale = max(np.max(np.abs(d["box0.sumRref"])), np.max(np.abs(d["box0.sumIref"])))
+        assert np.max(np.abs(gR - d["box0.sumRref"])) <= TOL * scale
+        assert np.max(np.abs(gI - d["box0.sumIref"])) <= TOL * scale
+        assert abs(en - d["box0.BoxReciprocal"][0]) <= TOL * abs(en)
+    sf, co = e.box_self_correction(0)
+    assert abs(sf - d["box0.BoxSelf"][0]) <= TOL * abs(sf)
+    assert abs(co - d["box0.MolCorrection.sum"][0]) <= TOL * abs(co)
+    m = int(d["box0.swap.mol"][0])
+    ref = d["box0.sysPotRef.recip"][0]
+    en = e.swap_reciprocal(0, m, *_xyz(d, "box0.swap.newCoords"), 1)
+    assert abs(en - (d["box0.SwapDestRecip"][0] + ref)) <= TOL * abs(en)
+    ms = d["molStart"]
+    old = [a[ms[m]:ms[m + 1]] for a in _xyz(d, "coords")]
+    en = e.swap_reciprocal(0, m, *old, 0)
+    assert abs(en - (d["box0.SwapSourceRecip"][0] + ref)) <= TOL * abs(en)
+
+
+def test_reciprocal_force_and_torque(gold):
+    d, e = gold
+    if not d["ff.ewald"][0]:
+        pytest.skip("no Ewald")
+    e.copy_recip(0)
+    e.box_force(0)
+    e.box_force_reciprocal(0)
+    e.calculate_torque(0)
+    gR, gM, gT = (e.get_forces(w) for w in (eng.ATOM_FORCE_REC, eng.MOL_FORCE_REC,
+                                            eng.MOL_TORQUE))
+    for i, c in enumerate("xyz"):
+        assert rel_err(gR[i], d[f"box0.BoxForceReciprocal.atomForceRec.{c}"]) <= TOL
+        assert rel_err(gM[i], d[f"box0.BoxForceReciprocal.molForceRec.{c}"]) <= TOL
+        assert rel_err(gT[i], d[f"box0.CalculateTorque.molTorque.{c}"]) <= TOL

@@ -12,7 +12,7 @@ from tests.helpers import (SMALL_SYSTEMS, box_atoms, box_mols, oracle_for, rando
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
-NAMES = [k for k, v in SMALL_SYSTEMS.items() if v is not None]
+NAMES = list(SMALL_SYSTEMS)
 
 
 @pytest.fixture(scope="module", params=NAMES)

@@ -1,0 +1,46 @@
+"""CPU tests of the host logic: the synthetic-system generator derives the
+force-field tables and Ewald constants exactly as the reference does (pinned
+by the golden dumps, which hold what the reference itself derived from the
+files the generator wrote)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from gomc_b200 import synth
+from oracle.make_golden import CASES
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_generator_matches_what_reference_parsed(name):
+    d = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    s = CASES[name][0]()
+    assert s.n_atoms == d["nAtoms"][0] and s.n_mols == d["nMols"][0]
+    assert np.array_equal(s.mol_start, d["molStart"])
+    assert np.array_equal(s.mol, d["particleMol"])
+    assert np.array_equal(s.charge, d["particleCharge"])
+    assert np.array_equal(s.kind, d["particleKind"])
+    assert np.array_equal(s.axis, d["box0.axis"])
+    sig, eps, nn = s.ff.tables()
+    assert np.array_equal(sig, d["ff.sigmaSq"])          # FFParticle::Blend
+    assert np.array_equal(eps, d["ff.epsilon_cn"])
+    assert np.array_equal(nn, d["ff.n"])
+    assert s.ff.alpha == d["ff.alpha"][0]                 # Forcefield.cpp:80
+    assert s.ff.recip_rcut == d["ff.recip_rcut"][0]       # Forcefield.cpp:82
+    # the reference re-wraps whole molecules on load; atoms stay congruent mod L
+    for c, arr in zip("xyz", (s.x, s.y, s.z)):
+        diff = np.abs(d[f"coords.{c}"] - arr)
+        L = s.axis[0]
+        assert np.all((diff < 1e-9) | (np.abs(diff - L) < 1e-9))
+
+
+def test_sizes_of_baseline_configs():
+    """Problem sizes of BASELINE.md section 3 (computed, not allocated)."""
+    import math
+    for n_mol, kmax_expected in ((10000, 25), (33334, 37)):
+        L = round((n_mol / 0.0334) ** (1 / 3), 3)
+        recip_rcut = -2.0 * math.log(1e-5) / 10.0
+        assert int(recip_rcut * L / (2 * math.pi)) + 1 == kmax_expected
