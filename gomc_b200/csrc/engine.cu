@@ -123,6 +123,7 @@ struct gomcb200_engine {
   std::vector<BoxState> box;
   int imageTotal = 0;
   int recipAlgo = 1;
+  int shardRank = 0, shardWorld = 1;
   // scratch
   DevBuf<double> part, blockA, blockB, result, molBuf, probeOut;
   DevBuf<Probe> probes;
@@ -252,7 +253,7 @@ int fetch_result(gomcb200_engine *e, int n) {
 
 template <bool FORCE>
 void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int useSmem,
-                 int smemAtoms, size_t smemBytes, int grid) {
+                 int smemAtoms, size_t smemBytes, int grid, int cell0) {
   BoxState &bx = e->box[b];
   double *fx = e->force[GOMCB200_ATOM_FORCE][0].p;
   double *fy = e->force[GOMCB200_ATOM_FORCE][1].p;
@@ -262,7 +263,7 @@ void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int 
     cudaFuncSetAttribute(k_pair_box<V, FORCE>,                                      \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); \
     k_pair_box<V, FORCE><<<grid, kPairThreads, smemBytes, e->stream>>>(             \
-        p, bx.grid, slices, useSmem, smemAtoms, bx.cellStart.p, bx.sx.p, bx.sy.p,  \
+        p, bx.grid, slices, cell0, useSmem, smemAtoms, bx.cellStart.p, bx.sx.p, bx.sy.p,  \
         bx.sz.p, bx.sq.p, bx.skm.p, bx.sortedAtoms.p, e->blockA.p, e->blockB.p, fx, \
         fy, fz);                                                                    \
   } while (0)
@@ -285,7 +286,10 @@ int run_pair(gomcb200_engine *e, int b, bool force) {
   const int nCells = bx.grid.nCells;
   int slices = (4 * e->numSMs + nCells - 1) / nCells;
   slices = std::max(1, std::min(slices, 16));
-  int grid = nCells * slices;
+  // multi-GPU: this rank owns cells [cell0, cell1) (x-major slab)
+  const int cell0 = (int)(((long long)nCells * e->shardRank) / e->shardWorld);
+  const int cell1 = (int)(((long long)nCells * (e->shardRank + 1)) / e->shardWorld);
+  int grid = (cell1 - cell0) * slices;
   // shared-memory staging of the neighbour cells (40 B per atom)
   size_t staticSmem = 20 * 1024;
   size_t capAtoms = (e->smemOptin > staticSmem ? (e->smemOptin - staticSmem) : 0) / 40;
@@ -297,12 +301,16 @@ int run_pair(gomcb200_engine *e, int b, bool force) {
   size_t smemBytes = useSmem ? (size_t)smemAtoms * 40 : 0;
   CK(e->blockA.reserve(grid + 1024));
   CK(e->blockB.reserve(grid + 1024));
+  if (grid == 0) {
+    CK(cudaMemsetAsync(e->result.p, 0, 8 * sizeof(double), e->stream));
+    return 0;
+  }
   if (force) {
     // ResetForce (src/CalculateEnergy.cpp:1408-1428) is implicit: every atom
     // and molecule of the box is overwritten below.
-    launch_pair<true>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid);
+    launch_pair<true>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
   } else {
-    launch_pair<false>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid);
+    launch_pair<false>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
   }
   CK(cudaGetLastError());
   k_final_reduce<<<1, 1024, 0, e->stream>>>(grid, 2, e->blockA.p, e->blockB.p, nullptr,
@@ -502,7 +510,11 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     if (AT < 1)
       return fail(GOMCB200_EINVAL, "k range too large for the factorised kernel");
     fa.AT = AT;
-    nSlabs = std::max(1, (e->numSMs + ks.nTiles / 2) / ks.nTiles);
+    // multi-GPU: this rank owns tiles [tile0, tile1) (tiles have equal work)
+    const int tile0 = (int)(((long long)ks.nTiles * e->shardRank) / e->shardWorld);
+    const int tile1 = (int)(((long long)ks.nTiles * (e->shardRank + 1)) / e->shardWorld);
+    const int myTiles = std::max(1, tile1 - tile0);
+    nSlabs = std::max(1, (e->numSMs + myTiles / 2) / myTiles);
     nSlabs = std::min(nSlabs, std::max(1, nAt / (2 * AT)));
     int per = (nAt + nSlabs - 1) / nSlabs;
     per = ((per + AT - 1) / AT) * AT;
@@ -517,8 +529,14 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     size_t smem = perAtom * AT;
     CK(cudaFuncSetAttribute(k_recip_fact, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)smem));
-    dim3 grid(ks.nTiles, nSlabs);
-    k_recip_fact<<<grid, kFactThreads, smem, e->stream>>>(fa, bx.packed.p, e->part.p);
+    if (e->shardWorld > 1)
+      CK(cudaMemsetAsync(e->part.p, 0, sizeof(double) * (size_t)nSlabs * 2 * nkStride,
+                         e->stream));
+    fa.tile0 = tile0;
+    if (tile1 > tile0) {
+      dim3 grid(tile1 - tile0, nSlabs);
+      k_recip_fact<<<grid, kFactThreads, smem, e->stream>>>(fa, bx.packed.p, e->part.p);
+    }
     e->launches += 1;
   } else {
     nSlabs = std::max(1, std::min(64, (4 * e->numSMs + nBlocks - 1) / nBlocks));
@@ -1390,6 +1408,19 @@ int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
   if (LJEn) *LJEn = e->hRes[8];
   if (REn) *REn = e->hRes[9];
   if (energyRecip) *energyRecip = recip;
+  return 0;
+}
+
+int gomcb200_set_shard(gomcb200_engine *e, int rank, int world) {
+  if (!e || world < 1 || rank < 0 || rank >= world) return fail(GOMCB200_EINVAL, "bad arguments");
+  e->shardRank = rank;
+  e->shardWorld = world;
+  return 0;
+}
+
+int gomcb200_mark_coords_changed(gomcb200_engine *e) {
+  if (!e) return fail(GOMCB200_EINVAL, "null engine");
+  mark_coords_dirty(e);
   return 0;
 }
 

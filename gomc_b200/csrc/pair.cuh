@@ -263,7 +263,8 @@ constexpr int kPairWarps = kPairThreads / 32;
 // arrays are read from global memory (cells too full to stage).
 template <int VDW, bool FORCE>
 __global__ void __launch_bounds__(kPairThreads)
-    k_pair_box(BoxParams p, CellGrid g, int slices, int useSmem, int smemAtoms,
+    k_pair_box(BoxParams p, CellGrid g, int slices, int cell0, int useSmem,
+               int smemAtoms,
                const int *__restrict__ cellStart, const double *__restrict__ sx,
                const double *__restrict__ sy, const double *__restrict__ sz,
                const double *__restrict__ sq, const int2 *__restrict__ skm,
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kPairThreads)
   __shared__ double red[2][kPairWarps];
   __shared__ int nRangesSh;
 
-  const int cell = blockIdx.x / slices, slice = blockIdx.x % slices;
+  const int cell = cell0 + blockIdx.x / slices, slice = blockIdx.x % slices;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int iBegin0 = cellStart[cell], iEnd0 = cellStart[cell + 1];
   const int nI = iEnd0 - iBegin0;

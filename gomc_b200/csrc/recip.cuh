@@ -324,6 +324,7 @@ struct FactArgs {
   int AT;             // atoms per chunk
   int nAtoms, atomsPerSlab;
   int nkStride;
+  int tile0;  // first tile of this rank (multi-GPU sharding)
   double cvx, cvy, cvz;  // 2pi/L per axis (XYZ::Inverse then *2pi, Ewald.cpp:852-854)
 };
 
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kFactThreads, 1)
   double2 *tileA = tabZ + fa.AT * fa.ZS;
   __shared__ int2 rowAB[kMaxRG * kTR];
 
-  const int4 tile = fa.tiles[blockIdx.x];
+  const int4 tile = fa.tiles[fa.tile0 + blockIdx.x];
   const int rowBegin = tile.x, RG = tile.y, CG = tile.z;
   const int R = RG * kTR;
   const int tid = threadIdx.x;

@@ -67,6 +67,8 @@ _SIGS = {
     "gomcb200_call_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
                                          _dp, _dp, _dp, _dp, _dp, _dp]),
     "gomcb200_call_full_box_energy": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "gomcb200_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "gomcb200_mark_coords_changed": (C.c_int, [_vp]),
     "gomcb200_set_recip_algo": (C.c_int, [_vp, C.c_int]),
     "gomcb200_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gomcb200_enable_timing": (C.c_int, [_vp, C.c_int]),
@@ -324,6 +326,12 @@ class Engine:
                                                     out[2])
 
     # ---- misc --------------------------------------------------------------
+    def set_shard(self, rank, world):
+        self._ck(self.L.gomcb200_set_shard(self.h, int(rank), int(world)))
+
+    def mark_coords_changed(self):
+        self._ck(self.L.gomcb200_mark_coords_changed(self.h))
+
     def set_recip_algo(self, algo):
         self._ck(self.L.gomcb200_set_recip_algo(self.h, int(algo)))
 

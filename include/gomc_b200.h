@@ -235,6 +235,21 @@ int gomcb200_call_full_box_energy(gomcb200_engine *e, int box,
                                   const double *z, double *LJEn, double *REn,
                                   double *energyRecip);
 
+/* ---- multi-GPU sharding (one engine per GPU, one process per GPU) -------- */
+/* Rank `rank` of `world` evaluates its share of every full-box sweep:
+ * a contiguous slab of cells for the pair path and a contiguous block of
+ * (kx,ky) rows of the k list for the structure factor.  Coordinates are
+ * replicated; energies returned by box_inter / box_force /
+ * box_reciprocal_sums / call_full_box_energy are then PARTIAL sums that the
+ * caller all-reduces (3 doubles, NCCL).  sumRnew/sumInew stay distributed:
+ * entries of k-vectors owned by other ranks are zero.  world == 1 restores
+ * the single-GPU behaviour. */
+int gomcb200_set_shard(gomcb200_engine *e, int rank, int world);
+/* Tell the engine that resident coordinates are to be treated as changed
+ * (forces cell re-binning and re-packing on the next sweep), as after a
+ * device-side MultiParticle transform. */
+int gomcb200_mark_coords_changed(gomcb200_engine *e);
+
 /* ---- tuning / introspection (tests and bench only) ---------------------- */
 /* algorithm for the structure-factor build: 0 = direct sincos per (atom,k)
  * (reference algorithm), 1 = factorised per-axis phases (default). */
