@@ -251,18 +251,23 @@ int fetch_result(gomcb200_engine *e, int n) {
   return 0;
 }
 
+// warps per CTA of the box sweep: the energy kernel fits 32 warps in the
+// register file (<= 64 regs/thread), the force kernel 20 (<= 102 regs/thread)
+constexpr int kWarpsEnergy = 32, kWarpsForce = 20;
+
 template <bool FORCE>
 void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int useSmem,
                  int smemAtoms, size_t smemBytes, int grid, int cell0) {
   BoxState &bx = e->box[b];
+  constexpr int NW = FORCE ? kWarpsForce : kWarpsEnergy;
   double *fx = e->force[GOMCB200_ATOM_FORCE][0].p;
   double *fy = e->force[GOMCB200_ATOM_FORCE][1].p;
   double *fz = e->force[GOMCB200_ATOM_FORCE][2].p;
 #define LAUNCH(V)                                                                   \
   do {                                                                              \
-    cudaFuncSetAttribute(k_pair_box<V, FORCE>,                                      \
+    cudaFuncSetAttribute(k_pair_box<V, FORCE, NW>,                                  \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); \
-    k_pair_box<V, FORCE><<<grid, kPairThreads, smemBytes, e->stream>>>(             \
+    k_pair_box<V, FORCE, NW><<<grid, NW * 32, smemBytes, e->stream>>>(              \
         p, bx.grid, slices, cell0, useSmem, smemAtoms, bx.cellStart.p, bx.sx.p, bx.sy.p,  \
         bx.sz.p, bx.sq.p, bx.skm.p, bx.sortedAtoms.p, e->blockA.p, e->blockB.p, fx, \
         fy, fz);                                                                    \
@@ -291,14 +296,16 @@ int run_pair(gomcb200_engine *e, int b, bool force) {
   const int cell1 = (int)(((long long)nCells * (e->shardRank + 1)) / e->shardWorld);
   int grid = (cell1 - cell0) * slices;
   // shared-memory staging of the neighbour cells (40 B per atom)
-  size_t staticSmem = 20 * 1024;
+  const int nWarps = force ? kWarpsForce : kWarpsEnergy;
+  const size_t queueBytes = sizeof(WarpQueue) * nWarps;
+  size_t staticSmem = 4 * 1024 + queueBytes;
   size_t capAtoms = (e->smemOptin > staticSmem ? (e->smemOptin - staticSmem) : 0) / 40;
   double avg = (double)bx.nAtoms / nCells;
-  size_t want = (size_t)(27.0 * avg * 1.4) + 96;
+  size_t want = (size_t)((force ? 27.0 : 14.0) * avg * 1.4) + 96;
   int smemAtoms = (int)std::min(capAtoms, want);
   smemAtoms &= ~1;
   int useSmem = smemAtoms >= 64;
-  size_t smemBytes = useSmem ? (size_t)smemAtoms * 40 : 0;
+  size_t smemBytes = queueBytes + (useSmem ? (size_t)smemAtoms * 40 : 0);
   CK(e->blockA.reserve(grid + 1024));
   CK(e->blockB.reserve(grid + 1024));
   if (grid == 0) {

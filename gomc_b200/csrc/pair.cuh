@@ -261,8 +261,8 @@ constexpr int kPairWarps = kPairThreads / 32;
 // !FORCE: half shell (own cell with j > i plus 13 forward cells).
 // Dynamic shared memory: staged j atoms (40 B each) when useSmem, else the j
 // arrays are read from global memory (cells too full to stage).
-template <int VDW, bool FORCE>
-__global__ void __launch_bounds__(kPairThreads)
+template <int VDW, bool FORCE, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
     k_pair_box(BoxParams p, CellGrid g, int slices, int cell0, int useSmem,
                int smemAtoms,
                const int *__restrict__ cellStart, const double *__restrict__ sx,
@@ -274,9 +274,11 @@ __global__ void __launch_bounds__(kPairThreads)
   extern __shared__ __align__(16) unsigned char dynSmem[];
   __shared__ JRange ranges[27];
   __shared__ JRange stagedRanges[27];
-  __shared__ WarpQueue queues[kPairWarps];
-  __shared__ double red[2][kPairWarps];
+  __shared__ double red[2][NWARPS];
   __shared__ int nRangesSh;
+  // dynamic smem: per-warp hit queues, then the staged neighbour atoms
+  WarpQueue *queues = reinterpret_cast<WarpQueue *>(dynSmem);
+  unsigned char *stageBase = dynSmem + sizeof(WarpQueue) * NWARPS;
 
   const int cell = cell0 + blockIdx.x / slices, slice = blockIdx.x % slices;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kPairThreads)
   int selfOffset = 0;  // self-range index = global sorted index + selfOffset
   const JRange *useRanges = ranges;
   if (useSmem && iEnd > iBegin) {
-    double *smx = reinterpret_cast<double *>(dynSmem);
+    double *smx = reinterpret_cast<double *>(stageBase);
     double *smy = smx + smemAtoms;
     double *smz = smy + smemAtoms;
     double *smq = smz + smemAtoms;
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(kPairThreads)
   __syncthreads();
 
   double eLJ = 0.0, eReal = 0.0;
-  for (int i = iBegin + warp; i < iEnd; i += kPairWarps) {
+  for (int i = iBegin + warp; i < iEnd; i += NWARPS) {
     PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
     double xi = sx[i], yi = sy[i], zi = sz[i], qi = sq[i];
     int2 kmi = skm[i];
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(kPairThreads)
   __syncthreads();
   if (threadIdx.x == 0) {
     double a = 0.0, b = 0.0;
-    for (int w = 0; w < kPairWarps; ++w) {
+    for (int w = 0; w < NWARPS; ++w) {
       a += red[0][w];
       b += red[1][w];
     }
