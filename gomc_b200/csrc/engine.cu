@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "pair.cuh"
 #include "recip.cuh"
+#include "recip_mma.cuh"
 
 using namespace gb;
 
@@ -75,6 +76,12 @@ struct KSet {
   DevBuf<int4> rows, tiles;
   int nTiles = 0, maxRows = 0;
   bool planValid = false;
+  // DMMA plan (recip_mma.cuh)
+  DevBuf<int4> mmaRows, mmaTiles, mmaItems;
+  std::vector<int4> hMmaTiles;
+  int mmaZS = 0, mmaPS = 0;
+  bool mmaValid = false;
+  int itemsForAtoms = -1, itemsForShard = -1, nItems = 0, maxSlabs = 0, itemsAT = 0;
 };
 
 struct BoxState {
@@ -122,10 +129,11 @@ struct gomcb200_engine {
   DevBuf<double> force[5][3];
   std::vector<BoxState> box;
   int imageTotal = 0;
-  int recipAlgo = 1;
+  int recipAlgo = 2;  // 0 direct, 1 factorised SIMT, 2 factorised DMMA
   int shardRank = 0, shardWorld = 1;
   // scratch
   DevBuf<double> part, blockA, blockB, result, molBuf, probeOut;
+  DevBuf<double2> phaseTables;
   DevBuf<Probe> probes;
   DevBuf<unsigned char> cubTemp;
   double *hRes = nullptr;       // pinned, 64 doubles
@@ -434,6 +442,81 @@ int build_plan(gomcb200_engine *e, KSet &ks, std::vector<RowRec> &rows) {
     CK(cudaStreamSynchronize(e->stream));
   }
   ks.planValid = true;
+  // ---- DMMA plan: 128-row tiles over the cmax-sorted rows, column blocks of 40
+  {
+    std::vector<int4> mrows;
+    for (const RowRec &rw : rows) mrows.push_back(make_int4(rw.a, rw.b, rw.cmax, rw.start));
+    while (mrows.size() % kMmaRows) mrows.push_back(make_int4(0, 0, -1, 0));
+    const int KZ1 = ks.nmax[2] + 1;
+    const int colBlocks = (KZ1 + 4 * kMmaMaxNT - 1) / (4 * kMmaMaxNT);
+    ks.hMmaTiles.clear();
+    for (int cb = 0; cb < colBlocks; ++cb) {
+      const int c0 = cb * 4 * kMmaMaxNT;
+      for (size_t rb = 0; rb < mrows.size(); rb += kMmaRows) {
+        int cmaxT = mrows[rb].z;  // rows are sorted: first row has the largest cmax
+        if (cmaxT < c0) break;
+        int need = std::min(cmaxT - c0 + 1, 4 * kMmaMaxNT);
+        int NT = (need + 3) / 4;
+        NT = std::min(kMmaMaxNT, (NT + 1) & ~1);  // instantiated for even NT
+        ks.hMmaTiles.push_back(make_int4((int)rb, c0, NT, cmaxT));
+      }
+    }
+    int ZS = colBlocks * 4 * kMmaMaxNT;
+    int PS = (ks.nmax[0] + 1) + (ks.nmax[1] + 1) + ZS;
+    while (PS % 8 != 2) { ++PS; ++ZS; }
+    ks.mmaZS = ZS;
+    ks.mmaPS = PS;
+    CK(ks.mmaRows.reserve(mrows.size() + 1));
+    CK(ks.mmaTiles.reserve(ks.hMmaTiles.size() + 1));
+    CK(cudaMemcpyAsync(ks.mmaRows.p, mrows.data(), mrows.size() * sizeof(int4),
+                       cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(ks.mmaTiles.p, ks.hMmaTiles.data(), ks.hMmaTiles.size() * sizeof(int4),
+                       cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    ks.mmaValid = !ks.hMmaTiles.empty();
+    ks.itemsForAtoms = -1;
+  }
+  return 0;
+}
+
+// Work items of the DMMA kernel: (tile, atom slab) pairs of roughly equal cost
+// (cost of a tile per atom ~ its NT), about 4 per SM; only this rank's tiles.
+int build_mma_items(gomcb200_engine *e, KSet &ks, int nAt, int AT) {
+  const int shardKey = e->shardRank * 1024 + e->shardWorld;
+  if (ks.itemsForAtoms == nAt && ks.itemsForShard == shardKey && ks.itemsAT == AT) return 0;
+  const int nT = (int)ks.hMmaTiles.size();
+  const int t0 = (int)(((long long)nT * e->shardRank) / e->shardWorld);
+  const int t1 = (int)(((long long)nT * (e->shardRank + 1)) / e->shardWorld);
+  const int nChunks = std::max(1, (nAt + AT - 1) / AT);
+  double totalCost = 0;
+  for (int t = t0; t < t1; ++t) totalCost += (double)ks.hMmaTiles[t].z * nChunks;
+  const double target = 4.0 * e->numSMs;
+  std::vector<int4> items;
+  int maxSlabs = 1;
+  for (int t = t0; t < t1; ++t) {
+    double share = (double)ks.hMmaTiles[t].z * nChunks / std::max(totalCost, 1.0) * target;
+    int slabs = (int)std::lround(share);
+    slabs = std::max(1, std::min(std::min(slabs, nChunks), 32));
+    maxSlabs = std::max(maxSlabs, slabs);
+    for (int s = 0; s < slabs; ++s) {
+      int cb = (int)(((long long)nChunks * s) / slabs), ce = (int)(((long long)nChunks * (s + 1)) / slabs);
+      if (ce > cb) items.push_back(make_int4(t, cb * AT, std::min(ce * AT, nChunks * AT), s));
+    }
+  }
+  // longest items first: better tail behaviour under the hardware scheduler
+  std::stable_sort(items.begin(), items.end(), [&](const int4 &x, const int4 &y) {
+    return (long long)(x.z - x.y) * ks.hMmaTiles[x.x].z > (long long)(y.z - y.y) * ks.hMmaTiles[y.x].z;
+  });
+  CK(ks.mmaItems.reserve(items.size() + 1));
+  if (!items.empty())
+    CK(cudaMemcpyAsync(ks.mmaItems.p, items.data(), items.size() * sizeof(int4),
+                       cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  ks.nItems = (int)items.size();
+  ks.maxSlabs = maxSlabs;
+  ks.itemsForAtoms = nAt;
+  ks.itemsForShard = shardKey;
+  ks.itemsAT = AT;
   return 0;
 }
 
@@ -502,7 +585,44 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
   const int nAt = bx.nCharged;
   int nSlabs = 1;
   if (e->timing) cudaEventRecord(e->ev[2], e->stream);
-  if (e->recipAlgo == 1 && ks.planValid && ks.nTiles > 0 && nAt > 0) {
+  if (e->recipAlgo == 2 && ks.mmaValid && nAt > 0) {
+    MmaArgs ma;
+    ma.rows = ks.mmaRows.p;
+    ma.tiles = ks.mmaTiles.p;
+    ma.KX1 = ks.nmax[0] + 1;
+    ma.KY1 = ks.nmax[1] + 1;
+    ma.PS = ks.mmaPS;
+    ma.zOff = ma.KX1 + ma.KY1;
+    ma.RS = kMmaRows + 2;
+    size_t budget = e->smemOptin > 8192 ? e->smemOptin - 3072 : 0;
+    size_t perAtom = (size_t)(2 * ma.PS + ma.RS) * sizeof(double2);
+    int AT = (int)std::min<size_t>(32, budget / perAtom) & ~3;
+    if (AT < 4) return fail(GOMCB200_EINVAL, "k range too large for the DMMA kernel");
+    ma.AT = AT;
+    ma.nkStride = nkStride;
+    rc = build_mma_items(e, ks, nAt, AT);
+    if (rc) return rc;
+    ma.items = ks.mmaItems.p;
+    const int nChunks = (nAt + AT - 1) / AT;
+    const int nPad = nChunks * AT;
+    const int KZ1 = ks.nmax[2] + 1;
+    CK(e->phaseTables.reserve((size_t)nPad * ma.PS + 16));
+    ma.tables = e->phaseTables.p;
+    {
+      long long total = (long long)nPad * ma.PS;
+      k_phase_tables<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(
+          nAt, nPad, ma.KX1, ma.KY1, ks.mmaZS, KZ1, ma.PS, ks.cv[0], ks.cv[1], ks.cv[2],
+          bx.packed.p, e->phaseTables.p);
+    }
+    nSlabs = ks.maxSlabs;
+    CK(e->part.reserve((size_t)nSlabs * 2 * nkStride + 64));
+    CK(cudaMemsetAsync(e->part.p, 0, sizeof(double) * (size_t)nSlabs * 2 * nkStride, e->stream));
+    size_t smem = perAtom * AT;
+    CK(cudaFuncSetAttribute(k_recip_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ks.nItems > 0)
+      k_recip_mma<<<ks.nItems, kMmaThreads, smem, e->stream>>>(ma, e->part.p);
+    e->launches += 2;
+  } else if (e->recipAlgo >= 1 && ks.planValid && ks.nTiles > 0 && nAt > 0) {
     FactArgs fa;
     fa.rows = ks.rows.p;
     fa.tiles = ks.tiles.p;
@@ -747,11 +867,13 @@ int gomcb200_destroy(gomcb200_engine *e) {
     for (auto &ks : bx.kset) {
       ks.kx.release(); ks.ky.release(); ks.kz.release(); ks.hsqr.release();
       ks.prefact.release(); ks.rows.release(); ks.tiles.release();
+      ks.mmaRows.release(); ks.mmaTiles.release(); ks.mmaItems.release();
     }
     for (auto &s : bx.sum) s.release();
     bx.packed.release();
   }
   e->part.release(); e->blockA.release(); e->blockB.release(); e->result.release();
+  e->phaseTables.release();
   e->molBuf.release(); e->probeOut.release(); e->probes.release(); e->cubTemp.release();
   if (e->hRes) cudaFreeHost(e->hRes);
   if (e->hStage) cudaFreeHost(e->hStage);
@@ -1281,6 +1403,22 @@ int gomcb200_set_recip_ref(gomcb200_engine *e, int box) {
     dst.maxRows = src.maxRows;
     dst.planValid = true;
   }
+  dst.mmaValid = false;
+  if (src.mmaValid) {
+    CK(dst.mmaRows.reserve(src.mmaRows.cap));
+    CK(dst.mmaTiles.reserve(src.mmaTiles.cap));
+    CK(cudaMemcpyAsync(dst.mmaRows.p, src.mmaRows.p,
+                       std::min(src.mmaRows.cap, dst.mmaRows.cap) * sizeof(int4),
+                       cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(dst.mmaTiles.p, src.mmaTiles.p,
+                       std::min(src.mmaTiles.cap, dst.mmaTiles.cap) * sizeof(int4),
+                       cudaMemcpyDeviceToDevice, e->stream));
+    dst.hMmaTiles = src.hMmaTiles;
+    dst.mmaZS = src.mmaZS;
+    dst.mmaPS = src.mmaPS;
+    dst.mmaValid = true;
+    dst.itemsForAtoms = -1;
+  }
   CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -1432,7 +1570,7 @@ int gomcb200_mark_coords_changed(gomcb200_engine *e) {
 }
 
 int gomcb200_set_recip_algo(gomcb200_engine *e, int algo) {
-  if (!e || algo < 0 || algo > 1) return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!e || algo < 0 || algo > 2) return fail(GOMCB200_EINVAL, "bad arguments");
   e->recipAlgo = algo;
   return 0;
 }

@@ -252,7 +252,8 @@ int gomcb200_mark_coords_changed(gomcb200_engine *e);
 
 /* ---- tuning / introspection (tests and bench only) ---------------------- */
 /* algorithm for the structure-factor build: 0 = direct sincos per (atom,k)
- * (reference algorithm), 1 = factorised per-axis phases (default). */
+ * (reference algorithm), 1 = factorised per-axis phases on the FP64 CUDA
+ * cores, 2 = the same factorisation on the FP64 MMA path (DMMA; default). */
 int gomcb200_set_recip_algo(gomcb200_engine *e, int algo);
 /* CUDA-event time (ms) of the kernels launched by the last call, and the
  * device time of its dominant kernel. */

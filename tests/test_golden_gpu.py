@@ -79,7 +79,7 @@ def test_reciprocal(gold):
     assert e.nk == nk
     for a, name in zip(e.get_kvectors(0, eng.K_REF, nk), ("kx", "ky", "kz", "hsqr", "prefact")):
         assert np.array_equal(a, d["box0." + name]), name
-    for algo in (0, 1):
+    for algo in (0, 1, 2):
         e.set_recip_algo(algo)
         en = e.box_reciprocal_sums(0)
         gR, gI = e.get_recip_sums(0, eng.SUM_NEW, nk)

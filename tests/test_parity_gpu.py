@@ -110,7 +110,7 @@ def test_kvectors_bit_exact(case):
         assert np.array_equal(a, b)          # index-compatible with the host list
 
 
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_box_reciprocal_sums(case, algo):
     s, e, o = case
     if not _ewald(s):
@@ -121,7 +121,7 @@ def test_box_reciprocal_sums(case, algo):
     e.set_recip_algo(algo)
     en = e.box_reciprocal_sums(0)
     gR, gI = e.get_recip_sums(0, eng.SUM_NEW, e.nk)
-    e.set_recip_algo(1)
+    e.set_recip_algo(2)
     scale = max(np.max(np.abs(sR)), np.max(np.abs(sI)))
     assert np.max(np.abs(gR - sR)) <= TOL * scale
     assert np.max(np.abs(gI - sI)) <= TOL * scale

@@ -22,11 +22,12 @@ for nm in [int(a) for a in sys.argv[1:]] or [10000, 33334]:
     r = {}
     r["box_inter"] = timeit(lambda: e.box_inter(0)); 
     r["box_force"] = timeit(lambda: e.box_force(0))
-    r["recip_fact"] = timeit(lambda: e.box_reciprocal_sums(0)); r["recip_fact_dev"] = e.last_timing()
+    r["recip_mma"] = timeit(lambda: e.box_reciprocal_sums(0)); r["recip_mma_dev"] = e.last_timing()
+    e.set_recip_algo(1); r["recip_fact"] = timeit(lambda: e.box_reciprocal_sums(0)); r["recip_fact_dev"] = e.last_timing(); e.set_recip_algo(2)
     if nm <= 10000:
         e.set_recip_algo(0)
         r["recip_direct"] = timeit(lambda: e.box_reciprocal_sums(0), 2); r["recip_direct_dev"] = e.last_timing()
-        e.set_recip_algo(1)
+        e.set_recip_algo(2)
     r["full_resident"] = timeit(lambda: e.call_full_box_energy(0)); r["full_resident_dev"] = e.last_timing()
     r["full_host"] = timeit(lambda: e.call_full_box_energy(0, s.x, s.y, s.z))
     m = nm // 2
