@@ -77,11 +77,12 @@ struct KSet {
   int nTiles = 0, maxRows = 0;
   bool planValid = false;
   // DMMA plan (recip_mma.cuh)
-  DevBuf<int4> mmaRows, mmaTiles, mmaItems;
+  DevBuf<int4> mmaRows, mmaTiles, mmaSegs;
+  DevBuf<int> mmaCtaSeg;
   std::vector<int4> hMmaTiles;
-  int mmaZS = 0, mmaPS = 0;
+  int mmaZS = 0;
   bool mmaValid = false;
-  int itemsForAtoms = -1, itemsForShard = -1, nItems = 0, maxSlabs = 0, itemsAT = 0;
+  int itemsForAtoms = -1, itemsForShard = -1, nCtas = 0, maxSlabs = 0, itemsAT = 0;
 };
 
 struct BoxState {
@@ -456,16 +457,13 @@ int build_plan(gomcb200_engine *e, KSet &ks, std::vector<RowRec> &rows) {
         int cmaxT = mrows[rb].z;  // rows are sorted: first row has the largest cmax
         if (cmaxT < c0) break;
         int need = std::min(cmaxT - c0 + 1, 4 * kMmaMaxNT);
-        int NT = (need + 3) / 4;
-        NT = std::min(kMmaMaxNT, (NT + 1) & ~1);  // instantiated for even NT
+        int NT = std::min(kMmaMaxNT, (need + 3) / 4);
         ks.hMmaTiles.push_back(make_int4((int)rb, c0, NT, cmaxT));
       }
     }
     int ZS = colBlocks * 4 * kMmaMaxNT;
-    int PS = (ks.nmax[0] + 1) + (ks.nmax[1] + 1) + ZS;
-    while (PS % 8 != 2) { ++PS; ++ZS; }
+    while (ZS % 8 != 2) ++ZS;  // conflict-free B fragments
     ks.mmaZS = ZS;
-    ks.mmaPS = PS;
     CK(ks.mmaRows.reserve(mrows.size() + 1));
     CK(ks.mmaTiles.reserve(ks.hMmaTiles.size() + 1));
     CK(cudaMemcpyAsync(ks.mmaRows.p, mrows.data(), mrows.size() * sizeof(int4),
@@ -479,40 +477,71 @@ int build_plan(gomcb200_engine *e, KSet &ks, std::vector<RowRec> &rows) {
   return 0;
 }
 
-// Work items of the DMMA kernel: (tile, atom slab) pairs of roughly equal cost
-// (cost of a tile per atom ~ its NT), about 4 per SM; only this rank's tiles.
-int build_mma_items(gomcb200_engine *e, KSet &ks, int nAt, int AT) {
+// Tiles with few columns are bound by their table loads, not by the DMMAs: a
+// chunk of an NT <= kMmaMinCostNT tile costs about as much as one of NT == kMmaMinCostNT.
+constexpr int kMmaMinCostNT = 4;
+
+// Work split of the DMMA kernel.  The job is a line of (tile, atom chunk) units,
+// unit weight = NT of the tile + 1 (A-tile generation); this rank takes its
+// contiguous share of the line and cuts it into one equal piece per SM
+// (persistent CTAs, single wave).  A piece = 1..3 segments {tile, chunkBegin,
+// chunkEnd, slab}; slab numbers the segments of a tile on this rank.
+int build_mma_segments(gomcb200_engine *e, KSet &ks, int nAt, int AT) {
   const int shardKey = e->shardRank * 1024 + e->shardWorld;
   if (ks.itemsForAtoms == nAt && ks.itemsForShard == shardKey && ks.itemsAT == AT) return 0;
   const int nT = (int)ks.hMmaTiles.size();
-  const int t0 = (int)(((long long)nT * e->shardRank) / e->shardWorld);
-  const int t1 = (int)(((long long)nT * (e->shardRank + 1)) / e->shardWorld);
-  const int nChunks = std::max(1, (nAt + AT - 1) / AT);
-  double totalCost = 0;
-  for (int t = t0; t < t1; ++t) totalCost += (double)ks.hMmaTiles[t].z * nChunks;
-  const double target = 4.0 * e->numSMs;
-  std::vector<int4> items;
-  int maxSlabs = 1;
-  for (int t = t0; t < t1; ++t) {
-    double share = (double)ks.hMmaTiles[t].z * nChunks / std::max(totalCost, 1.0) * target;
-    int slabs = (int)std::lround(share);
-    slabs = std::max(1, std::min(std::min(slabs, nChunks), 32));
-    maxSlabs = std::max(maxSlabs, slabs);
-    for (int s = 0; s < slabs; ++s) {
-      int cb = (int)(((long long)nChunks * s) / slabs), ce = (int)(((long long)nChunks * (s + 1)) / slabs);
-      if (ce > cb) items.push_back(make_int4(t, cb * AT, std::min(ce * AT, nChunks * AT), s));
+  const long long nChunks = std::max(1, (nAt + AT - 1) / AT);
+  std::vector<long long> prefix(nT + 1, 0);  // weight before tile t
+  auto weight = [&](int t) { return (long long)std::max(ks.hMmaTiles[t].z, kMmaMinCostNT) + 1; };
+  for (int t = 0; t < nT; ++t) prefix[t + 1] = prefix[t] + weight(t) * nChunks;
+  const long long W = prefix[nT];
+  const long long w0 = W * e->shardRank / e->shardWorld, w1 = W * (e->shardRank + 1) / e->shardWorld;
+  const int nCtas = (int)std::max<long long>(1, std::min<long long>(e->numSMs, (w1 - w0 + 10) / 11));
+  std::vector<int4> segs;
+  std::vector<int> ctaSeg(1, 0);
+  std::vector<int> slabOfTile(nT, 0);
+  // position on the line -> (tile, chunk): chunks of tile t have weight wt each
+  auto locate = [&](long long w, int &t, long long &chunk) {
+    t = (int)(std::upper_bound(prefix.begin(), prefix.end(), w) - prefix.begin()) - 1;
+    if (t >= nT) { t = nT; chunk = 0; return; }
+    long long wt = weight(t);
+    chunk = (w - prefix[t] + wt / 2) / wt;  // round to the nearest chunk boundary
+    if (chunk >= nChunks) { ++t; chunk = 0; }
+  };
+  int tPrev; long long cPrev;
+  locate(w0, tPrev, cPrev);
+  if (e->shardRank == 0) { tPrev = 0; cPrev = 0; }
+  for (int i = 1; i <= nCtas; ++i) {
+    int tEnd; long long cEnd;
+    if (i == nCtas) {
+      locate(w1, tEnd, cEnd);
+      if (e->shardRank == e->shardWorld - 1) { tEnd = nT; cEnd = 0; }
+    } else {
+      locate(w0 + (w1 - w0) * i / nCtas, tEnd, cEnd);
     }
+    int t = tPrev; long long c = cPrev;
+    while (t < tEnd || (t == tEnd && c < cEnd)) {
+      long long ce = (t == tEnd) ? cEnd : nChunks;
+      if (ce > c) segs.push_back(make_int4(t, (int)c, (int)ce, slabOfTile[t]++));
+      ++t;
+      c = 0;
+      if (t > tEnd) break;
+    }
+    ctaSeg.push_back((int)segs.size());
+    tPrev = tEnd;
+    cPrev = cEnd;
   }
-  // longest items first: better tail behaviour under the hardware scheduler
-  std::stable_sort(items.begin(), items.end(), [&](const int4 &x, const int4 &y) {
-    return (long long)(x.z - x.y) * ks.hMmaTiles[x.x].z > (long long)(y.z - y.y) * ks.hMmaTiles[y.x].z;
-  });
-  CK(ks.mmaItems.reserve(items.size() + 1));
-  if (!items.empty())
-    CK(cudaMemcpyAsync(ks.mmaItems.p, items.data(), items.size() * sizeof(int4),
+  int maxSlabs = 1;
+  for (int t = 0; t < nT; ++t) maxSlabs = std::max(maxSlabs, slabOfTile[t]);
+  CK(ks.mmaSegs.reserve(segs.size() + 1));
+  CK(ks.mmaCtaSeg.reserve(ctaSeg.size() + 1));
+  if (!segs.empty())
+    CK(cudaMemcpyAsync(ks.mmaSegs.p, segs.data(), segs.size() * sizeof(int4),
                        cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(ks.mmaCtaSeg.p, ctaSeg.data(), ctaSeg.size() * sizeof(int),
+                     cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  ks.nItems = (int)items.size();
+  ks.nCtas = nCtas;
   ks.maxSlabs = maxSlabs;
   ks.itemsForAtoms = nAt;
   ks.itemsForShard = shardKey;
@@ -590,37 +619,37 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     ma.rows = ks.mmaRows.p;
     ma.tiles = ks.mmaTiles.p;
     ma.KX1 = ks.nmax[0] + 1;
-    ma.KY1 = ks.nmax[1] + 1;
-    ma.PS = ks.mmaPS;
-    ma.zOff = ma.KX1 + ma.KY1;
-    ma.RS = kMmaRows + 2;
-    size_t budget = e->smemOptin > 8192 ? e->smemOptin - 3072 : 0;
-    size_t perAtom = (size_t)(2 * ma.PS + ma.RS) * sizeof(double2);
+    const int KY1 = ks.nmax[1] + 1, KZ1 = ks.nmax[2] + 1;
+    ma.XYS = ma.KX1 + KY1;
+    ma.ZS = ks.mmaZS;
+    size_t budget = e->smemOptin > 8192 ? e->smemOptin - 2048 : 0;
+    size_t perAtom = 2 * (size_t)(ma.XYS + ma.ZS + kMmaRS) * sizeof(double2);
     int AT = (int)std::min<size_t>(32, budget / perAtom) & ~3;
     if (AT < 4) return fail(GOMCB200_EINVAL, "k range too large for the DMMA kernel");
     ma.AT = AT;
     ma.nkStride = nkStride;
-    rc = build_mma_items(e, ks, nAt, AT);
+    rc = build_mma_segments(e, ks, nAt, AT);
     if (rc) return rc;
-    ma.items = ks.mmaItems.p;
+    ma.segs = ks.mmaSegs.p;
+    ma.ctaSeg = ks.mmaCtaSeg.p;
     const int nChunks = (nAt + AT - 1) / AT;
     const int nPad = nChunks * AT;
-    const int KZ1 = ks.nmax[2] + 1;
-    CK(e->phaseTables.reserve((size_t)nPad * ma.PS + 16));
-    ma.tables = e->phaseTables.p;
+    const size_t nXY = (size_t)nPad * ma.XYS, nZ = (size_t)nPad * ma.ZS;
+    CK(e->phaseTables.reserve(nXY + nZ + 16));
+    ma.tabXY = e->phaseTables.p;
+    ma.tabZ = e->phaseTables.p + nXY;
     {
-      long long total = (long long)nPad * ma.PS;
+      long long total = (long long)nPad * (ma.XYS + ma.ZS);
       k_phase_tables<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(
-          nAt, nPad, ma.KX1, ma.KY1, ks.mmaZS, KZ1, ma.PS, ks.cv[0], ks.cv[1], ks.cv[2],
-          bx.packed.p, e->phaseTables.p);
+          nAt, nPad, ma.KX1, KY1, KZ1, ma.ZS, ks.cv[0], ks.cv[1], ks.cv[2], bx.packed.p,
+          e->phaseTables.p, e->phaseTables.p + nXY);
     }
     nSlabs = ks.maxSlabs;
     CK(e->part.reserve((size_t)nSlabs * 2 * nkStride + 64));
     CK(cudaMemsetAsync(e->part.p, 0, sizeof(double) * (size_t)nSlabs * 2 * nkStride, e->stream));
     size_t smem = perAtom * AT;
     CK(cudaFuncSetAttribute(k_recip_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (ks.nItems > 0)
-      k_recip_mma<<<ks.nItems, kMmaThreads, smem, e->stream>>>(ma, e->part.p);
+    k_recip_mma<<<ks.nCtas, kMmaThreads, smem, e->stream>>>(ma, e->part.p);
     e->launches += 2;
   } else if (e->recipAlgo >= 1 && ks.planValid && ks.nTiles > 0 && nAt > 0) {
     FactArgs fa;
@@ -867,7 +896,7 @@ int gomcb200_destroy(gomcb200_engine *e) {
     for (auto &ks : bx.kset) {
       ks.kx.release(); ks.ky.release(); ks.kz.release(); ks.hsqr.release();
       ks.prefact.release(); ks.rows.release(); ks.tiles.release();
-      ks.mmaRows.release(); ks.mmaTiles.release(); ks.mmaItems.release();
+      ks.mmaRows.release(); ks.mmaTiles.release(); ks.mmaSegs.release(); ks.mmaCtaSeg.release();
     }
     for (auto &s : bx.sum) s.release();
     bx.packed.release();
@@ -1415,7 +1444,6 @@ int gomcb200_set_recip_ref(gomcb200_engine *e, int box) {
                        cudaMemcpyDeviceToDevice, e->stream));
     dst.hMmaTiles = src.hMmaTiles;
     dst.mmaZS = src.mmaZS;
-    dst.mmaPS = src.mmaPS;
     dst.mmaValid = true;
     dst.itemsForAtoms = -1;
   }

@@ -11,59 +11,75 @@
 // 4x less shared-memory operand traffic than the SIMT register tile, and a
 // slightly higher measured ceiling (37.2 vs 34.1 TFLOP/s, profiles/r1_fp64_peak.json).
 //
-// Data flow per CTA (8 warps, one work item = row tile x atom slab):
-//   * k_phase_tables (pre-kernel) writes per-atom phase tables
-//       [X: q*e^{i a tx}, a=0..KX][Y: e^{i b ty}, b=0..KY][Z: e^{i c tz}, c=0..ZS)
-//     once per evaluation (1.16e7 sincos for the 100k-atom box);
-//   * chunks of AT atoms of those tables are brought into shared memory with
-//     one cp.async.bulk (TMA, SASS UBLKCP) per chunk, double-buffered on an
-//     mbarrier, so table traffic overlaps the math;
-//   * all threads build the A tile (complex product X^a Y^b) for the chunk;
-//   * each warp owns 16 (a,b) rows x up to 40 c columns = MT(4) x NT(<=10)
-//     m8n8 accumulator tiles and streams the chunk four atoms per DMMA.
-// Partials per atom slab go to part[slab][re/im][k]; k_recip_finish sums them in
-// slab order (deterministic).
+// Kernel organisation (one persistent CTA per SM, 16 warps):
+//   * k_phase_tables (pre-kernel) writes per-atom phase tables once per
+//     evaluation: tabXY[atom] = {q e^{i a tx}, a<=KX ; e^{i b ty}, b<=KY} and
+//     tabZ[atom] = {e^{i c tz}, c<ZS}  (1.2e7 sincos for the 100k-atom box);
+//   * the host cuts the whole job -- a line of (row tile, atom chunk) units
+//     weighted by the tile's column count -- into one equal piece per SM, so
+//     there is a single wave and no tail; a piece is 1-3 "segments"
+//     (tile, chunk range, slab);
+//   * per chunk of AT atoms the XY and Z tables arrive in shared memory by
+//     cp.async.bulk (TMA, SASS UBLKCP) on mbarriers, two chunks ahead;
+//   * software pipeline: while the warps issue the DMMAs of chunk c they also
+//     build the A tile (complex products X^a Y^b) of chunk c+1 into the other
+//     buffer -- one element per thread per k4 step -- so the FP64 MMA pipe never
+//     waits for operand generation; one __syncthreads per chunk;
+//   * each warp owns 8 (a,b) rows x up to 40 c columns = MT(2) x NT(<=10) m8n8
+//     accumulator tiles (80 registers).
+// Partials per slab go to part[slab][re/im][k]; k_recip_finish sums them in slab
+// order (deterministic, no atomics).
 #pragma once
 #include "common.cuh"
 
 namespace gb {
 
-constexpr int kMmaThreads = 256;
-constexpr int kMmaWarps = 8;
-constexpr int kMmaMT = 4;                      // m8 tiles per warp: 16 (a,b) rows
-constexpr int kMmaRowsPerWarp = kMmaMT * 4;    // 16
+constexpr int kMmaThreads = 512;
+constexpr int kMmaWarps = 16;
+constexpr int kMmaMT = 2;                      // m8 tiles per warp: 8 (a,b) rows
+constexpr int kMmaRowsPerWarp = kMmaMT * 4;    // 8
 constexpr int kMmaRows = kMmaWarps * kMmaRowsPerWarp;  // 128 rows per tile
 constexpr int kMmaMaxNT = 10;                  // n8 tiles per column block: 40 c
+constexpr int kMmaRS = kMmaRows + 2;           // A tile row stride (double2), % 8 == 2
 
 struct MmaArgs {
   const int4 *rows;    // {a, b, cmax, start}, sorted by cmax descending, padded
-  const int4 *tiles;   // {rowBegin, c0, NT, unused}
-  const int4 *items;   // {tile, atomBegin, atomEnd, slab}
-  const double2 *tables;  // [atom][PS]
-  int KX1, KY1;        // X and Y table lengths
-  int PS;              // per-atom table stride (double2), PS % 8 == 2
-  int zOff;            // offset of Z inside an atom's table = KX1 + KY1
-  int RS;              // A tile row stride (double2), RS % 8 == 2, >= 128
+  const int4 *tiles;   // {rowBegin, c0, NT, cmaxTile}
+  const int4 *segs;    // {tile, chunkBegin, chunkEnd, slab}
+  const int *ctaSeg;   // [gridDim.x + 1] segment ranges per CTA
+  const double2 *tabXY;  // [atom][XYS]
+  const double2 *tabZ;   // [atom][ZS]
+  int KX1;             // X table length (Y follows at offset KX1)
+  int XYS;             // = KX1 + KY1
+  int ZS;              // Z row stride (double2), ZS % 8 == 2, >= 40 * colBlocks
   int AT;              // atoms per chunk (multiple of 4)
   int nkStride;
 };
 
 // ---- phase tables ----------------------------------------------------------
-// One thread per (atom, table entry).  cv = 2 pi / L per axis.
+// One thread per (atom, table entry).  cv = 2 pi / L per axis
+// (XYZ::Inverse then *= 2 pi, src/Ewald.cpp:852-854).
 __global__ void __launch_bounds__(256)
-    k_phase_tables(int nAtoms, int nAtomsPadded, int KX1, int KY1, int ZS, int KZ1,
-                   int PS, double cvx, double cvy, double cvz,
-                   const double4 *__restrict__ pb, double2 *__restrict__ tables) {
+    k_phase_tables(int nAtoms, int nAtomsPadded, int KX1, int KY1, int KZ1, int ZS,
+                   double cvx, double cvy, double cvz, const double4 *__restrict__ pb,
+                   double2 *__restrict__ tabXY, double2 *__restrict__ tabZ) {
+  const int PS = KX1 + KY1 + ZS;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)nAtomsPadded * PS;
   if (idx >= total) return;
   int atom = (int)(idx / PS), e = (int)(idx - (long long)atom * PS);
   double2 v = make_double2(0.0, 0.0);
-  if (atom < nAtoms) {
+  double coord = 0.0, cv = 0.0, scale = 1.0;
+  int n = 0;
+  bool valid = atom < nAtoms;
+  double2 *dst;
+  if (e < KX1 + KY1) {
+    dst = tabXY + (size_t)atom * (KX1 + KY1) + e;
+  } else {
+    dst = tabZ + (size_t)atom * ZS + (e - KX1 - KY1);
+  }
+  if (valid) {
     double4 a = pb[atom];
-    double coord, cv, scale = 1.0;
-    int n;
-    bool valid = true;
     if (e < KX1) {
       coord = a.x; cv = cvx; n = e; scale = a.w;  // charge folded into X
     } else if (e < KX1 + KY1) {
@@ -78,22 +94,21 @@ __global__ void __launch_bounds__(256)
       v = make_double2(scale * c, scale * s);
     }
   }
-  tables[idx] = v;
+  *dst = v;
 }
 
 // ---- PTX helpers -------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
   return (unsigned)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
   unsigned ok;
   asm volatile(
       "{\n"
@@ -102,20 +117,20 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
 // 1-D bulk copy global -> shared through the TMA unit (bytes % 16 == 0).
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
-                                         unsigned long long *bar) {
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes,
+                                         unsigned bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
@@ -124,150 +139,217 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
 }
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64x2(unsigned addr, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
 
+// A-tile element for this thread's row: (q X^a)(Y^b), conj(Y) when b < 0.
+__device__ __forceinline__ void agen_one(unsigned xyAtom, unsigned offX, unsigned offY,
+                                         double ysign, unsigned dst) {
+  double2 xv = lds_f64x2(xyAtom + offX);
+  double2 yv = lds_f64x2(xyAtom + offY);
+  yv.y *= ysign;
+  sts_f64x2(dst, xv.x * yv.x - xv.y * yv.y, xv.x * yv.y + xv.y * yv.x);
+}
+
+// One chunk: nK4 steps of (MT x NT) DMMAs on tileA/Z of this chunk, interleaved
+// with building the next chunk's A tile (one element per thread per step).
+// All addresses are 32-bit shared-window addresses.
 template <int NT>
-__device__ __forceinline__ void mma_chunk(double (&acc)[kMmaMT][kMmaMaxNT][2],
-                                          const double *__restrict__ aBase,
-                                          const double *__restrict__ zBase, int nK4,
-                                          int aStride4, int zStride4) {
-  // aBase/zBase already include the lane's (k = lane&3, m|n = lane>>2) offsets;
-  // *Stride4 = doubles per 4 atoms
+__device__ __forceinline__ void mma_chunk(double (&acc)[kMmaMT][kMmaMaxNT][2], unsigned aAddr,
+                                          unsigned zAddr, int nK4, unsigned aStep,
+                                          unsigned zStep, bool genNext, unsigned xyNext,
+                                          unsigned xyStep, unsigned offX, unsigned offY,
+                                          double ysign, unsigned aNext, unsigned aNextStep) {
   for (int k4 = 0; k4 < nK4; ++k4) {
     double a[kMmaMT], b[NT];
 #pragma unroll
-    for (int mt = 0; mt < kMmaMT; ++mt) a[mt] = aBase[mt * 8];
+    for (int mt = 0; mt < kMmaMT; ++mt) a[mt] = lds_f64(aAddr + mt * 64);
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) b[nt] = zBase[nt * 8];
+    for (int nt = 0; nt < NT; ++nt) b[nt] = lds_f64(zAddr + nt * 64);
+    if (genNext) agen_one(xyNext, offX, offY, ysign, aNext);
 #pragma unroll
-    for (int mt = 0; mt < kMmaMT; ++mt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-    aBase += aStride4;
-    zBase += zStride4;
+      for (int mt = 0; mt < kMmaMT; ++mt)
+        dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    aAddr += aStep;
+    zAddr += zStep;
+    xyNext += xyStep;
+    aNext += aNextStep;
   }
 }
 
 __global__ void __launch_bounds__(kMmaThreads, 1)
     k_recip_mma(MmaArgs ma, double *__restrict__ part) {
   extern __shared__ __align__(16) unsigned char dynSmem[];
-  __shared__ __align__(8) unsigned long long mbar[2];
-  __shared__ int2 rowAB[kMmaRows];
+  __shared__ __align__(8) unsigned long long mbarStore[4];  // XY0, XY1, Z0, Z1
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int4 item = ma.items[blockIdx.x];
-  const int4 tile = ma.tiles[item.x];
-  const int rowBegin = tile.x, c0 = tile.y, NT = tile.z;
-  const int aBegin = item.y, aEnd = item.z, slab = item.w;
-  const int AT = ma.AT, PS = ma.PS, RS = ma.RS;
+  const int AT = ma.AT, XYS = ma.XYS, ZS = ma.ZS;
+  const unsigned xyBytes = (unsigned)(AT * XYS * 16), zBytes = (unsigned)(AT * ZS * 16);
+  const unsigned aBytes = (unsigned)(AT * kMmaRS * 16);
+  const unsigned smBase = smem_u32(dynSmem);
+  // buffer / barrier addresses are computed, not indexed (keeps them in registers)
+  auto xyBufAt = [&](int i) { return smBase + (unsigned)i * xyBytes; };
+  auto zBufAt = [&](int i) { return smBase + 2 * xyBytes + (unsigned)i * zBytes; };
+  auto aBufAt = [&](int i) { return smBase + 2 * xyBytes + 2 * zBytes + (unsigned)i * aBytes; };
+  const unsigned barBase = smem_u32(&mbarStore[0]);
+  auto barXYAt = [&](int i) { return barBase + 8u * (unsigned)i; };
+  auto barZAt = [&](int i) { return barBase + 16u + 8u * (unsigned)i; };
+  unsigned phaseBits = 0;  // bit i: parity to wait for next on barrier i (XY0, XY1, Z0, Z1)
 
-  double2 *tab[2];
-  tab[0] = reinterpret_cast<double2 *>(dynSmem);
-  tab[1] = tab[0] + (size_t)AT * PS;
-  double2 *tileA = tab[1] + (size_t)AT * PS;
-
-  for (int r = tid; r < kMmaRows; r += kMmaThreads) {
-    int4 rw = ma.rows[rowBegin + r];
-    rowAB[r] = make_int2(rw.x, rw.y);
-  }
   if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(barXYAt(i), 1);
+      mbar_init(barZAt(i), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  const int nChunks = (aEnd - aBegin + AT - 1) / AT;
-  const unsigned chunkBytes = (unsigned)((size_t)AT * PS * sizeof(double2));
-  if (tid == 0 && nChunks > 0) {
-    mbar_expect_tx(&mbar[0], chunkBytes);
-    bulk_g2s(tab[0], ma.tables + (size_t)aBegin * PS, chunkBytes, &mbar[0]);
-  }
+  // A-generation role of this thread: row r of the tile, atoms g, g+4, ...
+  const int genRow = tid & (kMmaRows - 1), genG = tid >> 7;
+  const int nK4 = AT / 4;
 
-  double acc[kMmaMT][kMmaMaxNT][2];
-#pragma unroll
-  for (int mt = 0; mt < kMmaMT; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < kMmaMaxNT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  const int segBegin = ma.ctaSeg[blockIdx.x], segEnd = ma.ctaSeg[blockIdx.x + 1];
+  for (int sIdx = segBegin; sIdx < segEnd; ++sIdx) {
+    const int4 seg = ma.segs[sIdx];
+    const int4 tile = ma.tiles[seg.x];
+    const int rowBegin = tile.x, c0 = tile.y, NT = tile.z;
+    const int chunk0 = seg.y, nChunks = seg.z - seg.y, slab = seg.w;
 
-  const int RS2 = 2 * RS, PS2 = 2 * PS;
-  for (int c = 0; c < nChunks; ++c) {
-    const int buf = c & 1;
-    if (tid == 0 && c + 1 < nChunks) {
-      // the other buffer was last read (generic proxy) before the barrier that
-      // ended chunk c-1; order those reads before the async-proxy overwrite
+    const int4 myRow = ma.rows[rowBegin + genRow];
+    const unsigned offX = (unsigned)myRow.x * 16u;
+    const unsigned offY = (unsigned)(ma.KX1 + (myRow.y < 0 ? -myRow.y : myRow.y)) * 16u;
+    const double ysign = myRow.y < 0 ? -1.0 : 1.0;
+
+    double acc[kMmaMT][kMmaMaxNT][2];
+#pragma unroll
+    for (int mt = 0; mt < kMmaMT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < kMmaMaxNT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    // ---- prologue: XY(0), Z(0), XY(1) in flight; build A(0) ----------------
+    if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&mbar[buf ^ 1], chunkBytes);
-      bulk_g2s(tab[buf ^ 1], ma.tables + (size_t)(aBegin + (c + 1) * AT) * PS, chunkBytes,
-               &mbar[buf ^ 1]);
-    }
-    mbar_wait(&mbar[buf], (unsigned)((c >> 1) & 1));
-    const double2 *T = tab[buf];
-    // ---- A tile: A[at][row] = (q X^a)(Y^b), conj(Y) for b < 0 --------------
-    for (int t = tid; t < AT * kMmaRows; t += kMmaThreads) {
-      int at = t >> 7, r = t & (kMmaRows - 1);
-      int2 ab = rowAB[r];
-      double2 xv = T[at * PS + ab.x];
-      int bb = ab.y < 0 ? -ab.y : ab.y;
-      double2 yv = T[at * PS + ma.KX1 + bb];
-      if (ab.y < 0) yv.y = -yv.y;
-      tileA[at * RS + r] =
-          make_double2(xv.x * yv.x - xv.y * yv.y, xv.x * yv.y + xv.y * yv.x);
-    }
-    __syncthreads();
-    // ---- DMMA over the chunk, four atoms per instruction ---------------------
-    {
-      const double *aBase = reinterpret_cast<const double *>(tileA) + (lane & 3) * RS2 +
-                            warp * (kMmaRowsPerWarp * 2) + (lane >> 2);
-      const double *zBase = reinterpret_cast<const double *>(T) + (lane & 3) * PS2 +
-                            2 * (ma.zOff + c0) + (lane >> 2);
-      const int nK4 = AT / 4;
-      switch (NT) {
-        case 2: mma_chunk<2>(acc, aBase, zBase, nK4, 4 * RS2, 4 * PS2); break;
-        case 4: mma_chunk<4>(acc, aBase, zBase, nK4, 4 * RS2, 4 * PS2); break;
-        case 6: mma_chunk<6>(acc, aBase, zBase, nK4, 4 * RS2, 4 * PS2); break;
-        case 8: mma_chunk<8>(acc, aBase, zBase, nK4, 4 * RS2, 4 * PS2); break;
-        default: mma_chunk<10>(acc, aBase, zBase, nK4, 4 * RS2, 4 * PS2); break;
+      mbar_expect_tx(barXYAt(0), xyBytes);
+      bulk_g2s(xyBufAt(0), ma.tabXY + (size_t)chunk0 * AT * XYS, xyBytes, barXYAt(0));
+      mbar_expect_tx(barZAt(0), zBytes);
+      bulk_g2s(zBufAt(0), ma.tabZ + (size_t)chunk0 * AT * ZS, zBytes, barZAt(0));
+      if (nChunks > 1) {
+        mbar_expect_tx(barXYAt(1), xyBytes);
+        bulk_g2s(xyBufAt(1), ma.tabXY + (size_t)(chunk0 + 1) * AT * XYS, xyBytes, barXYAt(1));
       }
     }
+    mbar_wait(barXYAt(0), phaseBits & 1u);
+    phaseBits ^= 1u;
+    for (int j = 0; j < nK4; ++j) {
+      int at = 4 * j + genG;
+      agen_one(xyBufAt(0) + (unsigned)(at * XYS) * 16u, offX, offY, ysign,
+               aBufAt(0) + (unsigned)(at * kMmaRS + genRow) * 16u);
+    }
     __syncthreads();
-  }
 
-  // ---- epilogue: exchange Ar*/Ai* partners (lane ^ 4), write S(a,b,+-c) --------
-  double *pr = part + (size_t)(slab * 2 + 0) * ma.nkStride;
-  double *pi = part + (size_t)(slab * 2 + 1) * ma.nkStride;
-  const int comp = (lane >> 2) & 1;  // 0: this lane holds Ar*{cz,sz}; 1: Ai*{cz,sz}
-#pragma unroll
-  for (int mt = 0; mt < kMmaMT; ++mt) {
-    const int r = warp * kMmaRowsPerWarp + mt * 4 + (lane >> 3);
-    const int4 rw = ma.rows[rowBegin + r];
-    const int cmax = rw.z;
-    const bool origin = (rw.x == 0 && rw.y == 0);
-#pragma unroll
-    for (int nt = 0; nt < kMmaMaxNT; ++nt) {
-      if (nt >= NT) break;
-      double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
-      double o0 = __shfl_xor_sync(0xffffffffu, v0, 4);
-      double o1 = __shfl_xor_sync(0xffffffffu, v1, 4);
-      const int cc = c0 + nt * 4 + (lane & 3);
-      if (cc > cmax) continue;
-      // comp 0: v0 = P1 (Ar cz), v1 = P3 (Ar sz), o0 = P4 (Ai cz), o1 = P2 (Ai sz)
-      // comp 1: v0 = P4, v1 = P2, o0 = P1, o1 = P3
-      if (comp == 0) {  // writes S(a,b,+c)
-        double re = v0 - o1, im = v1 + o0;
-        if (origin) {
-          if (cc >= 1) {
-            pr[rw.w + cc - 1] = re;
-            pi[rw.w + cc - 1] = im;
-          }
-        } else {
-          pr[rw.w + cmax + cc] = re;
-          pi[rw.w + cmax + cc] = im;
+    for (int c = 0; c < nChunks; ++c) {
+      const int cur = c & 1, nxt = cur ^ 1;
+      if (tid == 0) {
+        // buffers xy[cur] (A(c) was built from it) and z[nxt] (MMA c-1 read it)
+        // are free since the barrier that ended iteration c-1
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (c + 2 < nChunks) {
+          mbar_expect_tx(barXYAt(cur), xyBytes);
+          bulk_g2s(xyBufAt(cur), ma.tabXY + (size_t)(chunk0 + c + 2) * AT * XYS, xyBytes,
+                   barXYAt(cur));
         }
-      } else if (!origin && cc > 0) {  // writes S(a,b,-c)
-        pr[rw.w + cmax - cc] = o0 + v1;   // P1 + P2
-        pi[rw.w + cmax - cc] = v0 - o1;   // P4 - P3
+        if (c + 1 < nChunks) {
+          mbar_expect_tx(barZAt(nxt), zBytes);
+          bulk_g2s(zBufAt(nxt), ma.tabZ + (size_t)(chunk0 + c + 1) * AT * ZS, zBytes,
+                   barZAt(nxt));
+        }
+      }
+      const bool genNext = c + 1 < nChunks;
+      mbar_wait(barZAt(cur), (phaseBits >> (2 + cur)) & 1u);
+      phaseBits ^= 1u << (2 + cur);
+      if (genNext) {
+        mbar_wait(barXYAt(nxt), (phaseBits >> nxt) & 1u);
+        phaseBits ^= 1u << nxt;
+      }
+      // lane fragment addresses: A[k = lane&3][m = lane>>2], B[k = lane&3][n = lane>>2]
+      const unsigned aAddr = aBufAt(cur) + (unsigned)((lane & 3) * kMmaRS * 16) +
+                             (unsigned)(warp * kMmaRowsPerWarp * 16) + (unsigned)((lane >> 2) * 8);
+      const unsigned zAddr = zBufAt(cur) + (unsigned)((lane & 3) * ZS * 16) + (unsigned)(c0 * 16) +
+                             (unsigned)((lane >> 2) * 8);
+      const unsigned aStep = 4u * kMmaRS * 16u, zStep = 4u * (unsigned)ZS * 16u;
+      const unsigned xyNext = xyBufAt(nxt) + (unsigned)(genG * XYS) * 16u;
+      const unsigned xyStep = 4u * (unsigned)XYS * 16u;
+      const unsigned aNext = aBufAt(nxt) + (unsigned)(genG * kMmaRS + genRow) * 16u;
+#define MMA_CASE(N)                                                                       \
+  case N:                                                                                 \
+    mma_chunk<N>(acc, aAddr, zAddr, nK4, aStep, zStep, genNext, xyNext, xyStep, offX, offY, \
+                 ysign, aNext, aStep);                                                    \
+    break;
+      switch (NT) {
+        MMA_CASE(1) MMA_CASE(2) MMA_CASE(3) MMA_CASE(4) MMA_CASE(5)
+        MMA_CASE(6) MMA_CASE(7) MMA_CASE(8) MMA_CASE(9)
+        default:
+          mma_chunk<10>(acc, aAddr, zAddr, nK4, aStep, zStep, genNext, xyNext, xyStep, offX,
+                        offY, ysign, aNext, aStep);
+      }
+#undef MMA_CASE
+      __syncthreads();
+    }
+
+    // ---- epilogue: exchange Ar*/Ai* partners (lane ^ 4), write S(a,b,+-c) ------
+    double *pr = part + (size_t)(slab * 2 + 0) * ma.nkStride;
+    double *pi = part + (size_t)(slab * 2 + 1) * ma.nkStride;
+    const int comp = (lane >> 2) & 1;  // 0: lane holds Ar*{cz,sz}; 1: Ai*{cz,sz}
+#pragma unroll
+    for (int mt = 0; mt < kMmaMT; ++mt) {
+      const int r = warp * kMmaRowsPerWarp + mt * 4 + (lane >> 3);
+      const int4 rw = ma.rows[rowBegin + r];
+      const int cmax = rw.z;
+      const bool origin = (rw.x == 0 && rw.y == 0);
+#pragma unroll
+      for (int nt = 0; nt < kMmaMaxNT; ++nt) {
+        if (nt < NT) {
+          double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+          double o0 = __shfl_xor_sync(0xffffffffu, v0, 4);
+          double o1 = __shfl_xor_sync(0xffffffffu, v1, 4);
+          const int cc = c0 + nt * 4 + (lane & 3);
+          if (cc <= cmax) {
+            // comp 0: v0 = P1 (Ar cz), v1 = P3 (Ar sz), o0 = P4 (Ai cz), o1 = P2 (Ai sz)
+            // comp 1: v0 = P4, v1 = P2, o0 = P1, o1 = P3
+            if (comp == 0) {  // writes S(a,b,+c)
+              double re = v0 - o1, im = v1 + o0;
+              if (origin) {
+                if (cc >= 1) {
+                  pr[rw.w + cc - 1] = re;
+                  pi[rw.w + cc - 1] = im;
+                }
+              } else {
+                pr[rw.w + cmax + cc] = re;
+                pi[rw.w + cmax + cc] = im;
+              }
+            } else if (!origin && cc > 0) {  // writes S(a,b,-c)
+              pr[rw.w + cmax - cc] = o0 + v1;  // P1 + P2
+              pi[rw.w + cmax - cc] = v0 - o1;  // P4 - P3
+            }
+          }
+        }
       }
     }
+    __syncthreads();  // tile A / table buffers are reused by the next segment
   }
 }
 
