@@ -1,0 +1,315 @@
+// GomcB200.h -- C++ host mirror of GOMC's energy interfaces over the C ABI.
+//
+// The reference reaches its hot path through two objects held by every move
+// (src/moves/MoveBase.h:83-84): `CalculateEnergy &calcEnRef` and
+// `Ewald *calcEwald` (Ewald / EwaldCached / NoEwald, chosen in
+// src/System.cpp:132-148).  The classes below keep those names, method names,
+// argument meaning and the reference's error behaviour (print + exit, as
+// gpuAssert does in src/GPU/VariablesCUDA.cuh:20-39), and forward to
+// include/gomc_b200.h.  Header-only; link with libgomc_b200.so.
+//
+// Coordinates are passed as SoA views (what XYZArray is, src/XYZArray.h:25-70).
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/gomc_b200.h"
+
+namespace gomc_b200 {
+
+struct XYZView {           // XYZArray: three parallel arrays
+  const double *x, *y, *z;
+  int count;
+};
+struct XYZ {
+  double x, y, z;
+};
+struct Intermolecular {    // src/EnergyTypes.h:40-73
+  double virial = 0.0, energy = 0.0;
+};
+struct Energy {            // the members of src/EnergyTypes.h:75-129 this path fills
+  double inter = 0.0, real = 0.0, recip = 0.0, self = 0.0, correction = 0.0,
+         tailCorrection = 0.0;
+};
+
+inline void check(int rc, const char *what) {
+  if (rc != GOMCB200_OK) {
+    fprintf(stderr, "GPUassert: %s failed (%d): %s\n", what, rc, gomcb200_last_error());
+    exit(EXIT_FAILURE);  // same convention as the reference's gpuAssert
+  }
+}
+
+// Owns the device engine (the role of VariablesCUDA, src/FFParticle.cpp:56).
+class EngineB200 {
+public:
+  EngineB200(int device, int boxTotal) { check(gomcb200_create(&e_, device, boxTotal), "create"); }
+  ~EngineB200() { gomcb200_destroy(e_); }
+  EngineB200(const EngineB200 &) = delete;
+  EngineB200 &operator=(const EngineB200 &) = delete;
+  gomcb200_engine *get() const { return e_; }
+
+  // FFParticle::Init -> InitGPUForceField (src/FFParticle.cpp:87)
+  void InitForceField(const double *sigmaSq, const double *epsilon_cn, const double *n,
+                      int vdwKind, int isMartini, int count, double rCut,
+                      const double *rCutCoulomb, double rCutLow, double rOn,
+                      const double *alpha, bool ewald, bool electrostatic) {
+    check(gomcb200_init_forcefield(e_, sigmaSq, epsilon_cn, n, vdwKind, isMartini, count, rCut,
+                                   rCutCoulomb, rCutLow, rOn, alpha, ewald, electrostatic, 1.0),
+          "InitGPUForceField");
+  }
+  // CalculateEnergy::Init (src/CalculateEnergy.cpp:60-81)
+  void InitTopology(const std::vector<int> &particleKind, const std::vector<int> &particleMol,
+                    const std::vector<double> &particleCharge, const std::vector<int> &molStart) {
+    molStart_ = molStart;
+    charge_ = particleCharge;
+    check(gomcb200_init_topology(e_, (int)particleKind.size(), (int)molStart.size() - 1,
+                                 particleKind.data(), particleMol.data(), particleCharge.data(),
+                                 molStart.data()),
+          "InitCoordinatesCUDA");
+  }
+  void SetBoxMolecules(int box, const std::vector<int> &mols) {
+    check(gomcb200_set_box_molecules(e_, box, mols.data(), (int)mols.size()), "SetBoxMolecules");
+  }
+  void SetBoxAxes(int box, const XYZ &axis) {  // UpdateCellBasisCUDA
+    double a[3] = {axis.x, axis.y, axis.z};
+    check(gomcb200_set_box_axes(e_, box, a), "UpdateCellBasisCUDA");
+  }
+  void SetCoordinates(const XYZView &c) {
+    check(gomcb200_set_coords(e_, c.x, c.y, c.z, 0, c.count), "SetCoordinates");
+  }
+  void SetCOM(const XYZView &c) { check(gomcb200_set_com(e_, c.x, c.y, c.z, 0, c.count), "SetCOM"); }
+  // what Translate::Accept / Rotate::Accept copy (src/moves/Translate.h:106-113)
+  void AcceptMolecule(int molIndex, const XYZView &molCoords, const XYZ &com) {
+    double c[3] = {com.x, com.y, com.z};
+    check(gomcb200_set_molecule_coords(e_, molIndex, molCoords.x, molCoords.y, molCoords.z, c),
+          "AcceptMolecule");
+  }
+  int MolStart(int m) const { return molStart_[m]; }
+  int MolLength(int m) const { return molStart_[m + 1] - molStart_[m]; }
+  double Charge(int atom) const { return charge_[atom]; }
+
+private:
+  gomcb200_engine *e_ = nullptr;
+  std::vector<int> molStart_;
+  std::vector<double> charge_;
+};
+
+// ---------------------------------------------------------------------------
+class CalculateEnergy {
+public:
+  explicit CalculateEnergy(EngineB200 &eng) : eng_(eng) {}
+
+  // src/CalculateEnergy.cpp:157-266 (pair sums; the LRC term stays on the host)
+  Energy BoxInter(const XYZView &coords, const XYZ &boxAxes, int box) {
+    Energy en;
+    double a[3] = {boxAxes.x, boxAxes.y, boxAxes.z};
+    check(gomcb200_call_box_inter(eng_.get(), box, coords.x, coords.y, coords.z, a, &en.real,
+                                  &en.inter),
+          "CallBoxInterGPU");
+    return en;
+  }
+  // src/CalculateEnergy.cpp:268-406; force arrays may be null (stay on the device)
+  Energy BoxForce(const XYZView &coords, double *aFx, double *aFy, double *aFz, double *mFx,
+                  double *mFy, double *mFz, const XYZ &boxAxes, int box) {
+    Energy en;
+    double a[3] = {boxAxes.x, boxAxes.y, boxAxes.z};
+    check(gomcb200_call_box_force(eng_.get(), box, coords.x, coords.y, coords.z, a, &en.real,
+                                  &en.inter, aFx, aFy, aFz, mFx, mFy, mFz),
+          "CallBoxForceGPU");
+    return en;
+  }
+  // src/CalculateEnergy.cpp:581-686; returns the overlap flag
+  bool MoleculeInter(Intermolecular &inter_LJ, Intermolecular &inter_coulomb,
+                     const XYZView &molCoords, int molIndex, int box) const {
+    int overlap = 0;
+    check(gomcb200_molecule_inter(eng_.get(), box, molIndex, molCoords.x, molCoords.y,
+                                  molCoords.z, &inter_LJ.energy, &inter_coulomb.energy,
+                                  &overlap),
+          "MoleculeInter");
+    return overlap != 0;
+  }
+  // src/CalculateEnergy.cpp:727-785
+  void ParticleInter(double *en, double *real, const XYZView &trialPos, bool *overlap,
+                     int partIndex, int molIndex, int box, int trials) const {
+    std::vector<int> ov(trials, 0);
+    check(gomcb200_particle_inter(eng_.get(), box, molIndex, partIndex, trials, trialPos.x,
+                                  trialPos.y, trialPos.z, en, real, ov.data()),
+          "ParticleInter");
+    for (int t = 0; t < trials; ++t) overlap[t] |= (ov[t] != 0);
+  }
+  // src/CalculateEnergy.cpp:1365-1406 (uses the resident force buffers and COM)
+  void CalculateTorque(double *tx, double *ty, double *tz, int first, int count, int box) {
+    check(gomcb200_calculate_torque(eng_.get(), box), "CalculateTorque");
+    if (tx || ty || tz)
+      check(gomcb200_get_forces(eng_.get(), GOMCB200_MOL_TORQUE, tx, ty, tz, first, count),
+            "CalculateTorque download");
+  }
+  void ResetForce(int) {}  // implicit: BoxForce overwrites every atom of the box
+
+private:
+  EngineB200 &eng_;
+};
+
+// ---------------------------------------------------------------------------
+// Ewald: the ~30 virtuals of src/Ewald.h:46-179 that are on the hot path.
+class Ewald {
+public:
+  Ewald(EngineB200 &eng, const double *alpha, const double *recip_rcut, int boxTotal)
+      : eng_(eng), alpha_(alpha, alpha + boxTotal), recipRcut_(recip_rcut, recip_rcut + boxTotal),
+        sysPotRecip_(boxTotal, 0.0) {}
+  virtual ~Ewald() {}
+
+  // Ewald::AllocMem (src/Ewald.cpp:141-188): excess = 1.0 NVT/GCMC, 1.25 GEMC, 1.5 NPT
+  virtual void AllocMem(const std::vector<XYZ> &axes, double excess) {
+    check(gomcb200_init_ewald(eng_.get(), 0, recipRcut_.data()), "InitEwaldVariablesCUDA");
+    int imageTotal = 0;
+    for (size_t b = 0; b < axes.size(); ++b) {
+      double a[3] = {axes[b].x, axes[b].y, axes[b].z};
+      int n = 0;
+      check(gomcb200_recip_count(eng_.get(), (int)b, a, excess, &n), "RecipCountInit");
+      imageTotal = n > imageTotal ? n : imageTotal;
+    }
+    check(gomcb200_init_ewald(eng_.get(), imageTotal, recipRcut_.data()), "InitEwaldVariablesCUDA");
+  }
+  virtual void RecipInit(int box, const XYZ &axis) {  // src/Ewald.cpp:644 -> :847
+    double a[3] = {axis.x, axis.y, axis.z};
+    int n = 0, kmax = 0;
+    check(gomcb200_recip_init(eng_.get(), box, a, &n, &kmax), "RecipInit");
+  }
+  virtual void BoxReciprocalSetup(int box, const XYZView &molCoords) {  // :193
+    eng_.SetCoordinates(molCoords);
+    check(gomcb200_box_reciprocal_setup(eng_.get(), box, &currentEnergyRecip_), "BoxReciprocalSetup");
+  }
+  virtual void BoxReciprocalSums(int box, const XYZView &molCoords) {  // :281
+    eng_.SetCoordinates(molCoords);
+    check(gomcb200_box_reciprocal_sums(eng_.get(), box, &currentEnergyRecip_), "BoxReciprocalSums");
+  }
+  virtual double BoxReciprocal(int box, bool isNewVolume) const {  // :375
+    double e = 0.0;
+    check(gomcb200_box_reciprocal(eng_.get(), box, isNewVolume, &e), "BoxReciprocal");
+    return e;
+  }
+  // returns E_new - sysPotRef.boxEnergy[box].recip, src/Ewald.cpp:409-473
+  virtual double MolReciprocal(const XYZView &molCoords, int molIndex, int box) {
+    double e = 0.0;
+    check(gomcb200_mol_reciprocal(eng_.get(), box, molIndex, molCoords.x, molCoords.y,
+                                  molCoords.z, &e),
+          "CallMolReciprocalGPU");
+    return e - sysPotRecip_[box];
+  }
+  virtual double SwapDestRecip(const XYZView &newMolCoords, int box, int molIndex) {  // :478
+    double e = 0.0;
+    check(gomcb200_swap_reciprocal(eng_.get(), box, molIndex, newMolCoords.x, newMolCoords.y,
+                                   newMolCoords.z, 1, &e),
+          "CallSwapReciprocalGPU");
+    return e - sysPotRecip_[box];
+  }
+  virtual double SwapSourceRecip(const XYZView &oldMolCoords, int box, int molIndex) {  // :657
+    double e = 0.0;
+    check(gomcb200_swap_reciprocal(eng_.get(), box, molIndex, oldMolCoords.x, oldMolCoords.y,
+                                   oldMolCoords.z, 0, &e),
+          "CallSwapReciprocalGPU");
+    return e - sysPotRecip_[box];
+  }
+  // src/Ewald.cpp:1311-1335: O(a^2) per molecule, host arithmetic as in both
+  // reference builds.  minImage handled by the caller's unwrapped trial molecule.
+  virtual double SwapCorrection(const XYZView &molCoords, int molIndex, int box,
+                                const XYZ &axis) const {
+    const int start = eng_.MolStart(molIndex), len = eng_.MolLength(molIndex);
+    double correction = 0.0;
+    for (int i = 0; i < len; ++i)
+      for (int j = i + 1; j < len; ++j) {
+        double dx = MinImageSigned(molCoords.x[i] - molCoords.x[j], axis.x);
+        double dy = MinImageSigned(molCoords.y[i] - molCoords.y[j], axis.y);
+        double dz = MinImageSigned(molCoords.z[i] - molCoords.z[j], axis.z);
+        double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+        correction -= eng_.Charge(start + i) * eng_.Charge(start + j) *
+                      std::erf(alpha_[box] * dist) / dist;
+      }
+    return 167103.208067979 * correction;  // num::qqFact
+  }
+  virtual double SwapSelf(int molIndex, int box) const {  // src/Ewald.cpp:1375-1391
+    const int start = eng_.MolStart(molIndex), len = eng_.MolLength(molIndex);
+    double en_self = 0.0;
+    for (int i = 0; i < len; ++i) en_self -= eng_.Charge(start + i) * eng_.Charge(start + i);
+    return en_self * alpha_[box] * 167103.208067979 * 1.12837916709551257390 * 0.5;
+  }
+  virtual void BoxSelfAndCorrection(int box, double &self, double &correction) const {
+    check(gomcb200_box_self_correction(eng_.get(), box, &self, &correction), "BoxSelf");
+  }
+  virtual void BoxForceReciprocal(double *rFx, double *rFy, double *rFz, double *mFx,
+                                  double *mFy, double *mFz, int nAtoms, int nMols, int box) {
+    check(gomcb200_box_force_reciprocal(eng_.get(), box), "CallBoxForceReciprocalGPU");
+    if (rFx || rFy || rFz)
+      check(gomcb200_get_forces(eng_.get(), GOMCB200_ATOM_FORCE_REC, rFx, rFy, rFz, 0, nAtoms),
+            "BoxForceReciprocal download");
+    if (mFx || mFy || mFz)
+      check(gomcb200_get_forces(eng_.get(), GOMCB200_MOL_FORCE_REC, mFx, mFy, mFz, 0, nMols),
+            "BoxForceReciprocal download");
+  }
+  // accept / reject state machine, src/Ewald.cpp:1021-1053, :1420-1487
+  virtual void SetRecipRef(int box) { check(gomcb200_set_recip_ref(eng_.get(), box), "SetRecipRef"); }
+  virtual void UpdateRecip(int box) { check(gomcb200_update_recip(eng_.get(), box), "UpdateRecip"); }
+  virtual void CopyRecip(int box) { check(gomcb200_copy_recip(eng_.get(), box), "CopyRecip"); }
+  virtual void UpdateRecipVec(int box) {
+    check(gomcb200_update_recip_vec(eng_.get(), box), "UpdateRecipVec");
+  }
+  virtual void RestoreMol(int) {}      // non-cached Ewald: nothing to restore
+  virtual void exgMolCache() {}
+  virtual void backupMolCache() {}
+  // sysPotRef.boxEnergy[box].recip, kept by the caller's SystemPotential
+  void SetSysPotRecip(int box, double recip) { sysPotRecip_[box] = recip; }
+
+protected:
+  static double MinImageSigned(double raw, double ax) {  // src/BoxDimensions.h:169-175
+    double half = ax * 0.5;
+    if (raw > half) raw -= ax;
+    else if (raw < -half) raw += ax;
+    return raw;
+  }
+  EngineB200 &eng_;
+  std::vector<double> alpha_, recipRcut_, sysPotRecip_;
+  mutable double currentEnergyRecip_ = 0.0;
+};
+
+// EwaldCached (src/EwaldCached.h:11): the 4*M*imageTotal*8 B per-molecule cos/sin
+// cache is a CPU optimisation.  On B200 recomputing the old position's a*nk sincos
+// is cheaper than streaming the cache, so the cached class shares every kernel
+// with Ewald and its cache-maintenance entry points are no-ops; results agree
+// with the reference's cached path to rounding (tests/test_host_mirror_gpu.py).
+class EwaldCached : public Ewald {
+public:
+  using Ewald::Ewald;
+  void RestoreMol(int) override {}
+  void exgMolCache() override {}
+  void backupMolCache() override {}
+};
+
+// NoEwald (src/NoEwald.h): every reciprocal term is zero.
+class NoEwald : public Ewald {
+public:
+  using Ewald::Ewald;
+  void AllocMem(const std::vector<XYZ> &, double) override {}
+  void RecipInit(int, const XYZ &) override {}
+  void BoxReciprocalSetup(int, const XYZView &) override {}
+  void BoxReciprocalSums(int, const XYZView &) override {}
+  double BoxReciprocal(int, bool) const override { return 0.0; }
+  double MolReciprocal(const XYZView &, int, int) override { return 0.0; }
+  double SwapDestRecip(const XYZView &, int, int) override { return 0.0; }
+  double SwapSourceRecip(const XYZView &, int, int) override { return 0.0; }
+  double SwapCorrection(const XYZView &, int, int, const XYZ &) const override { return 0.0; }
+  double SwapSelf(int, int) const override { return 0.0; }
+  void BoxSelfAndCorrection(int, double &self, double &correction) const override {
+    self = correction = 0.0;
+  }
+  void BoxForceReciprocal(double *, double *, double *, double *, double *, double *, int, int,
+                          int) override {}
+  void SetRecipRef(int) override {}
+  void UpdateRecip(int) override {}
+  void CopyRecip(int) override {}
+  void UpdateRecipVec(int) override {}
+};
+
+}  // namespace gomc_b200

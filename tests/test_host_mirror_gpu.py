@@ -1,0 +1,111 @@
+"""GPU test of the C++ host mirror (gomc_b200/host/GomcB200.h): a compiled driver
+uses the reference-named classes (CalculateEnergy, EwaldCached, NoEwald) the way
+System::Init and Translate::CalcEn/Accept do; results are checked against the
+oracle replaying the same accepted-move sequence."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from gomc_b200 import synth
+from tests.helpers import box_atoms, box_mols, oracle_for, random_move
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "gomc_b200", "host", "host_mirror_test")
+TOL = 1e-9
+
+
+def _write(path, s, moves):
+    sig, eps, nn = s.ff.tables()
+    with open(path, "wb") as f:
+        f.write(struct.pack("<6i", s.n_atoms, s.n_mols, len(s.ff.type_names), s.ff.vdw_kind,
+                            int(s.ff.ewald), len(moves)))
+        f.write(np.array([s.ff.r_cut, s.ff.r_cut_coulomb, s.ff.r_cut_low, s.ff.r_switch,
+                          s.ff.alpha, s.ff.recip_rcut, *s.axis], dtype="<f8").tobytes())
+        for a in (sig, eps, nn, s.x, s.y, s.z, s.charge, *s.com()):
+            f.write(np.asarray(a, dtype="<f8").tobytes())
+        for a in (s.kind, s.mol, s.mol_start):
+            f.write(np.asarray(a, dtype="<i4").tobytes())
+        for m, (nx, ny, nz) in moves:
+            f.write(struct.pack("<i", m))
+            for a in (nx, ny, nz):
+                f.write(np.asarray(a, dtype="<f8").tobytes())
+
+
+@pytest.mark.parametrize("name", ["spce", "argon"])
+def test_host_mirror_move_sequence(tmp_path, name):
+    assert os.path.exists(EXE), "run __graft_entry__.build()"
+    s = synth.make_spce(343, r_cut=8.0) if name == "spce" else synth.make_argon(500, r_cut=8.0)
+    o = oracle_for(s)
+    rng = np.random.default_rng(17)
+    x, y, z = s.x.copy(), s.y.copy(), s.z.copy()
+    moves = []
+    for t in range(8):
+        m = int(rng.integers(s.n_mols))
+        s.x, s.y, s.z = x, y, z          # random_move reads the current coordinates
+        moves.append((m, random_move(s, rng, m, 0.35)))
+        # the driver accepts every non-overlapping move: mirror that below
+        sl = slice(s.mol_start[m], s.mol_start[m + 1])
+        ba = box_atoms(s)
+        ba = ba[(ba < s.mol_start[m]) | (ba >= s.mol_start[m + 1])]
+        _, _, ov = o.molecule_inter(x, y, z, s.kind, s.mol, s.charge, ba, m, s.mol_start[m],
+                                    sl.stop - sl.start, *moves[-1][1])
+        if not ov:
+            x, y, z = x.copy(), y.copy(), z.copy()
+            x[sl], y[sl], z[sl] = moves[-1][1]
+    s = synth.make_spce(343, r_cut=8.0) if name == "spce" else synth.make_argon(500, r_cut=8.0)
+    inp = tmp_path / "in.bin"
+    _write(str(inp), s, moves)
+    out = subprocess.run([EXE, str(inp)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    r = json.loads(out.stdout)
+
+    # initial SystemTotal pieces
+    lj, re = o.box_inter(s.x, s.y, s.z, s.kind, s.mol, s.charge, box_atoms(s))
+    assert abs(r["inter"] - lj) <= TOL * abs(lj)
+    if s.ff.ewald:
+        kx, ky, kz, hs, pf, _ = o.recip_init_orth()
+        sR, sI = o.box_recip_sums(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge, kx, ky, kz)
+        assert abs(r["real"] - re) <= TOL * abs(re)
+        assert abs(r["recip"] - o.box_reciprocal(sR, sI, pf)) <= TOL * abs(r["recip"])
+        assert abs(r["self"] - o.box_self(box_mols(s), s.mol_start, s.charge)) <= TOL * abs(r["self"])
+        co = o.box_correction(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge)
+        assert abs(r["correction"] - co) <= TOL * abs(co)
+    else:
+        assert r["recip"] == 0.0 and r["self"] == 0.0
+
+    # replay the trial / accept sequence with the oracle
+    x, y, z = s.x.copy(), s.y.copy(), s.z.copy()
+    for (m, (nx, ny, nz)), g in zip(moves, r["moves"]):
+        sl = slice(s.mol_start[m], s.mol_start[m + 1])
+        ba = box_atoms(s)
+        ba = ba[(ba < s.mol_start[m]) | (ba >= s.mol_start[m + 1])]
+        dlj, dre, ov = o.molecule_inter(x, y, z, s.kind, s.mol, s.charge, ba, m,
+                                        s.mol_start[m], sl.stop - sl.start, nx, ny, nz)
+        assert g["mol"] == m and bool(g["overlap"]) == ov
+        assert abs(g["dLJ"] - dlj) <= TOL * max(abs(dlj), 1.0)
+        assert abs(g["dReal"] - dre) <= TOL * max(abs(dre), 1.0)
+        if s.ff.ewald:
+            assert abs(g["swapCorr"] - o.swap_correction(s.charge[sl], (nx, ny, nz))) \
+                <= TOL * abs(g["swapCorr"])
+            assert abs(g["swapSelf"] - o.swap_self(s.charge[sl])) <= TOL * abs(g["swapSelf"])
+            if not ov:
+                sR0, sI0 = o.box_recip_sums(box_mols(s), s.mol_start, x, y, z, s.charge, kx, ky, kz)
+                e_new, _, _ = o.mol_reciprocal(s.charge[sl], (x[sl], y[sl], z[sl]), (nx, ny, nz),
+                                               kx, ky, kz, pf, sR0, sI0)
+                d_ref = e_new - o.box_reciprocal(sR0, sI0, pf)
+                assert abs(g["dRecip"] - d_ref) <= 1e-9 * abs(e_new)
+        if not ov:
+            x, y, z = x.copy(), y.copy(), z.copy()
+            x[sl], y[sl], z[sl] = nx, ny, nz
+    # running sums stay consistent with a recomputation (RecalculateAndCheck, far tighter
+    # than the reference's 1e-3)
+    for k in ("inter", "real", "recip"):
+        a, b = r["running"][k], r["recomputed"][k]
+        assert abs(a - b) <= 1e-9 * max(abs(b), 1.0), k
+    lj2, re2 = o.box_inter(x, y, z, s.kind, s.mol, s.charge, box_atoms(s))
+    assert abs(r["recomputed"]["inter"] - lj2) <= TOL * abs(lj2)
