@@ -233,7 +233,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gomc_b200 import engine as eng
+    from gomc_b200 import engine as eng, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -259,7 +259,6 @@ def main():
     out = [C.c_double(), C.c_double(), C.c_double()]
     outp = [C.byref(o) for o in out]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    red = torch.zeros(3, dtype=torch.float64, device="cuda")
 
     def step(host):
         if host:
@@ -269,11 +268,8 @@ def main():
             rc = e.L.gomcb200_call_full_box_energy(e.h, 0, None, None, None, *outp)
         if rc:
             raise RuntimeError(e.L.gomcb200_last_error().decode())
-        if world > 1:   # the path's only exchange: three partial energies
-            red.copy_(torch.tensor([o.value for o in out], dtype=torch.float64))
-            dist.all_reduce(red)
-            return red.tolist()
-        return [o.value for o in out]
+        # the path's only exchange: three partial energies (NCCL all-reduce)
+        return shard.allreduce_energies([o.value for o in out], world, "cuda")
 
     def timed(host, k):
         tot, dom, wall = [], [], []
@@ -310,10 +306,8 @@ def main():
     ms_res = float(np.mean(dev_ms if world == 1 else wall_ms))
     ms_e2e = float(np.mean(wall_ms_h))
     ms_dom = float(np.mean(dom_ms))
-    if world > 1:
-        t = torch.tensor([ms_res, ms_e2e, ms_dom], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_res, ms_e2e, ms_dom = t.tolist()
+    ms_res, ms_e2e, ms_dom = (shard.max_over_ranks(v, world, "cuda")
+                              for v in (ms_res, ms_e2e, ms_dom))
 
     if rank == 0:
         peak = fp64_peak()
