@@ -287,13 +287,19 @@ def main():
             dom.append(b)
         return np.array(tot), np.array(dom), np.array(wall), en
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step(False)
         step(True)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # nvidia-smi needs ~1 s to deliver its first sample: keep the GPU under the same
+    # load until it does, so that the clocks are those of the timed region
+    t_wait = time.perf_counter()
+    while rank == 0 and not sampler.lines and time.perf_counter() - t_wait < 5.0:
+        step(False)
+    sampler.lines.clear()
     l0 = e.launch_count()
     dev_ms, dom_ms, wall_ms, en_res = timed(False, args.steps)
     l1 = e.launch_count()

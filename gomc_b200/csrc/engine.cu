@@ -79,7 +79,8 @@ struct KSet {
   // DMMA plan (recip_mma.cuh)
   DevBuf<int4> mmaRows, mmaTiles, mmaSegs;
   DevBuf<int> mmaCtaSeg;
-  std::vector<int4> hMmaTiles;
+  std::vector<int4> hMmaTiles, hRowsSorted;
+  int tilesForShard = -1;
   int mmaZS = 0;
   bool mmaValid = false;
   int itemsForAtoms = -1, itemsForShard = -1, nCtas = 0, maxSlabs = 0, itemsAT = 0;
@@ -443,43 +444,66 @@ int build_plan(gomcb200_engine *e, KSet &ks, std::vector<RowRec> &rows) {
     CK(cudaStreamSynchronize(e->stream));
   }
   ks.planValid = true;
-  // ---- DMMA plan: 128-row tiles over the cmax-sorted rows, column blocks of 40
-  {
-    std::vector<int4> mrows;
-    for (const RowRec &rw : rows) mrows.push_back(make_int4(rw.a, rw.b, rw.cmax, rw.start));
-    while (mrows.size() % kMmaRows) mrows.push_back(make_int4(0, 0, -1, 0));
-    const int KZ1 = ks.nmax[2] + 1;
-    const int colBlocks = (KZ1 + 4 * kMmaMaxNT - 1) / (4 * kMmaMaxNT);
-    ks.hMmaTiles.clear();
-    for (int cb = 0; cb < colBlocks; ++cb) {
-      const int c0 = cb * 4 * kMmaMaxNT;
-      for (size_t rb = 0; rb < mrows.size(); rb += kMmaRows) {
-        int cmaxT = mrows[rb].z;  // rows are sorted: first row has the largest cmax
-        if (cmaxT < c0) break;
-        int need = std::min(cmaxT - c0 + 1, 4 * kMmaMaxNT);
-        int NT = std::min(kMmaMaxNT, (need + 3) / 4);
-        ks.hMmaTiles.push_back(make_int4((int)rb, c0, NT, cmaxT));
-      }
-    }
-    int ZS = colBlocks * 4 * kMmaMaxNT;
-    while (ZS % 8 != 2) ++ZS;  // conflict-free B fragments
-    ks.mmaZS = ZS;
-    CK(ks.mmaRows.reserve(mrows.size() + 1));
-    CK(ks.mmaTiles.reserve(ks.hMmaTiles.size() + 1));
-    CK(cudaMemcpyAsync(ks.mmaRows.p, mrows.data(), mrows.size() * sizeof(int4),
-                       cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(ks.mmaTiles.p, ks.hMmaTiles.data(), ks.hMmaTiles.size() * sizeof(int4),
-                       cudaMemcpyHostToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    ks.mmaValid = !ks.hMmaTiles.empty();
-    ks.itemsForAtoms = -1;
-  }
+  // the DMMA plan is derived from the sorted rows per shard (build_mma_tiles)
+  ks.hRowsSorted.clear();
+  for (const RowRec &rw : rows) ks.hRowsSorted.push_back(make_int4(rw.a, rw.b, rw.cmax, rw.start));
+  ks.mmaValid = !ks.hRowsSorted.empty();
+  ks.itemsForAtoms = -1;
+  ks.tilesForShard = -1;
   return 0;
 }
 
 // Tiles with few columns are bound by their table loads, not by the DMMAs: a
 // chunk of an NT <= kMmaMinCostNT tile costs about as much as one of NT == kMmaMinCostNT.
 constexpr int kMmaMinCostNT = 4;
+
+// DMMA row tiles of THIS rank.  Multi-GPU: a rank owns a contiguous range of the
+// cmax-sorted (a,b) rows, balanced by the number of k-vectors in them, so that
+// every S(k) is complete on exactly one GPU and only scalar energies are
+// exchanged.  Rows are cut into 128-row tiles, columns into blocks of 40.
+int build_mma_tiles(gomcb200_engine *e, KSet &ks) {
+  const int shardKey = e->shardRank * 1024 + e->shardWorld;
+  if (ks.tilesForShard == shardKey) return 0;
+  const size_t nRows = ks.hRowsSorted.size();
+  std::vector<long long> cum(nRows + 1, 0);
+  for (size_t r = 0; r < nRows; ++r) cum[r + 1] = cum[r] + std::max(ks.hRowsSorted[r].z, kMmaMinCostNT * 4) + 4;
+  auto cut = [&](int rk) {
+    long long w = cum[nRows] * rk / e->shardWorld;
+    return (size_t)(std::lower_bound(cum.begin(), cum.end(), w) - cum.begin());
+  };
+  const size_t r0 = e->shardRank == 0 ? 0 : cut(e->shardRank);
+  const size_t r1 = e->shardRank == e->shardWorld - 1 ? nRows : cut(e->shardRank + 1);
+  std::vector<int4> mrows(ks.hRowsSorted.begin() + r0, ks.hRowsSorted.begin() + r1);
+  while (mrows.size() % kMmaRows) mrows.push_back(make_int4(0, 0, -1, 0));
+  const int KZ1 = ks.nmax[2] + 1;
+  const int colBlocks = (KZ1 + 4 * kMmaMaxNT - 1) / (4 * kMmaMaxNT);
+  ks.hMmaTiles.clear();
+  for (int cb = 0; cb < colBlocks; ++cb) {
+    const int c0 = cb * 4 * kMmaMaxNT;
+    for (size_t rb = 0; rb < mrows.size(); rb += kMmaRows) {
+      int cmaxT = mrows[rb].z;  // rows are sorted: first row has the largest cmax
+      if (cmaxT < c0) break;
+      int need = std::min(cmaxT - c0 + 1, 4 * kMmaMaxNT);
+      int NT = std::min(kMmaMaxNT, (need + 3) / 4);
+      ks.hMmaTiles.push_back(make_int4((int)rb, c0, NT, cmaxT));
+    }
+  }
+  int ZS = colBlocks * 4 * kMmaMaxNT;
+  while (ZS % 8 != 2) ++ZS;  // conflict-free B fragments
+  ks.mmaZS = ZS;
+  CK(ks.mmaRows.reserve(mrows.size() + 1));
+  CK(ks.mmaTiles.reserve(ks.hMmaTiles.size() + 1));
+  if (!mrows.empty())
+    CK(cudaMemcpyAsync(ks.mmaRows.p, mrows.data(), mrows.size() * sizeof(int4),
+                       cudaMemcpyHostToDevice, e->stream));
+  if (!ks.hMmaTiles.empty())
+    CK(cudaMemcpyAsync(ks.mmaTiles.p, ks.hMmaTiles.data(), ks.hMmaTiles.size() * sizeof(int4),
+                       cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  ks.tilesForShard = shardKey;
+  ks.itemsForAtoms = -1;
+  return 0;
+}
 
 // Work split of the DMMA kernel.  The job is a line of (tile, atom chunk) units,
 // unit weight = NT of the tile + 1 (A-tile generation); this rank takes its
@@ -488,6 +512,8 @@ constexpr int kMmaMinCostNT = 4;
 // chunkEnd, slab}; slab numbers the segments of a tile on this rank.
 int build_mma_segments(gomcb200_engine *e, KSet &ks, int nAt, int AT) {
   const int shardKey = e->shardRank * 1024 + e->shardWorld;
+  int rcT = build_mma_tiles(e, ks);
+  if (rcT) return rcT;
   if (ks.itemsForAtoms == nAt && ks.itemsForShard == shardKey && ks.itemsAT == AT) return 0;
   const int nT = (int)ks.hMmaTiles.size();
   const long long nChunks = std::max(1, (nAt + AT - 1) / AT);
@@ -495,7 +521,7 @@ int build_mma_segments(gomcb200_engine *e, KSet &ks, int nAt, int AT) {
   auto weight = [&](int t) { return (long long)std::max(ks.hMmaTiles[t].z, kMmaMinCostNT) + 1; };
   for (int t = 0; t < nT; ++t) prefix[t + 1] = prefix[t] + weight(t) * nChunks;
   const long long W = prefix[nT];
-  const long long w0 = W * e->shardRank / e->shardWorld, w1 = W * (e->shardRank + 1) / e->shardWorld;
+  const long long w0 = 0, w1 = W;  // the rank's tiles are its whole line
   const int nCtas = (int)std::max<long long>(1, std::min<long long>(e->numSMs, (w1 - w0 + 10) / 11));
   std::vector<int4> segs;
   std::vector<int> ctaSeg(1, 0);
@@ -510,12 +536,12 @@ int build_mma_segments(gomcb200_engine *e, KSet &ks, int nAt, int AT) {
   };
   int tPrev; long long cPrev;
   locate(w0, tPrev, cPrev);
-  if (e->shardRank == 0) { tPrev = 0; cPrev = 0; }
+  tPrev = 0; cPrev = 0;
   for (int i = 1; i <= nCtas; ++i) {
     int tEnd; long long cEnd;
     if (i == nCtas) {
       locate(w1, tEnd, cEnd);
-      if (e->shardRank == e->shardWorld - 1) { tEnd = nT; cEnd = 0; }
+      tEnd = nT; cEnd = 0;
     } else {
       locate(w0 + (w1 - w0) * i / nCtas, tEnd, cEnd);
     }
@@ -615,6 +641,8 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
   int nSlabs = 1;
   if (e->timing) cudaEventRecord(e->ev[2], e->stream);
   if (e->recipAlgo == 2 && ks.mmaValid && nAt > 0) {
+    rc = build_mma_tiles(e, ks);  // (re)derives tiles and ZS for the current shard
+    if (rc) return rc;
     MmaArgs ma;
     ma.rows = ks.mmaRows.p;
     ma.tiles = ks.mmaTiles.p;
@@ -1432,21 +1460,10 @@ int gomcb200_set_recip_ref(gomcb200_engine *e, int box) {
     dst.maxRows = src.maxRows;
     dst.planValid = true;
   }
-  dst.mmaValid = false;
-  if (src.mmaValid) {
-    CK(dst.mmaRows.reserve(src.mmaRows.cap));
-    CK(dst.mmaTiles.reserve(src.mmaTiles.cap));
-    CK(cudaMemcpyAsync(dst.mmaRows.p, src.mmaRows.p,
-                       std::min(src.mmaRows.cap, dst.mmaRows.cap) * sizeof(int4),
-                       cudaMemcpyDeviceToDevice, e->stream));
-    CK(cudaMemcpyAsync(dst.mmaTiles.p, src.mmaTiles.p,
-                       std::min(src.mmaTiles.cap, dst.mmaTiles.cap) * sizeof(int4),
-                       cudaMemcpyDeviceToDevice, e->stream));
-    dst.hMmaTiles = src.hMmaTiles;
-    dst.mmaZS = src.mmaZS;
-    dst.mmaValid = true;
-    dst.itemsForAtoms = -1;
-  }
+  dst.hRowsSorted = src.hRowsSorted;
+  dst.mmaValid = src.mmaValid;
+  dst.tilesForShard = -1;
+  dst.itemsForAtoms = -1;
   CK(cudaStreamSynchronize(e->stream));
   return 0;
 }

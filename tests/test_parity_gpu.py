@@ -214,3 +214,34 @@ def test_accept_state_machine(case):
     e.set_molecule_coords(m, *old)
     e.box_reciprocal_sums(0)
     e.update_recip(0)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_partials_sum_to_full(case, world):
+    """Multi-GPU sharding, emulated on one GPU: the partial energies of the ranks
+    add up to the unsharded result and every S(k) is owned by exactly one rank."""
+    s, e, o = case
+    lj0, re0, rc0 = e.call_full_box_energy(0)
+    fR, fI = (e.get_recip_sums(0, eng.SUM_NEW, e.nk) if _ewald(s) else (None, None))
+    lj = re = rc = 0.0
+    owned = np.zeros(e.nk, dtype=np.int32)
+    try:
+        for r in range(world):
+            e.set_shard(r, world)
+            a, b, c = e.call_full_box_energy(0)
+            lj, re, rc = lj + a, re + b, rc + c
+            if _ewald(s):
+                pR, pI = e.get_recip_sums(0, eng.SUM_NEW, e.nk)
+                mine = (pR != 0.0) | (pI != 0.0)
+                owned += mine
+                assert np.array_equal(pR[mine], fR[mine]) and np.array_equal(pI[mine], fI[mine])
+    finally:
+        e.set_shard(0, 1)
+    assert abs(lj - lj0) <= 1e-12 * abs(lj0)
+    assert abs(re - re0) <= 1e-12 * max(abs(re0), 1.0)
+    if _ewald(s):
+        assert abs(rc - rc0) <= 1e-12 * abs(rc0)
+        assert owned.max() <= 1
+        # k-vectors with S(k) == 0 exactly are indistinguishable from "not owned"
+        assert np.count_nonzero(owned == 0) <= np.count_nonzero((fR == 0.0) & (fI == 0.0))
+    e.call_full_box_energy(0)
