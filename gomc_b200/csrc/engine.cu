@@ -79,7 +79,8 @@ struct KSet {
   // DMMA plan (recip_mma.cuh)
   DevBuf<int4> mmaRows, mmaTiles, mmaSegs;
   DevBuf<int> mmaCtaSeg;
-  std::vector<int4> hMmaTiles, hRowsSorted;
+  std::vector<int4> hMmaTiles, hRowsSorted, hSegs;
+  std::vector<int> hCtaSeg;
   int tilesForShard = -1;
   int mmaZS = 0;
   bool mmaValid = false;
@@ -517,46 +518,44 @@ int build_mma_segments(gomcb200_engine *e, KSet &ks, int nAt, int AT) {
   if (ks.itemsForAtoms == nAt && ks.itemsForShard == shardKey && ks.itemsAT == AT) return 0;
   const int nT = (int)ks.hMmaTiles.size();
   const long long nChunks = std::max(1, (nAt + AT - 1) / AT);
-  std::vector<long long> prefix(nT + 1, 0);  // weight before tile t
-  auto weight = [&](int t) { return (long long)std::max(ks.hMmaTiles[t].z, kMmaMinCostNT) + 1; };
-  for (int t = 0; t < nT; ++t) prefix[t + 1] = prefix[t] + weight(t) * nChunks;
-  const long long W = prefix[nT];
-  const long long w0 = 0, w1 = W;  // the rank's tiles are its whole line
-  const int nCtas = (int)std::max<long long>(1, std::min<long long>(e->numSMs, (w1 - w0 + 10) / 11));
+  // measured cost model (profiles/r1g_mma_cost_model.txt, clock64 per CTA, AT = 24):
+  // cycles = sum_segments [ 44400 + chunks * cost(NT) ]; few-column tiles are
+  // bound by their table loads (floor ~3000 cycles per chunk)
+  static const long long kChunkCycles[11] = {3000, 3000, 3320, 3785, 4235, 4830,
+                                             5547, 6298, 7096, 7806, 8632};
+  auto chunkCost = [&](int t) {
+    return kChunkCycles[std::min(10, std::max(0, ks.hMmaTiles[t].z))] * AT / 24;
+  };
+  const long long segCost = 44400;
+  long long total = 0;
+  for (int t = 0; t < nT; ++t) total += chunkCost(t) * nChunks + segCost;
+  const int nCtas = (int)std::max<long long>(1, std::min<long long>(e->numSMs, total / (8 * segCost) + 1));
+  const long long target = (total + segCost * nCtas) / nCtas;
   std::vector<int4> segs;
   std::vector<int> ctaSeg(1, 0);
   std::vector<int> slabOfTile(nT, 0);
-  // position on the line -> (tile, chunk): chunks of tile t have weight wt each
-  auto locate = [&](long long w, int &t, long long &chunk) {
-    t = (int)(std::upper_bound(prefix.begin(), prefix.end(), w) - prefix.begin()) - 1;
-    if (t >= nT) { t = nT; chunk = 0; return; }
-    long long wt = weight(t);
-    chunk = (w - prefix[t] + wt / 2) / wt;  // round to the nearest chunk boundary
-    if (chunk >= nChunks) { ++t; chunk = 0; }
-  };
-  int tPrev; long long cPrev;
-  locate(w0, tPrev, cPrev);
-  tPrev = 0; cPrev = 0;
-  for (int i = 1; i <= nCtas; ++i) {
-    int tEnd; long long cEnd;
-    if (i == nCtas) {
-      locate(w1, tEnd, cEnd);
-      tEnd = nT; cEnd = 0;
-    } else {
-      locate(w0 + (w1 - w0) * i / nCtas, tEnd, cEnd);
+  long long acc = 0;
+  int cta = 0;
+  for (int t = 0; t < nT; ++t) {
+    long long c = 0;
+    const long long w = chunkCost(t);
+    while (c < nChunks) {
+      acc += segCost;
+      long long room = target - acc;
+      long long take = std::max(1LL, (room + w / 2) / w);
+      if (cta == nCtas - 1) take = nChunks - c;  // the last CTA takes what is left
+      take = std::min(take, nChunks - c);
+      segs.push_back(make_int4(t, (int)c, (int)(c + take), slabOfTile[t]++));
+      acc += take * w;
+      c += take;
+      if (acc + w / 2 >= target && cta < nCtas - 1) {
+        ctaSeg.push_back((int)segs.size());
+        ++cta;
+        acc = 0;
+      }
     }
-    int t = tPrev; long long c = cPrev;
-    while (t < tEnd || (t == tEnd && c < cEnd)) {
-      long long ce = (t == tEnd) ? cEnd : nChunks;
-      if (ce > c) segs.push_back(make_int4(t, (int)c, (int)ce, slabOfTile[t]++));
-      ++t;
-      c = 0;
-      if (t > tEnd) break;
-    }
-    ctaSeg.push_back((int)segs.size());
-    tPrev = tEnd;
-    cPrev = cEnd;
   }
+  while ((int)ctaSeg.size() < nCtas + 1) ctaSeg.push_back((int)segs.size());
   int maxSlabs = 1;
   for (int t = 0; t < nT; ++t) maxSlabs = std::max(maxSlabs, slabOfTile[t]);
   CK(ks.mmaSegs.reserve(segs.size() + 1));
@@ -567,6 +566,8 @@ int build_mma_segments(gomcb200_engine *e, KSet &ks, int nAt, int AT) {
   CK(cudaMemcpyAsync(ks.mmaCtaSeg.p, ctaSeg.data(), ctaSeg.size() * sizeof(int),
                      cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  ks.hSegs = segs;
+  ks.hCtaSeg = ctaSeg;
   ks.nCtas = nCtas;
   ks.maxSlabs = maxSlabs;
   ks.itemsForAtoms = nAt;
@@ -651,7 +652,8 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     ma.XYS = ma.KX1 + KY1;
     ma.ZS = ks.mmaZS;
     size_t budget = e->smemOptin > 8192 ? e->smemOptin - 2048 : 0;
-    size_t perAtom = 2 * (size_t)(ma.XYS + ma.ZS + kMmaRS) * sizeof(double2);
+    size_t perAtom = 2 * (size_t)(ma.XYS + ma.ZS) * sizeof(double2) +
+                     2 * (size_t)kMmaWarps * kMmaAWS;
     int AT = (int)std::min<size_t>(32, budget / perAtom) & ~3;
     if (AT < 4) return fail(GOMCB200_EINVAL, "k range too large for the DMMA kernel");
     ma.AT = AT;
@@ -677,8 +679,28 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     CK(cudaMemsetAsync(e->part.p, 0, sizeof(double) * (size_t)nSlabs * 2 * nkStride, e->stream));
     size_t smem = perAtom * AT;
     CK(cudaFuncSetAttribute(k_recip_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const bool dbg = getenv("GOMCB200_DEBUG_MMA") != nullptr;
+    DevBuf<long long> dbgBuf;
+    ma.ctaCycles = nullptr;
+    if (dbg) {
+      CK(dbgBuf.reserve(ks.nCtas + 1));
+      ma.ctaCycles = dbgBuf.p;
+    }
     k_recip_mma<<<ks.nCtas, kMmaThreads, smem, e->stream>>>(ma, e->part.p);
     e->launches += 2;
+    if (dbg) {
+      std::vector<long long> cyc(ks.nCtas);
+      std::vector<int4> hs(ks.hSegs);
+      CK(cudaStreamSynchronize(e->stream));
+      CK(cudaMemcpy(cyc.data(), dbgBuf.p, sizeof(long long) * ks.nCtas, cudaMemcpyDeviceToHost));
+      for (int c = 0; c < ks.nCtas; ++c) {
+        fprintf(stderr, "MMADBG cta %d cycles %lld segs", c, cyc[c]);
+        for (int sg = ks.hCtaSeg[c]; sg < ks.hCtaSeg[c + 1]; ++sg)
+          fprintf(stderr, " [NT=%d chunks=%d]", ks.hMmaTiles[hs[sg].x].z, hs[sg].z - hs[sg].y);
+        fprintf(stderr, "\n");
+      }
+      dbgBuf.release();
+    }
   } else if (e->recipAlgo >= 1 && ks.planValid && ks.nTiles > 0 && nAt > 0) {
     FactArgs fa;
     fa.rows = ks.rows.p;

@@ -24,7 +24,9 @@
 //   * software pipeline: while the warps issue the DMMAs of chunk c they also
 //     build the A tile (complex products X^a Y^b) of chunk c+1 into the other
 //     buffer -- one element per thread per k4 step -- so the FP64 MMA pipe never
-//     waits for operand generation; one __syncthreads per chunk;
+//     waits for operand generation.  The A tile is private to the warp that
+//     consumes it and table buffers are recycled by "last warp done refills",
+//     so there is no CTA-wide barrier in steady state;
 //   * each warp owns 8 (a,b) rows x up to 40 c columns = MT(2) x NT(<=10) m8n8
 //     accumulator tiles (80 registers).
 // Partials per slab go to part[slab][re/im][k]; k_recip_finish sums them in slab
@@ -40,7 +42,8 @@ constexpr int kMmaMT = 2;                      // m8 tiles per warp: 8 (a,b) row
 constexpr int kMmaRowsPerWarp = kMmaMT * 4;    // 8
 constexpr int kMmaRows = kMmaWarps * kMmaRowsPerWarp;  // 128 rows per tile
 constexpr int kMmaMaxNT = 10;                  // n8 tiles per column block: 40 c
-constexpr int kMmaRS = kMmaRows + 2;           // A tile row stride (double2), % 8 == 2
+constexpr int kMmaAWS = 160;  // bytes per atom of a warp's private A tile: 8 rows x 16 B + pad
+                              // (stride 20 doubles == 4 mod 16: conflict-free A fragments)
 
 struct MmaArgs {
   const int4 *rows;    // {a, b, cmax, start}, sorted by cmax descending, padded
@@ -54,6 +57,7 @@ struct MmaArgs {
   int ZS;              // Z row stride (double2), ZS % 8 == 2, >= 40 * colBlocks
   int AT;              // atoms per chunk (multiple of 4)
   int nkStride;
+  long long *ctaCycles;  // optional per-CTA clock64 duration (work-split calibration)
 };
 
 // ---- phase tables ----------------------------------------------------------
@@ -193,12 +197,15 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[kMmaMT][kMmaMaxNT][2], u
 __global__ void __launch_bounds__(kMmaThreads, 1)
     k_recip_mma(MmaArgs ma, double *__restrict__ part) {
   extern __shared__ __align__(16) unsigned char dynSmem[];
-  __shared__ __align__(8) unsigned long long mbarStore[4];  // XY0, XY1, Z0, Z1
+  __shared__ __align__(8) unsigned long long mbarStore[4];  // "full": XY0, XY1, Z0, Z1
+  __shared__ int doneCnt[4];  // warps finished with XY0, XY1, Z0, Z1 ("empty" side)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long tStart = clock64();
   const int AT = ma.AT, XYS = ma.XYS, ZS = ma.ZS;
   const unsigned xyBytes = (unsigned)(AT * XYS * 16), zBytes = (unsigned)(AT * ZS * 16);
-  const unsigned aBytes = (unsigned)(AT * kMmaRS * 16);
+  const unsigned aWarpBytes = (unsigned)(AT * kMmaAWS);
+  const unsigned aBytes = aWarpBytes * kMmaWarps;
   const unsigned smBase = smem_u32(dynSmem);
   // buffer / barrier addresses are computed, not indexed (keeps them in registers)
   auto xyBufAt = [&](int i) { return smBase + (unsigned)i * xyBytes; };
@@ -214,13 +221,35 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
       mbar_init(barXYAt(i), 1);
       mbar_init(barZAt(i), 1);
     }
+    for (int i = 0; i < 4; ++i) doneCnt[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // A-generation role of this thread: row r of the tile, atoms g, g+4, ...
-  const int genRow = tid & (kMmaRows - 1), genG = tid >> 7;
+  // A-generation role of this lane: one of the warp's own 8 rows, atoms g, g+4, ...
+  // (the A tile is private to the warp: no CTA-wide barrier in steady state)
+  const int genRow = warp * kMmaRowsPerWarp + (lane & 7), genG = lane >> 3;
   const int nK4 = AT / 4;
+  const unsigned aWarpOff = (unsigned)warp * aWarpBytes;
+
+  // "empty" signalling: every warp reports when it is done with a table buffer;
+  // the last one to report refills it through the TMA unit.
+  auto arriveAndRefill = [&](int which, unsigned dstBuf, unsigned bar, const double2 *src,
+                             unsigned bytes, bool more) {
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      int old = atomicAdd(&doneCnt[which], 1);
+      if (old == kMmaWarps - 1) {
+        atomicExch(&doneCnt[which], 0);
+        if (more) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(bar, bytes);
+          bulk_g2s(dstBuf, src, bytes, bar);
+        }
+      }
+    }
+  };
 
   const int segBegin = ma.ctaSeg[blockIdx.x], segEnd = ma.ctaSeg[blockIdx.x + 1];
   for (int sIdx = segBegin; sIdx < segEnd; ++sIdx) {
@@ -240,16 +269,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
 #pragma unroll
       for (int nt = 0; nt < kMmaMaxNT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    // ---- prologue: XY(0), Z(0), XY(1) in flight; build A(0) ----------------
+    // ---- prologue: XY(0), XY(1), Z(0), Z(1) in flight; build A(0) ----------
+    const double2 *xySrc = ma.tabXY + (size_t)chunk0 * AT * XYS;
+    const double2 *zSrc = ma.tabZ + (size_t)chunk0 * AT * ZS;
     if (tid == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(barXYAt(0), xyBytes);
-      bulk_g2s(xyBufAt(0), ma.tabXY + (size_t)chunk0 * AT * XYS, xyBytes, barXYAt(0));
-      mbar_expect_tx(barZAt(0), zBytes);
-      bulk_g2s(zBufAt(0), ma.tabZ + (size_t)chunk0 * AT * ZS, zBytes, barZAt(0));
-      if (nChunks > 1) {
-        mbar_expect_tx(barXYAt(1), xyBytes);
-        bulk_g2s(xyBufAt(1), ma.tabXY + (size_t)(chunk0 + 1) * AT * XYS, xyBytes, barXYAt(1));
+      for (int i = 0; i < 2 && i < nChunks; ++i) {
+        mbar_expect_tx(barXYAt(i), xyBytes);
+        bulk_g2s(xyBufAt(i), xySrc + (size_t)i * AT * XYS, xyBytes, barXYAt(i));
+        mbar_expect_tx(barZAt(i), zBytes);
+        bulk_g2s(zBufAt(i), zSrc + (size_t)i * AT * ZS, zBytes, barZAt(i));
       }
     }
     mbar_wait(barXYAt(0), phaseBits & 1u);
@@ -257,27 +286,14 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
     for (int j = 0; j < nK4; ++j) {
       int at = 4 * j + genG;
       agen_one(xyBufAt(0) + (unsigned)(at * XYS) * 16u, offX, offY, ysign,
-               aBufAt(0) + (unsigned)(at * kMmaRS + genRow) * 16u);
+               aBufAt(0) + aWarpOff + (unsigned)(at * kMmaAWS) + (unsigned)((lane & 7) * 16));
     }
-    __syncthreads();
+    // XY[0] is free once every warp has built its A(0): refill with XY(2)
+    arriveAndRefill(0, xyBufAt(0), barXYAt(0), xySrc + (size_t)2 * AT * XYS, xyBytes,
+                    2 < nChunks);
 
     for (int c = 0; c < nChunks; ++c) {
       const int cur = c & 1, nxt = cur ^ 1;
-      if (tid == 0) {
-        // buffers xy[cur] (A(c) was built from it) and z[nxt] (MMA c-1 read it)
-        // are free since the barrier that ended iteration c-1
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (c + 2 < nChunks) {
-          mbar_expect_tx(barXYAt(cur), xyBytes);
-          bulk_g2s(xyBufAt(cur), ma.tabXY + (size_t)(chunk0 + c + 2) * AT * XYS, xyBytes,
-                   barXYAt(cur));
-        }
-        if (c + 1 < nChunks) {
-          mbar_expect_tx(barZAt(nxt), zBytes);
-          bulk_g2s(zBufAt(nxt), ma.tabZ + (size_t)(chunk0 + c + 1) * AT * ZS, zBytes,
-                   barZAt(nxt));
-        }
-      }
       const bool genNext = c + 1 < nChunks;
       mbar_wait(barZAt(cur), (phaseBits >> (2 + cur)) & 1u);
       phaseBits ^= 1u << (2 + cur);
@@ -286,14 +302,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
         phaseBits ^= 1u << nxt;
       }
       // lane fragment addresses: A[k = lane&3][m = lane>>2], B[k = lane&3][n = lane>>2]
-      const unsigned aAddr = aBufAt(cur) + (unsigned)((lane & 3) * kMmaRS * 16) +
-                             (unsigned)(warp * kMmaRowsPerWarp * 16) + (unsigned)((lane >> 2) * 8);
+      const unsigned aAddr = aBufAt(cur) + aWarpOff + (unsigned)((lane & 3) * kMmaAWS) +
+                             (unsigned)((lane >> 2) * 8);
       const unsigned zAddr = zBufAt(cur) + (unsigned)((lane & 3) * ZS * 16) + (unsigned)(c0 * 16) +
                              (unsigned)((lane >> 2) * 8);
-      const unsigned aStep = 4u * kMmaRS * 16u, zStep = 4u * (unsigned)ZS * 16u;
+      const unsigned aStep = 4u * kMmaAWS, zStep = 4u * (unsigned)ZS * 16u;
       const unsigned xyNext = xyBufAt(nxt) + (unsigned)(genG * XYS) * 16u;
       const unsigned xyStep = 4u * (unsigned)XYS * 16u;
-      const unsigned aNext = aBufAt(nxt) + (unsigned)(genG * kMmaRS + genRow) * 16u;
+      const unsigned aNext = aBufAt(nxt) + aWarpOff + (unsigned)(genG * kMmaAWS) +
+                             (unsigned)((lane & 7) * 16);
+      __syncwarp();  // A(c) was written by this warp's lanes in the previous iteration
 #define MMA_CASE(N)                                                                       \
   case N:                                                                                 \
     mma_chunk<N>(acc, aAddr, zAddr, nK4, aStep, zStep, genNext, xyNext, xyStep, offX, offY, \
@@ -307,7 +325,12 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
                         offY, ysign, aNext, aStep);
       }
 #undef MMA_CASE
-      __syncthreads();
+      // this warp is done with Z[cur] (DMMAs of chunk c) and XY[nxt] (A(c+1) built)
+      arriveAndRefill(2 + cur, zBufAt(cur), barZAt(cur), zSrc + (size_t)(c + 2) * AT * ZS, zBytes,
+                      c + 2 < nChunks);
+      if (genNext)
+        arriveAndRefill(nxt, xyBufAt(nxt), barXYAt(nxt), xySrc + (size_t)(c + 3) * AT * XYS,
+                        xyBytes, c + 3 < nChunks);
     }
 
     // ---- epilogue: exchange Ar*/Ai* partners (lane ^ 4), write S(a,b,+-c) ------
@@ -351,6 +374,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1)
     }
     __syncthreads();  // tile A / table buffers are reused by the next segment
   }
+  if (ma.ctaCycles && tid == 0) ma.ctaCycles[blockIdx.x] = clock64() - tStart;
 }
 
 }  // namespace gb

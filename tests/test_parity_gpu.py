@@ -234,7 +234,10 @@ def test_sharded_partials_sum_to_full(case, world):
                 pR, pI = e.get_recip_sums(0, eng.SUM_NEW, e.nk)
                 mine = (pR != 0.0) | (pI != 0.0)
                 owned += mine
-                assert np.array_equal(pR[mine], fR[mine]) and np.array_equal(pI[mine], fI[mine])
+                # same k, different atom-slab split: equal up to summation order
+                scale = max(np.max(np.abs(fR)), np.max(np.abs(fI)))
+                assert np.max(np.abs(pR[mine] - fR[mine])) <= 1e-12 * scale
+                assert np.max(np.abs(pI[mine] - fI[mine])) <= 1e-12 * scale
     finally:
         e.set_shard(0, 1)
     assert abs(lj - lj0) <= 1e-12 * abs(lj0)
