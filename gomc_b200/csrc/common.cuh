@@ -164,6 +164,16 @@ __device__ __forceinline__ void calc_coulomb_en_vir(const BoxParams &p,
   }
 }
 
+// 32-bit shared-window addressing: explicit LDS/STS instead of generic LD/ST.
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
 // Fixed-order warp and block reductions (deterministic).
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

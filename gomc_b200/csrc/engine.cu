@@ -309,7 +309,7 @@ int run_pair(gomcb200_engine *e, int b, bool force) {
   // shared-memory staging of the neighbour cells (40 B per atom)
   const int nWarps = force ? kWarpsForce : kWarpsEnergy;
   const size_t queueBytes = sizeof(WarpQueue) * nWarps;
-  size_t staticSmem = 4 * 1024 + queueBytes;
+  size_t staticSmem = 12 * 1024 + queueBytes;
   size_t capAtoms = (e->smemOptin > staticSmem ? (e->smemOptin - staticSmem) : 0) / 40;
   double avg = (double)bx.nAtoms / nCells;
   size_t want = (size_t)((force ? 27.0 : 14.0) * avg * 1.4) + 96;

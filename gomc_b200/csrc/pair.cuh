@@ -143,79 +143,123 @@ __device__ __forceinline__ void eval_pair(const BoxParams &p, int ki, double qi,
   }
 }
 
+// Where the j atoms live: global arrays, or their shared-memory staging given as
+// 32-bit shared-window addresses (so that the loads are LDS, not generic LD).
+struct JArrays {
+  const double *x, *y, *z, *q;
+  const int2 *km;
+  unsigned sx, sy, sz, sq, skm;
+};
+template <bool SM>
+__device__ __forceinline__ double jload(const double *g, unsigned s, int j) {
+  return SM ? lds_f64(s + (unsigned)j * 8u) : g[j];
+}
+template <bool SM>
+__device__ __forceinline__ int2 jload_km(const int2 *g, unsigned s, int j) {
+  if (SM) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(s + (unsigned)j * 8u));
+    return v;
+  }
+  return g[j];
+}
+
 // One warp, one position (xi,yi,zi), ranges[rangeFirst::rangeStride].
 //  SWEEP_PROBE: position is not part of the j set; every in-range j counts.
 //  SWEEP_HALF : energy-only half shell; in the self range only j > selfIndex.
 //  SWEEP_FULL : all neighbours, own force; energy counted for jGlobal > iGlobal.
 // selfIndex is in the index space of the self range; iGlobal the global sorted
-// index of the atom.
-template <int VDW, bool FORCE, int SWEEP>
+// index of the atom.  SM: j arrays staged in shared memory.  GEN: at least one
+// axis has fewer than 4 cells (per-pair minimum image on that axis).
+// qBase: shared address of this warp's WarpQueue.
+template <int VDW, bool FORCE, int SWEEP, bool SM, bool GEN>
 __device__ __forceinline__ void warp_probe(
     const BoxParams &p, const int generic[3], double xi, double yi, double zi,
     int ki, double qi, int excludeMol, int selfIndex, int iGlobal, double sign,
     bool checkOverlap, const JRange *ranges, int nRanges, int rangeStride,
-    int rangeFirst, const double *__restrict__ jx,
-    const double *__restrict__ jy, const double *__restrict__ jz,
-    const double *__restrict__ jq, const int2 *__restrict__ jkm, WarpQueue &wq,
-    PairAcc &acc) {
+    int rangeFirst, const JArrays &ja, unsigned qBase, PairAcc &acc) {
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
+  const unsigned qJ = qBase, qX = qBase + 4u * kQueue, qY = qX + 8u * kQueue,
+                 qZ = qY + 8u * kQueue;
   int head = 0, count = 0;
-  for (int r = rangeFirst; r < nRanges; r += rangeStride) {
-    const JRange rg = ranges[r];
-    for (int base = rg.begin; base < rg.end; base += 32) {
-      int j = base + lane;
-      bool in = false;
-      int jEnc = j;
-      double dx = 0.0, dy = 0.0, dz = 0.0;
-      bool valid = j < rg.end;
-      if (SWEEP == SWEEP_HALF) valid = valid && !(rg.isSelf && j <= selfIndex);
-      if (SWEEP == SWEEP_FULL) valid = valid && !(rg.isSelf && j == selfIndex);
-      if (valid) {
-        dx = (xi - jx[j]) + rg.sx;
-        dy = (yi - jy[j]) + rg.sy;
-        dz = (zi - jz[j]) + rg.sz;
+
+  auto test = [&](const JRange &rg, int j, bool &in, int &jEnc, double &dx, double &dy,
+                  double &dz) {
+    in = false;
+    jEnc = j;
+    bool valid = j < rg.end;
+    if (SWEEP == SWEEP_HALF) valid = valid && !(rg.isSelf && j <= selfIndex);
+    if (SWEEP == SWEEP_FULL) valid = valid && !(rg.isSelf && j == selfIndex);
+    if (valid) {
+      dx = (xi - jload<SM>(ja.x, ja.sx, j)) + rg.sx;
+      dy = (yi - jload<SM>(ja.y, ja.sy, j)) + rg.sy;
+      dz = (zi - jload<SM>(ja.z, ja.sz, j)) + rg.sz;
+      if (GEN) {
         if (generic[0]) dx = min_image(dx, p.ax[0], p.half[0]);
         if (generic[1]) dy = min_image(dy, p.ax[1], p.half[1]);
         if (generic[2]) dz = min_image(dz, p.ax[2], p.half[2]);
-        double r2 = dist_sq(dx, dy, dz);
-        in = p.boxRcutSq > r2;  // BoxDimensions::InRcut, strict
-        if (SWEEP == SWEEP_FULL && (rg.gbase + (j - rg.begin)) > iGlobal)
-          jEnc |= 0x40000000;  // this side of the pair owns the energy
       }
-      unsigned m = __ballot_sync(0xffffffffu, in);
-      if (in) {
-        int pos = (head + count + __popc(m & ltMask)) & (kQueue - 1);
-        wq.j[pos] = jEnc;
-        wq.dx[pos] = dx;
-        wq.dy[pos] = dy;
-        wq.dz[pos] = dz;
+      double r2 = dist_sq(dx, dy, dz);
+      in = p.boxRcutSq > r2;  // BoxDimensions::InRcut, strict
+      if (SWEEP == SWEEP_FULL && (rg.gbase + (j - rg.begin)) > iGlobal)
+        jEnc |= 0x40000000;  // this side of the pair owns the energy
+    }
+  };
+  auto push = [&](bool in, int jEnc, double dx, double dy, double dz) {
+    unsigned m = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      unsigned pos = (unsigned)((head + count + __popc(m & ltMask)) & (kQueue - 1));
+      asm volatile("st.shared.s32 [%0], %1;" ::"r"(qJ + pos * 4u), "r"(jEnc) : "memory");
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(qX + pos * 8u), "d"(dx) : "memory");
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(qY + pos * 8u), "d"(dy) : "memory");
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(qZ + pos * 8u), "d"(dz) : "memory");
+    }
+    count += __popc(m);
+  };
+  auto drain = [&](bool active) {
+    if (active) {
+      unsigned pos = (unsigned)((head + lane) & (kQueue - 1));
+      int je;
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(je) : "r"(qJ + pos * 4u));
+      int jj = je & 0x3fffffff;
+      double ddx = lds_f64(qX + pos * 8u), ddy = lds_f64(qY + pos * 8u),
+             ddz = lds_f64(qZ + pos * 8u);
+      eval_pair<VDW, FORCE>(p, ki, qi, excludeMol, SWEEP != SWEEP_FULL || (je & 0x40000000),
+                            sign, checkOverlap, ddx, ddy, ddz, jload<SM>(ja.q, ja.sq, jj),
+                            jload_km<SM>(ja.km, ja.skm, jj), acc);
+    }
+  };
+
+  for (int r = rangeFirst; r < nRanges; r += rangeStride) {
+    const JRange rg = ranges[r];
+    for (int base = rg.begin; base < rg.end; base += 64) {
+      // two candidates per lane per round: halves the loop / queue bookkeeping
+      bool in0, in1;
+      int e0, e1;
+      double ax0 = 0, ay0 = 0, az0 = 0, ax1 = 0, ay1 = 0, az1 = 0;
+      test(rg, base + lane, in0, e0, ax0, ay0, az0);
+      test(rg, base + 32 + lane, in1, e1, ax1, ay1, az1);
+      push(in0, e0, ax0, ay0, az0);
+      if (count >= 32) {
+        __syncwarp();
+        drain(true);
+        head = (head + 32) & (kQueue - 1);
+        count -= 32;
+        __syncwarp();
       }
-      count += __popc(m);
+      push(in1, e1, ax1, ay1, az1);
       __syncwarp();
       if (count >= 32) {
-        int pos = (head + lane) & (kQueue - 1);
-        int je = wq.j[pos];
-        int jj = je & 0x3fffffff;
-        double ddx = wq.dx[pos], ddy = wq.dy[pos], ddz = wq.dz[pos];
-        eval_pair<VDW, FORCE>(p, ki, qi, excludeMol,
-                              SWEEP != SWEEP_FULL || (je & 0x40000000), sign,
-                              checkOverlap, ddx, ddy, ddz, jq[jj], jkm[jj], acc);
+        drain(true);
         head = (head + 32) & (kQueue - 1);
         count -= 32;
         __syncwarp();
       }
     }
   }
-  if (lane < count) {
-    int pos = (head + lane) & (kQueue - 1);
-    int je = wq.j[pos];
-    int jj = je & 0x3fffffff;
-    eval_pair<VDW, FORCE>(p, ki, qi, excludeMol,
-                          SWEEP != SWEEP_FULL || (je & 0x40000000), sign,
-                          checkOverlap, wq.dx[pos], wq.dy[pos], wq.dz[pos],
-                          jq[jj], jkm[jj], acc);
-  }
+  __syncwarp();
+  drain(lane < count);
   __syncwarp();
 }
 
@@ -253,6 +297,7 @@ __device__ __forceinline__ int build_ranges(const CellGrid &g,
   return n;
 }
 
+constexpr int kMaxIPerPass = 512;  // i-atoms of a cell slice handled per pass
 constexpr int kPairThreads = 256;
 constexpr int kPairWarps = kPairThreads / 32;
 
@@ -274,8 +319,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
   extern __shared__ __align__(16) unsigned char dynSmem[];
   __shared__ JRange ranges[27];
   __shared__ JRange stagedRanges[27];
-  __shared__ double red[2][NWARPS];
-  __shared__ int nRangesSh;
+  __shared__ double enLJ[kMaxIPerPass], enReal[kMaxIPerPass];
+  __shared__ int nRangesSh, nextI;
   // dynamic smem: per-warp hit queues, then the staged neighbour atoms
   WarpQueue *queues = reinterpret_cast<WarpQueue *>(dynSmem);
   unsigned char *stageBase = dynSmem + sizeof(WarpQueue) * NWARPS;
@@ -292,11 +337,17 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
   __syncthreads();
   const int nRanges = nRangesSh;
 
-  const double *jx = sx, *jy = sy, *jz = sz, *jq = sq;
-  const int2 *jkm = skm;
+  JArrays ja = {sx, sy, sz, sq, skm, 0u, 0u, 0u, 0u, 0u};
   int selfOffset = 0;  // self-range index = global sorted index + selfOffset
   const JRange *useRanges = ranges;
+  // stage only if this CTA's neighbourhood fits (else the global-memory path)
+  bool staged = false;
   if (useSmem && iEnd > iBegin) {
+    int tot = 0;
+    for (int r = 0; r < nRanges; ++r) tot += ranges[r].end - ranges[r].begin;
+    staged = tot <= smemAtoms;
+  }
+  if (staged) {
     double *smx = reinterpret_cast<double *>(stageBase);
     double *smy = smx + smemAtoms;
     double *smz = smy + smemAtoms;
@@ -322,47 +373,77 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
       if (rg.isSelf) selfOffset = off - rg.begin;
       off += len;
     }
-    jx = smx; jy = smy; jz = smz; jq = smq; jkm = smkm;
+    ja.sx = smem_u32(smx); ja.sy = smem_u32(smy); ja.sz = smem_u32(smz);
+    ja.sq = smem_u32(smq); ja.skm = smem_u32(smkm);
     useRanges = stagedRanges;
   }
-  __syncthreads();
+  const unsigned qBase = smem_u32(queues + warp);
+  const bool anyGeneric = g.generic[0] | g.generic[1] | g.generic[2];
+  constexpr int SW = FORCE ? SWEEP_FULL : SWEEP_HALF;
 
-  double eLJ = 0.0, eReal = 0.0;
-  for (int i = iBegin + warp; i < iEnd; i += NWARPS) {
-    PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
-    double xi = sx[i], yi = sy[i], zi = sz[i], qi = sq[i];
-    int2 kmi = skm[i];
-    warp_probe<VDW, FORCE, FORCE ? SWEEP_FULL : SWEEP_HALF>(
-        p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y, i + selfOffset, i, 1.0,
-        false, useRanges, nRanges, 1, 0, jx, jy, jz, jq, jkm, queues[warp],
-        acc);
-    eLJ += acc.lj;
-    eReal += acc.real;
-    if (FORCE) {
-      double f0 = warp_sum(acc.fx), f1 = warp_sum(acc.fy), f2 = warp_sum(acc.fz);
+  // i-atoms are handed to the warps dynamically (no tail inside the CTA); per-atom
+  // energies go to shared memory and are summed in atom order, so the result does
+  // not depend on which warp took which atom.
+  double blockLJ = 0.0, blockReal = 0.0;
+  for (int pass0 = iBegin; pass0 < iEnd; pass0 += kMaxIPerPass) {
+    const int passEnd = min(iEnd, pass0 + kMaxIPerPass);
+    if (threadIdx.x == 0) nextI = pass0;
+    __syncthreads();
+    for (;;) {
+      int i = 0;
+      if (lane == 0) i = atomicAdd(&nextI, 1);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      if (i >= passEnd) break;
+      PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
+      double xi = sx[i], yi = sy[i], zi = sz[i], qi = sq[i];
+      int2 kmi = skm[i];
+      if (staged) {
+        if (anyGeneric)
+          warp_probe<VDW, FORCE, SW, true, true>(p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y,
+                                                 i + selfOffset, i, 1.0, false, useRanges,
+                                                 nRanges, 1, 0, ja, qBase, acc);
+        else
+          warp_probe<VDW, FORCE, SW, true, false>(p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y,
+                                                  i + selfOffset, i, 1.0, false, useRanges,
+                                                  nRanges, 1, 0, ja, qBase, acc);
+      } else {
+        warp_probe<VDW, FORCE, SW, false, true>(p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y,
+                                                i + selfOffset, i, 1.0, false, useRanges,
+                                                nRanges, 1, 0, ja, qBase, acc);
+      }
+      double e0 = warp_sum(acc.lj), e1 = warp_sum(acc.real);
+      if (FORCE) {
+        double f0 = warp_sum(acc.fx), f1 = warp_sum(acc.fy), f2 = warp_sum(acc.fz);
+        if (lane == 0) {
+          int a = sortedAtoms[i];
+          fx[a] = f0;
+          fy[a] = f1;
+          fz[a] = f2;
+        }
+      }
       if (lane == 0) {
-        int a = sortedAtoms[i];
-        fx[a] = f0;
-        fy[a] = f1;
-        fz[a] = f2;
+        enLJ[i - pass0] = e0;
+        enReal[i - pass0] = e1;
       }
     }
-  }
-  eLJ = warp_sum(eLJ);
-  eReal = warp_sum(eReal);
-  if (lane == 0) {
-    red[0][warp] = eLJ;
-    red[1][warp] = eReal;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0.0, b = 0.0;
-    for (int w = 0; w < NWARPS; ++w) {
-      a += red[0][w];
-      b += red[1][w];
+    __syncthreads();
+    // fixed-order sum of the per-atom energies of this pass (warp 0, tree of 32)
+    if (warp == 0) {
+      double a = 0.0, b = 0.0;
+      for (int t = lane; t < passEnd - pass0; t += 32) {
+        a += enLJ[t];
+        b += enReal[t];
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      blockLJ += a;
+      blockReal += b;
     }
-    partLJ[blockIdx.x] = a;
-    partReal[blockIdx.x] = b;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partLJ[blockIdx.x] = blockLJ;
+    partReal[blockIdx.x] = blockReal;
   }
 }
 
@@ -468,10 +549,11 @@ __global__ void __launch_bounds__(kPairThreads)
   }
   __syncthreads();
   PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
-  warp_probe<VDW, false, SWEEP_PROBE>(
-      p, g.generic, pr.x, pr.y, pr.z, pr.kind, pr.q, excludeMol, -1, -1,
-      pr.sign, pr.checkOverlap != 0, ranges, nRangesSh, kPairWarps, warp, sx,
-      sy, sz, sq, skm, queues[warp], acc);
+  JArrays ja = {sx, sy, sz, sq, skm, 0u, 0u, 0u, 0u, 0u};
+  warp_probe<VDW, false, SWEEP_PROBE, false, true>(
+      p, g.generic, pr.x, pr.y, pr.z, pr.kind, pr.q, excludeMol, -1, -1, pr.sign,
+      pr.checkOverlap != 0, ranges, nRangesSh, kPairWarps, warp, ja, smem_u32(&queues[warp]),
+      acc);
   double a = warp_sum(acc.lj), b = warp_sum(acc.real);
   int ov = __any_sync(0xffffffffu, acc.overlap);
   if (lane == 0) {

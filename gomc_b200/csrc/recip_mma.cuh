@@ -102,9 +102,6 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- PTX helpers -------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) {
-  return (unsigned)__cvta_generic_to_shared(p);
-}
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -142,11 +139,6 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
-}
-__device__ __forceinline__ double lds_f64(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
 }
 __device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
   double2 v;
