@@ -20,6 +20,7 @@
 #include "pair.cuh"
 #include "recip.cuh"
 #include "recip_mma.cuh"
+#include "force_mma.cuh"
 
 using namespace gb;
 
@@ -80,6 +81,12 @@ struct KSet {
   DevBuf<int4> mmaRows, mmaTiles, mmaSegs;
   DevBuf<int> mmaCtaSeg;
   std::vector<int4> hMmaTiles, hRowsSorted, hSegs;
+  // DMMA reciprocal-force plan (force_mma.cuh)
+  DevBuf<int4> fmRows;
+  DevBuf<FmTile> fmTiles;
+  DevBuf<double> fmW;
+  int fmNTiles = 0;
+  bool fmValid = false;
   std::vector<int> hCtaSeg;
   int tilesForShard = -1;
   int mmaZS = 0;
@@ -451,6 +458,35 @@ int build_plan(gomcb200_engine *e, KSet &ks, std::vector<RowRec> &rows) {
   ks.mmaValid = !ks.hRowsSorted.empty();
   ks.itemsForAtoms = -1;
   ks.tilesForShard = -1;
+  // reciprocal-force plan: 16-row tiles of the same sorted rows
+  {
+    std::vector<int4> frows(ks.hRowsSorted);
+    while (frows.size() % kFmRows) frows.push_back(make_int4(0, 0, -1, 0));
+    std::vector<FmTile> ft;
+    size_t wOff = 0;
+    for (size_t rb = 0; rb < frows.size(); rb += kFmRows) {
+      int cmaxT = frows[rb].z;
+      FmTile t;
+      t.rowBegin = (int)rb;
+      t.KT = (2 * (cmaxT + 1) + 3) & ~3;
+      t.wOff = (int)wOff;
+      t.pad = 0;
+      wOff += (size_t)t.KT * kFmWS;
+      ft.push_back(t);
+    }
+    CK(ks.fmRows.reserve(frows.size() + 1));
+    CK(ks.fmTiles.reserve(ft.size() + 1));
+    CK(ks.fmW.reserve(wOff + 16));
+    if (!frows.empty()) {
+      CK(cudaMemcpyAsync(ks.fmRows.p, frows.data(), frows.size() * sizeof(int4),
+                         cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(ks.fmTiles.p, ft.data(), ft.size() * sizeof(FmTile),
+                         cudaMemcpyHostToDevice, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+    }
+    ks.fmNTiles = (int)ft.size();
+    ks.fmValid = !ft.empty();
+  }
   return 0;
 }
 
@@ -947,6 +983,7 @@ int gomcb200_destroy(gomcb200_engine *e) {
       ks.kx.release(); ks.ky.release(); ks.kz.release(); ks.hsqr.release();
       ks.prefact.release(); ks.rows.release(); ks.tiles.release();
       ks.mmaRows.release(); ks.mmaTiles.release(); ks.mmaSegs.release(); ks.mmaCtaSeg.release();
+      ks.fmRows.release(); ks.fmTiles.release(); ks.fmW.release();
     }
     for (auto &s : bx.sum) s.release();
     bx.packed.release();
@@ -1421,14 +1458,68 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
   if (rc) return rc;
   if (bx.nAtoms == 0) return 0;
   BoxParams p = make_params(e, box);
-  k_force_recip_direct<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
-      p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->q.p,
-      ks.n, ks.kx.p, ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p,
-      e->force[2][0].p, e->force[2][1].p, e->force[2][2].p);
+  double *rfx = e->force[2][0].p, *rfy = e->force[2][1].p, *rfz = e->force[2][2].p;
+  bool done = false;
+  if (e->recipAlgo == 2 && ks.fmValid && bx.nCharged > 0 && ks.n > 0) {
+    rc = ensure_packed(e, box);
+    if (rc) return rc;
+    FmArgs fa;
+    fa.tiles = ks.fmTiles.p;
+    fa.rows = ks.fmRows.p;
+    fa.wm = ks.fmW.p;
+    fa.pb = bx.packed.p;
+    fa.chargedAtoms = bx.chargedList.p;
+    fa.nTiles = ks.fmNTiles;
+    fa.nAtoms = bx.nCharged;
+    fa.KX1 = ks.nmax[0] + 1;
+    fa.KY1 = ks.nmax[1] + 1;
+    fa.KZ1 = ks.nmax[2] + 1;
+    int zfs = (2 * fa.KZ1 + 3) & ~3;
+    while (zfs % 16 != 4) zfs += 4;
+    fa.ZFS = zfs;
+    fa.XYS = fa.KX1 + fa.KY1;
+    fa.cvx = ks.cv[0];
+    fa.cvy = ks.cv[1];
+    fa.cvz = ks.cv[2];
+    const size_t wBuf = (size_t)((2 * fa.KZ1 + 3) & ~3) * kFmWS * 8;
+    auto smemFor = [&](int AB) {
+      return (size_t)AB * fa.ZFS * 8 + (size_t)AB * fa.XYS * 16 + 2 * wBuf;
+    };
+    const size_t budget = e->smemOptin > 4096 ? e->smemOptin - 2048 : 0;
+    int AB = smemFor(64) <= budget ? 64 : (smemFor(32) <= budget ? 32 : 0);
+    if (AB) {
+      k_force_wmat<<<ks.fmNTiles, 256, 0, e->stream>>>(ks.fmNTiles, ks.fmTiles.p, ks.fmRows.p,
+                                                      bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p,
+                                                      ks.prefact.p, ks.fmW.p);
+      k_force_recip_intra<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
+          p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->q.p,
+          rfx, rfy, rfz);
+      const int grid = (bx.nCharged + AB - 1) / AB;
+      const size_t smem = smemFor(AB);
+      if (AB == 64) {
+        CK(cudaFuncSetAttribute(k_force_recip_mma<64>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_force_recip_mma<64><<<grid, kFmThreads, smem, e->stream>>>(fa, rfx, rfy, rfz);
+      } else {
+        CK(cudaFuncSetAttribute(k_force_recip_mma<32>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_force_recip_mma<32><<<grid, kFmThreads, smem, e->stream>>>(fa, rfx, rfy, rfz);
+      }
+      e->launches += 3;
+      done = true;
+    }
+  }
+  if (!done) {
+    k_force_recip_direct<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
+        p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->q.p,
+        ks.n, ks.kx.p, ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p,
+        rfx, rfy, rfz);
+    e->launches += 1;
+  }
   k_mol_force<<<(bx.nMols + 255) / 256, 256, 0, e->stream>>>(
       bx.nMols, bx.molList.p, e->molStart.p, e->force[2][0].p, e->force[2][1].p,
       e->force[2][2].p, e->force[3][0].p, e->force[3][1].p, e->force[3][2].p);
-  e->launches += 2;
+  e->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
@@ -1486,6 +1577,20 @@ int gomcb200_set_recip_ref(gomcb200_engine *e, int box) {
   dst.mmaValid = src.mmaValid;
   dst.tilesForShard = -1;
   dst.itemsForAtoms = -1;
+  dst.fmValid = false;
+  if (src.fmValid) {
+    CK(dst.fmRows.reserve(src.fmRows.cap));
+    CK(dst.fmTiles.reserve(src.fmTiles.cap));
+    CK(dst.fmW.reserve(src.fmW.cap));
+    CK(cudaMemcpyAsync(dst.fmRows.p, src.fmRows.p,
+                       std::min(src.fmRows.cap, dst.fmRows.cap) * sizeof(int4),
+                       cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(dst.fmTiles.p, src.fmTiles.p,
+                       std::min(src.fmTiles.cap, dst.fmTiles.cap) * sizeof(FmTile),
+                       cudaMemcpyDeviceToDevice, e->stream));
+    dst.fmNTiles = src.fmNTiles;
+    dst.fmValid = true;
+  }
   CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
