@@ -304,6 +304,28 @@ def main():
     dev_ms, dom_ms, wall_ms, en_res = timed(False, args.steps)
     l1 = e.launch_count()
     dev_ms_h, _, wall_ms_h, en_host = timed(True, args.steps)
+    # secondary metric of BASELINE.json: MultiParticle moves/s = the energy/force work of
+    # MultiParticle::CalcEn (src/moves/MultiParticle.h:414-441): BoxReciprocalSums + BoxForce
+    # + BoxReciprocal + BoxForceReciprocal + torque, coordinates resident (single GPU)
+    mp_ms = None
+    if world == 1 and s.ff.ewald:
+        def mp_step():
+            e.L.gomcb200_mark_coords_changed(e.h)
+            e.box_reciprocal_sums(0)
+            e.box_force(0)
+            e.box_force_reciprocal(0)
+            e.calculate_torque(0)
+            e.get_forces(eng.MOL_TORQUE, 0, 1)      # forces stay on the device; sync point
+        for _ in range(3):
+            mp_step()
+        t_mp = []
+        for _ in range(max(5, args.steps // 2)):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mp_step()
+            t_mp.append((time.perf_counter() - t0) * 1e3)
+        mp_ms = float(np.mean(t_mp))
     clocks = sampler.stop() if rank == 0 else None
 
     # resident: device time of the step (CUDA events on the engine's stream) for
@@ -344,6 +366,11 @@ def main():
                          "peak_source": "tools/fp64_peak DFMA stream measured in this run "
                                         "(MEASURED_PEAKS.json has no FP64 entry)",
                          "dmma_peak": peak.get("dmma_tflops")},
+            "multiparticle": (None if mp_ms is None else {
+                "value": 1e3 / mp_ms, "unit": "MP energy/force evaluations per s",
+                "ms_per_step": mp_ms,
+                "step": "BoxReciprocalSums + BoxForce + BoxReciprocal + BoxForceReciprocal + "
+                        "CalculateTorque (MultiParticle::CalcEn), wall clock incl. launches"}),
             "energies": {"lj": en_res[0], "real": en_res[1], "recip": en_res[2],
                          "host_path_identical": en_res == en_host},
         }

@@ -134,6 +134,10 @@ struct gomcb200_engine {
   int nAtoms = 0, nMols = 0, maxMolLen = 0;
   std::vector<int> hKind, hMol, hMolStart;
   std::vector<double> hCharge;
+  // lazily maintained host mirror of the coordinates (single-molecule moves read
+  // the old positions from it instead of a D2H round trip)
+  std::vector<double> hx, hy, hz;
+  bool mirrorValid = false;
   DevBuf<int> kind, mol, molStart;
   DevBuf<double> x, y, z, q, comx, comy, comz;
   DevBuf<double> force[5][3];
@@ -803,6 +807,20 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
   return 0;
 }
 
+int ensure_mirror(gomcb200_engine *e) {
+  if (e->mirrorValid) return 0;
+  e->hx.resize(e->nAtoms);
+  e->hy.resize(e->nAtoms);
+  e->hz.resize(e->nAtoms);
+  CK(cudaStreamSynchronize(e->stream));
+  size_t bytes = sizeof(double) * (size_t)e->nAtoms;
+  CK(cudaMemcpy(e->hx.data(), e->x.p, bytes, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(e->hy.data(), e->y.p, bytes, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(e->hz.data(), e->z.p, bytes, cudaMemcpyDeviceToHost));
+  e->mirrorValid = true;
+  return 0;
+}
+
 int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
                   const double *ny, const double *nz, int mode, double *out) {
   BoxState &bx = e->box[b];
@@ -818,6 +836,10 @@ int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
   size_t nd = 1 + 7 * (size_t)len;
   rc = stage_reserve(e, nd * sizeof(double));
   if (rc) return rc;
+  if (mode == 0) {
+    rc = ensure_mirror(e);
+    if (rc) return rc;
+  }
   CK(e->molBuf.reserve(nd + 8));
   double *h = e->hStage;
   h[0] = (double)len;
@@ -827,21 +849,12 @@ int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
     m[1] = nx[a];
     m[2] = ny[a];
     m[3] = nz[a];
-    m[4] = m[5] = m[6] = 0.0;
+    m[4] = mode == 0 ? e->hx[s + a] : 0.0;  // old coordinates (host mirror)
+    m[5] = mode == 0 ? e->hy[s + a] : 0.0;
+    m[6] = mode == 0 ? e->hz[s + a] : 0.0;
   }
   CK(cudaMemcpyAsync(e->molBuf.p, h, nd * sizeof(double), cudaMemcpyHostToDevice,
                      e->stream));
-  if (mode == 0) {  // old coordinates are resident: strided device copies
-    CK(cudaMemcpy2DAsync(e->molBuf.p + 1 + 4, 7 * sizeof(double), e->x.p + s,
-                         sizeof(double), sizeof(double), len, cudaMemcpyDeviceToDevice,
-                         e->stream));
-    CK(cudaMemcpy2DAsync(e->molBuf.p + 1 + 5, 7 * sizeof(double), e->y.p + s,
-                         sizeof(double), sizeof(double), len, cudaMemcpyDeviceToDevice,
-                         e->stream));
-    CK(cudaMemcpy2DAsync(e->molBuf.p + 1 + 6, 7 * sizeof(double), e->z.p + s,
-                         sizeof(double), sizeof(double), len, cudaMemcpyDeviceToDevice,
-                         e->stream));
-  }
   const int nBlocks = (nk + 255) / 256;
   CK(e->blockA.reserve(nBlocks + 1024));
   k_mol_recip<<<nBlocks, 256, 7 * len * sizeof(double), e->stream>>>(
@@ -903,10 +916,13 @@ int run_probes(gomcb200_engine *e, int b, int excludeMol, int n, std::vector<dou
     launch_probe<VDW_STD>(e, b, p, excludeMol, n);
   e->launches += 1;
   CK(cudaGetLastError());
-  out.resize(3 * (size_t)n);
-  CK(cudaMemcpyAsync(out.data(), e->probeOut.p, sizeof(double) * 3 * n,
-                     cudaMemcpyDeviceToHost, e->stream));
+  // results come back through the pinned staging area, right after the probes
+  double *hOut = reinterpret_cast<double *>(reinterpret_cast<char *>(e->hStage) +
+                                            sizeof(Probe) * (size_t)n);
+  CK(cudaMemcpyAsync(hOut, e->probeOut.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost,
+                     e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  out.assign(hOut, hOut + 3 * (size_t)n);
   return 0;
 }
 
@@ -1149,6 +1165,13 @@ int gomcb200_set_coords(gomcb200_engine *e, const double *x, const double *y, co
   CK(cudaSetDevice(e->device));
   int rc = upload3(e, e->x, e->y, e->z, x, y, z, first, count, e->nAtoms);
   if (rc) return rc;
+  if (count > 4096) {
+    e->mirrorValid = false;  // refreshed lazily by the next single-molecule call
+  } else if (e->mirrorValid) {
+    memcpy(e->hx.data() + first, x, sizeof(double) * (size_t)count);
+    memcpy(e->hy.data() + first, y, sizeof(double) * (size_t)count);
+    memcpy(e->hz.data() + first, z, sizeof(double) * (size_t)count);
+  }
   mark_coords_dirty(e);
   return 0;
 }
@@ -1224,12 +1247,11 @@ int gomcb200_molecule_inter(gomcb200_engine *e, int box, int molIndex, const dou
     return fail(GOMCB200_EINVAL, "bad arguments");
   CK(cudaSetDevice(e->device));
   const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
-  rc = stage_reserve(e, sizeof(Probe) * 2 * (size_t)len + 6 * sizeof(double) * len);
+  rc = stage_reserve(e, (sizeof(Probe) + 3 * sizeof(double)) * 2 * (size_t)len + 64);
   if (rc) return rc;
-  // old coordinates of the molecule: host mirror is not kept, read them back
-  std::vector<double> ox(len), oy(len), oz(len);
-  rc = gomcb200_get_coords(e, ox.data(), oy.data(), oz.data(), s, len);
+  rc = ensure_mirror(e);  // old coordinates of the molecule
   if (rc) return rc;
+  const double *ox = e->hx.data() + s, *oy = e->hy.data() + s, *oz = e->hz.data() + s;
   Probe *pr = reinterpret_cast<Probe *>(e->hStage);
   for (int a = 0; a < len; ++a) {  // order of src/CalculateEnergy.cpp:590-678
     Probe o = {ox[a], oy[a], oz[a], e->hCharge[s + a], -1.0, e->hKind[s + a], 0, 0};
@@ -1264,7 +1286,7 @@ int gomcb200_particle_inter(gomcb200_engine *e, int box, int molIndex, int partI
   CK(cudaSetDevice(e->device));
   const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
   if (partIndex < 0 || partIndex >= len) return fail(GOMCB200_EINVAL, "partIndex out of range");
-  rc = stage_reserve(e, sizeof(Probe) * (size_t)trials);
+  rc = stage_reserve(e, (sizeof(Probe) + 3 * sizeof(double)) * (size_t)trials + 64);
   if (rc) return rc;
   Probe *pr = reinterpret_cast<Probe *>(e->hStage);
   for (int t = 0; t < trials; ++t) {
