@@ -84,6 +84,8 @@ struct KSet {
   // DMMA reciprocal-force plan (force_mma.cuh)
   DevBuf<int4> fmRows;
   DevBuf<FmTile> fmTiles;
+  DevBuf<FmBlock> fmBlocks;
+  int fmNBlocks = 0;
   DevBuf<double> fmW;
   int fmNTiles = 0;
   bool fmValid = false;
@@ -478,6 +480,24 @@ int build_plan(gomcb200_engine *e, KSet &ks, std::vector<RowRec> &rows) {
       wOff += (size_t)t.KT * kFmWS;
       ft.push_back(t);
     }
+    std::vector<FmBlock> fb;
+    for (const FmTile &t : ft)
+      for (int k0 = 0; k0 < t.KT; k0 += kFmKB) {
+        FmBlock b;
+        b.rowBegin = t.rowBegin;
+        b.k0 = k0;
+        b.kLen = std::min(kFmKB, t.KT - k0);
+        b.wOff = t.wOff + k0 * kFmWS;
+        b.first = k0 == 0;
+        b.last = k0 + kFmKB >= t.KT;
+        b.pad0 = b.pad1 = 0;
+        fb.push_back(b);
+      }
+    CK(ks.fmBlocks.reserve(fb.size() + 1));
+    if (!fb.empty())
+      CK(cudaMemcpyAsync(ks.fmBlocks.p, fb.data(), fb.size() * sizeof(FmBlock),
+                         cudaMemcpyHostToDevice, e->stream));
+    ks.fmNBlocks = (int)fb.size();
     CK(ks.fmRows.reserve(frows.size() + 1));
     CK(ks.fmTiles.reserve(ft.size() + 1));
     CK(ks.fmW.reserve(wOff + 16));
@@ -999,7 +1019,7 @@ int gomcb200_destroy(gomcb200_engine *e) {
       ks.kx.release(); ks.ky.release(); ks.kz.release(); ks.hsqr.release();
       ks.prefact.release(); ks.rows.release(); ks.tiles.release();
       ks.mmaRows.release(); ks.mmaTiles.release(); ks.mmaSegs.release(); ks.mmaCtaSeg.release();
-      ks.fmRows.release(); ks.fmTiles.release(); ks.fmW.release();
+      ks.fmRows.release(); ks.fmTiles.release(); ks.fmW.release(); ks.fmBlocks.release();
     }
     for (auto &s : bx.sum) s.release();
     bx.packed.release();
@@ -1486,6 +1506,8 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
     rc = ensure_packed(e, box);
     if (rc) return rc;
     FmArgs fa;
+    fa.blocks = ks.fmBlocks.p;
+    fa.nBlocks = ks.fmNBlocks;
     fa.tiles = ks.fmTiles.p;
     fa.rows = ks.fmRows.p;
     fa.wm = ks.fmW.p;
@@ -1503,7 +1525,7 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
     fa.cvx = ks.cv[0];
     fa.cvy = ks.cv[1];
     fa.cvz = ks.cv[2];
-    const size_t wBuf = (size_t)((2 * fa.KZ1 + 3) & ~3) * kFmWS * 8;
+    const size_t wBuf = (size_t)kFmKB * kFmWS * 8;
     auto smemFor = [&](int AB) {
       return (size_t)AB * fa.ZFS * 8 + (size_t)AB * fa.XYS * 16 + 2 * wBuf;
     };
@@ -1610,6 +1632,11 @@ int gomcb200_set_recip_ref(gomcb200_engine *e, int box) {
     CK(cudaMemcpyAsync(dst.fmTiles.p, src.fmTiles.p,
                        std::min(src.fmTiles.cap, dst.fmTiles.cap) * sizeof(FmTile),
                        cudaMemcpyDeviceToDevice, e->stream));
+    CK(dst.fmBlocks.reserve(src.fmBlocks.cap));
+    CK(cudaMemcpyAsync(dst.fmBlocks.p, src.fmBlocks.p,
+                       std::min(src.fmBlocks.cap, dst.fmBlocks.cap) * sizeof(FmBlock),
+                       cudaMemcpyDeviceToDevice, e->stream));
+    dst.fmNBlocks = src.fmNBlocks;
     dst.fmNTiles = src.fmNTiles;
     dst.fmValid = true;
   }

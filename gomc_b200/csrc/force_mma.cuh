@@ -33,6 +33,13 @@ struct FmTile {  // per row tile
   int wOff;      // offset (doubles) of the tile's Wm block [KT][kFmWS]
   int pad;
 };
+constexpr int kFmKB = 80;  // k rows per streamed W block (one TMA copy)
+struct FmBlock {  // a tile is streamed as ceil(KT / kFmKB) blocks
+  int rowBegin;   // of the tile
+  int k0, kLen;   // k range of this block (multiples of 4)
+  int wOff;       // offset (doubles) of the block inside Wm
+  int first, last, pad0, pad1;  // first / last block of its tile
+};
 
 // Wm[k][4 r + o] from the structure factor (see header).  One thread per (tile,k,r).
 __global__ void __launch_bounds__(256)
@@ -94,6 +101,8 @@ __global__ void __launch_bounds__(256)
 }
 
 struct FmArgs {
+  const FmBlock *blocks;
+  int nBlocks;
   const FmTile *tiles;
   const int4 *rows;
   const double *wm;
@@ -126,10 +135,8 @@ __global__ void __launch_bounds__(kFmThreads, 1)
   double *zf = reinterpret_cast<double *>(dynSmem);                 // [AB][ZFS]
   double2 *xy = reinterpret_cast<double2 *>(zf + (size_t)AB * fa.ZFS);  // [AB][XYS]
   double *wbuf0 = reinterpret_cast<double *>(xy + (size_t)AB * fa.XYS);
-  const unsigned wBytesMax = (unsigned)(2 * ((fa.KZ1 + 1) / 2 * 2 + 2) * kFmWS * 8);  // generous
-  (void)wBytesMax;
   const unsigned zfAddr = smem_u32(zf), xyAddr = smem_u32(xy), wAddr0 = smem_u32(wbuf0);
-  const unsigned wStrideBuf = (unsigned)(((2 * fa.KZ1 + 3) & ~3) * kFmWS * 8);  // bytes per buffer
+  const unsigned wStrideBuf = (unsigned)(kFmKB * kFmWS * 8);  // bytes per W buffer
   const unsigned bar0 = smem_u32(&mbarStore[0]);
 
   if (tid == 0) {
@@ -163,17 +170,13 @@ __global__ void __launch_bounds__(kFmThreads, 1)
   }
   __syncthreads();
 
-  // first W tile
-  if (tid == 0 && fa.nTiles > 0) {
-    FmTile t0 = fa.tiles[0];
-    unsigned bytes = (unsigned)(t0.KT * kFmWS * 8);
+  // first W block
+  if (tid == 0 && fa.nBlocks > 0) {
+    FmBlock b0 = fa.blocks[0];
+    unsigned bytes = (unsigned)(b0.kLen * kFmWS * 8);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(bar0, bytes);
-    bulk_g2s(wAddr0, fa.wm + t0.wOff, bytes, bar0);
-  }
-  if (tid < kFmRows && fa.nTiles > 0) {
-    int4 rw = fa.rows[fa.tiles[0].rowBegin + tid];
-    rowAB[0][tid] = make_int2(rw.x, rw.y);
+    bulk_g2s(wAddr0, fa.wm + b0.wOff, bytes, bar0);
   }
 
   double fx = 0.0, fy = 0.0, fz = 0.0;  // for atom (8*mtile + lane>>2), this lane's rows
@@ -181,35 +184,34 @@ __global__ void __launch_bounds__(kFmThreads, 1)
   const unsigned aFrag = zfAddr + (unsigned)((myAtom * fa.ZFS + (lane & 3)) * 8);
   const unsigned xyAtom = xyAddr + (unsigned)(myAtom * fa.XYS) * 16u;
   unsigned phase = 0;
+  double acc[NTW][2];
+#pragma unroll
+  for (int nt = 0; nt < NTW; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
 
-  for (int t = 0; t < fa.nTiles; ++t) {
+  for (int t = 0; t < fa.nBlocks; ++t) {
     const int buf = t & 1;
-    const FmTile tl = fa.tiles[t];
-    __syncthreads();  // everyone finished tile t-1: its buffer and rowAB slot are free
-    if (t + 1 < fa.nTiles) {
-      if (tid == 0) {
-        FmTile tn = fa.tiles[t + 1];
-        unsigned bytes = (unsigned)(tn.KT * kFmWS * 8);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar0 + 8u * (buf ^ 1), bytes);
-        bulk_g2s(wAddr0 + (buf ^ 1) * wStrideBuf, fa.wm + tn.wOff, bytes, bar0 + 8u * (buf ^ 1));
-      }
-      if (tid >= 32 && tid < 32 + kFmRows) {
-        int4 rw = fa.rows[fa.tiles[t + 1].rowBegin + (tid - 32)];
-        rowAB[buf ^ 1][tid - 32] = make_int2(rw.x, rw.y);
-      }
+    const FmBlock bl = fa.blocks[t];
+    __syncthreads();  // everyone finished block t-1: its buffer is free
+    if (t + 1 < fa.nBlocks && tid == 0) {
+      FmBlock bn = fa.blocks[t + 1];
+      unsigned bytes = (unsigned)(bn.kLen * kFmWS * 8);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar0 + 8u * (buf ^ 1), bytes);
+      bulk_g2s(wAddr0 + (buf ^ 1) * wStrideBuf, fa.wm + bn.wOff, bytes, bar0 + 8u * (buf ^ 1));
+    }
+    if (bl.first && tid < kFmRows) {  // (a,b) of the tile's rows, read in the contraction
+      int4 rw = fa.rows[bl.rowBegin + tid];
+      rowAB[0][tid] = make_int2(rw.x, rw.y);
     }
     mbar_wait(bar0 + 8u * buf, (phase >> buf) & 1u);
     phase ^= 1u << buf;
 
-    double acc[NTW][2];
-#pragma unroll
-    for (int nt = 0; nt < NTW; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
     const unsigned bFrag = wAddr0 + buf * wStrideBuf +
                            (unsigned)(((lane & 3) * kFmWS + 8 * (npart * NTW) + (lane >> 2)) * 8);
-    const int nK4 = tl.KT >> 2;
+    const unsigned aBlk = aFrag + (unsigned)bl.k0 * 8u;
+    const int nK4 = bl.kLen >> 2;
     for (int k4 = 0; k4 < nK4; ++k4) {
-      double a = lds_f64(aFrag + (unsigned)k4 * 32u);
+      double a = lds_f64(aBlk + (unsigned)k4 * 32u);
       double b[NTW];
 #pragma unroll
       for (int nt = 0; nt < NTW; ++nt)
@@ -217,23 +219,27 @@ __global__ void __launch_bounds__(kFmThreads, 1)
 #pragma unroll
       for (int nt = 0; nt < NTW; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], a, b[nt]);
     }
-    // contraction with A = X^a Y^b: this lane holds (G_r, G_i) of G0 (lane&1 == 0)
-    // or G1 (lane&1 == 1) for row 2*ntGlobal + ((lane&3)>>1) of the tile
+    if (bl.last) {
+      __syncthreads();  // rowAB of this tile visible (written at its first block)
+      // contraction with A = X^a Y^b: this lane holds (G_r, G_i) of G0 (lane&1 == 0)
+      // or G1 (lane&1 == 1) for row 2*ntGlobal + ((lane&3)>>1) of the tile
 #pragma unroll
-    for (int nt = 0; nt < NTW; ++nt) {
-      const int r = 2 * (npart * NTW + nt) + ((lane & 3) >> 1);
-      const int2 ab = rowAB[buf][r];
-      double2 xv = lds_f64x2(xyAtom + (unsigned)ab.x * 16u);
-      const int bb = ab.y < 0 ? -ab.y : ab.y;
-      double2 yv = lds_f64x2(xyAtom + (unsigned)(fa.KX1 + bb) * 16u);
-      if (ab.y < 0) yv.y = -yv.y;
-      const double ar = xv.x * yv.x - xv.y * yv.y, ai = xv.x * yv.y + xv.y * yv.x;
-      const double im = ar * acc[nt][1] + ai * acc[nt][0];
-      if ((lane & 1) == 0) {
-        fx = fma((double)ab.x, im, fx);
-        fy = fma((double)ab.y, im, fy);
-      } else {
-        fz += im;
+      for (int nt = 0; nt < NTW; ++nt) {
+        const int r = 2 * (npart * NTW + nt) + ((lane & 3) >> 1);
+        const int2 ab = rowAB[0][r];
+        double2 xv = lds_f64x2(xyAtom + (unsigned)ab.x * 16u);
+        const int bb = ab.y < 0 ? -ab.y : ab.y;
+        double2 yv = lds_f64x2(xyAtom + (unsigned)(fa.KX1 + bb) * 16u);
+        if (ab.y < 0) yv.y = -yv.y;
+        const double ar = xv.x * yv.x - xv.y * yv.y, ai = xv.x * yv.y + xv.y * yv.x;
+        const double im = ar * acc[nt][1] + ai * acc[nt][0];
+        if ((lane & 1) == 0) {
+          fx = fma((double)ab.x, im, fx);
+          fy = fma((double)ab.y, im, fy);
+        } else {
+          fz += im;
+        }
+        acc[nt][0] = acc[nt][1] = 0.0;
       }
     }
   }
