@@ -15,7 +15,8 @@ constexpr double kQQFact = 167103.208067979;  // lib/NumLib.h:22
 constexpr double kTwoOverSqrtPi = 1.12837916709551257390;  // M_2_SQRTPI
 constexpr double kPi = 3.14159265358979323846;
 
-enum { VDW_STD = 0, VDW_SHIFT = 1, VDW_SWITCH = 2 };
+enum { VDW_STD = 0, VDW_SHIFT = 1, VDW_SWITCH = 2, VDW_EXP6 = 3, VDW_MARTINI = 4 };
+constexpr double kBigNum = 1.7976931348623158e+308;  // num::BIGNUM = DBL_MAX, lib/NumLib.h:15,24
 
 // Per-box constants handed to kernels by value.
 struct BoxParams {
@@ -26,6 +27,11 @@ struct BoxParams {
   int kindCount, vdwKind, ewald, electrostatic;
   const double *sigmaSq, *epsilon_cn, *n, *shiftConst;
   const int *nHalf;  // n/2 when that is an integer in [1,64], else 0
+  // EXP6 tables (FF_EXP6::Init, src/FFExp6.h:99-147), handed in by the host
+  const double *rMin, *expConst, *rMaxSq;
+  // Martini switch (FF_SWITCH_MARTINI::Init, src/FFSwitchMartini.h:121-213)
+  const double *mAn, *mBn, *mCn, *mSign, *mSig6;
+  double rOn, A6, B6, C6, A1, B1, C1, diElectric_1;
 };
 
 __device__ __forceinline__ double min_image(double raw, double ax, double half) {
@@ -65,6 +71,32 @@ template <int VDW>
 __device__ __forceinline__ double calc_en(const BoxParams &p, double r2,
                                           int idx) {
   if (p.rCutSq < r2) return 0.0;
+  if (VDW == VDW_EXP6) {  // src/FFExp6.h:184-224
+    if (r2 < p.rMaxSq[idx]) return kBigNum;
+    double dist = sqrt(r2);
+    double rm = p.rMin[idx];
+    double rRat = rm / dist;
+    double rRat2 = rRat * rRat;
+    double attract = rRat2 * rRat2 * rRat2;
+    double alpha_ij = (double)(unsigned)p.n[idx];  // truncated to uint, FFExp6.h:215
+    double repulse = (6.0 / alpha_ij) * exp(alpha_ij * (1.0 - dist / rm));
+    return p.expConst[idx] * (repulse - attract);
+  }
+  if (VDW == VDW_MARTINI) {  // src/FFSwitchMartini.h:279-302
+    double r_2 = 1.0 / r2;
+    double r_6 = r_2 * r_2 * r_2;
+    double n_ij = p.n[idx];
+    double r_n = pow(r_2, n_ij * 0.5);
+    double rij_ron = sqrt(r2) - p.rOn;
+    double rij_ron_2 = rij_ron * rij_ron;
+    double rij_ron_3 = rij_ron_2 * rij_ron;
+    double rij_ron_4 = rij_ron_2 * rij_ron_2;
+    double An = p.mAn[idx], Bn = p.mBn[idx], Cn = p.mCn[idx];
+    bool sw = r2 > p.rOnSq;
+    double shiftRep = sw ? (-(An / 3.0) * rij_ron_3 - (Bn / 4.0) * rij_ron_4 - Cn) : -Cn;
+    double shiftAtt = sw ? (-(p.A6 / 3.0) * rij_ron_3 - (p.B6 / 4.0) * rij_ron_4 - p.C6) : -p.C6;
+    return p.epsilon_cn[idx] * (p.mSign[idx] * (r_n + shiftRep) - p.mSig6[idx] * (r_6 + shiftAtt));
+  }
   double eps = p.epsilon_cn[idx];
   if (eps == 0.0) return 0.0;  // exact: eps*(finite) == 0
   double rRat2 = p.sigmaSq[idx] / r2;
@@ -87,6 +119,39 @@ __device__ __forceinline__ void calc_en_vir(const BoxParams &p, double r2,
   en = 0.0;
   vir = 0.0;
   if (p.rCutSq < r2) return;
+  if (VDW == VDW_EXP6) {  // src/FFExp6.h:184-257
+    if (r2 < p.rMaxSq[idx]) {
+      en = kBigNum;
+      vir = kBigNum;
+      return;
+    }
+    double dist = sqrt(r2);
+    double rm = p.rMin[idx];
+    double rRat = rm / dist;
+    double rRat2 = rRat * rRat;
+    double attract = rRat2 * rRat2 * rRat2;
+    double alpha_ij = (double)(unsigned)p.n[idx];
+    double ex = exp(alpha_ij * (1.0 - dist / rm));
+    en = p.expConst[idx] * ((6.0 / alpha_ij) * ex - attract);
+    vir = 6.0 * p.expConst[idx] * ((dist / rm) * ex - attract) / r2;
+    return;
+  }
+  if (VDW == VDW_MARTINI) {  // src/FFSwitchMartini.h:279-348 (r_8 = (r^2)^4 as written there)
+    en = calc_en<VDW_MARTINI>(p, r2, idx);
+    double n_ij = p.n[idx];
+    double r_1 = 1.0 / sqrt(r2);
+    double r_8 = r2 * r2 * r2 * r2;
+    double r_n2 = pow(r_1, n_ij + 2.0);
+    double rij_ron = sqrt(r2) - p.rOn;
+    double rij_ron_2 = rij_ron * rij_ron;
+    double rij_ron_3 = rij_ron_2 * rij_ron;
+    bool sw = r2 > p.rOnSq;
+    double dshiftRep = sw ? (p.mAn[idx] * rij_ron_2 + p.mBn[idx] * rij_ron_3) * r_1 : 0.0;
+    double dshiftAtt = sw ? (p.A6 * rij_ron_2 + p.B6 * rij_ron_3) * r_1 : 0.0;
+    vir = p.epsilon_cn[idx] *
+          (p.mSign[idx] * (n_ij * r_n2 + dshiftRep) - p.mSig6[idx] * (6.0 * r_8 + dshiftAtt));
+    return;
+  }
   double eps = p.epsilon_cn[idx];
   if (eps == 0.0) {
     if (VDW == VDW_SHIFT) en = -p.shiftConst[idx];
@@ -122,6 +187,10 @@ __device__ __forceinline__ double calc_coulomb(const BoxParams &p, double r2,
   if (p.rCutCoulombSq < r2) return 0.0;
   double dist = sqrt(r2);
   if (p.ewald) return qq * erfc(p.alpha * dist) / dist;
+  if (VDW == VDW_MARTINI) {  // src/FFSwitchMartini.h:379-396
+    double coul = -(p.A1 / 3.0) * (dist * r2) - (p.B1 / 4.0) * (r2 * r2) - p.C1;
+    return qq * p.diElectric_1 * (1.0 / dist + coul);
+  }
   if (VDW == VDW_SHIFT) return qq * (1.0 / dist - 1.0 / p.rCut);
   if (VDW == VDW_SWITCH) {
     double s = r2 / p.rCutSq - 1.0;
@@ -149,7 +218,12 @@ __device__ __forceinline__ void calc_coulomb_en_vir(const BoxParams &p,
     vir = qq * (ec / dist + (p.alpha * kTwoOverSqrtPi) * ex) / r2;
     return;
   }
-  if (VDW == VDW_SHIFT) {
+  if (VDW == VDW_MARTINI) {  // src/FFSwitchMartini.h:379-396, :440-447
+    double coul = -(p.A1 / 3.0) * (dist * r2) - (p.B1 / 4.0) * (r2 * r2) - p.C1;
+    en = qq * p.diElectric_1 * (1.0 / dist + coul);
+    double virCoul = p.A1 / r2 + p.B1 / (dist * r2);
+    vir = qq * p.diElectric_1 * (1.0 / (dist * r2) + virCoul / dist);
+  } else if (VDW == VDW_SHIFT) {
     en = qq * (1.0 / dist - 1.0 / p.rCut);
     vir = qq / (r2 * dist);
   } else if (VDW == VDW_SWITCH) {

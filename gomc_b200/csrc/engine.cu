@@ -130,6 +130,9 @@ struct gomcb200_engine {
   double rCut = 0, rCutLow = 0, rOn = 0;
   std::vector<double> rCutCoulomb, alpha, recipRcut;
   DevBuf<double> sigmaSq, epsilon_cn, nTab, shiftConst;
+  DevBuf<double> rMin, expConst, rMaxSq, mAn, mBn, mCn, mSign, mSig6;
+  double mA6 = 0, mB6 = 0, mC6 = 0, mA1 = 0, mB1 = 0, mC1 = 0, diElectric_1 = 1.0;
+  bool haveExp6 = false;
   DevBuf<int> nHalf;
   // topology
   bool haveTopo = false;
@@ -192,6 +195,18 @@ BoxParams make_params(const gomcb200_engine *e, int b) {
   p.n = e->nTab.p;
   p.shiftConst = e->shiftConst.p;
   p.nHalf = e->nHalf.p;
+  p.rMin = e->rMin.p;
+  p.expConst = e->expConst.p;
+  p.rMaxSq = e->rMaxSq.p;
+  p.mAn = e->mAn.p;
+  p.mBn = e->mBn.p;
+  p.mCn = e->mCn.p;
+  p.mSign = e->mSign.p;
+  p.mSig6 = e->mSig6.p;
+  p.rOn = e->rOn;
+  p.A6 = e->mA6; p.B6 = e->mB6; p.C6 = e->mC6;
+  p.A1 = e->mA1; p.B1 = e->mB1; p.C1 = e->mC1;
+  p.diElectric_1 = e->diElectric_1;
   return p;
 }
 
@@ -200,6 +215,8 @@ int check_box(const gomcb200_engine *e, int b, bool needAxes = true) {
   if (b < 0 || b >= e->nBoxes) return fail(GOMCB200_EINVAL, "box %d out of range", b);
   if (!e->haveFF) return fail(GOMCB200_EINVAL, "gomcb200_init_forcefield not called");
   if (!e->haveTopo) return fail(GOMCB200_EINVAL, "gomcb200_init_topology not called");
+  if (e->vdwKind == VDW_EXP6 && !e->haveExp6)
+    return fail(GOMCB200_EINVAL, "Potential EXP6: gomcb200_init_exp6 not called");
   if (needAxes && !e->box[b].haveAxes)
     return fail(GOMCB200_EINVAL, "gomcb200_set_box_axes not called for box %d", b);
   return 0;
@@ -300,6 +317,10 @@ void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int 
     LAUNCH(VDW_SHIFT);
   else if (e->vdwKind == VDW_SWITCH)
     LAUNCH(VDW_SWITCH);
+  else if (e->vdwKind == VDW_EXP6)
+    LAUNCH(VDW_EXP6);
+  else if (e->vdwKind == VDW_MARTINI)
+    LAUNCH(VDW_MARTINI);
   else
     LAUNCH(VDW_STD);
 #undef LAUNCH
@@ -932,6 +953,10 @@ int run_probes(gomcb200_engine *e, int b, int excludeMol, int n, std::vector<dou
     launch_probe<VDW_SHIFT>(e, b, p, excludeMol, n);
   else if (e->vdwKind == VDW_SWITCH)
     launch_probe<VDW_SWITCH>(e, b, p, excludeMol, n);
+  else if (e->vdwKind == VDW_EXP6)
+    launch_probe<VDW_EXP6>(e, b, p, excludeMol, n);
+  else if (e->vdwKind == VDW_MARTINI)
+    launch_probe<VDW_MARTINI>(e, b, p, excludeMol, n);
   else
     launch_probe<VDW_STD>(e, b, p, excludeMol, n);
   e->launches += 1;
@@ -1006,6 +1031,8 @@ int gomcb200_destroy(gomcb200_engine *e) {
   cudaStreamSynchronize(e->stream);
   e->sigmaSq.release(); e->epsilon_cn.release(); e->nTab.release();
   e->shiftConst.release(); e->nHalf.release();
+  e->rMin.release(); e->expConst.release(); e->rMaxSq.release();
+  e->mAn.release(); e->mBn.release(); e->mCn.release(); e->mSign.release(); e->mSig6.release();
   e->kind.release(); e->mol.release(); e->molStart.release();
   e->x.release(); e->y.release(); e->z.release(); e->q.release();
   e->comx.release(); e->comy.release(); e->comz.release();
@@ -1043,14 +1070,17 @@ int gomcb200_init_forcefield(gomcb200_engine *e, const double *sigmaSq,
                              const double *rCutCoulomb, double rCutLow, double rOn,
                              const double *alpha, int ewald, int electrostatic,
                              double diElectric_1) {
-  (void)diElectric_1;
   if (!e || !sigmaSq || !epsilon_cn || !n || count < 1)
     return fail(GOMCB200_EINVAL, "bad arguments");
-  if (isMartini) return fail(GOMCB200_EINVAL, "Martini switch potential not supported yet");
-  if (vdwKind < 0 || vdwKind > 2)
-    return fail(GOMCB200_EINVAL, "vdwKind %d not supported (EXP6 is a next-round row)", vdwKind);
+  if (vdwKind < 0 || vdwKind > 3) return fail(GOMCB200_EINVAL, "unknown vdwKind %d", vdwKind);
+  if (isMartini && vdwKind != VDW_SWITCH)
+    return fail(GOMCB200_EINVAL, "Martini parameters need Potential SWITCH");
   CK(cudaSetDevice(e->device));
-  e->vdwKind = vdwKind;
+  // Forcefield::Init picks FF_SWITCH_MARTINI for SWITCH + Martini (src/Forcefield.cpp:100-103)
+  e->vdwKind = (isMartini && vdwKind == VDW_SWITCH) ? VDW_MARTINI : vdwKind;
+  vdwKind = e->vdwKind;
+  e->diElectric_1 = diElectric_1;
+  e->haveExp6 = false;
   e->ewald = ewald;
   e->electrostatic = electrostatic;
   e->kindCount = count;
@@ -1078,6 +1108,33 @@ int gomcb200_init_forcefield(gomcb200_engine *e, const double *sigmaSq,
       shift[i] = epsilon_cn[i] * (repulse - attract);
     }
   }
+  if (vdwKind == VDW_MARTINI) {  // FF_SWITCH_MARTINI::Init, src/FFSwitchMartini.h:121-213
+    const double rOnCoul = 0.0;
+    const double d = rCut - rOn, dc = rCut - rOnCoul;
+    e->mA6 = 6.0 * (7.0 * rOn - 10.0 * rCut) / (pow(rCut, 8.0) * d * d);
+    e->mB6 = -6.0 * (7.0 * rOn - 9.0 * rCut) / (pow(rCut, 8.0) * d * d * d);
+    e->mC6 = pow(rCut, -6.0) - e->mA6 / 3.0 * d * d * d - e->mB6 / 4.0 * d * d * d * d;
+    e->mA1 = (2.0 * rOnCoul - 5.0 * rCut) / (rCut * rCut * rCut * dc * dc);
+    e->mB1 = -1.0 * (2.0 * rOnCoul - 4.0 * rCut) / (rCut * rCut * rCut * dc * dc * dc);
+    e->mC1 = 1.0 / rCut - e->mA1 / 3.0 * dc * dc * dc - e->mB1 / 4.0 * dc * dc * dc * dc;
+    std::vector<double> An(sz), Bn(sz), Cn(sz), sg(sz), s6(sz);
+    for (size_t i = 0; i < sz; ++i) {
+      double pn = n[i];
+      An[i] = pn * ((pn + 1.0) * rOn - (pn + 4.0) * rCut) / (pow(rCut, pn + 2.0) * d * d);
+      Bn[i] = -pn * ((pn + 1.0) * rOn - (pn + 3.0) * rCut) / (pow(rCut, pn + 2.0) * d * d * d);
+      Cn[i] = 1.0 / pow(rCut, pn) - An[i] / 3.0 * d * d * d - Bn[i] / 4.0 * d * d * d * d;
+      double sigma = sqrt(sigmaSq[i]);
+      s6[i] = pow(sigma, 6.0);
+      sg[i] = pow(sigma, pn);
+    }
+    CK(e->mAn.reserve(sz)); CK(e->mBn.reserve(sz)); CK(e->mCn.reserve(sz));
+    CK(e->mSign.reserve(sz)); CK(e->mSig6.reserve(sz));
+    CK(cudaMemcpy(e->mAn.p, An.data(), sz * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->mBn.p, Bn.data(), sz * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->mCn.p, Cn.data(), sz * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->mSign.p, sg.data(), sz * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->mSig6.p, s6.data(), sz * sizeof(double), cudaMemcpyHostToDevice));
+  }
   CK(e->sigmaSq.reserve(sz)); CK(e->epsilon_cn.reserve(sz)); CK(e->nTab.reserve(sz));
   CK(e->shiftConst.reserve(sz)); CK(e->nHalf.reserve(sz));
   CK(cudaMemcpy(e->sigmaSq.p, sigmaSq, sz * sizeof(double), cudaMemcpyHostToDevice));
@@ -1086,6 +1143,21 @@ int gomcb200_init_forcefield(gomcb200_engine *e, const double *sigmaSq,
   CK(cudaMemcpy(e->shiftConst.p, shift.data(), sz * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->nHalf.p, nHalf.data(), sz * sizeof(int), cudaMemcpyHostToDevice));
   e->haveFF = true;
+  return 0;
+}
+
+int gomcb200_init_exp6(gomcb200_engine *e, const double *rMin, const double *expConst,
+                       const double *rMaxSq, int size) {
+  if (!e || !rMin || !expConst || !rMaxSq) return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!e->haveFF) return fail(GOMCB200_EINVAL, "gomcb200_init_forcefield not called");
+  if (size != e->kindCount * e->kindCount)
+    return fail(GOMCB200_EINVAL, "size %d != count^2 %d", size, e->kindCount * e->kindCount);
+  CK(cudaSetDevice(e->device));
+  CK(e->rMin.reserve(size)); CK(e->expConst.reserve(size)); CK(e->rMaxSq.reserve(size));
+  CK(cudaMemcpy(e->rMin.p, rMin, size * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->expConst.p, expConst, size * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(e->rMaxSq.p, rMaxSq, size * sizeof(double), cudaMemcpyHostToDevice));
+  e->haveExp6 = true;
   return 0;
 }
 

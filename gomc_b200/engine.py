@@ -32,6 +32,7 @@ _SIGS = {
     "gomcb200_init_forcefield": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int,
                                            C.c_double, _dp, C.c_double, C.c_double, _dp,
                                            C.c_int, C.c_int, C.c_double]),
+    "gomcb200_init_exp6": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int]),
     "gomcb200_init_topology": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _dp, _ip]),
     "gomcb200_set_box_molecules": (C.c_int, [_vp, C.c_int, _ip, C.c_int]),
     "gomcb200_set_box_axes": (C.c_int, [_vp, C.c_int, _dp]),
@@ -141,13 +142,19 @@ class Engine:
 
     # ---- setup -----------------------------------------------------------
     def init_forcefield(self, sigma_sq, epsilon_cn, n, vdw_kind, count, r_cut, r_cut_coulomb,
-                        r_cut_low, r_switch, alpha, ewald, electrostatic, is_martini=0):
+                        r_cut_low, r_switch, alpha, ewald, electrostatic, is_martini=0,
+                        dielectric=1.0):
         (a, pa), (b, pb), (c, pc) = _d(sigma_sq), _d(epsilon_cn), _d(n)
         (rc_, prc), (al, pal) = _d(np.atleast_1d(r_cut_coulomb)), _d(np.atleast_1d(alpha))
         self._ck(self.L.gomcb200_init_forcefield(self.h, pa, pb, pc, int(vdw_kind),
                                                  int(is_martini), int(count), float(r_cut), prc,
                                                  float(r_cut_low), float(r_switch), pal,
-                                                 int(ewald), int(electrostatic), 1.0))
+                                                 int(ewald), int(electrostatic),
+                                                 1.0 / float(dielectric)))
+
+    def init_exp6(self, r_min, exp_const, r_max_sq):
+        (a, pa), (b, pb), (c, pc) = _d(r_min), _d(exp_const), _d(r_max_sq)
+        self._ck(self.L.gomcb200_init_exp6(self.h, pa, pb, pc, len(a)))
 
     def init_topology(self, kind, mol, charge, mol_start):
         (k, pk), (m, pm), (q, pq), (s, ps) = _i(kind), _i(mol), _d(charge), _i(mol_start)
@@ -354,7 +361,10 @@ class Engine:
         e = cls(1, device)
         e.init_forcefield(sig, eps, nn, ff.vdw_kind, len(ff.type_names), ff.r_cut,
                           [ff.r_cut_coulomb], ff.r_cut_low, ff.r_switch, [ff.alpha],
-                          ff.ewald, ff.electrostatic)
+                          ff.ewald, ff.electrostatic, is_martini=ff.is_martini,
+                          dielectric=ff.dielectric)
+        if ff.vdw_kind == 3:
+            e.init_exp6(*ff.exp6_tables())
         e.init_topology(s.kind, s.mol, s.charge, s.mol_start)
         e.set_box_molecules(0, np.arange(s.n_mols, dtype=np.int32))
         e.set_box_axes(0, s.axis)

@@ -54,10 +54,16 @@ public:
   void InitForceField(const double *sigmaSq, const double *epsilon_cn, const double *n,
                       int vdwKind, int isMartini, int count, double rCut,
                       const double *rCutCoulomb, double rCutLow, double rOn,
-                      const double *alpha, bool ewald, bool electrostatic) {
+                      const double *alpha, bool ewald, bool electrostatic,
+                      double diElectric_1 = 1.0) {
     check(gomcb200_init_forcefield(e_, sigmaSq, epsilon_cn, n, vdwKind, isMartini, count, rCut,
-                                   rCutCoulomb, rCutLow, rOn, alpha, ewald, electrostatic, 1.0),
+                                   rCutCoulomb, rCutLow, rOn, alpha, ewald, electrostatic,
+                                   diElectric_1),
           "InitGPUForceField");
+  }
+  // FF_EXP6::Init -> InitExp6VariablesCUDA (src/FFExp6.h:145)
+  void InitExp6(const double *rMin, const double *expConst, const double *rMaxSq, int size) {
+    check(gomcb200_init_exp6(e_, rMin, expConst, rMaxSq, size), "InitExp6VariablesCUDA");
   }
   // CalculateEnergy::Init (src/CalculateEnergy.cpp:60-81)
   void InitTopology(const std::vector<int> &particleKind, const std::vector<int> &particleMol,

@@ -17,8 +17,10 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-VDW_STD, VDW_SHIFT, VDW_SWITCH = 0, 1, 2
-_POT_NAME = {VDW_STD: "VDW", VDW_SHIFT: "SHIFT", VDW_SWITCH: "SWITCH"}
+VDW_STD, VDW_SHIFT, VDW_SWITCH, VDW_EXP6 = 0, 1, 2, 3
+_POT_NAME = {VDW_STD: "VDW", VDW_SHIFT: "SHIFT", VDW_SWITCH: "SWITCH", VDW_EXP6: "EXP6"}
+KCAL_PER_MOL_TO_K = 503.21959899      # src/FFSetup.cpp:25
+RIJ_OVER_2_TO_SIG = 1.7817974362807   # src/FFSetup.cpp:26
 
 
 @dataclass
@@ -48,6 +50,8 @@ class ForceField:
     ewald: bool = True
     electrostatic: bool = True
     lrc: bool = True
+    is_martini: bool = False       # ParaTypeMARTINI + Potential SWITCH -> FF_SWITCH_MARTINI
+    dielectric: float = 15.0       # Martini only (src/ConfigSetup.cpp:1684-1686 default)
     bond_params: list = field(default_factory=list)   # (t1, t2, b0)
     angle_params: list = field(default_factory=list)  # (t1, t2, t3, theta0)
 
@@ -71,7 +75,10 @@ class ForceField:
         for i in range(K):
             for j in range(K):
                 idx = i + j * K
-                n_ij = (self.n[i] + self.n[j]) * 0.5
+                if self.vdw_kind == VDW_EXP6:   # geometric mean, FFParticle.cpp:165-167
+                    n_ij = math.sqrt(self.n[i] * self.n[j])
+                else:
+                    n_ij = (self.n[i] + self.n[j]) * 0.5
                 cn = n_ij / (n_ij - 6.0) * math.pow(n_ij / 6.0, 6.0 / (n_ij - 6.0))
                 s = (self.sigma[i] + self.sigma[j]) * 0.5
                 e = math.sqrt(self.epsilon[i] * self.epsilon[j])
@@ -79,6 +86,31 @@ class ForceField:
                 eps_cn[idx] = cn * e
                 nn[idx] = n_ij
         return sig, eps_cn, nn
+
+    def exp6_tables(self):
+        """rMin, expConst, rMaxSq of FF_EXP6::Init (src/FFExp6.h:99-147).  The
+        reference finds the two roots with a float-precision Brent solver
+        (lib/NumLib.h:232-300, tol 1e-7); here scipy's brentq on the same
+        functions -- parity tests feed the SAME arrays to the oracle and the
+        engine, and the golden fixtures carry the reference's own values."""
+        from scipy.optimize import brentq
+        sig, eps_cn, nn = self.tables()
+        K = len(self.type_names)
+        r_min, exp_c, r_max_sq = np.zeros(K * K), np.zeros(K * K), np.zeros(K * K)
+        for i in range(K):
+            for j in range(K):
+                idx = i + j * K
+                a, sigma = nn[idx], math.sqrt(sig[idx])
+                eps = math.sqrt(self.epsilon[i] * self.epsilon[j])
+                exp_c[idx] = eps * a / (a - 6.0)
+                if sigma == 0.0:
+                    continue
+                f1 = lambda x: (6.0 / a) * math.exp(a * (1.0 - sigma / x)) - (x / sigma) ** 6
+                r_min[idx] = brentq(f1, sigma, 3.0 * sigma, xtol=1e-9)
+                rm = r_min[idx]
+                f2 = lambda x: (-1.0 / rm) * math.exp(a * (1.0 - x / rm)) + (rm / x) ** 6 / x
+                r_max_sq[idx] = brentq(f2, 1e-3 * sigma, sigma, xtol=1e-9) ** 2
+        return r_min, exp_c, r_max_sq
 
 
 @dataclass
@@ -249,15 +281,16 @@ def make_electrolyte(n_water=330000, n_pairs=5000, seed=123, r_cut=10.0,
 
 
 def make_mixture(n_a=150, n_b=100, seed=5, L=26.0, r_cut=8.0, vdw_kind=VDW_STD,
-                 r_switch=0.0, n_b_exp=14.0):
+                 r_switch=0.0, n_b_exp=14.0, martini=False, ewald=True, du_eps=0.0,
+                 du_sigma=0.0):
     """Small two-kind Mie mixture with charged dimers: exercises the kind table
     (non-integer n/2 via n=13 cross terms), charged + neutral atoms in one
     molecule and multi-kind LRC."""
-    ff = ForceField(["CA", "CB", "DU"], np.array([98.0, 46.0, 0.0]),
-                    np.array([3.75, 3.0, 0.0]), np.array([12.0, n_b_exp, 12.0]),
+    ff = ForceField(["CA", "CB", "DU"], np.array([98.0, 46.0, du_eps]),
+                    np.array([3.75, 3.0, du_sigma]), np.array([12.0, n_b_exp, 12.0]),
                     vdw_kind=vdw_kind, r_cut=r_cut, r_cut_coulomb=r_cut,
-                    r_switch=r_switch, tolerance=1e-5,
-                    lrc=(vdw_kind == VDW_STD),
+                    r_switch=r_switch, tolerance=1e-5, ewald=ewald,
+                    lrc=(vdw_kind == VDW_STD), is_martini=martini,
                     bond_params=[("CB", "CB", 1.5), ("CB", "DU", 0.8)],
                     angle_params=[("CB", "CB", "DU", 120.0)])
     a = MolKind("AAA", ["C1"], ["CA"], [0.0], [16.0])
@@ -285,9 +318,15 @@ def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
         f.write("\nANGLES\n")
         for t1, t2, t3, th in ff.angle_params:
             f.write(f"{t1}\t{t2}\t{t3}\t999999999999\t{th}\n")
-        f.write("\nDIHEDRALS\n\nNONBONDED_MIE\n")
-        for t, e, s, n in zip(ff.type_names, ff.epsilon, ff.sigma, ff.n):
-            f.write(f"{t}\t{float(e)!r}\t{float(s)!r}\t{float(n)!r}\n")
+        if ff.is_martini:   # CHARMM units: -eps in kcal/mol, Rmin/2 (src/FFSetup.cpp:265-279)
+            f.write("\nDIHEDRALS\n\nNONBONDED\n")
+            for t, e, s, n in zip(ff.type_names, ff.epsilon, ff.sigma, ff.n):
+                f.write(f"{t}\t0.0\t{-float(e) / KCAL_PER_MOL_TO_K!r}\t"
+                        f"{float(s) / RIJ_OVER_2_TO_SIG!r}\n")
+        else:
+            f.write("\nDIHEDRALS\n\nNONBONDED_MIE\n")
+            for t, e, s, n in zip(ff.type_names, ff.epsilon, ff.sigma, ff.n):
+                f.write(f"{t}\t{float(e)!r}\t{float(s)!r}\t{float(n)!r}\n")
         f.write("\nEND\n")
     # ---- PDB + PSF -------------------------------------------------------
     n = sys.n_atoms
@@ -332,7 +371,8 @@ def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
 Restart false
 PRNG INTSEED
 Random_Seed 123
-ParaTypeMie on
+{'ParaTypeMARTINI on' if ff.is_martini else 'ParaTypeMie on'}
+{('Dielectric ' + repr(float(ff.dielectric))) if ff.is_martini else ''}
 Parameters par.inp
 Coordinates 0 box0.pdb
 Structure 0 box0.psf

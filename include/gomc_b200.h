@@ -28,6 +28,7 @@
  *    usable CUDA device gomcb200_create fails.
  *
  * Arithmetic is IEEE double throughout; lambda == 1 (no fractional molecule).
+ * Potentials: VDW (Mie), SHIFT, SWITCH, SWITCH+Martini, EXP6.
  * Orthogonal boxes only in this revision (gomcb200_set_box_axes).
  * Threading: one host thread per engine, like the reference.
  */
@@ -51,7 +52,12 @@ enum {
 };
 
 /* src/GPU/ConstantDefinitionsCUDAKernel.cuh:18-20 */
-enum { GOMCB200_VDW_STD = 0, GOMCB200_VDW_SHIFT = 1, GOMCB200_VDW_SWITCH = 2 };
+enum {
+  GOMCB200_VDW_STD = 0,
+  GOMCB200_VDW_SHIFT = 1,
+  GOMCB200_VDW_SWITCH = 2, /* with isMartini: FF_SWITCH_MARTINI */
+  GOMCB200_VDW_EXP6 = 3
+};
 
 /* which force / k-vector buffer */
 enum {
@@ -88,6 +94,12 @@ int gomcb200_init_forcefield(gomcb200_engine *e, const double *sigmaSq,
                              double rCutLow, double rOn, const double *alpha,
                              int ewald, int electrostatic,
                              double diElectric_1);
+
+/* InitExp6VariablesCUDA, src/GPU/ConstantDefinitionsCUDAKernel.cuh:34-35:
+ * the rMin / expConst / rMaxSq tables FF_EXP6::Init derives with Brent's method
+ * (src/FFExp6.h:99-147); required before any energy call when vdwKind is EXP6. */
+int gomcb200_init_exp6(gomcb200_engine *e, const double *rMin,
+                       const double *expConst, const double *rMaxSq, int size);
 
 /* InitCoordinatesCUDA (ConstantDefinitionsCUDAKernel.cuh:31-32) plus the
  * per-atom vectors CalculateEnergy::Init / Ewald::Init build

@@ -95,10 +95,74 @@ static inline double shift_const(const orc_params *p, int idx) {
   return p->epsilon_cn[idx] * (repulse - attract);
 }
 
+/* FF_SWITCH_MARTINI::Init constants, src/FFSwitchMartini.h:121-213 */
+typedef struct {
+  double A6, B6, C6, A1, B1, C1, An, Bn, Cn, sign, sig6;
+} martini_consts;
+static martini_consts martini_init(const orc_params *p, int idx) {
+  martini_consts m;
+  double rCut = p->rCut, rOn = p->rOn, rOnCoul = 0.0;
+  m.A6 = 6.0 * (7.0 * rOn - 10.0 * rCut) / (pow(rCut, 8.0) * (rCut - rOn) * (rCut - rOn));
+  m.B6 = -6.0 * (7.0 * rOn - 9.0 * rCut) /
+         (pow(rCut, 8.0) * (rCut - rOn) * (rCut - rOn) * (rCut - rOn));
+  m.C6 = pow(rCut, -6.0) - m.A6 / 3.0 * (rCut - rOn) * (rCut - rOn) * (rCut - rOn) -
+         m.B6 / 4.0 * (rCut - rOn) * (rCut - rOn) * (rCut - rOn) * (rCut - rOn);
+  m.A1 = (2.0 * rOnCoul - 5.0 * rCut) /
+         (rCut * rCut * rCut * (rCut - rOnCoul) * (rCut - rOnCoul));
+  m.B1 = -1.0 * (2.0 * rOnCoul - 4.0 * rCut) /
+         (rCut * rCut * rCut * (rCut - rOnCoul) * (rCut - rOnCoul) * (rCut - rOnCoul));
+  m.C1 = 1.0 / rCut - m.A1 / 3.0 * (rCut - rOnCoul) * (rCut - rOnCoul) * (rCut - rOnCoul) -
+         m.B1 / 4.0 * (rCut - rOnCoul) * (rCut - rOnCoul) * (rCut - rOnCoul) *
+             (rCut - rOnCoul);
+  double pn = p->n[idx];
+  m.An = pn * ((pn + 1.0) * rOn - (pn + 4.0) * rCut) /
+         (pow(rCut, pn + 2.0) * (rCut - rOn) * (rCut - rOn));
+  m.Bn = -pn * ((pn + 1.0) * rOn - (pn + 3.0) * rCut) /
+         (pow(rCut, pn + 2.0) * (rCut - rOn) * (rCut - rOn) * (rCut - rOn));
+  m.Cn = 1.0 / pow(rCut, pn) - m.An / 3.0 * (rCut - rOn) * (rCut - rOn) * (rCut - rOn) -
+         m.Bn / 4.0 * (rCut - rOn) * (rCut - rOn) * (rCut - rOn) * (rCut - rOn);
+  double sigma = sqrt(p->sigmaSq[idx]);
+  m.sig6 = pow(sigma, 6.0);
+  m.sign = pow(sigma, pn);
+  return m;
+}
+
+#ifndef DBL_MAX
+#define DBL_MAX 1.7976931348623158e+308 /* num::BIGNUM, lib/NumLib.h:15,24 */
+#endif
+
 double orc_calc_en(const orc_params *p, double distSq, int kind1, int kind2) {
   double rCutSq = p->rCut * p->rCut;
   if (rCutSq < distSq) return 0.0; /* FFParticle.cpp:297 */
   int idx = kind1 + kind2 * p->kindCount; /* FFParticle.h:111 */
+  if (p->vdwKind == ORC_VDW_SWITCH && p->isMartini) { /* FFSwitchMartini.h:279-302 */
+    martini_consts m = martini_init(p, idx);
+    double rOnSq = p->rOn * p->rOn;
+    double r_2 = 1.0 / distSq;
+    double r_4 = r_2 * r_2;
+    double r_6 = r_4 * r_2;
+    double n_ij = p->n[idx];
+    double r_n = pow(r_2, (n_ij * 0.5));
+    double rij_ron = sqrt(distSq) - p->rOn;
+    double rij_ron_2 = rij_ron * rij_ron;
+    double rij_ron_3 = rij_ron_2 * rij_ron;
+    double rij_ron_4 = rij_ron_2 * rij_ron_2;
+    double shifttempRep = -(m.An / 3.0) * rij_ron_3 - (m.Bn / 4.0) * rij_ron_4 - m.Cn;
+    double shifttempAtt = -(m.A6 / 3.0) * rij_ron_3 - (m.B6 / 4.0) * rij_ron_4 - m.C6;
+    double shiftRep = (distSq > rOnSq ? shifttempRep : -m.Cn);
+    double shiftAtt = (distSq > rOnSq ? shifttempAtt : -m.C6);
+    return p->epsilon_cn[idx] * (m.sign * (r_n + shiftRep) - m.sig6 * (r_6 + shiftAtt));
+  }
+  if (p->vdwKind == ORC_VDW_EXP6) { /* FFExp6.h:184-224 */
+    if (distSq < p->rMaxSq[idx]) return DBL_MAX;
+    double dist = sqrt(distSq);
+    double rRat = p->rMin[idx] / dist;
+    double rRat2 = rRat * rRat;
+    double attract = rRat2 * rRat2 * rRat2;
+    unsigned alpha_ij = (unsigned)p->n[idx]; /* truncated to uint, FFExp6.h:215 */
+    double repulse = (6.0 / alpha_ij) * exp(alpha_ij * (1.0 - dist / p->rMin[idx]));
+    return p->expConst[idx] * (repulse - attract);
+  }
   switch (p->vdwKind) {
   case ORC_VDW_SHIFT: { /* FFShift.h:167-175 */
     double rRat2 = p->sigmaSq[idx] / distSq;
@@ -130,6 +194,33 @@ double orc_calc_vir(const orc_params *p, double distSq, int kind1, int kind2) {
   double rCutSq = p->rCut * p->rCut;
   if (rCutSq < distSq) return 0.0;
   int idx = kind1 + kind2 * p->kindCount;
+  if (p->vdwKind == ORC_VDW_SWITCH && p->isMartini) { /* FFSwitchMartini.h:328-348 */
+    martini_consts m = martini_init(p, idx);
+    double rOnSq = p->rOn * p->rOn;
+    double n_ij = p->n[idx];
+    double r_1 = 1.0 / sqrt(distSq);
+    double r_8 = distSq * distSq * distSq * distSq; /* sic: (r^2)^4, not r^-8 */
+    double r_n2 = pow(r_1, n_ij + 2.0);
+    double rij_ron = sqrt(distSq) - p->rOn;
+    double rij_ron_2 = rij_ron * rij_ron;
+    double rij_ron_3 = rij_ron_2 * rij_ron;
+    double dshifttempRep = m.An * rij_ron_2 + m.Bn * rij_ron_3;
+    double dshifttempAtt = m.A6 * rij_ron_2 + m.B6 * rij_ron_3;
+    double dshiftRep = (distSq > rOnSq ? dshifttempRep * r_1 : 0);
+    double dshiftAtt = (distSq > rOnSq ? dshifttempAtt * r_1 : 0);
+    return p->epsilon_cn[idx] *
+           (m.sign * (n_ij * r_n2 + dshiftRep) - m.sig6 * (6.0 * r_8 + dshiftAtt));
+  }
+  if (p->vdwKind == ORC_VDW_EXP6) { /* FFExp6.h:226-257 */
+    if (distSq < p->rMaxSq[idx]) return DBL_MAX;
+    double dist = sqrt(distSq);
+    double rRat = p->rMin[idx] / dist;
+    double rRat2 = rRat * rRat;
+    double attract = rRat2 * rRat2 * rRat2;
+    unsigned alpha_ij = (unsigned)p->n[idx];
+    double repulse = (dist / p->rMin[idx]) * exp(alpha_ij * (1.0 - dist / p->rMin[idx]));
+    return 6.0 * p->expConst[idx] * (repulse - attract) / distSq;
+  }
   if (p->vdwKind == ORC_VDW_SWITCH) { /* FFSwitch.h:199-218 */
     double rOnSq = p->rOn * p->rOn;
     double factor1 = rCutSq - 3 * rOnSq;
@@ -163,6 +254,13 @@ double orc_calc_coulomb(const orc_params *p, double distSq,
     double val = p->alpha * dist;
     return qi_qj_fact * erfc(val) / dist;
   }
+  if (p->vdwKind == ORC_VDW_SWITCH && p->isMartini) { /* FFSwitchMartini.h:379-396 */
+    martini_consts m = martini_init(p, 0);
+    double rij_ronCoul_3 = dist * distSq;
+    double rij_ronCoul_4 = distSq * distSq;
+    double coul = -(m.A1 / 3.0) * rij_ronCoul_3 - (m.B1 / 4.0) * rij_ronCoul_4 - m.C1;
+    return qi_qj_fact * p->diElectric_1 * (1.0 / dist + coul);
+  }
   switch (p->vdwKind) {
   case ORC_VDW_SHIFT: /* FFShift.h:245-249 */
     return qi_qj_fact * (1.0 / dist - 1.0 / p->rCut);
@@ -189,6 +287,13 @@ double orc_calc_coulomb_vir(const orc_params *p, double distSq, double qi_qj) {
     else
       temp = erfc(p->alpha * dist); /* FFShift.h:289, FFSwitch.h:299 */
     return qi_qj * (temp / dist + constValue * expConstValue) / distSq;
+  }
+  if (p->vdwKind == ORC_VDW_SWITCH && p->isMartini) { /* FFSwitchMartini.h:440-447 */
+    martini_consts m = martini_init(p, 0);
+    double rij_ronCoul_2 = distSq;
+    double rij_ronCoul_3 = dist * distSq;
+    double virCoul = m.A1 / rij_ronCoul_2 + m.B1 / rij_ronCoul_3;
+    return qi_qj * p->diElectric_1 * (1.0 / (dist * distSq) + virCoul / dist);
   }
   if (p->vdwKind == ORC_VDW_SWITCH) { /* FFSwitch.h:302-307 */
     double rCutSq = p->rCut * p->rCut;

@@ -28,7 +28,7 @@ extern "C" {
 /* lib/NumLib.h:22 */
 #define ORC_QQFACT 167103.208067979
 
-enum { ORC_VDW_STD = 0, ORC_VDW_SHIFT = 1, ORC_VDW_SWITCH = 2 };
+enum { ORC_VDW_STD = 0, ORC_VDW_SHIFT = 1, ORC_VDW_SWITCH = 2, ORC_VDW_EXP6 = 3 };
 
 /* Force-field + per-box constants.  Mirrors what Forcefield::Init
  * (src/Forcefield.cpp:29-84), FFParticle::Blend (src/FFParticle.cpp:155-199)
@@ -48,6 +48,14 @@ typedef struct {
   const double *sigmaSq;    /* [kindCount^2], index kind1 + kind2*count         */
   const double *epsilon_cn; /* [kindCount^2]                                    */
   const double *n;          /* [kindCount^2]                                    */
+  /* ---- EXP6 (src/FFExp6.h:99-147): tables the reference derives with Brent's
+   * method at init; handed in, as the reference hands them to its GPU build
+   * (InitExp6VariablesCUDA).  NULL unless vdwKind == ORC_VDW_EXP6. */
+  const double *rMin, *expConst, *rMaxSq;
+  /* ---- Martini switch (src/FFSwitchMartini.h): vdwKind == ORC_VDW_SWITCH with
+   * isMartini != 0; constants are derived from rCut, rOn, n, sigmaSq. */
+  int isMartini;
+  double diElectric_1;      /* 1 / forcefield.dielectric                        */
 } orc_params;
 
 /* ---- cell list (src/CellList.cpp:138-285, src/CellList.h:88-101) ---------- */

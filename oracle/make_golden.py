@@ -30,6 +30,15 @@ CASES = {
     "mixture_shift": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SHIFT), 4, 5),
     "mixture_switch": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.5), 4, 5),
     "mixture_n13": (lambda: synth.make_mixture(n_b_exp=13.0, seed=9), 4, 5),
+    # EXP6: n is the exp-6 alpha (geometric mixing, truncated to uint in the energy);
+    # every kind has a non-zero sigma (rMin = 0 gives NaN forces in the reference too)
+    "mixture_exp6": (lambda: synth.make_mixture(vdw_kind=synth.VDW_EXP6, n_b_exp=16.0,
+                                                du_eps=12.0, du_sigma=1.2), 4, 5),
+    # Martini switch (ParaTypeMARTINI + Potential SWITCH), Ewald off -> switched Coulomb
+    "mixture_martini": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.0,
+                                                   martini=True, ewald=False, n_b_exp=12.0), 4, 5),
+    "mixture_martini_ewald": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.0,
+                                                         martini=True, ewald=True, seed=4, n_b_exp=12.0), 4, 5),
 }
 
 

@@ -27,7 +27,9 @@ class OrcParams(C.Structure):
                 ("kindCount", C.c_int), ("rCut", C.c_double), ("rCutLow", C.c_double),
                 ("rOn", C.c_double), ("rCutCoulomb", C.c_double), ("alpha", C.c_double),
                 ("recip_rcut", C.c_double), ("axis", C.c_double * 3),
-                ("sigmaSq", _dp), ("epsilon_cn", _dp), ("n", _dp)]
+                ("sigmaSq", _dp), ("epsilon_cn", _dp), ("n", _dp),
+                ("rMin", _dp), ("expConst", _dp), ("rMaxSq", _dp),
+                ("isMartini", C.c_int), ("diElectric_1", C.c_double)]
 
 
 def build(force=False):
@@ -76,16 +78,23 @@ class Oracle:
     """Stateless reference calculator bound to one (force field, box)."""
 
     def __init__(self, *, vdw_kind, ewald, electrostatic, kind_count, r_cut, r_cut_low,
-                 r_switch, r_cut_coulomb, alpha, recip_rcut, axis, sigma_sq, epsilon_cn, n):
+                 r_switch, r_cut_coulomb, alpha, recip_rcut, axis, sigma_sq, epsilon_cn, n,
+                 r_min=None, exp_const=None, r_max_sq=None, is_martini=0, dielectric=1.0):
         self.L = lib()
         self._keep = [_d(sigma_sq), _d(epsilon_cn), _d(n)]
+        if r_min is not None:
+            self._keep += [_d(r_min), _d(exp_const), _d(r_max_sq)]
         p = OrcParams()
         p.vdwKind, p.ewald, p.electrostatic = int(vdw_kind), int(ewald), int(electrostatic)
         p.kindCount = int(kind_count)
         p.rCut, p.rCutLow, p.rOn = float(r_cut), float(r_cut_low), float(r_switch)
         p.rCutCoulomb, p.alpha, p.recip_rcut = float(r_cut_coulomb), float(alpha), float(recip_rcut)
         p.axis[0], p.axis[1], p.axis[2] = (float(v) for v in axis)
-        p.sigmaSq, p.epsilon_cn, p.n = (k[1] for k in self._keep)
+        p.sigmaSq, p.epsilon_cn, p.n = (k[1] for k in self._keep[:3])
+        if r_min is not None:
+            p.rMin, p.expConst, p.rMaxSq = (k[1] for k in self._keep[3:6])
+        p.isMartini = int(is_martini)
+        p.diElectric_1 = 1.0 / float(dielectric)
         self.p = p
         self.pp = C.byref(p)
 
@@ -96,7 +105,10 @@ class Oracle:
         return cls(vdw_kind=ff.vdw_kind, ewald=ff.ewald, electrostatic=ff.electrostatic,
                    kind_count=len(ff.type_names), r_cut=ff.r_cut, r_cut_low=ff.r_cut_low,
                    r_switch=ff.r_switch, r_cut_coulomb=ff.r_cut_coulomb, alpha=ff.alpha,
-                   recip_rcut=ff.recip_rcut, axis=s.axis, sigma_sq=sig, epsilon_cn=eps, n=nn)
+                   recip_rcut=ff.recip_rcut, axis=s.axis, sigma_sq=sig, epsilon_cn=eps, n=nn,
+                   is_martini=ff.is_martini, dielectric=ff.dielectric,
+                   **(dict(zip(("r_min", "exp_const", "r_max_sq"), ff.exp6_tables()))
+                      if ff.vdw_kind == 3 else {}))
 
     @classmethod
     def from_dump(cls, d, box=0):
@@ -106,7 +118,11 @@ class Oracle:
                    r_switch=sc(d, "ff.rswitch"),
                    r_cut_coulomb=d["ff.rCutCoulomb"][box], alpha=d["ff.alpha"][box],
                    recip_rcut=d["ff.recip_rcut"][box], axis=d[f"box{box}.axis"],
-                   sigma_sq=d["ff.sigmaSq"], epsilon_cn=d["ff.epsilon_cn"], n=d["ff.n"])
+                   sigma_sq=d["ff.sigmaSq"], epsilon_cn=d["ff.epsilon_cn"], n=d["ff.n"],
+                   is_martini=sc(d, "ff.isMartini"),
+                   dielectric=(sc(d, "ff.dielectric") if "ff.dielectric" in d else 1.0),
+                   **({"r_min": d["ff.rMin"], "exp_const": d["ff.expConst"],
+                       "r_max_sq": d["ff.rMaxSq"]} if "ff.rMin" in d else {}))
 
     # ---- pair functors ---------------------------------------------------
     def calc_en(self, r2, k1, k2):

@@ -45,6 +45,7 @@
 #include "EwaldCached.h"
 #include "NoEwald.h"
 #include "FFParticle.h"
+#include "FFExp6.h"
 #include "TrialMol.h"
 #undef private
 #undef protected
@@ -125,6 +126,13 @@ void dump_static(Dump &out, StaticVals &sv, System &sys) {
   out.f64("ff.sigmaSq", fp.sigmaSq, fp.count * fp.count);
   out.f64("ff.epsilon_cn", fp.epsilon_cn, fp.count * fp.count);
   out.f64("ff.n", fp.n, fp.count * fp.count);
+  out.f64("ff.dielectric", ff.dielectric);
+  if (ff.exp6) {
+    FF_EXP6 &fe = static_cast<FF_EXP6 &>(fp);
+    out.f64("ff.rMin", fe.rMin, fp.count * fp.count);
+    out.f64("ff.expConst", fe.expConst, fp.count * fp.count);
+    out.f64("ff.rMaxSq", fe.rMaxSq, fp.count * fp.count);
+  }
   out.xyz("coords", sys.coordinates);
   out.xyz("com", sys.com);
   out.i32("particleKind", sys.calcEnergy.particleKind);

@@ -41,4 +41,8 @@ SMALL_SYSTEMS = {
     "mixture_std": lambda: synth.make_mixture(),
     "mixture_shift": lambda: synth.make_mixture(vdw_kind=synth.VDW_SHIFT),
     "mixture_switch": lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.5),
+    "mixture_exp6": lambda: synth.make_mixture(vdw_kind=synth.VDW_EXP6, n_b_exp=16.0,
+                                               du_eps=12.0, du_sigma=1.2),
+    "mixture_martini": lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.0,
+                                                  martini=True, ewald=False, n_b_exp=12.0),
 }

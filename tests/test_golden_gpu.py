@@ -26,7 +26,11 @@ def gold(request):
     e.init_forcefield(d["ff.sigmaSq"], d["ff.epsilon_cn"], d["ff.n"], int(d["ff.vdwKind"][0]),
                       int(d["ff.kindCount"][0]), float(d["ff.rCut"][0]), d["ff.rCutCoulomb"][:1],
                       float(d["ff.rCutLow"][0]), float(d["ff.rswitch"][0]), d["ff.alpha"][:1],
-                      int(d["ff.ewald"][0]), int(d["ff.electrostatic"][0]))
+                      int(d["ff.ewald"][0]), int(d["ff.electrostatic"][0]),
+                      is_martini=int(d["ff.isMartini"][0]),
+                      dielectric=float(d["ff.dielectric"][0]) if "ff.dielectric" in d else 1.0)
+    if "ff.rMin" in d:
+        e.init_exp6(d["ff.rMin"], d["ff.expConst"], d["ff.rMaxSq"])
     e.init_topology(d["particleKind"], d["particleMol"], d["particleCharge"], d["molStart"])
     e.set_box_molecules(0, d["box0.mols"])
     e.set_box_axes(0, d["box0.axis"])

@@ -25,9 +25,18 @@ def test_generator_matches_what_reference_parsed(name):
     assert np.array_equal(s.kind, d["particleKind"])
     assert np.array_equal(s.axis, d["box0.axis"])
     sig, eps, nn = s.ff.tables()
-    assert np.array_equal(sig, d["ff.sigmaSq"])          # FFParticle::Blend
-    assert np.array_equal(eps, d["ff.epsilon_cn"])
+    if s.ff.is_martini:   # CHARMM-unit round trip of the parameter file: 1e-14, not bit-exact
+        assert np.allclose(sig, d["ff.sigmaSq"], rtol=1e-13, atol=0)
+        assert np.allclose(eps, d["ff.epsilon_cn"], rtol=1e-13, atol=0)
+    else:
+        assert np.array_equal(sig, d["ff.sigmaSq"])          # FFParticle::Blend
+        assert np.array_equal(eps, d["ff.epsilon_cn"])
     assert np.array_equal(nn, d["ff.n"])
+    if s.ff.vdw_kind == synth.VDW_EXP6:   # Brent roots: the reference works in float
+        r_min, exp_c, r_max_sq = s.ff.exp6_tables()
+        assert np.allclose(r_min, d["ff.rMin"], rtol=1e-6)
+        assert np.allclose(exp_c, d["ff.expConst"], rtol=1e-13)
+        assert np.allclose(r_max_sq, d["ff.rMaxSq"], rtol=1e-5)
     assert s.ff.alpha == d["ff.alpha"][0]                 # Forcefield.cpp:80
     assert s.ff.recip_rcut == d["ff.recip_rcut"][0]       # Forcefield.cpp:82
     # the reference re-wraps whole molecules on load; atoms stay congruent mod L
