@@ -32,6 +32,10 @@ struct BoxParams {
   // Martini switch (FF_SWITCH_MARTINI::Init, src/FFSwitchMartini.h:121-213)
   const double *mAn, *mBn, *mCn, *mSign, *mSig6;
   double rOn, A6, B6, C6, A1, B1, C1, diElectric_1;
+  // non-orthogonal cell: rows of B = normalised cell vectors, Bi = inverse of B
+  // (BoxDimensionsNonOrth, src/BoxDimensionsNonOrth.h:79-109); ax[] = edge lengths
+  int nonOrth;
+  double B[9], Bi[9];
 };
 
 __device__ __forceinline__ double min_image(double raw, double ax, double half) {
@@ -41,6 +45,27 @@ __device__ __forceinline__ double min_image(double raw, double ax, double half) 
   else if (raw < -half)
     raw += ax;
   return raw;
+}
+
+// BoxDimensions::MinImage / BoxDimensionsNonOrth::MinImage on a difference vector:
+// unslant (v * Bi), signed wrap per axis, slant back (v * B).
+__device__ __forceinline__ void min_image_vec(const BoxParams &p, double &dx, double &dy,
+                                              double &dz) {
+  if (p.nonOrth) {
+    double ux = dx * p.Bi[0] + dy * p.Bi[3] + dz * p.Bi[6];
+    double uy = dx * p.Bi[1] + dy * p.Bi[4] + dz * p.Bi[7];
+    double uz = dx * p.Bi[2] + dy * p.Bi[5] + dz * p.Bi[8];
+    ux = min_image(ux, p.ax[0], p.half[0]);
+    uy = min_image(uy, p.ax[1], p.half[1]);
+    uz = min_image(uz, p.ax[2], p.half[2]);
+    dx = ux * p.B[0] + uy * p.B[3] + uz * p.B[6];
+    dy = ux * p.B[1] + uy * p.B[4] + uz * p.B[7];
+    dz = ux * p.B[2] + uy * p.B[5] + uz * p.B[8];
+  } else {
+    dx = min_image(dx, p.ax[0], p.half[0]);
+    dy = min_image(dy, p.ax[1], p.half[1]);
+    dz = min_image(dz, p.ax[2], p.half[2]);
+  }
 }
 
 // One definition of r^2 so that the cut-off test and the functor see the

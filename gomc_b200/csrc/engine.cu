@@ -99,6 +99,8 @@ struct KSet {
 struct BoxState {
   double axis[3] = {0, 0, 0};
   bool haveAxes = false;
+  bool nonOrth = false;
+  double B[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Bi[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   std::vector<int> hMols, hAtoms, hCharged;
   DevBuf<int> molList, atomList, chargedList;
   int nMols = 0, nAtoms = 0, nCharged = 0;
@@ -207,6 +209,11 @@ BoxParams make_params(const gomcb200_engine *e, int b) {
   p.A6 = e->mA6; p.B6 = e->mB6; p.C6 = e->mC6;
   p.A1 = e->mA1; p.B1 = e->mB1; p.C1 = e->mC1;
   p.diElectric_1 = e->diElectric_1;
+  p.nonOrth = bx.nonOrth;
+  for (int i = 0; i < 9; ++i) {
+    p.B[i] = bx.B[i];
+    p.Bi[i] = bx.Bi[i];
+  }
   return p;
 }
 
@@ -243,8 +250,10 @@ int ensure_cells(gomcb200_engine *e, int b) {
     int ed = (int)std::floor(bx.axis[d] / br);
     g.edge[d] = std::max(ed, 3);
     g.cellSize[d] = bx.axis[d] / g.edge[d];
-    g.generic[d] = g.edge[d] < 4;
+    g.generic[d] = g.edge[d] < 4 || bx.nonOrth;
   }
+  g.nonOrth = bx.nonOrth;
+  for (int i = 0; i < 9; ++i) g.Bi[i] = bx.Bi[i];
   g.nCells = g.edge[0] * g.edge[1] * g.edge[2];
   bx.grid = g;
   CK(bx.keys.reserve(n + 1));
@@ -390,8 +399,76 @@ struct RowRec {
 };
 
 // Enumerates the half-space k list.  ks == nullptr: count only.
+// Ewald::RecipInitNonOrth / RecipCountInit for a slanted cell (src/Ewald.cpp:905-1018):
+// reciprocal rows = adjoint(cell) * 2 pi / det; no (a,b)-row table (the valid c
+// range of a row is not symmetric), so such boxes use the direct kernels.
+int recip_enumerate_nonorth(const gomcb200_engine *e, int b, const double ax[3], KSet *ks) {
+  const BoxState &bx = e->box[b];
+  const double alpha = e->alpha[b];
+  const double recip_rcut = e->recipRcut[b];
+  const double rr2 = recip_rcut * recip_rcut;
+  const double alpsqr4 = 1.0 / (4.0 * (alpha * alpha));
+  double cb[9], inv[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) cb[3 * r + c] = bx.B[3 * r + c] * ax[r];
+  auto X = [&](int i) { return cb[3 * i]; };
+  auto Y = [&](int i) { return cb[3 * i + 1]; };
+  auto Z = [&](int i) { return cb[3 * i + 2]; };
+  inv[0] = Y(1) * Z(2) - Y(2) * Z(1);   // XYZArray::AdjointMatrix, src/XYZArray.h:507-522
+  inv[1] = Y(2) * Z(0) - Y(0) * Z(2);
+  inv[2] = Y(0) * Z(1) - Y(1) * Z(0);
+  inv[3] = X(2) * Z(1) - X(1) * Z(2);
+  inv[4] = X(0) * Z(2) - X(2) * Z(0);
+  inv[5] = X(1) * Z(0) - X(0) * Z(1);
+  inv[6] = X(1) * Y(2) - X(2) * Y(1);
+  inv[7] = X(2) * Y(0) - X(0) * Y(2);
+  inv[8] = X(0) * Y(1) - X(1) * Y(0);
+  const double det = X(0) * inv[0] + X(1) * inv[1] + X(2) * inv[2];
+  const double bxc[3] = {Y(1) * Z(2) - Z(1) * Y(2), Z(1) * X(2) - X(1) * Z(2),
+                         X(1) * Y(2) - Y(1) * X(2)};
+  const double volume = std::fabs(X(0) * bxc[0] + Y(0) * bxc[1] + Z(0) * bxc[2]);
+  for (int i = 0; i < 9; ++i) inv[i] *= (2.0 * M_PI) / det;
+  const double vol = volume / (4.0 * M_PI);
+  int nmax[3];
+  for (int d = 0; d < 3; ++d) nmax[d] = int(recip_rcut * ax[d] / (2.0 * M_PI)) + 1;
+  if (ks) {
+    ks->hkx.clear(); ks->hky.clear(); ks->hkz.clear(); ks->hhsqr.clear();
+    ks->hprefact.clear();
+    for (int d = 0; d < 3; ++d) { ks->nmax[d] = nmax[d]; ks->cv[d] = 0.0; }
+    ks->kmax = std::max(std::max(nmax[0], nmax[1]), std::max(nmax[1], nmax[2]));
+  }
+  int counter = 0;
+  for (int ix = 0; ix <= nmax[0]; ix++) {
+    int nky_min = (ix == 0) ? 0 : -nmax[1];
+    for (int iy = nky_min; iy <= nmax[1]; iy++) {
+      int nkz_min = (ix == 0 && iy == 0) ? 1 : -nmax[2];
+      for (int iz = nkz_min; iz <= nmax[2]; iz++) {
+        double kX = inv[0] * ix + inv[1] * iy + inv[2] * iz;
+        double kY = inv[3] * ix + inv[4] * iy + inv[5] * iz;
+        double kZ = inv[6] * ix + inv[7] * iy + inv[8] * iz;
+        double ksqr = kX * kX + kY * kY + kZ * kZ;
+        if (ksqr < rr2) {
+          if (ks) {
+            ks->hkx.push_back(kX);
+            ks->hky.push_back(kY);
+            ks->hkz.push_back(kZ);
+            ks->hhsqr.push_back(ksqr);
+            ks->hprefact.push_back(kQQFact * exp(-ksqr * alpsqr4) / (ksqr * vol));
+          }
+          counter++;
+        }
+      }
+    }
+  }
+  return counter;
+}
+
 int recip_enumerate(const gomcb200_engine *e, int b, const double ax[3], KSet *ks,
                     std::vector<RowRec> *rowsOut) {
+  if (e->box[b].nonOrth) {
+    if (rowsOut) rowsOut->clear();
+    return recip_enumerate_nonorth(e, b, ax, ks);
+  }
   const double alpha = e->alpha[b];
   const double recip_rcut = e->recipRcut[b];
   const double rr2 = recip_rcut * recip_rcut;
@@ -831,10 +908,21 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     int per = nAt > 0 ? (nAt + nSlabs - 1) / nSlabs : 1;
     nSlabs = nAt > 0 ? (nAt + per - 1) / per : 1;
     CK(e->part.reserve((size_t)nSlabs * 2 * nkStride + 64));
-    dim3 grid(nBlocks, nSlabs);
-    k_recip_direct<<<grid, 256, 0, e->stream>>>(nk, nkStride, nAt, per, bx.packed.p,
-                                               ks.kx.p, ks.ky.p, ks.kz.p, e->part.p);
-    e->launches += 1;
+    // multi-GPU: a contiguous share of the k list per rank, zero elsewhere
+    const int k0 = (int)(((long long)nk * e->shardRank) / e->shardWorld);
+    const int k1 = (int)(((long long)nk * (e->shardRank + 1)) / e->shardWorld);
+    if (e->shardWorld > 1)
+      CK(cudaMemsetAsync(e->part.p, 0, sizeof(double) * (size_t)nSlabs * 2 * nkStride,
+                         e->stream));
+    if (k1 > k0 && nAt > 0) {
+      dim3 grid((k1 - k0 + 255) / 256, nSlabs);
+      k_recip_direct<<<grid, 256, 0, e->stream>>>(k0, k1, nkStride, nAt, per, bx.packed.p,
+                                                 ks.kx.p, ks.ky.p, ks.kz.p, e->part.p);
+      e->launches += 1;
+    } else if (e->shardWorld == 1) {
+      CK(cudaMemsetAsync(e->part.p, 0, sizeof(double) * (size_t)nSlabs * 2 * nkStride,
+                         e->stream));
+    }
   }
   CK(cudaGetLastError());
   if (e->timing) cudaEventRecord(e->ev[3], e->stream);
@@ -1251,6 +1339,23 @@ int gomcb200_set_box_axes(gomcb200_engine *e, int box, const double axis[3]) {
   return 0;
 }
 
+int gomcb200_set_box_cell_basis(gomcb200_engine *e, int box, const double cellBasis[9],
+                                const double cellBasisInv[9], const double axis[3]) {
+  if (!e || box < 0 || box >= e->nBoxes || !axis) return fail(GOMCB200_EINVAL, "bad arguments");
+  int rc = gomcb200_set_box_axes(e, box, axis);
+  if (rc) return rc;
+  BoxState &bx = e->box[box];
+  bx.nonOrth = cellBasis != nullptr;
+  if (cellBasis) {
+    if (!cellBasisInv) return fail(GOMCB200_EINVAL, "cellBasisInv missing");
+    for (int i = 0; i < 9; ++i) {
+      bx.B[i] = cellBasis[i];
+      bx.Bi[i] = cellBasisInv[i];
+    }
+  }
+  return 0;
+}
+
 int gomcb200_set_coords(gomcb200_engine *e, const double *x, const double *y, const double *z,
                         int first, int count) {
   if (!e || !e->haveTopo) return fail(GOMCB200_EINVAL, "topology not initialised");
@@ -1468,6 +1573,8 @@ int gomcb200_recip_init(gomcb200_engine *e, int box, const double axis[3], int *
                 e->imageTotal);
   int rc = upload_kset(e, ks);
   if (rc) return rc;
+  ks.mmaValid = false;
+  ks.fmValid = false;
   if (!rows.empty()) {
     rc = build_plan(e, ks, rows);
     if (rc) return rc;

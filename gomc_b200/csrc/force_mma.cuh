@@ -296,9 +296,8 @@ __global__ void __launch_bounds__(128)
     double constValue = p.alpha * kTwoOverSqrtPi;
     for (int j = molStart[m]; j < molStart[m + 1]; ++j) {
       if (j == a) continue;
-      double dx = min_image(xa - x[j], p.ax[0], p.half[0]);
-      double dy = min_image(ya - y[j], p.ax[1], p.half[1]);
-      double dz = min_image(za - z[j], p.ax[2], p.half[2]);
+      double dx = xa - x[j], dy = ya - y[j], dz = za - z[j];
+      min_image_vec(p, dx, dy, dz);
       double r2 = dx * dx + dy * dy + dz * dz;
       double dist = sqrt(r2);
       double ex = exp(-1.0 * p.alphaSq * r2);

@@ -24,11 +24,21 @@ struct CellGrid {
   int nCells;
   double cellSize[3];
   int generic[3];  // 1: fewer than 4 cells on that axis -> per-pair min-image
+  int nonOrth;     // cells are assigned in unslant coordinates (src/CellList.h:88-101)
+  double Bi[9];
 };
 
 // CellList::PositionToCell, src/CellList.h:88-101 (orthogonal box).
 __device__ __forceinline__ int position_to_cell(const CellGrid &g, double x,
                                                 double y, double z) {
+  if (g.nonOrth) {  // BoxDimensionsNonOrth::TransformUnSlant
+    double ux = x * g.Bi[0] + y * g.Bi[3] + z * g.Bi[6];
+    double uy = x * g.Bi[1] + y * g.Bi[4] + z * g.Bi[7];
+    double uz = x * g.Bi[2] + y * g.Bi[5] + z * g.Bi[8];
+    x = ux;
+    y = uy;
+    z = uz;
+  }
   int cx = (int)(x / g.cellSize[0]);
   int cy = (int)(y / g.cellSize[1]);
   int cz = (int)(z / g.cellSize[2]);
@@ -196,9 +206,13 @@ __device__ __forceinline__ void warp_probe(
       dy = (yi - jload<SM>(ja.y, ja.sy, j)) + rg.sy;
       dz = (zi - jload<SM>(ja.z, ja.sz, j)) + rg.sz;
       if (GEN) {
-        if (generic[0]) dx = min_image(dx, p.ax[0], p.half[0]);
-        if (generic[1]) dy = min_image(dy, p.ax[1], p.half[1]);
-        if (generic[2]) dz = min_image(dz, p.ax[2], p.half[2]);
+        if (p.nonOrth) {
+          min_image_vec(p, dx, dy, dz);
+        } else {
+          if (generic[0]) dx = min_image(dx, p.ax[0], p.half[0]);
+          if (generic[1]) dy = min_image(dy, p.ax[1], p.half[1]);
+          if (generic[2]) dz = min_image(dz, p.ax[2], p.half[2]);
+        }
       }
       double r2 = dist_sq(dx, dy, dz);
       in = p.boxRcutSq > r2;  // BoxDimensions::InRcut, strict
@@ -506,9 +520,8 @@ __global__ void k_torque(BoxParams p, int nMolsBox,
   int m = molList[t];
   double a = 0.0, b = 0.0, c = 0.0;
   for (int i = molStart[m]; i < molStart[m + 1]; ++i) {
-    double dx = min_image(x[i] - cx[m], p.ax[0], p.half[0]);
-    double dy = min_image(y[i] - cy[m], p.ax[1], p.half[1]);
-    double dz = min_image(z[i] - cz[m], p.ax[2], p.half[2]);
+    double dx = x[i] - cx[m], dy = y[i] - cy[m], dz = z[i] - cz[m];
+    min_image_vec(p, dx, dy, dz);
     double fx = afx[i] + rfx[i], fy = afy[i] + rfy[i], fz = afz[i] + rfz[i];
     a += dy * fz - dz * fy;
     b += dz * fx - dx * fz;

@@ -41,12 +41,12 @@ __global__ void k_pack_charged(int n, const int *__restrict__ chargedAtoms,
 // part[(slab*2 + {0,1})*nkStride + k].
 constexpr int kDirectTile = 256;
 __global__ void __launch_bounds__(256)
-    k_recip_direct(int nk, int nkStride, int nAtoms, int atomsPerSlab,
+    k_recip_direct(int k0, int nk, int nkStride, int nAtoms, int atomsPerSlab,
                    const double4 *__restrict__ pb, const double *__restrict__ kx,
                    const double *__restrict__ ky, const double *__restrict__ kz,
                    double *__restrict__ part) {
   __shared__ double4 tile[kDirectTile];
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;  // this rank's k range is [k0, nk)
   int slab = blockIdx.y;
   int a0 = slab * atomsPerSlab;
   int a1 = min(nAtoms, a0 + atomsPerSlab);
@@ -217,9 +217,8 @@ __global__ void __launch_bounds__(128)
       double constValue = p.alpha * kTwoOverSqrtPi;
       for (int j = molStart[m]; j < molStart[m + 1]; ++j) {
         if (j == a) continue;
-        double dx = min_image(xa - x[j], p.ax[0], p.half[0]);
-        double dy = min_image(ya - y[j], p.ax[1], p.half[1]);
-        double dz = min_image(za - z[j], p.ax[2], p.half[2]);
+        double dx = xa - x[j], dy = ya - y[j], dz = za - z[j];
+        min_image_vec(p, dx, dy, dz);
         double r2 = dx * dx + dy * dy + dz * dz;
         double dist = sqrt(r2);
         double ex = exp(-1.0 * p.alphaSq * r2);
@@ -284,9 +283,8 @@ __global__ void __launch_bounds__(256)
       self += q[i] * q[i];
       if (fabs(q[i]) < 0.000000001) continue;
       for (int j = i + 1; j < e; ++j) {
-        double dx = min_image(x[i] - x[j], p.ax[0], p.half[0]);
-        double dy = min_image(y[i] - y[j], p.ax[1], p.half[1]);
-        double dz = min_image(z[i] - z[j], p.ax[2], p.half[2]);
+        double dx = x[i] - x[j], dy = y[i] - y[j], dz = z[i] - z[j];
+        min_image_vec(p, dx, dy, dz);
         double dist = sqrt(dx * dx + dy * dy + dz * dz);
         corr += q[i] * q[j] * erf(p.alpha * dist) / dist;
       }

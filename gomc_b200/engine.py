@@ -36,6 +36,7 @@ _SIGS = {
     "gomcb200_init_topology": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _dp, _ip]),
     "gomcb200_set_box_molecules": (C.c_int, [_vp, C.c_int, _ip, C.c_int]),
     "gomcb200_set_box_axes": (C.c_int, [_vp, C.c_int, _dp]),
+    "gomcb200_set_box_cell_basis": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
     "gomcb200_set_coords": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
     "gomcb200_get_coords": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
     "gomcb200_set_com": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
@@ -169,6 +170,11 @@ class Engine:
     def set_box_axes(self, box, axis):
         a, pa = _d(axis)
         self._ck(self.L.gomcb200_set_box_axes(self.h, box, pa))
+
+    def set_box_cell_basis(self, box, cell_basis, cell_basis_inv, axis):
+        (b, pb), (bi, pbi), (a, pa) = _d(np.reshape(cell_basis, -1)), \
+            _d(np.reshape(cell_basis_inv, -1)), _d(axis)
+        self._ck(self.L.gomcb200_set_box_cell_basis(self.h, box, pb, pbi, pa))
 
     def set_coords(self, x, y, z, first=0):
         (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
@@ -367,7 +373,10 @@ class Engine:
             e.init_exp6(*ff.exp6_tables())
         e.init_topology(s.kind, s.mol, s.charge, s.mol_start)
         e.set_box_molecules(0, np.arange(s.n_mols, dtype=np.int32))
-        e.set_box_axes(0, s.axis)
+        if getattr(s, "cell_basis", None) is not None:
+            e.set_box_cell_basis(0, s.cell_basis, s.cell_basis_inv, s.axis)
+        else:
+            e.set_box_axes(0, s.axis)
         e.set_coords(s.x, s.y, s.z)
         e.set_com(*s.com())
         if recip and ff.ewald and ff.electrostatic:

@@ -82,6 +82,14 @@ public:
     double a[3] = {axis.x, axis.y, axis.z};
     check(gomcb200_set_box_axes(e_, box, a), "UpdateCellBasisCUDA");
   }
+  // UpdateCellBasisCUDA + UpdateInvCellBasisCUDA for a BoxDimensionsNonOrth box
+  // (src/CalculateEnergy.cpp:177-190): normalised cell vectors, their inverse, edge lengths
+  void SetBoxCellBasis(int box, const double cellBasis[9], const double cellBasisInv[9],
+                       const XYZ &axis) {
+    double a[3] = {axis.x, axis.y, axis.z};
+    check(gomcb200_set_box_cell_basis(e_, box, cellBasis, cellBasisInv, a),
+          "UpdateInvCellBasisCUDA");
+  }
   void SetCoordinates(const XYZView &c) {
     check(gomcb200_set_coords(e_, c.x, c.y, c.z, 0, c.count), "SetCoordinates");
   }

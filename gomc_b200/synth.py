@@ -127,6 +127,12 @@ class System:
     charge: np.ndarray        # per atom
     mol_start: np.ndarray     # int32 [nMols+1]
     mol_kind: np.ndarray      # int32 per molecule
+    # non-orthogonal cell (None for an orthogonal box): rows = cell vectors a, b, c;
+    # cell_basis = the normalised rows, cell_basis_inv = its inverse
+    # (BoxDimensionsNonOrth::Init, src/BoxDimensionsNonOrth.cpp:14-110); axis = edge lengths
+    cell_vectors: np.ndarray | None = None
+    cell_basis: np.ndarray | None = None
+    cell_basis_inv: np.ndarray | None = None
 
     @property
     def n_atoms(self) -> int:
@@ -140,6 +146,16 @@ class System:
         """Geometric centre of every molecule after unwrapping about its first
         atom, wrapped back into the box (what COM::CalcCOM does with
         uniform weights; used only as the torque reference point)."""
+        if self.cell_basis is not None:
+            r = np.stack([self.x, self.y, self.z], 1)
+            u = r @ self.cell_basis_inv
+            ref = u[self.mol_start[:-1]]
+            lens = np.diff(self.mol_start)
+            d = u - np.repeat(ref, lens, axis=0)
+            d -= self.axis * np.round(d / self.axis)
+            c = ref + np.add.reduceat(d, self.mol_start[:-1], axis=0) / lens[:, None]
+            c = np.mod(c, self.axis) @ self.cell_basis
+            return c[:, 0].copy(), c[:, 1].copy(), c[:, 2].copy()
         L = self.axis
         cx = np.zeros(self.n_mols)
         cy = np.zeros(self.n_mols)
@@ -186,10 +202,13 @@ def _lattice(n, L, rng, jitter):
     return pos
 
 
-def _assemble(name, ff, mol_kinds, counts, L, seed, jitter=0.3):
+def _assemble(name, ff, mol_kinds, counts, L, seed, jitter=0.3, cell_vectors=None):
     rng = np.random.default_rng(seed)
     n_mols = int(sum(counts))
     centres = _lattice(n_mols, L, rng, jitter)
+    if cell_vectors is not None:      # lattice sites in fractional coordinates of the cell
+        cell_vectors = np.asarray(cell_vectors, dtype=np.float64)
+        centres = (centres / L) @ cell_vectors
     order = rng.permutation(n_mols)          # mix kinds over lattice sites
     type_index = {t: i for i, t in enumerate(ff.type_names)}
     xs, kinds, mols, charges, starts, mkind = [], [], [], [], [0], []
@@ -211,13 +230,27 @@ def _assemble(name, ff, mol_kinds, counts, L, seed, jitter=0.3):
         mkind.extend([k] * cnt)
         m += cnt
     pos = np.concatenate(xs)
-    pos = np.mod(pos, L)
-    pos = np.round(pos, 3)
-    pos[pos >= L] -= L     # rounding may land exactly on L
-    pos = np.round(pos, 3)
+    extra = {}
+    if cell_vectors is not None:
+        lengths = np.linalg.norm(cell_vectors, axis=1)
+        basis = cell_vectors / lengths[:, None]
+        basis_inv = np.linalg.inv(basis)
+        pos = np.round(pos, 3)
+        u = np.mod(pos @ basis_inv, lengths)          # wrap in unslant space
+        u = np.minimum(u, np.nextafter(lengths, 0))
+        pos = u @ basis
+        extra = dict(cell_vectors=cell_vectors, cell_basis=basis, cell_basis_inv=basis_inv)
+        axis = lengths
+    else:
+        pos = np.mod(pos, L)
+        pos = np.round(pos, 3)
+        pos[pos >= L] -= L     # rounding may land exactly on L
+        pos = np.round(pos, 3)
+        axis = np.array([L, L, L], dtype=np.float64)
     return System(
+        **extra,
         name=name, ff=ff, mol_kinds=list(mol_kinds),
-        axis=np.array([L, L, L], dtype=np.float64),
+        axis=axis,
         x=np.ascontiguousarray(pos[:, 0]), y=np.ascontiguousarray(pos[:, 1]),
         z=np.ascontiguousarray(pos[:, 2]),
         kind=np.concatenate(kinds).astype(np.int32),
@@ -249,8 +282,17 @@ def make_argon(n_atoms=4000, density=0.0213, seed=123, r_cut=10.0, vdw_kind=VDW_
     return _assemble(f"argon{n_atoms}", ff, [mk], [n_atoms], L, seed)
 
 
+def triclinic_cell(L, angles_deg=(80.0, 75.0, 70.0)):
+    """Cell vectors with edge length L and the given (alpha, beta, gamma)
+    (same construction as BoxDimensions::Init, src/BoxDimensions.cpp:21-39)."""
+    al, be, ga = (math.cos(math.radians(a)) for a in angles_deg)
+    t = (al - be * ga) / math.sqrt(1.0 - ga * ga)
+    return L * np.array([[1.0, 0.0, 0.0], [ga, math.sqrt(1.0 - ga * ga), 0.0],
+                         [be, t, math.sqrt(1.0 - be * be - t * t)]])
+
+
 def make_spce(n_mols=10000, density=0.0334, seed=123, r_cut=10.0, r_cut_coulomb=None,
-              tolerance=1e-5, vdw_kind=VDW_STD, r_switch=0.0, ewald=True):
+              tolerance=1e-5, vdw_kind=VDW_STD, r_switch=0.0, ewald=True, cell_vectors=None):
     """Configs 2 and 4: rigid SPC/E water, Ewald on."""
     rcc = r_cut if r_cut_coulomb is None else r_cut_coulomb
     L = round((n_mols / density) ** (1.0 / 3.0), 3)
@@ -261,7 +303,7 @@ def make_spce(n_mols=10000, density=0.0334, seed=123, r_cut=10.0, r_cut_coulomb=
                     bond_params=[("OW", "HW", 1.0)],
                     angle_params=[("HW", "OW", "HW", 109.47)])
     return _assemble(f"spce{n_mols}", ff, [_spce_kind()], [n_mols], L, seed,
-                     jitter=0.15)
+                     jitter=0.15, cell_vectors=cell_vectors)
 
 
 def make_electrolyte(n_water=330000, n_pairs=5000, seed=123, r_cut=10.0,
@@ -331,8 +373,9 @@ def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
     # ---- PDB + PSF -------------------------------------------------------
     n = sys.n_atoms
     with open(os.path.join(out_dir, "box0.pdb"), "w") as f:
-        f.write("CRYST1%9.3f%9.3f%9.3f  90.00  90.00  90.00 P 1           1\n"
-                % tuple(sys.axis))
+        if sys.cell_vectors is None:   # (triclinic cells come from in.conf only)
+            f.write("CRYST1%9.3f%9.3f%9.3f  90.00  90.00  90.00 P 1           1\n"
+                    % tuple(sys.axis))
         for a in range(n):
             m = int(sys.mol[a])
             mk = sys.mol_kinds[int(sys.mol_kind[m])]
@@ -367,6 +410,7 @@ def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
         f.write("%8d !NDON: donors\n\n\n%8d !NACC: acceptors\n\n\n" % (0, 0))
     # ---- in.conf ---------------------------------------------------------
     L = sys.axis
+    CV = sys.cell_vectors if sys.cell_vectors is not None else np.diag(L)
     conf = f"""ExpertMode True
 Restart false
 PRNG INTSEED
@@ -396,9 +440,9 @@ AdjSteps 5
 DisFreq {0.40 if multiparticle else 0.60}
 RotFreq {0.40 if multiparticle and any(len(k.atom_names) > 1 for k in sys.mol_kinds) else (0.40 if not multiparticle else 0.0)}
 {('MultiParticleFreq ' + ('0.20' if any(len(k.atom_names) > 1 for k in sys.mol_kinds) else '0.60')) if multiparticle else ''}
-CellBasisVector1 0 {float(L[0])!r} 0.0 0.0
-CellBasisVector2 0 0.0 {float(L[1])!r} 0.0
-CellBasisVector3 0 0.0 0.0 {float(L[2])!r}
+CellBasisVector1 0 {float(CV[0][0])!r} {float(CV[0][1])!r} {float(CV[0][2])!r}
+CellBasisVector2 0 {float(CV[1][0])!r} {float(CV[1][1])!r} {float(CV[1][2])!r}
+CellBasisVector3 0 {float(CV[2][0])!r} {float(CV[2][1])!r} {float(CV[2][2])!r}
 CBMC_First 10
 CBMC_Nth 8
 CBMC_Ang 50

@@ -29,7 +29,7 @@
  *
  * Arithmetic is IEEE double throughout; lambda == 1 (no fractional molecule).
  * Potentials: VDW (Mie), SHIFT, SWITCH, SWITCH+Martini, EXP6.
- * Orthogonal boxes only in this revision (gomcb200_set_box_axes).
+ * Orthogonal (gomcb200_set_box_axes) and non-orthogonal (gomcb200_set_box_cell_basis) cells.
  * Threading: one host thread per engine, like the reference.
  */
 #ifndef GOMC_B200_H
@@ -117,6 +117,17 @@ int gomcb200_set_box_molecules(gomcb200_engine *e, int box,
 /* UpdateCellBasisCUDA (ConstantDefinitionsCUDAKernel.cuh:38-39) for an
  * orthogonal cell: axis = BoxDimensions::axis.Get(box). */
 int gomcb200_set_box_axes(gomcb200_engine *e, int box, const double axis[3]);
+
+/* UpdateCellBasisCUDA + UpdateInvCellBasisCUDA (ConstantDefinitionsCUDAKernel.cuh:38-42)
+ * for a non-orthogonal cell: row-major 3x3, rows = the NORMALISED cell vectors
+ * (BoxDimensionsNonOrth::cellBasis[box]) and the inverse of that matrix
+ * (cellBasis_Inv[box]); axis = the cell edge lengths.  NULL matrices restore the
+ * orthogonal case.  Slanted boxes use the per-term reciprocal kernels (the valid
+ * c range of an (a,b) row is not symmetric there); the pair path is unchanged. */
+int gomcb200_set_box_cell_basis(gomcb200_engine *e, int box,
+                                const double cellBasis[9],
+                                const double cellBasisInv[9],
+                                const double axis[3]);
 
 /* Coordinates / centres of mass (System::coordinates, System::com), global
  * atom / molecule indexing; [first, first+count). */

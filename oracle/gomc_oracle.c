@@ -53,12 +53,36 @@ static inline double min_image_signed(double raw, double ax, double halfAx) {
 static inline double box_rcut(const orc_params *p) {
   return p->rCut > p->rCutCoulomb ? p->rCut : p->rCutCoulomb;
 }
+/* BoxDimensionsNonOrth::TransformUnSlant / TransformSlant,
+ * src/BoxDimensionsNonOrth.h:84-109 (row vector times matrix). */
+static inline void vec_mat(const double a[3], const double m[9], double out[3]) {
+  out[0] = a[0] * m[0] + a[1] * m[3] + a[2] * m[6];
+  out[1] = a[0] * m[1] + a[1] * m[4] + a[2] * m[7];
+  out[2] = a[0] * m[2] + a[1] * m[5] + a[2] * m[8];
+}
+/* BoxDimensions::MinImage (src/BoxDimensions.h:61-66) or the non-orthogonal
+ * override (src/BoxDimensionsNonOrth.cpp:240-245): unslant, wrap, slant. */
+static inline void min_image_vec(const orc_params *p, double d[3]) {
+  if (p->nonOrth) {
+    double u[3];
+    vec_mat(d, p->cellBasisInv, u);
+    u[0] = min_image_signed(u[0], p->axis[0], p->axis[0] * 0.5);
+    u[1] = min_image_signed(u[1], p->axis[1], p->axis[1] * 0.5);
+    u[2] = min_image_signed(u[2], p->axis[2], p->axis[2] * 0.5);
+    vec_mat(u, p->cellBasis, d);
+  } else {
+    d[0] = min_image_signed(d[0], p->axis[0], p->axis[0] * 0.5);
+    d[1] = min_image_signed(d[1], p->axis[1], p->axis[1] * 0.5);
+    d[2] = min_image_signed(d[2], p->axis[2], p->axis[2] * 0.5);
+  }
+}
 static inline int in_rcut(const orc_params *p, double boxRcutSq, double xi,
                           double yi, double zi, double xj, double yj,
                           double zj, double *distSq, double d[3]) {
-  d[0] = min_image_signed(xi - xj, p->axis[0], p->axis[0] * 0.5);
-  d[1] = min_image_signed(yi - yj, p->axis[1], p->axis[1] * 0.5);
-  d[2] = min_image_signed(zi - zj, p->axis[2], p->axis[2] * 0.5);
+  d[0] = xi - xj;
+  d[1] = yi - yj;
+  d[2] = zi - zj;
+  min_image_vec(p, d);
   *distSq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
   return boxRcutSq > *distSq;
 }
@@ -318,8 +342,16 @@ int orc_cell_edges(const orc_params *p, int edge[3]) {
 }
 
 /* CellList::PositionToCell, src/CellList.h:88-101 (orthogonal: unslant = id) */
+static const orc_params *g_cellParams = 0; /* set by csr_make / orc_cell_list_build */
 static inline int position_to_cell(const double cellSize[3], const int edge[3],
                                    double px, double py, double pz) {
+  if (g_cellParams && g_cellParams->nonOrth) { /* TransformUnSlant first */
+    double a[3] = {px, py, pz}, u[3];
+    vec_mat(a, g_cellParams->cellBasisInv, u);
+    px = u[0];
+    py = u[1];
+    pz = u[2];
+  }
   int cx = (int)(px / cellSize[0]);
   int cy = (int)(py / cellSize[1]);
   int cz = (int)(pz / cellSize[2]);
@@ -352,6 +384,7 @@ int orc_cell_list_build(const orc_params *p, int nAtomsTotal, const double *x,
                         int *mapParticleToCell, int *neighborList) {
   int edge[3];
   int nCells = orc_cell_edges(p, edge);
+  g_cellParams = p;
   double cellSize[3] = {p->axis[0] / edge[0], p->axis[1] / edge[1],
                         p->axis[2] / edge[2]};
   /* counting sort by cell, scanning atoms in ascending index order: gives
@@ -645,9 +678,9 @@ int orc_calculate_torque(const orc_params *p, int nBoxMols, const int *boxMols,
     int m = boxMols[mi];
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (int a = molStart[m]; a < molStart[m + 1]; ++a) {
-      double dx = min_image_signed(x[a] - comX[m], p->axis[0], p->axis[0] * 0.5);
-      double dy = min_image_signed(y[a] - comY[m], p->axis[1], p->axis[1] * 0.5);
-      double dz = min_image_signed(z[a] - comZ[m], p->axis[2], p->axis[2] * 0.5);
+      double dd[3] = {x[a] - comX[m], y[a] - comY[m], z[a] - comZ[m]};
+      min_image_vec(p, dd);
+      double dx = dd[0], dy = dd[1], dz = dd[2];
       double fx = aFx[a] + rFx[a], fy = aFy[a] + rFy[a], fz = aFz[a] + rFz[a];
       /* geom::Cross, lib/GeomLib.h */
       sx += dy * fz - dz * fy;
@@ -682,7 +715,18 @@ double orc_energy_lrc(const orc_params *p, int nMolKinds,
                       const int *numKindInBox) {
   /* SHIFT/SWITCH have zero LRC (FFShift.h / FFSwitch.h EnergyLRC return 0) */
   if (p->vdwKind != ORC_VDW_STD) return 0.0;
-  double volInv = 1.0 / (p->axis[0] * p->axis[1] * p->axis[2]);
+  double volume = p->axis[0] * p->axis[1] * p->axis[2];
+  if (p->nonOrth) { /* |A . (B x C)|, BoxDimensionsNonOrth::Init */
+    double a[3], b[3], c[3];
+    for (int k = 0; k < 3; ++k) {
+      a[k] = p->cellBasis[k] * p->axis[0];
+      b[k] = p->cellBasis[3 + k] * p->axis[1];
+      c[k] = p->cellBasis[6 + k] * p->axis[2];
+    }
+    volume = fabs(a[0] * (b[1] * c[2] - b[2] * c[1]) + a[1] * (b[2] * c[0] - b[0] * c[2]) +
+                  a[2] * (b[0] * c[1] - b[1] * c[0]));
+  }
+  double volInv = 1.0 / volume;
   double en = 0.0;
   /* pairEnCorrections, src/Molecules.cpp (sum over atom pairs of the two
    * molecule kinds), then CalculateEnergy::EnergyCorrection :1261-1269 */
@@ -741,6 +785,73 @@ int orc_recip_init_orth(const orc_params *p, double *kx, double *ky,
             hsqr[counter] = ksqr;
             prefact[counter] =
                 ORC_QQFACT * exp(-ksqr * alpsqr4) / (ksqr * vol);
+          }
+          counter++;
+        }
+      }
+    }
+  }
+  return counter;
+}
+
+int orc_recip_init_nonorth(const orc_params *p, double *kx, double *ky,
+                           double *kz, double *hsqr, double *prefact,
+                           int *kmaxOut) {
+  /* src/Ewald.cpp:905-965: cellB = normalised basis scaled by the edge lengths,
+   * reciprocal rows = adjoint * 2 pi / det */
+  int counter = 0;
+  double alpsqr4 = 1.0 / (4.0 * (p->alpha * p->alpha));
+  double cb[9], inv[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) cb[3 * r + c] = p->cellBasis[3 * r + c] * p->axis[r];
+  /* XYZArray::AdjointMatrix, src/XYZArray.h:507-522 (x[i] = cb[3i], ...) */
+#define X(i) cb[3 * (i)]
+#define Y(i) cb[3 * (i) + 1]
+#define Z(i) cb[3 * (i) + 2]
+  inv[0] = Y(1) * Z(2) - Y(2) * Z(1);
+  inv[1] = Y(2) * Z(0) - Y(0) * Z(2);
+  inv[2] = Y(0) * Z(1) - Y(1) * Z(0);
+  inv[3] = X(2) * Z(1) - X(1) * Z(2);
+  inv[4] = X(0) * Z(2) - X(2) * Z(0);
+  inv[5] = X(1) * Z(0) - X(0) * Z(1);
+  inv[6] = X(1) * Y(2) - X(2) * Y(1);
+  inv[7] = X(2) * Y(0) - X(0) * Y(2);
+  inv[8] = X(0) * Y(1) - X(1) * Y(0);
+  double det = X(0) * inv[0] + X(1) * inv[1] + X(2) * inv[2];
+  /* volume = |A . (B x C)| (BoxDimensionsNonOrth::Init) */
+  double bxc[3] = {Y(1) * Z(2) - Z(1) * Y(2), Z(1) * X(2) - X(1) * Z(2),
+                   X(1) * Y(2) - Y(1) * X(2)};
+  double volume = fabs(X(0) * bxc[0] + Y(0) * bxc[1] + Z(0) * bxc[2]);
+#undef X
+#undef Y
+#undef Z
+  for (int i = 0; i < 9; ++i) inv[i] *= (2.0 * M_PI) / det;
+  double vol = volume / (4.0 * M_PI);
+  double rr2 = p->recip_rcut * p->recip_rcut;
+  int nkx_max = (int)(p->recip_rcut * p->axis[0] / (2.0 * M_PI)) + 1;
+  int nky_max = (int)(p->recip_rcut * p->axis[1] / (2.0 * M_PI)) + 1;
+  int nkz_max = (int)(p->recip_rcut * p->axis[2] / (2.0 * M_PI)) + 1;
+  if (kmaxOut) {
+    int m = nkx_max > nky_max ? nkx_max : nky_max;
+    *kmaxOut = m > nkz_max ? m : nkz_max;
+  }
+  for (int ix = 0; ix <= nkx_max; ix++) {
+    int nky_min = (ix == 0) ? 0 : -nky_max;
+    for (int iy = nky_min; iy <= nky_max; iy++) {
+      int nkz_min = (ix == 0 && iy == 0) ? 1 : -nkz_max;
+      for (int iz = nkz_min; iz <= nkz_max; iz++) {
+        /* Dot(cellB_Inv.Get(r), XYZ(x,y,z)) */
+        double kX = inv[0] * ix + inv[1] * iy + inv[2] * iz;
+        double kY = inv[3] * ix + inv[4] * iy + inv[5] * iz;
+        double kZ = inv[6] * ix + inv[7] * iy + inv[8] * iz;
+        double ksqr = kX * kX + kY * kY + kZ * kZ;
+        if (ksqr < rr2) {
+          if (kx) {
+            kx[counter] = kX;
+            ky[counter] = kY;
+            kz[counter] = kZ;
+            hsqr[counter] = ksqr;
+            prefact[counter] = ORC_QQFACT * exp(-ksqr * alpsqr4) / (ksqr * vol);
           }
           counter++;
         }

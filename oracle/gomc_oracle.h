@@ -56,6 +56,11 @@ typedef struct {
    * isMartini != 0; constants are derived from rCut, rOn, n, sigmaSq. */
   int isMartini;
   double diElectric_1;      /* 1 / forcefield.dielectric                        */
+  /* ---- non-orthogonal cell (src/BoxDimensionsNonOrth.{h,cpp}): row-major 3x3,
+   * rows = the NORMALISED cell basis vectors and the inverse of that matrix;
+   * axis[] then holds the cell edge lengths.  nonOrth == 0: ignored. */
+  int nonOrth;
+  double cellBasis[9], cellBasisInv[9];
 } orc_params;
 
 /* ---- cell list (src/CellList.cpp:138-285, src/CellList.h:88-101) ---------- */
@@ -142,6 +147,10 @@ double orc_calc_coulomb_vir(const orc_params *p, double distSq,
 int orc_recip_init_orth(const orc_params *p, double *kx, double *ky,
                         double *kz, double *hsqr, double *prefact,
                         int *kmaxOut);
+/* Ewald::RecipInitNonOrth, src/Ewald.cpp:905-965 (same calling convention). */
+int orc_recip_init_nonorth(const orc_params *p, double *kx, double *ky,
+                           double *kz, double *hsqr, double *prefact,
+                           int *kmaxOut);
 
 /* Ewald::BoxReciprocalSetup / BoxReciprocalSums, src/Ewald.cpp:193-361:
  * molecule-outer, k-inner, skipping |q|<1e-9 atoms (src/Ewald.cpp:107-111). */

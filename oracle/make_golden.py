@@ -37,6 +37,9 @@ CASES = {
     # Martini switch (ParaTypeMARTINI + Potential SWITCH), Ewald off -> switched Coulomb
     "mixture_martini": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.0,
                                                    martini=True, ewald=False, n_b_exp=12.0), 4, 5),
+    # non-orthogonal cell (80/75/70 degrees): BoxDimensionsNonOrth + RecipInitNonOrth
+    "spce216_triclinic": (lambda: synth.make_spce(
+        216, r_cut=6.0, cell_vectors=synth.triclinic_cell(20.494)), 6, 7),
     "mixture_martini_ewald": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.0,
                                                          martini=True, ewald=True, seed=4, n_b_exp=12.0), 4, 5),
 }

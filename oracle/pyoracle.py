@@ -29,7 +29,9 @@ class OrcParams(C.Structure):
                 ("recip_rcut", C.c_double), ("axis", C.c_double * 3),
                 ("sigmaSq", _dp), ("epsilon_cn", _dp), ("n", _dp),
                 ("rMin", _dp), ("expConst", _dp), ("rMaxSq", _dp),
-                ("isMartini", C.c_int), ("diElectric_1", C.c_double)]
+                ("isMartini", C.c_int), ("diElectric_1", C.c_double),
+                ("nonOrth", C.c_int), ("cellBasis", C.c_double * 9),
+                ("cellBasisInv", C.c_double * 9)]
 
 
 def build(force=False):
@@ -79,7 +81,8 @@ class Oracle:
 
     def __init__(self, *, vdw_kind, ewald, electrostatic, kind_count, r_cut, r_cut_low,
                  r_switch, r_cut_coulomb, alpha, recip_rcut, axis, sigma_sq, epsilon_cn, n,
-                 r_min=None, exp_const=None, r_max_sq=None, is_martini=0, dielectric=1.0):
+                 r_min=None, exp_const=None, r_max_sq=None, is_martini=0, dielectric=1.0,
+                 cell_basis=None, cell_basis_inv=None):
         self.L = lib()
         self._keep = [_d(sigma_sq), _d(epsilon_cn), _d(n)]
         if r_min is not None:
@@ -95,6 +98,13 @@ class Oracle:
             p.rMin, p.expConst, p.rMaxSq = (k[1] for k in self._keep[3:6])
         p.isMartini = int(is_martini)
         p.diElectric_1 = 1.0 / float(dielectric)
+        p.nonOrth = 0
+        if cell_basis is not None:
+            p.nonOrth = 1
+            for i, v in enumerate(np.asarray(cell_basis, dtype=np.float64).reshape(-1)):
+                p.cellBasis[i] = float(v)
+            for i, v in enumerate(np.asarray(cell_basis_inv, dtype=np.float64).reshape(-1)):
+                p.cellBasisInv[i] = float(v)
         self.p = p
         self.pp = C.byref(p)
 
@@ -107,6 +117,8 @@ class Oracle:
                    r_switch=ff.r_switch, r_cut_coulomb=ff.r_cut_coulomb, alpha=ff.alpha,
                    recip_rcut=ff.recip_rcut, axis=s.axis, sigma_sq=sig, epsilon_cn=eps, n=nn,
                    is_martini=ff.is_martini, dielectric=ff.dielectric,
+                   cell_basis=getattr(s, "cell_basis", None),
+                   cell_basis_inv=getattr(s, "cell_basis_inv", None),
                    **(dict(zip(("r_min", "exp_const", "r_max_sq"), ff.exp6_tables()))
                       if ff.vdw_kind == 3 else {}))
 
@@ -121,6 +133,8 @@ class Oracle:
                    sigma_sq=d["ff.sigmaSq"], epsilon_cn=d["ff.epsilon_cn"], n=d["ff.n"],
                    is_martini=sc(d, "ff.isMartini"),
                    dielectric=(sc(d, "ff.dielectric") if "ff.dielectric" in d else 1.0),
+                   cell_basis=d.get(f"box{box}.cellBasis") if not sc(d, f"box{box}.orthogonal") else None,
+                   cell_basis_inv=d.get(f"box{box}.cellBasisInv"),
                    **({"r_min": d["ff.rMin"], "exp_const": d["ff.expConst"],
                        "r_max_sq": d["ff.rMaxSq"]} if "ff.rMin" in d else {}))
 
@@ -212,10 +226,13 @@ class Oracle:
 
     # ---- reciprocal path -------------------------------------------------
     def recip_init_orth(self):
+        """RecipInit: the orthogonal or non-orthogonal enumeration, as Ewald::RecipInit
+        dispatches (src/Ewald.cpp:644-652)."""
         kmax = C.c_int()
-        nk = self.L.orc_recip_init_orth(self.pp, None, None, None, None, None, C.byref(kmax))
+        fn = self.L.orc_recip_init_nonorth if self.p.nonOrth else self.L.orc_recip_init_orth
+        nk = fn(self.pp, None, None, None, None, None, C.byref(kmax))
         arr = [np.zeros(nk) for _ in range(5)]
-        self.L.orc_recip_init_orth(self.pp, *[a.ctypes.data_as(_dp) for a in arr], C.byref(kmax))
+        fn(self.pp, *[a.ctypes.data_as(_dp) for a in arr], C.byref(kmax))
         return (*arr, kmax.value)   # kx, ky, kz, hsqr, prefact, kmax
 
     def box_recip_sums(self, box_mols, mol_start, x, y, z, charge, kx, ky, kz, k0=0, k1=None):

@@ -46,6 +46,7 @@
 #include "NoEwald.h"
 #include "FFParticle.h"
 #include "FFExp6.h"
+#include "BoxDimensionsNonOrth.h"
 #include "TrialMol.h"
 #undef private
 #undef protected
@@ -160,6 +161,18 @@ void dump_static(Dump &out, StaticVals &sv, System &sys) {
     out.f64(bname("axis", b), a3, 3);
     out.i32(bname("orthogonal", b), (int)sys.boxDimRef.orthogonal[b]);
     out.f64(bname("boxRcut", b), sys.boxDimRef.rCut[b]);
+    out.f64(bname("volume", b), sys.boxDimRef.volume[b]);
+    if (!sys.boxDimRef.orthogonal[b]) {
+      BoxDimensionsNonOrth &no = static_cast<BoxDimensionsNonOrth &>(sys.boxDimRef);
+      double cb[9], ci[9];
+      for (int r = 0; r < 3; ++r) {
+        XYZ v = no.cellBasis[b].Get(r), w = no.cellBasis_Inv[b].Get(r);
+        cb[3 * r] = v.x; cb[3 * r + 1] = v.y; cb[3 * r + 2] = v.z;
+        ci[3 * r] = w.x; ci[3 * r + 1] = w.y; ci[3 * r + 2] = w.z;
+      }
+      out.f64(bname("cellBasis", b), cb, 9);
+      out.f64(bname("cellBasisInv", b), ci, 9);
+    }
     std::vector<int> molsInBox, numKind;
     MoleculeLookup::box_iterator it = sys.molLookupRef.BoxBegin(b),
                                  end = sys.molLookupRef.BoxEnd(b);
@@ -283,7 +296,10 @@ int run_golden(int argc, char **argv) {
       // rigid displacement, large for odd t (tests PBC wrap), small otherwise;
       // every 4th move also puts the molecule on top of a neighbour to
       // exercise the overlap flag.
-      double amp = (t % 2) ? 0.45 * std::min(ax.x, std::min(ax.y, ax.z)) : 0.4;
+      // (slanted cells: keep the unslant displacement below one cell length, the
+      // reference's WrapPBC wraps only once)
+      double big = sys.boxDimRef.orthogonal[b] ? 0.45 : 0.2;
+      double amp = (t % 2) ? big * std::min(ax.x, std::min(ax.y, ax.z)) : 0.4;
       XYZ shift(U(rng) * amp, U(rng) * amp, U(rng) * amp);
       if (t % 4 == 3 && molsInBox.size() > 1) {
         uint other = molsInBox[(size_t)(rng() % molsInBox.size())];

@@ -28,6 +28,12 @@ def random_move(s, rng, m, amp):
     """Rigid displacement of molecule m by up to amp per axis, wrapped."""
     sl = slice(s.mol_start[m], s.mol_start[m + 1])
     d = rng.uniform(-amp, amp, size=3)
+    if getattr(s, "cell_basis", None) is not None:   # wrap in unslant coordinates
+        r = np.stack([s.x[sl], s.y[sl], s.z[sl]], 1) + d
+        u = np.mod(r @ s.cell_basis_inv, s.axis)
+        u = np.minimum(u, np.nextafter(s.axis, 0))
+        r = u @ s.cell_basis
+        return r[:, 0].copy(), r[:, 1].copy(), r[:, 2].copy()
     nx = np.mod(s.x[sl] + d[0], s.axis[0])
     ny = np.mod(s.y[sl] + d[1], s.axis[1])
     nz = np.mod(s.z[sl] + d[2], s.axis[2])
@@ -41,6 +47,8 @@ SMALL_SYSTEMS = {
     "mixture_std": lambda: synth.make_mixture(),
     "mixture_shift": lambda: synth.make_mixture(vdw_kind=synth.VDW_SHIFT),
     "mixture_switch": lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.5),
+    "spce_triclinic": lambda: synth.make_spce(
+        343, r_cut=6.0, cell_vectors=synth.triclinic_cell(24.5, (85.0, 70.0, 100.0))),
     "mixture_exp6": lambda: synth.make_mixture(vdw_kind=synth.VDW_EXP6, n_b_exp=16.0,
                                                du_eps=12.0, du_sigma=1.2),
     "mixture_martini": lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.0,

@@ -33,7 +33,10 @@ def gold(request):
         e.init_exp6(d["ff.rMin"], d["ff.expConst"], d["ff.rMaxSq"])
     e.init_topology(d["particleKind"], d["particleMol"], d["particleCharge"], d["molStart"])
     e.set_box_molecules(0, d["box0.mols"])
-    e.set_box_axes(0, d["box0.axis"])
+    if int(d["box0.orthogonal"][0]):
+        e.set_box_axes(0, d["box0.axis"])
+    else:
+        e.set_box_cell_basis(0, d["box0.cellBasis"], d["box0.cellBasisInv"], d["box0.axis"])
     e.set_coords(*_xyz(d, "coords"))
     e.set_com(*_xyz(d, "com"))
     e.nk = 0

@@ -62,9 +62,14 @@ def test_molecule_inter(case):
             other = (m + 1) % s.n_mols
             a0 = s.mol_start[other]
             sl = slice(s.mol_start[m], s.mol_start[m + 1])
-            nx = np.mod(s.x[sl] - s.x[sl][0] + s.x[a0] + 0.3, s.axis[0])
-            ny = np.mod(s.y[sl] - s.y[sl][0] + s.y[a0] + 0.2, s.axis[1])
-            nz = np.mod(s.z[sl] - s.z[sl][0] + s.z[a0] + 0.1, s.axis[2])
+            nx = s.x[sl] - s.x[sl][0] + s.x[a0] + 0.3
+            ny = s.y[sl] - s.y[sl][0] + s.y[a0] + 0.2
+            nz = s.z[sl] - s.z[sl][0] + s.z[a0] + 0.1
+            if s.cell_basis is None:
+                nx, ny, nz = (np.mod(v, s.axis[k]) for k, v in enumerate((nx, ny, nz)))
+            else:
+                u = np.mod(np.stack([nx, ny, nz], 1) @ s.cell_basis_inv, s.axis)
+                nx, ny, nz = (np.minimum(u, np.nextafter(s.axis, 0)) @ s.cell_basis).T.copy()
         lj, re, ov = e.molecule_inter(0, m, nx, ny, nz)
         ba = box_atoms(s)
         ba = ba[(ba < s.mol_start[m]) | (ba >= s.mol_start[m + 1])]
@@ -83,6 +88,8 @@ def test_particle_inter(case):
     m = int(rng.integers(s.n_mols))
     trials = 7
     tx, ty, tz = (rng.uniform(0, s.axis[d], trials) for d in range(3))
+    if s.cell_basis is not None:   # uniform in the slanted cell
+        tx, ty, tz = (np.stack([tx, ty, tz], 1) @ s.cell_basis).T.copy()
     en, re, ov = e.particle_inter(0, m, 0, tx, ty, tz)
     ba = box_atoms(s)
     ba = ba[(ba < s.mol_start[m]) | (ba >= s.mol_start[m + 1])]
