@@ -345,7 +345,7 @@ def main():
         traffic = None
         tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tj):
-            traffic = json.load(open(tj)).get("k_recip_fact_dram_bytes")
+            traffic = json.load(open(tj)).get("k_recip_mma_dram_bytes")
         line = {
             "metric": METRIC, "value": 1e3 / ms_res, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
@@ -357,7 +357,7 @@ def main():
                     "h2d_bytes_per_step": 3 * 8 * s.n_atoms, "d2h_bytes_per_step": 24},
             "gpu_launches": int(l1 - l0),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "k_recip_fact (structure-factor sums)",
+            "roofline": {"bound": "fp64", "kernel": "structure-factor stage: k_phase_tables + k_recip_mma (DMMA) + k_recip_finish",
                          "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach / peak_tf) if (ach and peak_tf) else None,
                          "traffic": traffic,
