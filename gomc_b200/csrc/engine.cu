@@ -951,7 +951,8 @@ int ensure_mirror(gomcb200_engine *e) {
 }
 
 int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
-                  const double *ny, const double *nz, int mode, double *out) {
+                  const double *ny, const double *nz, int mode, double *out,
+                  size_t stageOffset = 0, bool sync = true) {
   BoxState &bx = e->box[b];
   KSet &ks = bx.kset[1 - bx.cur];  // Ref set
   const int nk = ks.n;
@@ -963,14 +964,14 @@ int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
   if (rc) return rc;
   const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
   size_t nd = 1 + 7 * (size_t)len;
-  rc = stage_reserve(e, nd * sizeof(double));
+  rc = stage_reserve(e, stageOffset + nd * sizeof(double));
   if (rc) return rc;
   if (mode == 0) {
     rc = ensure_mirror(e);
     if (rc) return rc;
   }
   CK(e->molBuf.reserve(nd + 8));
-  double *h = e->hStage;
+  double *h = reinterpret_cast<double *>(reinterpret_cast<char *>(e->hStage) + stageOffset);
   h[0] = (double)len;
   for (int a = 0; a < len; ++a) {
     double *m = h + 1 + 7 * a;
@@ -993,6 +994,10 @@ int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
                                            nullptr, e->result.p);
   e->launches += 2;
   CK(cudaGetLastError());
+  if (!sync) {  // caller synchronises once for several queued operations
+    CK(cudaMemcpyAsync(e->hRes, e->result.p, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    return 0;
+  }
   rc = fetch_result(e, 1);
   if (rc) return rc;
   *out = e->hRes[0];
@@ -1029,7 +1034,8 @@ void launch_probe(gomcb200_engine *e, int b, const BoxParams &p, int excludeMol,
 }
 
 // probes staged in e->hStage as Probe[n]; results in e->hStage after the call
-int run_probes(gomcb200_engine *e, int b, int excludeMol, int n, std::vector<double> &out) {
+int run_probes(gomcb200_engine *e, int b, int excludeMol, int n, std::vector<double> &out,
+               bool sync = true) {
   int rc = ensure_cells(e, b);
   if (rc) return rc;
   BoxParams p = make_params(e, b);
@@ -1054,6 +1060,7 @@ int run_probes(gomcb200_engine *e, int b, int excludeMol, int n, std::vector<dou
                                             sizeof(Probe) * (size_t)n);
   CK(cudaMemcpyAsync(hOut, e->probeOut.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost,
                      e->stream));
+  if (!sync) return 0;
   CK(cudaStreamSynchronize(e->stream));
   out.assign(hOut, hOut + 3 * (size_t)n);
   return 0;
@@ -1469,6 +1476,56 @@ int gomcb200_molecule_inter(gomcb200_engine *e, int box, int molIndex, const dou
   if (dLJ) *dLJ = lj;
   if (dReal) *dReal = re;
   if (overlap) *overlap = ov;
+  return 0;
+}
+
+int gomcb200_molecule_trial(gomcb200_engine *e, int box, int molIndex, const double *newX,
+                            const double *newY, const double *newZ, double *dLJ, double *dReal,
+                            int *overlap, double *energyRecipNew) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (molIndex < 0 || molIndex >= e->nMols || !newX || !newY || !newZ)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  const size_t probeBytes = (sizeof(Probe) + 3 * sizeof(double)) * 2 * (size_t)len;
+  const size_t molOff = (probeBytes + 63) & ~(size_t)63;
+  rc = stage_reserve(e, molOff + (1 + 7 * (size_t)len) * sizeof(double) + 64);
+  if (rc) return rc;
+  rc = ensure_mirror(e);
+  if (rc) return rc;
+  Probe *pr = reinterpret_cast<Probe *>(e->hStage);
+  for (int a = 0; a < len; ++a) {
+    Probe o = {e->hx[s + a], e->hy[s + a], e->hz[s + a], e->hCharge[s + a], -1.0,
+               e->hKind[s + a], 0, 0};
+    Probe n = {newX[a], newY[a], newZ[a], e->hCharge[s + a], 1.0, e->hKind[s + a], 1, 0};
+    pr[2 * a] = o;
+    pr[2 * a + 1] = n;
+  }
+  std::vector<double> unused;
+  rc = run_probes(e, box, molIndex, 2 * len, unused, /*sync=*/false);
+  if (rc) return rc;
+  BoxState &bx = e->box[box];
+  const bool recip = e->ewald && e->electrostatic && bx.kset[1 - bx.cur].n > 0;
+  double dummy = 0.0;
+  if (recip) {
+    rc = run_mol_recip(e, box, molIndex, newX, newY, newZ, 0, &dummy, molOff, /*sync=*/false);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(e->stream));  // the only synchronisation of the trial
+  const double *hOut = reinterpret_cast<const double *>(reinterpret_cast<const char *>(e->hStage) +
+                                                        sizeof(Probe) * 2 * (size_t)len);
+  double lj = 0.0, re = 0.0;
+  int ov = 0;
+  for (int t = 0; t < 2 * len; ++t) {
+    lj += hOut[3 * t];
+    re += hOut[3 * t + 1];
+    if (hOut[3 * t + 2] != 0.0) ov = 1;
+  }
+  if (dLJ) *dLJ = lj;
+  if (dReal) *dReal = re;
+  if (overlap) *overlap = ov;
+  if (energyRecipNew) *energyRecipNew = recip ? e->hRes[0] : 0.0;
   return 0;
 }
 

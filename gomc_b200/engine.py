@@ -44,6 +44,7 @@ _SIGS = {
     "gomcb200_box_inter": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gomcb200_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gomcb200_molecule_inter": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip]),
+    "gomcb200_molecule_trial": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _dp]),
     "gomcb200_particle_inter": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
                                           _dp, _dp, _dp, _ip]),
     "gomcb200_calculate_torque": (C.c_int, [_vp, C.c_int]),
@@ -215,6 +216,13 @@ class Engine:
         self._ck(self.L.gomcb200_molecule_inter(self.h, box, mol_index, px, py, pz,
                                                 C.byref(lj), C.byref(re), C.byref(ov)))
         return lj.value, re.value, bool(ov.value)
+
+    def molecule_trial(self, box, mol_index, nx, ny, nz):
+        (nx, px), (ny, py), (nz, pz) = _d(nx), _d(ny), _d(nz)
+        lj, re, ov, er = C.c_double(), C.c_double(), C.c_int(), C.c_double()
+        self._ck(self.L.gomcb200_molecule_trial(self.h, box, mol_index, px, py, pz, C.byref(lj),
+                                                C.byref(re), C.byref(ov), C.byref(er)))
+        return lj.value, re.value, bool(ov.value), er.value
 
     def particle_inter(self, box, mol_index, part_index, tx, ty, tz):
         (tx, px), (ty, py), (tz, pz) = _d(tx), _d(ty), _d(tz)

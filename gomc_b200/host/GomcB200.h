@@ -144,6 +144,17 @@ public:
           "MoleculeInter");
     return overlap != 0;
   }
+  // MoleculeInter + Ewald::MolReciprocal of one trial with a single synchronisation
+  // (the pair Translate::CalcEn issues, src/moves/Translate.h:82-95)
+  bool MoleculeTrial(Intermolecular &inter_LJ, Intermolecular &inter_coulomb, double &recipNew,
+                     const XYZView &molCoords, int molIndex, int box) const {
+    int overlap = 0;
+    check(gomcb200_molecule_trial(eng_.get(), box, molIndex, molCoords.x, molCoords.y,
+                                  molCoords.z, &inter_LJ.energy, &inter_coulomb.energy, &overlap,
+                                  &recipNew),
+          "MoleculeTrial");
+    return overlap != 0;
+  }
   // src/CalculateEnergy.cpp:727-785
   void ParticleInter(double *en, double *real, const XYZView &trialPos, bool *overlap,
                      int partIndex, int molIndex, int box, int trials) const {

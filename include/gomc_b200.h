@@ -161,6 +161,14 @@ int gomcb200_molecule_inter(gomcb200_engine *e, int box, int molIndex,
                             const double *newX, const double *newY,
                             const double *newZ, double *dLJ, double *dReal,
                             int *overlap);
+/* One single-molecule trial = MoleculeInter + MolReciprocal (what Translate::CalcEn /
+ * Rotate::CalcEn call back to back, src/moves/Translate.h:82-95) queued together
+ * with a single host synchronisation.  The reciprocal term is computed even when
+ * the move overlaps (the reference skips it then; the caller ignores it). */
+int gomcb200_molecule_trial(gomcb200_engine *e, int box, int molIndex,
+                            const double *newX, const double *newY,
+                            const double *newZ, double *dLJ, double *dReal,
+                            int *overlap, double *energyRecipNew);
 /* CalculateEnergy::ParticleInter, src/CalculateEnergy.cpp:727-785: en[] and
  * real[] are incremented, overlap[] or-ed. */
 int gomcb200_particle_inter(gomcb200_engine *e, int box, int molIndex,

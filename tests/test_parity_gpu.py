@@ -71,6 +71,11 @@ def test_molecule_inter(case):
                 u = np.mod(np.stack([nx, ny, nz], 1) @ s.cell_basis_inv, s.axis)
                 nx, ny, nz = (np.minimum(u, np.nextafter(s.axis, 0)) @ s.cell_basis).T.copy()
         lj, re, ov = e.molecule_inter(0, m, nx, ny, nz)
+        # the fused single-synchronisation trial returns the same bits
+        flj, fre, fov, frc = e.molecule_trial(0, m, nx, ny, nz)
+        assert (flj, fre, fov) == (lj, re, ov)
+        if _ewald(s):
+            assert frc == e.mol_reciprocal(0, m, nx, ny, nz)
         ba = box_atoms(s)
         ba = ba[(ba < s.mol_start[m]) | (ba >= s.mol_start[m + 1])]
         olj, ore, oov = o.molecule_inter(s.x, s.y, s.z, s.kind, s.mol, s.charge, ba, m,
