@@ -218,6 +218,83 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------
+def small_box_extras(eng, device, flush, reps=200):
+    """E1/E3/E4 of SURVEY.md section 8(d) on BASELINE.json configs[1] (SPC/E, 10 000
+    molecules, nk = 30 782): the single-molecule and swap trials are latency-bound,
+    so they are wall-clock per call through the C ABI, host buffers in, scalars out."""
+    import torch
+    s = make_system("spce10k")
+    e = eng.Engine.from_system(s, device=device)
+    rng = np.random.default_rng(5)
+
+    def trial_coords(m):
+        sl = slice(s.mol_start[m], s.mol_start[m + 1])
+        d = rng.uniform(-0.5, 0.5, 3)
+        return s.x[sl] + d[0], s.y[sl] + d[1], s.z[sl] + d[2]
+
+    def wall(fn, n, flush_each=False):
+        t = []
+        for i in range(n):
+            if flush_each:
+                flush.zero_()
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn(i)
+            t.append((time.perf_counter() - t0) * 1e3)
+        return float(np.mean(t))
+
+    def e1(_):
+        e.L.gomcb200_mark_coords_changed(e.h)
+        e.call_full_box_energy(0)
+    for i in range(3):
+        e1(i)
+    ms_e1 = wall(e1, 20, True)
+    e.call_full_box_energy(0)
+    e.set_recip_ref(0)
+    mols = [int(m) for m in rng.integers(0, s.n_mols, reps + 10)]
+    dp = C.POINTER(C.c_double)
+    keep = []
+
+    def ptrs(arrs):  # ctypes pointers made once: the loop times the C ABI, not numpy
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+        keep.append(arrs)
+        return [a.ctypes.data_as(dp) for a in arrs]
+    moves = [ptrs(trial_coords(m)) for m in mols]
+    olds = [ptrs((s.x[s.mol_start[m]:s.mol_start[m + 1]], s.y[s.mol_start[m]:s.mol_start[m + 1]],
+                  s.z[s.mol_start[m]:s.mol_start[m + 1]])) for m in mols]
+    lj, re, rc, co, se = (C.c_double() for _ in range(5))
+    ov = C.c_int()
+    r = [C.byref(v) for v in (lj, re, ov, rc, co, se)]
+    Lib, h = e.L, e.h
+
+    def e3(i):  # MoleculeInter + MolReciprocal, accept every other trial (UpdateRecip)
+        m = mols[i]
+        if Lib.gomcb200_molecule_trial(h, 0, m, *moves[i], r[0], r[1], r[2], r[3]):
+            raise RuntimeError(Lib.gomcb200_last_error().decode())
+        if i & 1:
+            Lib.gomcb200_set_molecule_coords(h, m, *moves[i], None)
+            Lib.gomcb200_update_recip(h, 0)
+    for i in range(reps, reps + 10):
+        e3(i)
+    ms_e3 = wall(e3, reps)
+
+    def e4(i):  # SwapDestRecip + SwapSourceRecip + SwapCorrection x2 (+ SwapSelf)
+        m = mols[i]
+        if (Lib.gomcb200_swap_trial(h, 0, m, *moves[i], 1, r[3], r[4], r[5]) or
+                Lib.gomcb200_swap_trial(h, 0, m, *olds[i], 0, r[3], r[4], r[5])):
+            raise RuntimeError(Lib.gomcb200_last_error().decode())
+    for i in range(reps, reps + 10):
+        e4(i)
+    ms_e4 = wall(e4, reps)
+    nk = e.nk
+    e.close()
+    return {"workload": "spce10k (BASELINE configs[1])", "n_atoms": int(s.n_atoms), "nk": int(nk),
+            "E1_full_box_evals_per_s": 1e3 / ms_e1, "E1_ms": ms_e1,
+            "E3_single_molecule_trials_per_s": 1e3 / ms_e3, "E3_ms": ms_e3,
+            "E4_swap_trials_per_s": 1e3 / ms_e4, "E4_ms": ms_e4,
+            "timing": "wall clock per call incl. H2D of the trial molecule and D2H of the scalars"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,6 +303,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="spce100k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -327,6 +405,9 @@ def main():
             t_mp.append((time.perf_counter() - t0) * 1e3)
         mp_ms = float(np.mean(t_mp))
     clocks = sampler.stop() if rank == 0 else None
+    extras = None
+    if world == 1 and args.workload == "spce100k" and not args.no_extras:
+        extras = small_box_extras(eng, local, flush)
 
     # resident: device time of the step (CUDA events on the engine's stream) for
     # N = 1; with sharding the step ends with the all-reduce, so wall time between
@@ -371,6 +452,7 @@ def main():
                 "ms_per_step": mp_ms,
                 "step": "BoxReciprocalSums + BoxForce + BoxReciprocal + BoxForceReciprocal + "
                         "CalculateTorque (MultiParticle::CalcEn), wall clock incl. launches"}),
+            "small_box": extras,
             "energies": {"lj": en_res[0], "real": en_res[1], "recip": en_res[2],
                          "host_path_identical": en_res == en_host},
         }

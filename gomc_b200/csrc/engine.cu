@@ -5,6 +5,7 @@
 // recip.cuh on one stream and returns scalars through pinned memory.
 // No CPU fallback: every entry point needs a CUDA device.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -19,6 +20,7 @@
 #include "common.cuh"
 #include "pair.cuh"
 #include "recip.cuh"
+#include "trial.cuh"
 #include "recip_mma.cuh"
 #include "force_mma.cuh"
 
@@ -108,6 +110,7 @@ struct BoxState {
   bool cellsDirty = true;
   CellGrid grid;
   DevBuf<int> keys, keysSorted, vals, sortedAtoms, cellStart;
+  DevBuf<int> sortedPos;  // global atom index -> position in the cell-sorted copy
   DevBuf<double> sx, sy, sz, sq;
   DevBuf<int2> skm;
   // reciprocal space
@@ -140,6 +143,7 @@ struct gomcb200_engine {
   bool haveTopo = false;
   int nAtoms = 0, nMols = 0, maxMolLen = 0;
   std::vector<int> hKind, hMol, hMolStart;
+  std::vector<int> hMolBox;  // box of each molecule (-1: in no box)
   std::vector<double> hCharge;
   // lazily maintained host mirror of the coordinates (single-molecule moves read
   // the old positions from it instead of a D2H round trip)
@@ -158,6 +162,11 @@ struct gomcb200_engine {
   DevBuf<Probe> probes;
   DevBuf<unsigned char> cubTemp;
   double *hRes = nullptr;       // pinned, 64 doubles
+  // fused single-molecule trial: mapped pinned {6 results, flag}, ticket, partials
+  double *hTrial = nullptr, *dTrial = nullptr;
+  unsigned long long trialSeq = 0;
+  DevBuf<unsigned> ticket;
+  DevBuf<double> trialPart;
   double *hStage = nullptr;     // pinned staging for small uploads
   size_t hStageCap = 0;
   // timing
@@ -266,6 +275,7 @@ int ensure_cells(gomcb200_engine *e, int b) {
   CK(bx.sz.reserve(n + 1));
   CK(bx.sq.reserve(n + 1));
   CK(bx.skm.reserve(n + 1));
+  CK(bx.sortedPos.reserve(e->nAtoms + 1));
   if (n > 0) {
     int blocks = (n + 255) / 256;
     k_cell_keys<<<blocks, 256, 0, e->stream>>>(g, n, bx.atomList.p, e->x.p, e->y.p,
@@ -283,7 +293,7 @@ int ensure_cells(gomcb200_engine *e, int b) {
     k_gather_sorted<<<blocks, 256, 0, e->stream>>>(n, bx.sortedAtoms.p, e->x.p, e->y.p,
                                                   e->z.p, e->q.p, e->kind.p, e->mol.p,
                                                   bx.sx.p, bx.sy.p, bx.sz.p, bx.sq.p,
-                                                  bx.skm.p);
+                                                  bx.skm.p, bx.sortedPos.p);
     e->launches += 4;
   }
   k_cell_bounds<<<(g.nCells + 1 + 255) / 256, 256, 0, e->stream>>>(
@@ -950,21 +960,13 @@ int ensure_mirror(gomcb200_engine *e) {
   return 0;
 }
 
-int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
-                  const double *ny, const double *nz, int mode, double *out,
-                  size_t stageOffset = 0, bool sync = true) {
-  BoxState &bx = e->box[b];
-  KSet &ks = bx.kset[1 - bx.cur];  // Ref set
-  const int nk = ks.n;
-  if (nk == 0) {
-    *out = 0.0;
-    return 0;
-  }
-  int rc = ensure_sums(e, bx, nk);
-  if (rc) return rc;
+// Stage {len, per atom: q, new xyz, old xyz} of one molecule into the pinned
+// area (at stageOffset) and queue its upload to molBuf.
+int stage_molbuf(gomcb200_engine *e, int molIndex, const double *nx, const double *ny,
+                 const double *nz, int mode, size_t stageOffset) {
   const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
   size_t nd = 1 + 7 * (size_t)len;
-  rc = stage_reserve(e, stageOffset + nd * sizeof(double));
+  int rc = stage_reserve(e, stageOffset + nd * sizeof(double));
   if (rc) return rc;
   if (mode == 0) {
     rc = ensure_mirror(e);
@@ -985,6 +987,24 @@ int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
   }
   CK(cudaMemcpyAsync(e->molBuf.p, h, nd * sizeof(double), cudaMemcpyHostToDevice,
                      e->stream));
+  return 0;
+}
+
+int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
+                  const double *ny, const double *nz, int mode, double *out,
+                  size_t stageOffset = 0, bool sync = true) {
+  BoxState &bx = e->box[b];
+  KSet &ks = bx.kset[1 - bx.cur];  // Ref set
+  const int nk = ks.n;
+  if (nk == 0) {
+    *out = 0.0;
+    return 0;
+  }
+  int rc = ensure_sums(e, bx, nk);
+  if (rc) return rc;
+  const int len = e->hMolStart[molIndex + 1] - e->hMolStart[molIndex];
+  rc = stage_molbuf(e, molIndex, nx, ny, nz, mode, stageOffset);
+  if (rc) return rc;
   const int nBlocks = (nk + 255) / 256;
   CK(e->blockA.reserve(nBlocks + 1024));
   k_mol_recip<<<nBlocks, 256, 7 * len * sizeof(double), e->stream>>>(
@@ -1066,6 +1086,92 @@ int run_probes(gomcb200_engine *e, int b, int excludeMol, int n, std::vector<dou
   return 0;
 }
 
+template <int VDW>
+void launch_trial(gomcb200_engine *e, int b, const BoxParams &p, const TrialArgs &a, int nBlocks) {
+  BoxState &bx = e->box[b];
+  KSet &ks = bx.kset[1 - bx.cur];
+  k_mol_trial<VDW><<<nBlocks, kPairThreads, 0, e->stream>>>(
+      p, bx.grid, a, bx.cellStart.p, bx.sx.p, bx.sy.p, bx.sz.p, bx.sq.p, bx.skm.p, ks.kx.p,
+      ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRref].p, bx.sum[bx.iIref].p,
+      bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p, e->trialPart.p, e->blockA.p, e->ticket.p,
+      e->dTrial, reinterpret_cast<volatile unsigned long long *>(e->dTrial + 8));
+}
+
+// One-launch single-molecule trial (trial.cuh), molecules of <= kTrialMaxAtoms atoms.
+// out = {lj, real, overlap, recipNew, correction, self}
+int run_trial_fused(gomcb200_engine *e, int b, int molIndex, const double *nx, const double *ny,
+                    const double *nz, int mode, bool probes, bool recip, bool correction,
+                    double out[6]) {
+  BoxState &bx = e->box[b];
+  int rc = 0;
+  if (probes) {
+    rc = ensure_cells(e, b);
+    if (rc) return rc;
+  }
+  const int nk = recip ? bx.kset[1 - bx.cur].n : 0;
+  if (nk) {
+    rc = ensure_sums(e, bx, nk);
+    if (rc) return rc;
+  }
+  if (mode == 0) {
+    rc = ensure_mirror(e);
+    if (rc) return rc;
+  }
+  const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  TrialArgs a;
+  a.len = len;
+  a.mode = mode;
+  a.excludeMol = molIndex;
+  a.nk = nk;
+  a.nProbeBlocks = probes ? 2 * len * kProbeSplit : 0;
+  a.doCorrection = correction ? 1 : 0;
+  a.seq = ++e->trialSeq;
+  for (int i = 0; i < len; ++i) {
+    a.kind[i] = e->hKind[s + i];
+    a.q[i] = e->hCharge[s + i];
+    a.nx[i] = nx[i];
+    a.ny[i] = ny[i];
+    a.nz[i] = nz[i];
+    a.ox[i] = mode == 0 ? e->hx[s + i] : 0.0;
+    a.oy[i] = mode == 0 ? e->hy[s + i] : 0.0;
+    a.oz[i] = mode == 0 ? e->hz[s + i] : 0.0;
+  }
+  int nRecipBlocks = (nk + kPairThreads - 1) / kPairThreads;
+  if (a.nProbeBlocks + nRecipBlocks == 0) nRecipBlocks = 1;  // the finalising block
+  CK(e->blockA.reserve(nRecipBlocks + 1024));
+  const int nBlocks = a.nProbeBlocks + nRecipBlocks;
+  BoxParams p = make_params(e, b);
+  if (e->vdwKind == VDW_SHIFT)
+    launch_trial<VDW_SHIFT>(e, b, p, a, nBlocks);
+  else if (e->vdwKind == VDW_SWITCH)
+    launch_trial<VDW_SWITCH>(e, b, p, a, nBlocks);
+  else if (e->vdwKind == VDW_EXP6)
+    launch_trial<VDW_EXP6>(e, b, p, a, nBlocks);
+  else if (e->vdwKind == VDW_MARTINI)
+    launch_trial<VDW_MARTINI>(e, b, p, a, nBlocks);
+  else
+    launch_trial<VDW_STD>(e, b, p, a, nBlocks);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  // the kernel publishes a.seq in mapped host memory after its results
+  volatile unsigned long long *flag =
+      reinterpret_cast<volatile unsigned long long *>(e->hTrial + 8);
+  for (unsigned spin = 1; *flag != a.seq; ++spin) {
+    if ((spin & 0xfffffu) == 0) {  // every ~1M polls make sure the launch is still alive
+      cudaError_t q = cudaStreamQuery(e->stream);
+      if (q != cudaErrorNotReady) {
+        if (q == cudaSuccess && *flag == a.seq) break;
+        return fail(GOMCB200_ECUDA, "single-molecule trial kernel: %s",
+                    q == cudaSuccess ? "finished without publishing its result"
+                                     : cudaGetErrorString(q));
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  for (int i = 0; i < 6; ++i) out[i] = e->hTrial[i];
+  return 0;
+}
+
 void timing_begin(gomcb200_engine *e) {
   if (e->timing) cudaEventRecord(e->ev[0], e->stream);
 }
@@ -1115,6 +1221,12 @@ int gomcb200_create(gomcb200_engine **out, int device, int nBoxes) {
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CK(cudaHostAlloc(&e->hRes, 64 * sizeof(double), cudaHostAllocDefault));
   CK(e->result.reserve(64));
+  CK(cudaHostAlloc(&e->hTrial, 16 * sizeof(double), cudaHostAllocMapped));
+  memset(e->hTrial, 0, 16 * sizeof(double));
+  CK(cudaHostGetDevicePointer(&e->dTrial, e->hTrial, 0));
+  CK(e->ticket.reserve(4));
+  CK(cudaMemset(e->ticket.p, 0, 4 * sizeof(unsigned)));
+  CK(e->trialPart.reserve(3 * 2 * kTrialMaxAtoms * kProbeSplit + 8));
   for (auto &ev : e->ev) CK(cudaEventCreate(&ev));
   *out = e;
   return 0;
@@ -1150,6 +1262,7 @@ int gomcb200_destroy(gomcb200_engine *e) {
   e->phaseTables.release();
   e->molBuf.release(); e->probeOut.release(); e->probes.release(); e->cubTemp.release();
   if (e->hRes) cudaFreeHost(e->hRes);
+  if (e->hTrial) cudaFreeHost(e->hTrial);
   if (e->hStage) cudaFreeHost(e->hStage);
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   cudaStreamDestroy(e->stream);
@@ -1303,10 +1416,14 @@ int gomcb200_set_box_molecules(gomcb200_engine *e, int box, const int *molIndice
   CK(cudaSetDevice(e->device));
   BoxState &bx = e->box[box];
   bx.hMols.assign(molIndices, molIndices + nMolsInBox);
+  if ((int)e->hMolBox.size() != e->nMols) e->hMolBox.assign(e->nMols, -1);
+  for (int &mb : e->hMolBox)
+    if (mb == box) mb = -1;
   bx.hAtoms.clear();
   bx.hCharged.clear();
   for (int m : bx.hMols) {
     if (m < 0 || m >= e->nMols) return fail(GOMCB200_EINVAL, "molecule index %d out of range", m);
+    e->hMolBox[m] = box;
     for (int a = e->hMolStart[m]; a < e->hMolStart[m + 1]; ++a) {
       bx.hAtoms.push_back(a);
       // Ewald::Init particleHasNoCharge, src/Ewald.cpp:107-111
@@ -1405,6 +1522,49 @@ int gomcb200_set_molecule_coords(gomcb200_engine *e, int molIndex, const double 
   if (!e || !e->haveTopo || molIndex < 0 || molIndex >= e->nMols)
     return fail(GOMCB200_EINVAL, "bad arguments");
   int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  if (len <= kTrialMaxAtoms && x && y && z) {
+    // one parameter-carried launch, no copy, no synchronisation (trial.cuh)
+    CK(cudaSetDevice(e->device));
+    const int b = (int)e->hMolBox.size() == e->nMols ? e->hMolBox[molIndex] : -1;
+    AcceptArgs a;
+    a.len = len;
+    a.first = s;
+    a.molIndex = molIndex;
+    a.hasCom = com ? 1 : 0;
+    a.inPlace = 0;
+    for (int d = 0; d < 3; ++d) a.com[d] = com ? com[d] : 0.0;
+    if (b >= 0 && !e->box[b].cellsDirty && !e->box[b].nonOrth && e->mirrorValid) {
+      const CellGrid &g = e->box[b].grid;
+      a.inPlace = 1;
+      for (int i = 0; i < len && a.inPlace; ++i)
+        if (position_to_cell(g, x[i], y[i], z[i]) !=
+            position_to_cell(g, e->hx[s + i], e->hy[s + i], e->hz[s + i]))
+          a.inPlace = 0;
+    }
+    for (int i = 0; i < len; ++i) {
+      a.x[i] = x[i];
+      a.y[i] = y[i];
+      a.z[i] = z[i];
+    }
+    BoxState &bs = e->box[b >= 0 ? b : 0];
+    k_accept_mol<<<1, kTrialMaxAtoms, 0, e->stream>>>(a, e->x.p, e->y.p, e->z.p, e->comx.p,
+                                                     e->comy.p, e->comz.p, bs.sortedPos.p,
+                                                     bs.sx.p, bs.sy.p, bs.sz.p);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    if (e->mirrorValid) {
+      memcpy(e->hx.data() + s, x, sizeof(double) * (size_t)len);
+      memcpy(e->hy.data() + s, y, sizeof(double) * (size_t)len);
+      memcpy(e->hz.data() + s, z, sizeof(double) * (size_t)len);
+    }
+    if (b >= 0) {
+      e->box[b].packedDirty = true;
+      if (!a.inPlace) e->box[b].cellsDirty = true;
+    } else {
+      mark_coords_dirty(e);
+    }
+    return 0;
+  }
   int rc = gomcb200_set_coords(e, x, y, z, s, len);
   if (rc) return rc;
   if (com) rc = gomcb200_set_com(e, com, com + 1, com + 2, molIndex, 1);
@@ -1451,6 +1611,15 @@ int gomcb200_molecule_inter(gomcb200_engine *e, int box, int molIndex, const dou
     return fail(GOMCB200_EINVAL, "bad arguments");
   CK(cudaSetDevice(e->device));
   const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  if (len <= kTrialMaxAtoms) {
+    double r[6];
+    rc = run_trial_fused(e, box, molIndex, newX, newY, newZ, 0, true, false, false, r);
+    if (rc) return rc;
+    if (dLJ) *dLJ = r[0];
+    if (dReal) *dReal = r[1];
+    if (overlap) *overlap = r[2] != 0.0;
+    return 0;
+  }
   rc = stage_reserve(e, (sizeof(Probe) + 3 * sizeof(double)) * 2 * (size_t)len + 64);
   if (rc) return rc;
   rc = ensure_mirror(e);  // old coordinates of the molecule
@@ -1488,6 +1657,17 @@ int gomcb200_molecule_trial(gomcb200_engine *e, int box, int molIndex, const dou
     return fail(GOMCB200_EINVAL, "bad arguments");
   CK(cudaSetDevice(e->device));
   const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  if (len <= kTrialMaxAtoms) {
+    double r[6];
+    rc = run_trial_fused(e, box, molIndex, newX, newY, newZ, 0, true,
+                         e->ewald && e->electrostatic, false, r);
+    if (rc) return rc;
+    if (dLJ) *dLJ = r[0];
+    if (dReal) *dReal = r[1];
+    if (overlap) *overlap = r[2] != 0.0;
+    if (energyRecipNew) *energyRecipNew = r[3];
+    return 0;
+  }
   const size_t probeBytes = (sizeof(Probe) + 3 * sizeof(double)) * 2 * (size_t)len;
   const size_t molOff = (probeBytes + 63) & ~(size_t)63;
   rc = stage_reserve(e, molOff + (1 + 7 * (size_t)len) * sizeof(double) + 64);
@@ -1526,6 +1706,74 @@ int gomcb200_molecule_trial(gomcb200_engine *e, int box, int molIndex, const dou
   if (dReal) *dReal = re;
   if (overlap) *overlap = ov;
   if (energyRecipNew) *energyRecipNew = recip ? e->hRes[0] : 0.0;
+  return 0;
+}
+
+int gomcb200_swap_correction(gomcb200_engine *e, int box, int molIndex, const double *x,
+                             const double *y, const double *z, double *correction,
+                             double *self) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (molIndex < 0 || molIndex >= e->nMols || !x || !y || !z)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!(e->ewald && e->electrostatic)) {
+    if (correction) *correction = 0.0;
+    if (self) *self = 0.0;
+    return 0;
+  }
+  CK(cudaSetDevice(e->device));
+  rc = stage_molbuf(e, molIndex, x, y, z, 1, 0);
+  if (rc) return rc;
+  k_swap_correction<<<1, 128, 0, e->stream>>>(make_params(e, box), e->molBuf.p, e->result.p + 1);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  rc = fetch_result(e, 3);
+  if (rc) return rc;
+  if (correction) *correction = e->hRes[1];
+  if (self) *self = e->hRes[2];
+  return 0;
+}
+
+int gomcb200_swap_trial(gomcb200_engine *e, int box, int molIndex, const double *x,
+                        const double *y, const double *z, int insert, double *energyRecipNew,
+                        double *correction, double *self) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (molIndex < 0 || molIndex >= e->nMols || !x || !y || !z)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  double en = 0.0, co = 0.0, se = 0.0;
+  if (e->ewald && e->electrostatic &&
+      e->hMolStart[molIndex + 1] - e->hMolStart[molIndex] <= kTrialMaxAtoms) {
+    CK(cudaSetDevice(e->device));
+    double r[6];
+    rc = run_trial_fused(e, box, molIndex, x, y, z, insert ? 1 : 2, false, true, true, r);
+    if (rc) return rc;
+    en = r[3];
+    co = r[4];
+    se = r[5];
+  } else if (e->ewald && e->electrostatic) {
+    CK(cudaSetDevice(e->device));
+    BoxState &bx = e->box[box];
+    const bool recip = bx.kset[1 - bx.cur].n > 0;
+    if (recip) {
+      rc = run_mol_recip(e, box, molIndex, x, y, z, insert ? 1 : 2, &en, 0, /*sync=*/false);
+    } else {
+      rc = stage_molbuf(e, molIndex, x, y, z, 1, 0);
+    }
+    if (rc) return rc;
+    k_swap_correction<<<1, 128, 0, e->stream>>>(make_params(e, box), e->molBuf.p,
+                                                e->result.p + 1);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    rc = fetch_result(e, 3);  // the only synchronisation of the trial
+    if (rc) return rc;
+    en = recip ? e->hRes[0] : 0.0;
+    co = e->hRes[1];
+    se = e->hRes[2];
+  }
+  if (energyRecipNew) *energyRecipNew = en;
+  if (correction) *correction = co;
+  if (self) *self = se;
   return 0;
 }
 

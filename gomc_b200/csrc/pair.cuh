@@ -29,7 +29,7 @@ struct CellGrid {
 };
 
 // CellList::PositionToCell, src/CellList.h:88-101 (orthogonal box).
-__device__ __forceinline__ int position_to_cell(const CellGrid &g, double x,
+__host__ __device__ __forceinline__ int position_to_cell(const CellGrid &g, double x,
                                                 double y, double z) {
   if (g.nonOrth) {  // BoxDimensionsNonOrth::TransformUnSlant
     double ux = x * g.Bi[0] + y * g.Bi[3] + z * g.Bi[6];
@@ -84,10 +84,12 @@ __global__ void k_gather_sorted(int n, const int *__restrict__ sortedAtoms,
                                 const double *__restrict__ q,
                                 const int *__restrict__ kind,
                                 const int *__restrict__ mol, double *sx,
-                                double *sy, double *sz, double *sq, int2 *skm) {
+                                double *sy, double *sz, double *sq, int2 *skm,
+                                int *sortedPos) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   int a = sortedAtoms[t];
+  sortedPos[a] = t;
   sx[t] = x[a];
   sy[t] = y[a];
   sz[t] = z[a];

@@ -298,6 +298,41 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Ewald::SwapCorrection (src/Ewald.cpp:1311-1370) and SwapSelf (:1375-1391) of
+// the molecule staged in molBuf {len, per atom: q, x, y, z, ...}.  One block;
+// out[0] = correction, out[1] = self.
+__global__ void __launch_bounds__(128)
+    k_swap_correction(BoxParams p, const double *__restrict__ molBuf, double *__restrict__ out) {
+  __shared__ double scratch[32];
+  const int len = (int)molBuf[0];
+  const int nPairs = len * (len - 1) / 2;
+  double corr = 0.0, self = 0.0;
+  for (int t = threadIdx.x; t < nPairs; t += blockDim.x) {
+    // pair index -> (i, j), i < j, row-major over i
+    int i = 0, rem = t;
+    while (rem >= len - 1 - i) {
+      rem -= len - 1 - i;
+      ++i;
+    }
+    const int j = i + 1 + rem;
+    const double *a = molBuf + 1 + 7 * i, *b = molBuf + 1 + 7 * j;
+    double dx = a[1] - b[1], dy = a[2] - b[2], dz = a[3] - b[3];
+    min_image_vec(p, dx, dy, dz);
+    double dist = sqrt(dx * dx + dy * dy + dz * dz);
+    corr -= a[0] * b[0] * erf(p.alpha * dist) / dist;
+  }
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    double q = molBuf[1 + 7 * i];
+    self -= q * q;
+  }
+  double c = block_sum(corr, scratch);
+  double sf = block_sum(self, scratch);
+  if (threadIdx.x == 0) {
+    out[0] = kQQFact * c;
+    out[1] = sf * p.alpha * kQQFact * 1.12837916709551257390 * 0.5;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Factorised structure factor.
 //

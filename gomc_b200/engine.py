@@ -45,6 +45,8 @@ _SIGS = {
     "gomcb200_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gomcb200_molecule_inter": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip]),
     "gomcb200_molecule_trial": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _dp]),
+    "gomcb200_swap_correction": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]),
+    "gomcb200_swap_trial": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp]),
     "gomcb200_particle_inter": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
                                           _dp, _dp, _dp, _ip]),
     "gomcb200_calculate_torque": (C.c_int, [_vp, C.c_int]),
@@ -223,6 +225,20 @@ class Engine:
         self._ck(self.L.gomcb200_molecule_trial(self.h, box, mol_index, px, py, pz, C.byref(lj),
                                                 C.byref(re), C.byref(ov), C.byref(er)))
         return lj.value, re.value, bool(ov.value), er.value
+
+    def swap_correction(self, box, mol_index, x, y, z):
+        (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        co, se = C.c_double(), C.c_double()
+        self._ck(self.L.gomcb200_swap_correction(self.h, box, mol_index, px, py, pz, C.byref(co),
+                                                 C.byref(se)))
+        return co.value, se.value
+
+    def swap_trial(self, box, mol_index, x, y, z, insert):
+        (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        en, co, se = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.gomcb200_swap_trial(self.h, box, mol_index, px, py, pz, int(insert),
+                                            C.byref(en), C.byref(co), C.byref(se)))
+        return en.value, co.value, se.value
 
     def particle_inter(self, box, mol_index, part_index, tx, ty, tz):
         (tx, px), (ty, py), (tz, pz) = _d(tx), _d(ty), _d(tz)

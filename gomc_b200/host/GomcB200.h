@@ -238,28 +238,32 @@ public:
           "CallSwapReciprocalGPU");
     return e - sysPotRecip_[box];
   }
-  // src/Ewald.cpp:1311-1335: O(a^2) per molecule, host arithmetic as in both
-  // reference builds.  minImage handled by the caller's unwrapped trial molecule.
+  // src/Ewald.cpp:1311-1335 / :1340-1370 (one-block kernel; min-image on the device)
   virtual double SwapCorrection(const XYZView &molCoords, int molIndex, int box,
-                                const XYZ &axis) const {
-    const int start = eng_.MolStart(molIndex), len = eng_.MolLength(molIndex);
-    double correction = 0.0;
-    for (int i = 0; i < len; ++i)
-      for (int j = i + 1; j < len; ++j) {
-        double dx = MinImageSigned(molCoords.x[i] - molCoords.x[j], axis.x);
-        double dy = MinImageSigned(molCoords.y[i] - molCoords.y[j], axis.y);
-        double dz = MinImageSigned(molCoords.z[i] - molCoords.z[j], axis.z);
-        double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
-        correction -= eng_.Charge(start + i) * eng_.Charge(start + j) *
-                      std::erf(alpha_[box] * dist) / dist;
-      }
-    return 167103.208067979 * correction;  // num::qqFact
+                                const XYZ & /*axis*/) const {
+    double c = 0.0;
+    check(gomcb200_swap_correction(eng_.get(), box, molIndex, molCoords.x, molCoords.y,
+                                   molCoords.z, &c, nullptr),
+          "SwapCorrection");
+    return c;
   }
   virtual double SwapSelf(int molIndex, int box) const {  // src/Ewald.cpp:1375-1391
-    const int start = eng_.MolStart(molIndex), len = eng_.MolLength(molIndex);
-    double en_self = 0.0;
-    for (int i = 0; i < len; ++i) en_self -= eng_.Charge(start + i) * eng_.Charge(start + i);
-    return en_self * alpha_[box] * 167103.208067979 * 1.12837916709551257390 * 0.5;
+    const int len = eng_.MolLength(molIndex);
+    std::vector<double> zero(len, 0.0);
+    double s = 0.0;
+    check(gomcb200_swap_correction(eng_.get(), box, molIndex, zero.data(), zero.data(),
+                                   zero.data(), nullptr, &s),
+          "SwapSelf");
+    return s;
+  }
+  // Swap{Dest,Source}Recip + SwapCorrection + SwapSelf of one box with one sync
+  virtual void SwapTrial(const XYZView &molCoords, int box, int molIndex, bool insert,
+                         double &recipDelta, double &correction, double &self) {
+    double e = 0.0;
+    check(gomcb200_swap_trial(eng_.get(), box, molIndex, molCoords.x, molCoords.y, molCoords.z,
+                              insert ? 1 : 0, &e, &correction, &self),
+          "SwapTrial");
+    recipDelta = e - sysPotRecip_[box];
   }
   virtual void BoxSelfAndCorrection(int box, double &self, double &correction) const {
     check(gomcb200_box_self_correction(eng_.get(), box, &self, &correction), "BoxSelf");

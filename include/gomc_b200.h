@@ -232,6 +232,18 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box);
  * (MolExchangeReciprocal src/Ewald.cpp:794-806, ChangeRecip :626-630). */
 int gomcb200_get_recip_sums(gomcb200_engine *e, int box, int which,
                             double *sumR, double *sumI, int n);
+/* Ewald::SwapCorrection (src/Ewald.cpp:1311-1335 and :1340-1370; charges of
+ * molIndex, trial coordinates x/y/z) and Ewald::SwapSelf (:1375-1391). */
+int gomcb200_swap_correction(gomcb200_engine *e, int box, int molIndex,
+                             const double *x, const double *y, const double *z,
+                             double *correction, double *self);
+/* One swap trial in one box: Swap{Dest,Source}Recip + SwapCorrection + SwapSelf
+ * (the calls MoleculeTransfer::CalcEn makes per box,
+ * src/moves/MoleculeTransfer.h:120-140) with a single synchronisation. */
+int gomcb200_swap_trial(gomcb200_engine *e, int box, int molIndex,
+                        const double *x, const double *y, const double *z,
+                        int insert, double *energyRecipNew, double *correction,
+                        double *self);
 /* state machine, src/Ewald.cpp:1021-1053, :1420-1487 */
 int gomcb200_set_recip_ref(gomcb200_engine *e, int box);    /* SetRecipRef / CopyCurrentToRefCUDA */
 int gomcb200_copy_recip(gomcb200_engine *e, int box);       /* CopyRecip / CopyRefToNewCUDA       */

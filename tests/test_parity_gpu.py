@@ -71,11 +71,12 @@ def test_molecule_inter(case):
                 u = np.mod(np.stack([nx, ny, nz], 1) @ s.cell_basis_inv, s.axis)
                 nx, ny, nz = (np.minimum(u, np.nextafter(s.axis, 0)) @ s.cell_basis).T.copy()
         lj, re, ov = e.molecule_inter(0, m, nx, ny, nz)
-        # the fused single-synchronisation trial returns the same bits
+        # the one-launch trial (trial.cuh) agrees with the separate calls
         flj, fre, fov, frc = e.molecule_trial(0, m, nx, ny, nz)
         assert (flj, fre, fov) == (lj, re, ov)
         if _ewald(s):
-            assert frc == e.mol_reciprocal(0, m, nx, ny, nz)
+            rc = e.mol_reciprocal(0, m, nx, ny, nz)
+            assert abs(frc - rc) <= 1e-13 * abs(rc)
         ba = box_atoms(s)
         ba = ba[(ba < s.mol_start[m]) | (ba >= s.mol_start[m + 1])]
         olj, ore, oov = o.molecule_inter(s.x, s.y, s.z, s.kind, s.mol, s.charge, ba, m,
@@ -162,6 +163,14 @@ def test_mol_and_swap_reciprocal(case):
             en = e.swap_reciprocal(0, m, nx, ny, nz, insert)
             oe, oR, oI = o.swap_recip(insert, s.charge[sl], (nx, ny, nz), kx, ky, kz, pf, sR, sI)
             assert abs(en - oe) <= TOL * abs(oe)
+            # SwapCorrection / SwapSelf, alone and fused with the reciprocal delta
+            oc, osf = o.swap_correction(s.charge[sl], (nx, ny, nz)), o.swap_self(s.charge[sl])
+            co, se = e.swap_correction(0, m, nx, ny, nz)
+            assert abs(co - oc) <= TOL * abs(oc) and abs(se - osf) <= TOL * abs(osf)
+            ft = e.swap_trial(0, m, nx, ny, nz, insert)
+            assert all(abs(a - b) <= 1e-13 * abs(b) for a, b in zip(ft, (en, co, se)))
+            gR, gI = e.get_recip_sums(0, eng.SUM_NEW, e.nk)
+            assert rel_err(gR, oR) <= TOL and rel_err(gI, oI) <= TOL
     # the reference sums must be untouched by trial moves (state machine rule 1)
     rR, rI = e.get_recip_sums(0, eng.SUM_REF, e.nk)
     assert rel_err(rR, sR) <= TOL and rel_err(rI, sI) <= TOL

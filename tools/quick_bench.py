@@ -35,6 +35,7 @@ for nm in [int(a) for a in sys.argv[1:]] or [10000, 33334]:
     nx, ny, nz = s.x[sl] + 0.3, s.y[sl] + 0.2, s.z[sl] - 0.1
     r["molecule_inter"] = timeit(lambda: e.molecule_inter(0, m, nx, ny, nz), 20)
     r["mol_reciprocal"] = timeit(lambda: e.mol_reciprocal(0, m, nx, ny, nz), 20)
+    r["swap_trial"] = timeit(lambda: e.swap_trial(0, m, nx, ny, nz, 1), 20)
     r["molecule_trial"] = timeit(lambda: e.molecule_trial(0, m, nx, ny, nz), 20)
     e.copy_recip(0)
     r["force_recip_mma"] = timeit(lambda: (e.box_force_reciprocal(0), e.get_forces(eng.MOL_FORCE_REC, 0, 1)), 3)
