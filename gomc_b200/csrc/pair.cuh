@@ -282,16 +282,19 @@ __device__ __forceinline__ void warp_probe(
 // Neighbour ranges of a cell.  halfShell: own cell + the 13 "forward" cells
 // (each unordered cell pair exactly once; needs >= 3 cells per axis, which
 // CellList::ResizeGrid guarantees).
+// Cooperative: thread t of the CTA fills range t (call from all threads, then
+// __syncthreads()); returns the range count.
 __device__ __forceinline__ int build_ranges(const CellGrid &g,
                                             const BoxParams &p, int cell,
                                             bool halfShell,
                                             const int *__restrict__ cellStart,
                                             JRange *ranges) {
-  int cz = cell % g.edge[2];
-  int cy = (cell / g.edge[2]) % g.edge[1];
-  int cx = cell / (g.edge[2] * g.edge[1]);
-  int n = 0;
-  for (int d = (halfShell ? 13 : 0); d < 27; ++d) {
+  const int d0 = halfShell ? 13 : 0;
+  const int d = d0 + (int)threadIdx.x;
+  if (d < 27) {
+    int cz = cell % g.edge[2];
+    int cy = (cell / g.edge[2]) % g.edge[1];
+    int cx = cell / (g.edge[2] * g.edge[1]);
     int dx = d / 9 - 1, dy = (d / 3) % 3 - 1, dz = d % 3 - 1;
     int nx = cx + dx, ny = cy + dy, nz = cz + dz;
     JRange r;
@@ -308,9 +311,9 @@ __device__ __forceinline__ int build_ranges(const CellGrid &g,
     r.begin = cellStart[nc];
     r.end = cellStart[nc + 1];
     r.gbase = r.begin;
-    ranges[n++] = r;
+    ranges[d - d0] = r;
   }
-  return n;
+  return 27 - d0;
 }
 
 constexpr int kMaxIPerPass = 512;  // i-atoms of a cell slice handled per pass
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
   __shared__ JRange ranges[27];
   __shared__ JRange stagedRanges[27];
   __shared__ double enLJ[kMaxIPerPass], enReal[kMaxIPerPass];
-  __shared__ int nRangesSh, nextI;
+  __shared__ int nextI;
   // dynamic smem: per-warp hit queues, then the staged neighbour atoms
   WarpQueue *queues = reinterpret_cast<WarpQueue *>(dynSmem);
   unsigned char *stageBase = dynSmem + sizeof(WarpQueue) * NWARPS;
@@ -348,10 +351,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
   const int iBegin = iBegin0 + (int)(((long long)nI * slice) / slices);
   const int iEnd = iBegin0 + (int)(((long long)nI * (slice + 1)) / slices);
 
-  if (threadIdx.x == 0)
-    nRangesSh = build_ranges(g, p, cell, !FORCE, cellStart, ranges);
+  const int nRanges = build_ranges(g, p, cell, !FORCE, cellStart, ranges);
   __syncthreads();
-  const int nRanges = nRangesSh;
 
   JArrays ja = {sx, sy, sz, sq, skm, 0u, 0u, 0u, 0u, 0u};
   int selfOffset = 0;  // self-range index = global sorted index + selfOffset
@@ -555,13 +556,10 @@ __global__ void __launch_bounds__(kPairThreads)
   __shared__ WarpQueue queues[kPairWarps];
   __shared__ double red[2][kPairWarps];
   __shared__ int ovl[kPairWarps];
-  __shared__ int nRangesSh;
   const Probe pr = probes[blockIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    int cell = position_to_cell(g, pr.x, pr.y, pr.z);
-    nRangesSh = build_ranges(g, p, cell, false, cellStart, ranges);
-  }
+  const int nRangesSh =
+      build_ranges(g, p, position_to_cell(g, pr.x, pr.y, pr.z), false, cellStart, ranges);
   __syncthreads();
   PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
   JArrays ja = {sx, sy, sz, sq, skm, 0u, 0u, 0u, 0u, 0u};

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kPairThreads)
   __shared__ WarpQueue queues[kPairWarps];
   __shared__ double red[2][kPairWarps];
   __shared__ int ovl[kPairWarps];
-  __shared__ int nRangesSh, isLast;
+  __shared__ int isLast;
   __shared__ double scratch[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -60,10 +60,8 @@ __global__ void __launch_bounds__(kPairThreads)
     const bool isNew = t & 1;
     const double px = isNew ? a.nx[at] : a.ox[at], py = isNew ? a.ny[at] : a.oy[at],
                  pz = isNew ? a.nz[at] : a.oz[at];
-    if (threadIdx.x == 0) {
-      int cell = position_to_cell(g, px, py, pz);
-      nRangesSh = build_ranges(g, p, cell, false, cellStart, ranges);
-    }
+    const int nRangesSh =
+        build_ranges(g, p, position_to_cell(g, px, py, pz), false, cellStart, ranges);
     __syncthreads();
     PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
     JArrays ja = {sx, sy, sz, sq, skm, 0u, 0u, 0u, 0u, 0u};
