@@ -217,6 +217,46 @@ def run_reference(args):
     return 0
 
 
+def reference_gpu_build(s, reps=5, force=True):
+    """The reference's own shipped GPU build (src/GPU, compiled unmodified for sm_100 by
+    oracle/ref_build.mk `gpu`) timed on this GPU: BoxInter + BoxReciprocalSums +
+    BoxReciprocal over the FULL k list, host wall clock inside the probe as SURVEY.md
+    section 8(d) prescribes.  A comparator, not an oracle.  None when not built."""
+    probe = os.path.join(ROOT, "oracle", "_ref", "gomc_probe_GPU_NVT")
+    if not os.path.exists(probe):
+        return None
+    from gomc_b200 import synth
+    from oracle import pyoracle as po
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_gomc_inputs(s, d)
+        cmd = [probe, "time", "in.conf", "dump.bin", "1", str(reps)] + (["force"] if force else [])
+        try:
+            r = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600)
+        except subprocess.TimeoutExpired:
+            return {"unavailable": "reference GPU probe timed out"}
+        if r.returncode != 0:
+            return {"unavailable": "reference GPU probe failed: " + (r.stderr or r.stdout)[-300:]}
+        dmp = po.read_dump(os.path.join(d, "dump.bin"))
+    med = lambda k: float(np.median(dmp[k])) if k in dmp and len(dmp[k]) else 0.0
+    t_inter, t_sums, t_rec = med("time.BoxInter"), med("time.BoxReciprocalSums.slab"), \
+        med("time.BoxReciprocal.slab")
+    t = t_inter + t_sums + t_rec
+    out = {"value": 1.0 / t, "unit": UNIT, "ms_per_step": 1e3 * t,
+           "BoxInter_ms": 1e3 * t_inter, "BoxReciprocalSums_ms": 1e3 * t_sums,
+           "BoxReciprocal_ms": 1e3 * t_rec,
+           "energies": {"lj": float(dmp["time.lj"][0]), "real": float(dmp["time.real"][0]),
+                        "recip": float(dmp["time.recipSlab"][0])},
+           "what": "unmodified GOMC GPU build (CallBoxInterGPU + CallBoxReciprocalSumsGPU), "
+                   f"same box, host buffers in, median of {reps}"}
+    if force:
+        # (the GPU probe runs BoxForceReciprocal over the full k list)
+        out["BoxForce_ms"] = 1e3 * med("time.BoxForce")
+        out["BoxForceReciprocal_ms"] = 1e3 * med("time.BoxForceReciprocal.slab8")
+        out["multiparticle_ms"] = (out["BoxReciprocalSums_ms"] + out["BoxForce_ms"] +
+                                   out["BoxForceReciprocal_ms"])
+    return out
+
+
 # --------------------------------------------------------------------------
 def small_box_extras(eng, device, flush, reps=200):
     """E1/E3/E4 of SURVEY.md section 8(d) on BASELINE.json configs[1] (SPC/E, 10 000
@@ -304,6 +344,7 @@ def main():
     ap.add_argument("--workload", default="spce100k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -458,6 +499,8 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_port(s)
+        if not args.no_ref_gpu and world == 1:
+            line["reference_gpu_build"] = reference_gpu_build(s)
         print(json.dumps(line))
     e.close()
     if world > 1:

@@ -47,6 +47,33 @@ $(OUT)/gomc_probe_$(1): $$(OBJ_$(1)) $(OUT)/obj_$(1)/ref_probe.o
 endef
 $(foreach e,NVT GEMC GCMC NPT,$(eval $(call ENS_RULES,$(e))))
 
+# ---- the reference's shipped GPU build (performance comparator only) --------
+# Same unmodified sources with -DGOMC_CUDA (CMake/GOMCCUDASetup.cmake:2-3) plus
+# src/GPU/*.cu through nvcc with separable compilation, for sm_100.  It is NOT a
+# parity oracle (its device arithmetic is not bit-equal to the CPU path); bench.py
+# times it on the GPU box next to this repo's engine.
+#   make -f oracle/ref_build.mk gpu -j8
+CUDA_HOME ?= /usr/local/cuda
+NVCC      := $(CUDA_HOME)/bin/nvcc
+GPUARCH   ?= -gencode arch=compute_100,code=sm_100
+GPUDEFS   := -DGOMC_CUDA -DENSEMBLE=1
+CUSRC     := $(wildcard $(REF)/src/GPU/*.cu)
+GOBJ      := $(patsubst $(REF)/%.cpp,$(OUT)/obj_GPU_NVT/%.o,$(SRC))
+GCUOBJ    := $(patsubst $(REF)/%.cu,$(OUT)/obj_GPU_NVT/%.cu.o,$(CUSRC))
+$(OUT)/obj_GPU_NVT/%.o: $(REF)/%.cpp $(OUT)/include/GOMC_Config.h
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) $(GPUDEFS) $(INC) -I$(CUDA_HOME)/include -c $< -o $@
+$(OUT)/obj_GPU_NVT/%.cu.o: $(REF)/%.cu $(OUT)/include/GOMC_Config.h
+	@mkdir -p $(dir $@)
+	$(NVCC) -ccbin $(CXX) -O3 -std=c++17 -w -rdc=true $(GPUARCH) $(GPUDEFS) \
+	  -Xcompiler -fopenmp $(INC) -c $< -o $@
+$(OUT)/obj_GPU_NVT/ref_probe.o: oracle/ref_probe.cpp $(OUT)/include/GOMC_Config.h
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) $(GPUDEFS) $(INC) -I$(CUDA_HOME)/include -c $< -o $@
+$(OUT)/gomc_probe_GPU_NVT: $(GOBJ) $(GCUOBJ) $(OUT)/obj_GPU_NVT/ref_probe.o
+	$(NVCC) -ccbin $(CXX) $(GPUARCH) -Xcompiler -fopenmp $^ -o $@
+gpu: $(OUT)/gomc_probe_GPU_NVT
+
 clean:
 	rm -rf $(OUT)
-.PHONY: all clean
+.PHONY: all gpu clean

@@ -481,8 +481,14 @@ int run_time(int argc, char **argv) {
     ew.AllocMem();
     for (uint b = 0; b < BOXES_WITH_U_NB; ++b) {
       ew.RecipInit(b, sys.boxDimRef);
+#ifdef GOMC_CUDA
+      // the GPU build uploads the k-vectors to the device inside
+      // BoxReciprocalSetup (src/Ewald.cpp:199-228) and can afford the sweep
+      ew.BoxReciprocalSetup(b, sys.coordinates);
+#else
       std::memset(ew.sumRnew[b], 0, sizeof(double) * ew.imageSize[b]);
       std::memset(ew.sumInew[b], 0, sizeof(double) * ew.imageSize[b]);
+#endif
       ew.SetRecipRef(b);
     }
   }
@@ -524,7 +530,9 @@ int run_time(int argc, char **argv) {
                               b);
       double f1 = now();
       if (ewaldOn) {
+#ifndef GOMC_CUDA
         ew.imageSizeRef[b] = std::max(1u, nkSlab / 8);
+#endif
         // BoxForceReciprocal opens one parallel region per atom; sample the
         // first molecules only by shrinking nothing else -- cost is linear in
         // the slab size, reported as such.
