@@ -1974,6 +1974,112 @@ int gomcb200_swap_reciprocal(gomcb200_engine *e, int box, int molIndex, const do
   return run_mol_recip(e, box, molIndex, x, y, z, insert ? 1 : 2, energyRecipNew);
 }
 
+int gomcb200_mol_exchange_reciprocal(gomcb200_engine *e, int box, int n, const double *w,
+                                     const double *x, const double *y, const double *z,
+                                     int firstCall, double scale, double *energyRecipNew) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (n < 0 || (n && (!w || !x || !y || !z)) || !energyRecipNew)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[1 - bx.cur];
+  const int nk = ks.n;
+  *energyRecipNew = 0.0;
+  if (nk == 0 || !(e->ewald && e->electrostatic)) return 0;
+  rc = ensure_sums(e, bx, nk);
+  if (rc) return rc;
+  rc = stage_reserve(e, 4 * (size_t)n * sizeof(double) + 64);
+  if (rc) return rc;
+  CK(e->molBuf.reserve(4 * (size_t)n + 8));
+  double *h = e->hStage;
+  const double *src[4] = {w, x, y, z};
+  for (int f = 0; f < 4; ++f)
+    if (n) memcpy(h + (size_t)f * n, src[f], sizeof(double) * (size_t)n);
+  if (n)
+    CK(cudaMemcpyAsync(e->molBuf.p, h, 4 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
+                       e->stream));
+  const int nBlocks = (nk + 255) / 256;
+  CK(e->blockA.reserve(nBlocks + 1024));
+  const double *bR = firstCall ? bx.sum[bx.iRref].p : bx.sum[bx.iRnew].p;
+  const double *bI = firstCall ? bx.sum[bx.iIref].p : bx.sum[bx.iInew].p;
+  k_recip_weighted<<<nBlocks, 256, 0, e->stream>>>(nk, n, e->molBuf.p, scale, ks.kx.p, ks.ky.p,
+                                                  ks.kz.p, ks.prefact.p, bR, bI,
+                                                  bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p,
+                                                  e->blockA.p);
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(nBlocks, 1, e->blockA.p, nullptr, nullptr, nullptr,
+                                           e->result.p);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  rc = fetch_result(e, 1);
+  if (rc) return rc;
+  *energyRecipNew = e->hRes[0];
+  return 0;
+}
+
+int gomcb200_change_lambda_mol_reciprocal(gomcb200_engine *e, int box, int molIndex,
+                                          const double *x, const double *y, const double *z,
+                                          double lambdaCoef, double *energyRecipNew) {
+  if (!e || !e->haveTopo || molIndex < 0 || molIndex >= e->nMols || !x || !y || !z)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  std::vector<double> w, cx, cy, cz;
+  for (int a = 0; a < len; ++a) {
+    if (std::fabs(e->hCharge[s + a]) < 0.000000001) continue;  // particleHasNoCharge
+    w.push_back(e->hCharge[s + a]);
+    cx.push_back(x[a]);
+    cy.push_back(y[a]);
+    cz.push_back(z[a]);
+  }
+  return gomcb200_mol_exchange_reciprocal(e, box, (int)w.size(), w.data(), cx.data(), cy.data(),
+                                          cz.data(), 1, lambdaCoef, energyRecipNew);
+}
+
+int gomcb200_change_recip(gomcb200_engine *e, int box, int molIndex, int nStates,
+                          const double *lambdaCoul, int iState, double *energyRecip) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (molIndex < 0 || molIndex >= e->nMols || nStates < 1 || nStates > kMaxLambdaStates ||
+      !lambdaCoul || iState < 0 || iState >= nStates || !energyRecip)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[1 - bx.cur];
+  const int nk = ks.n;
+  for (int s = 0; s < nStates; ++s) energyRecip[s] = 0.0;
+  if (nk == 0 || !(e->ewald && e->electrostatic)) return 0;
+  rc = ensure_sums(e, bx, nk);
+  if (rc) return rc;
+  rc = stage_reserve(e, kMaxLambdaStates * sizeof(double));
+  if (rc) return rc;
+  CK(e->molBuf.reserve(kMaxLambdaStates + 8));
+  for (int s = 0; s < nStates; ++s)
+    e->hStage[s] = std::sqrt(lambdaCoul[s]) - std::sqrt(lambdaCoul[iState]);
+  CK(cudaMemcpyAsync(e->molBuf.p, e->hStage, nStates * sizeof(double), cudaMemcpyHostToDevice,
+                     e->stream));
+  const int nBlocks = (nk + 255) / 256;
+  CK(e->blockA.reserve((size_t)nBlocks * nStates + 1024));
+  const int first = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - first;
+  k_change_recip<<<nBlocks, 256, 0, e->stream>>>(nk, first, len, e->x.p, e->y.p, e->z.p, e->q.p,
+                                                nStates, e->molBuf.p, ks.kx.p, ks.ky.p, ks.kz.p,
+                                                ks.prefact.p, bx.sum[bx.iRref].p,
+                                                bx.sum[bx.iIref].p, e->blockA.p);
+  e->launches += 1;
+  for (int s0 = 0; s0 < nStates; s0 += 4) {
+    const int c = std::min(4, nStates - s0);
+    const double *a[4];
+    for (int j = 0; j < 4; ++j) a[j] = e->blockA.p + (size_t)(s0 + std::min(j, c - 1)) * nBlocks;
+    k_final_reduce<<<1, 1024, 0, e->stream>>>(nBlocks, c, a[0], a[1], a[2], a[3],
+                                             e->result.p + s0);
+    e->launches += 1;
+  }
+  CK(cudaGetLastError());
+  rc = fetch_result(e, nStates);
+  if (rc) return rc;
+  for (int s = 0; s < nStates; ++s) energyRecip[s] = e->hRes[s];
+  return 0;
+}
+
 int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
   int rc = check_box(e, box);
   if (rc) return rc;

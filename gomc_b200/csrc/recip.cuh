@@ -181,6 +181,89 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------
+// Weighted point charges: new = base + scale * sum_p w_p (cos, sin)(k.r_p).
+// Ewald::MolExchangeReciprocal (src/Ewald.cpp:714-826; base = ref on the first
+// call, the new sums afterwards) and Ewald::ChangeLambdaRecip (:534-585).
+// buf = {w[n], x[n], y[n], z[n]}.
+__global__ void __launch_bounds__(256)
+    k_recip_weighted(int nk, int n, const double *__restrict__ buf, double scale,
+                     const double *__restrict__ kx, const double *__restrict__ ky,
+                     const double *__restrict__ kz, const double *__restrict__ prefact,
+                     const double *baseR, const double *baseI, double *sumRnew,
+                     double *sumInew, double *__restrict__ blockEnergy) {
+  __shared__ double scratch[32];
+  __shared__ double sm[4][256];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = k < nk;
+  const double kxv = live ? kx[k] : 0.0, kyv = live ? ky[k] : 0.0, kzv = live ? kz[k] : 0.0;
+  double sR = 0.0, sI = 0.0;
+  for (int c0 = 0; c0 < n; c0 += 256) {
+    const int cn = min(256, n - c0);
+    __syncthreads();
+    if ((int)threadIdx.x < cn)
+      for (int f = 0; f < 4; ++f) sm[f][threadIdx.x] = buf[(size_t)f * n + c0 + threadIdx.x];
+    __syncthreads();
+    if (live)
+      for (int a = 0; a < cn; ++a) {
+        double d = __dadd_rn(__dadd_rn(__dmul_rn(sm[1][a], kxv), __dmul_rn(sm[2][a], kyv)),
+                             __dmul_rn(sm[3][a], kzv));
+        double sn, cs;
+        sincos(d, &sn, &cs);
+        sR += sm[0][a] * cs;
+        sI += sm[0][a] * sn;
+      }
+  }
+  double e = 0.0;
+  if (live) {
+    double r = baseR[k] + scale * sR, i = baseI[k] + scale * sI;
+    sumRnew[k] = r;
+    sumInew[k] = i;
+    e = (r * r + i * i) * prefact[k];
+  }
+  double s = block_sum(e, scratch);
+  if (threadIdx.x == 0) blockEnergy[blockIdx.x] = s;
+}
+
+// Ewald::ChangeRecip, src/Ewald.cpp:589-642: E_recip of every lambda state with the
+// molecule's charges scaled by sqrt(lambda_s) - sqrt(lambda_iState); resident
+// coordinates.  blockEnergy[s * gridDim.x + block].
+constexpr int kMaxLambdaStates = 64;
+__global__ void __launch_bounds__(256)
+    k_change_recip(int nk, int first, int len, const double *__restrict__ x,
+                   const double *__restrict__ y, const double *__restrict__ z,
+                   const double *__restrict__ q, int nStates,
+                   const double *__restrict__ coefDiff, const double *__restrict__ kx,
+                   const double *__restrict__ ky, const double *__restrict__ kz,
+                   const double *__restrict__ prefact, const double *__restrict__ sumRref,
+                   const double *__restrict__ sumIref, double *__restrict__ blockEnergy) {
+  __shared__ double scratch[32];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  double sR = 0.0, sI = 0.0, rr = 0.0, ri = 0.0, pf = 0.0;
+  if (k < nk) {
+    const double kxv = kx[k], kyv = ky[k], kzv = kz[k];
+    for (int a = first; a < first + len; ++a) {
+      const double qa = q[a];
+      if (fabs(qa) < 0.000000001) continue;
+      double d = __dadd_rn(__dadd_rn(__dmul_rn(x[a], kxv), __dmul_rn(y[a], kyv)),
+                           __dmul_rn(z[a], kzv));
+      double sn, cs;
+      sincos(d, &sn, &cs);
+      sR += qa * cs;
+      sI += qa * sn;
+    }
+    rr = sumRref[k];
+    ri = sumIref[k];
+    pf = prefact[k];
+  }
+  for (int s = 0; s < nStates; ++s) {
+    const double c = coefDiff[s];
+    const double a = rr + c * sR, b = ri + c * sI;
+    double e = block_sum(pf * (a * a + b * b), scratch);
+    if (threadIdx.x == 0) blockEnergy[(size_t)s * gridDim.x + blockIdx.x] = e;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Reciprocal force, direct algorithm (Ewald::BoxForceReciprocal CPU branch,
 // src/Ewald.cpp:1541-1592).  One thread per box atom, k staged in tiles.
 constexpr int kForceTile = 128;

@@ -45,6 +45,11 @@ _SIGS = {
     "gomcb200_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gomcb200_molecule_inter": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip]),
     "gomcb200_molecule_trial": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _dp]),
+    "gomcb200_mol_exchange_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp,
+                                                   C.c_int, C.c_double, _dp]),
+    "gomcb200_change_lambda_mol_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp,
+                                                        C.c_double, _dp]),
+    "gomcb200_change_recip": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp]),
     "gomcb200_swap_correction": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]),
     "gomcb200_swap_trial": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp]),
     "gomcb200_particle_inter": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
@@ -225,6 +230,28 @@ class Engine:
         self._ck(self.L.gomcb200_molecule_trial(self.h, box, mol_index, px, py, pz, C.byref(lj),
                                                 C.byref(re), C.byref(ov), C.byref(er)))
         return lj.value, re.value, bool(ov.value), er.value
+
+    def mol_exchange_reciprocal(self, box, w, x, y, z, first_call=True, scale=1.0):
+        (w, pw), (x, px), (y, py), (z, pz) = _d(w), _d(x), _d(y), _d(z)
+        en = C.c_double()
+        self._ck(self.L.gomcb200_mol_exchange_reciprocal(self.h, box, len(w), pw, px, py, pz,
+                                                         int(first_call), float(scale),
+                                                         C.byref(en)))
+        return en.value
+
+    def change_lambda_mol_reciprocal(self, box, mol_index, x, y, z, lambda_coef):
+        (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        en = C.c_double()
+        self._ck(self.L.gomcb200_change_lambda_mol_reciprocal(self.h, box, mol_index, px, py, pz,
+                                                              float(lambda_coef), C.byref(en)))
+        return en.value
+
+    def change_recip(self, box, mol_index, lambda_coul, i_state):
+        (lam, pl) = _d(lambda_coul)
+        out = np.zeros(len(lam))
+        self._ck(self.L.gomcb200_change_recip(self.h, box, mol_index, len(lam), pl, int(i_state),
+                                              out.ctypes.data_as(_dp)))
+        return out
 
     def swap_correction(self, box, mol_index, x, y, z):
         (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)

@@ -265,6 +265,54 @@ public:
           "SwapTrial");
     recipDelta = e - sysPotRecip_[box];
   }
+  // src/Ewald.cpp:714-826.  newMols/oldMols: coordinates of the inserted / removed
+  // molecules (molecule indices give the charges); lambdaCoef = 1 (no fractional
+  // molecule).  Returns E_new - sysPotRef recip.
+  virtual double MolExchangeReciprocal(const std::vector<XYZView> &newMols,
+                                       const std::vector<XYZView> &oldMols,
+                                       const std::vector<int> &molIndexNew,
+                                       const std::vector<int> &molIndexOld, int box,
+                                       bool first_call) {
+    std::vector<double> w, x, y, z;
+    auto add = [&](const XYZView &c, int m, double sign) {
+      const int start = eng_.MolStart(m);
+      for (int p = 0; p < eng_.MolLength(m); ++p) {
+        const double q = eng_.Charge(start + p);
+        if (std::fabs(q) < 0.000000001) continue;  // particleHasNoCharge
+        w.push_back(sign * q);
+        x.push_back(c.x[p]);
+        y.push_back(c.y[p]);
+        z.push_back(c.z[p]);
+      }
+    };
+    for (size_t m = 0; m < newMols.size(); ++m) add(newMols[m], molIndexNew[m], 1.0);
+    for (size_t m = 0; m < oldMols.size(); ++m) add(oldMols[m], molIndexOld[m], -1.0);
+    double e = 0.0;
+    check(gomcb200_mol_exchange_reciprocal(eng_.get(), box, (int)w.size(), w.data(), x.data(),
+                                           y.data(), z.data(), first_call ? 1 : 0, 1.0, &e),
+          "CallMolExchangeReciprocalGPU");
+    return e - sysPotRecip_[box];
+  }
+  // src/Ewald.cpp:534-585
+  virtual double ChangeLambdaRecip(const XYZView &molCoords, double lambdaOld, double lambdaNew,
+                                   int molIndex, int box) {
+    double e = 0.0;
+    check(gomcb200_change_lambda_mol_reciprocal(eng_.get(), box, molIndex, molCoords.x,
+                                                molCoords.y, molCoords.z,
+                                                std::sqrt(lambdaNew) - std::sqrt(lambdaOld), &e),
+          "CallChangeLambdaMolReciprocalGPU");
+    return e - sysPotRecip_[box];
+  }
+  // src/Ewald.cpp:589-642: energyDiff[s] = E_recip(lambda_s) - sysPotRef recip
+  virtual void ChangeRecip(double *energyDiffRecip, double &dUdL_CoulRecip,
+                           const std::vector<double> &lambda_Coul, int iState, int molIndex,
+                           int box) const {
+    check(gomcb200_change_recip(eng_.get(), box, molIndex, (int)lambda_Coul.size(),
+                                lambda_Coul.data(), iState, energyDiffRecip),
+          "ChangeRecip");
+    for (size_t s = 0; s < lambda_Coul.size(); ++s) energyDiffRecip[s] -= sysPotRecip_[box];
+    dUdL_CoulRecip += energyDiffRecip[lambda_Coul.size() - 1] - energyDiffRecip[0];
+  }
   virtual void BoxSelfAndCorrection(int box, double &self, double &correction) const {
     check(gomcb200_box_self_correction(eng_.get(), box, &self, &correction), "BoxSelf");
   }
@@ -329,6 +377,12 @@ public:
   double SwapDestRecip(const XYZView &, int, int) override { return 0.0; }
   double SwapSourceRecip(const XYZView &, int, int) override { return 0.0; }
   double SwapCorrection(const XYZView &, int, int, const XYZ &) const override { return 0.0; }
+  double MolExchangeReciprocal(const std::vector<XYZView> &, const std::vector<XYZView> &,
+                               const std::vector<int> &, const std::vector<int> &, int,
+                               bool) override { return 0.0; }
+  double ChangeLambdaRecip(const XYZView &, double, double, int, int) override { return 0.0; }
+  void ChangeRecip(double *d, double &, const std::vector<double> &l, int, int,
+                   int) const override { for (size_t s = 0; s < l.size(); ++s) d[s] = 0.0; }
   double SwapSelf(int, int) const override { return 0.0; }
   void BoxSelfAndCorrection(int, double &self, double &correction) const override {
     self = correction = 0.0;

@@ -232,6 +232,31 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box);
  * (MolExchangeReciprocal src/Ewald.cpp:794-806, ChangeRecip :626-630). */
 int gomcb200_get_recip_sums(gomcb200_engine *e, int box, int which,
                             double *sumR, double *sumI, int n);
+/* Ewald::MolExchangeReciprocal (src/Ewald.cpp:714-826; the reference's
+ * CallMolExchangeReciprocalGPU, CalculateEwaldCUDAKernel.cuh:45-48, only uploads
+ * host results -- here the sums are computed on the device).  n weighted point
+ * charges in the reference's loop order: w = +q*lambdaCoef for every charged atom
+ * of the inserted molecules, then -(q*lambdaCoef) for the removed ones.
+ * firstCall: base = reference sums, else the current new sums.  scale = 1. */
+int gomcb200_mol_exchange_reciprocal(gomcb200_engine *e, int box, int n,
+                                     const double *w, const double *x,
+                                     const double *y, const double *z,
+                                     int firstCall, double scale,
+                                     double *energyRecipNew);
+/* CallChangeLambdaMolReciprocalGPU (CalculateEwaldCUDAKernel.cuh:37-43) ==
+ * Ewald::ChangeLambdaRecip, src/Ewald.cpp:534-585;
+ * lambdaCoef = sqrt(lambdaNew) - sqrt(lambdaOld). */
+int gomcb200_change_lambda_mol_reciprocal(gomcb200_engine *e, int box,
+                                          int molIndex, const double *x,
+                                          const double *y, const double *z,
+                                          double lambdaCoef,
+                                          double *energyRecipNew);
+/* Ewald::ChangeRecip, src/Ewald.cpp:589-642 (host-only in the reference):
+ * energyRecip[s], s < nStates <= 64, of the resident molecule molIndex with its
+ * charges scaled by sqrt(lambdaCoul[s]) - sqrt(lambdaCoul[iState]). */
+int gomcb200_change_recip(gomcb200_engine *e, int box, int molIndex, int nStates,
+                          const double *lambdaCoul, int iState,
+                          double *energyRecip);
 /* Ewald::SwapCorrection (src/Ewald.cpp:1311-1335 and :1340-1370; charges of
  * molIndex, trial coordinates x/y/z) and Ewald::SwapSelf (:1375-1391). */
 int gomcb200_swap_correction(gomcb200_engine *e, int box, int molIndex,

@@ -940,6 +940,53 @@ double orc_mol_reciprocal(int molLen, const double *q, const double *oldX,
   return eNew;
 }
 
+double orc_recip_weighted(int n, const double *w, const double *x,
+                          const double *y, const double *z, int nk,
+                          const double *kx, const double *ky, const double *kz,
+                          const double *prefact, const double *baseR,
+                          const double *baseI, double scale, double *sumRnew,
+                          double *sumInew) {
+  double eNew = 0.0; /* src/Ewald.cpp:744-807 (scale 1) / :557-580 */
+  for (int i = 0; i < nk; ++i) {
+    double sR = 0.0, sI = 0.0;
+    for (int a = 0; a < n; ++a) {
+      double dot = x[a] * kx[i] + y[a] * ky[i] + z[a] * kz[i];
+      sR += w[a] * cos(dot);
+      sI += w[a] * sin(dot);
+    }
+    sumRnew[i] = baseR[i] + scale * sR;
+    sumInew[i] = baseI[i] + scale * sI;
+    eNew += (sumRnew[i] * sumRnew[i] + sumInew[i] * sumInew[i]) * prefact[i];
+  }
+  return eNew;
+}
+
+void orc_change_recip(int molLen, const double *q, const double *mx,
+                      const double *my, const double *mz, int nk,
+                      const double *kx, const double *ky, const double *kz,
+                      const double *prefact, const double *sumRref,
+                      const double *sumIref, int nStates,
+                      const double *lambdaCoul, int iState,
+                      double *energyRecip) {
+  for (int s = 0; s < nStates; ++s) energyRecip[s] = 0.0;
+  for (int i = 0; i < nk; ++i) { /* src/Ewald.cpp:603-630 */
+    double sR = 0.0, sI = 0.0;
+    for (int a = 0; a < molLen; ++a) {
+      if (fabs(q[a]) < 0.000000001) continue;
+      double dot = mx[a] * kx[i] + my[a] * ky[i] + mz[a] * kz[i];
+      sR += q[a] * cos(dot);
+      sI += q[a] * sin(dot);
+    }
+    for (int s = 0; s < nStates; ++s) {
+      double coefDiff = sqrt(lambdaCoul[s]) - sqrt(lambdaCoul[iState]);
+      energyRecip[s] += prefact[i] * ((sumRref[i] + coefDiff * sR) *
+                                          (sumRref[i] + coefDiff * sR) +
+                                      (sumIref[i] + coefDiff * sI) *
+                                          (sumIref[i] + coefDiff * sI));
+    }
+  }
+}
+
 double orc_swap_recip(int insert, int molLen, const double *q,
                       const double *mx, const double *my, const double *mz,
                       int nk, const double *kx, const double *ky,

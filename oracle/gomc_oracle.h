@@ -204,6 +204,27 @@ int orc_box_force_reciprocal(const orc_params *p, int nBoxMols,
                              double *rFz, double *mFx, double *mFy,
                              double *mFz);
 
+/* Ewald::MolExchangeReciprocal (src/Ewald.cpp:714-826: w = +q*lambdaCoef for the
+ * inserted atoms in order, then -(q*lambdaCoef) for the removed ones, charged
+ * atoms only, scale = 1, base = ref sums on the first call else the new sums)
+ * and Ewald::ChangeLambdaRecip (:534-585: w = q, scale = sqrt(lNew)-sqrt(lOld)).
+ * Returns E_new. */
+double orc_recip_weighted(int n, const double *w, const double *x,
+                          const double *y, const double *z, int nk,
+                          const double *kx, const double *ky, const double *kz,
+                          const double *prefact, const double *baseR,
+                          const double *baseI, double scale, double *sumRnew,
+                          double *sumInew);
+/* Ewald::ChangeRecip, src/Ewald.cpp:589-642: energyRecip[s] for every lambda
+ * state (caller subtracts sysPotRef recip). */
+void orc_change_recip(int molLen, const double *q, const double *mx,
+                      const double *my, const double *mz, int nk,
+                      const double *kx, const double *ky, const double *kz,
+                      const double *prefact, const double *sumRref,
+                      const double *sumIref, int nStates,
+                      const double *lambdaCoul, int iState,
+                      double *energyRecip);
+
 /* Ewald::MolCorrection (src/Ewald.cpp:1056-1085), summed over boxMols. */
 double orc_box_correction(const orc_params *p, int nBoxMols,
                           const int *boxMols, const int *molStart,

@@ -55,6 +55,10 @@ def lib():
         L.orc_box_reciprocal.restype = C.c_double
         L.orc_mol_reciprocal.restype = C.c_double
         L.orc_swap_recip.restype = C.c_double
+        L.orc_recip_weighted.restype = C.c_double
+        L.orc_recip_weighted.argtypes = [C.c_int] + [_dp] * 4 + [C.c_int] + [_dp] * 6 + \
+            [C.c_double, _dp, _dp]
+        L.orc_change_recip.restype = None
         L.orc_box_correction.restype = C.c_double
         L.orc_box_self.restype = C.c_double
         L.orc_swap_correction.restype = C.c_double
@@ -273,6 +277,28 @@ class Oracle:
                                   *[a[1] for a in ks], sRn.ctypes.data_as(_dp),
                                   sIn.ctypes.data_as(_dp))
         return e, sRn, sIn
+
+    def recip_weighted(self, w, xyz, kx, ky, kz, prefact, baseR, baseI, scale=1.0):
+        (w, pw) = _d(w)
+        m = [_d(a) for a in xyz]
+        ks = [_d(a) for a in (kx, ky, kz, prefact, baseR, baseI)]
+        nk = len(ks[0][0])
+        sRn, sIn = np.zeros(nk), np.zeros(nk)
+        e = self.L.orc_recip_weighted(len(w), pw, *[a[1] for a in m], nk, *[a[1] for a in ks],
+                                      float(scale), sRn.ctypes.data_as(_dp),
+                                      sIn.ctypes.data_as(_dp))
+        return e, sRn, sIn
+
+    def change_recip(self, q, mxyz, kx, ky, kz, prefact, sRref, sIref, lambda_coul, i_state):
+        (q, pq) = _d(q)
+        m = [_d(a) for a in mxyz]
+        ks = [_d(a) for a in (kx, ky, kz, prefact, sRref, sIref)]
+        (lam, pl) = _d(lambda_coul)
+        out = np.zeros(len(lam))
+        self.L.orc_change_recip(len(q), pq, *[a[1] for a in m], len(ks[0][0]),
+                                *[a[1] for a in ks], len(lam), pl, int(i_state),
+                                out.ctypes.data_as(_dp))
+        return out
 
     def box_force_reciprocal(self, box_mols, mol_start, x, y, z, charge, kx, ky, kz, prefact,
                              sR, sI, n_mols):

@@ -410,6 +410,65 @@ int run_golden(int argc, char **argv) {
       out.f64(bname("ParticleInter.real", b), re);
       out.i32(bname("ParticleInter.overlap", b), ovi);
     }
+
+    // ---- MEMC / NeMTMC / free-energy reciprocal deltas (own RNG stream so
+    // that the entries above keep their values) ------------------------------
+    if (ff.ewald && molsInBox.size() > 3) {
+      std::mt19937_64 rng2(seed * 7919ULL + 17ULL * b + 1ULL);
+      std::uniform_real_distribution<double> U2(-1.0, 1.0);
+      uint pick[4];
+      for (int i = 0; i < 4; ++i)
+        pick[i] = molsInBox[(size_t)(rng2() % molsInBox.size())];
+      // two exchange calls: (insert copy of pick0 at shifted place, remove
+      // pick1) with first_call = true, then (pick2 in, pick3 out) on top
+      std::vector<int> exMol;
+      std::vector<double> exE;
+      for (int call = 0; call < 2; ++call) {
+        uint mN = pick[2 * call], mO = pick[2 * call + 1];
+        uint lenN = mols.GetKind(mN).NumAtoms();
+        cbmc::TrialMol tN(mols.GetKind(mN), sys.boxDimRef, b);
+        cbmc::TrialMol tO(mols.GetKind(mO), sys.boxDimRef, b);
+        XYZArray nc(lenN);
+        XYZ shift(U2(rng2) * 4.0, U2(rng2) * 4.0, U2(rng2) * 4.0);
+        for (uint a = 0; a < lenN; ++a)
+          nc.Set(a, sys.boxDimRef.WrapPBC(
+                        sys.coordinates.Get(mols.MolStart(mN) + a) + shift, b));
+        tN.SetCoords(nc, 0);
+        tO.SetCoords(sys.coordinates, mols.MolStart(mO));
+        std::vector<cbmc::TrialMol> vN(1, tN), vO(1, tO);
+        std::vector<uint> iN(1, mN), iO(1, mO);
+        double d = ew.MolExchangeReciprocal(vN, vO, iN, iO, call == 0);
+        exMol.push_back((int)mN);
+        exMol.push_back((int)mO);
+        exE.push_back(d);
+        out.xyz(bname(call ? "exchange1.newCoords" : "exchange0.newCoords", b), nc);
+      }
+      out.i32(bname("exchange.mols", b), exMol);
+      out.f64(bname("exchange.dRecip", b), exE);
+      out.f64(bname("exchange.sumRnew", b), ew.sumRnew[b], ew.imageSizeRef[b]);
+      out.f64(bname("exchange.sumInew", b), ew.sumInew[b], ew.imageSizeRef[b]);
+      // ChangeLambdaRecip: molecule pick0 at its current coordinates
+      {
+        uint m = pick[0];
+        uint len = mols.GetKind(m).NumAtoms();
+        XYZArray mc(len);
+        for (uint a = 0; a < len; ++a)
+          mc.Set(a, sys.coordinates.Get(mols.MolStart(m) + a));
+        double d = ew.ChangeLambdaRecip(mc, 0.3, 0.85, m, b);
+        out.i32(bname("changeLambda.mol", b), (int)m);
+        out.f64(bname("changeLambda.dRecip", b), d);
+        out.f64(bname("changeLambda.sumRnew", b), ew.sumRnew[b], ew.imageSizeRef[b]);
+        std::vector<double> lam = {0.0, 0.2, 0.5, 0.75, 1.0};
+        std::vector<Energy> ediff(lam.size());
+        Energy dUdL;
+        ew.ChangeRecip(ediff.data(), dUdL, lam, 2, m, b);
+        std::vector<double> er;
+        for (auto &e : ediff) er.push_back(e.recip);
+        out.f64(bname("changeRecip.lambda", b), lam);
+        out.f64(bname("changeRecip.dRecip", b), er);
+        out.f64(bname("changeRecip.dUdL", b), dUdL.recip);
+      }
+    }
   }
   return 0;
 }

@@ -105,6 +105,50 @@ def test_reciprocal(gold):
     old = [a[ms[m]:ms[m + 1]] for a in _xyz(d, "coords")]
     en = e.swap_reciprocal(0, m, *old, 0)
     assert abs(en - (d["box0.SwapSourceRecip"][0] + ref)) <= TOL * abs(en)
+    # swap corrections against the reference's numbers
+    co, se = e.swap_correction(0, m, *_xyz(d, "box0.swap.newCoords"))
+    assert abs(co - d["box0.SwapCorrection.new"][0]) <= TOL * abs(co)
+    assert abs(se - d["box0.SwapSelf"][0]) <= TOL * abs(se)
+    co, _ = e.swap_correction(0, m, *old)
+    assert abs(co - d["box0.SwapCorrection.old"][0]) <= TOL * abs(co)
+
+
+def test_exchange_and_lambda_reciprocal(gold):
+    """MolExchangeReciprocal (two chained calls), ChangeLambdaRecip, ChangeRecip."""
+    from tests.test_oracle_golden import exchange_weights
+    d, e = gold
+    if not d["ff.ewald"][0] or "box0.exchange.mols" not in d:
+        pytest.skip("no Ewald")
+    nk = int(d["box0.nk"][0])
+    e.box_reciprocal_sums(0)
+    e.set_recip_ref(0)
+    ref = d["box0.sysPotRef.recip"][0]
+    ms, q = d["molStart"], d["particleCharge"]
+    xyz = _xyz(d, "coords")
+    calls = exchange_weights(q, ms, d["box0.exchange.mols"],
+                             [_xyz(d, "box0.exchange0.newCoords"),
+                              _xyz(d, "box0.exchange1.newCoords")], xyz)
+    for c, (w, cx) in enumerate(calls):
+        en = e.mol_exchange_reciprocal(0, w, *cx, first_call=(c == 0))
+        want = d["box0.exchange.dRecip"][c] + ref
+        assert abs(en - want) <= TOL * abs(want)
+    gR, gI = e.get_recip_sums(0, eng.SUM_NEW, nk)
+    scale = max(np.max(np.abs(d["box0.sumRref"])), np.max(np.abs(d["box0.sumIref"])))
+    assert np.max(np.abs(gR - d["box0.exchange.sumRnew"])) <= TOL * scale
+    assert np.max(np.abs(gI - d["box0.exchange.sumInew"])) <= TOL * scale
+    m = int(d["box0.changeLambda.mol"][0])
+    mc = [a[ms[m]:ms[m + 1]] for a in xyz]
+    en = e.change_lambda_mol_reciprocal(0, m, *mc, np.sqrt(0.85) - np.sqrt(0.3))
+    want = d["box0.changeLambda.dRecip"][0] + ref
+    assert abs(en - want) <= TOL * abs(want)
+    gR, _ = e.get_recip_sums(0, eng.SUM_NEW, nk)
+    assert np.max(np.abs(gR - d["box0.changeLambda.sumRnew"])) <= TOL * scale
+    er = e.change_recip(0, m, d["box0.changeRecip.lambda"], 2)
+    want = d["box0.changeRecip.dRecip"] + ref
+    assert np.max(np.abs(er - want)) <= TOL * np.max(np.abs(want))
+    # the reference sums are never written by trial deltas
+    rR, _ = e.get_recip_sums(0, eng.SUM_REF, nk)
+    assert np.max(np.abs(rR - d["box0.sumRref"])) <= TOL * scale
 
 
 def test_reciprocal_force_and_torque(gold):
