@@ -564,6 +564,136 @@ int orc_box_force(const orc_params *p, int nAtomsTotal, int nMols,
 }
 
 /* ------------------------------------------------------------------------ */
+/* Virial                                                                    */
+
+/* BoxDimensions::UnwrapPBC (scalar), src/BoxDimensions.cpp:297-320 */
+static inline double unwrap_scalar(double v, double ref, double ax, double halfAx) {
+  if (fabs(ref - v) > halfAx) {
+    if (ref < halfAx)
+      v -= ax;
+    else
+      v += ax;
+  }
+  return v;
+}
+/* BoxDimensions::UnwrapPBC(x,y,z,b,ref) and the non-orthogonal override
+ * (src/BoxDimensionsNonOrth.cpp:305-319). */
+static inline void unwrap_vec(const orc_params *p, double v[3], const double ref[3]) {
+  if (p->nonOrth) {
+    double u[3], ur[3];
+    vec_mat(v, p->cellBasisInv, u);
+    vec_mat(ref, p->cellBasisInv, ur);
+    for (int d = 0; d < 3; ++d)
+      u[d] = unwrap_scalar(u[d], ur[d], p->axis[d], p->axis[d] * 0.5);
+    vec_mat(u, p->cellBasis, v);
+  } else {
+    for (int d = 0; d < 3; ++d)
+      v[d] = unwrap_scalar(v[d], ref[d], p->axis[d], p->axis[d] * 0.5);
+  }
+}
+
+int orc_virial_calc(const orc_params *p, int nAtomsTotal, const double *x,
+                    const double *y, const double *z, const int *kind,
+                    const int *mol, const double *charge, const double *comX,
+                    const double *comY, const double *comZ,
+                    const int *boxAtoms, int nBox, double vT[3], double rT[3]) {
+  cell_csr c = csr_make(p, nAtomsTotal, x, y, z, boxAtoms, nBox);
+  double boxRcutSq = box_rcut(p) * box_rcut(p);
+  double vT11 = 0.0, vT22 = 0.0, vT33 = 0.0, rT11 = 0.0, rT22 = 0.0, rT33 = 0.0;
+  for (int ci = 0; ci < nBox; ++ci) { /* src/CalculateEnergy.cpp:464-531 */
+    int cur = c.cellVector[ci];
+    int curCell = c.map[cur];
+    for (int nc = 0; nc < 27; ++nc) {
+      int nbrCell = c.nbr[curCell * 27 + nc];
+      int end = c.cellStart[nbrCell + 1];
+      for (int ni = c.cellStart[nbrCell]; ni < end; ++ni) {
+        int nb = c.cellVector[ni];
+        if (cur < nb && mol[cur] != mol[nb]) {
+          double distSq, d[3];
+          if (in_rcut(p, boxRcutSq, x[cur], y[cur], z[cur], x[nb], y[nb],
+                      z[nb], &distSq, d)) {
+            double cc[3] = {comX[mol[cur]] - comX[mol[nb]],
+                            comY[mol[cur]] - comY[mol[nb]],
+                            comZ[mol[cur]] - comZ[mol[nb]]};
+            min_image_vec(p, cc);
+            if (p->electrostatic) {
+              double qi_qj = charge[cur] * charge[nb];
+              if (qi_qj != 0.0) {
+                double pRF = orc_calc_coulomb_vir(p, distSq, qi_qj);
+                rT11 += pRF * (d[0] * cc[0]);
+                rT22 += pRF * (d[1] * cc[1]);
+                rT33 += pRF * (d[2] * cc[2]);
+              }
+            }
+            double pVF = orc_calc_vir(p, distSq, kind[cur], kind[nb]);
+            vT11 += pVF * (d[0] * cc[0]);
+            vT22 += pVF * (d[1] * cc[1]);
+            vT33 += pVF * (d[2] * cc[2]);
+          }
+        }
+      }
+    }
+  }
+  vT[0] = vT11;
+  vT[1] = vT22;
+  vT[2] = vT33;
+  rT[0] = rT11 * ORC_QQFACT; /* :555-567 */
+  rT[1] = rT22 * ORC_QQFACT;
+  rT[2] = rT33 * ORC_QQFACT;
+  csr_free(&c);
+  return 0;
+}
+
+int orc_virial_reciprocal(const orc_params *p, int nBoxMols, const int *boxMols,
+                          const int *molStart, const double *x, const double *y,
+                          const double *z, const double *charge,
+                          const double *comX, const double *comY,
+                          const double *comZ, int nk, const double *kx,
+                          const double *ky, const double *kz,
+                          const double *hsqr, const double *prefact,
+                          const double *sumRref, const double *sumIref,
+                          double wT[3]) {
+  double wT11 = 0.0, wT22 = 0.0, wT33 = 0.0;
+  double constVal = 1.0 / (4.0 * (p->alpha * p->alpha)); /* src/Ewald.cpp:1177 */
+  for (int i = 0; i < nk; ++i) {                         /* :1229-1244 */
+    double factor =
+        prefact[i] * (sumRref[i] * sumRref[i] + sumIref[i] * sumIref[i]);
+    wT11 += factor * (1.0 - 2.0 * (constVal + 1.0 / hsqr[i]) * kx[i] * kx[i]);
+    wT22 += factor * (1.0 - 2.0 * (constVal + 1.0 / hsqr[i]) * ky[i] * ky[i]);
+    wT33 += factor * (1.0 - 2.0 * (constVal + 1.0 / hsqr[i]) * kz[i] * kz[i]);
+  }
+  for (int mi = 0; mi < nBoxMols; ++mi) { /* intramolecular part, :1247-1285 */
+    int m = boxMols[mi];
+    double com[3] = {comX[m], comY[m], comZ[m]};
+    for (int a = molStart[m]; a < molStart[m + 1]; ++a) {
+      if (fabs(charge[a]) < 0.000000001) continue;
+      double at[3] = {x[a], y[a], z[a]};
+      unwrap_vec(p, at, com);
+      double diff[3] = {at[0] - com[0], at[1] - com[1], at[2] - com[2]};
+      double q = charge[a] * 1.0;
+      /* one OpenMP reduction region per atom (:1272-1284): the k sum goes
+       * into a zero-initialised private copy that is then added to wT */
+      double p11 = 0.0, p22 = 0.0, p33 = 0.0;
+      for (int i = 0; i < nk; ++i) {
+        double arg = x[a] * kx[i] + y[a] * ky[i] + z[a] * kz[i];
+        double factor =
+            prefact[i] * 2.0 * (sumIref[i] * cos(arg) - sumRref[i] * sin(arg)) * q;
+        p11 += factor * (kx[i] * diff[0]);
+        p22 += factor * (ky[i] * diff[1]);
+        p33 += factor * (kz[i] * diff[2]);
+      }
+      wT11 += p11;
+      wT22 += p22;
+      wT33 += p33;
+    }
+  }
+  wT[0] = wT11;
+  wT[1] = wT22;
+  wT[2] = wT33;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* MoleculeInter / ParticleInter                                             */
 
 /* energy of one probe position against the 27 cells around it; sign = -1 for

@@ -204,6 +204,25 @@ int orc_box_force_reciprocal(const orc_params *p, int nBoxMols,
                              double *rFz, double *mFx, double *mFy,
                              double *mFz);
 
+/* CalculateEnergy::VirialCalc, pair part (src/CalculateEnergy.cpp:411-567):
+ * diagonal of the LJ tensor vT and of the real-space Coulomb tensor rT (already
+ * multiplied by qqFact).  Tail correction and reciprocal part are separate. */
+int orc_virial_calc(const orc_params *p, int nAtomsTotal, const double *x,
+                    const double *y, const double *z, const int *kind,
+                    const int *mol, const double *charge, const double *comX,
+                    const double *comY, const double *comZ,
+                    const int *boxAtoms, int nBox, double vT[3], double rT[3]);
+/* Ewald::VirialReciprocal, src/Ewald.cpp:1168-1305 (CPU branch): diagonal wT. */
+int orc_virial_reciprocal(const orc_params *p, int nBoxMols, const int *boxMols,
+                          const int *molStart, const double *x, const double *y,
+                          const double *z, const double *charge,
+                          const double *comX, const double *comY,
+                          const double *comZ, int nk, const double *kx,
+                          const double *ky, const double *kz,
+                          const double *hsqr, const double *prefact,
+                          const double *sumRref, const double *sumIref,
+                          double wT[3]);
+
 /* Ewald::MolExchangeReciprocal (src/Ewald.cpp:714-826: w = +q*lambdaCoef for the
  * inserted atoms in order, then -(q*lambdaCoef) for the removed ones, charged
  * atoms only, scale = 1, base = ref sums on the first call else the new sums)

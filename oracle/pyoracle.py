@@ -192,6 +192,26 @@ class Oracle:
                              *[a.ctypes.data_as(_dp) for a in mF])
         return lj.value, re.value, aF, mF
 
+    def virial_calc(self, x, y, z, kind, mol, charge, com, box_atoms):
+        (x, px), (y, py), (z, pz), (q, pq) = _d(x), _d(y), _d(z), _d(charge)
+        (k, pk), (m, pm), (ba, pba) = _i(kind), _i(mol), _i(box_atoms)
+        cm = [_d(a) for a in com]
+        vT, rT = np.zeros(3), np.zeros(3)
+        self.L.orc_virial_calc(self.pp, len(x), px, py, pz, pk, pm, pq, *[a[1] for a in cm],
+                               pba, len(ba), vT.ctypes.data_as(_dp), rT.ctypes.data_as(_dp))
+        return vT, rT
+
+    def virial_reciprocal(self, box_mols, mol_start, x, y, z, charge, com, kx, ky, kz, hsqr,
+                          prefact, sR, sI):
+        (bm, pbm), (ms, pms) = _i(box_mols), _i(mol_start)
+        arrs = [_d(a) for a in (x, y, z, charge, *com)]
+        ks = [_d(a) for a in (kx, ky, kz, hsqr, prefact, sR, sI)]
+        wT = np.zeros(3)
+        self.L.orc_virial_reciprocal(self.pp, len(bm), pbm, pms, *[a[1] for a in arrs],
+                                     len(ks[0][0]), *[a[1] for a in ks],
+                                     wT.ctypes.data_as(_dp))
+        return wT
+
     def molecule_inter(self, x, y, z, kind, mol, charge, box_atoms, mol_index, mol_start,
                        mol_len, nx, ny, nz):
         (x, px), (y, py), (z, pz), (q, pq) = _d(x), _d(y), _d(z), _d(charge)

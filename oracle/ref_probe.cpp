@@ -243,6 +243,18 @@ int run_golden(int argc, char **argv) {
     out.f64(bname("BoxInter.real", b), pot.boxEnergy[b].real);
     out.f64(bname("BoxInter.tailCorrection", b),
             pot.boxEnergy[b].tailCorrection);
+    // ---- VirialCalc (pair tensors + tail correction + VirialReciprocal) ----
+    {
+      Virial v = ce.VirialCalc(b);
+      double it[3] = {v.interTens[0][0], v.interTens[1][1], v.interTens[2][2]};
+      double rt[3] = {v.realTens[0][0], v.realTens[1][1], v.realTens[2][2]};
+      double wt[3] = {v.recipTens[0][0], v.recipTens[1][1], v.recipTens[2][2]};
+      out.f64(bname("Virial.interTens", b), it, 3);
+      out.f64(bname("Virial.realTens", b), rt, 3);
+      out.f64(bname("Virial.recipTens", b), wt, 3);
+      double sc[5] = {v.inter, v.real, v.recip, v.tailCorrection, v.total};
+      out.f64(bname("Virial.scalars", b), sc, 5);
+    }
     // ---- BoxForce (needs multiParticleEnabled for ResetForce) -------------
     {
       XYZArray aF(sys.coordinates.Count()), mF(mols.count);
