@@ -36,7 +36,20 @@ struct BoxParams {
   // (BoxDimensionsNonOrth, src/BoxDimensionsNonOrth.h:79-109); ax[] = edge lengths
   int nonOrth;
   double B[9], Bi[9];
+  // molecule centres of mass (virial sweep only)
+  const double *comx, *comy, *comz;
 };
+
+// BoxDimensions::UnwrapPBC (scalar), src/BoxDimensions.cpp:297-320
+__device__ __forceinline__ double unwrap_scalar(double v, double ref, double ax, double half) {
+  if (fabs(ref - v) > half) {
+    if (ref < half)
+      v -= ax;
+    else
+      v += ax;
+  }
+  return v;
+}
 
 __device__ __forceinline__ double min_image(double raw, double ax, double half) {
   // BoxDimensions::MinImageSigned, src/BoxDimensions.h:169-175
@@ -65,6 +78,30 @@ __device__ __forceinline__ void min_image_vec(const BoxParams &p, double &dx, do
     dx = min_image(dx, p.ax[0], p.half[0]);
     dy = min_image(dy, p.ax[1], p.half[1]);
     dz = min_image(dz, p.ax[2], p.half[2]);
+  }
+}
+
+// BoxDimensions::UnwrapPBC(x,y,z,b,ref) / the non-orthogonal override
+// (src/BoxDimensionsNonOrth.cpp:305-319): unslant point and reference, unwrap, slant.
+__device__ __forceinline__ void unwrap_vec(const BoxParams &p, double &x, double &y, double &z,
+                                           double rx, double ry, double rz) {
+  if (p.nonOrth) {
+    double ux = x * p.Bi[0] + y * p.Bi[3] + z * p.Bi[6];
+    double uy = x * p.Bi[1] + y * p.Bi[4] + z * p.Bi[7];
+    double uz = x * p.Bi[2] + y * p.Bi[5] + z * p.Bi[8];
+    double vx = rx * p.Bi[0] + ry * p.Bi[3] + rz * p.Bi[6];
+    double vy = rx * p.Bi[1] + ry * p.Bi[4] + rz * p.Bi[7];
+    double vz = rx * p.Bi[2] + ry * p.Bi[5] + rz * p.Bi[8];
+    ux = unwrap_scalar(ux, vx, p.ax[0], p.half[0]);
+    uy = unwrap_scalar(uy, vy, p.ax[1], p.half[1]);
+    uz = unwrap_scalar(uz, vz, p.ax[2], p.half[2]);
+    x = ux * p.B[0] + uy * p.B[3] + uz * p.B[6];
+    y = ux * p.B[1] + uy * p.B[4] + uz * p.B[7];
+    z = ux * p.B[2] + uy * p.B[5] + uz * p.B[8];
+  } else {
+    x = unwrap_scalar(x, rx, p.ax[0], p.half[0]);
+    y = unwrap_scalar(y, ry, p.ax[1], p.half[1]);
+    z = unwrap_scalar(z, rz, p.ax[2], p.half[2]);
   }
 }
 

@@ -152,6 +152,7 @@ struct gomcb200_engine {
   DevBuf<int> kind, mol, molStart;
   DevBuf<double> x, y, z, q, comx, comy, comz;
   DevBuf<double> force[5][3];
+  DevBuf<double> scratchF[3];  // k-space forces for VirialReciprocal
   std::vector<BoxState> box;
   int imageTotal = 0;
   int recipAlgo = 2;  // 0 direct, 1 factorised SIMT, 2 factorised DMMA
@@ -223,6 +224,9 @@ BoxParams make_params(const gomcb200_engine *e, int b) {
     p.B[i] = bx.B[i];
     p.Bi[i] = bx.Bi[i];
   }
+  p.comx = e->comx.p;
+  p.comy = e->comy.p;
+  p.comz = e->comz.p;
   return p;
 }
 
@@ -313,13 +317,14 @@ int fetch_result(gomcb200_engine *e, int n) {
 
 // warps per CTA of the box sweep: the energy kernel fits 32 warps in the
 // register file (<= 64 regs/thread), the force kernel 20 (<= 102 regs/thread)
-constexpr int kWarpsEnergy = 32, kWarpsForce = 20;
+constexpr int kWarpsEnergy = 32, kWarpsForce = 20, kWarpsVirial = 16;
 
-template <bool FORCE>
+template <int FORCE>  // MODE_ENERGY, MODE_FORCE or MODE_VIRIAL
 void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int useSmem,
                  int smemAtoms, size_t smemBytes, int grid, int cell0) {
   BoxState &bx = e->box[b];
-  constexpr int NW = FORCE ? kWarpsForce : kWarpsEnergy;
+  constexpr int NW = FORCE == MODE_ENERGY ? kWarpsEnergy
+                                          : (FORCE == MODE_VIRIAL ? kWarpsVirial : kWarpsForce);
   double *fx = e->force[GOMCB200_ATOM_FORCE][0].p;
   double *fy = e->force[GOMCB200_ATOM_FORCE][1].p;
   double *fz = e->force[GOMCB200_ATOM_FORCE][2].p;
@@ -346,8 +351,10 @@ void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int 
   e->launches += 1;
 }
 
-// pair sweep; results (LJ, real) land in e->result[0..1]
-int run_pair(gomcb200_engine *e, int b, bool force) {
+// pair sweep; results (LJ, real) land in e->result[0..1]; mode MODE_VIRIAL: the six
+// tensor sums (LJ 11/22/33, Coulomb 11/22/33 without qqFact) in e->result[0..5]
+int run_pair(gomcb200_engine *e, int b, int mode) {
+  const bool force = mode == MODE_FORCE;
   int rc = ensure_cells(e, b);
   if (rc) return rc;
   BoxState &bx = e->box[b];
@@ -360,9 +367,10 @@ int run_pair(gomcb200_engine *e, int b, bool force) {
   const int cell1 = (int)(((long long)nCells * (e->shardRank + 1)) / e->shardWorld);
   int grid = (cell1 - cell0) * slices;
   // shared-memory staging of the neighbour cells (40 B per atom)
-  const int nWarps = force ? kWarpsForce : kWarpsEnergy;
+  const int nWarps = mode == MODE_ENERGY ? kWarpsEnergy
+                                         : (mode == MODE_VIRIAL ? kWarpsVirial : kWarpsForce);
   const size_t queueBytes = sizeof(WarpQueue) * nWarps;
-  size_t staticSmem = 12 * 1024 + queueBytes;
+  size_t staticSmem = (mode == MODE_VIRIAL ? 28 : 12) * 1024 + queueBytes;
   size_t capAtoms = (e->smemOptin > staticSmem ? (e->smemOptin - staticSmem) : 0) / 40;
   double avg = (double)bx.nAtoms / nCells;
   size_t want = (size_t)((force ? 27.0 : 14.0) * avg * 1.4) + 96;
@@ -370,18 +378,31 @@ int run_pair(gomcb200_engine *e, int b, bool force) {
   smemAtoms &= ~1;
   int useSmem = smemAtoms >= 64;
   size_t smemBytes = queueBytes + (useSmem ? (size_t)smemAtoms * 40 : 0);
-  CK(e->blockA.reserve(grid + 1024));
+  CK(e->blockA.reserve((mode == MODE_VIRIAL ? 6 : 1) * (size_t)grid + 1024));
   CK(e->blockB.reserve(grid + 1024));
   if (grid == 0) {
     CK(cudaMemsetAsync(e->result.p, 0, 8 * sizeof(double), e->stream));
     return 0;
   }
+  if (mode == MODE_VIRIAL) {
+    launch_pair<MODE_VIRIAL>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
+    CK(cudaGetLastError());
+    const double *a = e->blockA.p;
+    k_final_reduce<<<1, 1024, 0, e->stream>>>(grid, 4, a, e->blockB.p, a + 2 * (size_t)grid,
+                                             a + 3 * (size_t)grid, e->result.p);
+    k_final_reduce<<<1, 1024, 0, e->stream>>>(grid, 2, a + 4 * (size_t)grid,
+                                             a + 5 * (size_t)grid, nullptr, nullptr,
+                                             e->result.p + 4);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+  }
   if (force) {
     // ResetForce (src/CalculateEnergy.cpp:1408-1428) is implicit: every atom
     // and molecule of the box is overwritten below.
-    launch_pair<true>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
+    launch_pair<MODE_FORCE>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
   } else {
-    launch_pair<false>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
+    launch_pair<MODE_ENERGY>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
   }
   CK(cudaGetLastError());
   k_final_reduce<<<1, 1024, 0, e->stream>>>(grid, 2, e->blockA.p, e->blockB.p, nullptr,
@@ -2080,18 +2101,16 @@ int gomcb200_change_recip(gomcb200_engine *e, int box, int molIndex, int nStates
   return 0;
 }
 
-int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
-  int rc = check_box(e, box);
-  if (rc) return rc;
-  CK(cudaSetDevice(e->device));
+// Reciprocal force of every atom of the box from the sums (sumR, sumI) into rf*;
+// withIntra: include the intramolecular correction force (src/Ewald.cpp:1556-1569),
+// else the pure k-space part (what VirialReciprocal's per-atom k sum is made of).
+static int run_force_recip(gomcb200_engine *e, int box, const double *sumR, const double *sumI,
+                           double *rfx, double *rfy, double *rfz, bool withIntra) {
   BoxState &bx = e->box[box];
   KSet &ks = bx.kset[1 - bx.cur];
-  rc = ensure_sums(e, bx, ks.n);
-  if (rc) return rc;
-  if (bx.nAtoms == 0) return 0;
   BoxParams p = make_params(e, box);
-  double *rfx = e->force[2][0].p, *rfy = e->force[2][1].p, *rfz = e->force[2][2].p;
   bool done = false;
+  int rc;
   if (e->recipAlgo == 2 && ks.fmValid && bx.nCharged > 0 && ks.n > 0) {
     rc = ensure_packed(e, box);
     if (rc) return rc;
@@ -2123,11 +2142,17 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
     int AB = smemFor(64) <= budget ? 64 : (smemFor(32) <= budget ? 32 : 0);
     if (AB) {
       k_force_wmat<<<ks.fmNTiles, 256, 0, e->stream>>>(ks.fmNTiles, ks.fmTiles.p, ks.fmRows.p,
-                                                      bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p,
-                                                      ks.prefact.p, ks.fmW.p);
-      k_force_recip_intra<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
-          p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->q.p,
-          rfx, rfy, rfz);
+                                                      sumR, sumI, ks.prefact.p, ks.fmW.p);
+      if (withIntra) {
+        k_force_recip_intra<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
+            p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p,
+            e->q.p, rfx, rfy, rfz);
+      } else {  // the DMMA kernel accumulates onto the buffers
+        const size_t bytes = sizeof(double) * (size_t)e->nAtoms;
+        CK(cudaMemsetAsync(rfx, 0, bytes, e->stream));
+        CK(cudaMemsetAsync(rfy, 0, bytes, e->stream));
+        CK(cudaMemsetAsync(rfz, 0, bytes, e->stream));
+      }
       const int grid = (bx.nCharged + AB - 1) / AB;
       const size_t smem = smemFor(AB);
       if (AB == 64) {
@@ -2146,15 +2171,88 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
   if (!done) {
     k_force_recip_direct<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
         p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->q.p,
-        ks.n, ks.kx.p, ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p,
-        rfx, rfy, rfz);
+        ks.n, ks.kx.p, ks.ky.p, ks.kz.p, ks.prefact.p, sumR, sumI, rfx, rfy, rfz,
+        withIntra ? 1 : 0);
     e->launches += 1;
   }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[1 - bx.cur];
+  rc = ensure_sums(e, bx, ks.n);
+  if (rc) return rc;
+  if (bx.nAtoms == 0) return 0;
+  rc = run_force_recip(e, box, bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p, e->force[2][0].p,
+                       e->force[2][1].p, e->force[2][2].p, true);
+  if (rc) return rc;
   k_mol_force<<<(bx.nMols + 255) / 256, 256, 0, e->stream>>>(
       bx.nMols, bx.molList.p, e->molStart.p, e->force[2][0].p, e->force[2][1].p,
       e->force[2][2].p, e->force[3][0].p, e->force[3][1].p, e->force[3][2].p);
   e->launches += 1;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- virial -----------------------------------------------------------------
+int gomcb200_box_inter_virial(gomcb200_engine *e, int box, double vT[3], double rT[3]) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (!vT || !rT) return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  rc = run_pair(e, box, MODE_VIRIAL);
+  if (rc) return rc;
+  rc = fetch_result(e, 6);
+  if (rc) return rc;
+  for (int c = 0; c < 3; ++c) {
+    vT[c] = e->hRes[c];
+    rT[c] = e->hRes[3 + c] * kQQFact;  // src/CalculateEnergy.cpp:555-567
+  }
+  return 0;
+}
+
+int gomcb200_virial_reciprocal(gomcb200_engine *e, int box, double wT[3]) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (!wT) return fail(GOMCB200_EINVAL, "bad arguments");
+  wT[0] = wT[1] = wT[2] = 0.0;
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[1 - bx.cur];
+  if (!(e->ewald && e->electrostatic) || ks.n == 0 || bx.nAtoms == 0) return 0;
+  rc = ensure_sums(e, bx, ks.n);
+  if (rc) return rc;
+  const double *sR = bx.sum[bx.iRref].p, *sI = bx.sum[bx.iIref].p;
+  const int gk = (ks.n + 255) / 256, ga = (bx.nAtoms + 255) / 256;
+  CK(e->blockA.reserve(3 * (size_t)gk + 1024));
+  CK(e->blockB.reserve(3 * (size_t)ga + 1024));
+  for (int c = 0; c < 3; ++c) CK(e->scratchF[c].reserve(e->nAtoms + 1));
+  const double constVal = 1.0 / (4.0 * (e->alpha[box] * e->alpha[box]));
+  k_virial_recip_k<<<gk, 256, 0, e->stream>>>(ks.n, constVal, ks.kx.p, ks.ky.p, ks.kz.p,
+                                             ks.hsqr.p, ks.prefact.p, sR, sI, e->blockA.p);
+  e->launches += 1;
+  rc = run_force_recip(e, box, sR, sI, e->scratchF[0].p, e->scratchF[1].p, e->scratchF[2].p,
+                       false);
+  if (rc) return rc;
+  k_virial_recip_intra<<<ga, 256, 0, e->stream>>>(make_params(e, box), bx.nAtoms, bx.atomList.p,
+                                                 e->mol.p, e->x.p, e->y.p, e->z.p, e->q.p,
+                                                 e->scratchF[0].p, e->scratchF[1].p,
+                                                 e->scratchF[2].p, e->blockB.p);
+  const double *a = e->blockA.p, *b = e->blockB.p;
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(gk, 3, a, a + gk, a + 2 * (size_t)gk, nullptr,
+                                           e->result.p);
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(ga, 3, b, b + ga, b + 2 * (size_t)ga, nullptr,
+                                           e->result.p + 3);
+  e->launches += 3;
+  CK(cudaGetLastError());
+  rc = fetch_result(e, 6);
+  if (rc) return rc;
+  for (int c = 0; c < 3; ++c) wT[c] = e->hRes[c] + e->hRes[3 + c];
   return 0;
 }
 

@@ -117,11 +117,16 @@ struct WarpQueue {
 struct PairAcc {
   double lj, real, fx, fy, fz;
   int overlap;
+  // virial mode only: sixth accumulator and the COM of the i atom's molecule
+  double ex, cix, ciy, ciz;
 };
+// pair evaluation modes: energies; energies + forces; virial tensors
+// (acc.lj/real/fx = LJ diag 11/22/33, acc.fy/fz/ex = Coulomb diag 11/22/33)
+enum { MODE_ENERGY = 0, MODE_FORCE = 1, MODE_VIRIAL = 2 };
 
 enum { SWEEP_PROBE = 0, SWEEP_HALF = 1, SWEEP_FULL = 2 };
 
-template <int VDW, bool FORCE>
+template <int VDW, int MODE>
 __device__ __forceinline__ void eval_pair(const BoxParams &p, int ki, double qi,
                                           int excludeMol, bool countEnergy,
                                           double sign, bool checkOverlap,
@@ -131,7 +136,25 @@ __device__ __forceinline__ void eval_pair(const BoxParams &p, int ki, double qi,
   double r2 = dist_sq(dx, dy, dz);
   if (checkOverlap && r2 < p.rCutLowSq) acc.overlap = 1;
   int idx = ki + kmj.x * p.kindCount;
-  if (FORCE) {
+  if (MODE == MODE_VIRIAL) {
+    // CalculateEnergy::VirialCalc, src/CalculateEnergy.cpp:483-527
+    double cx = acc.cix - p.comx[kmj.y], cy = acc.ciy - p.comy[kmj.y],
+           cz = acc.ciz - p.comz[kmj.y];
+    min_image_vec(p, cx, cy, cz);
+    double eL, wL, eC = 0.0, wC = 0.0;
+    calc_en_vir<VDW>(p, r2, idx, eL, wL);
+    if (p.electrostatic) {
+      double qq = qi * qj;  // qqFact multiplies the finished tensor (:555-567)
+      if (qq != 0.0) calc_coulomb_en_vir<VDW>(p, r2, qq, eC, wC);
+    }
+    const double t1 = dx * cx, t2 = dy * cy, t3 = dz * cz;
+    acc.lj += wL * t1;
+    acc.real += wL * t2;
+    acc.fx += wL * t3;
+    acc.fy += wC * t1;
+    acc.fz += wC * t2;
+    acc.ex += wC * t3;
+  } else if (MODE == MODE_FORCE) {
     double eL, wL, eC = 0.0, wC = 0.0;
     calc_en_vir<VDW>(p, r2, idx, eL, wL);
     if (p.electrostatic) {
@@ -184,7 +207,7 @@ __device__ __forceinline__ int2 jload_km(const int2 *g, unsigned s, int j) {
 // index of the atom.  SM: j arrays staged in shared memory.  GEN: at least one
 // axis has fewer than 4 cells (per-pair minimum image on that axis).
 // qBase: shared address of this warp's WarpQueue.
-template <int VDW, bool FORCE, int SWEEP, bool SM, bool GEN>
+template <int VDW, int MODE, int SWEEP, bool SM, bool GEN>
 __device__ __forceinline__ void warp_probe(
     const BoxParams &p, const int generic[3], double xi, double yi, double zi,
     int ki, double qi, int excludeMol, int selfIndex, int iGlobal, double sign,
@@ -241,7 +264,7 @@ __device__ __forceinline__ void warp_probe(
       int jj = je & 0x3fffffff;
       double ddx = lds_f64(qX + pos * 8u), ddy = lds_f64(qY + pos * 8u),
              ddz = lds_f64(qZ + pos * 8u);
-      eval_pair<VDW, FORCE>(p, ki, qi, excludeMol, SWEEP != SWEEP_FULL || (je & 0x40000000),
+      eval_pair<VDW, MODE>(p, ki, qi, excludeMol, SWEEP != SWEEP_FULL || (je & 0x40000000),
                             sign, checkOverlap, ddx, ddy, ddz, jload<SM>(ja.q, ja.sq, jj),
                             jload_km<SM>(ja.km, ja.skm, jj), acc);
     }
@@ -325,7 +348,7 @@ constexpr int kPairWarps = kPairThreads / 32;
 // !FORCE: half shell (own cell with j > i plus 13 forward cells).
 // Dynamic shared memory: staged j atoms (40 B each) when useSmem, else the j
 // arrays are read from global memory (cells too full to stage).
-template <int VDW, bool FORCE, int NWARPS>
+template <int VDW, int MODE, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
     k_pair_box(BoxParams p, CellGrid g, int slices, int cell0, int useSmem,
                int smemAtoms,
@@ -335,10 +358,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
                const int *__restrict__ sortedAtoms, double *__restrict__ partLJ,
                double *__restrict__ partReal, double *__restrict__ fx,
                double *__restrict__ fy, double *__restrict__ fz) {
+  constexpr bool FORCE = MODE == MODE_FORCE;
+  constexpr bool VIRIAL = MODE == MODE_VIRIAL;
   extern __shared__ __align__(16) unsigned char dynSmem[];
   __shared__ JRange ranges[27];
   __shared__ JRange stagedRanges[27];
   __shared__ double enLJ[kMaxIPerPass], enReal[kMaxIPerPass];
+  __shared__ double enVir[VIRIAL ? 4 : 1][VIRIAL ? kMaxIPerPass : 1];
   __shared__ int nextI;
   // dynamic smem: per-warp hit queues, then the staged neighbour atoms
   WarpQueue *queues = reinterpret_cast<WarpQueue *>(dynSmem);
@@ -402,6 +428,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
   // energies go to shared memory and are summed in atom order, so the result does
   // not depend on which warp took which atom.
   double blockLJ = 0.0, blockReal = 0.0;
+  double blockVir[4] = {0.0, 0.0, 0.0, 0.0};
   for (int pass0 = iBegin; pass0 < iEnd; pass0 += kMaxIPerPass) {
     const int passEnd = min(iEnd, pass0 + kMaxIPerPass);
     if (threadIdx.x == 0) nextI = pass0;
@@ -411,20 +438,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
       if (lane == 0) i = atomicAdd(&nextI, 1);
       i = __shfl_sync(0xffffffffu, i, 0);
       if (i >= passEnd) break;
-      PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
+      PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0, 0.0, 0.0, 0.0, 0.0};
       double xi = sx[i], yi = sy[i], zi = sz[i], qi = sq[i];
       int2 kmi = skm[i];
+      if (VIRIAL) {
+        acc.cix = p.comx[kmi.y];
+        acc.ciy = p.comy[kmi.y];
+        acc.ciz = p.comz[kmi.y];
+      }
       if (staged) {
         if (anyGeneric)
-          warp_probe<VDW, FORCE, SW, true, true>(p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y,
+          warp_probe<VDW, MODE, SW, true, true>(p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y,
                                                  i + selfOffset, i, 1.0, false, useRanges,
                                                  nRanges, 1, 0, ja, qBase, acc);
         else
-          warp_probe<VDW, FORCE, SW, true, false>(p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y,
+          warp_probe<VDW, MODE, SW, true, false>(p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y,
                                                   i + selfOffset, i, 1.0, false, useRanges,
                                                   nRanges, 1, 0, ja, qBase, acc);
       } else {
-        warp_probe<VDW, FORCE, SW, false, true>(p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y,
+        warp_probe<VDW, MODE, SW, false, true>(p, g.generic, xi, yi, zi, kmi.x, qi, kmi.y,
                                                 i + selfOffset, i, 1.0, false, useRanges,
                                                 nRanges, 1, 0, ja, qBase, acc);
       }
@@ -442,6 +474,16 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
         enLJ[i - pass0] = e0;
         enReal[i - pass0] = e1;
       }
+      if (VIRIAL) {
+        double v2 = warp_sum(acc.fx), v3 = warp_sum(acc.fy), v4 = warp_sum(acc.fz),
+               v5 = warp_sum(acc.ex);
+        if (lane == 0) {
+          enVir[0][i - pass0] = v2;
+          enVir[1][i - pass0] = v3;
+          enVir[2][i - pass0] = v4;
+          enVir[3][i - pass0] = v5;
+        }
+      }
     }
     __syncthreads();
     // fixed-order sum of the per-atom energies of this pass (warp 0, tree of 32)
@@ -455,12 +497,21 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
       b = warp_sum(b);
       blockLJ += a;
       blockReal += b;
+      if (VIRIAL) {
+        for (int v = 0; v < 4; ++v) {
+          double c = 0.0;
+          for (int t = lane; t < passEnd - pass0; t += 32) c += enVir[v][t];
+          blockVir[v] += warp_sum(c);
+        }
+      }
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     partLJ[blockIdx.x] = blockLJ;
     partReal[blockIdx.x] = blockReal;
+    if (VIRIAL)  // partLJ holds 6 stripes of gridDim.x partials in this mode
+      for (int v = 0; v < 4; ++v) partLJ[(size_t)(v + 2) * gridDim.x + blockIdx.x] = blockVir[v];
   }
 }
 
@@ -561,7 +612,7 @@ __global__ void __launch_bounds__(kPairThreads)
   const int nRangesSh =
       build_ranges(g, p, position_to_cell(g, pr.x, pr.y, pr.z), false, cellStart, ranges);
   __syncthreads();
-  PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
+  PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0, 0.0, 0.0, 0.0, 0.0};
   JArrays ja = {sx, sy, sz, sq, skm, 0u, 0u, 0u, 0u, 0u};
   warp_probe<VDW, false, SWEEP_PROBE, false, true>(
       p, g.generic, pr.x, pr.y, pr.z, pr.kind, pr.q, excludeMol, -1, -1, pr.sign,

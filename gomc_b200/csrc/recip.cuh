@@ -181,6 +181,61 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------
+// Ewald::VirialReciprocal, src/Ewald.cpp:1168-1305.
+// k part (:1229-1244): part[c * gridDim.x + block], c = 0..2.
+__global__ void __launch_bounds__(256)
+    k_virial_recip_k(int nk, double constVal, const double *__restrict__ kx,
+                     const double *__restrict__ ky, const double *__restrict__ kz,
+                     const double *__restrict__ hsqr, const double *__restrict__ prefact,
+                     const double *__restrict__ sumR, const double *__restrict__ sumI,
+                     double *__restrict__ part) {
+  __shared__ double scratch[32];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  double w[3] = {0.0, 0.0, 0.0};
+  if (k < nk) {
+    const double factor = prefact[k] * (sumR[k] * sumR[k] + sumI[k] * sumI[k]);
+    const double c = 2.0 * (constVal + 1.0 / hsqr[k]);
+    w[0] = factor * (1.0 - c * kx[k] * kx[k]);
+    w[1] = factor * (1.0 - c * ky[k] * ky[k]);
+    w[2] = factor * (1.0 - c * kz[k] * kz[k]);
+  }
+  for (int c = 0; c < 3; ++c) {
+    double s = block_sum(w[c], scratch);
+    if (threadIdx.x == 0) part[(size_t)c * gridDim.x + blockIdx.x] = s;
+  }
+}
+// Intramolecular part (:1247-1285).  Its per-atom k sum is minus the k-space
+// reciprocal force on the atom (same factor as :1575-1586 with the sign flipped), so
+// it is contracted from the force kernel's output: w_c -= F_c * (unwrap(r) - com)_c.
+__global__ void __launch_bounds__(256)
+    k_virial_recip_intra(BoxParams p, int nBoxAtoms, const int *__restrict__ atomList,
+                         const int *__restrict__ mol, const double *__restrict__ x,
+                         const double *__restrict__ y, const double *__restrict__ z,
+                         const double *__restrict__ q, const double *__restrict__ fkx,
+                         const double *__restrict__ fky, const double *__restrict__ fkz,
+                         double *__restrict__ part) {
+  __shared__ double scratch[32];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double w[3] = {0.0, 0.0, 0.0};
+  if (t < nBoxAtoms) {
+    const int a = atomList[t];
+    if (!(fabs(q[a]) < 0.000000001)) {
+      const int m = mol[a];
+      const double cx = p.comx[m], cy = p.comy[m], cz = p.comz[m];
+      double ux = x[a], uy = y[a], uz = z[a];
+      unwrap_vec(p, ux, uy, uz, cx, cy, cz);
+      w[0] = -fkx[a] * (ux - cx);
+      w[1] = -fky[a] * (uy - cy);
+      w[2] = -fkz[a] * (uz - cz);
+    }
+  }
+  for (int c = 0; c < 3; ++c) {
+    double s = block_sum(w[c], scratch);
+    if (threadIdx.x == 0) part[(size_t)c * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Weighted point charges: new = base + scale * sum_p w_p (cos, sin)(k.r_p).
 // Ewald::MolExchangeReciprocal (src/Ewald.cpp:714-826; base = ref on the first
 // call, the new sums afterwards) and Ewald::ChangeLambdaRecip (:534-585).
@@ -282,7 +337,7 @@ __global__ void __launch_bounds__(128)
                          const double *__restrict__ prefact,
                          const double *__restrict__ sumR,
                          const double *__restrict__ sumI, double *rfx,
-                         double *rfy, double *rfz) {
+                         double *rfy, double *rfz, int withIntra = 1) {
   __shared__ double tk[5][kForceTile];
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int a = t < nBoxAtoms ? atomList[t] : -1;
@@ -295,7 +350,7 @@ __global__ void __launch_bounds__(128)
     za = z[a];
     qa = q[a];
     charged = !(fabs(qa) < 0.000000001);
-    if (charged) {  // intramolecular correction force, :1556-1569
+    if (charged && withIntra) {  // intramolecular correction force, :1556-1569
       int m = mol[a];
       double constValue = p.alpha * kTwoOverSqrtPi;
       for (int j = molStart[m]; j < molStart[m + 1]; ++j) {

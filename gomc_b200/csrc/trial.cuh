@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kPairThreads)
     const int nRangesSh =
         build_ranges(g, p, position_to_cell(g, px, py, pz), false, cellStart, ranges);
     __syncthreads();
-    PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
+    PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0, 0.0, 0.0, 0.0, 0.0};
     JArrays ja = {sx, sy, sz, sq, skm, 0u, 0u, 0u, 0u, 0u};
     warp_probe<VDW, false, SWEEP_PROBE, false, true>(
         p, g.generic, px, py, pz, a.kind[at], a.q[at], a.excludeMol, -1, -1,

@@ -45,6 +45,8 @@ _SIGS = {
     "gomcb200_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gomcb200_molecule_inter": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip]),
     "gomcb200_molecule_trial": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _dp]),
+    "gomcb200_box_inter_virial": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "gomcb200_virial_reciprocal": (C.c_int, [_vp, C.c_int, _dp]),
     "gomcb200_mol_exchange_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp,
                                                    C.c_int, C.c_double, _dp]),
     "gomcb200_change_lambda_mol_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp,
@@ -230,6 +232,17 @@ class Engine:
         self._ck(self.L.gomcb200_molecule_trial(self.h, box, mol_index, px, py, pz, C.byref(lj),
                                                 C.byref(re), C.byref(ov), C.byref(er)))
         return lj.value, re.value, bool(ov.value), er.value
+
+    def box_inter_virial(self, box=0):
+        vT, rT = np.zeros(3), np.zeros(3)
+        self._ck(self.L.gomcb200_box_inter_virial(self.h, box, vT.ctypes.data_as(_dp),
+                                                  rT.ctypes.data_as(_dp)))
+        return vT, rT
+
+    def virial_reciprocal(self, box=0):
+        wT = np.zeros(3)
+        self._ck(self.L.gomcb200_virial_reciprocal(self.h, box, wT.ctypes.data_as(_dp)))
+        return wT
 
     def mol_exchange_reciprocal(self, box, w, x, y, z, first_call=True, scale=1.0):
         (w, pw), (x, px), (y, py), (z, pz) = _d(w), _d(x), _d(y), _d(z)

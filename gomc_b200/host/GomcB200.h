@@ -34,6 +34,11 @@ struct Energy {            // the members of src/EnergyTypes.h:75-129 this path 
          tailCorrection = 0.0;
 };
 
+struct Virial {            // src/EnergyTypes.h:176-327 (members this path fills)
+  double inter = 0.0, real = 0.0, recip = 0.0, tailCorrection = 0.0;
+  double interTens[3][3] = {}, realTens[3][3] = {}, recipTens[3][3] = {};
+};
+
 inline void check(int rc, const char *what) {
   if (rc != GOMCB200_OK) {
     fprintf(stderr, "GPUassert: %s failed (%d): %s\n", what, rc, gomcb200_last_error());
@@ -133,6 +138,23 @@ public:
                                   &en.inter, aFx, aFy, aFz, mFx, mFy, mFz),
           "CallBoxForceGPU");
     return en;
+  }
+  // src/CalculateEnergy.cpp:411-579: pair tensors (CallBoxInterForceGPU) plus the
+  // reciprocal part through calcEwald (CallVirialReciprocalGPU); resident coordinates
+  // and COMs.  Like the reference only the tensor diagonals are computed; the tail
+  // correction (VirialCorrection) is left to the caller's host formula.
+  template <class EwaldT>
+  Virial VirialCalc(EwaldT &calcEwald, int box) {
+    Virial v;
+    double vT[3], rT[3];
+    check(gomcb200_box_inter_virial(eng_.get(), box, vT, rT), "CallBoxInterForceGPU");
+    for (int c = 0; c < 3; ++c) {
+      v.interTens[c][c] = vT[c];
+      v.realTens[c][c] = rT[c];
+    }
+    v.inter = vT[0] + vT[1] + vT[2];
+    v.real = rT[0] + rT[1] + rT[2];
+    return calcEwald.VirialReciprocal(v, box);
   }
   // src/CalculateEnergy.cpp:581-686; returns the overlap flag
   bool MoleculeInter(Intermolecular &inter_LJ, Intermolecular &inter_coulomb,
@@ -313,6 +335,14 @@ public:
     for (size_t s = 0; s < lambda_Coul.size(); ++s) energyDiffRecip[s] -= sysPotRecip_[box];
     dUdL_CoulRecip += energyDiffRecip[lambda_Coul.size() - 1] - energyDiffRecip[0];
   }
+  virtual Virial VirialReciprocal(const Virial &virial, int box) const {  // :1168-1305
+    Virial v = virial;
+    double wT[3];
+    check(gomcb200_virial_reciprocal(eng_.get(), box, wT), "CallVirialReciprocalGPU");
+    for (int c = 0; c < 3; ++c) v.recipTens[c][c] = wT[c];
+    v.recip = wT[0] + wT[1] + wT[2];
+    return v;
+  }
   virtual void BoxSelfAndCorrection(int box, double &self, double &correction) const {
     check(gomcb200_box_self_correction(eng_.get(), box, &self, &correction), "BoxSelf");
   }
@@ -384,6 +414,7 @@ public:
   void ChangeRecip(double *d, double &, const std::vector<double> &l, int, int,
                    int) const override { for (size_t s = 0; s < l.size(); ++s) d[s] = 0.0; }
   double SwapSelf(int, int) const override { return 0.0; }
+  Virial VirialReciprocal(const Virial &virial, int) const override { return virial; }
   void BoxSelfAndCorrection(int, double &self, double &correction) const override {
     self = correction = 0.0;
   }

@@ -232,6 +232,17 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box);
  * (MolExchangeReciprocal src/Ewald.cpp:794-806, ChangeRecip :626-630). */
 int gomcb200_get_recip_sums(gomcb200_engine *e, int box, int which,
                             double *sumR, double *sumI, int n);
+/* CallBoxInterForceGPU (CalculateForceCUDAKernel.cuh:17-34) == the pair part of
+ * CalculateEnergy::VirialCalc, src/CalculateEnergy.cpp:411-567: diagonal of the LJ
+ * virial tensor vT and of the real-space Coulomb tensor rT (qqFact included); the
+ * reference computes only the diagonal.  Uses the resident coordinates and COMs.
+ * The tail correction (VirialCorrection, :1317-1336) stays a host formula. */
+int gomcb200_box_inter_virial(gomcb200_engine *e, int box, double vT[3],
+                              double rT[3]);
+/* CallVirialReciprocalGPU (CalculateForceCUDAKernel.cuh:45-50) ==
+ * Ewald::VirialReciprocal, src/Ewald.cpp:1168-1305: diagonal wT from the
+ * reference sums and Ref k-vectors. */
+int gomcb200_virial_reciprocal(gomcb200_engine *e, int box, double wT[3]);
 /* Ewald::MolExchangeReciprocal (src/Ewald.cpp:714-826; the reference's
  * CallMolExchangeReciprocalGPU, CalculateEwaldCUDAKernel.cuh:45-48, only uploads
  * host results -- here the sums are computed on the device).  n weighted point

@@ -113,6 +113,24 @@ def test_reciprocal(gold):
     assert abs(co - d["box0.SwapCorrection.old"][0]) <= TOL * abs(co)
 
 
+def test_virial(gold):
+    d, e = gold
+    if "box0.Virial.interTens" not in d:
+        pytest.skip("fixture predates the virial dump")
+    vT, rT = e.box_inter_virial(0)
+    assert rel_err(vT, d["box0.Virial.interTens"]) <= TOL
+    if d["ff.electrostatic"][0]:
+        assert rel_err(rT, d["box0.Virial.realTens"]) <= TOL
+    if d["ff.ewald"][0]:
+        e.box_reciprocal_sums(0)
+        e.set_recip_ref(0)
+        for algo in (0, 2):
+            e.set_recip_algo(algo)
+            wT = e.virial_reciprocal(0)
+            assert rel_err(wT, d["box0.Virial.recipTens"]) <= TOL
+        e.set_recip_algo(2)
+
+
 def test_exchange_and_lambda_reciprocal(gold):
     """MolExchangeReciprocal (two chained calls), ChangeLambdaRecip, ChangeRecip."""
     from tests.test_oracle_golden import exchange_weights
