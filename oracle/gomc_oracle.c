@@ -10,6 +10,7 @@
 #include "gomc_oracle.h"
 
 #include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -691,6 +692,223 @@ int orc_virial_reciprocal(const orc_params *p, int nBoxMols, const int *boxMols,
   wT[1] = wT22;
   wT[2] = wT33;
   return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* MultiParticle move: counter-based RNG, trial transform, acceptance weight  */
+
+/* Philox4x64-10 (Salmon, Moraes, Dror, Shaw, SC'11), as instantiated by
+ * lib/Random123/philox.h:229-251,275 (multipliers, Weyl key increments, 10 rounds). */
+static inline void philox_mulhilo(uint64_t a, uint64_t b, uint64_t *hi, uint64_t *lo) {
+  unsigned __int128 pr = (unsigned __int128)a * b;
+  *hi = (uint64_t)(pr >> 64);
+  *lo = (uint64_t)pr;
+}
+void orc_philox4x64_10(const uint64_t ctrIn[4], const uint64_t keyIn[2], uint64_t out[4]) {
+  uint64_t c[4] = {ctrIn[0], ctrIn[1], ctrIn[2], ctrIn[3]};
+  uint64_t k[2] = {keyIn[0], keyIn[1]};
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) { /* bumpkey */
+      k[0] += 0x9E3779B97F4A7C15ULL;
+      k[1] += 0xBB67AE8584CAA73BULL;
+    }
+    uint64_t hi0, lo0, hi1, lo1;
+    philox_mulhilo(0xD2E7470EE14C6C93ULL, c[0], &hi0, &lo0);
+    philox_mulhilo(0xCA5A826395121157ULL, c[2], &hi1, &lo1);
+    uint64_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+/* r123::u01<double>(uint64) and r123::uneg11<double>(uint64),
+ * lib/Random123/uniform.hpp:175-184, :206-215 */
+static inline double r123_u01(uint64_t in) {
+  const double factor = 1.0 / (18446744073709551615.0 + 1.0);
+  return (double)in * factor + 0.5 * factor;
+}
+static inline double r123_uneg11(uint64_t in) {
+  const double factor = 1.0 / (9223372036854775807.0 + 1.0);
+  return (double)(int64_t)in * factor + 0.5 * factor;
+}
+/* Random123Wrapper::getRNG, src/Random123Wrapper.cpp:16-22 */
+static inline void mp_rng(uint64_t counter, uint64_t keyValue, uint64_t step,
+                          uint64_t seed, uint64_t r[4]) {
+  uint64_t c[4] = {counter, keyValue, 0, 0}, k[2] = {step, seed};
+  orc_philox4x64_10(c, k, r);
+}
+
+/* BoxDimensions::WrapPBC (scalar), src/BoxDimensions.cpp:261-295, and the
+ * non-orthogonal override, src/BoxDimensionsNonOrth.cpp:268-281 */
+static inline double wrap_scalar(double v, double ax) {
+  if (v >= ax)
+    v -= ax;
+  else if (v < 0)
+    v += ax;
+  return v;
+}
+static inline void wrap_vec(const orc_params *p, double v[3]) {
+  if (p->nonOrth) {
+    double u[3];
+    vec_mat(v, p->cellBasisInv, u);
+    for (int d = 0; d < 3; ++d) u[d] = wrap_scalar(u[d], p->axis[d]);
+    vec_mat(u, p->cellBasis, v);
+  } else {
+    for (int d = 0; d < 3; ++d) v[d] = wrap_scalar(v[d], p->axis[d]);
+  }
+}
+
+/* TransformMatrix::FromAxisAngle(theta, CrossProduct(axis), TensorProduct(axis)),
+ * src/TransformMatrix.h:165-214 */
+static void axis_angle(double theta, const double ax[3], double m[3][3]) {
+  double cross[3][3] = {{0.0, -(ax[2]), ax[1]}, {ax[2], 0.0, -(ax[0])}, {-(ax[1]), ax[0], 0.0}};
+  double tens[3][3];
+  for (int i = 0; i < 3; ++i) {
+    tens[0][i] = ax[0];
+    tens[1][i] = ax[1];
+    tens[2][i] = ax[2];
+  }
+  for (int i = 0; i < 3; ++i) {
+    tens[i][0] *= ax[0];
+    tens[i][1] *= ax[1];
+    tens[i][2] *= ax[2];
+  }
+  double c = cos(theta), s = sin(theta);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      m[i][j] = (i == j) ? c : 0.0;
+      m[i][j] += s * cross[i][j] + (1 - c) * tens[i][j];
+    }
+}
+
+/* rotate the atoms of molecule [s,e) about its COM: MultiParticle::RotateForceBiased
+ * / RotateRandom, src/moves/MultiParticle.h:615-643, :667-692 */
+static void mp_rotate_mol(const orc_params *p, int s, int e, const double m[3][3],
+                          const double com[3], double *nx, double *ny, double *nz) {
+  for (int a = s; a < e; ++a) {
+    double t[3] = {nx[a], ny[a], nz[a]};
+    unwrap_vec(p, t, com);
+    t[0] += -com[0];
+    t[1] += -com[1];
+    t[2] += -com[2];
+    double r[3] = {m[0][0] * t[0] + m[0][1] * t[1] + m[0][2] * t[2],
+                   m[1][0] * t[0] + m[1][1] * t[1] + m[1][2] * t[2],
+                   m[2][0] * t[0] + m[2][1] * t[1] + m[2][2] * t[2]};
+    r[0] += com[0];
+    r[1] += com[1];
+    r[2] += com[2];
+    wrap_vec(p, r);
+    nx[a] = r[0];
+    ny[a] = r[1];
+    nz[a] = r[2];
+  }
+}
+static void mp_translate_mol(const orc_params *p, int s, int e, const double sh[3], int m,
+                             double *nx, double *ny, double *nz, double *ncx, double *ncy,
+                             double *ncz) { /* :645-665, :694-715 */
+  for (int a = s; a < e; ++a) {
+    double t[3] = {nx[a] + sh[0], ny[a] + sh[1], nz[a] + sh[2]};
+    wrap_vec(p, t);
+    nx[a] = t[0];
+    ny[a] = t[1];
+    nz[a] = t[2];
+  }
+  double c[3] = {ncx[m] + sh[0], ncy[m] + sh[1], ncz[m] + sh[2]};
+  wrap_vec(p, c);
+  ncx[m] = c[0];
+  ncy[m] = c[1];
+  ncz[m] = c[2];
+}
+
+int orc_mp_transform(const orc_params *p, int moveType, int nBoxMols, const int *boxMols,
+                     const int *molStart, const double *fx, const double *fy,
+                     const double *fz, const double *rfx, const double *rfy,
+                     const double *rfz, double max, double lambda, double beta,
+                     uint64_t step, uint64_t seed, uint64_t keyValue, double *kX,
+                     double *kY, double *kZ, int *inForceRange, double *nx, double *ny,
+                     double *nz, double *ncx, double *ncy, double *ncz) {
+  for (int mi = 0; mi < nBoxMols; ++mi) { /* CalculateTrialDistRot, :566-613 */
+    int m = boxMols[mi];
+    double f[3] = {fx[m], fy[m], fz[m]};
+    if (rfx) { /* displace: molForceRef + molForceRecRef */
+      f[0] += rfx[m];
+      f[1] += rfy[m];
+      f[2] += rfz[m];
+    }
+    double lb[3] = {f[0] * lambda * beta, f[1] * lambda * beta, f[2] * lambda * beta};
+    /* CalcRandomTransform, :545-564 */
+    double lbmax[3] = {lb[0] * max, lb[1] * max, lb[2] * max};
+    double val[3] = {0.0, 0.0, 0.0};
+    int inRange = fabs(lbmax[0]) > 1E-12 && fabs(lbmax[0]) < 30 && fabs(lbmax[1]) > 1E-12 &&
+                  fabs(lbmax[1]) < 30 && fabs(lbmax[2]) > 1E-12 && fabs(lbmax[2]) < 30;
+    uint64_t r[4];
+    mp_rng((uint64_t)m, keyValue, step, seed, r);
+    if (inRange) {
+      for (int d = 0; d < 3; ++d)
+        val[d] = log(exp(-1.0 * lbmax[d]) + 2.0 * r123_u01(r[d]) * sinh(lbmax[d])) / lb[d];
+    }
+    kX[m] = val[0];
+    kY[m] = val[1];
+    kZ[m] = val[2];
+    inForceRange[m] = inRange;
+    double com[3] = {ncx[m], ncy[m], ncz[m]};
+    if (moveType == 1) { /* mp::MPROTATE */
+      double mat[3][3];
+      if (inRange) {
+        double rotLen = sqrt(val[0] * val[0] + val[1] * val[1] + val[2] * val[2]);
+        double inv = 1.0 / rotLen;
+        double axis[3] = {val[0] * inv, val[1] * inv, val[2] * inv};
+        axis_angle(rotLen, axis, mat);
+      } else {
+        double symRand = max * r123_uneg11(r[0]);
+        double u = r123_uneg11(r[1]);
+        double theta = 2.0 * M_PI * r123_u01(r[2]);
+        double rootTerm = sqrt(1.0 - u * u);
+        double axis[3] = {rootTerm * cos(theta), rootTerm * sin(theta), u};
+        axis_angle(symRand, axis, mat);
+      }
+      mp_rotate_mol(p, molStart[m], molStart[m + 1], mat, com, nx, ny, nz);
+    } else {
+      double sh[3] = {val[0], val[1], val[2]};
+      if (!inRange)
+        for (int d = 0; d < 3; ++d) sh[d] = max * r123_uneg11(r[d]);
+      mp_translate_mol(p, molStart[m], molStart[m + 1], sh, m, nx, ny, nz, ncx, ncy, ncz);
+    }
+  }
+  return 0;
+}
+
+/* MultiParticle::CalculateWRatio / GetCoeff, src/moves/MultiParticle.h:443-513
+ * (one OpenMP product reduction: private copy starts at 1, then multiplies w_ratio) */
+double orc_mp_coeff(int nBoxMols, const int *boxMols, const int *inForceRange,
+                    const double *ofx, const double *ofy, const double *ofz,
+                    const double *orx, const double *ory, const double *orz,
+                    const double *nfx, const double *nfy, const double *nfz,
+                    const double *nrx, const double *nry, const double *nrz,
+                    const double *kX, const double *kY, const double *kZ, double max,
+                    double lambda, double beta) {
+  double lBeta = lambda * beta;
+  double priv = 1.0;
+  for (int mi = 0; mi < nBoxMols; ++mi) {
+    int m = boxMols[mi];
+    if (!inForceRange[m]) continue;
+    double o[3] = {ofx[m], ofy[m], ofz[m]}, n[3] = {nfx[m], nfy[m], nfz[m]};
+    if (orx) {
+      o[0] += orx[m]; o[1] += ory[m]; o[2] += orz[m];
+      n[0] += nrx[m]; n[1] += nry[m]; n[2] += nrz[m];
+    }
+    double k[3] = {kX[m], kY[m], kZ[m]};
+    double w = 1.0;
+    for (int d = 0; d < 3; ++d) {
+      double lbn = n[d] * lBeta, lbo = o[d] * lBeta;
+      w *= lbn * exp(-lbn * k[d]) / (2.0 * sinh(lbn * max));
+      w /= lbo * exp(lbo * k[d]) / (2.0 * sinh(lbo * max));
+    }
+    priv *= w;
+  }
+  double w_ratio = 1.0;
+  w_ratio *= priv;
+  if (!isfinite(w_ratio)) w_ratio = 0.0;
+  return w_ratio;
 }
 
 /* ------------------------------------------------------------------------ */

@@ -21,6 +21,7 @@
 #ifndef GOMC_ORACLE_H
 #define GOMC_ORACLE_H
 
+#include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -203,6 +204,30 @@ int orc_box_force_reciprocal(const orc_params *p, int nBoxMols,
                              const double *sumI, double *rFx, double *rFy,
                              double *rFz, double *mFx, double *mFy,
                              double *mFz);
+
+/* Philox4x64-10 as instantiated by lib/Random123/philox.h (the generator behind
+ * Random123Wrapper, src/Random123Wrapper.cpp:16-22). */
+void orc_philox4x64_10(const uint64_t ctr[4], const uint64_t key[2], uint64_t out[4]);
+/* MultiParticle::CalculateTrialDistRot (src/moves/MultiParticle.h:566-715):
+ * moveType 0 displace (f = molForceRef, rf = molForceRecRef), 1 rotate
+ * (f = molTorqueRef, rf = NULL).  nx/ny/nz and ncx/ncy/ncz hold the current
+ * coordinates / COMs on entry and the trial ones on return; k = t_k or r_k. */
+int orc_mp_transform(const orc_params *p, int moveType, int nBoxMols, const int *boxMols,
+                     const int *molStart, const double *fx, const double *fy,
+                     const double *fz, const double *rfx, const double *rfy,
+                     const double *rfz, double max, double lambda, double beta,
+                     uint64_t step, uint64_t seed, uint64_t keyValue, double *kX,
+                     double *kY, double *kZ, int *inForceRange, double *nx, double *ny,
+                     double *nz, double *ncx, double *ncy, double *ncz);
+/* MultiParticle::GetCoeff, src/moves/MultiParticle.h:460-513 (o* old, n* new
+ * forces or torques; *r* the reciprocal parts, NULL for rotation). */
+double orc_mp_coeff(int nBoxMols, const int *boxMols, const int *inForceRange,
+                    const double *ofx, const double *ofy, const double *ofz,
+                    const double *orx, const double *ory, const double *orz,
+                    const double *nfx, const double *nfy, const double *nfz,
+                    const double *nrx, const double *nry, const double *nrz,
+                    const double *kX, const double *kY, const double *kZ, double max,
+                    double lambda, double beta);
 
 /* CalculateEnergy::VirialCalc, pair part (src/CalculateEnergy.cpp:411-567):
  * diagonal of the LJ tensor vT and of the real-space Coulomb tensor rT (already

@@ -48,6 +48,7 @@
 #include "FFExp6.h"
 #include "BoxDimensionsNonOrth.h"
 #include "TrialMol.h"
+#include "MultiParticle.h"
 #undef private
 #undef protected
 
@@ -421,6 +422,64 @@ int run_golden(int argc, char **argv) {
       out.f64(bname("ParticleInter.en", b), en);
       out.f64(bname("ParticleInter.real", b), re);
       out.i32(bname("ParticleInter.overlap", b), ovi);
+    }
+
+    // ---- MultiParticle move: trial transform, CalcEn, acceptance weight ----
+    // Drives the move object's own methods (private members opened above) the way
+    // MultiParticle::Prep / Transform / CalcEn / Accept do, with a fixed box and
+    // move type instead of the PRNG draws.
+    if (b == 0 && sys.moves[mv::MULTIPARTICLE] != NULL) {
+      MultiParticle *mp = static_cast<MultiParticle *>(sys.moves[mv::MULTIPARTICLE]);
+      const int nTypes = mp->allTranslate ? 1 : 2;
+      for (int type = 0; type < nTypes; ++type) {
+        const char *tn = type == mp::MPROTATE ? "mpRotate" : "mpDisplace";
+        std::string pre = std::string(tn) + ".";
+        ulong step = 4242 + 17 * type;
+        sys.r123wrapper.SetStep(step);
+        mp->bPick = b;
+        mp->moveType = type;
+        mp->SetMolInBox(b);
+        std::fill(mp->inForceRange.begin(), mp->inForceRange.end(), false);
+        // reference forces / torques of the current positions (Prep, :219-236)
+        if (ff.ewald) {
+          ew.CopyRecip(b);
+          ew.BoxForceReciprocal(sys.coordinates, sys.atomForceRecRef,
+                                sys.molForceRecRef, b);
+        }
+        ce.BoxForce(sys.potential, sys.coordinates, sys.atomForceRef,
+                    sys.molForceRef, sys.boxDimRef, b);
+        ce.CalculateTorque(mp->moleculeIndex, sys.coordinates, sys.com,
+                           sys.atomForceRef, sys.atomForceRecRef,
+                           mp->molTorqueRef, b);
+        sys.coordinates.CopyRange(mp->newMolsPos, 0, 0, sys.coordinates.Count());
+        sys.com.CopyRange(mp->newCOMs, 0, 0, sys.com.Count());
+        mp->CalculateTrialDistRot();
+        double par[6] = {mp->moveSetRef.GetTMAX(b), mp->moveSetRef.GetRMAX(b),
+                         mp->lambda * mp->BETA, (double)step,
+                         (double)sys.r123wrapper.GetSeedValue(),
+                         (double)sys.r123wrapper.GetKeyValue()};
+        out.f64(bname((pre + "params").c_str(), b), par, 6);
+        out.xyz(bname((pre + "molForceRef").c_str(), b), sys.molForceRef);
+        out.xyz(bname((pre + "molForceRecRef").c_str(), b), sys.molForceRecRef);
+        out.xyz(bname((pre + "molTorqueRef").c_str(), b), mp->molTorqueRef);
+        out.xyz(bname((pre + "k").c_str(), b), type == mp::MPROTATE ? mp->r_k : mp->t_k);
+        out.i32(bname((pre + "inForceRange").c_str(), b), mp->inForceRange);
+        out.xyz(bname((pre + "newMolsPos").c_str(), b), mp->newMolsPos);
+        out.xyz(bname((pre + "newCOMs").c_str(), b), mp->newCOMs);
+        mp->CalcEn();
+        double w = mp->GetCoeff();
+        out.f64(bname((pre + "wRatio").c_str(), b), w);
+        double en[3] = {mp->sysPotNew.boxEnergy[b].inter,
+                        mp->sysPotNew.boxEnergy[b].real,
+                        mp->sysPotNew.boxEnergy[b].recip};
+        out.f64(bname((pre + "newEnergy").c_str(), b), en, 3);
+        out.xyz(bname((pre + "molForceNew").c_str(), b), mp->molForceNew);
+        out.xyz(bname((pre + "molForceRecNew").c_str(), b), mp->molForceRecNew);
+        out.xyz(bname((pre + "molTorqueNew").c_str(), b), mp->molTorqueNew);
+        // reject: restore the cell list (Accept's else branch, :537-539)
+        sys.cellList.GridAll(sys.boxDimRef, sys.coordinates, sys.molLookupRef);
+        ew.exgMolCache();
+      }
     }
 
     // ---- MEMC / NeMTMC / free-energy reciprocal deltas (own RNG stream so
