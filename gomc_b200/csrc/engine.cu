@@ -21,6 +21,7 @@
 #include "pair.cuh"
 #include "recip.cuh"
 #include "trial.cuh"
+#include "mp.cuh"
 #include "recip_mma.cuh"
 #include "force_mma.cuh"
 
@@ -153,6 +154,12 @@ struct gomcb200_engine {
   DevBuf<double> x, y, z, q, comx, comy, comz;
   DevBuf<double> force[5][3];
   DevBuf<double> scratchF[3];  // k-space forces for VirialReciprocal
+  // MultiParticle move: the other coordinate / COM / force set (trial while the
+  // reference one is active and vice versa), t_k or r_k, in-range flags
+  DevBuf<double> xT, yT, zT, comxT, comyT, comzT, forceT[5][3], mpK[3];
+  DevBuf<int> mpInRange;
+  DevBuf<signed char> mpInvolved;
+  bool trialActive = false;
   std::vector<BoxState> box;
   int imageTotal = 0;
   int recipAlgo = 2;  // 0 direct, 1 factorised SIMT, 2 factorised DMMA
@@ -1418,6 +1425,7 @@ int gomcb200_init_topology(gomcb200_engine *e, int nAtoms, int nMols, const int 
       CK(cudaMemset(e->force[w][c].p, 0, e->force[w][c].cap * sizeof(double)));
     }
   }
+  e->trialActive = false;
   CK(cudaMemcpy(e->kind.p, particleKind, nAtoms * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->mol.p, particleMol, nAtoms * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->q.p, particleCharge, nAtoms * sizeof(double), cudaMemcpyHostToDevice));
@@ -1536,6 +1544,18 @@ int gomcb200_set_com(gomcb200_engine *e, const double *x, const double *y, const
   if (!e || !e->haveTopo) return fail(GOMCB200_EINVAL, "topology not initialised");
   CK(cudaSetDevice(e->device));
   return upload3(e, e->comx, e->comy, e->comz, x, y, z, first, count, e->nMols);
+}
+
+int gomcb200_get_com(gomcb200_engine *e, double *x, double *y, double *z, int first, int count) {
+  if (!e || !e->haveTopo || first < 0 || count < 0 || first + count > e->nMols)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  size_t bytes = sizeof(double) * (size_t)count;
+  if (x) CK(cudaMemcpy(x, e->comx.p + first, bytes, cudaMemcpyDeviceToHost));
+  if (y) CK(cudaMemcpy(y, e->comy.p + first, bytes, cudaMemcpyDeviceToHost));
+  if (z) CK(cudaMemcpy(z, e->comz.p + first, bytes, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int gomcb200_set_molecule_coords(gomcb200_engine *e, int molIndex, const double *x,
@@ -2196,6 +2216,158 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
       e->force[2][2].p, e->force[3][0].p, e->force[3][1].p, e->force[3][2].p);
   e->launches += 1;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- MultiParticle move -------------------------------------------------------
+static int mp_reserve(gomcb200_engine *e) {
+  const size_t na = (size_t)e->nAtoms + 1, nm = (size_t)e->nMols + 1;
+  CK(e->xT.reserve(na)); CK(e->yT.reserve(na)); CK(e->zT.reserve(na));
+  CK(e->comxT.reserve(nm)); CK(e->comyT.reserve(nm)); CK(e->comzT.reserve(nm));
+  for (int w = 0; w < 5; ++w) {
+    size_t n = (w == GOMCB200_ATOM_FORCE || w == GOMCB200_ATOM_FORCE_REC) ? na : nm;
+    for (int c = 0; c < 3; ++c)
+      if (e->forceT[w][c].cap < n) {
+        CK(e->forceT[w][c].reserve(n));
+        CK(cudaMemset(e->forceT[w][c].p, 0, e->forceT[w][c].cap * sizeof(double)));
+      }
+  }
+  for (int c = 0; c < 3; ++c) CK(e->mpK[c].reserve(nm));
+  CK(e->mpInRange.reserve(nm));
+  return 0;
+}
+
+int gomcb200_mp_transform(gomcb200_engine *e, int box, int moveType, double max,
+                          double lambdaBETA, unsigned long long step, unsigned int key,
+                          unsigned long long seed, const signed char *isMoleculeInvolved) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (moveType < 0 || moveType > 1) return fail(GOMCB200_EINVAL, "moveType must be 0 or 1");
+  if (e->trialActive)
+    return fail(GOMCB200_EINVAL, "trial coordinates are active: gomcb200_mp_select(e, 0) first");
+  CK(cudaSetDevice(e->device));
+  rc = mp_reserve(e);
+  if (rc) return rc;
+  BoxState &bx = e->box[box];
+  const size_t ba = sizeof(double) * (size_t)e->nAtoms, bm = sizeof(double) * (size_t)e->nMols;
+  // newMolsPos / newCOMs start as copies of the reference (MultiParticle::Prep, :238-239)
+  CK(cudaMemcpyAsync(e->xT.p, e->x.p, ba, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->yT.p, e->y.p, ba, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->zT.p, e->z.p, ba, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->comxT.p, e->comx.p, bm, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->comyT.p, e->comy.p, bm, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->comzT.p, e->comz.p, bm, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemsetAsync(e->mpInRange.p, 0, sizeof(int) * (size_t)e->nMols, e->stream));
+  for (int c = 0; c < 3; ++c) CK(cudaMemsetAsync(e->mpK[c].p, 0, bm, e->stream));
+  if (bx.nMols == 0) return 0;
+  MpArgs a;
+  a.moveType = moveType;
+  a.nMolsBox = bx.nMols;
+  a.max = max;
+  a.lambdaBeta = lambdaBETA;
+  a.step = step;
+  a.seed = seed;
+  a.key = key;
+  a.molList = bx.molList.p;
+  a.molStart = e->molStart.p;
+  a.involved = nullptr;
+  if (isMoleculeInvolved) {
+    CK(e->mpInvolved.reserve(e->nMols + 1));
+    CK(cudaMemcpyAsync(e->mpInvolved.p, isMoleculeInvolved, (size_t)e->nMols,
+                       cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));  // the caller's buffer may be pageable
+    a.involved = e->mpInvolved.p;
+  }
+  a.x = e->x.p; a.y = e->y.p; a.z = e->z.p;
+  a.cx = e->comx.p; a.cy = e->comy.p; a.cz = e->comz.p;
+  const int fw = moveType == 1 ? GOMCB200_MOL_TORQUE : GOMCB200_MOL_FORCE;
+  a.fx = e->force[fw][0].p; a.fy = e->force[fw][1].p; a.fz = e->force[fw][2].p;
+  a.rfx = a.rfy = a.rfz = nullptr;
+  if (moveType == 0) {
+    a.rfx = e->force[GOMCB200_MOL_FORCE_REC][0].p;
+    a.rfy = e->force[GOMCB200_MOL_FORCE_REC][1].p;
+    a.rfz = e->force[GOMCB200_MOL_FORCE_REC][2].p;
+  }
+  a.nx = e->xT.p; a.ny = e->yT.p; a.nz = e->zT.p;
+  a.ncx = e->comxT.p; a.ncy = e->comyT.p; a.ncz = e->comzT.p;
+  a.kx = e->mpK[0].p; a.ky = e->mpK[1].p; a.kz = e->mpK[2].p;
+  a.inForceRange = e->mpInRange.p;
+  k_mp_transform<<<(bx.nMols + 127) / 128, 128, 0, e->stream>>>(make_params(e, box), a);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int gomcb200_mp_get_trial(gomcb200_engine *e, double *kx, double *ky, double *kz,
+                          int *inForceRange) {
+  if (!e || !e->haveTopo || e->mpInRange.cap == 0)
+    return fail(GOMCB200_EINVAL, "gomcb200_mp_transform not called");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  const size_t bm = sizeof(double) * (size_t)e->nMols;
+  if (kx) CK(cudaMemcpy(kx, e->mpK[0].p, bm, cudaMemcpyDeviceToHost));
+  if (ky) CK(cudaMemcpy(ky, e->mpK[1].p, bm, cudaMemcpyDeviceToHost));
+  if (kz) CK(cudaMemcpy(kz, e->mpK[2].p, bm, cudaMemcpyDeviceToHost));
+  if (inForceRange)
+    CK(cudaMemcpy(inForceRange, e->mpInRange.p, sizeof(int) * (size_t)e->nMols,
+                  cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gomcb200_mp_select(gomcb200_engine *e, int trial) {
+  if (!e || !e->haveTopo) return fail(GOMCB200_EINVAL, "topology not initialised");
+  if ((trial != 0) == e->trialActive) return 0;
+  if (e->xT.cap == 0) return fail(GOMCB200_EINVAL, "gomcb200_mp_transform not called");
+  // O(1): the two sets trade places; every kernel reads the active one
+  std::swap(e->x, e->xT); std::swap(e->y, e->yT); std::swap(e->z, e->zT);
+  std::swap(e->comx, e->comxT); std::swap(e->comy, e->comyT); std::swap(e->comz, e->comzT);
+  for (int w = 0; w < 5; ++w)
+    for (int c = 0; c < 3; ++c) std::swap(e->force[w][c], e->forceT[w][c]);
+  e->trialActive = trial != 0;
+  e->mirrorValid = false;
+  mark_coords_dirty(e);
+  return 0;
+}
+
+int gomcb200_mp_accept(gomcb200_engine *e, int box) {
+  // MultiParticle::Accept, :522-534: the trial set (active) becomes the reference
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (!e->trialActive) return fail(GOMCB200_EINVAL, "no active trial coordinates");
+  e->trialActive = false;  // buffers stay swapped: what was the trial is now current
+  return gomcb200_update_recip(e, box);
+}
+
+int gomcb200_mp_coeff(gomcb200_engine *e, int box, int moveType, double max, double lambdaBETA,
+                      double *wRatio) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (!wRatio || moveType < 0 || moveType > 1) return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!e->trialActive)
+    return fail(GOMCB200_EINVAL, "needs the trial set active (new forces computed on it)");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  *wRatio = 1.0;
+  if (bx.nMols == 0) return 0;
+  const int nb = (bx.nMols + 255) / 256;
+  CK(e->blockA.reserve(nb + 1024));
+  const int fw = moveType == 1 ? GOMCB200_MOL_TORQUE : GOMCB200_MOL_FORCE;
+  const int rw = GOMCB200_MOL_FORCE_REC;
+  const bool rec = moveType == 0;
+  // while the trial set is active: force[] = new, forceT[] = reference
+  k_mp_coeff<<<nb, 256, 0, e->stream>>>(
+      bx.nMols, bx.molList.p, e->mpInRange.p, max, lambdaBETA, e->forceT[fw][0].p,
+      e->forceT[fw][1].p, e->forceT[fw][2].p, rec ? e->forceT[rw][0].p : nullptr,
+      rec ? e->forceT[rw][1].p : nullptr, rec ? e->forceT[rw][2].p : nullptr, e->force[fw][0].p,
+      e->force[fw][1].p, e->force[fw][2].p, rec ? e->force[rw][0].p : nullptr,
+      rec ? e->force[rw][1].p : nullptr, rec ? e->force[rw][2].p : nullptr, e->mpK[0].p,
+      e->mpK[1].p, e->mpK[2].p, e->blockA.p);
+  k_mp_coeff_final<<<1, 256, 0, e->stream>>>(nb, e->blockA.p, e->result.p);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  rc = fetch_result(e, 1);
+  if (rc) return rc;
+  *wRatio = e->hRes[0];
   return 0;
 }
 

@@ -40,11 +40,18 @@ _SIGS = {
     "gomcb200_set_coords": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
     "gomcb200_get_coords": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
     "gomcb200_set_com": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
+    "gomcb200_get_com": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
     "gomcb200_set_molecule_coords": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp]),
     "gomcb200_box_inter": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gomcb200_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gomcb200_molecule_inter": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip]),
     "gomcb200_molecule_trial": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _dp]),
+    "gomcb200_mp_transform": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double,
+                                        C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_void_p]),
+    "gomcb200_mp_get_trial": (C.c_int, [_vp, _dp, _dp, _dp, _ip]),
+    "gomcb200_mp_select": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_mp_coeff": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
+    "gomcb200_mp_accept": (C.c_int, [_vp, C.c_int]),
     "gomcb200_box_inter_virial": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gomcb200_virial_reciprocal": (C.c_int, [_vp, C.c_int, _dp]),
     "gomcb200_mol_exchange_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp,
@@ -197,6 +204,13 @@ class Engine:
                                             first, count))
         return out
 
+    def get_com(self, first=0, count=None):
+        count = self.n_mols - first if count is None else count
+        out = [np.zeros(count) for _ in range(3)]
+        self._ck(self.L.gomcb200_get_com(self.h, *[o.ctypes.data_as(_dp) for o in out],
+                                         first, count))
+        return out
+
     def set_com(self, x, y, z, first=0):
         (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
         self._ck(self.L.gomcb200_set_com(self.h, px, py, pz, first, len(x)))
@@ -232,6 +246,34 @@ class Engine:
         self._ck(self.L.gomcb200_molecule_trial(self.h, box, mol_index, px, py, pz, C.byref(lj),
                                                 C.byref(re), C.byref(ov), C.byref(er)))
         return lj.value, re.value, bool(ov.value), er.value
+
+    def mp_transform(self, box, move_type, vmax, lambda_beta, step, key, seed, involved=None):
+        ptr = None
+        if involved is not None:
+            involved = np.ascontiguousarray(involved, dtype=np.int8)
+            ptr = involved.ctypes.data_as(C.c_void_p)
+        self._ck(self.L.gomcb200_mp_transform(self.h, box, int(move_type), float(vmax),
+                                              float(lambda_beta), int(step), int(key),
+                                              int(seed), ptr))
+
+    def mp_get_trial(self, n_mols):
+        k = [np.zeros(n_mols) for _ in range(3)]
+        inr = np.zeros(n_mols, dtype=np.int32)
+        self._ck(self.L.gomcb200_mp_get_trial(self.h, *[a.ctypes.data_as(_dp) for a in k],
+                                              inr.ctypes.data_as(_ip)))
+        return k, inr
+
+    def mp_select(self, trial):
+        self._ck(self.L.gomcb200_mp_select(self.h, int(trial)))
+
+    def mp_coeff(self, box, move_type, vmax, lambda_beta):
+        w = C.c_double()
+        self._ck(self.L.gomcb200_mp_coeff(self.h, box, int(move_type), float(vmax),
+                                          float(lambda_beta), C.byref(w)))
+        return w.value
+
+    def mp_accept(self, box=0):
+        self._ck(self.L.gomcb200_mp_accept(self.h, box))
 
     def box_inter_virial(self, box=0):
         vT, rT = np.zeros(3), np.zeros(3)

@@ -426,4 +426,64 @@ public:
   void UpdateRecipVec(int) override {}
 };
 
+// MultiParticle (src/moves/MultiParticle.h): the device-resident move.  The move
+// loop above it (box pick, move-type draw, acceptance test, move-settings update) is
+// the caller's and unchanged; this class mirrors the methods that touch coordinates
+// and forces.  lambda = 0.5 as in the reference constructor (:95).
+class MultiParticle {
+public:
+  MultiParticle(EngineB200 &eng, CalculateEnergy &calcEn, Ewald &calcEwald, double BETA)
+      : eng_(eng), calcEn_(calcEn), calcEwald_(calcEwald), BETA_(BETA) {}
+  enum { MPDISPLACE = 0, MPROTATE = 1 };
+
+  // Prep (:164-247): reference forces / torques of the current positions
+  void Prep(int box, int moveType) {
+    bPick_ = box;
+    moveType_ = moveType;
+    calcEwald_.CopyRecip(box);
+    calcEwald_.BoxForceReciprocal(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, box);
+    check(gomcb200_box_force(eng_.get(), box, &refInter_, &refReal_), "BoxForce");
+    calcEn_.CalculateTorque(nullptr, nullptr, nullptr, 0, 0, box);
+  }
+  // Transform (:329-411) == CallTranslateParticlesGPU / CallRotateParticlesGPU
+  void Transform(double t_max, double r_max, unsigned long long step, unsigned int key,
+                 unsigned long long seed, const signed char *isMoleculeInvolved = nullptr) {
+    max_ = moveType_ == MPROTATE ? r_max : t_max;
+    check(gomcb200_mp_transform(eng_.get(), bPick_, moveType_, max_, lambda_ * BETA_, step, key,
+                                seed, isMoleculeInvolved),
+          moveType_ == MPROTATE ? "CallRotateParticlesGPU" : "CallTranslateParticlesGPU");
+  }
+  // CalcEn (:414-441): energies and forces of the trial positions
+  Energy CalcEn() {
+    check(gomcb200_mp_select(eng_.get(), 1), "mp_select");
+    Energy en;
+    check(gomcb200_box_reciprocal_sums(eng_.get(), bPick_, &en.recip), "BoxReciprocalSums");
+    check(gomcb200_box_force(eng_.get(), bPick_, &en.inter, &en.real), "BoxForce");
+    calcEwald_.BoxForceReciprocal(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0,
+                                  bPick_);
+    calcEn_.CalculateTorque(nullptr, nullptr, nullptr, 0, 0, bPick_);
+    return en;
+  }
+  // GetCoeff (:460-513)
+  double GetCoeff() const {
+    double w = 1.0;
+    check(gomcb200_mp_coeff(eng_.get(), bPick_, moveType_, max_, lambda_ * BETA_, &w), "GetCoeff");
+    return w;
+  }
+  // Accept (:515-541): result decided by the caller (pr < MPCoeff * uBoltz)
+  void Accept(bool result) {
+    if (result)
+      check(gomcb200_mp_accept(eng_.get(), bPick_), "mp_accept");
+    else
+      check(gomcb200_mp_select(eng_.get(), 0), "mp_select");
+  }
+
+private:
+  EngineB200 &eng_;
+  CalculateEnergy &calcEn_;
+  Ewald &calcEwald_;
+  double BETA_, lambda_ = 0.5, max_ = 0.0, refInter_ = 0.0, refReal_ = 0.0;
+  int bPick_ = 0, moveType_ = 0;
+};
+
 }  // namespace gomc_b200

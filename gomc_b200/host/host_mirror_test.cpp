@@ -104,8 +104,24 @@ int main(int argc, char **argv) {
   calcEwald->BoxReciprocalSums(0, coords);
   chk.recip = calcEwald->BoxReciprocal(0, false);
   printf("], \"running\": {\"inter\": %.17g, \"real\": %.17g, \"recip\": %.17g}, "
-         "\"recomputed\": {\"inter\": %.17g, \"real\": %.17g, \"recip\": %.17g}}\n",
+         "\"recomputed\": {\"inter\": %.17g, \"real\": %.17g, \"recip\": %.17g}",
          pot.inter, pot.real, pot.recip, chk.inter, chk.real, chk.recip);
+  // one MultiParticle displacement step (src/moves/MultiParticle.h: Prep, Transform,
+  // CalcEn, GetCoeff, Accept(false)) through the mirror class
+  {
+    calcEwald->SetRecipRef(0);
+    MultiParticle mp(eng, calcEnergy, *calcEwald, 1.0 / 300.0);
+    mp.Prep(0, MultiParticle::MPDISPLACE);
+    mp.Transform(0.02, 0.03, 77, 0, 123);
+    Energy en = mp.CalcEn();
+    double w = mp.GetCoeff();
+    mp.Accept(false);
+    Energy back = calcEnergy.BoxInter(coords, axis, 0);
+    printf(", \"mp\": {\"inter\": %.17g, \"real\": %.17g, \"recip\": %.17g, \"w\": %.17g, "
+           "\"inter_after_reject\": %.17g}",
+           en.inter, en.real, en.recip, w, back.inter);
+  }
+  printf("}\n");
   delete calcEwald;
   fclose(f);
   return 0;

@@ -137,6 +137,9 @@ int gomcb200_get_coords(gomcb200_engine *e, double *x, double *y, double *z,
                         int first, int count);
 int gomcb200_set_com(gomcb200_engine *e, const double *x, const double *y,
                      const double *z, int first, int count);
+/* Molecule centres of mass of the active coordinate set (device -> host). */
+int gomcb200_get_com(gomcb200_engine *e, double *x, double *y, double *z,
+                     int first, int count);
 /* Accepted single-molecule move: new coordinates + COM of one molecule
  * (what Translate::Accept copies, src/moves/Translate.h:106-113). */
 int gomcb200_set_molecule_coords(gomcb200_engine *e, int molIndex,
@@ -232,6 +235,34 @@ int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box);
  * (MolExchangeReciprocal src/Ewald.cpp:794-806, ChangeRecip :626-630). */
 int gomcb200_get_recip_sums(gomcb200_engine *e, int box, int which,
                             double *sumR, double *sumI, int n);
+/* ---- MultiParticle move (device-resident trial state) -------------------- */
+/* CallTranslateParticlesGPU (moveType 0) / CallRotateParticlesGPU (moveType 1),
+ * src/GPU/TransformParticlesCUDAKernel.cuh:20-37 == MultiParticle::
+ * CalculateTrialDistRot, src/moves/MultiParticle.h:566-715.  Reads the resident
+ * reference coordinates, COMs and molecule forces (+ reciprocal) or torques,
+ * draws Random123Wrapper's variates (Philox4x64-10, counter {molecule, key},
+ * key {step, seed}) and writes the trial coordinates / COMs, t_k or r_k and the
+ * inForceRange flags into the engine's second coordinate set.
+ * isMoleculeInvolved: nMols flags, or NULL for every molecule of the box. */
+int gomcb200_mp_transform(gomcb200_engine *e, int box, int moveType, double max,
+                          double lambdaBETA, unsigned long long step,
+                          unsigned int key, unsigned long long seed,
+                          const signed char *isMoleculeInvolved);
+/* t_k / r_k (nMols each) and inForceRange (nMols) of the last transform. */
+int gomcb200_mp_get_trial(gomcb200_engine *e, double *kx, double *ky, double *kz,
+                          int *inForceRange);
+/* trial = 1: the trial coordinates/COMs become the active set and the force
+ * buffers switch to the "New" set (MultiParticle::CalcEn works on newMolsPos,
+ * atomForceNew, ..., :414-441); trial = 0: back to the reference (reject).
+ * O(1) pointer exchange. */
+int gomcb200_mp_select(gomcb200_engine *e, int trial);
+/* MultiParticle::GetCoeff, :460-513, from the reference and new force sets. */
+int gomcb200_mp_coeff(gomcb200_engine *e, int box, int moveType, double max,
+                      double lambdaBETA, double *wRatio);
+/* MultiParticle::Accept, :522-534: the active trial set becomes the reference
+ * (coordinates, COMs, forces, torques) and UpdateRecip(box). */
+int gomcb200_mp_accept(gomcb200_engine *e, int box);
+
 /* CallBoxInterForceGPU (CalculateForceCUDAKernel.cuh:17-34) == the pair part of
  * CalculateEnergy::VirialCalc, src/CalculateEnergy.cpp:411-567: diagonal of the LJ
  * virial tensor vT and of the real-space Coulomb tensor rT (qqFact included); the

@@ -131,6 +131,65 @@ def test_virial(gold):
         e.set_recip_algo(2)
 
 
+@pytest.mark.parametrize("kind", ["mpDisplace", "mpRotate"])
+def test_multiparticle_move(gold, kind):
+    """Device MultiParticle step against the reference move object: same variates
+    (Philox4x64-10), trial coordinates, energies on them, acceptance weight, reject."""
+    d, e = gold
+    pre = f"box0.{kind}."
+    if pre + "params" not in d:
+        pytest.skip("no such move in this fixture")
+    if not int(d["box0.orthogonal"][0]):
+        L = None          # positions compared directly (no wrap ambiguity expected)
+    tmax, rmax, lbeta, step, seed, key = d[pre + "params"]
+    rot = kind == "mpRotate"
+    vmax = rmax if rot else tmax
+    bm = d["box0.mols"]
+    ewald = bool(d["ff.ewald"][0])
+    # reference forces / torques of the current positions (MultiParticle::Prep)
+    if ewald:
+        e.box_reciprocal_sums(0)
+        e.set_recip_ref(0)
+        e.copy_recip(0)
+        e.box_force_reciprocal(0)
+    lj0, re0 = e.box_force(0)
+    e.calculate_torque(0)
+    e.mp_transform(0, int(rot), vmax, lbeta, int(step), int(key), int(seed))
+    k, inr = e.mp_get_trial(e.n_mols)
+    assert np.array_equal(inr[bm], d[pre + "inForceRange"][bm])
+    for c, a in zip("xyz", k):
+        assert rel_err(a[bm], d[pre + "k." + c][bm]) <= TOL
+    e.mp_select(1)
+    ax = d["box0.axis"]
+    for c, a, cm, L in zip("xyz", e.get_coords(), e.get_com(), ax):
+        dx = a - d[pre + "newMolsPos." + c]
+        dc = cm - d[pre + "newCOMs." + c]
+        if int(d["box0.orthogonal"][0]):       # a point on the box face may wrap either way
+            dx -= L * np.round(dx / L)
+            dc -= L * np.round(dc / L)
+        assert np.max(np.abs(dx)) <= TOL * L and np.max(np.abs(dc)) <= TOL * L
+    # MultiParticle::CalcEn on the trial set
+    if ewald:
+        rc = e.box_reciprocal_sums(0)
+    lj, re = e.box_force(0)
+    if ewald:
+        e.box_force_reciprocal(0)
+    e.calculate_torque(0)
+    want = d[pre + "newEnergy"]
+    assert abs(lj - want[0]) <= TOL * abs(want[0])
+    assert abs(re - want[1]) <= TOL * max(abs(want[1]), 1e-300)
+    if ewald:
+        assert abs(rc - want[2]) <= TOL * abs(want[2])
+    w = e.mp_coeff(0, int(rot), vmax, lbeta)
+    assert abs(w - d[pre + "wRatio"][0]) <= 1e-8 * abs(d[pre + "wRatio"][0])
+    # reject: reference set back, energies as before
+    e.mp_select(0)
+    lj1, re1 = e.box_force(0)
+    assert (lj1, re1) == (lj0, re0)
+    for c, a in zip("xyz", e.get_coords()):
+        assert np.array_equal(a, d["coords." + c])
+
+
 def test_exchange_and_lambda_reciprocal(gold):
     """MolExchangeReciprocal (two chained calls), ChangeLambdaRecip, ChangeRecip."""
     from tests.test_oracle_golden import exchange_weights

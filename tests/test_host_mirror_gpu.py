@@ -107,5 +107,32 @@ def test_host_mirror_move_sequence(tmp_path, name):
     for k in ("inter", "real", "recip"):
         a, b = r["running"][k], r["recomputed"][k]
         assert abs(a - b) <= 1e-9 * max(abs(b), 1.0), k
+    # the MultiParticle displacement step replayed with the oracle on the final coordinates
+    g = r["mp"]
+    bm, ba = box_mols(s), box_atoms(s)
+    beta, lam, tmax = 1.0 / 300.0, 0.5, 0.02
+    _, _, aF, mF = o.box_force(x, y, z, s.kind, s.mol, s.charge, ba, s.n_mols)
+    mR = None
+    if s.ff.ewald:
+        sRc, sIc = o.box_recip_sums(bm, s.mol_start, x, y, z, s.charge, kx, ky, kz)
+        _, mR = o.box_force_reciprocal(bm, s.mol_start, x, y, z, s.charge, kx, ky, kz, pf,
+                                       sRc, sIc, s.n_mols)
+    else:
+        mR = [np.zeros(s.n_mols) for _ in range(3)]
+    com = [np.zeros(s.n_mols) for _ in range(3)]
+    k, inr, new, _ = o.mp_transform(0, bm, s.mol_start, (x, y, z), com, mF, mR, tmax, lam, beta,
+                                    77, 123, 0)
+    ljn, ren, _, mFn = o.box_force(*new, s.kind, s.mol, s.charge, ba, s.n_mols)
+    assert abs(g["inter"] - ljn) <= TOL * abs(ljn)
+    mRn = [np.zeros(s.n_mols) for _ in range(3)]
+    if s.ff.ewald:
+        assert abs(g["real"] - ren) <= TOL * abs(ren)
+        sRn, sIn = o.box_recip_sums(bm, s.mol_start, *new, s.charge, kx, ky, kz)
+        assert abs(g["recip"] - o.box_reciprocal(sRn, sIn, pf)) <= TOL * abs(g["recip"])
+        _, mRn = o.box_force_reciprocal(bm, s.mol_start, *new, s.charge, kx, ky, kz, pf,
+                                        sRn, sIn, s.n_mols)
+    w = o.mp_coeff(bm, inr, mF, mR, mFn, mRn, k, tmax, lam, beta)
+    assert abs(g["w"] - w) <= 1e-8 * abs(w)
+    assert abs(g["inter_after_reject"] - r["recomputed"]["inter"]) <= 1e-12 * abs(g["inter"])
     lj2, re2 = o.box_inter(x, y, z, s.kind, s.mol, s.charge, box_atoms(s))
     assert abs(r["recomputed"]["inter"] - lj2) <= TOL * abs(lj2)
