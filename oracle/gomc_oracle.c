@@ -156,9 +156,56 @@ static martini_consts martini_init(const orc_params *p, int idx) {
 #define DBL_MAX 1.7976931348623158e+308 /* num::BIGNUM, lib/NumLib.h:15,24 */
 #endif
 
+/* ---- fractional molecule (free energy / NeMTMC): lib/Lambda.h state of one box
+ * plus the soft-core constants of src/Forcefield.cpp:58-75.  Test-infrastructure
+ * global: set with orc_set_lambda before calling the functions below. */
+static struct {
+  int mol; /* -1: no fractional molecule */
+  double vdw, coulomb, sc_alpha, sc_sigma_6;
+  int sc_power, sc_coul, molKind;
+} g_lambda = {-1, 1.0, 1.0, 0.0, 0.0, 0, 0, -1};
+void orc_set_lambda(int mol, double lambdaVDW, double lambdaCoulomb, double sc_alpha,
+                    double sc_sigma_6, int sc_power, int sc_coul, int molKind) {
+  g_lambda.mol = mol;
+  g_lambda.molKind = molKind;
+  g_lambda.vdw = lambdaVDW;
+  g_lambda.coulomb = lambdaCoulomb;
+  g_lambda.sc_alpha = sc_alpha;
+  g_lambda.sc_sigma_6 = sc_sigma_6;
+  g_lambda.sc_power = sc_power;
+  g_lambda.sc_coul = sc_coul;
+}
+/* CalculateEnergy::GetLambdaVDW / GetLambdaCoulomb, src/CalculateEnergy.cpp:1558-1572 */
+static inline double pair_lambda_vdw(int molA, int molB) {
+  double l = 1.0;
+  l *= (molA == g_lambda.mol ? g_lambda.vdw : 1.0);
+  l *= (molB == g_lambda.mol ? g_lambda.vdw : 1.0);
+  return l;
+}
+static inline double pair_lambda_coulomb(int molA, int molB) {
+  double l = 1.0;
+  l *= (molA == g_lambda.mol ? g_lambda.coulomb : 1.0);
+  l *= (molB == g_lambda.mol ? g_lambda.coulomb : 1.0);
+  return l;
+}
+/* Ewald::GetLambdaCoef, src/Ewald.cpp:1598-1602 */
+static inline double mol_lambda_coef(int mol) {
+  return sqrt(mol == g_lambda.mol ? g_lambda.coulomb : 1.0);
+}
+/* soft-core r^2, identical text in every functor (e.g. src/FFParticle.cpp:306-311) */
+static inline double soft_rsq(const orc_params *p, double distSq, int idx, double lambda) {
+  double sigma6 = p->sigmaSq[idx] * p->sigmaSq[idx] * p->sigmaSq[idx];
+  sigma6 = sigma6 > g_lambda.sc_sigma_6 ? sigma6 : g_lambda.sc_sigma_6;
+  double dist6 = distSq * distSq * distSq;
+  double lambdaCoef = g_lambda.sc_alpha * pow((1.0 - lambda), (double)g_lambda.sc_power);
+  double softDist6 = lambdaCoef * sigma6 + dist6;
+  return cbrt(softDist6);
+}
+static _Thread_local int g_nocut = 0; /* the two-argument functor forms have no cut-off test */
+
 double orc_calc_en(const orc_params *p, double distSq, int kind1, int kind2) {
   double rCutSq = p->rCut * p->rCut;
-  if (rCutSq < distSq) return 0.0; /* FFParticle.cpp:297 */
+  if (!g_nocut && rCutSq < distSq) return 0.0; /* FFParticle.cpp:297 */
   int idx = kind1 + kind2 * p->kindCount; /* FFParticle.h:111 */
   if (p->vdwKind == ORC_VDW_SWITCH && p->isMartini) { /* FFSwitchMartini.h:279-302 */
     martini_consts m = martini_init(p, idx);
@@ -217,7 +264,7 @@ double orc_calc_en(const orc_params *p, double distSq, int kind1, int kind2) {
 
 double orc_calc_vir(const orc_params *p, double distSq, int kind1, int kind2) {
   double rCutSq = p->rCut * p->rCut;
-  if (rCutSq < distSq) return 0.0;
+  if (!g_nocut && rCutSq < distSq) return 0.0;
   int idx = kind1 + kind2 * p->kindCount;
   if (p->vdwKind == ORC_VDW_SWITCH && p->isMartini) { /* FFSwitchMartini.h:328-348 */
     martini_consts m = martini_init(p, idx);
@@ -273,7 +320,7 @@ double orc_calc_vir(const orc_params *p, double distSq, int kind1, int kind2) {
 double orc_calc_coulomb(const orc_params *p, double distSq,
                         double qi_qj_fact) {
   double rcc2 = p->rCutCoulomb * p->rCutCoulomb;
-  if (rcc2 < distSq) return 0.0; /* FFParticle.cpp:364 */
+  if (!g_nocut && rcc2 < distSq) return 0.0; /* FFParticle.cpp:364 */
   double dist = sqrt(distSq);
   if (p->ewald) { /* FFParticle.cpp:388-394, FFShift.h:239-244, FFSwitch.h:247-252 */
     double val = p->alpha * dist;
@@ -301,7 +348,7 @@ double orc_calc_coulomb(const orc_params *p, double distSq,
 
 double orc_calc_coulomb_vir(const orc_params *p, double distSq, double qi_qj) {
   double rcc2 = p->rCutCoulomb * p->rCutCoulomb;
-  if (rcc2 < distSq) return 0.0;
+  if (!g_nocut && rcc2 < distSq) return 0.0;
   double dist = sqrt(distSq);
   if (p->ewald) {
     double constValue = p->alpha * M_2_SQRTPI;
@@ -328,6 +375,71 @@ double orc_calc_coulomb_vir(const orc_params *p, double distSq, double qi_qj) {
     return -qi_qj * (dSwitchVal / distSq - switchVal / (distSq * dist));
   }
   return qi_qj / (distSq * dist);
+}
+
+/* The lambda-taking functor forms (src/FFParticle.cpp:295-315, :327-348, :360-386,
+ * :400-429; the subclasses repeat them, FF_EXP6 tests rMaxSq first, src/FFExp6.h:184-211,
+ * :226-252). */
+static double calc_en_l(const orc_params *p, double distSq, int k1, int k2, double lambda) {
+  if (p->rCut * p->rCut < distSq) return 0.0;
+  int idx = k1 + k2 * p->kindCount;
+  if (p->vdwKind == ORC_VDW_EXP6 && distSq < p->rMaxSq[idx]) return DBL_MAX;
+  double r;
+  g_nocut = 1;
+  if (lambda >= 0.999999)
+    r = orc_calc_en(p, distSq, k1, k2);
+  else
+    r = lambda * orc_calc_en(p, soft_rsq(p, distSq, idx, lambda), k1, k2);
+  g_nocut = 0;
+  return r;
+}
+static double calc_vir_l(const orc_params *p, double distSq, int k1, int k2, double lambda) {
+  if (p->rCut * p->rCut < distSq) return 0.0;
+  int idx = k1 + k2 * p->kindCount;
+  if (p->vdwKind == ORC_VDW_EXP6 && distSq < p->rMaxSq[idx]) return DBL_MAX;
+  double r;
+  g_nocut = 1;
+  if (lambda >= 0.999999) {
+    r = orc_calc_vir(p, distSq, k1, k2);
+  } else {
+    double softRsq = soft_rsq(p, distSq, idx, lambda);
+    double correction = distSq / softRsq;
+    r = lambda * correction * correction * orc_calc_vir(p, softRsq, k1, k2);
+  }
+  g_nocut = 0;
+  return r;
+}
+static double calc_coulomb_l(const orc_params *p, double distSq, int k1, int k2,
+                             double qi_qj_fact, double lambda) {
+  if (p->rCutCoulomb * p->rCutCoulomb < distSq) return 0.0;
+  double r;
+  g_nocut = 1;
+  if (lambda >= 0.999999)
+    r = orc_calc_coulomb(p, distSq, qi_qj_fact);
+  else if (g_lambda.sc_coul)
+    r = lambda * orc_calc_coulomb(p, soft_rsq(p, distSq, k1 + k2 * p->kindCount, lambda),
+                                  qi_qj_fact);
+  else
+    r = lambda * orc_calc_coulomb(p, distSq, qi_qj_fact);
+  g_nocut = 0;
+  return r;
+}
+static double calc_coulomb_vir_l(const orc_params *p, double distSq, int k1, int k2,
+                                 double qi_qj, double lambda) {
+  if (p->rCutCoulomb * p->rCutCoulomb < distSq) return 0.0;
+  double r;
+  g_nocut = 1;
+  if (lambda >= 0.999999) {
+    r = orc_calc_coulomb_vir(p, distSq, qi_qj);
+  } else if (g_lambda.sc_coul) {
+    double softRsq = soft_rsq(p, distSq, k1 + k2 * p->kindCount, lambda);
+    double correction = distSq / softRsq;
+    r = lambda * correction * correction * orc_calc_coulomb_vir(p, softRsq, qi_qj);
+  } else {
+    r = lambda * orc_calc_coulomb_vir(p, distSq, qi_qj);
+  }
+  g_nocut = 0;
+  return r;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -478,9 +590,11 @@ int orc_box_inter(const orc_params *p, int nAtomsTotal, const double *x,
             if (p->electrostatic) {
               double qi_qj_fact = charge[cur] * charge[nb] * ORC_QQFACT;
               if (qi_qj_fact != 0.0)
-                tempREn += orc_calc_coulomb(p, distSq, qi_qj_fact);
+                tempREn += calc_coulomb_l(p, distSq, kind[cur], kind[nb], qi_qj_fact,
+                                          pair_lambda_coulomb(mol[cur], mol[nb]));
             }
-            tempLJEn += orc_calc_en(p, distSq, kind[cur], kind[nb]);
+            tempLJEn += calc_en_l(p, distSq, kind[cur], kind[nb],
+                                  pair_lambda_vdw(mol[cur], mol[nb]));
           }
         }
       }
@@ -529,15 +643,17 @@ int orc_box_force(const orc_params *p, int nAtomsTotal, int nMols,
             if (p->electrostatic) {
               double qi_qj_fact = charge[cur] * charge[nb] * ORC_QQFACT;
               if (qi_qj_fact != 0.0) {
-                tempREn += orc_calc_coulomb(p, distSq, qi_qj_fact);
-                double v = orc_calc_coulomb_vir(p, distSq, qi_qj_fact);
+                double lc = pair_lambda_coulomb(mol[cur], mol[nb]);
+                tempREn += calc_coulomb_l(p, distSq, kind[cur], kind[nb], qi_qj_fact, lc);
+                double v = calc_coulomb_vir_l(p, distSq, kind[cur], kind[nb], qi_qj_fact, lc);
                 fR[0] = d[0] * v;
                 fR[1] = d[1] * v;
                 fR[2] = d[2] * v;
               }
             }
-            tempLJEn += orc_calc_en(p, distSq, kind[cur], kind[nb]);
-            double w = orc_calc_vir(p, distSq, kind[cur], kind[nb]);
+            double lv = pair_lambda_vdw(mol[cur], mol[nb]);
+            tempLJEn += calc_en_l(p, distSq, kind[cur], kind[nb], lv);
+            double w = calc_vir_l(p, distSq, kind[cur], kind[nb], lv);
             fL[0] = d[0] * w;
             fL[1] = d[1] * w;
             fL[2] = d[2] * w;
@@ -620,13 +736,15 @@ int orc_virial_calc(const orc_params *p, int nAtomsTotal, const double *x,
             if (p->electrostatic) {
               double qi_qj = charge[cur] * charge[nb];
               if (qi_qj != 0.0) {
-                double pRF = orc_calc_coulomb_vir(p, distSq, qi_qj);
+                double pRF = calc_coulomb_vir_l(p, distSq, kind[cur], kind[nb], qi_qj,
+                                                pair_lambda_coulomb(mol[cur], mol[nb]));
                 rT11 += pRF * (d[0] * cc[0]);
                 rT22 += pRF * (d[1] * cc[1]);
                 rT33 += pRF * (d[2] * cc[2]);
               }
             }
-            double pVF = orc_calc_vir(p, distSq, kind[cur], kind[nb]);
+            double pVF = calc_vir_l(p, distSq, kind[cur], kind[nb],
+                                    pair_lambda_vdw(mol[cur], mol[nb]));
             vT11 += pVF * (d[0] * cc[0]);
             vT22 += pVF * (d[1] * cc[1]);
             vT33 += pVF * (d[2] * cc[2]);
@@ -671,7 +789,7 @@ int orc_virial_reciprocal(const orc_params *p, int nBoxMols, const int *boxMols,
       double at[3] = {x[a], y[a], z[a]};
       unwrap_vec(p, at, com);
       double diff[3] = {at[0] - com[0], at[1] - com[1], at[2] - com[2]};
-      double q = charge[a] * 1.0;
+      double q = charge[a] * mol_lambda_coef(m);
       /* one OpenMP reduction region per atom (:1272-1284): the k sum goes
        * into a zero-initialised private copy that is then added to wT */
       double p11 = 0.0, p22 = 0.0, p33 = 0.0;
@@ -925,7 +1043,7 @@ static void probe_sweep(const orc_params *p, const cell_csr *c,
                         const int *kind, const double *charge, double px,
                         double py, double pz, int kindI, double qI,
                         double sign, int checkOverlap, double *lj,
-                        double *real, int *overlap) {
+                        double *real, int *overlap, const int *mol, int molI) {
   double boxRcutSq = box_rcut(p) * box_rcut(p);
   double rCutLowSq = p->rCutLow * p->rCutLow;
   int cell = position_to_cell(cellSize, edge, px, py, pz);
@@ -940,9 +1058,10 @@ static void probe_sweep(const orc_params *p, const cell_csr *c,
         if (p->electrostatic) {
           double qi_qj_fact = qI * charge[nb] * ORC_QQFACT;
           if (qi_qj_fact != 0.0)
-            *real += sign * orc_calc_coulomb(p, distSq, qi_qj_fact);
+            *real += sign * calc_coulomb_l(p, distSq, kindI, kind[nb], qi_qj_fact,
+                                           pair_lambda_coulomb(molI, mol[nb]));
         }
-        *lj += sign * orc_calc_en(p, distSq, kindI, kind[nb]);
+        *lj += sign * calc_en_l(p, distSq, kindI, kind[nb], pair_lambda_vdw(molI, mol[nb]));
       }
     }
   }
@@ -955,8 +1074,6 @@ int orc_molecule_inter(const orc_params *p, int nAtomsTotal, const double *x,
                        int molStart, int molLen, const double *newX,
                        const double *newY, const double *newZ, double *dLJ,
                        double *dReal) {
-  (void)mol;
-  (void)molIndex;
   cell_csr c = csr_make(p, nAtomsTotal, x, y, z, boxAtoms, nBox);
   int edge[3];
   orc_cell_edges(p, edge);
@@ -969,11 +1086,11 @@ int orc_molecule_inter(const orc_params *p, int nAtomsTotal, const double *x,
     /* subtract old energy, src/CalculateEnergy.cpp:593-634 */
     probe_sweep(p, &c, cellSize, edge, x, y, z, kind, charge, x[atom], y[atom],
                 z[atom], kind[atom], charge[atom], -1.0, 0, &lj, &real,
-                &overlap);
+                &overlap, mol, molIndex);
     /* add new energy, :637-678 */
     probe_sweep(p, &c, cellSize, edge, x, y, z, kind, charge, newX[a], newY[a],
                 newZ[a], kind[atom], charge[atom], 1.0, 1, &lj, &real,
-                &overlap);
+                &overlap, mol, molIndex);
   }
   *dLJ = lj;
   *dReal = real;
@@ -988,8 +1105,6 @@ int orc_particle_inter(const orc_params *p, int nAtomsTotal, const double *x,
                        double qI, int trials, const double *tx,
                        const double *ty, const double *tz, double *en,
                        double *real, int *overlap) {
-  (void)mol;
-  (void)molIndex;
   cell_csr c = csr_make(p, nAtomsTotal, x, y, z, boxAtoms, nBox);
   int edge[3];
   orc_cell_edges(p, edge);
@@ -999,7 +1114,7 @@ int orc_particle_inter(const orc_params *p, int nAtomsTotal, const double *x,
     double lj = 0.0, re = 0.0;
     int ov = 0;
     probe_sweep(p, &c, cellSize, edge, x, y, z, kind, charge, tx[t], ty[t],
-                tz[t], kindI, qI, 1.0, 1, &lj, &re, &ov);
+                tz[t], kindI, qI, 1.0, 1, &lj, &re, &ov, mol, molIndex);
     en[t] += lj;
     real[t] += re;
     overlap[t] |= ov;
@@ -1235,8 +1350,9 @@ int orc_box_recip_sums_slab(int nBoxMols, const int *boxMols,
         sumReal += charge[a] * cos(dot);
         sumImaginary += charge[a] * sin(dot);
       }
-      accR += 1.0 * sumReal; /* lambdaCoef == 1 */
-      accI += 1.0 * sumImaginary;
+      double lambdaCoef = mol_lambda_coef(m); /* src/Ewald.cpp:240,266-267 */
+      accR += (lambdaCoef * sumReal);
+      accI += (lambdaCoef * sumImaginary);
     }
     sumR[i] = accR;
     sumI[i] = accI;
@@ -1269,6 +1385,18 @@ double orc_mol_reciprocal(int molLen, const double *q, const double *oldX,
                           const double *prefact, const double *sumRref,
                           const double *sumIref, double *sumRnew,
                           double *sumInew) {
+  return orc_mol_reciprocal_l(molLen, q, oldX, oldY, oldZ, newX, newY, newZ, nk, kx, ky, kz,
+                              prefact, sumRref, sumIref, sumRnew, sumInew, 1.0);
+}
+
+double orc_mol_reciprocal_l(int molLen, const double *q, const double *oldX,
+                            const double *oldY, const double *oldZ,
+                            const double *newX, const double *newY,
+                            const double *newZ, int nk, const double *kx,
+                            const double *ky, const double *kz,
+                            const double *prefact, const double *sumRref,
+                            const double *sumIref, double *sumRnew,
+                            double *sumInew, double lambdaCoef) {
   double eNew = 0.0; /* src/Ewald.cpp:434-466 */
   for (int i = 0; i < nk; ++i) {
     double sRn = 0.0, sIn = 0.0, sRo = 0.0, sIo = 0.0;
@@ -1281,8 +1409,8 @@ double orc_mol_reciprocal(int molLen, const double *q, const double *oldX,
       sRo += q[a] * cos(dotOld);
       sIo += q[a] * sin(dotOld);
     }
-    sumRnew[i] = sumRref[i] + 1.0 * (sRn - sRo);
-    sumInew[i] = sumIref[i] + 1.0 * (sIn - sIo);
+    sumRnew[i] = sumRref[i] + lambdaCoef * (sRn - sRo);
+    sumInew[i] = sumIref[i] + lambdaCoef * (sIn - sIo);
     eNew += (sumRnew[i] * sumRnew[i] + sumInew[i] * sumInew[i]) * prefact[i];
   }
   return eNew;
@@ -1379,6 +1507,7 @@ int orc_box_force_reciprocal(const orc_params *p, int nBoxMols,
 #endif
   for (int mi = 0; mi < nBoxMols; ++mi) { /* :1541-1592 */
     int m = boxMols[mi];
+    double lambdaCoef = mol_lambda_coef(m);
     double msx = 0.0, msy = 0.0, msz = 0.0;
     for (int a = molStart[m]; a < molStart[m + 1]; ++a) {
       double X = 0.0, Y = 0.0, Z = 0.0;
@@ -1391,7 +1520,7 @@ int orc_box_force_reciprocal(const orc_params *p, int nBoxMols,
             double dist = sqrt(distSq);
             double expConstValue = exp(-1.0 * alphaSq * distSq);
             double qiqj = charge[a] * charge[j] * ORC_QQFACT;
-            double intraForce = qiqj * 1.0 * 1.0 / distSq;
+            double intraForce = qiqj * lambdaCoef * lambdaCoef / distSq;
             intraForce *=
                 ((erf(p->alpha * dist) / dist) - constValue * expConstValue);
             X -= intraForce * d[0];
@@ -1401,7 +1530,7 @@ int orc_box_force_reciprocal(const orc_params *p, int nBoxMols,
         }
         for (int i = 0; i < nk; ++i) { /* :1575-1586 */
           double dot = x[a] * kx[i] + y[a] * ky[i] + z[a] * kz[i];
-          double factor = 2.0 * charge[a] * prefact[i] * 1.0 *
+          double factor = 2.0 * charge[a] * prefact[i] * lambdaCoef *
                           (sin(dot) * sumR[i] - cos(dot) * sumI[i]);
           X += factor * kx[i];
           Y += factor * ky[i];
@@ -1451,7 +1580,8 @@ double orc_box_correction(const orc_params *p, int nBoxMols,
     int s = molStart[m], len = molStart[m + 1] - s;
     /* Ewald::MolCorrection, src/Ewald.cpp:1056-1085 */
     double c = mol_correction(p, len, charge + s, x + s, y + s, z + s, 1);
-    total += -1.0 * ORC_QQFACT * c * 1.0 * 1.0;
+    double lambdaCoef = mol_lambda_coef(m);
+    total += -1.0 * ORC_QQFACT * c * lambdaCoef * lambdaCoef;
   }
   return total;
 }
@@ -1467,7 +1597,13 @@ double orc_box_self(const orc_params *p, int nBoxMols, const int *boxMols,
     double molSelf = 0.0;
     for (int a = molStart[m]; a < molStart[m + 1]; ++a)
       molSelf += charge[a] * charge[a];
-    self += molSelf;
+    /* src/Ewald.cpp:1140-1155 takes the fractional molecule out of its kind's count and
+     * adds it back times lambdaRef.GetLambdaCoulomb(i, box) -- called with the KIND index
+     * i where a molecule index is expected, so the factor is lambda only when the
+     * fractional molecule's index equals its kind index, and 1 otherwise.  As written. */
+    self += molSelf * ((m == g_lambda.mol && g_lambda.mol == g_lambda.molKind)
+                           ? g_lambda.coulomb
+                           : 1.0);
   }
   self *= -1.0 * p->alpha * ORC_QQFACT * M_2_SQRTPI * 0.5;
   return self;

@@ -205,6 +205,24 @@ int orc_box_force_reciprocal(const orc_params *p, int nBoxMols,
                              double *rFz, double *mFx, double *mFy,
                              double *mFz);
 
+/* Fractional molecule of the box (lib/Lambda.h) and soft-core constants
+ * (src/Forcefield.cpp:58-75) for every function below: pair lambdas as
+ * CalculateEnergy::GetLambdaVDW/GetLambdaCoulomb (src/CalculateEnergy.cpp:1558-1572),
+ * reciprocal coefficient sqrt(lambdaCoulomb) as Ewald::GetLambdaCoef
+ * (src/Ewald.cpp:1598-1602).  mol = -1 switches it off (the default).  Global state
+ * of the test oracle, not thread-safe across callers. */
+void orc_set_lambda(int mol, double lambdaVDW, double lambdaCoulomb, double sc_alpha,
+                    double sc_sigma_6, int sc_power, int sc_coul, int molKind);
+/* orc_mol_reciprocal with the molecule's lambdaCoef (src/Ewald.cpp:419,459-462). */
+double orc_mol_reciprocal_l(int molLen, const double *q, const double *oldX,
+                            const double *oldY, const double *oldZ,
+                            const double *newX, const double *newY,
+                            const double *newZ, int nk, const double *kx,
+                            const double *ky, const double *kz,
+                            const double *prefact, const double *sumRref,
+                            const double *sumIref, double *sumRnew,
+                            double *sumInew, double lambdaCoef);
+
 /* Philox4x64-10 as instantiated by lib/Random123/philox.h (the generator behind
  * Random123Wrapper, src/Random123Wrapper.cpp:16-22). */
 void orc_philox4x64_10(const uint64_t ctr[4], const uint64_t key[2], uint64_t out[4]);

@@ -42,6 +42,20 @@ CASES = {
         216, r_cut=6.0, cell_vectors=synth.triclinic_cell(20.494)), 6, 7),
     "mixture_martini_ewald": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.0,
                                                          martini=True, ewald=True, seed=4, n_b_exp=12.0), 4, 5),
+    # one fractional molecule (free-energy / NeMTMC state): soft-core LJ, with and without
+    # soft-core Coulomb.  Extra probe arguments:
+    #   pick, lambdaVDW, lambdaCoulomb, sc_alpha, sc_sigma, sc_power, sc_coul
+    "spce100_lambda": (lambda: synth.make_spce(100, r_cut=7.0), 6, 7,
+                       (17, 0.6, 0.35, 0.5, 3.0, 2, 0)),
+    # molecule 0 of kind 0: the only case where the reference's BoxSelf scales the
+    # fractional molecule (it passes the kind index where a molecule index is expected)
+    "spce100_lambda_mol0": (lambda: synth.make_spce(100, r_cut=7.0), 4, 7,
+                            (0, 0.3, 0.55, 0.5, 3.0, 2, 1)),
+    "mixture_shift_lambda_sccoul": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SHIFT), 4, 5,
+                                    (3, 0.45, 0.7, 0.5, 3.0, 2, 1)),
+    "mixture_switch_lambda": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH,
+                                                         r_switch=6.5), 4, 5,
+                              (40, 0.8, 0.5, 0.5, 3.0, 2, 1)),
 }
 
 
@@ -53,12 +67,17 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     env = dict(os.environ, OMP_NUM_THREADS="1")
-    for name, (make, n_moves, seed) in CASES.items():
+    only = set(sys.argv[1:])
+    for name, case in CASES.items():
+        if only and name not in only:
+            continue
+        make, n_moves, seed = case[:3]
+        extra = [str(v) for v in case[3]] if len(case) > 3 else []
         s = make()
         with tempfile.TemporaryDirectory() as d:
             synth.write_gomc_inputs(s, d)
-            log = subprocess.run([probe, "golden", "in.conf", "dump.bin", str(n_moves), str(seed)],
-                                 cwd=d, env=env, capture_output=True, text=True)
+            log = subprocess.run([probe, "golden", "in.conf", "dump.bin", str(n_moves), str(seed)]
+                                 + extra, cwd=d, env=env, capture_output=True, text=True)
             if log.returncode != 0:
                 print(log.stdout[-3000:], log.stderr[-2000:])
                 raise SystemExit(f"probe failed on {name}")

@@ -54,6 +54,7 @@ def lib():
         L.orc_energy_lrc.restype = C.c_double
         L.orc_box_reciprocal.restype = C.c_double
         L.orc_mol_reciprocal.restype = C.c_double
+        L.orc_mol_reciprocal_l.restype = C.c_double
         L.orc_swap_recip.restype = C.c_double
         L.orc_recip_weighted.restype = C.c_double
         L.orc_recip_weighted.argtypes = [C.c_int] + [_dp] * 4 + [C.c_int] + [_dp] * 6 + \
@@ -111,6 +112,22 @@ class Oracle:
                 p.cellBasisInv[i] = float(v)
         self.p = p
         self.pp = C.byref(p)
+        self.lambda_mol = -1
+        self.set_lambda(-1)
+
+    def set_lambda(self, mol, lambda_vdw=1.0, lambda_coulomb=1.0, sc_alpha=0.0, sc_sigma_6=0.0,
+                   sc_power=0, sc_coul=0, mol_kind=-1):
+        """Fractional molecule + soft-core constants (global state of the C oracle; the
+        last Oracle constructed / configured wins)."""
+        self.lambda_mol, self.lambda_coulomb = int(mol), float(lambda_coulomb)
+        self.L.orc_set_lambda(C.c_int(int(mol)), C.c_double(lambda_vdw),
+                              C.c_double(lambda_coulomb), C.c_double(sc_alpha),
+                              C.c_double(sc_sigma_6), C.c_int(int(sc_power)),
+                              C.c_int(int(sc_coul)), C.c_int(int(mol_kind)))
+
+    def lambda_coef(self, mol):
+        """Ewald::GetLambdaCoef, src/Ewald.cpp:1598-1602."""
+        return float(np.sqrt(self.lambda_coulomb)) if int(mol) == self.lambda_mol else 1.0
 
     @classmethod
     def from_system(cls, s):
@@ -128,6 +145,15 @@ class Oracle:
 
     @classmethod
     def from_dump(cls, d, box=0):
+        o = cls._from_dump(d, box)
+        if "lambda.params" in d and box == 0:
+            lp = d["lambda.params"]
+            o.set_lambda(int(lp[0]), lp[1], lp[2], lp[3], lp[4], int(lp[5]), int(lp[6]),
+                         int(lp[7]))
+        return o
+
+    @classmethod
+    def _from_dump(cls, d, box=0):
         return cls(vdw_kind=sc(d, "ff.vdwKind"), ewald=sc(d, "ff.ewald"),
                    electrostatic=sc(d, "ff.electrostatic"), kind_count=sc(d, "ff.kindCount"),
                    r_cut=sc(d, "ff.rCut"), r_cut_low=sc(d, "ff.rCutLow"),
@@ -310,16 +336,16 @@ class Oracle:
         (sR, a), (sI, b), (pf, c) = _d(sR), _d(sI), _d(prefact)
         return self.L.orc_box_reciprocal(len(sR), a, b, c)
 
-    def mol_reciprocal(self, q, old, new, kx, ky, kz, prefact, sRref, sIref):
+    def mol_reciprocal(self, q, old, new, kx, ky, kz, prefact, sRref, sIref, lambda_coef=1.0):
         (q, pq) = _d(q)
         o = [_d(a) for a in old]
         nw = [_d(a) for a in new]
         ks = [_d(a) for a in (kx, ky, kz, prefact, sRref, sIref)]
         nk = len(ks[0][0])
         sRn, sIn = np.zeros(nk), np.zeros(nk)
-        e = self.L.orc_mol_reciprocal(len(q), pq, *[a[1] for a in o], *[a[1] for a in nw], nk,
-                                      *[a[1] for a in ks], sRn.ctypes.data_as(_dp),
-                                      sIn.ctypes.data_as(_dp))
+        e = self.L.orc_mol_reciprocal_l(len(q), pq, *[a[1] for a in o], *[a[1] for a in nw], nk,
+                                        *[a[1] for a in ks], sRn.ctypes.data_as(_dp),
+                                        sIn.ctypes.data_as(_dp), C.c_double(lambda_coef))
         return e, sRn, sIn
 
     def swap_recip(self, insert, q, mxyz, kx, ky, kz, prefact, sRref, sIref):

@@ -218,6 +218,29 @@ int run_golden(int argc, char **argv) {
   CalculateEnergy &ce = sys.calcEnergy;
   Dump out(outPath);
   out.i32("threads", omp_get_max_threads());
+  // optional fractional molecule in box 0 (free energy / NeMTMC state):
+  //   <pick> <lambdaVDW> <lambdaCoulomb> <sc_alpha> <sc_sigma> <sc_power> <sc_coul>
+  if (argc > 12) {
+    std::vector<uint> inBox0;
+    for (MoleculeLookup::box_iterator it = sys.molLookupRef.BoxBegin(0);
+         it != sys.molLookupRef.BoxEnd(0); ++it)
+      inBox0.push_back(*it);
+    uint lm = inBox0[(size_t)atoi(argv[6]) % inBox0.size()];
+    double lv = atof(argv[7]), lc = atof(argv[8]);
+    Forcefield &ffw = const_cast<Forcefield &>(sv.forcefield);
+    ffw.sc_alpha = atof(argv[9]);
+    ffw.sc_sigma = atof(argv[10]);
+    ffw.sc_sigma_6 = pow(ffw.sc_sigma, 6.0); // src/Forcefield.cpp:75
+    ffw.sc_power = (uint)atoi(argv[11]);
+    ffw.sc_coul = atoi(argv[12]) != 0;
+    sys.lambdaRef.Set(lv, lc, lm, mols.GetMolKind(lm), 0);
+    // the reference state System::Init built with lambda = 1 is rebuilt
+    sys.calcEwald->UpdateVectorsAndRecipTerms(false);
+    sys.potential = sys.calcEnergy.SystemTotal();
+    double lp[8] = {(double)lm, lv, lc, ffw.sc_alpha, ffw.sc_sigma_6,
+                    (double)ffw.sc_power, (double)ffw.sc_coul, (double)mols.GetMolKind(lm)};
+    out.f64("lambda.params", lp, 8);
+  }
   dump_static(out, sv, sys);
   std::mt19937_64 rng(seed);
   std::uniform_real_distribution<double> U(-1.0, 1.0);
