@@ -38,6 +38,10 @@ struct BoxParams {
   double B[9], Bi[9];
   // molecule centres of mass (virial sweep only)
   const double *comx, *comy, *comz;
+  // fractional molecule of the box (lib/Lambda.h; -1: none) and the soft-core constants
+  // (src/Forcefield.cpp:58-75)
+  int lambdaMol, scCoul;
+  double lambdaVDW, lambdaCoulomb, scAlpha, scSigma6, scPower;
 };
 
 // BoxDimensions::UnwrapPBC (scalar), src/BoxDimensions.cpp:297-320
@@ -129,10 +133,12 @@ __device__ __forceinline__ double mie_repulse(double rRat2, double attract,
   return pow(rRat2, n * 0.5);
 }
 
-template <int VDW>
+// CUT = false: the reference's two-argument functor forms (no cut-off test), which
+// the soft-core wrappers call with the softened r^2.
+template <int VDW, bool CUT = true>
 __device__ __forceinline__ double calc_en(const BoxParams &p, double r2,
                                           int idx) {
-  if (p.rCutSq < r2) return 0.0;
+  if (CUT && p.rCutSq < r2) return 0.0;
   if (VDW == VDW_EXP6) {  // src/FFExp6.h:184-224
     if (r2 < p.rMaxSq[idx]) return kBigNum;
     double dist = sqrt(r2);
@@ -175,12 +181,12 @@ __device__ __forceinline__ double calc_en(const BoxParams &p, double r2,
   return e;
 }
 
-template <int VDW>
+template <int VDW, bool CUT = true>
 __device__ __forceinline__ void calc_en_vir(const BoxParams &p, double r2,
                                             int idx, double &en, double &vir) {
   en = 0.0;
   vir = 0.0;
-  if (p.rCutSq < r2) return;
+  if (CUT && p.rCutSq < r2) return;
   if (VDW == VDW_EXP6) {  // src/FFExp6.h:184-257
     if (r2 < p.rMaxSq[idx]) {
       en = kBigNum;
@@ -199,7 +205,7 @@ __device__ __forceinline__ void calc_en_vir(const BoxParams &p, double r2,
     return;
   }
   if (VDW == VDW_MARTINI) {  // src/FFSwitchMartini.h:279-348 (r_8 = (r^2)^4 as written there)
-    en = calc_en<VDW_MARTINI>(p, r2, idx);
+    en = calc_en<VDW_MARTINI, CUT>(p, r2, idx);
     double n_ij = p.n[idx];
     double r_1 = 1.0 / sqrt(r2);
     double r_8 = r2 * r2 * r2 * r2;
@@ -243,10 +249,10 @@ __device__ __forceinline__ void calc_en_vir(const BoxParams &p, double r2,
   }
 }
 
-template <int VDW>
+template <int VDW, bool CUT = true>
 __device__ __forceinline__ double calc_coulomb(const BoxParams &p, double r2,
                                                double qq) {
-  if (p.rCutCoulombSq < r2) return 0.0;
+  if (CUT && p.rCutCoulombSq < r2) return 0.0;
   double dist = sqrt(r2);
   if (p.ewald) return qq * erfc(p.alpha * dist) / dist;
   if (VDW == VDW_MARTINI) {  // src/FFSwitchMartini.h:379-396
@@ -262,13 +268,13 @@ __device__ __forceinline__ double calc_coulomb(const BoxParams &p, double r2,
   return qq / dist;
 }
 
-template <int VDW>
+template <int VDW, bool CUT = true>
 __device__ __forceinline__ void calc_coulomb_en_vir(const BoxParams &p,
                                                     double r2, double qq,
                                                     double &en, double &vir) {
   en = 0.0;
   vir = 0.0;
-  if (p.rCutCoulombSq < r2) return;
+  if (CUT && p.rCutCoulombSq < r2) return;
   double dist = sqrt(r2);
   if (p.ewald) {
     double x = p.alpha * dist;
@@ -301,6 +307,73 @@ __device__ __forceinline__ void calc_coulomb_en_vir(const BoxParams &p,
 }
 
 // 32-bit shared-window addressing: explicit LDS/STS instead of generic LD/ST.
+// ---- lambda-taking functor forms (fractional molecule) -------------------------
+// src/FFParticle.cpp:295-315, :327-348, :360-386, :400-429 and the identical text in
+// FFShift.h, FFSwitch.h, FFSwitchMartini.h, FFExp6.h (which tests rMaxSq first).
+__device__ __forceinline__ double soft_rsq(const BoxParams &p, double r2, int idx, double lambda) {
+  double s2 = p.sigmaSq[idx];
+  double sigma6 = fmax(s2 * s2 * s2, p.scSigma6);
+  double dist6 = r2 * r2 * r2;
+  double lambdaCoef = p.scAlpha * pow(1.0 - lambda, p.scPower);
+  return cbrt(lambdaCoef * sigma6 + dist6);
+}
+template <int VDW>
+__device__ __forceinline__ double calc_en_l(const BoxParams &p, double r2, int idx, double lambda) {
+  if (lambda >= 0.999999) return calc_en<VDW>(p, r2, idx);
+  if (p.rCutSq < r2) return 0.0;
+  if (VDW == VDW_EXP6 && r2 < p.rMaxSq[idx]) return kBigNum;
+  return lambda * calc_en<VDW, false>(p, soft_rsq(p, r2, idx, lambda), idx);
+}
+template <int VDW>
+__device__ __forceinline__ void calc_en_vir_l(const BoxParams &p, double r2, int idx,
+                                              double lambda, double &en, double &vir) {
+  if (lambda >= 0.999999) {
+    calc_en_vir<VDW>(p, r2, idx, en, vir);
+    return;
+  }
+  en = vir = 0.0;
+  if (p.rCutSq < r2) return;
+  if (VDW == VDW_EXP6 && r2 < p.rMaxSq[idx]) {
+    en = vir = kBigNum;
+    return;
+  }
+  const double soft = soft_rsq(p, r2, idx, lambda);
+  const double corr = r2 / soft;
+  calc_en_vir<VDW, false>(p, soft, idx, en, vir);
+  en *= lambda;
+  vir *= lambda * corr * corr;
+}
+template <int VDW>
+__device__ __forceinline__ double calc_coulomb_l(const BoxParams &p, double r2, int idx,
+                                                 double qq, double lambda) {
+  if (lambda >= 0.999999) return calc_coulomb<VDW>(p, r2, qq);
+  if (p.rCutCoulombSq < r2) return 0.0;
+  const double r = p.scCoul ? soft_rsq(p, r2, idx, lambda) : r2;
+  return lambda * calc_coulomb<VDW, false>(p, r, qq);
+}
+template <int VDW>
+__device__ __forceinline__ void calc_coulomb_en_vir_l(const BoxParams &p, double r2, int idx,
+                                                      double qq, double lambda, double &en,
+                                                      double &vir) {
+  if (lambda >= 0.999999) {
+    calc_coulomb_en_vir<VDW>(p, r2, qq, en, vir);
+    return;
+  }
+  en = vir = 0.0;
+  if (p.rCutCoulombSq < r2) return;
+  if (p.scCoul) {
+    const double soft = soft_rsq(p, r2, idx, lambda);
+    const double corr = r2 / soft;
+    calc_coulomb_en_vir<VDW, false>(p, soft, qq, en, vir);
+    en *= lambda;
+    vir *= lambda * corr * corr;
+  } else {
+    calc_coulomb_en_vir<VDW, false>(p, r2, qq, en, vir);
+    en *= lambda;
+    vir *= lambda;
+  }
+}
+
 __device__ __forceinline__ unsigned smem_u32(const void *p) {
   return (unsigned)__cvta_generic_to_shared(p);
 }

@@ -121,6 +121,9 @@ struct BoxState {
   int iRnew = 0, iInew = 1, iRref = 2, iIref = 3;
   DevBuf<double4> packed;
   bool packedDirty = true;
+  // fractional molecule of this box (lib/Lambda.h)
+  int lambdaMol = -1, lambdaMolKind = -1;
+  double lambdaVDW = 1.0, lambdaCoulomb = 1.0;
 };
 
 }  // namespace
@@ -146,6 +149,10 @@ struct gomcb200_engine {
   std::vector<int> hKind, hMol, hMolStart;
   std::vector<int> hMolBox;  // box of each molecule (-1: in no box)
   std::vector<double> hCharge;
+  std::vector<double> hChargeEff;  // charge * sqrt(lambdaCoulomb) of its molecule (Ewald terms)
+  DevBuf<double> qEff;
+  double scAlpha = 0.0, scSigma6 = 0.0, scPower = 0.0;
+  int scCoul = 0;
   // lazily maintained host mirror of the coordinates (single-molecule moves read
   // the old positions from it instead of a D2H round trip)
   std::vector<double> hx, hy, hz;
@@ -234,6 +241,13 @@ BoxParams make_params(const gomcb200_engine *e, int b) {
   p.comx = e->comx.p;
   p.comy = e->comy.p;
   p.comz = e->comz.p;
+  p.lambdaMol = bx.lambdaMol;
+  p.lambdaVDW = bx.lambdaVDW;
+  p.lambdaCoulomb = bx.lambdaCoulomb;
+  p.scAlpha = e->scAlpha;
+  p.scSigma6 = e->scSigma6;
+  p.scPower = e->scPower;
+  p.scCoul = e->scCoul;
   return p;
 }
 
@@ -335,14 +349,22 @@ void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int 
   double *fx = e->force[GOMCB200_ATOM_FORCE][0].p;
   double *fy = e->force[GOMCB200_ATOM_FORCE][1].p;
   double *fz = e->force[GOMCB200_ATOM_FORCE][2].p;
-#define LAUNCH(V)                                                                   \
+#define LAUNCH_M(V, M)                                                              \
   do {                                                                              \
-    cudaFuncSetAttribute(k_pair_box<V, FORCE, NW>,                                  \
+    cudaFuncSetAttribute(k_pair_box<V, M, NW>,                                      \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); \
-    k_pair_box<V, FORCE, NW><<<grid, NW * 32, smemBytes, e->stream>>>(              \
+    k_pair_box<V, M, NW><<<grid, NW * 32, smemBytes, e->stream>>>(                  \
         p, bx.grid, slices, cell0, useSmem, smemAtoms, bx.cellStart.p, bx.sx.p, bx.sy.p,  \
         bx.sz.p, bx.sq.p, bx.skm.p, bx.sortedAtoms.p, e->blockA.p, e->blockB.p, fx, \
         fy, fz);                                                                    \
+  } while (0)
+  // boxes with a fractional molecule run the instantiation that carries the soft-core branch
+#define LAUNCH(V)                                 \
+  do {                                            \
+    if (bx.lambdaMol >= 0)                        \
+      LAUNCH_M(V, FORCE | MODE_LAMBDA);           \
+    else                                          \
+      LAUNCH_M(V, FORCE);                         \
   } while (0)
   if (e->vdwKind == VDW_SHIFT)
     LAUNCH(VDW_SHIFT);
@@ -355,6 +377,7 @@ void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int 
   else
     LAUNCH(VDW_STD);
 #undef LAUNCH
+#undef LAUNCH_M
   e->launches += 1;
 }
 
@@ -811,7 +834,7 @@ int ensure_packed(gomcb200_engine *e, int b) {
   CK(bx.packed.reserve(bx.nCharged + 1));
   if (bx.nCharged > 0) {
     k_pack_charged<<<(bx.nCharged + 255) / 256, 256, 0, e->stream>>>(
-        bx.nCharged, bx.chargedList.p, e->x.p, e->y.p, e->z.p, e->q.p, bx.packed.p);
+        bx.nCharged, bx.chargedList.p, e->x.p, e->y.p, e->z.p, e->qEff.p, bx.packed.p);
     e->launches += 1;
   }
   bx.packedDirty = false;
@@ -1005,7 +1028,7 @@ int stage_molbuf(gomcb200_engine *e, int molIndex, const double *nx, const doubl
   h[0] = (double)len;
   for (int a = 0; a < len; ++a) {
     double *m = h + 1 + 7 * a;
-    m[0] = e->hCharge[s + a];
+    m[0] = e->hChargeEff[s + a];  // Ewald terms see q * lambdaCoef
     m[1] = nx[a];
     m[2] = ny[a];
     m[3] = nz[a];
@@ -1076,9 +1099,14 @@ void mark_coords_dirty(gomcb200_engine *e) {
 template <int VDW>
 void launch_probe(gomcb200_engine *e, int b, const BoxParams &p, int excludeMol, int n) {
   BoxState &bx = e->box[b];
-  k_probe<VDW><<<n, kPairThreads, 0, e->stream>>>(p, bx.grid, excludeMol, e->probes.p,
-                                                 bx.cellStart.p, bx.sx.p, bx.sy.p, bx.sz.p,
-                                                 bx.sq.p, bx.skm.p, e->probeOut.p);
+  if (bx.lambdaMol >= 0)
+    k_probe<VDW, MODE_LAMBDA><<<n, kPairThreads, 0, e->stream>>>(
+        p, bx.grid, excludeMol, e->probes.p, bx.cellStart.p, bx.sx.p, bx.sy.p, bx.sz.p, bx.sq.p,
+        bx.skm.p, e->probeOut.p);
+  else
+    k_probe<VDW><<<n, kPairThreads, 0, e->stream>>>(p, bx.grid, excludeMol, e->probes.p,
+                                                   bx.cellStart.p, bx.sx.p, bx.sy.p, bx.sz.p,
+                                                   bx.sq.p, bx.skm.p, e->probeOut.p);
 }
 
 // probes staged in e->hStage as Probe[n]; results in e->hStage after the call
@@ -1118,11 +1146,20 @@ template <int VDW>
 void launch_trial(gomcb200_engine *e, int b, const BoxParams &p, const TrialArgs &a, int nBlocks) {
   BoxState &bx = e->box[b];
   KSet &ks = bx.kset[1 - bx.cur];
-  k_mol_trial<VDW><<<nBlocks, kPairThreads, 0, e->stream>>>(
-      p, bx.grid, a, bx.cellStart.p, bx.sx.p, bx.sy.p, bx.sz.p, bx.sq.p, bx.skm.p, ks.kx.p,
-      ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRref].p, bx.sum[bx.iIref].p,
-      bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p, e->trialPart.p, e->blockA.p, e->ticket.p,
-      e->dTrial, reinterpret_cast<volatile unsigned long long *>(e->dTrial + 8));
+  volatile unsigned long long *flag =
+      reinterpret_cast<volatile unsigned long long *>(e->dTrial + 8);
+  if (bx.lambdaMol >= 0)
+    k_mol_trial<VDW, MODE_LAMBDA><<<nBlocks, kPairThreads, 0, e->stream>>>(
+        p, bx.grid, a, bx.cellStart.p, bx.sx.p, bx.sy.p, bx.sz.p, bx.sq.p, bx.skm.p, ks.kx.p,
+        ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRref].p, bx.sum[bx.iIref].p,
+        bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p, e->trialPart.p, e->blockA.p, e->ticket.p,
+        e->dTrial, flag);
+  else
+    k_mol_trial<VDW><<<nBlocks, kPairThreads, 0, e->stream>>>(
+        p, bx.grid, a, bx.cellStart.p, bx.sx.p, bx.sy.p, bx.sz.p, bx.sq.p, bx.skm.p, ks.kx.p,
+        ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRref].p, bx.sum[bx.iIref].p,
+        bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p, e->trialPart.p, e->blockA.p, e->ticket.p,
+        e->dTrial, flag);
 }
 
 // One-launch single-molecule trial (trial.cuh), molecules of <= kTrialMaxAtoms atoms.
@@ -1157,6 +1194,7 @@ int run_trial_fused(gomcb200_engine *e, int b, int molIndex, const double *nx, c
   for (int i = 0; i < len; ++i) {
     a.kind[i] = e->hKind[s + i];
     a.q[i] = e->hCharge[s + i];
+    a.qr[i] = e->hChargeEff[s + i];
     a.nx[i] = nx[i];
     a.ny[i] = ny[i];
     a.nz[i] = nz[i];
@@ -1382,6 +1420,51 @@ int gomcb200_init_forcefield(gomcb200_engine *e, const double *sigmaSq,
   return 0;
 }
 
+int gomcb200_init_softcore(gomcb200_engine *e, double sc_alpha, double sc_sigma_6, int sc_power,
+                           int sc_coul) {
+  if (!e) return fail(GOMCB200_EINVAL, "bad arguments");
+  e->scAlpha = sc_alpha;
+  e->scSigma6 = sc_sigma_6;
+  e->scPower = (double)sc_power;
+  e->scCoul = sc_coul ? 1 : 0;
+  return 0;
+}
+
+int gomcb200_update_lambda(gomcb200_engine *e, int box, int molIndex, int molKind,
+                           double lambdaVDW, double lambdaCoulomb, int isFraction) {
+  if (!e || box < 0 || box >= e->nBoxes || !e->haveTopo)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  if (isFraction && (molIndex < 0 || molIndex >= e->nMols))
+    return fail(GOMCB200_EINVAL, "molecule index %d out of range", molIndex);
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  auto set_eff = [&](int m, double coef) -> int {
+    const int s = e->hMolStart[m], len = e->hMolStart[m + 1] - s;
+    for (int a = s; a < s + len; ++a) e->hChargeEff[a] = e->hCharge[a] * coef;
+    CK(cudaMemcpyAsync(e->qEff.p + s, e->hChargeEff.data() + s, sizeof(double) * (size_t)len,
+                       cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+  };
+  if (bx.lambdaMol >= 0) {
+    int rc = set_eff(bx.lambdaMol, 1.0);
+    if (rc) return rc;
+  }
+  if (isFraction) {
+    bx.lambdaMol = molIndex;
+    bx.lambdaMolKind = molKind;
+    bx.lambdaVDW = lambdaVDW;
+    bx.lambdaCoulomb = lambdaCoulomb;
+    int rc = set_eff(molIndex, std::sqrt(lambdaCoulomb));  // Ewald::GetLambdaCoef
+    if (rc) return rc;
+  } else {
+    bx.lambdaMol = bx.lambdaMolKind = -1;
+    bx.lambdaVDW = bx.lambdaCoulomb = 1.0;
+  }
+  bx.packedDirty = true;
+  return 0;
+}
+
 int gomcb200_init_exp6(gomcb200_engine *e, const double *rMin, const double *expConst,
                        const double *rMaxSq, int size) {
   if (!e || !rMin || !expConst || !rMaxSq) return fail(GOMCB200_EINVAL, "bad arguments");
@@ -1409,6 +1492,11 @@ int gomcb200_init_topology(gomcb200_engine *e, int nAtoms, int nMols, const int 
   e->hKind.assign(particleKind, particleKind + nAtoms);
   e->hMol.assign(particleMol, particleMol + nAtoms);
   e->hCharge.assign(particleCharge, particleCharge + nAtoms);
+  e->hChargeEff = e->hCharge;
+  for (auto &bx : e->box) {
+    bx.lambdaMol = bx.lambdaMolKind = -1;
+    bx.lambdaVDW = bx.lambdaCoulomb = 1.0;
+  }
   e->hMolStart.assign(molStart, molStart + nMols + 1);
   e->maxMolLen = 0;
   for (int m = 0; m < nMols; ++m)
@@ -1429,6 +1517,8 @@ int gomcb200_init_topology(gomcb200_engine *e, int nAtoms, int nMols, const int 
   CK(cudaMemcpy(e->kind.p, particleKind, nAtoms * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->mol.p, particleMol, nAtoms * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->q.p, particleCharge, nAtoms * sizeof(double), cudaMemcpyHostToDevice));
+  CK(e->qEff.reserve(na));
+  CK(cudaMemcpy(e->qEff.p, particleCharge, nAtoms * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(e->molStart.p, molStart, (nMols + 1) * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemset(e->comx.p, 0, e->comx.cap * sizeof(double)));
   CK(cudaMemset(e->comy.p, 0, e->comy.cap * sizeof(double)));
@@ -2166,7 +2256,7 @@ static int run_force_recip(gomcb200_engine *e, int box, const double *sumR, cons
       if (withIntra) {
         k_force_recip_intra<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
             p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p,
-            e->q.p, rfx, rfy, rfz);
+            e->qEff.p, rfx, rfy, rfz);
       } else {  // the DMMA kernel accumulates onto the buffers
         const size_t bytes = sizeof(double) * (size_t)e->nAtoms;
         CK(cudaMemsetAsync(rfx, 0, bytes, e->stream));
@@ -2190,7 +2280,7 @@ static int run_force_recip(gomcb200_engine *e, int box, const double *sumR, cons
   }
   if (!done) {
     k_force_recip_direct<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
-        p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->q.p,
+        p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->qEff.p,
         ks.n, ks.kx.p, ks.ky.p, ks.kz.p, ks.prefact.p, sumR, sumI, rfx, rfy, rfz,
         withIntra ? 1 : 0);
     e->launches += 1;
@@ -2412,7 +2502,7 @@ int gomcb200_virial_reciprocal(gomcb200_engine *e, int box, double wT[3]) {
                        false);
   if (rc) return rc;
   k_virial_recip_intra<<<ga, 256, 0, e->stream>>>(make_params(e, box), bx.nAtoms, bx.atomList.p,
-                                                 e->mol.p, e->x.p, e->y.p, e->z.p, e->q.p,
+                                                 e->mol.p, e->x.p, e->y.p, e->z.p, e->qEff.p,
                                                  e->scratchF[0].p, e->scratchF[1].p,
                                                  e->scratchF[2].p, e->blockB.p);
   const double *a = e->blockA.p, *b = e->blockB.p;
@@ -2552,9 +2642,10 @@ int gomcb200_box_self_correction(gomcb200_engine *e, int box, double *self, doub
   int nBlocks = (bx.nMols + 255) / 256;
   CK(e->blockA.reserve(nBlocks + 1024));
   CK(e->blockB.reserve(nBlocks + 1024));
-  k_self_correction<<<nBlocks, 256, 0, e->stream>>>(p, bx.nMols, bx.molList.p, e->molStart.p,
-                                                   e->x.p, e->y.p, e->z.p, e->q.p, e->blockA.p,
-                                                   e->blockB.p);
+  const bool selfQuirk = bx.lambdaMol >= 0 && bx.lambdaMol == bx.lambdaMolKind;
+  k_self_correction<<<nBlocks, 256, 0, e->stream>>>(
+      p, bx.nMols, bx.molList.p, e->molStart.p, e->x.p, e->y.p, e->z.p, e->q.p, e->blockA.p,
+      e->blockB.p, selfQuirk ? bx.lambdaMol : -1, bx.lambdaCoulomb, bx.lambdaCoulomb);
   k_final_reduce<<<1, 1024, 0, e->stream>>>(nBlocks, 2, e->blockA.p, e->blockB.p, nullptr,
                                            nullptr, e->result.p);
   e->launches += 2;

@@ -122,11 +122,13 @@ struct PairAcc {
 };
 // pair evaluation modes: energies; energies + forces; virial tensors
 // (acc.lj/real/fx = LJ diag 11/22/33, acc.fy/fz/ex = Coulomb diag 11/22/33)
-enum { MODE_ENERGY = 0, MODE_FORCE = 1, MODE_VIRIAL = 2 };
+// MODE_LAMBDA is OR-ed in when the box has a fractional molecule: only those
+// instantiations carry the soft-core branch, the usual kernels stay as lean as before.
+enum { MODE_ENERGY = 0, MODE_FORCE = 1, MODE_VIRIAL = 2, MODE_LAMBDA = 4 };
 
 enum { SWEEP_PROBE = 0, SWEEP_HALF = 1, SWEEP_FULL = 2 };
 
-template <int VDW, int MODE>
+template <int VDW, int MODEL>
 __device__ __forceinline__ void eval_pair(const BoxParams &p, int ki, double qi,
                                           int excludeMol, bool countEnergy,
                                           double sign, bool checkOverlap,
@@ -136,6 +138,49 @@ __device__ __forceinline__ void eval_pair(const BoxParams &p, int ki, double qi,
   double r2 = dist_sq(dx, dy, dz);
   if (checkOverlap && r2 < p.rCutLowSq) acc.overlap = 1;
   int idx = ki + kmj.x * p.kindCount;
+  constexpr int MODE = MODEL & 3;
+  constexpr bool LAM = (MODEL & MODE_LAMBDA) != 0;
+  // fractional molecule: GetLambdaVDW / GetLambdaCoulomb (src/CalculateEnergy.cpp:1558-1572);
+  // excludeMol is the molecule of the i atom / probe in every sweep
+  if (LAM && p.lambdaMol >= 0 && (excludeMol == p.lambdaMol || kmj.y == p.lambdaMol)) {
+    const double lv = p.lambdaVDW, lc = p.lambdaCoulomb;
+    if (MODE == MODE_ENERGY) {
+      if (p.electrostatic) {
+        double qq = qi * qj * kQQFact;
+        if (qq != 0.0) acc.real += sign * calc_coulomb_l<VDW>(p, r2, idx, qq, lc);
+      }
+      acc.lj += sign * calc_en_l<VDW>(p, r2, idx, lv);
+      return;
+    }
+    double eL, wL, eC = 0.0, wC = 0.0;
+    calc_en_vir_l<VDW>(p, r2, idx, lv, eL, wL);
+    if (p.electrostatic) {
+      double qq = qi * qj * (MODE == MODE_VIRIAL ? 1.0 : kQQFact);
+      if (qq != 0.0) calc_coulomb_en_vir_l<VDW>(p, r2, idx, qq, lc, eC, wC);
+    }
+    if (MODE == MODE_VIRIAL) {
+      double cx = acc.cix - p.comx[kmj.y], cy = acc.ciy - p.comy[kmj.y],
+             cz = acc.ciz - p.comz[kmj.y];
+      min_image_vec(p, cx, cy, cz);
+      const double t1 = dx * cx, t2 = dy * cy, t3 = dz * cz;
+      acc.lj += wL * t1;
+      acc.real += wL * t2;
+      acc.fx += wL * t3;
+      acc.fy += wC * t1;
+      acc.fz += wC * t2;
+      acc.ex += wC * t3;
+    } else {
+      if (countEnergy) {
+        acc.lj += eL;
+        acc.real += eC;
+      }
+      double w = wL + wC;
+      acc.fx += dx * w;
+      acc.fy += dy * w;
+      acc.fz += dz * w;
+    }
+    return;
+  }
   if (MODE == MODE_VIRIAL) {
     // CalculateEnergy::VirialCalc, src/CalculateEnergy.cpp:483-527
     double cx = acc.cix - p.comx[kmj.y], cy = acc.ciy - p.comy[kmj.y],
@@ -358,8 +403,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
                const int *__restrict__ sortedAtoms, double *__restrict__ partLJ,
                double *__restrict__ partReal, double *__restrict__ fx,
                double *__restrict__ fy, double *__restrict__ fz) {
-  constexpr bool FORCE = MODE == MODE_FORCE;
-  constexpr bool VIRIAL = MODE == MODE_VIRIAL;
+  constexpr bool FORCE = (MODE & 3) == MODE_FORCE;
+  constexpr bool VIRIAL = (MODE & 3) == MODE_VIRIAL;
   extern __shared__ __align__(16) unsigned char dynSmem[];
   __shared__ JRange ranges[27];
   __shared__ JRange stagedRanges[27];
@@ -596,7 +641,7 @@ struct Probe {
   int kind, checkOverlap, pad;
 };
 
-template <int VDW>
+template <int VDW, int MODE = MODE_ENERGY>
 __global__ void __launch_bounds__(kPairThreads)
     k_probe(BoxParams p, CellGrid g, int excludeMol,
             const Probe *__restrict__ probes, const int *__restrict__ cellStart,
@@ -614,7 +659,7 @@ __global__ void __launch_bounds__(kPairThreads)
   __syncthreads();
   PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0, 0.0, 0.0, 0.0, 0.0};
   JArrays ja = {sx, sy, sz, sq, skm, 0u, 0u, 0u, 0u, 0u};
-  warp_probe<VDW, false, SWEEP_PROBE, false, true>(
+  warp_probe<VDW, MODE, SWEEP_PROBE, false, true>(
       p, g.generic, pr.x, pr.y, pr.z, pr.kind, pr.q, excludeMol, -1, -1, pr.sign,
       pr.checkOverlap != 0, ranges, nRangesSh, kPairWarps, warp, ja, smem_u32(&queues[warp]),
       acc);

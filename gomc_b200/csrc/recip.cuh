@@ -410,7 +410,8 @@ __global__ void __launch_bounds__(256)
                       const double *__restrict__ x, const double *__restrict__ y,
                       const double *__restrict__ z, const double *__restrict__ q,
                       double *__restrict__ blockSelf,
-                      double *__restrict__ blockCorr) {
+                      double *__restrict__ blockCorr, int selfScaleMol, double selfScale,
+                      double corrScale) {
   __shared__ double scratch[32];
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   double self = 0.0, corr = 0.0;
@@ -427,6 +428,11 @@ __global__ void __launch_bounds__(256)
         corr += q[i] * q[j] * erf(p.alpha * dist) / dist;
       }
     }
+    // fractional molecule: MolCorrection scales by lambdaCoef^2 (src/Ewald.cpp:1084);
+    // BoxSelf by lambda, but only in the case its kind-for-molecule index mix-up lets
+    // through (:1140-1155) -- the host passes selfScaleMol = -1 otherwise
+    if (m == p.lambdaMol) corr *= corrScale;
+    if (m == selfScaleMol) self *= selfScale;
   }
   double a = block_sum(self, scratch);
   double b = block_sum(corr, scratch);

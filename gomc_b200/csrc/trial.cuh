@@ -26,13 +26,14 @@ struct TrialArgs {
   int doCorrection;  // SwapCorrection + SwapSelf of the new coordinates
   unsigned long long seq;
   int kind[kTrialMaxAtoms];
-  double q[kTrialMaxAtoms];
+  double q[kTrialMaxAtoms];   // true charges (pair part)
+  double qr[kTrialMaxAtoms];  // charge * lambdaCoef of the molecule (Ewald part)
   double nx[kTrialMaxAtoms], ny[kTrialMaxAtoms], nz[kTrialMaxAtoms];
   double ox[kTrialMaxAtoms], oy[kTrialMaxAtoms], oz[kTrialMaxAtoms];
 };
 
 // hostOut: {lj, real, overlap, recipNew, correction, self}
-template <int VDW>
+template <int VDW, int MODE = MODE_ENERGY>
 __global__ void __launch_bounds__(kPairThreads)
     k_mol_trial(BoxParams p, CellGrid g, const __grid_constant__ TrialArgs a,
                 const int *__restrict__ cellStart, const double *__restrict__ sx,
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kPairThreads)
     __syncthreads();
     PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0, 0.0, 0.0, 0.0, 0.0};
     JArrays ja = {sx, sy, sz, sq, skm, 0u, 0u, 0u, 0u, 0u};
-    warp_probe<VDW, false, SWEEP_PROBE, false, true>(
+    warp_probe<VDW, MODE, SWEEP_PROBE, false, true>(
         p, g.generic, px, py, pz, a.kind[at], a.q[at], a.excludeMol, -1, -1,
         isNew ? 1.0 : -1.0, isNew, ranges, nRangesSh, kPairWarps * kProbeSplit,
         sub * kPairWarps + warp, ja, smem_u32(&queues[warp]), acc);
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(kPairThreads)
       const double kxv = kx[k], kyv = ky[k], kzv = kz[k];
       double rn = 0.0, in = 0.0, ro = 0.0, io = 0.0;
       for (int at = 0; at < a.len; ++at) {
-        const double q = a.q[at];
-        if (fabs(q) < 0.000000001) continue;  // particleHasNoCharge
+        const double q = a.qr[at];
+        if (fabs(a.q[at]) < 0.000000001) continue;  // particleHasNoCharge
         double dn = __dadd_rn(__dadd_rn(__dmul_rn(a.nx[at], kxv), __dmul_rn(a.ny[at], kyv)),
                               __dmul_rn(a.nz[at], kzv));
         double s, c;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(kPairThreads)
       double dx = a.nx[i] - a.nx[j], dy = a.ny[i] - a.ny[j], dz = a.nz[i] - a.nz[j];
       min_image_vec(p, dx, dy, dz);
       double dist = sqrt(dx * dx + dy * dy + dz * dz);
-      corr -= a.q[i] * a.q[j] * erf(p.alpha * dist) / dist;
+      corr -= a.qr[i] * a.qr[j] * erf(p.alpha * dist) / dist;
     }
     for (int i = threadIdx.x; i < a.len; i += blockDim.x) self -= a.q[i] * a.q[i];
   }

@@ -46,6 +46,9 @@ _SIGS = {
     "gomcb200_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gomcb200_molecule_inter": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip]),
     "gomcb200_molecule_trial": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _dp]),
+    "gomcb200_init_softcore": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "gomcb200_update_lambda": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                         C.c_int]),
     "gomcb200_mp_transform": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                         C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_void_p]),
     "gomcb200_mp_get_trial": (C.c_int, [_vp, _dp, _dp, _dp, _ip]),
@@ -246,6 +249,16 @@ class Engine:
         self._ck(self.L.gomcb200_molecule_trial(self.h, box, mol_index, px, py, pz, C.byref(lj),
                                                 C.byref(re), C.byref(ov), C.byref(er)))
         return lj.value, re.value, bool(ov.value), er.value
+
+    def init_softcore(self, sc_alpha, sc_sigma_6, sc_power, sc_coul):
+        self._ck(self.L.gomcb200_init_softcore(self.h, float(sc_alpha), float(sc_sigma_6),
+                                               int(sc_power), int(sc_coul)))
+
+    def update_lambda(self, box, mol_index, mol_kind, lambda_vdw, lambda_coulomb,
+                      is_fraction=True):
+        self._ck(self.L.gomcb200_update_lambda(self.h, box, int(mol_index), int(mol_kind),
+                                               float(lambda_vdw), float(lambda_coulomb),
+                                               int(is_fraction)))
 
     def mp_transform(self, box, move_type, vmax, lambda_beta, step, key, seed, involved=None):
         ptr = None

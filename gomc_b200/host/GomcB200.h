@@ -70,6 +70,17 @@ public:
   void InitExp6(const double *rMin, const double *expConst, const double *rMaxSq, int size) {
     check(gomcb200_init_exp6(e_, rMin, expConst, rMaxSq, size), "InitExp6VariablesCUDA");
   }
+  // forcefield.sc_alpha / sc_sigma_6 / sc_power / sc_coul (src/Forcefield.cpp:58-75)
+  void InitSoftcore(double sc_alpha, double sc_sigma_6, int sc_power, bool sc_coul) {
+    check(gomcb200_init_softcore(e_, sc_alpha, sc_sigma_6, sc_power, sc_coul), "InitSoftcore");
+  }
+  // Lambda::Set / UnSet -> UpdateGPULambda (lib/Lambda.h:65-88)
+  void SetLambda(double vdw, double coulomb, int mol, int kind, int box) {
+    check(gomcb200_update_lambda(e_, box, mol, kind, vdw, coulomb, 1), "UpdateGPULambda");
+  }
+  void UnSetLambda(int box) {
+    check(gomcb200_update_lambda(e_, box, 0, 0, 1.0, 1.0, 0), "UpdateGPULambda");
+  }
   // CalculateEnergy::Init (src/CalculateEnergy.cpp:60-81)
   void InitTopology(const std::vector<int> &particleKind, const std::vector<int> &particleMol,
                     const std::vector<double> &particleCharge, const std::vector<int> &molStart) {

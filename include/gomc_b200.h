@@ -95,6 +95,20 @@ int gomcb200_init_forcefield(gomcb200_engine *e, const double *sigmaSq,
                              int ewald, int electrostatic,
                              double diElectric_1);
 
+/* Soft-core constants of the free-energy / NeMTMC functors (forcefield.sc_alpha,
+ * sc_sigma_6, sc_power, sc_coul; src/Forcefield.cpp:58-75) -- what the reference
+ * passes with every CallBoxInterGPU / CallBoxForceGPU call. */
+int gomcb200_init_softcore(gomcb200_engine *e, double sc_alpha, double sc_sigma_6,
+                           int sc_power, int sc_coul);
+/* UpdateGPULambda (ConstantDefinitionsCUDAKernel.cuh:31-33; lib/Lambda.h:65-88):
+ * the fractional molecule of a box.  Pair terms use lambdaVDW / lambdaCoulomb for
+ * pairs involving it (CalculateEnergy::GetLambdaVDW, src/CalculateEnergy.cpp:
+ * 1558-1572); every Ewald term sees its charges times sqrt(lambdaCoulomb)
+ * (Ewald::GetLambdaCoef, src/Ewald.cpp:1598-1602).  molKind is the molecule's kind
+ * index (BoxSelf compares it with the molecule index, :1140-1155).
+ * isFraction = 0 clears the state. */
+int gomcb200_update_lambda(gomcb200_engine *e, int box, int molIndex, int molKind,
+                           double lambdaVDW, double lambdaCoulomb, int isFraction);
 /* InitExp6VariablesCUDA, src/GPU/ConstantDefinitionsCUDAKernel.cuh:34-35:
  * the rMin / expConst / rMaxSq tables FF_EXP6::Init derives with Brent's method
  * (src/FFExp6.h:99-147); required before any energy call when vdwKind is EXP6. */

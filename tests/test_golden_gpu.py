@@ -39,6 +39,10 @@ def gold(request):
         e.set_box_cell_basis(0, d["box0.cellBasis"], d["box0.cellBasisInv"], d["box0.axis"])
     e.set_coords(*_xyz(d, "coords"))
     e.set_com(*_xyz(d, "com"))
+    if "lambda.params" in d:        # fractional molecule (free energy / NeMTMC state)
+        lp = d["lambda.params"]
+        e.init_softcore(lp[3], lp[4], int(lp[5]), int(lp[6]))
+        e.update_lambda(0, int(lp[0]), int(lp[7]), lp[1], lp[2])
     e.nk = 0
     if d["ff.ewald"][0]:
         e.nk = e.setup_ewald(d["box0.axis"], d["ff.recip_rcut"][:1])
@@ -202,9 +206,11 @@ def test_exchange_and_lambda_reciprocal(gold):
     ref = d["box0.sysPotRef.recip"][0]
     ms, q = d["molStart"], d["particleCharge"]
     xyz = _xyz(d, "coords")
+    lp = d.get("lambda.params")
+    coef = (lambda m: float(np.sqrt(lp[2])) if lp is not None and int(m) == int(lp[0]) else 1.0)
     calls = exchange_weights(q, ms, d["box0.exchange.mols"],
                              [_xyz(d, "box0.exchange0.newCoords"),
-                              _xyz(d, "box0.exchange1.newCoords")], xyz)
+                              _xyz(d, "box0.exchange1.newCoords")], xyz, coef)
     for c, (w, cx) in enumerate(calls):
         en = e.mol_exchange_reciprocal(0, w, *cx, first_call=(c == 0))
         want = d["box0.exchange.dRecip"][c] + ref
