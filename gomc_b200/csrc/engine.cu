@@ -2327,9 +2327,29 @@ static int mp_reserve(gomcb200_engine *e) {
   return 0;
 }
 
+static int mp_transform_impl(gomcb200_engine *e, int box, int brownian, int moveType,
+                             double max, double lambdaBETA, unsigned long long step,
+                             unsigned int key, unsigned long long seed,
+                             const signed char *isMoleculeInvolved);
+
 int gomcb200_mp_transform(gomcb200_engine *e, int box, int moveType, double max,
                           double lambdaBETA, unsigned long long step, unsigned int key,
                           unsigned long long seed, const signed char *isMoleculeInvolved) {
+  return mp_transform_impl(e, box, 0, moveType, max, lambdaBETA, step, key, seed,
+                           isMoleculeInvolved);
+}
+
+int gomcb200_bm_transform(gomcb200_engine *e, int box, int moveType, double max, double BETA,
+                          unsigned long long step, unsigned int key, unsigned long long seed,
+                          const signed char *isMoleculeInvolved) {
+  return mp_transform_impl(e, box, 1, moveType, max, BETA, step, key, seed,
+                           isMoleculeInvolved);
+}
+
+static int mp_transform_impl(gomcb200_engine *e, int box, int brownian, int moveType,
+                             double max, double lambdaBETA, unsigned long long step,
+                             unsigned int key, unsigned long long seed,
+                             const signed char *isMoleculeInvolved) {
   int rc = check_box(e, box);
   if (rc) return rc;
   if (moveType < 0 || moveType > 1) return fail(GOMCB200_EINVAL, "moveType must be 0 or 1");
@@ -2351,6 +2371,7 @@ int gomcb200_mp_transform(gomcb200_engine *e, int box, int moveType, double max,
   for (int c = 0; c < 3; ++c) CK(cudaMemsetAsync(e->mpK[c].p, 0, bm, e->stream));
   if (bx.nMols == 0) return 0;
   MpArgs a;
+  a.brownian = brownian;
   a.moveType = moveType;
   a.nMolsBox = bx.nMols;
   a.max = max;
@@ -2453,6 +2474,38 @@ int gomcb200_mp_coeff(gomcb200_engine *e, int box, int moveType, double max, dou
       rec ? e->force[rw][1].p : nullptr, rec ? e->force[rw][2].p : nullptr, e->mpK[0].p,
       e->mpK[1].p, e->mpK[2].p, e->blockA.p);
   k_mp_coeff_final<<<1, 256, 0, e->stream>>>(nb, e->blockA.p, e->result.p);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  rc = fetch_result(e, 1);
+  if (rc) return rc;
+  *wRatio = e->hRes[0];
+  return 0;
+}
+
+int gomcb200_bm_coeff(gomcb200_engine *e, int box, int moveType, double max, double BETA,
+                      double *wRatio) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (!wRatio || moveType < 0 || moveType > 1) return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!e->trialActive)
+    return fail(GOMCB200_EINVAL, "needs the trial set active (new forces computed on it)");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  *wRatio = 0.0;
+  if (bx.nMols == 0) return 0;
+  const int nb = (bx.nMols + 255) / 256;
+  CK(e->blockA.reserve(nb + 1024));
+  const int fw = moveType == 1 ? GOMCB200_MOL_TORQUE : GOMCB200_MOL_FORCE;
+  const int rw = GOMCB200_MOL_FORCE_REC;
+  const bool rec = moveType == 0;
+  k_bm_coeff<<<nb, 256, 0, e->stream>>>(
+      bx.nMols, bx.molList.p, max, BETA, e->forceT[fw][0].p, e->forceT[fw][1].p,
+      e->forceT[fw][2].p, rec ? e->forceT[rw][0].p : nullptr, rec ? e->forceT[rw][1].p : nullptr,
+      rec ? e->forceT[rw][2].p : nullptr, e->force[fw][0].p, e->force[fw][1].p,
+      e->force[fw][2].p, rec ? e->force[rw][0].p : nullptr, rec ? e->force[rw][1].p : nullptr,
+      rec ? e->force[rw][2].p : nullptr, e->mpK[0].p, e->mpK[1].p, e->mpK[2].p, e->blockA.p);
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(nb, 1, e->blockA.p, nullptr, nullptr, nullptr,
+                                           e->result.p);
   e->launches += 2;
   CK(cudaGetLastError());
   rc = fetch_result(e, 1);

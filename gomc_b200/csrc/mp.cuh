@@ -73,6 +73,7 @@ __device__ __forceinline__ void wrap_vec(const BoxParams &p, double &x, double &
 }
 
 struct MpArgs {
+  int brownian;  // 0: MultiParticle (force-biased, range test); 1: MultiParticleBrownian
   int moveType;  // 0 displace (mp::MPDISPLACE), 1 rotate (mp::MPROTATE)
   int nMolsBox;
   double max, lambdaBeta;
@@ -106,9 +107,26 @@ __global__ void __launch_bounds__(128) k_mp_transform(BoxParams p, MpArgs a) {
     inRange = inRange && fabs(lbmax[d]) > 1E-12 && fabs(lbmax[d]) < 30;
   }
   const Philox4 r = philox4x64_10((unsigned long long)m, a.key, a.step, a.seed);
-  if (inRange)
+  if (a.brownian) {
+    // MultiParticleBrownian::CalcRandomTransform: lb * max + N(0, sqrt(2 max)), variates of
+    // Random123Wrapper::GetGaussianCoords (Box-Muller, lib/Random123/boxmuller.hpp:126-137);
+    // lambdaBeta carries BETA here, every molecule takes the force-biased branch
+    inRange = true;
+    const double PI = 3.1415926535897932;
+    const double stdDev = sqrt(2.0 * a.max);
+    double s0, c0, s1, c1;
+    sincos(PI * r123_uneg11(r.v[0]), &s0, &c0);
+    sincos(PI * r123_uneg11(r.v[2]), &s1, &c1);
+    const double rad0 = sqrt(-2. * log(r123_u01(r.v[1])));
+    const double rad1 = sqrt(-2. * log(r123_u01(r.v[3])));
+    (void)c1;
+    val[0] = lbmax[0] + (s0 * rad0) * stdDev;
+    val[1] = lbmax[1] + (c0 * rad0) * stdDev;
+    val[2] = lbmax[2] + (s1 * rad1) * stdDev;
+  } else if (inRange) {
     for (int d = 0; d < 3; ++d)
       val[d] = log(exp(-1.0 * lbmax[d]) + 2.0 * r123_u01(r.v[d]) * sinh(lbmax[d])) / lb[d];
+  }
   a.kx[m] = val[0];
   a.ky[m] = val[1];
   a.kz[m] = val[2];
@@ -214,6 +232,43 @@ __global__ void __launch_bounds__(256)
   }
   if (threadIdx.x == 0) part[blockIdx.x] = sm[0];
 }
+// MultiParticleBrownian::GetCoeff (log of the weight ratio): sum over the molecules of
+// (|old*BETA*max - k|^2 - |new*BETA*max + k|^2) / (4 max); part[block].
+__global__ void __launch_bounds__(256)
+    k_bm_coeff(int nMolsBox, const int *__restrict__ molList, double max, double beta,
+               const double *ofx, const double *ofy, const double *ofz, const double *orx,
+               const double *ory, const double *orz, const double *nfx, const double *nfy,
+               const double *nfz, const double *nrx, const double *nry, const double *nrz,
+               const double *__restrict__ kx, const double *__restrict__ ky,
+               const double *__restrict__ kz, double *__restrict__ part) {
+  __shared__ double scratch[32];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double w = 0.0;
+  if (t < nMolsBox) {
+    const int m = molList[t];
+    double o[3] = {ofx[m], ofy[m], ofz[m]}, n[3] = {nfx[m], nfy[m], nfz[m]};
+    if (orx) {
+      o[0] += orx[m];
+      o[1] += ory[m];
+      o[2] += orz[m];
+      n[0] += nrx[m];
+      n[1] += nry[m];
+      n[2] += nrz[m];
+    }
+    const double k[3] = {kx[m], ky[m], kz[m]};
+    double so = 0.0, sn = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      const double ov = o[d] * beta * max - k[d], nv = n[d] * beta * max + k[d];
+      so += ov * ov;
+      sn += nv * nv;
+    }
+    const double max4 = 4.0 * max;
+    w = so / max4 - sn / max4;
+  }
+  double s = block_sum(w, scratch);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
 __global__ void k_mp_coeff_final(int n, const double *__restrict__ part, double *out) {
   __shared__ double sm[256];
   double w = 1.0;

@@ -51,6 +51,9 @@ _SIGS = {
                                          C.c_int]),
     "gomcb200_mp_transform": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double,
                                         C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_void_p]),
+    "gomcb200_bm_transform": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double,
+                                        C.c_ulonglong, C.c_uint, C.c_ulonglong, C.c_void_p]),
+    "gomcb200_bm_coeff": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
     "gomcb200_mp_get_trial": (C.c_int, [_vp, _dp, _dp, _dp, _ip]),
     "gomcb200_mp_select": (C.c_int, [_vp, C.c_int]),
     "gomcb200_mp_coeff": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, _dp]),
@@ -268,6 +271,16 @@ class Engine:
         self._ck(self.L.gomcb200_mp_transform(self.h, box, int(move_type), float(vmax),
                                               float(lambda_beta), int(step), int(key),
                                               int(seed), ptr))
+
+    def bm_transform(self, box, move_type, vmax, beta, step, key, seed):
+        self._ck(self.L.gomcb200_bm_transform(self.h, box, int(move_type), float(vmax),
+                                              float(beta), int(step), int(key), int(seed), None))
+
+    def bm_coeff(self, box, move_type, vmax, beta):
+        w = C.c_double()
+        self._ck(self.L.gomcb200_bm_coeff(self.h, box, int(move_type), float(vmax), float(beta),
+                                          C.byref(w)))
+        return w.value
 
     def mp_get_trial(self, n_mols):
         k = [np.zeros(n_mols) for _ in range(3)]

@@ -489,12 +489,33 @@ public:
       check(gomcb200_mp_select(eng_.get(), 0), "mp_select");
   }
 
-private:
+protected:
   EngineB200 &eng_;
   CalculateEnergy &calcEn_;
   Ewald &calcEwald_;
   double BETA_, lambda_ = 0.5, max_ = 0.0, refInter_ = 0.0, refReal_ = 0.0;
   int bPick_ = 0, moveType_ = 0;
+};
+
+// MultiParticleBrownian (src/moves/MultiParticleBrownianMotion.h): Gaussian trial
+// transform, GetCoeff returns the logarithm of the weight ratio (accept with
+// exp(-BETA * dU + MPCoeff), :480-484).
+class MultiParticleBrownian : public MultiParticle {
+public:
+  using MultiParticle::MultiParticle;
+  void Transform(double t_max, double r_max, unsigned long long step, unsigned int key,
+                 unsigned long long seed, const signed char *isMoleculeInvolved = nullptr) {
+    max_ = moveType_ == MPROTATE ? r_max : t_max;
+    check(gomcb200_bm_transform(eng_.get(), bPick_, moveType_, max_, BETA_, step, key, seed,
+                                isMoleculeInvolved),
+          moveType_ == MPROTATE ? "BrownianMotionRotateParticlesGPU"
+                                : "BrownianMotionTranslateParticlesGPU");
+  }
+  double GetCoeff() const {
+    double w = 0.0;
+    check(gomcb200_bm_coeff(eng_.get(), bPick_, moveType_, max_, BETA_, &w), "GetCoeff");
+    return w;
+  }
 };
 
 }  // namespace gomc_b200

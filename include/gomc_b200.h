@@ -262,6 +262,18 @@ int gomcb200_mp_transform(gomcb200_engine *e, int box, int moveType, double max,
                           double lambdaBETA, unsigned long long step,
                           unsigned int key, unsigned long long seed,
                           const signed char *isMoleculeInvolved);
+/* BrownianMotionTranslateParticlesGPU / BrownianMotionRotateParticlesGPU
+ * (src/GPU/TransformParticlesCUDAKernel.cuh:40-52) == MultiParticleBrownian::
+ * CalculateTrialDistRot, src/moves/MultiParticleBrownianMotion.h: k = force*BETA*max
+ * + N(0, sqrt(2 max)) (Box-Muller on the same Philox stream), every molecule moved.
+ * gomcb200_bm_coeff is MultiParticleBrownian::GetCoeff (the LOG of the weight
+ * ratio).  Trial state handling as for gomcb200_mp_transform. */
+int gomcb200_bm_transform(gomcb200_engine *e, int box, int moveType, double max,
+                          double BETA, unsigned long long step, unsigned int key,
+                          unsigned long long seed,
+                          const signed char *isMoleculeInvolved);
+int gomcb200_bm_coeff(gomcb200_engine *e, int box, int moveType, double max,
+                      double BETA, double *wRatio);
 /* t_k / r_k (nMols each) and inForceRange (nMols) of the last transform. */
 int gomcb200_mp_get_trial(gomcb200_engine *e, double *kx, double *ky, double *kz,
                           int *inForceRange);

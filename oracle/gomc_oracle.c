@@ -995,6 +995,86 @@ int orc_mp_transform(const orc_params *p, int moveType, int nBoxMols, const int 
   return 0;
 }
 
+/* MultiParticleBrownian::CalculateTrialDistRot, src/moves/MultiParticleBrownianMotion.h:
+ * val = (force or torque) * BETA * max + N(0, sqrt(2 max)) with Random123Wrapper::
+ * GetGaussianCoords (two Box-Muller pairs, lib/Random123/boxmuller.hpp:126-137), then the
+ * same rigid translate / rotate as above; no force range test. */
+int orc_bm_transform(const orc_params *p, int moveType, int nBoxMols, const int *boxMols,
+                     const int *molStart, const double *fx, const double *fy,
+                     const double *fz, const double *rfx, const double *rfy,
+                     const double *rfz, double max, double beta, uint64_t step,
+                     uint64_t seed, uint64_t keyValue, double *kX, double *kY, double *kZ,
+                     double *nx, double *ny, double *nz, double *ncx, double *ncy,
+                     double *ncz) {
+  const double PI = 3.1415926535897932; /* boxmuller.hpp:104 */
+  for (int mi = 0; mi < nBoxMols; ++mi) {
+    int m = boxMols[mi];
+    double f[3] = {fx[m], fy[m], fz[m]};
+    if (rfx) {
+      f[0] += rfx[m];
+      f[1] += rfy[m];
+      f[2] += rfz[m];
+    }
+    double lb[3] = {f[0] * beta, f[1] * beta, f[2] * beta};
+    double stdDev = sqrt(2.0 * max);
+    uint64_t r[4];
+    mp_rng((uint64_t)m, keyValue, step, seed, r);
+    double a0 = PI * r123_uneg11(r[0]), a1 = PI * r123_uneg11(r[2]);
+    double rad0 = sqrt(-2. * log(r123_u01(r[1]))), rad1 = sqrt(-2. * log(r123_u01(r[3])));
+    double g[3] = {sin(a0) * rad0, cos(a0) * rad0, sin(a1) * rad1};
+    double val[3];
+    for (int d = 0; d < 3; ++d) val[d] = lb[d] * max + (0.0 + g[d] * stdDev);
+    kX[m] = val[0];
+    kY[m] = val[1];
+    kZ[m] = val[2];
+    double com[3] = {ncx[m], ncy[m], ncz[m]};
+    if (moveType == 1) {
+      double rotLen = sqrt(val[0] * val[0] + val[1] * val[1] + val[2] * val[2]);
+      double inv = 1.0 / rotLen;
+      double axis[3] = {val[0] * inv, val[1] * inv, val[2] * inv};
+      double mat[3][3];
+      axis_angle(rotLen, axis, mat);
+      mp_rotate_mol(p, molStart[m], molStart[m + 1], mat, com, nx, ny, nz);
+    } else {
+      mp_translate_mol(p, molStart[m], molStart[m + 1], val, m, nx, ny, nz, ncx, ncy, ncz);
+    }
+  }
+  return 0;
+}
+
+/* MultiParticleBrownian::GetCoeff / CalculateWRatio (same file, :415-472): a sum (the
+ * logarithm of the weight ratio), one OpenMP + reduction. */
+double orc_bm_coeff(int nBoxMols, const int *boxMols, const double *ofx, const double *ofy,
+                    const double *ofz, const double *orx, const double *ory,
+                    const double *orz, const double *nfx, const double *nfy,
+                    const double *nfz, const double *nrx, const double *nry,
+                    const double *nrz, const double *kX, const double *kY,
+                    const double *kZ, double max, double beta) {
+  double max4 = 4.0 * max;
+  double priv = 0.0;
+  for (int mi = 0; mi < nBoxMols; ++mi) {
+    int m = boxMols[mi];
+    double o[3] = {ofx[m], ofy[m], ofz[m]}, n[3] = {nfx[m], nfy[m], nfz[m]};
+    if (orx) {
+      o[0] += orx[m]; o[1] += ory[m]; o[2] += orz[m];
+      n[0] += nrx[m]; n[1] += nry[m]; n[2] += nrz[m];
+    }
+    double k[3] = {kX[m], kY[m], kZ[m]};
+    double ov[3], nv[3];
+    for (int d = 0; d < 3; ++d) {
+      ov[d] = o[d] * beta * max - k[d];
+      nv[d] = n[d] * beta * max + k[d];
+    }
+    double w = 0.0;
+    w -= ((nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]) / max4);
+    w += ((ov[0] * ov[0] + ov[1] * ov[1] + ov[2] * ov[2]) / max4);
+    priv += w;
+  }
+  double w_ratio = 0.0;
+  w_ratio += priv;
+  return w_ratio;
+}
+
 /* MultiParticle::CalculateWRatio / GetCoeff, src/moves/MultiParticle.h:443-513
  * (one OpenMP product reduction: private copy starts at 1, then multiplies w_ratio) */
 double orc_mp_coeff(int nBoxMols, const int *boxMols, const int *inForceRange,

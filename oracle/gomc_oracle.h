@@ -237,6 +237,21 @@ int orc_mp_transform(const orc_params *p, int moveType, int nBoxMols, const int 
                      uint64_t step, uint64_t seed, uint64_t keyValue, double *kX,
                      double *kY, double *kZ, int *inForceRange, double *nx, double *ny,
                      double *nz, double *ncx, double *ncy, double *ncz);
+/* MultiParticleBrownian (src/moves/MultiParticleBrownianMotion.h): trial transform
+ * (:CalculateTrialDistRot, Gaussian variates) and GetCoeff (log of the weight ratio). */
+int orc_bm_transform(const orc_params *p, int moveType, int nBoxMols, const int *boxMols,
+                     const int *molStart, const double *fx, const double *fy,
+                     const double *fz, const double *rfx, const double *rfy,
+                     const double *rfz, double max, double beta, uint64_t step,
+                     uint64_t seed, uint64_t keyValue, double *kX, double *kY, double *kZ,
+                     double *nx, double *ny, double *nz, double *ncx, double *ncy,
+                     double *ncz);
+double orc_bm_coeff(int nBoxMols, const int *boxMols, const double *ofx, const double *ofy,
+                    const double *ofz, const double *orx, const double *ory,
+                    const double *orz, const double *nfx, const double *nfy,
+                    const double *nfz, const double *nrx, const double *nry,
+                    const double *nrz, const double *kX, const double *kY,
+                    const double *kZ, double max, double beta);
 /* MultiParticle::GetCoeff, src/moves/MultiParticle.h:460-513 (o* old, n* new
  * forces or torques; *r* the reciprocal parts, NULL for rotation). */
 double orc_mp_coeff(int nBoxMols, const int *boxMols, const int *inForceRange,

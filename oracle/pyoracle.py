@@ -239,6 +239,37 @@ class Oracle:
             *[a.ctypes.data_as(_dp) for a in new], *[a.ctypes.data_as(_dp) for a in ncm])
         return k, inr, new, ncm
 
+    def bm_transform(self, move_type, box_mols, mol_start, xyz, com, f, rf, vmax, beta, step,
+                     seed, key):
+        """MultiParticleBrownian trial transform: returns (k, newXYZ, newCOM)."""
+        (bm, pbm), (ms, pms) = _i(box_mols), _i(mol_start)
+        n_mols = len(ms) - 1
+        new = [np.array(a, dtype=np.float64, copy=True) for a in xyz]
+        ncm = [np.array(a, dtype=np.float64, copy=True) for a in com]
+        fa = [_d(a) for a in f]
+        ra = [_d(a) for a in rf] if rf is not None else None
+        k = [np.zeros(n_mols) for _ in range(3)]
+        u64 = C.c_uint64
+        self.L.orc_bm_transform(
+            self.pp, C.c_int(move_type), C.c_int(len(bm)), pbm, pms, *[a[1] for a in fa],
+            *([a[1] for a in ra] if ra else [None] * 3), C.c_double(vmax), C.c_double(beta),
+            u64(int(step)), u64(int(seed)), u64(int(key)), *[a.ctypes.data_as(_dp) for a in k],
+            *[a.ctypes.data_as(_dp) for a in new], *[a.ctypes.data_as(_dp) for a in ncm])
+        return k, new, ncm
+
+    def bm_coeff(self, box_mols, old_f, old_rf, new_f, new_rf, k, vmax, beta):
+        (bm, pbm) = _i(box_mols)
+        def ptrs(v):
+            if v is None:
+                return [None] * 3, []
+            a = [_d(t) for t in v]
+            return [t[1] for t in a], a
+        po, k1 = ptrs(old_f); pr, k2 = ptrs(old_rf); pn, k3 = ptrs(new_f); pq, k4 = ptrs(new_rf)
+        pk, k5 = ptrs(k)
+        self.L.orc_bm_coeff.restype = C.c_double
+        return self.L.orc_bm_coeff(C.c_int(len(bm)), pbm, *po, *pr, *pn, *pq, *pk,
+                                   C.c_double(vmax), C.c_double(beta))
+
     def mp_coeff(self, box_mols, in_force_range, old_f, old_rf, new_f, new_rf, k, vmax, lam,
                  beta):
         (bm, pbm), (ir, pir) = _i(box_mols), _i(in_force_range)

@@ -49,6 +49,7 @@
 #include "BoxDimensionsNonOrth.h"
 #include "TrialMol.h"
 #include "MultiParticle.h"
+#include "MultiParticleBrownianMotion.h"
 #undef private
 #undef protected
 
@@ -502,6 +503,64 @@ int run_golden(int argc, char **argv) {
         // reject: restore the cell list (Accept's else branch, :537-539)
         sys.cellList.GridAll(sys.boxDimRef, sys.coordinates, sys.molLookupRef);
         ew.exgMolCache();
+      }
+    }
+
+    // ---- MultiParticleBrownian move (same driving pattern) --------------------
+    if (b == 0 && sys.moves[mv::MULTIPARTICLE_BM] != NULL) {
+      MultiParticleBrownian *bm =
+          static_cast<MultiParticleBrownian *>(sys.moves[mv::MULTIPARTICLE_BM]);
+      const int nTypes = bm->allTranslate ? 1 : 2;
+      for (int type = 0; type < nTypes; ++type) {
+        const char *tn = type == mp::MPROTATE ? "bmRotate" : "bmDisplace";
+        std::string pre = std::string(tn) + ".";
+        ulong step = 5151 + 13 * type;
+        sys.r123wrapper.SetStep(step);
+        bm->bPick = b;
+        bm->moveType = type;
+        bm->SetMolInBox(b);
+        if (ff.ewald) {
+          ew.CopyRecip(b);
+          ew.BoxForceReciprocal(sys.coordinates, sys.atomForceRecRef,
+                                sys.molForceRecRef, b);
+        }
+        ce.BoxForce(sys.potential, sys.coordinates, sys.atomForceRef,
+                    sys.molForceRef, sys.boxDimRef, b);
+        ce.CalculateTorque(bm->moleculeIndex, sys.coordinates, sys.com,
+                           sys.atomForceRef, sys.atomForceRecRef,
+                           bm->molTorqueRef, b);
+        sys.coordinates.CopyRange(bm->newMolsPos, 0, 0, sys.coordinates.Count());
+        sys.com.CopyRange(bm->newCOMs, 0, 0, sys.com.Count());
+        bm->CalculateTrialDistRot();
+        double par[6] = {bm->moveSetRef.GetTMAX(b), bm->moveSetRef.GetRMAX(b),
+                         bm->BETA, (double)step,
+                         (double)sys.r123wrapper.GetSeedValue(),
+                         (double)sys.r123wrapper.GetKeyValue()};
+        out.f64(bname((pre + "params").c_str(), b), par, 6);
+        out.xyz(bname((pre + "molTorqueRef").c_str(), b), bm->molTorqueRef);
+        out.xyz(bname((pre + "k").c_str(), b), type == mp::MPROTATE ? bm->r_k : bm->t_k);
+        out.xyz(bname((pre + "newMolsPos").c_str(), b), bm->newMolsPos);
+        out.xyz(bname((pre + "newCOMs").c_str(), b), bm->newCOMs);
+        // without a force-range test a badly overlapping start configuration can
+        // throw a molecule further than one box length (WrapPBC wraps once); the
+        // reference's cell list aborts on that, so the energy part is skipped then
+        bool inside = true;
+        XYZ ax2 = sys.boxDimRef.GetAxis(b);
+        for (uint a = 0; a < bm->newMolsPos.Count() && inside; ++a) {
+          XYZ u = bm->newMolsPos.Get(a);
+          if (!sys.boxDimRef.orthogonal[b])
+            u = static_cast<BoxDimensionsNonOrth &>(sys.boxDimRef).TransformUnSlant(u, b);
+          inside = u.x >= 0 && u.x < ax2.x && u.y >= 0 && u.y < ax2.y && u.z >= 0 && u.z < ax2.z;
+        }
+        if (inside) {
+          bm->CalcEn();
+          out.f64(bname((pre + "wRatio").c_str(), b), bm->GetCoeff());
+          out.xyz(bname((pre + "molForceNew").c_str(), b), bm->molForceNew);
+          out.xyz(bname((pre + "molForceRecNew").c_str(), b), bm->molForceRecNew);
+          out.xyz(bname((pre + "molTorqueNew").c_str(), b), bm->molTorqueNew);
+          sys.cellList.GridAll(sys.boxDimRef, sys.coordinates, sys.molLookupRef);
+          ew.exgMolCache();
+        }
       }
     }
 

@@ -194,6 +194,65 @@ def test_multiparticle_move(gold, kind):
         assert np.array_equal(a, d["coords." + c])
 
 
+@pytest.mark.parametrize("kind", ["bmDisplace", "bmRotate"])
+def test_brownian_multiparticle_move(gold, kind):
+    d, e = gold
+    pre = f"box0.{kind}."
+    if pre + "params" not in d:
+        pytest.skip("no such move in this fixture")
+    tmax, rmax, beta, step, seed, key = d[pre + "params"]
+    rot = kind == "bmRotate"
+    vmax = rmax if rot else tmax
+    bm = d["box0.mols"]
+    ewald = bool(d["ff.ewald"][0])
+    if ewald:
+        e.box_reciprocal_sums(0)
+        e.set_recip_ref(0)
+        e.copy_recip(0)
+        e.box_force_reciprocal(0)
+    e.box_force(0)
+    e.calculate_torque(0)
+    e.bm_transform(0, int(rot), vmax, beta, int(step), int(key), int(seed))
+    k, _ = e.mp_get_trial(e.n_mols)
+    for c, a in zip("xyz", k):
+        assert rel_err(a[bm], d[pre + "k." + c][bm]) <= TOL
+    e.mp_select(1)
+    try:
+        _check_bm_trial(d, e, pre, rot, vmax, beta, bm, ewald)
+    finally:
+        e.mp_select(0)                        # never leave the module fixture on the trial set
+    for c, a in zip("xyz", e.get_coords()):
+        assert np.array_equal(a, d["coords." + c])
+
+
+def _check_bm_trial(d, e, pre, rot, vmax, beta, bm, ewald):
+    orth = bool(int(d["box0.orthogonal"][0]))
+    for c, a, cm, L in zip("xyz", e.get_coords(), e.get_com(), d["box0.axis"]):
+        dx = a - d[pre + "newMolsPos." + c]
+        dc = cm - d[pre + "newCOMs." + c]
+        if orth:
+            dx -= L * np.round(dx / L)
+            dc -= L * np.round(dc / L)
+        # displacements scale with force * BETA * max: compare relative to their size
+        scale = max(L, float(np.max(np.abs(d[pre + "k." + c][bm]))))
+        assert np.max(np.abs(dx)) <= TOL * scale and np.max(np.abs(dc)) <= TOL * scale
+    if pre + "wRatio" in d:
+        if ewald:
+            e.box_reciprocal_sums(0)
+        e.box_force(0)
+        if ewald:
+            e.box_force_reciprocal(0)
+        e.calculate_torque(0)
+        w, want = e.bm_coeff(0, int(rot), vmax, beta), d[pre + "wRatio"][0]
+        kmax = max(float(np.max(np.abs(d[pre + "k." + c][bm]))) for c in "xyz")
+        if not np.isfinite(want):
+            assert w == want                  # EXP6 overlap: -inf on both sides
+        elif kmax < 1e3:
+            assert abs(w - want) <= 1e-8 * max(abs(want), 1.0)
+        # else: the start configuration's forces are astronomically large (overlapping
+        # Martini beads) and a rotation by ~1e11 rad is ill-conditioned in any arithmetic
+
+
 def test_exchange_and_lambda_reciprocal(gold):
     """MolExchangeReciprocal (two chained calls), ChangeLambdaRecip, ChangeRecip."""
     from tests.test_oracle_golden import exchange_weights
