@@ -426,7 +426,7 @@ def main():
     # secondary metric of BASELINE.json: MultiParticle moves/s = the energy/force work of
     # MultiParticle::CalcEn (src/moves/MultiParticle.h:414-441): BoxReciprocalSums + BoxForce
     # + BoxReciprocal + BoxForceReciprocal + torque, coordinates resident (single GPU)
-    mp_ms = None
+    mp_ms = mp_move_ms = None
     if world == 1 and s.ff.ewald:
         def mp_step():
             e.L.gomcb200_mark_coords_changed(e.h)
@@ -445,6 +445,32 @@ def main():
             mp_step()
             t_mp.append((time.perf_counter() - t0) * 1e3)
         mp_ms = float(np.mean(t_mp))
+        # whole MultiParticle move on the device: trial transform (Philox), CalcEn on the
+        # trial set, acceptance weight, reject (pointer exchange back)
+        e.set_com(*s.com())
+        e.copy_recip(0)
+        mp_step()                                    # reference forces / torques
+
+        def mp_move(i):
+            e.mp_transform(0, i & 1, 0.02, 0.5 / 300.0, 1000 + i, 0, 123)
+            e.mp_select(1)
+            e.box_reciprocal_sums(0)
+            e.box_force(0)
+            e.box_force_reciprocal(0)
+            e.calculate_torque(0)
+            w = e.mp_coeff(0, i & 1, 0.02, 0.5 / 300.0)
+            e.mp_select(0)
+            return w
+        for i in range(2):
+            mp_move(i)
+        t_mv = []
+        for i in range(max(5, args.steps // 2)):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mp_move(i)
+            t_mv.append((time.perf_counter() - t0) * 1e3)
+        mp_move_ms = float(np.mean(t_mv))
     clocks = sampler.stop() if rank == 0 else None
     extras = None
     if world == 1 and args.workload == "spce100k" and not args.no_extras:
@@ -492,7 +518,10 @@ def main():
                 "value": 1e3 / mp_ms, "unit": "MP energy/force evaluations per s",
                 "ms_per_step": mp_ms,
                 "step": "BoxReciprocalSums + BoxForce + BoxReciprocal + BoxForceReciprocal + "
-                        "CalculateTorque (MultiParticle::CalcEn), wall clock incl. launches"}),
+                        "CalculateTorque (MultiParticle::CalcEn), wall clock incl. launches",
+                "full_move_ms": mp_move_ms,
+                "full_move": "device trial transform + CalcEn on the trial set + GetCoeff + "
+                             "reject, coordinates never leave the GPU"}),
             "small_box": extras,
             "energies": {"lj": en_res[0], "real": en_res[1], "recip": en_res[2],
                          "host_path_identical": en_res == en_host},
