@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -23,6 +24,7 @@
 #include "trial.cuh"
 #include "mp.cuh"
 #include "recip_mma.cuh"
+#include "recip_i8.cuh"
 #include "force_mma.cuh"
 
 using namespace gb;
@@ -84,6 +86,9 @@ struct KSet {
   DevBuf<int4> mmaRows, mmaTiles, mmaSegs;
   DevBuf<int> mmaCtaSeg;
   std::vector<int4> hMmaTiles, hRowsSorted, hSegs;
+  // int8 tensor-core path (recip_i8.cuh): tiles of 64 rows x 32 c values
+  DevBuf<int4> i8Tiles, i8Rows;
+  int i8NTiles = 0, i8NCB = 0, i8NSL = 6, i8CPer = 32, i8Nb = 64;
   // DMMA reciprocal-force plan (force_mma.cuh)
   DevBuf<int4> fmRows;
   DevBuf<FmTile> fmTiles;
@@ -169,11 +174,12 @@ struct gomcb200_engine {
   bool trialActive = false;
   std::vector<BoxState> box;
   int imageTotal = 0;
-  int recipAlgo = 2;  // 0 direct, 1 factorised SIMT, 2 factorised DMMA
+  int recipAlgo = 2;  // 0 direct, 1 factorised SIMT, 2 factorised DMMA, 3 int8 tensor cores
   int shardRank = 0, shardWorld = 1;
   // scratch
   DevBuf<double> part, blockA, blockB, result, molBuf, probeOut;
   DevBuf<double2> phaseTables;
+  DevBuf<unsigned char> zPlanes;  // int8 path: byte planes of the Z phases
   DevBuf<Probe> probes;
   DevBuf<unsigned char> cubTemp;
   double *hRes = nullptr;       // pinned, 64 doubles
@@ -708,6 +714,55 @@ int build_mma_tiles(gomcb200_engine *e, KSet &ks) {
       ks.hMmaTiles.push_back(make_int4((int)rb, c0, NT, cmaxT));
     }
   }
+  {  // int8 path: tiles of 8 a values x 8 b values (the XY table slice a tile needs is then
+     // 16 entries instead of all of them), one tile per column block it reaches
+    ks.i8NSL = KZ1 <= 32 ? 6 : 5;
+    ks.i8CPer = KZ1 <= 32 ? ((KZ1 + 7) / 8) * 8 : (KZ1 <= 40 ? ((KZ1 + 7) / 8) * 8 : 40);
+    ks.i8Nb = 2 * ks.i8CPer;
+    const int ncb = (KZ1 + ks.i8CPer - 1) / ks.i8CPer;
+    const int KX1 = ks.nmax[0] + 1;
+    std::map<std::pair<int, int>, std::vector<int4>> blocks;
+    for (const int4 &rw : mrows) {
+      if (rw.z < 0) continue;
+      const int bb = rw.y >= 0 ? rw.y / 8 : -((-rw.y + 7) / 8);  // floor(b / 8)
+      auto &slots = blocks[{rw.x / 8, bb}];
+      if (slots.empty()) slots.assign(kI8Pairs, make_int4(0, 0, -1, 0));
+      slots[(rw.x & 7) * 8 + (rw.y - 8 * bb)] = rw;
+    }
+    std::vector<int4> irows, it;
+    std::vector<std::pair<int, int4>> order;  // (cmax of the tile, descriptor), big first
+    for (auto &kv : blocks) {
+      const int ab = kv.first.first, bb = kv.first.second;
+      int cmaxT = -1;
+      for (const int4 &rw : kv.second) cmaxT = std::max(cmaxT, rw.z);
+      const int yFirst = bb >= 0 ? 8 * bb : -(8 * bb + 7);  // smallest |b| of the block
+      const int rb = (int)irows.size();
+      irows.insert(irows.end(), kv.second.begin(), kv.second.end());
+      order.push_back({cmaxT, make_int4(rb, 0, 8 * ab, KX1 + yFirst)});
+    }
+    std::sort(order.begin(), order.end(),
+              [](const std::pair<int, int4> &l, const std::pair<int, int4> &r) {
+                return l.first > r.first;
+              });
+    for (int cb = 0; cb < ncb; ++cb)
+      for (auto &o : order) {
+        if (o.first < ks.i8CPer * cb) break;
+        int4 d = o.second;
+        d.y = cb;
+        it.push_back(d);
+      }
+    ks.i8NTiles = (int)it.size();
+    ks.i8NCB = ncb;
+    CK(ks.i8Rows.reserve(irows.size() + 1));
+    CK(ks.i8Tiles.reserve(it.size() + 1));
+    if (!irows.empty())
+      CK(cudaMemcpyAsync(ks.i8Rows.p, irows.data(), irows.size() * sizeof(int4),
+                         cudaMemcpyHostToDevice, e->stream));
+    if (!it.empty())
+      CK(cudaMemcpyAsync(ks.i8Tiles.p, it.data(), it.size() * sizeof(int4),
+                         cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));  // the vectors are locals
+  }
   int ZS = colBlocks * 4 * kMmaMaxNT;
   while (ZS % 8 != 2) ++ZS;  // conflict-free B fragments
   ks.mmaZS = ZS;
@@ -860,7 +915,70 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
   const int nAt = bx.nCharged;
   int nSlabs = 1;
   if (e->timing) cudaEventRecord(e->ev[2], e->stream);
-  if (e->recipAlgo == 2 && ks.mmaValid && nAt > 0) {
+  bool i8Done = false;
+  if (e->recipAlgo == 3 && ks.mmaValid && nAt > 0) {
+    rc = build_mma_tiles(e, ks);
+    if (rc) return rc;
+    I8Args ia;
+    ia.KX1 = ks.nmax[0] + 1;
+    const int KY1 = ks.nmax[1] + 1;
+    ia.XYS = ia.KX1 + KY1;
+    ia.NCB = ks.i8NCB;
+    ia.cPer = ks.i8CPer;
+    ia.nb = ks.i8Nb;
+    ia.nTiles = ks.i8NTiles;
+    const int NSL = ks.i8NSL;
+    ia.nSteps = (nAt + kI8StepAtoms - 1) / kI8StepAtoms;
+    ia.nChunks = (ia.nSteps + kI8ChunkSteps - 1) / kI8ChunkSteps;
+    ia.nkStride = nkStride;
+    const size_t planeB = (size_t)ia.nb * 32;
+    const size_t smem = (size_t)kI8TR * kI8TabEntries * 32 * 16 + kI8AR * (size_t)NSL * kI8PlaneA +
+                        kI8BR * (size_t)NSL * planeB + (2 * kI8TR + 2 * kI8BR + 2 * kI8AR + 1) * 8 + 16 +
+                        34 * 16;  // + the issuer's instruction list (16 B aligned)
+    if (smem + 1024 <= e->smemOptin && ks.i8NTiles > 0) {
+      // |A| < 1 needs q / qScale with qScale a power of two above every |q| of the box
+      double qmax = 0.0;
+      for (int a : bx.hCharged) qmax = std::max(qmax, std::fabs(e->hChargeEff[a]));
+      int ex = 0;
+      std::frexp(qmax, &ex);  // qmax = m * 2^ex, m in [0.5, 1)
+      const double qScale = std::ldexp(1.0, ex);
+      ia.outScale = std::ldexp(qScale, 8 * i8_min_group(NSL) - i8_frac_a(NSL) - i8_frac_b(NSL));
+      ia.sumScale = qScale;
+      const int nPad = ia.nSteps * kI8StepAtoms;
+      CK(e->phaseTables.reserve((size_t)nPad * ia.XYS + 1024));  // slices may overrun by < 16 entries
+      CK(e->zPlanes.reserve((size_t)ia.nSteps * ia.NCB * NSL * planeB + 16));
+      const long long total = (long long)nPad * (ia.XYS + ia.cPer * ia.NCB);
+      const unsigned tg = (unsigned)((total + 255) / 256);
+      if (NSL == 6)
+        k_i8_tables<6><<<tg, 256, 0, e->stream>>>(nAt, nPad, ia.KX1, KY1, ia.NCB, ia.cPer,
+                                                  ks.cv[0], ks.cv[1], ks.cv[2], 1.0 / qScale,
+                                                  bx.packed.p, e->phaseTables.p, e->zPlanes.p);
+      else
+        k_i8_tables<5><<<tg, 256, 0, e->stream>>>(nAt, nPad, ia.KX1, KY1, ia.NCB, ia.cPer,
+                                                  ks.cv[0], ks.cv[1], ks.cv[2], 1.0 / qScale,
+                                                  bx.packed.p, e->phaseTables.p, e->zPlanes.p);
+      nSlabs = ia.nChunks;
+      CK(e->part.reserve((size_t)nSlabs * 2 * nkStride + 64));
+      CK(cudaMemsetAsync(e->part.p, 0, sizeof(double) * (size_t)nSlabs * 2 * nkStride, e->stream));
+      ia.rows = ks.i8Rows.p;
+      ia.tiles = ks.i8Tiles.p;
+      ia.tabXY = e->phaseTables.p;
+      ia.zPlanes = e->zPlanes.p;
+      ia.part = e->part.p;
+      const int grid = ks.i8NTiles * ia.nChunks;
+      if (NSL == 6) {
+        CK(cudaFuncSetAttribute(k_recip_i8<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_recip_i8<6><<<grid, kI8Threads, smem, e->stream>>>(ia);
+      } else {
+        CK(cudaFuncSetAttribute(k_recip_i8<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_recip_i8<5><<<grid, kI8Threads, smem, e->stream>>>(ia);
+      }
+      e->launches += 2;
+      i8Done = true;
+    }
+  }
+  if (i8Done) {
+  } else if (e->recipAlgo >= 2 && ks.mmaValid && nAt > 0) {
     rc = build_mma_tiles(e, ks);  // (re)derives tiles and ZS for the current shard
     if (rc) return rc;
     MmaArgs ma;
@@ -2221,7 +2339,7 @@ static int run_force_recip(gomcb200_engine *e, int box, const double *sumR, cons
   BoxParams p = make_params(e, box);
   bool done = false;
   int rc;
-  if (e->recipAlgo == 2 && ks.fmValid && bx.nCharged > 0 && ks.n > 0) {
+  if (e->recipAlgo >= 2 && ks.fmValid && bx.nCharged > 0 && ks.n > 0) {
     rc = ensure_packed(e, box);
     if (rc) return rc;
     FmArgs fa;
@@ -2795,7 +2913,7 @@ int gomcb200_mark_coords_changed(gomcb200_engine *e) {
 }
 
 int gomcb200_set_recip_algo(gomcb200_engine *e, int algo) {
-  if (!e || algo < 0 || algo > 2) return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!e || algo < 0 || algo > 3) return fail(GOMCB200_EINVAL, "bad arguments");
   e->recipAlgo = algo;
   return 0;
 }

@@ -90,7 +90,7 @@ def test_reciprocal(gold):
     assert e.nk == nk
     for a, name in zip(e.get_kvectors(0, eng.K_REF, nk), ("kx", "ky", "kz", "hsqr", "prefact")):
         assert np.array_equal(a, d["box0." + name]), name
-    for algo in (0, 1, 2):
+    for algo in (0, 1, 2, 3):      # per-term, SIMT factorised, FP64 MMA, INT8 tensor cores
         e.set_recip_algo(algo)
         en = e.box_reciprocal_sums(0)
         gR, gI = e.get_recip_sums(0, eng.SUM_NEW, nk)
@@ -98,6 +98,7 @@ def test_reciprocal(gold):
         assert np.max(np.abs(gR - d["box0.sumRref"])) <= TOL * scale
         assert np.max(np.abs(gI - d["box0.sumIref"])) <= TOL * scale
         assert abs(en - d["box0.BoxReciprocal"][0]) <= TOL * abs(en)
+    e.set_recip_algo(2)
     sf, co = e.box_self_correction(0)
     assert abs(sf - d["box0.BoxSelf"][0]) <= TOL * abs(sf)
     assert abs(co - d["box0.MolCorrection.sum"][0]) <= TOL * abs(co)

@@ -123,7 +123,7 @@ def test_kvectors_bit_exact(case):
         assert np.array_equal(a, b)          # index-compatible with the host list
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3])
 def test_box_reciprocal_sums(case, algo):
     s, e, o = case
     if not _ewald(s):
@@ -269,3 +269,29 @@ def test_sharded_partials_sum_to_full(case, world):
         # k-vectors with S(k) == 0 exactly are indistinguishable from "not owned"
         assert np.count_nonzero(owned == 0) <= np.count_nonzero((fR == 0.0) & (fI == 0.0))
     e.call_full_box_energy(0)
+
+
+def test_int8_structure_factor_large_box():
+    """The INT8 tensor-core structure factor (recip algorithm 3) on the 100k-atom box of
+    BASELINE configs[3]: five-slice path (c range > 32), many atom chunks and tiles.  No CPU
+    oracle finishes this size in seconds, so the FP64 MMA kernel -- itself held to the oracle
+    and to the reference's dumps on the small systems -- is the comparison; 1e-9 as everywhere."""
+    from gomc_b200 import synth
+    s = synth.make_spce(33334)
+    e = eng.Engine.from_system(s)
+    try:
+        out = {}
+        for algo in (2, 3):
+            e.set_recip_algo(algo)
+            e.mark_coords_changed()
+            en = e.box_reciprocal_sums(0)
+            out[algo] = (en,) + tuple(e.get_recip_sums(0, eng.SUM_NEW, e.nk))
+        scale = max(np.max(np.abs(out[2][1])), np.max(np.abs(out[2][2])))
+        assert abs(out[3][0] - out[2][0]) <= TOL * abs(out[2][0])
+        assert np.max(np.abs(out[3][1] - out[2][1])) <= TOL * scale
+        assert np.max(np.abs(out[3][2] - out[2][2])) <= TOL * scale
+        # deterministic: integer accumulation, fixed-order FP64 reduction
+        e.mark_coords_changed()
+        assert e.box_reciprocal_sums(0) == out[3][0]
+    finally:
+        e.close()
