@@ -471,6 +471,18 @@ def main():
             mp_move(i)
             t_mv.append((time.perf_counter() - t0) * 1e3)
         mp_move_ms = float(np.mean(t_mv))
+    # opt-in INT8 tensor-core structure factor (recip algorithm 3): same step, same timing
+    i8 = None
+    if world == 1 and s.ff.ewald:
+        e.set_recip_algo(3)
+        for _ in range(3):
+            step(False)
+        d3, m3, _, en3 = timed(False, max(5, args.steps // 2))
+        e.set_recip_algo(2)
+        i8 = {"ms_per_step": float(np.mean(d3)), "structure_factor_stage_ms": float(np.mean(m3)),
+              "recip_rel_diff_vs_default": abs(en3[2] - en_res[2]) / abs(en_res[2]),
+              "what": "gomcb200_set_recip_algo(e, 3): tcgen05.mma kind::i8 + TMEM, byte-sliced "
+                      "fixed point (DESIGN.md 4.1b); not the default"}
     clocks = sampler.stop() if rank == 0 else None
     extras = None
     if world == 1 and args.workload == "spce100k" and not args.no_extras:
@@ -522,6 +534,7 @@ def main():
                 "full_move_ms": mp_move_ms,
                 "full_move": "device trial transform + CalcEn on the trial set + GetCoeff + "
                              "reject, coordinates never leave the GPU"}),
+            "int8_tensor_core": i8,
             "small_box": extras,
             "energies": {"lj": en_res[0], "real": en_res[1], "recip": en_res[2],
                          "host_path_identical": en_res == en_host},

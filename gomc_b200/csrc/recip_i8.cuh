@@ -43,9 +43,9 @@ constexpr int kI8Pairs = 64;             // (a,b) rows per tile
 constexpr int kI8PlaneA = 128 * 32;      // bytes of one A slice plane
 constexpr int kI8ChunkSteps = 128;       // 4096 atoms per chunk (int32 overflow bound)
 constexpr int kI8TmemCols = 512;
-constexpr int kI8AR = 3;                 // A plane ring stages
-constexpr int kI8BR = 5;                 // B plane ring stages
-constexpr int kI8TR = 6;                 // XY table ring stages
+constexpr int kI8AR = 4;                 // A plane ring stages (producers fill two per round)
+constexpr int kI8BR = 4;                 // B plane ring stages (powers of two: cheap ring math)
+constexpr int kI8TR = 4;                 // XY table ring stages
 constexpr int kI8TabEntries = 16;        // staged XY entries per step: 8 X (a block) + 8 Y (b block)
 // NSL byte slices per operand; slice pairs with i + j >= NSL - 2 are kept, in NSL + 1
 // accumulator groups.  NSL = 6 (47/46 fractional bits, 26 MMAs, dropped part < 2^-52 per
@@ -156,6 +156,13 @@ __device__ __forceinline__ void i8_mma(unsigned tmem, unsigned long long da, uns
 __device__ __forceinline__ void i8_commit(unsigned mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
                : "memory");
+}
+// PTX prmt in its default mode: a selector nibble with the msb set replicates the sign bit
+// of the selected byte (CUDA's __byte_perm ignores that bit)
+__device__ __forceinline__ int i8_prmt_sext(unsigned x, unsigned sel) {
+  int r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(sel));
+  return r;
 }
 __device__ __forceinline__ void i8_mbar_arrive(unsigned mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
@@ -304,55 +311,83 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
     // offsets inside the staged slices: X entries tile.z .. +7, then Y entries tile.w .. +7
     const int offX = rwp.z < 0 ? -1 : (rwp.x - tile.z) * 32 * 16;  // empty slot: zeros
     const int offY = (8 + ia.KX1 + (rwp.y < 0 ? -rwp.y : rwp.y) - tile.w) * 32 * 16;
-    const double ysign = rwp.y < 0 ? -1.0 : 1.0;
     const double magic = 1.5 * (double)(1ll << (52 - i8_frac_a(NSL)));
     const unsigned offRe = i8_off(2 * pr, 4 * quad), offIm = i8_off(2 * pr + 1, 4 * quad);
-    // sum over this thread's atoms of the QUANTISED a (multiples of 2^-frac below 1, at most
-    // 4096 atoms: exact in FP64); the epilogue needs it to undo the +1 offset of B
-    double sumRe = 0.0, sumIm = 0.0;
-    for (int s = 0; s < nSteps; ++s) {
-      const int st = s % kI8TR, sa = s % kI8AR;
-      mbar_wait(bTabFull + 8 * st, (s / kI8TR) & 1);
-      unsigned lo[2][4], hi[2][4];
-      const unsigned tb = smem_u32(tab0 + st * tabBytes) + quad * 16;
+    // sum over this thread's atoms of the QUANTISED a, kept as an integer (exact; the integer
+    // pipe has room, the FP64 pipe does not); the epilogue needs it to undo the +1 offset of B
+    // (low words as 64-bit sums, the signed top 8*NSL-32 bits as 32-bit sums)
+    unsigned long long loRe = 0, loIm = 0;
+    int hiRe = 0, hiIm = 0;
+    constexpr unsigned kSext = NSL == 5 ? 0x8880u : 0x9910u;  // PRMT: sign-extend 8 / 16 bits
+    const unsigned ymask = rwp.y < 0 ? 0x80000000u : 0u;  // conj(Y): flip the sign of Im
+    // two steps per round: twice the independent work per warp, one proxy fence per round
+    for (int s = 0; s < nSteps; s += 2) {
+      const int n2 = nSteps - s >= 2 ? 2 : 1;
+      unsigned lo[2][2][4], hi[2][2][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        double re = 0.0, im = 0.0;
-        if (offX >= 0) {
-          double2 xv = lds_f64x2(tb + offX + i * 128);
-          double2 yv = lds_f64x2(tb + offY + i * 128);
-          yv.y *= ysign;
-          re = xv.x * yv.x - xv.y * yv.y;
-          im = xv.x * yv.y + xv.y * yv.x;
+      for (int u = 0; u < 2; ++u) {
+        if (u < n2) {
+          const int st = (s + u) % kI8TR;
+          mbar_wait(bTabFull + 8 * st, ((s + u) / kI8TR) & 1);
+          const unsigned tb = smem_u32(tab0 + st * tabBytes) + quad * 16;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            double re = 0.0, im = 0.0;
+            if (offX >= 0) {
+              double2 xv = lds_f64x2(tb + offX + i * 128);
+              double2 yv = lds_f64x2(tb + offY + i * 128);
+              yv.y = __hiloint2double(__double2hiint(yv.y) ^ (int)ymask, __double2loint(yv.y));
+              re = xv.x * yv.x - xv.y * yv.y;
+              im = xv.x * yv.y + xv.y * yv.x;
+            }
+            const double mr = re + magic, mi = im + magic;
+            lo[u][0][i] = (unsigned)__double2loint(mr);
+            hi[u][0][i] = (unsigned)__double2hiint(mr);
+            lo[u][1][i] = (unsigned)__double2loint(mi);
+            hi[u][1][i] = (unsigned)__double2hiint(mi);
+            loRe += lo[u][0][i];
+            loIm += lo[u][1][i];
+            hiRe += i8_prmt_sext(hi[u][0][i], kSext);
+            hiIm += i8_prmt_sext(hi[u][1][i], kSext);
+          }
+          __syncwarp();
+          if (lane == 0) i8_mbar_arrive(bTabEmpty + 8 * st);  // table stage can be refilled
         }
-        const double mr = re + magic, mi = im + magic;
-        sumRe += mr - magic;
-        sumIm += mi - magic;
-        lo[0][i] = (unsigned)__double2loint(mr);
-        hi[0][i] = (unsigned)__double2hiint(mr);
-        lo[1][i] = (unsigned)__double2loint(mi);
-        hi[1][i] = (unsigned)__double2hiint(mi);
       }
-      __syncwarp();
-      if (lane == 0) i8_mbar_arrive(bTabEmpty + 8 * st);  // table stage can be refilled
-      if (s >= kI8AR) mbar_wait(bADone + 8 * sa, ((s / kI8AR) - 1) & 1);  // A planes free
-      unsigned char *ap = aPl0 + sa * NSL * kI8PlaneA;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const unsigned off = c ? offIm : offRe;
+      for (int u = 0; u < 2; ++u) {
+        if (u < n2) {
+          const int sa = (s + u) % kI8AR;
+          if (s + u >= kI8AR) mbar_wait(bADone + 8 * sa, (((s + u) / kI8AR) - 1) & 1);  // planes free
+          unsigned char *ap = aPl0 + sa * NSL * kI8PlaneA;
 #pragma unroll
-        for (int j = 0; j < NSL; ++j) {
-          const unsigned *w = j < 4 ? lo[c] : hi[c];
-          const unsigned b = j < 4 ? j : j - 4;
-          const unsigned t01 = __byte_perm(w[0], w[1], b | ((4 + b) << 4));
-          const unsigned t23 = __byte_perm(w[2], w[3], b | ((4 + b) << 4));
-          *reinterpret_cast<unsigned *>(ap + j * kI8PlaneA + off) = __byte_perm(t01, t23, 0x5410);
+          for (int c = 0; c < 2; ++c) {
+            const unsigned off = c ? offIm : offRe;
+            // 4x4 byte transpose: word j of the output = byte j of the four atoms
+            const unsigned *w = lo[u][c], *h = hi[u][c];
+            const unsigned t0 = __byte_perm(w[0], w[1], 0x5140), t1 = __byte_perm(w[2], w[3], 0x5140);
+            const unsigned t2 = __byte_perm(w[0], w[1], 0x7362), t3 = __byte_perm(w[2], w[3], 0x7362);
+            const unsigned t4 = __byte_perm(h[0], h[1], 0x5140), t5 = __byte_perm(h[2], h[3], 0x5140);
+            unsigned *dst = reinterpret_cast<unsigned *>(ap + off);
+            dst[0 * kI8PlaneA / 4] = __byte_perm(t0, t1, 0x5410);
+            dst[1 * kI8PlaneA / 4] = __byte_perm(t0, t1, 0x7632);
+            dst[2 * kI8PlaneA / 4] = __byte_perm(t2, t3, 0x5410);
+            dst[3 * kI8PlaneA / 4] = __byte_perm(t2, t3, 0x7632);
+            dst[4 * kI8PlaneA / 4] = __byte_perm(t4, t5, 0x5410);
+            if (NSL == 6) dst[5 * kI8PlaneA / 4] = __byte_perm(t4, t5, 0x7632);
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic -> async proxy
       __syncwarp();
-      if (lane == 0) i8_mbar_arrive(bAFull + 8 * sa);
+      if (lane == 0) {
+        i8_mbar_arrive(bAFull + 8 * (s % kI8AR));
+        if (n2 == 2) i8_mbar_arrive(bAFull + 8 * ((s + 1) % kI8AR));
+      }
     }
+    const double fscale = 1.0 / (double)(1ll << i8_frac_a(NSL));
+    const double sumRe = (double)(((long long)hiRe << 32) + (long long)loRe) * fscale;
+    const double sumIm = (double)(((long long)hiIm << 32) + (long long)loIm) * fscale;
     // row sums of a: 8 quads per row, combined through shared memory (table ring is idle now)
     double *rowSum = reinterpret_cast<double *>(tab0);  // [128 rows][8 quads]
     asm volatile("bar.sync 1, %0;" ::"n"(kI8Producers) : "memory");  // every warp left the loop
