@@ -237,11 +237,14 @@ def test_accept_state_machine(case):
     e.update_recip(0)
 
 
+@pytest.mark.parametrize("algo", [2, 3])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_sharded_partials_sum_to_full(case, world):
+def test_sharded_partials_sum_to_full(case, world, algo):
     """Multi-GPU sharding, emulated on one GPU: the partial energies of the ranks
-    add up to the unsharded result and every S(k) is owned by exactly one rank."""
+    add up to the unsharded result and every S(k) is owned by exactly one rank
+    (default FP64-MMA structure factor and the opt-in INT8 one)."""
     s, e, o = case
+    e.set_recip_algo(algo)
     lj0, re0, rc0 = e.call_full_box_energy(0)
     fR, fI = (e.get_recip_sums(0, eng.SUM_NEW, e.nk) if _ewald(s) else (None, None))
     lj = re = rc = 0.0
@@ -261,6 +264,7 @@ def test_sharded_partials_sum_to_full(case, world):
                 assert np.max(np.abs(pI[mine] - fI[mine])) <= 1e-12 * scale
     finally:
         e.set_shard(0, 1)
+        e.set_recip_algo(2)
     assert abs(lj - lj0) <= 1e-12 * abs(lj0)
     assert abs(re - re0) <= 1e-12 * max(abs(re0), 1.0)
     if _ewald(s):
