@@ -1983,6 +1983,43 @@ int gomcb200_swap_correction(gomcb200_engine *e, int box, int molIndex, const do
   return 0;
 }
 
+int gomcb200_change_self_correction(gomcb200_engine *e, int box, int molIndex, double *enSelf,
+                                    double *correction) {
+  int rc = check_box(e, box);
+  if (rc) return rc;
+  if (molIndex < 0 || molIndex >= e->nMols) return fail(GOMCB200_EINVAL, "bad arguments");
+  if (enSelf) *enSelf = 0.0;
+  if (correction) *correction = 0.0;
+  if (!(e->ewald && e->electrostatic)) return 0;
+  CK(cudaSetDevice(e->device));
+  rc = ensure_mirror(e);  // resident coordinates of the molecule
+  if (rc) return rc;
+  const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  const size_t nd = 1 + 7 * (size_t)len;
+  rc = stage_reserve(e, nd * sizeof(double));
+  if (rc) return rc;
+  CK(e->molBuf.reserve(nd + 8));
+  double *h = e->hStage;
+  h[0] = (double)len;
+  for (int a = 0; a < len; ++a) {
+    double *m = h + 1 + 7 * a;
+    m[0] = e->hCharge[s + a];  // lambda = 1 charges (src/Ewald.cpp:1099-1114, :1403-1408)
+    m[1] = e->hx[s + a];
+    m[2] = e->hy[s + a];
+    m[3] = e->hz[s + a];
+    m[4] = m[5] = m[6] = 0.0;
+  }
+  CK(cudaMemcpyAsync(e->molBuf.p, h, nd * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  k_swap_correction<<<1, 128, 0, e->stream>>>(make_params(e, box), e->molBuf.p, e->result.p + 1);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  rc = fetch_result(e, 3);
+  if (rc) return rc;
+  if (correction) *correction = e->hRes[1];
+  if (enSelf) *enSelf = e->hRes[2];
+  return 0;
+}
+
 int gomcb200_swap_trial(gomcb200_engine *e, int box, int molIndex, const double *x,
                         const double *y, const double *z, int insert, double *energyRecipNew,
                         double *correction, double *self) {

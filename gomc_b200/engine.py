@@ -65,6 +65,7 @@ _SIGS = {
     "gomcb200_change_lambda_mol_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp,
                                                         C.c_double, _dp]),
     "gomcb200_change_recip": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp]),
+    "gomcb200_change_self_correction": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp]),
     "gomcb200_swap_correction": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]),
     "gomcb200_swap_trial": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp]),
     "gomcb200_particle_inter": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
@@ -333,6 +334,12 @@ class Engine:
         self._ck(self.L.gomcb200_change_recip(self.h, box, mol_index, len(lam), pl, int(i_state),
                                               out.ctypes.data_as(_dp)))
         return out
+
+    def change_self_correction(self, box, mol_index):
+        es, ec = C.c_double(), C.c_double()
+        self._ck(self.L.gomcb200_change_self_correction(self.h, box, mol_index, C.byref(es),
+                                                        C.byref(ec)))
+        return es.value, ec.value
 
     def swap_correction(self, box, mol_index, x, y, z):
         (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)

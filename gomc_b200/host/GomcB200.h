@@ -346,6 +346,22 @@ public:
     for (size_t s = 0; s < lambda_Coul.size(); ++s) energyDiffRecip[s] -= sysPotRecip_[box];
     dUdL_CoulRecip += energyDiffRecip[lambda_Coul.size() - 1] - energyDiffRecip[0];
   }
+  // src/Ewald.cpp:1395-1417 and :1089-1122: energyDiff[s] += (lambda_s - lambda_iState) * E
+  virtual void ChangeSelfAndCorrection(double *energyDiffSelf, double *energyDiffCorrection,
+                                       double &dUdL_self, double &dUdL_correction,
+                                       const std::vector<double> &lambda_Coul, int iState,
+                                       int molIndex, int box) const {
+    double en_self = 0.0, correction = 0.0;
+    check(gomcb200_change_self_correction(eng_.get(), box, molIndex, &en_self, &correction),
+          "ChangeSelf/ChangeCorrection");
+    for (size_t s = 0; s < lambda_Coul.size(); ++s) {
+      const double coefDiff = lambda_Coul[s] - lambda_Coul[iState];
+      energyDiffSelf[s] += coefDiff * en_self;
+      energyDiffCorrection[s] += coefDiff * correction;
+    }
+    dUdL_self += en_self;
+    dUdL_correction += correction;
+  }
   virtual Virial VirialReciprocal(const Virial &virial, int box) const {  // :1168-1305
     Virial v = virial;
     double wT[3];
@@ -426,6 +442,8 @@ public:
                    int) const override { for (size_t s = 0; s < l.size(); ++s) d[s] = 0.0; }
   double SwapSelf(int, int) const override { return 0.0; }
   Virial VirialReciprocal(const Virial &virial, int) const override { return virial; }
+  void ChangeSelfAndCorrection(double *, double *, double &, double &,
+                               const std::vector<double> &, int, int, int) const override {}
   void BoxSelfAndCorrection(int, double &self, double &correction) const override {
     self = correction = 0.0;
   }

@@ -325,6 +325,11 @@ int gomcb200_change_lambda_mol_reciprocal(gomcb200_engine *e, int box,
 int gomcb200_change_recip(gomcb200_engine *e, int box, int molIndex, int nStates,
                           const double *lambdaCoul, int iState,
                           double *energyRecip);
+/* The lambda = 1 self and correction energies of the resident molecule molIndex that
+ * Ewald::ChangeSelf (src/Ewald.cpp:1395-1417) and Ewald::ChangeCorrection (:1089-1122)
+ * scale by (lambda_Coul[s] - lambda_Coul[iState]) for every free-energy state. */
+int gomcb200_change_self_correction(gomcb200_engine *e, int box, int molIndex,
+                                    double *enSelf, double *correction);
 /* Ewald::SwapCorrection (src/Ewald.cpp:1311-1335 and :1340-1370; charges of
  * molIndex, trial coordinates x/y/z) and Ewald::SwapSelf (:1375-1391). */
 int gomcb200_swap_correction(gomcb200_engine *e, int box, int molIndex,

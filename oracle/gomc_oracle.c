@@ -1697,6 +1697,21 @@ double orc_swap_correction(const orc_params *p, int molLen, const double *q,
   return ORC_QQFACT * (-c);
 }
 
+/* Ewald::ChangeSelf (src/Ewald.cpp:1395-1417) and ChangeCorrection (:1089-1122): lambda = 1
+ * self / correction of one molecule (true charges, resident coordinates); the caller
+ * scales by lambda_s - lambda_iState. */
+void orc_change_self_correction(const orc_params *p, int molLen, const double *q,
+                                const double *mx, const double *my, const double *mz,
+                                double *enSelf, double *correction) {
+  double en_self = 0.0;
+  for (int i = 0; i < molLen; ++i) en_self += (q[i] * q[i]);
+  en_self *= -1.0 * p->alpha * ORC_QQFACT * M_2_SQRTPI * 0.5;
+  double c = mol_correction(p, molLen, q, mx, my, mz, 1);
+  c *= -1.0 * ORC_QQFACT;
+  *enSelf = en_self;
+  *correction = c;
+}
+
 double orc_swap_self(const orc_params *p, int molLen, const double *q) {
   double en_self = 0.0; /* src/Ewald.cpp:1375-1391 */
   for (int i = 0; i < molLen; ++i) en_self -= q[i] * q[i];

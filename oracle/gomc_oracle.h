@@ -314,6 +314,11 @@ double orc_box_self(const orc_params *p, int nBoxMols, const int *boxMols,
 double orc_swap_correction(const orc_params *p, int molLen, const double *q,
                            const double *mx, const double *my,
                            const double *mz);
+/* Ewald::ChangeSelf (:1395-1417) / ChangeCorrection (:1089-1122): the lambda = 1 self and
+ * correction energies of one molecule that the callers scale by lambda differences. */
+void orc_change_self_correction(const orc_params *p, int molLen, const double *q,
+                                const double *mx, const double *my, const double *mz,
+                                double *enSelf, double *correction);
 /* Ewald::SwapSelf, src/Ewald.cpp:1375-1391. */
 double orc_swap_self(const orc_params *p, int molLen, const double *q);
 

@@ -439,6 +439,14 @@ class Oracle:
         m = [_d(a) for a in mxyz]
         return self.L.orc_swap_correction(self.pp, len(q), pq, *[a[1] for a in m])
 
+    def change_self_correction(self, q, mxyz):
+        (q, pq) = _d(q)
+        m = [_d(a) for a in mxyz]
+        es, ec = C.c_double(), C.c_double()
+        self.L.orc_change_self_correction(self.pp, len(q), pq, *[a[1] for a in m],
+                                          C.byref(es), C.byref(ec))
+        return es.value, ec.value
+
     def swap_self(self, q):
         (q, pq) = _d(q)
         return self.L.orc_swap_self(self.pp, len(q), pq)

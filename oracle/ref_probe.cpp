@@ -620,6 +620,20 @@ int run_golden(int argc, char **argv) {
         out.f64(bname("changeRecip.lambda", b), lam);
         out.f64(bname("changeRecip.dRecip", b), er);
         out.f64(bname("changeRecip.dUdL", b), dUdL.recip);
+        // ChangeSelf / ChangeCorrection on the same molecule and lambda states
+        std::vector<Energy> ed2(lam.size());
+        Energy dUdL2;
+        ew.ChangeSelf(ed2.data(), dUdL2, lam, 2, m, b);
+        ew.ChangeCorrection(ed2.data(), dUdL2, lam, 2, m, b);
+        std::vector<double> es, ec;
+        for (auto &e : ed2) {
+          es.push_back(e.self);
+          ec.push_back(e.correction);
+        }
+        out.f64(bname("changeSelf.dSelf", b), es);
+        out.f64(bname("changeCorrection.dCorrection", b), ec);
+        double dd[2] = {dUdL2.self, dUdL2.correction};
+        out.f64(bname("changeSelfCorrection.dUdL", b), dd, 2);
       }
     }
   }

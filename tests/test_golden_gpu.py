@@ -289,6 +289,11 @@ def test_exchange_and_lambda_reciprocal(gold):
     er = e.change_recip(0, m, d["box0.changeRecip.lambda"], 2)
     want = d["box0.changeRecip.dRecip"] + ref
     assert np.max(np.abs(er - want)) <= TOL * np.max(np.abs(want))
+    if "box0.changeSelf.dSelf" in d:        # ChangeSelf / ChangeCorrection
+        lam = d["box0.changeRecip.lambda"]
+        es, ec = e.change_self_correction(0, m)
+        assert rel_err((lam - lam[2]) * es, d["box0.changeSelf.dSelf"]) <= TOL
+        assert rel_err((lam - lam[2]) * ec, d["box0.changeCorrection.dCorrection"]) <= TOL
     # the reference sums are never written by trial deltas
     rR, _ = e.get_recip_sums(0, eng.SUM_REF, nk)
     assert np.max(np.abs(rR - d["box0.sumRref"])) <= TOL * scale
