@@ -932,8 +932,9 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     ia.nChunks = (ia.nSteps + kI8ChunkSteps - 1) / kI8ChunkSteps;
     ia.nkStride = nkStride;
     const size_t planeB = (size_t)ia.nb * 32;
-    const size_t smem = (size_t)kI8TR * kI8TabEntries * 32 * 16 + kI8AR * (size_t)NSL * kI8PlaneA +
-                        kI8BR * (size_t)NSL * planeB + (2 * kI8TR + 2 * kI8BR + 2 * kI8AR + 1) * 8 + 16 +
+    const int TR = i8_tr(NSL), BR = i8_br(NSL);
+    const size_t smem = (size_t)TR * kI8TabEntries * 32 * 16 + kI8AR * (size_t)NSL * kI8PlaneA +
+                        BR * (size_t)NSL * planeB + (2 * TR + 2 * BR + 2 * kI8AR + 1) * 8 + 16 +
                         34 * 16;  // + the issuer's instruction list (16 B aligned)
     if (smem + 1024 <= e->smemOptin && ks.i8NTiles > 0) {
       // |A| < 1 needs q / qScale with qScale a power of two above every |q| of the box

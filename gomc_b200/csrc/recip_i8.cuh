@@ -19,8 +19,9 @@
 //           column blocks of up to 80 columns (6 groups x 80 = 480 TMEM columns).
 //
 // CTA = (tile of 8 a values x 8 b values = 64 (a,b) rows = 128 real rows, column block, chunk):
-//   warp 0   : cp.async.bulk loader: the two 8-entry slices of the XY phase table the tile
-//              needs (8 KB per 32-atom step) and the B byte planes of the step, each on its ring;
+//   warp 0   : cp.async.bulk loader of the two 8-entry slices of the XY phase table the tile
+//              needs (8 KB per 32-atom step); warp 18: loader of the B byte planes -- separate
+//              rings, so the table runs ahead of the producers independently of the MMAs;
 //   warp 1   : MMA issuer (one lane): per step a prepared list of <= 12 instructions -- the B
 //              planes of consecutive slices are adjacent in shared memory, so one instruction
 //              with N = up to 256 covers several slice pairs whose results land in adjacent
@@ -29,14 +30,18 @@
 //              fixed point -> PRMT byte transposition -> no-swizzle K-major canonical layout);
 //   warps 2-5 also run the epilogue (tcgen05.ld, FP64 recombination, S(a,b,+-c) partials).
 // Measured (tools/umma_i8_probe.cu): one M128 K32 kind::i8 instruction takes 59 / 74 / 138
-// cycles at N = 64 / 128 / 256, i.e. 4.4k / 7.1k / 7.6k MAC per cycle per SM.
+// cycles at N = 64 / 128 / 256, i.e. 4.4k / 7.1k / 7.6k MAC per cycle per SM and ~90-100 B per
+// cycle of shared-memory operand fetch.  With K = 32 the operands of a step are 80 KB for
+// 6.2 MMAC, so this kernel is bound by operand fetch (shared with the producers' own traffic),
+// not by the integer math: clock64 instrumentation shows the producer warps waiting for
+// A-plane stages to be released 52 % of the time (compute 13 %, stores 23 %).
 #pragma once
 #include "common.cuh"
 #include "recip_mma.cuh"
 
 namespace gb {
 
-constexpr int kI8Threads = 576;          // loader warp, issuer warp, 16 producer warps
+constexpr int kI8Threads = 608;          // table loader, issuer, 16 producer warps, B loader
 constexpr int kI8Producers = 512;
 constexpr int kI8StepAtoms = 32;  // K of one UMMA
 constexpr int kI8Pairs = 64;             // (a,b) rows per tile
@@ -44,8 +49,10 @@ constexpr int kI8PlaneA = 128 * 32;      // bytes of one A slice plane
 constexpr int kI8ChunkSteps = 128;       // 4096 atoms per chunk (int32 overflow bound)
 constexpr int kI8TmemCols = 512;
 constexpr int kI8AR = 4;                 // A plane ring stages (producers fill two per round)
-constexpr int kI8BR = 4;                 // B plane ring stages (powers of two: cheap ring math)
-constexpr int kI8TR = 4;                 // XY table ring stages
+// ring depths: deep enough that neither loader is ever the pacing item (a bulk copy takes
+// about as long as three steps of MMAs); the six-slice planes are larger, so fewer fit
+__host__ __device__ constexpr int i8_tr(int nsl) { return nsl == 5 ? 8 : 4; }  // XY table ring
+__host__ __device__ constexpr int i8_br(int nsl) { return nsl == 5 ? 6 : 4; }  // B plane ring
 constexpr int kI8TabEntries = 16;        // staged XY entries per step: 8 X (a block) + 8 Y (b block)
 // NSL byte slices per operand; slice pairs with i + j >= NSL - 2 are kept, in NSL + 1
 // accumulator groups.  NSL = 6 (47/46 fractional bits, 26 MMAs, dropped part < 2^-52 per
@@ -157,13 +164,6 @@ __device__ __forceinline__ void i8_commit(unsigned mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
                : "memory");
 }
-// PTX prmt in its default mode: a selector nibble with the msb set replicates the sign bit
-// of the selected byte (CUDA's __byte_perm ignores that bit)
-__device__ __forceinline__ int i8_prmt_sext(unsigned x, unsigned sel) {
-  int r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(sel));
-  return r;
-}
 __device__ __forceinline__ void i8_mbar_arrive(unsigned mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
@@ -171,6 +171,7 @@ __device__ __forceinline__ void i8_mbar_arrive(unsigned mbar) {
 template <int NSL>
 __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
   constexpr int G = NSL + 1;               // accumulator groups
+  constexpr int kI8TR = i8_tr(NSL), kI8BR = i8_br(NSL);
   constexpr int SMIN = i8_min_group(NSL);  // smallest kept i + j
   extern __shared__ __align__(128) unsigned char i8smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -227,18 +228,25 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
   const unsigned tmem = *tmemSlot;
 
   if (warp == 0) {
-    // ===== loader =====
+    // ===== XY table loader (runs ahead of the producers, independent of the MMAs) =====
     if (lane == 0) {
       const double2 *xSrc = ia.tabXY + (size_t)tile.z * 32;
       const double2 *ySrc = ia.tabXY + (size_t)tile.w * 32;
       for (int s = 0; s < nSteps; ++s) {
-        const int st = s % kI8TR, sb = s % kI8BR;
+        const int st = s % kI8TR;
         if (s >= kI8TR) mbar_wait(bTabEmpty + 8 * st, ((s / kI8TR) - 1) & 1);
         mbar_expect_tx(bTabFull + 8 * st, (unsigned)tabBytes);
         const size_t stepOff = (size_t)(step0 + s) * ia.XYS * 32;
         bulk_g2s(smem_u32(tab0 + st * tabBytes), xSrc + stepOff, tabBytes / 2, bTabFull + 8 * st);
         bulk_g2s(smem_u32(tab0 + st * tabBytes + tabBytes / 2), ySrc + stepOff, tabBytes / 2,
                  bTabFull + 8 * st);
+      }
+    }
+  } else if (warp == kI8Threads / 32 - 1) {
+    // ===== B plane loader =====
+    if (lane == 0) {
+      for (int s = 0; s < nSteps; ++s) {
+        const int sb = s % kI8BR;
         if (s >= kI8BR) mbar_wait(bBDone + 8 * sb, ((s / kI8BR) - 1) & 1);
         mbar_expect_tx(bBFull + 8 * sb, (unsigned)(NSL * planeB));
         bulk_g2s(smem_u32(bPl0 + sb * NSL * planeB),
@@ -313,13 +321,12 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
     const int offY = (8 + ia.KX1 + (rwp.y < 0 ? -rwp.y : rwp.y) - tile.w) * 32 * 16;
     const double magic = 1.5 * (double)(1ll << (52 - i8_frac_a(NSL)));
     const unsigned offRe = i8_off(2 * pr, 4 * quad), offIm = i8_off(2 * pr + 1, 4 * quad);
-    // sum over this thread's atoms of the QUANTISED a, kept as an integer (exact; the integer
-    // pipe has room, the FP64 pipe does not); the epilogue needs it to undo the +1 offset of B
-    // (low words as 64-bit sums, the signed top 8*NSL-32 bits as 32-bit sums)
-    unsigned long long loRe = 0, loIm = 0;
-    int hiRe = 0, hiIm = 0;
-    constexpr unsigned kSext = NSL == 5 ? 0x8880u : 0x9910u;  // PRMT: sign-extend 8 / 16 bits
-    const unsigned ymask = rwp.y < 0 ? 0x80000000u : 0u;  // conj(Y): flip the sign of Im
+    // sum over this thread's atoms of the QUANTISED a, kept as integers per byte plane (one
+    // dp4a per stored word; exact); the epilogue needs it to undo the +1 offset of B
+    int accRe[NSL], accIm[NSL];
+#pragma unroll
+    for (int j = 0; j < NSL; ++j) accRe[j] = accIm[j] = 0;
+    const bool conjY = rwp.y < 0;  // same for every row of a tile (b blocks do not straddle 0)
     // two steps per round: twice the independent work per warp, one proxy fence per round
     for (int s = 0; s < nSteps; s += 2) {
       const int n2 = nSteps - s >= 2 ? 2 : 1;
@@ -332,23 +339,24 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
           const unsigned tb = smem_u32(tab0 + st * tabBytes) + quad * 16;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            double re = 0.0, im = 0.0;
+            double mr = magic, mi = magic;
             if (offX >= 0) {
-              double2 xv = lds_f64x2(tb + offX + i * 128);
-              double2 yv = lds_f64x2(tb + offY + i * 128);
-              yv.y = __hiloint2double(__double2hiint(yv.y) ^ (int)ymask, __double2loint(yv.y));
-              re = xv.x * yv.x - xv.y * yv.y;
-              im = xv.x * yv.y + xv.y * yv.x;
+              const double2 xv = lds_f64x2(tb + offX + i * 128);
+              const double2 yv = lds_f64x2(tb + offY + i * 128);
+              // (x * y or x * conj(y)) + magic in four FMAs; the magic addend puts the result
+              // on the fixed-point grid (one extra rounding of half a grid step)
+              if (conjY) {
+                mr = fma(xv.x, yv.x, fma(xv.y, yv.y, magic));
+                mi = fma(xv.y, yv.x, fma(-xv.x, yv.y, magic));
+              } else {
+                mr = fma(xv.x, yv.x, fma(-xv.y, yv.y, magic));
+                mi = fma(xv.x, yv.y, fma(xv.y, yv.x, magic));
+              }
             }
-            const double mr = re + magic, mi = im + magic;
             lo[u][0][i] = (unsigned)__double2loint(mr);
             hi[u][0][i] = (unsigned)__double2hiint(mr);
             lo[u][1][i] = (unsigned)__double2loint(mi);
             hi[u][1][i] = (unsigned)__double2hiint(mi);
-            loRe += lo[u][0][i];
-            loIm += lo[u][1][i];
-            hiRe += i8_prmt_sext(hi[u][0][i], kSext);
-            hiIm += i8_prmt_sext(hi[u][1][i], kSext);
           }
           __syncwarp();
           if (lane == 0) i8_mbar_arrive(bTabEmpty + 8 * st);  // table stage can be refilled
@@ -362,19 +370,26 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
           unsigned char *ap = aPl0 + sa * NSL * kI8PlaneA;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const unsigned off = c ? offIm : offRe;
             // 4x4 byte transpose: word j of the output = byte j of the four atoms
             const unsigned *w = lo[u][c], *h = hi[u][c];
             const unsigned t0 = __byte_perm(w[0], w[1], 0x5140), t1 = __byte_perm(w[2], w[3], 0x5140);
             const unsigned t2 = __byte_perm(w[0], w[1], 0x7362), t3 = __byte_perm(w[2], w[3], 0x7362);
             const unsigned t4 = __byte_perm(h[0], h[1], 0x5140), t5 = __byte_perm(h[2], h[3], 0x5140);
-            unsigned *dst = reinterpret_cast<unsigned *>(ap + off);
-            dst[0 * kI8PlaneA / 4] = __byte_perm(t0, t1, 0x5410);
-            dst[1 * kI8PlaneA / 4] = __byte_perm(t0, t1, 0x7632);
-            dst[2 * kI8PlaneA / 4] = __byte_perm(t2, t3, 0x5410);
-            dst[3 * kI8PlaneA / 4] = __byte_perm(t2, t3, 0x7632);
-            dst[4 * kI8PlaneA / 4] = __byte_perm(t4, t5, 0x5410);
-            if (NSL == 6) dst[5 * kI8PlaneA / 4] = __byte_perm(t4, t5, 0x7632);
+            unsigned o[6];
+            o[0] = __byte_perm(t0, t1, 0x5410);
+            o[1] = __byte_perm(t0, t1, 0x7632);
+            o[2] = __byte_perm(t2, t3, 0x5410);
+            o[3] = __byte_perm(t2, t3, 0x7632);
+            o[4] = __byte_perm(t4, t5, 0x5410);
+            o[5] = __byte_perm(t4, t5, 0x7632);
+            unsigned *dst = reinterpret_cast<unsigned *>(ap + (c ? offIm : offRe));
+            int *acc = c ? accIm : accRe;
+#pragma unroll
+            for (int j = 0; j < NSL; ++j) {
+              dst[j * kI8PlaneA / 4] = o[j];
+              acc[j] = j == NSL - 1 ? __dp4a((int)o[j], 0x01010101, acc[j])               // signed top
+                                    : (int)__dp4a(o[j], 0x01010101u, (unsigned)acc[j]);  // unsigned
+            }
           }
         }
       }
@@ -385,9 +400,14 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
         if (n2 == 2) i8_mbar_arrive(bAFull + 8 * ((s + 1) % kI8AR));
       }
     }
+    long long totRe = 0, totIm = 0;
+#pragma unroll
+    for (int j = 0; j < NSL; ++j) {
+      totRe += (long long)accRe[j] << (8 * j);
+      totIm += (long long)accIm[j] << (8 * j);
+    }
     const double fscale = 1.0 / (double)(1ll << i8_frac_a(NSL));
-    const double sumRe = (double)(((long long)hiRe << 32) + (long long)loRe) * fscale;
-    const double sumIm = (double)(((long long)hiIm << 32) + (long long)loIm) * fscale;
+    const double sumRe = (double)totRe * fscale, sumIm = (double)totIm * fscale;
     // row sums of a: 8 quads per row, combined through shared memory (table ring is idle now)
     double *rowSum = reinterpret_cast<double *>(tab0);  // [128 rows][8 quads]
     asm volatile("bar.sync 1, %0;" ::"n"(kI8Producers) : "memory");  // every warp left the loop
