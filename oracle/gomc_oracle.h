@@ -15,8 +15,9 @@
  * (oracle/make_golden.py).
  *
  * Every function cites the reference file:line it follows (paths relative to
- * the GOMC tree).  lambda == 1 everywhere (no free-energy / NeMTMC fractional
- * molecule), which is the case for all five BASELINE configs.
+ * the GOMC tree).  lambda == 1 (the case of all five BASELINE configs) unless a
+ * fractional molecule is declared with orc_set_lambda; four lambda fixtures pin
+ * that state too.
  */
 #ifndef GOMC_ORACLE_H
 #define GOMC_ORACLE_H
