@@ -13,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -80,7 +81,7 @@ struct KSet {
   double cv[3] = {0, 0, 0};
   // factorised-sum plan
   DevBuf<int4> rows, tiles;
-  int nTiles = 0, maxRows = 0;
+  int nTiles = 0, maxRows = 0, nRowsPadded = 0;
   bool planValid = false;
   // DMMA plan (recip_mma.cuh)
   DevBuf<int4> mmaRows, mmaTiles, mmaSegs;
@@ -546,41 +547,92 @@ int recip_enumerate(const gomcb200_engine *e, int b, const double ax[3], KSet *k
   int nmax[3];
   for (int d = 0; d < 3; ++d) nmax[d] = int(recip_rcut * ax[d] / (2.0 * M_PI)) + 1;
   if (ks) {
-    ks->hkx.clear(); ks->hky.clear(); ks->hkz.clear(); ks->hhsqr.clear();
-    ks->hprefact.clear();
     for (int d = 0; d < 3; ++d) { ks->nmax[d] = nmax[d]; ks->cv[d] = cv[d]; }
     ks->kmax = std::max(std::max(nmax[0], nmax[1]), std::max(nmax[1], nmax[2]));
   }
-  int counter = 0;
-  for (int ix = 0; ix <= nmax[0]; ix++) {
+  // Same loop nest, order and floating-point expressions as the reference; for large
+  // boxes (1e6 k-vectors per volume trial) the x slabs are enumerated by a few host
+  // threads in two passes (count, then fill at the prefix offsets), which leaves the k
+  // list and its order bit-identical to the serial enumeration.
+  const int nX = nmax[0] + 1;
+  struct RowScan {
+    int iy, zlo, zhi, cnt;
+  };
+  std::vector<std::vector<RowScan>> slabRows(nX);
+  std::vector<int> slabCount(nX, 0), slabStart(nX + 1, 0);
+  auto scan_slab = [&](int ix) {
     int nky_min = (ix == 0) ? 0 : -nmax[1];
+    int total = 0;
     for (int iy = nky_min; iy <= nmax[1]; iy++) {
       int nkz_min = (ix == 0 && iy == 0) ? 1 : -nmax[2];
-      int first = -1, zlo = 0, zhi = 0, cnt = 0;
+      RowScan r = {iy, 0, 0, 0};
       for (int iz = nkz_min; iz <= nmax[2]; iz++) {
         double kX = cv[0] * ix, kY = cv[1] * iy, kZ = cv[2] * iz;
         double ksqr = kX * kX + kY * kY + kZ * kZ;
         if (ksqr < rr2) {
-          if (ks) {
-            ks->hkx.push_back(kX);
-            ks->hky.push_back(kY);
-            ks->hkz.push_back(kZ);
-            ks->hhsqr.push_back(ksqr);
-            ks->hprefact.push_back(kQQFact * exp(-ksqr * alpsqr4) / (ksqr * vol));
-          }
-          if (first < 0) { first = counter; zlo = iz; }
-          zhi = iz;
-          ++cnt;
-          counter++;
+          if (r.cnt == 0) r.zlo = iz;
+          r.zhi = iz;
+          ++r.cnt;
         }
       }
-      if (rowsOut && cnt > 0) {
+      if (r.cnt > 0) slabRows[ix].push_back(r);
+      total += r.cnt;
+    }
+    slabCount[ix] = total;
+  };
+  auto fill_slab = [&](int ix) {
+    int pos = slabStart[ix];
+    for (const RowScan &r : slabRows[ix]) {
+      int nkz_min = (ix == 0 && r.iy == 0) ? 1 : -nmax[2];
+      for (int iz = nkz_min; iz <= nmax[2]; iz++) {
+        double kX = cv[0] * ix, kY = cv[1] * r.iy, kZ = cv[2] * iz;
+        double ksqr = kX * kX + kY * kY + kZ * kZ;
+        if (ksqr < rr2) {
+          ks->hkx[pos] = kX;
+          ks->hky[pos] = kY;
+          ks->hkz[pos] = kZ;
+          ks->hhsqr[pos] = ksqr;
+          ks->hprefact[pos] = kQQFact * exp(-ksqr * alpsqr4) / (ksqr * vol);
+          ++pos;
+        }
+      }
+    }
+  };
+  auto run_slabs = [&](auto &&fn) {
+    const long long cube = (long long)nX * (2 * nmax[1] + 1) * (2 * nmax[2] + 1);
+    int nThreads = cube > 200000 ? (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (nThreads <= 1) {
+      for (int ix = 0; ix < nX; ++ix) fn(ix);
+      return;
+    }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nThreads; ++t)
+      pool.emplace_back([&]() {
+        for (int ix = next.fetch_add(1); ix < nX; ix = next.fetch_add(1)) fn(ix);
+      });
+    for (auto &th : pool) th.join();
+  };
+  run_slabs(scan_slab);
+  for (int ix = 0; ix < nX; ++ix) slabStart[ix + 1] = slabStart[ix] + slabCount[ix];
+  const int counter = slabStart[nX];
+  if (ks) {
+    ks->hkx.resize(counter); ks->hky.resize(counter); ks->hkz.resize(counter);
+    ks->hhsqr.resize(counter); ks->hprefact.resize(counter);
+    run_slabs(fill_slab);
+  }
+  if (rowsOut) {
+    for (int ix = 0; ix < nX; ++ix) {
+      int first = slabStart[ix];
+      for (const RowScan &r : slabRows[ix]) {
         // valid c form one run symmetric about 0 (ksqr is even and monotone
         // in |c|); anything else would break the factorised indexing.
-        bool origin = (ix == 0 && iy == 0);
-        bool ok = origin ? (zlo == 1 && cnt == zhi) : (zlo == -zhi && cnt == 2 * zhi + 1);
+        bool origin = (ix == 0 && r.iy == 0);
+        bool ok = origin ? (r.zlo == 1 && r.cnt == r.zhi)
+                         : (r.zlo == -r.zhi && r.cnt == 2 * r.zhi + 1);
         if (!ok) return -1;
-        rowsOut->push_back({ix, iy, zhi, first});
+        rowsOut->push_back({ix, r.iy, r.zhi, first});
+        first += r.cnt;
       }
     }
   }
@@ -612,6 +664,7 @@ int build_plan(gomcb200_engine *e, KSet &ks, std::vector<RowRec> &rows) {
     i += R;
   }
   ks.nTiles = (int)htiles.size();
+  ks.nRowsPadded = (int)hrows.size();
   ks.maxRows = maxRows;
   CK(ks.rows.reserve(hrows.size() + 1));
   CK(ks.tiles.reserve(htiles.size() + 1));
@@ -850,7 +903,7 @@ int build_mma_segments(gomcb200_engine *e, KSet &ks, int nAt, int AT) {
   return 0;
 }
 
-int upload_kset(gomcb200_engine *e, KSet &ks) {
+int upload_kset(gomcb200_engine *e, KSet &ks, bool prefactOnly = false) {
   size_t n = ks.hkx.size();
   size_t cap = std::max<size_t>(n, (size_t)e->imageTotal) + 1;
   CK(ks.kx.reserve(cap));
@@ -860,10 +913,12 @@ int upload_kset(gomcb200_engine *e, KSet &ks) {
   CK(ks.prefact.reserve(cap));
   if (n) {
     size_t bytes = n * sizeof(double);
-    CK(cudaMemcpyAsync(ks.kx.p, ks.hkx.data(), bytes, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(ks.ky.p, ks.hky.data(), bytes, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(ks.kz.p, ks.hkz.data(), bytes, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(ks.hsqr.p, ks.hhsqr.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+    if (!prefactOnly) {
+      CK(cudaMemcpyAsync(ks.kx.p, ks.hkx.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(ks.ky.p, ks.hky.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(ks.kz.p, ks.hkz.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(ks.hsqr.p, ks.hhsqr.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+    }
     CK(cudaMemcpyAsync(ks.prefact.p, ks.hprefact.data(), bytes, cudaMemcpyHostToDevice,
                        e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -2163,13 +2218,19 @@ int gomcb200_recip_init(gomcb200_engine *e, int box, const double axis[3], int *
     return fail(GOMCB200_EKMAX,
                 "Kmax exceeded due to large change in system volume (%d > imageTotal %d)", n,
                 e->imageTotal);
-  int rc = upload_kset(e, ks);
+  // With a row table the device regenerates kx, ky, kz and |k|^2 itself (same products and
+  // sums, no contraction, hence the same bits as the host list that get_kvectors returns);
+  // only the prefactor, whose exp() must stay the host's, crosses PCIe.
+  int rc = upload_kset(e, ks, !rows.empty());
   if (rc) return rc;
   ks.mmaValid = false;
   ks.fmValid = false;
   if (!rows.empty()) {
     rc = build_plan(e, ks, rows);
     if (rc) return rc;
+    k_gen_kvectors<<<(unsigned)ks.nRowsPadded, 64, 0, e->stream>>>(
+        ks.rows.p, ks.cv[0], ks.cv[1], ks.cv[2], ks.kx.p, ks.ky.p, ks.kz.p, ks.hsqr.p);
+    CK(cudaGetLastError());
   }
   if (imageSize) *imageSize = n;
   if (kmax) *kmax = ks.kmax;
@@ -2180,9 +2241,19 @@ int gomcb200_get_kvectors(gomcb200_engine *e, int box, int which, double *kx, do
                           double *kz, double *hsqr, double *prefact, int n) {
   if (!e || box < 0 || box >= e->nBoxes) return fail(GOMCB200_EINVAL, "bad arguments");
   BoxState &bx = e->box[box];
-  KSet &ks = bx.kset[which == GOMCB200_K_NEW ? bx.cur : 1 - bx.cur];
+  KSet &ks = bx.kset[(which & 1) == GOMCB200_K_NEW ? bx.cur : 1 - bx.cur];
   if (n > ks.n) return fail(GOMCB200_EINVAL, "n %d > imageSize %d", n, ks.n);
   size_t bytes = sizeof(double) * (size_t)n;
+  if (which & GOMCB200_K_DEVICE) {  // the copies the kernels read
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (kx) CK(cudaMemcpy(kx, ks.kx.p, bytes, cudaMemcpyDeviceToHost));
+    if (ky) CK(cudaMemcpy(ky, ks.ky.p, bytes, cudaMemcpyDeviceToHost));
+    if (kz) CK(cudaMemcpy(kz, ks.kz.p, bytes, cudaMemcpyDeviceToHost));
+    if (hsqr) CK(cudaMemcpy(hsqr, ks.hsqr.p, bytes, cudaMemcpyDeviceToHost));
+    if (prefact) CK(cudaMemcpy(prefact, ks.prefact.p, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+  }
   if (kx) memcpy(kx, ks.hkx.data(), bytes);
   if (ky) memcpy(ky, ks.hky.data(), bytes);
   if (kz) memcpy(kz, ks.hkz.data(), bytes);
@@ -2773,6 +2844,7 @@ int gomcb200_set_recip_ref(gomcb200_engine *e, int box) {
     CK(cudaMemcpyAsync(dst.tiles.p, src.tiles.p, std::min(nt, dst.tiles.cap) * sizeof(int4),
                        cudaMemcpyDeviceToDevice, e->stream));
     dst.nTiles = src.nTiles;
+    dst.nRowsPadded = src.nRowsPadded;
     dst.maxRows = src.maxRows;
     dst.planValid = true;
   }

@@ -633,4 +633,26 @@ __global__ void __launch_bounds__(kFactThreads, 1)
   }
 }
 
+// Regenerates the k list of an orthogonal box from its (a, b) row table: one block per
+// row {a, b, cmax, first}; entries first.. hold c = -cmax..cmax (1..cmax for the a = b = 0
+// row).  Each product and sum is rounded separately, in the order of Ewald::RecipInitOrth
+// (src/Ewald.cpp:860-903), so the values equal the host enumeration bit for bit.
+__global__ void k_gen_kvectors(const int4 *__restrict__ rows, double cv0, double cv1, double cv2,
+                               double *__restrict__ kx, double *__restrict__ ky,
+                               double *__restrict__ kz, double *__restrict__ hsqr) {
+  const int4 rw = rows[blockIdx.x];
+  if (rw.z < 0) return;
+  const int clo = (rw.x == 0 && rw.y == 0) ? 1 : -rw.z;
+  const double kX = __dmul_rn(cv0, (double)rw.x), kY = __dmul_rn(cv1, (double)rw.y);
+  const double xy = __dadd_rn(__dmul_rn(kX, kX), __dmul_rn(kY, kY));
+  for (int c = clo + threadIdx.x; c <= rw.z; c += blockDim.x) {
+    const double kZ = __dmul_rn(cv2, (double)c);
+    const int i = rw.w + (c - clo);
+    kx[i] = kX;
+    ky[i] = kY;
+    kz[i] = kZ;
+    hsqr[i] = __dadd_rn(xy, __dmul_rn(kZ, kZ));
+  }
+}
+
 }  // namespace gb

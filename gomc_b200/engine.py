@@ -20,6 +20,7 @@ _vp = C.c_void_p
 
 ATOM_FORCE, MOL_FORCE, ATOM_FORCE_REC, MOL_FORCE_REC, MOL_TORQUE = range(5)
 K_NEW, K_REF = 0, 1
+K_DEVICE = 2          # OR-ed into K_NEW / K_REF: read back the device-resident copy
 SUM_NEW, SUM_REF = 0, 1
 
 # name -> (restype, argtypes); mirrors include/gomc_b200.h one to one

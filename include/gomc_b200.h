@@ -67,7 +67,8 @@ enum {
   GOMCB200_MOL_FORCE_REC = 3,  /* System::molForceRecRef  */
   GOMCB200_MOL_TORQUE = 4      /* MultiParticle molTorque */
 };
-enum { GOMCB200_K_NEW = 0, GOMCB200_K_REF = 1 };       /* kx[]  vs kxRef[]   */
+enum { GOMCB200_K_NEW = 0, GOMCB200_K_REF = 1,           /* kx[]  vs kxRef[]   */
+       GOMCB200_K_DEVICE = 2 };  /* OR-ed in: read back the device-resident copy */
 enum { GOMCB200_SUM_NEW = 0, GOMCB200_SUM_REF = 1 };   /* sumRnew vs sumRref */
 
 const char *gomcb200_last_error(void);

@@ -90,6 +90,9 @@ def test_reciprocal(gold):
     assert e.nk == nk
     for a, name in zip(e.get_kvectors(0, eng.K_REF, nk), ("kx", "ky", "kz", "hsqr", "prefact")):
         assert np.array_equal(a, d["box0." + name]), name
+    for a, name in zip(e.get_kvectors(0, eng.K_REF | eng.K_DEVICE, nk),
+                       ("kx", "ky", "kz", "hsqr", "prefact")):
+        assert np.array_equal(a, d["box0." + name]), "device " + name
     for algo in (0, 1, 2, 3):      # per-term, SIMT factorised, FP64 MMA, INT8 tensor cores
         e.set_recip_algo(algo)
         en = e.box_reciprocal_sums(0)

@@ -121,6 +121,11 @@ def test_kvectors_bit_exact(case):
     g = e.get_kvectors(0, eng.K_REF, e.nk)
     for a, b in zip(g, (kx, ky, kz, hs, pf)):
         assert np.array_equal(a, b)          # index-compatible with the host list
+    # the copy the kernels read (kx, ky, kz, |k|^2 regenerated on the device from the row
+    # table) carries the same bits
+    for which in (eng.K_REF, eng.K_NEW):
+        for a, b in zip(e.get_kvectors(0, which | eng.K_DEVICE, e.nk), (kx, ky, kz, hs, pf)):
+            assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("algo", [0, 1, 2, 3])
