@@ -175,7 +175,10 @@ struct gomcb200_engine {
   bool trialActive = false;
   std::vector<BoxState> box;
   int imageTotal = 0;
-  int recipAlgo = 2;  // 0 direct, 1 factorised SIMT, 2 factorised DMMA, 3 int8 tensor cores
+  // 0 direct, 1 factorised SIMT, 2 factorised DMMA, 3 int8 tensor cores, 4 = choose 2 or 3 by
+  // the size of the sum: charged atoms x k-vectors >= recipAutoWork goes to the int8 kernel
+  int recipAlgo = 4;
+  double recipAutoWork = 1e11;
   int shardRank = 0, shardWorld = 1;
   // scratch
   DevBuf<double> part, blockA, blockB, result, molBuf, probeOut;
@@ -971,7 +974,10 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
   int nSlabs = 1;
   if (e->timing) cudaEventRecord(e->ev[2], e->stream);
   bool i8Done = false;
-  if (e->recipAlgo == 3 && ks.mmaValid && nAt > 0) {
+  // whole-box size (not the shard's), so that every rank of a sharded box picks the same kernel
+  const bool wantI8 =
+      e->recipAlgo == 3 || (e->recipAlgo == 4 && (double)nAt * (double)nk >= e->recipAutoWork);
+  if (wantI8 && ks.mmaValid && nAt > 0) {
     rc = build_mma_tiles(e, ks);
     if (rc) return rc;
     I8Args ia;
@@ -3023,8 +3029,14 @@ int gomcb200_mark_coords_changed(gomcb200_engine *e) {
 }
 
 int gomcb200_set_recip_algo(gomcb200_engine *e, int algo) {
-  if (!e || algo < 0 || algo > 3) return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!e || algo < 0 || algo > 4) return fail(GOMCB200_EINVAL, "bad arguments");
   e->recipAlgo = algo;
+  return 0;
+}
+
+int gomcb200_set_recip_auto_work(gomcb200_engine *e, double work) {
+  if (!e || !(work >= 0.0)) return fail(GOMCB200_EINVAL, "bad arguments");
+  e->recipAutoWork = work;
   return 0;
 }
 

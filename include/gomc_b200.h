@@ -393,10 +393,17 @@ int gomcb200_set_shard(gomcb200_engine *e, int rank, int world);
 int gomcb200_mark_coords_changed(gomcb200_engine *e);
 
 /* ---- tuning / introspection (tests and bench only) ---------------------- */
-/* algorithm for the structure-factor build: 0 = direct sincos per (atom,k)
+/* algorithm for the structure-factor build (the sums behind BoxReciprocalSetup/
+ * BoxReciprocalSums, src/Ewald.cpp:213-330): 0 = direct sincos per (atom,k)
  * (reference algorithm), 1 = factorised per-axis phases on the FP64 CUDA
- * cores, 2 = the same factorisation on the FP64 MMA path (DMMA; default). */
+ * cores, 2 = the same factorisation on the FP64 MMA path (DMMA), 3 = byte-
+ * sliced fixed point on the INT8 tensor cores (tcgen05 + TMEM; agrees with 2
+ * to < 1e-11 relative), 4 = default: 2, or 3 once charged atoms x k-vectors
+ * of the box reaches the work threshold below (1e11: boxes of ~3e5 atoms up,
+ * where the INT8 kernel measured 2.6x faster). */
 int gomcb200_set_recip_algo(gomcb200_engine *e, int algo);
+/* work threshold (charged atoms x k-vectors) of algorithm 4 */
+int gomcb200_set_recip_auto_work(gomcb200_engine *e, double work);
 /* CUDA-event time (ms) of the kernels launched by the last call, and the
  * device time of its dominant kernel. */
 int gomcb200_last_timing(const gomcb200_engine *e, float *totalMs,

@@ -147,6 +147,34 @@ def test_box_reciprocal_sums(case, algo):
     assert abs(e.box_reciprocal(0, False) - eo) <= TOL * abs(eo)
 
 
+def test_recip_algo_auto_selects_by_work(case):
+    """Algorithm 4 (the default) is algorithm 2 below the work threshold and algorithm 3 from
+    it on: same bits as the explicitly selected kernel."""
+    s, e, o = case
+    if not _ewald(s):
+        pytest.skip("no Ewald")
+
+    def sums(algo, work=None):
+        e.set_recip_algo(algo)
+        if work is not None:
+            e.set_recip_auto_work(work)
+        e.mark_coords_changed()
+        en = e.box_reciprocal_sums(0)
+        return (en,) + tuple(e.get_recip_sums(0, eng.SUM_NEW, e.nk))
+
+    try:
+        fp64, i8 = sums(2), sums(3)
+        lo, hi = sums(4, 1e30), sums(4, 0.0)
+        for a, b in zip(lo, fp64):
+            assert np.array_equal(a, b)
+        for a, b in zip(hi, i8):
+            assert np.array_equal(a, b)
+        assert abs(i8[0] - fp64[0]) <= 1e-10 * abs(fp64[0])
+    finally:
+        e.set_recip_auto_work(1e11)
+        e.set_recip_algo(4)
+
+
 def test_mol_and_swap_reciprocal(case):
     s, e, o = case
     if not _ewald(s):
