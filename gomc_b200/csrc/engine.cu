@@ -89,7 +89,7 @@ struct KSet {
   std::vector<int4> hMmaTiles, hRowsSorted, hSegs;
   // int8 tensor-core path (recip_i8.cuh): tiles of 64 rows x 32 c values
   DevBuf<int4> i8Tiles, i8Rows;
-  int i8NTiles = 0, i8NCB = 0, i8NSL = 6, i8CPer = 32, i8Nb = 64;
+  int i8NTiles = 0, i8NTilesAll = 0, i8NCB = 0, i8NSL = 6, i8CPer = 32, i8Nb = 64;
   // DMMA reciprocal-force plan (force_mma.cuh)
   DevBuf<int4> fmRows;
   DevBuf<FmTile> fmTiles;
@@ -771,14 +771,17 @@ int build_mma_tiles(gomcb200_engine *e, KSet &ks) {
     }
   }
   {  // int8 path: tiles of 8 a values x 8 b values (the XY table slice a tile needs is then
-     // 16 entries instead of all of them), one tile per column block it reaches
+     // 16 entries instead of all of them), one tile per column block it reaches.  Multi-GPU:
+     // the blocks are cut from ALL rows of the box (a rank's cmax band is a thin ring in the
+     // (a, b) plane and would fill 8 x 8 blocks badly) and the equal-cost tiles are dealt
+     // round-robin, so again every S(k) is complete on exactly one GPU.
     ks.i8NSL = KZ1 <= 32 ? 6 : 5;
     ks.i8CPer = KZ1 <= 32 ? ((KZ1 + 7) / 8) * 8 : (KZ1 <= 40 ? ((KZ1 + 7) / 8) * 8 : 40);
     ks.i8Nb = 2 * ks.i8CPer;
     const int ncb = (KZ1 + ks.i8CPer - 1) / ks.i8CPer;
     const int KX1 = ks.nmax[0] + 1;
     std::map<std::pair<int, int>, std::vector<int4>> blocks;
-    for (const int4 &rw : mrows) {
+    for (const int4 &rw : ks.hRowsSorted) {
       if (rw.z < 0) continue;
       const int bb = rw.y >= 0 ? rw.y / 8 : -((-rw.y + 7) / 8);  // floor(b / 8)
       auto &slots = blocks[{rw.x / 8, bb}];
@@ -800,13 +803,15 @@ int build_mma_tiles(gomcb200_engine *e, KSet &ks) {
               [](const std::pair<int, int4> &l, const std::pair<int, int4> &r) {
                 return l.first > r.first;
               });
+    int nAll = 0;
     for (int cb = 0; cb < ncb; ++cb)
       for (auto &o : order) {
         if (o.first < ks.i8CPer * cb) break;
         int4 d = o.second;
         d.y = cb;
-        it.push_back(d);
+        if (nAll++ % e->shardWorld == e->shardRank) it.push_back(d);
       }
+    ks.i8NTilesAll = nAll;
     ks.i8NTiles = (int)it.size();
     ks.i8NCB = ncb;
     CK(ks.i8Rows.reserve(irows.size() + 1));
@@ -997,7 +1002,12 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     const size_t smem = (size_t)TR * kI8TabEntries * 32 * 16 + kI8AR * (size_t)NSL * kI8PlaneA +
                         BR * (size_t)NSL * planeB + (2 * TR + 2 * BR + 2 * kI8AR + 1) * 8 + 16 +
                         34 * 16;  // + the issuer's instruction list (16 B aligned)
-    if (smem + 1024 <= e->smemOptin && ks.i8NTiles > 0) {
+    if (smem + 1024 <= e->smemOptin && ks.i8NTilesAll > 0 && ks.i8NTiles == 0) {
+      // more ranks than tiles: this rank owns no k-vector
+      CK(e->part.reserve((size_t)2 * nkStride + 64));
+      CK(cudaMemsetAsync(e->part.p, 0, sizeof(double) * (size_t)2 * nkStride, e->stream));
+      i8Done = true;
+    } else if (smem + 1024 <= e->smemOptin && ks.i8NTiles > 0) {
       // |A| < 1 needs q / qScale with qScale a power of two above every |q| of the box
       double qmax = 0.0;
       for (int a : bx.hCharged) qmax = std::max(qmax, std::fabs(e->hChargeEff[a]));

@@ -139,7 +139,7 @@ def test_box_reciprocal_sums(case, algo):
     e.set_recip_algo(algo)
     en = e.box_reciprocal_sums(0)
     gR, gI = e.get_recip_sums(0, eng.SUM_NEW, e.nk)
-    e.set_recip_algo(2)
+    e.set_recip_algo(4)
     scale = max(np.max(np.abs(sR)), np.max(np.abs(sI)))
     assert np.max(np.abs(gR - sR)) <= TOL * scale
     assert np.max(np.abs(gI - sI)) <= TOL * scale
@@ -293,11 +293,12 @@ def test_sharded_partials_sum_to_full(case, world, algo):
                 owned += mine
                 # same k, different atom-slab split: equal up to summation order
                 scale = max(np.max(np.abs(fR)), np.max(np.abs(fI)))
-                assert np.max(np.abs(pR[mine] - fR[mine])) <= 1e-12 * scale
-                assert np.max(np.abs(pI[mine] - fI[mine])) <= 1e-12 * scale
+                if mine.any():          # a box with fewer INT8 tiles than ranks leaves some idle
+                    assert np.max(np.abs(pR[mine] - fR[mine])) <= 1e-12 * scale
+                    assert np.max(np.abs(pI[mine] - fI[mine])) <= 1e-12 * scale
     finally:
         e.set_shard(0, 1)
-        e.set_recip_algo(2)
+        e.set_recip_algo(4)
     assert abs(lj - lj0) <= 1e-12 * abs(lj0)
     assert abs(re - re0) <= 1e-12 * max(abs(re0), 1.0)
     if _ewald(s):
