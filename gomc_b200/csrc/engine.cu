@@ -111,6 +111,7 @@ struct BoxState {
   bool nonOrth = false;
   double B[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Bi[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   std::vector<int> hMols, hAtoms, hCharged;
+  double qMaxAbs = 0.0;  // largest |charge| in the box (fixed-point scale of the int8 kernel)
   DevBuf<int> molList, atomList, chargedList;
   int nMols = 0, nAtoms = 0, nCharged = 0;
   // cell-sorted copy
@@ -1009,8 +1010,8 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
       i8Done = true;
     } else if (smem + 1024 <= e->smemOptin && ks.i8NTiles > 0) {
       // |A| < 1 needs q / qScale with qScale a power of two above every |q| of the box
-      double qmax = 0.0;
-      for (int a : bx.hCharged) qmax = std::max(qmax, std::fabs(e->hChargeEff[a]));
+      // (|qEff| = |q| sqrt(lambda) <= |q|: the bound taken when the box was filled holds)
+      const double qmax = bx.qMaxAbs;
       int ex = 0;
       std::frexp(qmax, &ex);  // qmax = m * 2^ex, m in [0.5, 1)
       const double qScale = std::ldexp(1.0, ex);
@@ -1730,13 +1731,17 @@ int gomcb200_set_box_molecules(gomcb200_engine *e, int box, const int *molIndice
     if (mb == box) mb = -1;
   bx.hAtoms.clear();
   bx.hCharged.clear();
+  bx.qMaxAbs = 0.0;
   for (int m : bx.hMols) {
     if (m < 0 || m >= e->nMols) return fail(GOMCB200_EINVAL, "molecule index %d out of range", m);
     e->hMolBox[m] = box;
     for (int a = e->hMolStart[m]; a < e->hMolStart[m + 1]; ++a) {
       bx.hAtoms.push_back(a);
       // Ewald::Init particleHasNoCharge, src/Ewald.cpp:107-111
-      if (!(std::fabs(e->hCharge[a]) < 0.000000001)) bx.hCharged.push_back(a);
+      if (!(std::fabs(e->hCharge[a]) < 0.000000001)) {
+        bx.hCharged.push_back(a);
+        bx.qMaxAbs = std::max(bx.qMaxAbs, std::fabs(e->hCharge[a]));
+      }
     }
   }
   // ascending atom order: stable radix sort then yields ascending-within-cell
