@@ -320,7 +320,13 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
     const int offX = rwp.z < 0 ? -1 : (rwp.x - tile.z) * 32 * 16;  // empty slot: zeros
     const int offY = (8 + ia.KX1 + (rwp.y < 0 ? -rwp.y : rwp.y) - tile.w) * 32 * 16;
     const double magic = 1.5 * (double)(1ll << (52 - i8_frac_a(NSL)));
+    // Re goes to row 2*pr, Im to row 2*pr+1.  A warp holds 4 pairs x 8 quads, and the two K
+    // chunks of a row are 128 B apart (same banks), so the quads of the second chunk store
+    // their Im word while those of the first store Re, and vice versa: the 32 words of one
+    // store instruction then cover all 32 banks.
+    const bool swp = quad >= 4;
     const unsigned offRe = i8_off(2 * pr, 4 * quad), offIm = i8_off(2 * pr + 1, 4 * quad);
+    const unsigned offS[2] = {swp ? offIm : offRe, swp ? offRe : offIm};
     // sum over this thread's atoms of the QUANTISED a, kept as integers per byte plane (one
     // dp4a per stored word; exact); the epilogue needs it to undo the +1 offset of B
     int accRe[NSL], accIm[NSL];
@@ -353,10 +359,11 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
                 mi = fma(xv.x, yv.y, fma(xv.y, yv.x, magic));
               }
             }
-            lo[u][0][i] = (unsigned)__double2loint(mr);
-            hi[u][0][i] = (unsigned)__double2hiint(mr);
-            lo[u][1][i] = (unsigned)__double2loint(mi);
-            hi[u][1][i] = (unsigned)__double2hiint(mi);
+            const double v0 = swp ? mi : mr, v1 = swp ? mr : mi;  // slot 0 / slot 1
+            lo[u][0][i] = (unsigned)__double2loint(v0);
+            hi[u][0][i] = (unsigned)__double2hiint(v0);
+            lo[u][1][i] = (unsigned)__double2loint(v1);
+            hi[u][1][i] = (unsigned)__double2hiint(v1);
           }
           __syncwarp();
           if (lane == 0) i8_mbar_arrive(bTabEmpty + 8 * st);  // table stage can be refilled
@@ -382,8 +389,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
             o[3] = __byte_perm(t2, t3, 0x7632);
             o[4] = __byte_perm(t4, t5, 0x5410);
             o[5] = __byte_perm(t4, t5, 0x7632);
-            unsigned *dst = reinterpret_cast<unsigned *>(ap + (c ? offIm : offRe));
-            int *acc = c ? accIm : accRe;
+            unsigned *dst = reinterpret_cast<unsigned *>(ap + offS[c]);
+            int *acc = c ? accIm : accRe;  // slot sums; swapped back after the loop
 #pragma unroll
             for (int j = 0; j < NSL; ++j) {
               dst[j * kI8PlaneA / 4] = o[j];
@@ -403,8 +410,8 @@ __global__ void __launch_bounds__(kI8Threads, 1) k_recip_i8(I8Args ia) {
     long long totRe = 0, totIm = 0;
 #pragma unroll
     for (int j = 0; j < NSL; ++j) {
-      totRe += (long long)accRe[j] << (8 * j);
-      totIm += (long long)accIm[j] << (8 * j);
+      totRe += (long long)(swp ? accIm[j] : accRe[j]) << (8 * j);
+      totIm += (long long)(swp ? accRe[j] : accIm[j]) << (8 * j);
     }
     const double fscale = 1.0 / (double)(1ll << i8_frac_a(NSL));
     const double sumRe = (double)totRe * fscale, sumIm = (double)totIm * fscale;
