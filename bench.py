@@ -423,14 +423,29 @@ def main():
     torch.cuda.synchronize()
     # nvidia-smi needs ~1 s to deliver its first sample: keep the GPU under the same
     # load until it does, so that the clocks are those of the timed region
-    t_wait = time.perf_counter()
-    while rank == 0 and not sampler.lines and time.perf_counter() - t_wait < 5.0:
-        step(False)
+    def load_until_samples(n, max_s):
+        # same step, untimed, until rank 0 holds n samples; every rank runs the same number
+        # of steps (the step ends in a collective), rank 0 decides
+        t_wait = time.perf_counter()
+        while True:
+            go = int(rank == 0 and len(sampler.lines) < n and time.perf_counter() - t_wait < max_s)
+            if world > 1:
+                flag = torch.tensor([go], device="cuda")
+                dist.broadcast(flag, 0)
+                go = int(flag.item())
+            if not go:
+                return
+            step(False)
+
+    load_until_samples(1, 5.0)
     sampler.lines.clear()
     l0 = e.launch_count()
     dev_ms, dom_ms, wall_ms, en_res = timed(False, args.steps)
     l1 = e.launch_count()
     dev_ms_h, _, wall_ms_h, en_host = timed(True, args.steps)
+    # a short timed region (sharded runs take tens of ms) can fall between two 100 ms
+    # nvidia-smi samples: keep the same load running until three samples exist
+    load_until_samples(3, 3.0)
     # secondary metric of BASELINE.json: MultiParticle moves/s = the energy/force work of
     # MultiParticle::CalcEn (src/moves/MultiParticle.h:414-441): BoxReciprocalSums + BoxForce
     # + BoxReciprocal + BoxForceReciprocal + torque, coordinates resident (single GPU)
