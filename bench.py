@@ -7,6 +7,8 @@ the synthetic SPC/E box BASELINE's target is quoted on (100 002 atoms,
 Rcut = RcutCoulomb = 10 A, Tolerance 1e-5 -> 102 978 k-vectors).
 
   python bench.py --gpus N --steps K --warmup W [--workload spce100k|spce10k|argon4k|electrolyte1m]
+                  [--recip-algo 2|3]    # force the FP64-MMA / INT8 structure-factor kernel
+                                        # (default: the engine's choice, INT8 from 1e11 atom x k terms)
   python bench.py --impl reference ...   # the reference's own CPU path on the host cores
 
 One JSON line on stdout (rank 0).  `value` is timed with inputs resident in
