@@ -27,6 +27,7 @@
 #include "recip_mma.cuh"
 #include "recip_i8.cuh"
 #include "force_mma.cuh"
+#include "nufft.h"
 
 using namespace gb;
 
@@ -52,10 +53,29 @@ int fail(int code, const char *fmt, ...) {
                   cudaGetErrorString(_e));                                    \
   } while (0)
 
+// Owning device buffer: freed when the engine (or the KSet / BoxState holding it) goes away.
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), cap(o.cap) {
+    o.p = nullptr;
+    o.cap = 0;
+  }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p;
+      cap = o.cap;
+      o.p = nullptr;
+      o.cap = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
@@ -103,6 +123,9 @@ struct KSet {
   int mmaZS = 0;
   bool mmaValid = false;
   int itemsForAtoms = -1, itemsForShard = -1, nCtas = 0, maxSlabs = 0, itemsAT = 0;
+  // non-uniform FFT path (nufft.cu): fine grid + window of this k set
+  gbn::NufftGrid ng;
+  bool ngValid = false;
 };
 
 struct BoxState {
@@ -176,9 +199,10 @@ struct gomcb200_engine {
   bool trialActive = false;
   std::vector<BoxState> box;
   int imageTotal = 0;
-  // 0 direct, 1 factorised SIMT, 2 factorised DMMA, 3 int8 tensor cores, 4 = choose 2 or 3 by
-  // the size of the sum: charged atoms x k-vectors >= recipAutoWork goes to the int8 kernel
+  // 0 direct, 1 factorised SIMT, 2 factorised DMMA, 3 int8 tensor cores, 5 = non-uniform FFT,
+  // 4 = automatic: the non-uniform FFT for orthogonal boxes, the direct kernels otherwise
   int recipAlgo = 4;
+  gbn::Nufft *nufft = nullptr;
   double recipAutoWork = 1e11;
   int shardRank = 0, shardWorld = 1;
   // scratch
@@ -271,6 +295,18 @@ int check_box(const gomcb200_engine *e, int b, bool needAxes = true) {
     return fail(GOMCB200_EINVAL, "Potential EXP6: gomcb200_init_exp6 not called");
   if (needAxes && !e->box[b].haveAxes)
     return fail(GOMCB200_EINVAL, "gomcb200_set_box_axes not called for box %d", b);
+  return 0;
+}
+
+// Entry points that read or update the whole structure factor, or the forces of every atom,
+// are only valid on an unsharded engine: with gomcb200_set_shard(world > 1) the sums of
+// k-vectors owned by other ranks are zero and forces exist only for this rank's cell slab.
+int check_unsharded(const gomcb200_engine *e, const char *what) {
+  if (e && e->shardWorld > 1)
+    return fail(GOMCB200_EINVAL,
+                "%s is not available on a sharded engine (gomcb200_set_shard world %d): "
+                "only the full-box sweeps are sharded",
+                what, e->shardWorld);
   return 0;
 }
 
@@ -979,11 +1015,20 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
   const int nAt = bx.nCharged;
   int nSlabs = 1;
   if (e->timing) cudaEventRecord(e->ev[2], e->stream);
-  bool i8Done = false;
-  // whole-box size (not the shard's), so that every rank of a sharded box picks the same kernel
-  const bool wantI8 =
-      e->recipAlgo == 3 || (e->recipAlgo == 4 && (double)nAt * (double)nk >= e->recipAutoWork);
-  if (wantI8 && ks.mmaValid && nAt > 0) {
+  bool i8Done = false, nufftDone = false;
+  const bool wantI8 = e->recipAlgo == 3;
+  if ((e->recipAlgo == 4 || e->recipAlgo == 5) && ks.planValid && ks.ngValid && nAt > 0) {
+    // non-uniform FFT: the whole structure factor at O(N w^3 + n^3 log n).  Multi-GPU: it is
+    // cheap enough to be replicated (every rank then holds the complete sums, which the
+    // single-molecule deltas need); rank 0 alone reports the energy.
+    CK(e->part.reserve((size_t)2 * nkStride + 64));
+    rc = gbn::nufft_type1(e->nufft, e->stream, ks.ng, bx.axis, bx.packed.p, nAt, ks.rows.p,
+                          ks.nRowsPadded, e->part.p, e->part.p + nkStride, &e->launches);
+    if (rc) return fail(GOMCB200_ECUDA, "nufft_type1: %s", gbn::nufft_last_error(e->nufft));
+    nSlabs = 1;
+    nufftDone = true;
+  }
+  if (!nufftDone && wantI8 && ks.mmaValid && nAt > 0) {
     rc = build_mma_tiles(e, ks);
     if (rc) return rc;
     I8Args ia;
@@ -1050,7 +1095,7 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
       i8Done = true;
     }
   }
-  if (i8Done) {
+  if (i8Done || nufftDone) {
   } else if (e->recipAlgo >= 2 && ks.mmaValid && nAt > 0) {
     rc = build_mma_tiles(e, ks);  // (re)derives tiles and ZS for the current shard
     if (rc) return rc;
@@ -1185,6 +1230,8 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
                                            nullptr, e->result.p);
   e->launches += 2;
   CK(cudaGetLastError());
+  if (nufftDone && e->shardWorld > 1 && e->shardRank != 0)  // replicated: counted once
+    CK(cudaMemsetAsync(e->result.p, 0, sizeof(double), e->stream));
   return 0;
 }
 
@@ -1223,7 +1270,9 @@ int stage_molbuf(gomcb200_engine *e, int molIndex, const double *nx, const doubl
     m[1] = nx[a];
     m[2] = ny[a];
     m[3] = nz[a];
-    m[4] = mode == 0 ? e->hx[s + a] : 0.0;  // old coordinates (host mirror)
+    // old coordinates (host mirror); the swap modes carry the lambda = 1 charge there
+    // instead (SwapSelf uses it, src/Ewald.cpp:1375-1391)
+    m[4] = mode == 0 ? e->hx[s + a] : e->hCharge[s + a];
     m[5] = mode == 0 ? e->hy[s + a] : 0.0;
     m[6] = mode == 0 ? e->hz[s + a] : 0.0;
   }
@@ -1485,6 +1534,7 @@ int gomcb200_create(gomcb200_engine **out, int device, int nBoxes) {
   CK(cudaMemset(e->ticket.p, 0, 4 * sizeof(unsigned)));
   CK(e->trialPart.reserve(3 * 2 * kTrialMaxAtoms * kProbeSplit + 8));
   for (auto &ev : e->ev) CK(cudaEventCreate(&ev));
+  e->nufft = gbn::nufft_create();
   *out = e;
   return 0;
 }
@@ -1493,35 +1543,12 @@ int gomcb200_destroy(gomcb200_engine *e) {
   if (!e) return 0;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  e->sigmaSq.release(); e->epsilon_cn.release(); e->nTab.release();
-  e->shiftConst.release(); e->nHalf.release();
-  e->rMin.release(); e->expConst.release(); e->rMaxSq.release();
-  e->mAn.release(); e->mBn.release(); e->mCn.release(); e->mSign.release(); e->mSig6.release();
-  e->kind.release(); e->mol.release(); e->molStart.release();
-  e->x.release(); e->y.release(); e->z.release(); e->q.release();
-  e->comx.release(); e->comy.release(); e->comz.release();
-  for (auto &f : e->force) for (auto &c : f) c.release();
-  for (auto &bx : e->box) {
-    bx.molList.release(); bx.atomList.release(); bx.chargedList.release();
-    bx.keys.release(); bx.keysSorted.release(); bx.vals.release();
-    bx.sortedAtoms.release(); bx.cellStart.release();
-    bx.sx.release(); bx.sy.release(); bx.sz.release(); bx.sq.release(); bx.skm.release();
-    for (auto &ks : bx.kset) {
-      ks.kx.release(); ks.ky.release(); ks.kz.release(); ks.hsqr.release();
-      ks.prefact.release(); ks.rows.release(); ks.tiles.release();
-      ks.mmaRows.release(); ks.mmaTiles.release(); ks.mmaSegs.release(); ks.mmaCtaSeg.release();
-      ks.fmRows.release(); ks.fmTiles.release(); ks.fmW.release(); ks.fmBlocks.release();
-    }
-    for (auto &s : bx.sum) s.release();
-    bx.packed.release();
-  }
-  e->part.release(); e->blockA.release(); e->blockB.release(); e->result.release();
-  e->phaseTables.release();
-  e->molBuf.release(); e->probeOut.release(); e->probes.release(); e->cubTemp.release();
+  // every DevBuf member releases its memory in the engine's destructor (delete below)
   if (e->hRes) cudaFreeHost(e->hRes);
   if (e->hTrial) cudaFreeHost(e->hTrial);
   if (e->hStage) cudaFreeHost(e->hStage);
   for (auto &ev : e->ev) cudaEventDestroy(ev);
+  gbn::nufft_destroy(e->nufft);
   cudaStreamDestroy(e->stream);
   delete e;
   return 0;
@@ -1916,6 +1943,8 @@ int gomcb200_box_inter(gomcb200_engine *e, int box, double *LJEn, double *REn) {
 int gomcb200_box_force(gomcb200_engine *e, int box, double *LJEn, double *REn) {
   int rc = check_box(e, box);
   if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_box_force");
+  if (rc) return rc;
   CK(cudaSetDevice(e->device));
   timing_begin(e);
   rc = run_pair(e, box, true);
@@ -1978,6 +2007,8 @@ int gomcb200_molecule_trial(gomcb200_engine *e, int box, int molIndex, const dou
                             const double *newY, const double *newZ, double *dLJ, double *dReal,
                             int *overlap, double *energyRecipNew) {
   int rc = check_box(e, box);
+  if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_molecule_trial");
   if (rc) return rc;
   if (molIndex < 0 || molIndex >= e->nMols || !newX || !newY || !newZ)
     return fail(GOMCB200_EINVAL, "bad arguments");
@@ -2084,7 +2115,8 @@ int gomcb200_change_self_correction(gomcb200_engine *e, int box, int molIndex, d
     m[1] = e->hx[s + a];
     m[2] = e->hy[s + a];
     m[3] = e->hz[s + a];
-    m[4] = m[5] = m[6] = 0.0;
+    m[4] = e->hCharge[s + a];
+    m[5] = m[6] = 0.0;
   }
   CK(cudaMemcpyAsync(e->molBuf.p, h, nd * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   k_swap_correction<<<1, 128, 0, e->stream>>>(make_params(e, box), e->molBuf.p, e->result.p + 1);
@@ -2101,6 +2133,8 @@ int gomcb200_swap_trial(gomcb200_engine *e, int box, int molIndex, const double 
                         const double *y, const double *z, int insert, double *energyRecipNew,
                         double *correction, double *self) {
   int rc = check_box(e, box);
+  if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_swap_trial");
   if (rc) return rc;
   if (molIndex < 0 || molIndex >= e->nMols || !x || !y || !z)
     return fail(GOMCB200_EINVAL, "bad arguments");
@@ -2172,6 +2206,8 @@ int gomcb200_particle_inter(gomcb200_engine *e, int box, int molIndex, int partI
 
 int gomcb200_calculate_torque(gomcb200_engine *e, int box) {
   int rc = check_box(e, box);
+  if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_calculate_torque");
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   BoxState &bx = e->box[box];
@@ -2246,9 +2282,11 @@ int gomcb200_recip_init(gomcb200_engine *e, int box, const double axis[3], int *
   if (rc) return rc;
   ks.mmaValid = false;
   ks.fmValid = false;
+  ks.ngValid = false;
   if (!rows.empty()) {
     rc = build_plan(e, ks, rows);
     if (rc) return rc;
+    ks.ngValid = gbn::nufft_choose(ks.nmax, &ks.ng) == 0;
     k_gen_kvectors<<<(unsigned)ks.nRowsPadded, 64, 0, e->stream>>>(
         ks.rows.p, ks.cv[0], ks.cv[1], ks.cv[2], ks.kx.p, ks.ky.p, ks.kz.p, ks.hsqr.p);
     CK(cudaGetLastError());
@@ -2336,6 +2374,8 @@ int gomcb200_mol_reciprocal(gomcb200_engine *e, int box, int molIndex, const dou
                             const double *newY, const double *newZ, double *energyRecipNew) {
   int rc = check_box(e, box);
   if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_mol_reciprocal");
+  if (rc) return rc;
   if (molIndex < 0 || molIndex >= e->nMols || !newX || !newY || !newZ || !energyRecipNew)
     return fail(GOMCB200_EINVAL, "bad arguments");
   CK(cudaSetDevice(e->device));
@@ -2347,6 +2387,8 @@ int gomcb200_swap_reciprocal(gomcb200_engine *e, int box, int molIndex, const do
                              double *energyRecipNew) {
   int rc = check_box(e, box);
   if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_swap_reciprocal");
+  if (rc) return rc;
   if (molIndex < 0 || molIndex >= e->nMols || !x || !y || !z || !energyRecipNew)
     return fail(GOMCB200_EINVAL, "bad arguments");
   CK(cudaSetDevice(e->device));
@@ -2357,6 +2399,8 @@ int gomcb200_mol_exchange_reciprocal(gomcb200_engine *e, int box, int n, const d
                                      const double *x, const double *y, const double *z,
                                      int firstCall, double scale, double *energyRecipNew) {
   int rc = check_box(e, box);
+  if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_mol_exchange_reciprocal");
   if (rc) return rc;
   if (n < 0 || (n && (!w || !x || !y || !z)) || !energyRecipNew)
     return fail(GOMCB200_EINVAL, "bad arguments");
@@ -2418,6 +2462,8 @@ int gomcb200_change_recip(gomcb200_engine *e, int box, int molIndex, int nStates
                           const double *lambdaCoul, int iState, double *energyRecip) {
   int rc = check_box(e, box);
   if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_change_recip");
+  if (rc) return rc;
   if (molIndex < 0 || molIndex >= e->nMols || nStates < 1 || nStates > kMaxLambdaStates ||
       !lambdaCoul || iState < 0 || iState >= nStates || !energyRecip)
     return fail(GOMCB200_EINVAL, "bad arguments");
@@ -2469,7 +2515,28 @@ static int run_force_recip(gomcb200_engine *e, int box, const double *sumR, cons
   BoxParams p = make_params(e, box);
   bool done = false;
   int rc;
-  if (e->recipAlgo >= 2 && ks.fmValid && bx.nCharged > 0 && ks.n > 0) {
+  if ((e->recipAlgo == 4 || e->recipAlgo == 5) && ks.planValid && ks.ngValid && bx.nCharged > 0 &&
+      ks.n > 0) {
+    // type-2 non-uniform FFT: potential on the fine grid, analytic window gradient
+    rc = ensure_packed(e, box);
+    if (rc) return rc;
+    if (withIntra) {
+      k_force_recip_intra<<<(bx.nAtoms + 127) / 128, 128, 0, e->stream>>>(
+          p, bx.nAtoms, bx.atomList.p, e->mol.p, e->molStart.p, e->x.p, e->y.p, e->z.p,
+          e->qEff.p, rfx, rfy, rfz);
+      e->launches += 1;
+    } else {
+      const size_t bytes = sizeof(double) * (size_t)e->nAtoms;
+      CK(cudaMemsetAsync(rfx, 0, bytes, e->stream));
+      CK(cudaMemsetAsync(rfy, 0, bytes, e->stream));
+      CK(cudaMemsetAsync(rfz, 0, bytes, e->stream));
+    }
+    rc = gbn::nufft_type2_force(e->nufft, e->stream, ks.ng, bx.axis, bx.packed.p,
+                                bx.chargedList.p, bx.nCharged, ks.rows.p, ks.nRowsPadded,
+                                ks.prefact.p, sumR, sumI, rfx, rfy, rfz, 0, &e->launches);
+    if (rc) return fail(GOMCB200_ECUDA, "nufft_type2_force: %s", gbn::nufft_last_error(e->nufft));
+    done = true;
+  } else if (e->recipAlgo >= 2 && ks.fmValid && bx.nCharged > 0 && ks.n > 0) {
     rc = ensure_packed(e, box);
     if (rc) return rc;
     FmArgs fa;
@@ -2539,6 +2606,8 @@ static int run_force_recip(gomcb200_engine *e, int box, const double *sumR, cons
 
 int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
   int rc = check_box(e, box);
+  if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_box_force_reciprocal");
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   BoxState &bx = e->box[box];
@@ -2615,6 +2684,18 @@ static int mp_transform_impl(gomcb200_engine *e, int box, int brownian, int move
   CK(cudaMemcpyAsync(e->comxT.p, e->comx.p, bm, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(e->comyT.p, e->comy.p, bm, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(e->comzT.p, e->comz.p, bm, cudaMemcpyDeviceToDevice, e->stream));
+  if (e->nBoxes > 1) {
+    // two boxes (GEMC/GCMC): the other box's forces and torques must survive the buffer
+    // exchange of an accepted move -- MultiParticle::Prep copies atomForceRef, molForceRef,
+    // the Rec forces and the torques into the New sets (src/moves/MultiParticle.h:235-239)
+    for (int w = 0; w < 5; ++w) {
+      const size_t bytes =
+          (w == GOMCB200_ATOM_FORCE || w == GOMCB200_ATOM_FORCE_REC) ? ba : bm;
+      for (int c = 0; c < 3; ++c)
+        CK(cudaMemcpyAsync(e->forceT[w][c].p, e->force[w][c].p, bytes, cudaMemcpyDeviceToDevice,
+                           e->stream));
+    }
+  }
   CK(cudaMemsetAsync(e->mpInRange.p, 0, sizeof(int) * (size_t)e->nMols, e->stream));
   for (int c = 0; c < 3; ++c) CK(cudaMemsetAsync(e->mpK[c].p, 0, bm, e->stream));
   if (bx.nMols == 0) return 0;
@@ -2701,6 +2782,8 @@ int gomcb200_mp_coeff(gomcb200_engine *e, int box, int moveType, double max, dou
                       double *wRatio) {
   int rc = check_box(e, box);
   if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_mp_coeff");
+  if (rc) return rc;
   if (!wRatio || moveType < 0 || moveType > 1) return fail(GOMCB200_EINVAL, "bad arguments");
   if (!e->trialActive)
     return fail(GOMCB200_EINVAL, "needs the trial set active (new forces computed on it)");
@@ -2733,6 +2816,8 @@ int gomcb200_mp_coeff(gomcb200_engine *e, int box, int moveType, double max, dou
 int gomcb200_bm_coeff(gomcb200_engine *e, int box, int moveType, double max, double BETA,
                       double *wRatio) {
   int rc = check_box(e, box);
+  if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_bm_coeff");
   if (rc) return rc;
   if (!wRatio || moveType < 0 || moveType > 1) return fail(GOMCB200_EINVAL, "bad arguments");
   if (!e->trialActive)
@@ -2781,6 +2866,8 @@ int gomcb200_box_inter_virial(gomcb200_engine *e, int box, double vT[3], double 
 
 int gomcb200_virial_reciprocal(gomcb200_engine *e, int box, double wT[3]) {
   int rc = check_box(e, box);
+  if (rc) return rc;
+  rc = check_unsharded(e, "gomcb200_virial_reciprocal");
   if (rc) return rc;
   if (!wT) return fail(GOMCB200_EINVAL, "bad arguments");
   wT[0] = wT[1] = wT[2] = 0.0;
@@ -2870,6 +2957,8 @@ int gomcb200_set_recip_ref(gomcb200_engine *e, int box) {
     dst.planValid = true;
   }
   dst.hRowsSorted = src.hRowsSorted;
+  dst.ng = src.ng;
+  dst.ngValid = src.ngValid && dst.planValid;
   dst.mmaValid = src.mmaValid;
   dst.tilesForShard = -1;
   dst.itemsForAtoms = -1;
@@ -3044,7 +3133,7 @@ int gomcb200_mark_coords_changed(gomcb200_engine *e) {
 }
 
 int gomcb200_set_recip_algo(gomcb200_engine *e, int algo) {
-  if (!e || algo < 0 || algo > 4) return fail(GOMCB200_EINVAL, "bad arguments");
+  if (!e || algo < 0 || algo > 5) return fail(GOMCB200_EINVAL, "bad arguments");
   e->recipAlgo = algo;
   return 0;
 }

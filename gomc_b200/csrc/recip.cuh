@@ -466,7 +466,9 @@ __global__ void __launch_bounds__(128)
     corr -= a[0] * b[0] * erf(p.alpha * dist) / dist;
   }
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
-    double q = molBuf[1 + 7 * i];
+    // lambda = 1 charge (slot 4 of the swap-mode record): SwapSelf is not scaled by the
+    // fractional molecule's lambda, the correction above is (src/Ewald.cpp:1340-1391)
+    double q = molBuf[1 + 7 * i + 4];
     self -= q * q;
   }
   double c = block_sum(corr, scratch);

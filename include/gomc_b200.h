@@ -27,7 +27,8 @@
  *    gomc_b200/host keeps that behaviour.)  There is no CPU fallback: with no
  *    usable CUDA device gomcb200_create fails.
  *
- * Arithmetic is IEEE double throughout; lambda == 1 (no fractional molecule).
+ * Arithmetic is IEEE double throughout.  A fractional molecule (lambda < 1, soft-core
+ * pair functors and lambda-scaled Ewald terms) is set with gomcb200_update_lambda.
  * Potentials: VDW (Mie), SHIFT, SWITCH, SWITCH+Martini, EXP6.
  * Orthogonal (gomcb200_set_box_axes) and non-orthogonal (gomcb200_set_box_cell_basis) cells.
  * Threading: one host thread per engine, like the reference.
@@ -384,8 +385,11 @@ int gomcb200_call_full_box_energy(gomcb200_engine *e, int box,
  * replicated; energies returned by box_inter / box_force /
  * box_reciprocal_sums / call_full_box_energy are then PARTIAL sums that the
  * caller all-reduces (3 doubles, NCCL).  sumRnew/sumInew stay distributed:
- * entries of k-vectors owned by other ranks are zero.  world == 1 restores
- * the single-GPU behaviour. */
+ * entries of k-vectors owned by other ranks are zero.  Entry points that need the
+ * complete sums or every atom's force (molecule/swap trials, the reciprocal deltas,
+ * box_force, box_force_reciprocal, virial_reciprocal, calculate_torque, mp/bm_coeff)
+ * return GOMCB200_EINVAL while world > 1.  world == 1 restores the single-GPU
+ * behaviour. */
 int gomcb200_set_shard(gomcb200_engine *e, int rank, int world);
 /* Tell the engine that resident coordinates are to be treated as changed
  * (forces cell re-binning and re-packing on the next sweep), as after a

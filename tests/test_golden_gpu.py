@@ -93,7 +93,8 @@ def test_reciprocal(gold):
     for a, name in zip(e.get_kvectors(0, eng.K_REF | eng.K_DEVICE, nk),
                        ("kx", "ky", "kz", "hsqr", "prefact")):
         assert np.array_equal(a, d["box0." + name]), "device " + name
-    for algo in (0, 1, 2, 3):      # per-term, SIMT factorised, FP64 MMA, INT8 tensor cores
+    # per-term, SIMT factorised, FP64 MMA, INT8 tensor cores, non-uniform FFT
+    for algo in (0, 1, 2, 3, 5):
         e.set_recip_algo(algo)
         en = e.box_reciprocal_sums(0)
         gR, gI = e.get_recip_sums(0, eng.SUM_NEW, nk)
@@ -132,7 +133,7 @@ def test_virial(gold):
     if d["ff.ewald"][0]:
         e.box_reciprocal_sums(0)
         e.set_recip_ref(0)
-        for algo in (0, 2):
+        for algo in (0, 2, 5):
             e.set_recip_algo(algo)
             wT = e.virial_reciprocal(0)
             assert rel_err(wT, d["box0.Virial.recipTens"]) <= TOL

@@ -128,7 +128,7 @@ def test_kvectors_bit_exact(case):
             assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2, 3])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3, 5])
 def test_box_reciprocal_sums(case, algo):
     s, e, o = case
     if not _ewald(s):
@@ -147,31 +147,36 @@ def test_box_reciprocal_sums(case, algo):
     assert abs(e.box_reciprocal(0, False) - eo) <= TOL * abs(eo)
 
 
-def test_recip_algo_auto_selects_by_work(case):
-    """Algorithm 4 (the default) is algorithm 2 below the work threshold and algorithm 3 from
-    it on: same bits as the explicitly selected kernel."""
+def test_recip_algo_auto_is_nufft(case):
+    """Algorithm 4 (the default) is the non-uniform FFT (algorithm 5) for an orthogonal box and
+    the per-term kernel for a slanted one: same bits as the explicitly selected kernel.  The
+    non-uniform FFT itself agrees with the FP64-MMA sum to 1e-11 of max |S| (window error
+    ~1e-13), far inside the 1e-9 bar, and the INT8 kernel to 1e-10."""
     s, e, o = case
     if not _ewald(s):
         pytest.skip("no Ewald")
 
-    def sums(algo, work=None):
+    def sums(algo):
         e.set_recip_algo(algo)
-        if work is not None:
-            e.set_recip_auto_work(work)
         e.mark_coords_changed()
         en = e.box_reciprocal_sums(0)
         return (en,) + tuple(e.get_recip_sums(0, eng.SUM_NEW, e.nk))
 
     try:
-        fp64, i8 = sums(2), sums(3)
-        lo, hi = sums(4, 1e30), sums(4, 0.0)
-        for a, b in zip(lo, fp64):
-            assert np.array_equal(a, b)
-        for a, b in zip(hi, i8):
+        slanted = getattr(s, "cell_basis", None) is not None
+        fp64, i8, auto, nf = sums(2), sums(3), sums(4), sums(5)
+        for a, b in zip(auto, sums(0) if slanted else nf):
             assert np.array_equal(a, b)
         assert abs(i8[0] - fp64[0]) <= 1e-10 * abs(fp64[0])
+        scale = max(np.max(np.abs(fp64[1])), np.max(np.abs(fp64[2])))
+        assert abs(nf[0] - fp64[0]) <= 1e-11 * abs(fp64[0])
+        assert np.max(np.abs(nf[1] - fp64[1])) <= 1e-11 * scale
+        assert np.max(np.abs(nf[2] - fp64[2])) <= 1e-11 * scale
+        # bit-reproducible: gather spreading in sorted order, no atomics
+        again = sums(5)
+        for a, b in zip(again, nf):
+            assert np.array_equal(a, b)
     finally:
-        e.set_recip_auto_work(1e11)
         e.set_recip_algo(4)
 
 
@@ -209,7 +214,8 @@ def test_mol_and_swap_reciprocal(case):
     assert rel_err(rR, sR) <= TOL and rel_err(rI, sI) <= TOL
 
 
-def test_force_reciprocal_and_torque(case):
+@pytest.mark.parametrize("algo", [2, 5])   # FP64-MMA GEMM; type-2 non-uniform FFT
+def test_force_reciprocal_and_torque(case, algo):
     s, e, o = case
     if not _ewald(s):
         pytest.skip("no Ewald")
@@ -217,7 +223,11 @@ def test_force_reciprocal_and_torque(case):
     sR, sI = o.box_recip_sums(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge, kx, ky, kz)
     e.copy_recip(0)
     e.box_force(0)
-    e.box_force_reciprocal(0)
+    e.set_recip_algo(algo)
+    try:
+        e.box_force_reciprocal(0)
+    finally:
+        e.set_recip_algo(4)
     e.calculate_torque(0)
     rF, mR = o.box_force_reciprocal(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge, kx, ky,
                                     kz, pf, sR, sI, s.n_mols)
