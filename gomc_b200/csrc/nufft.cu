@@ -39,7 +39,6 @@ namespace gbn {
 namespace {
 
 constexpr int kBrick = 16;     // bin edge in grid points (>= w/2 + 1)
-constexpr int kSlice = 128;    // candidate atoms tested per round of the spread kernel
 constexpr int kMaxW = 16;
 constexpr int kZPad = kBrick - 1;            // zero padding either side of the z table
 constexpr int kZTab = kMaxW + 2 * kZPad + 2; // 48 entries
@@ -148,89 +147,115 @@ __global__ void k_nufft_tables(GridGeom g, int nAtoms, double beta,
 }
 
 // ---- spread (gather) ----------------------------------------------------------------
-// One CTA = one 16 x 16 x 16 brick of the fine grid.  Warp w owns the 8 x 4 patch of
-// (x, y) columns (w & 1, w >> 1) of the brick, each lane one column with its 16 z values
-// in registers.  The atoms of the 27 neighbouring bins are taken in fixed order, 128
-// candidates per round; those whose stencil reaches the brick are compacted (ordered)
-// and their window tables staged in shared memory; every warp then adds the atoms that
-// reach its patch: a = Tx[ix] * Ty[iy] once, 16 DFMA with broadcast LDS of the z table.
+// One CTA (4 warps) = one 16 x 16 x 16 brick of the fine grid; warp w owns the 8 x 8 patch
+// of (x, y) columns (w & 1, w >> 1), each lane two columns (y and y + 4) with their 16 z
+// values in registers (32 accumulators).  The atoms of the 27 neighbouring bins are the
+// candidates; warp w scans the bins w, w+4, ... in order and contributes up to kTake atoms
+// whose stencil reaches the brick to each round (its own list segment: no CTA-wide
+// compaction, and the order -- segment 0, 1, 2, 3, each in scan order -- is fixed, so the
+// floating-point sums are reproducible).  Per round: stage the window tables of the listed
+// atoms in shared memory, then every warp adds the atoms that reach its patch:
+// a0/a1 = Tx[ix] * Ty[iy] once, then 32 DFMA against 8 LDS.128 of the zero-padded z table.
+constexpr int kTake = 16;               // atoms per warp per round
+constexpr int kChunk = 4 * kTake;       // table slots per round
+
 template <int W>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(128, 4)
     k_nufft_spread(GridGeom g, const int *__restrict__ binStart, const int4 *__restrict__ start,
                    const double *__restrict__ tab, double *__restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  double *sTx = reinterpret_cast<double *>(smemRaw);  // [kSlice][W]
-  double *sTy = sTx + kSlice * W;                     // [kSlice][W]
-  double *sTz = sTy + kSlice * W;                     // [kSlice][kZTab], zero padded
-  int *sX0 = reinterpret_cast<int *>(sTz + kSlice * kZTab);
-  int *sY0 = sX0 + kSlice;
-  int *sZo = sY0 + kSlice;
-  int *sSrc = sZo + kSlice;  // sorted position of the compacted atom
-  __shared__ int warpCount[8];
-  __shared__ int nRelSh;
+  double *sTz = reinterpret_cast<double *>(smemRaw);  // [kChunk][kZTab], zero padded, 16 B rows
+  double *sTx = sTz + kChunk * kZTab;                 // [kChunk][W]
+  double *sTy = sTx + kChunk * W;                     // [kChunk][W]
+  int *sX0 = reinterpret_cast<int *>(sTy + kChunk * W);
+  int *sY0 = sX0 + kChunk;
+  int *sZo = sY0 + kChunk;
+  int *sSrc = sZo + kChunk;
+  __shared__ int cnt[4];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned ltMask = (1u << lane) - 1u;
   const int bz = blockIdx.x % g.nb[2];
   const int by = (blockIdx.x / g.nb[2]) % g.nb[1];
   const int bx = blockIdx.x / (g.nb[2] * g.nb[1]);
   const int bx0 = bx * kBrick, by0 = by * kBrick, bz0 = bz * kBrick;
-  const int gx = bx0 + 8 * (warp & 1) + (lane & 7);
-  const int gy = by0 + 4 * (warp >> 1) + (lane >> 3);
+  const int px0 = bx0 + 8 * (warp & 1), py0 = by0 + 8 * (warp >> 1);
+  const int gx = px0 + (lane & 7);
+  const int gyA = py0 + (lane >> 3), gyB = gyA + 4;
   const int mx = g.n[0] - 1, my = g.n[1] - 1, mz = g.n[2] - 1;
 
-  double acc[kBrick];
+  double acc0[kBrick], acc1[kBrick];
 #pragma unroll
-  for (int j = 0; j < kBrick; ++j) acc[j] = 0.0;
+  for (int j = 0; j < kBrick; ++j) acc0[j] = acc1[j] = 0.0;
+  for (int t = threadIdx.x; t < kChunk * kZTab; t += blockDim.x) sTz[t] = 0.0;
 
-  // zero the z-table padding once (the staged part is rewritten every round)
-  for (int t = threadIdx.x; t < kSlice * kZTab; t += blockDim.x) sTz[t] = 0.0;
+  // candidate cursor of this warp (all warp-uniform)
+  int curNbr = warp - 4, curPos = 0, curEnd = 0;
+  unsigned pendMask = 0u;
+  int pendBase = 0;
+  int pstX = 0, pstY = 0, pZo = 0;  // this lane's candidate of the pending batch
 
-  for (int nbr = 0; nbr < 27; ++nbr) {
-    int cx = bx + nbr / 9 - 1, cy = by + (nbr / 3) % 3 - 1, cz = bz + nbr % 3 - 1;
-    cx += cx < 0 ? g.nb[0] : 0;
-    cx -= cx >= g.nb[0] ? g.nb[0] : 0;
-    cy += cy < 0 ? g.nb[1] : 0;
-    cy -= cy >= g.nb[1] ? g.nb[1] : 0;
-    cz += cz < 0 ? g.nb[2] : 0;
-    cz -= cz >= g.nb[2] ? g.nb[2] : 0;
-    const int bin = (cx * g.nb[1] + cy) * g.nb[2] + cz;
-    const int sBeg = binStart[bin], sEnd = binStart[bin + 1];
-    for (int base = sBeg; base < sEnd; base += kSlice) {
-      __syncthreads();  // previous round fully consumed
-      // ---- test + ordered compaction (threads 0..127, four warps) ----
-      bool rel = false;
-      int4 st = make_int4(0, 0, 0, 0);
-      int zo = 0;
-      const int s = base + (int)threadIdx.x;
-      if (threadIdx.x < kSlice && s < sEnd) {
-        st = start[s];
-        // offset of the brick's first point inside the stencil, unwrapped to
-        // [-(kBrick-1), n-kBrick]: brick point j has stencil index o + j, so the stencil
-        // reaches the brick iff o < W (n >= 64 > W + kBrick keeps this unambiguous)
-        const int ox = ((bx0 - st.x + (kBrick - 1)) & mx) - (kBrick - 1);
-        const int oy = ((by0 - st.y + (kBrick - 1)) & my) - (kBrick - 1);
-        const int oz = ((bz0 - st.z + (kBrick - 1)) & mz) - (kBrick - 1);
-        rel = ox < W && oy < W && oz < W;
-        zo = oz;
+  for (;;) {
+    // ---- fill: up to kTake relevant atoms of this warp's bins ----
+    int nw = 0;
+    while (nw < kTake) {
+      if (pendMask == 0u) {
+        while (curPos >= curEnd && curNbr + 4 < 27) {
+          curNbr += 4;
+          int cx = bx + curNbr / 9 - 1, cy = by + (curNbr / 3) % 3 - 1, cz = bz + curNbr % 3 - 1;
+          cx += cx < 0 ? g.nb[0] : 0;
+          cx -= cx >= g.nb[0] ? g.nb[0] : 0;
+          cy += cy < 0 ? g.nb[1] : 0;
+          cy -= cy >= g.nb[1] ? g.nb[1] : 0;
+          cz += cz < 0 ? g.nb[2] : 0;
+          cz -= cz >= g.nb[2] ? g.nb[2] : 0;
+          const int bin = (cx * g.nb[1] + cy) * g.nb[2] + cz;
+          curPos = binStart[bin];
+          curEnd = binStart[bin + 1];
+        }
+        if (curPos >= curEnd) break;  // exhausted
+        const int s = curPos + lane;
+        bool rel = false;
+        if (s < curEnd) {
+          const int4 st = start[s];
+          // offset of the brick's first point inside the stencil, unwrapped to
+          // [-(kBrick-1), n-kBrick]: brick point j has stencil index o + j, so the stencil
+          // reaches the brick iff o < W (n >= 64 > W + kBrick keeps this unambiguous)
+          const int ox = ((bx0 - st.x + (kBrick - 1)) & mx) - (kBrick - 1);
+          const int oy = ((by0 - st.y + (kBrick - 1)) & my) - (kBrick - 1);
+          const int oz = ((bz0 - st.z + (kBrick - 1)) & mz) - (kBrick - 1);
+          rel = ox < W && oy < W && oz < W;
+          pstX = st.x;
+          pstY = st.y;
+          pZo = oz + kZPad;  // index of the brick's first z point in the padded table
+        }
+        pendMask = __ballot_sync(0xffffffffu, rel);
+        pendBase = curPos;
+        curPos += 32;
+        if (pendMask == 0u) continue;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, rel);
-      if (lane == 0) warpCount[warp] = __popc(m);
-      __syncthreads();
-      int before = 0;
-      for (int w2 = 0; w2 < warp; ++w2) before += warpCount[w2];
-      if (rel) {
-        const int pos = before + __popc(m & ((1u << lane) - 1u));
-        sX0[pos] = st.x;
-        sY0[pos] = st.y;
-        sZo[pos] = zo + kZPad;  // index of the brick's first z point in the padded table
-        sSrc[pos] = s;
+      const int take = min(__popc(pendMask), kTake - nw);
+      const int myRank = __popc(pendMask & ltMask);
+      if (((pendMask >> lane) & 1u) && myRank < take) {
+        const int pos = warp * kTake + nw + myRank;
+        sX0[pos] = pstX;
+        sY0[pos] = pstY;
+        sZo[pos] = pZo;
+        sSrc[pos] = pendBase + lane;
       }
-      if (threadIdx.x == 0) nRelSh = warpCount[0] + warpCount[1] + warpCount[2] + warpCount[3];
-      __syncthreads();
-      const int nRel = nRelSh;
-      // ---- stage the tables of the compacted atoms ----
-      for (int t = threadIdx.x; t < nRel * 3 * W; t += blockDim.x) {
-        const int r = t / (3 * W), e = t - r * 3 * W;
+      for (int t = 0; t < take; ++t) pendMask &= pendMask - 1u;  // drop the taken bits
+      nw += take;
+    }
+    if (lane == 0) cnt[warp] = nw;
+    __syncthreads();
+    const int c0 = cnt[0], c1 = cnt[1], c2 = cnt[2], c3 = cnt[3];
+    if (c0 + c1 + c2 + c3 == 0) break;
+    // ---- stage the tables of the listed atoms ----
+    for (int t = threadIdx.x; t < kChunk * 3 * W; t += blockDim.x) {
+      const int r = t / (3 * W), e = t - r * 3 * W;
+      const int seg = r / kTake;
+      const int n = seg == 0 ? c0 : (seg == 1 ? c1 : (seg == 2 ? c2 : c3));
+      if ((r - seg * kTake) < n) {
         const int d = e / W, j = e - d * W;
         const double v = tab[(size_t)sSrc[r] * 3 * W + e];
         if (d == 0)
@@ -240,24 +265,69 @@ __global__ void __launch_bounds__(256, 2)
         else
           sTz[r * kZTab + kZPad + j] = v;
       }
-      __syncthreads();
-      // ---- accumulate ----
-      for (int r = 0; r < nRel; ++r) {
-        const int ix = (gx - sX0[r]) & mx, iy = (gy - sY0[r]) & my;
-        const bool in = ix < W && iy < W;
-        if (__any_sync(0xffffffffu, in)) {
-          const double a = in ? sTx[r * W + ix] * sTy[r * W + iy] : 0.0;
-          const double *tz = sTz + r * kZTab + sZo[r];
+    }
+    __syncthreads();
+    // ---- accumulate: lanes 0-15 test segment 2h, lanes 16-31 segment 2h+1 against the patch ----
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int seg = 2 * h + (lane >> 4);
+      const int n = seg == 0 ? c0 : (seg == 1 ? c1 : (seg == 2 ? c2 : c3));
+      const int slot = seg * kTake + (lane & 15);
+      bool hit = false;
+      if ((lane & 15) < n) {
+        const int ox = ((px0 - sX0[slot] + 7) & mx) - 7;  // patch is 8 wide: [-7, n-8]
+        const int oy = ((py0 - sY0[slot] + 7) & my) - 7;
+        hit = ox < W && oy < W;
+      }
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1u;
+        const int r = (2 * h + (b >> 4)) * kTake + (b & 15);
+        const int ix = (gx - sX0[r]) & mx;
+        const int y0 = sY0[r];
+        const int iyA = (gyA - y0) & my, iyB = (gyB - y0) & my;
+        const double tx = ix < W ? sTx[r * W + ix] : 0.0;
+        const double a0 = iyA < W ? tx * sTy[r * W + iyA] : 0.0;
+        const double a1 = iyB < W ? tx * sTy[r * W + iyB] : 0.0;
+        const int zo = sZo[r];
+        const double *tz = sTz + r * kZTab + zo;
+        if (zo & 1) {
+          const double t0 = tz[0];
+          acc0[0] = fma(a0, t0, acc0[0]);
+          acc1[0] = fma(a1, t0, acc1[0]);
 #pragma unroll
-          for (int j = 0; j < kBrick; ++j) acc[j] = fma(a, tz[j], acc[j]);
+          for (int j = 1; j < kBrick - 1; j += 2) {
+            const double2 t = *reinterpret_cast<const double2 *>(tz + j);
+            acc0[j] = fma(a0, t.x, acc0[j]);
+            acc1[j] = fma(a1, t.x, acc1[j]);
+            acc0[j + 1] = fma(a0, t.y, acc0[j + 1]);
+            acc1[j + 1] = fma(a1, t.y, acc1[j + 1]);
+          }
+          const double tl = tz[kBrick - 1];
+          acc0[kBrick - 1] = fma(a0, tl, acc0[kBrick - 1]);
+          acc1[kBrick - 1] = fma(a1, tl, acc1[kBrick - 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kBrick; j += 2) {
+            const double2 t = *reinterpret_cast<const double2 *>(tz + j);
+            acc0[j] = fma(a0, t.x, acc0[j]);
+            acc1[j] = fma(a1, t.x, acc1[j]);
+            acc0[j + 1] = fma(a0, t.y, acc0[j + 1]);
+            acc1[j + 1] = fma(a1, t.y, acc1[j + 1]);
+          }
         }
       }
     }
+    __syncthreads();  // lists and tables are rewritten by the next round
   }
-  double *out = grid + ((size_t)gx * g.n[1] + gy) * g.n[2] + bz0;
+  double *outA = grid + ((size_t)gx * g.n[1] + gyA) * g.n[2] + bz0;
+  double *outB = grid + ((size_t)gx * g.n[1] + gyB) * g.n[2] + bz0;
 #pragma unroll
-  for (int j = 0; j < kBrick; j += 2)
-    *reinterpret_cast<double2 *>(out + j) = make_double2(acc[j], acc[j + 1]);
+  for (int j = 0; j < kBrick; j += 2) {
+    *reinterpret_cast<double2 *>(outA + j) = make_double2(acc0[j], acc0[j + 1]);
+    *reinterpret_cast<double2 *>(outB + j) = make_double2(acc1[j], acc1[j + 1]);
+  }
 }
 
 // ---- FFT passes ---------------------------------------------------------------------
@@ -525,10 +595,11 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Interpolation with the analytic window derivative: F = -q grad phi.  One warp per atom
-// (bin-sorted order, so neighbouring warps read neighbouring grid regions): lane (ix
-// half, iy) walks W/2 x-columns... each lane owns (ix, iy) pairs strided by 32 and runs
-// the z stencil; fixed-order shuffle reduction.
+// Interpolation with the analytic window gradient: F = -q grad phi.  One warp per atom in
+// bin-sorted order (neighbouring warps read neighbouring grid regions: L1 / L2 hits).  A
+// half-warp reads one (x, y) column of the stencil as 16 consecutive z values (coalesced);
+// lane = (half h, z index jz) keeps its z weights in registers and accumulates, per x
+// plane, P = sum_y psi_y v and Q = sum_y psi'_y v; fixed-order shuffle reduction.
 template <int W>
 __global__ void __launch_bounds__(256)
     k_nufft_interp_force(GridGeom g, int nAtoms, const int4 *__restrict__ start,
@@ -549,22 +620,36 @@ __global__ void __launch_bounds__(256)
   const double *tx = sT[warp], *ty = tx + W, *tz = ty + W;
   const double *dx = tz + W, *dy = dx + W, *dz = dy + W;
   const int mx = g.n[0] - 1, my = g.n[1] - 1, mz = g.n[2] - 1;
-  double ax = 0.0, ay = 0.0, az = 0.0;
-  for (int c = lane; c < W * W; c += 32) {
-    const int ix = c / W, iy = c - ix * W;
-    const int gxp = (st.x + ix) & mx, gyp = (st.y + iy) & my;
-    const double *col = grid + ((size_t)gxp * g.n[1] + gyp) * g.n[2];
-    double s0 = 0.0, s1 = 0.0;
+  const int jz = lane & 15, h = lane >> 4;
+  const bool zin = jz < W;
+  const double tzl = zin ? tz[jz] : 0.0, dzl = zin ? dz[jz] : 0.0;
+  double ty8[W / 2], dy8[W / 2];
+  int yoff[W / 2];
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-      const double v = col[(st.z + j) & mz];
-      s0 = fma(tz[j], v, s0);
-      s1 = fma(dz[j], v, s1);
-    }
-    ax = fma(dx[ix] * ty[iy], s0, ax);
-    ay = fma(tx[ix] * dy[iy], s0, ay);
-    az = fma(tx[ix] * ty[iy], s1, az);
+  for (int k = 0; k < W / 2; ++k) {
+    ty8[k] = ty[2 * k + h];
+    dy8[k] = dy[2 * k + h];
+    yoff[k] = ((st.y + 2 * k + h) & my) * g.n[2] + ((st.z + jz) & mz);
   }
+  double A = 0.0, B = 0.0, C = 0.0;
+#pragma unroll 2
+  for (int ix = 0; ix < W; ++ix) {
+    const double *plane = grid + (size_t)((st.x + ix) & mx) * g.n[1] * g.n[2];
+    double v[W / 2];
+#pragma unroll
+    for (int k = 0; k < W / 2; ++k) v[k] = zin ? plane[yoff[k]] : 0.0;
+    double P = 0.0, Q = 0.0;
+#pragma unroll
+    for (int k = 0; k < W / 2; ++k) {
+      P = fma(ty8[k], v[k], P);
+      Q = fma(dy8[k], v[k], Q);
+    }
+    const double txv = tx[ix];
+    A = fma(dx[ix], P, A);
+    B = fma(txv, Q, B);
+    C = fma(txv, P, C);
+  }
+  double ax = tzl * A, ay = tzl * B, az = dzl * C;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ax += __shfl_xor_sync(0xffffffffu, ax, o);
@@ -572,8 +657,7 @@ __global__ void __launch_bounds__(256)
     az += __shfl_xor_sync(0xffffffffu, az, o);
   }
   if (lane == 0) {
-    // dtab holds d psi / d t with t in grid units and q folded into the x tables:
-    // F = -q grad phi, d/dx = (n / L) d/dt
+    // the x tables carry q; d psi / dt is per grid unit: F = -q grad phi, d/dx = (n / L) d/dt
     const int a = atomIndex[st.w];
     fx[a] += -ax * (double)g.n[0] * g.invL[0];
     fy[a] += -ay * (double)g.n[1] * g.invL[1];
@@ -827,17 +911,17 @@ int nufft_type1(Nufft *nf, cudaStream_t st, const NufftGrid &g, const double L[3
   nf->binnedW = g.w;
   // spread
   {
-    const size_t smem = sizeof(double) * ((size_t)kSlice * (2 * g.w + kZTab)) + sizeof(int) * 4 * kSlice;
+    const size_t smem = sizeof(double) * ((size_t)kChunk * (2 * g.w + kZTab)) + sizeof(int) * 4 * kChunk;
     const int nBricks = gg.nb[0] * gg.nb[1] * gg.nb[2];
     if (g.w == 12) {
       if ((rc = set_smem(nf, k_nufft_spread<12>, smem))) return rc;
-      k_nufft_spread<12><<<nBricks, 256, smem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
+      k_nufft_spread<12><<<nBricks, 128, smem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
     } else if (g.w == 14) {
       if ((rc = set_smem(nf, k_nufft_spread<14>, smem))) return rc;
-      k_nufft_spread<14><<<nBricks, 256, smem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
+      k_nufft_spread<14><<<nBricks, 128, smem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
     } else {
       if ((rc = set_smem(nf, k_nufft_spread<16>, smem))) return rc;
-      k_nufft_spread<16><<<nBricks, 256, smem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
+      k_nufft_spread<16><<<nBricks, 128, smem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
     }
   }
   // pruned FFT: z, y, x
