@@ -40,8 +40,6 @@ namespace {
 
 constexpr int kBrick = 16;     // bin edge in grid points (>= w/2 + 1)
 constexpr int kMaxW = 16;
-constexpr int kZPad = kBrick - 1;            // zero padding either side of the z table
-constexpr int kZTab = kMaxW + 2 * kZPad + 2; // 48 entries
 
 template <typename T>
 struct Buf {
@@ -147,31 +145,54 @@ __global__ void k_nufft_tables(GridGeom g, int nAtoms, double beta,
 }
 
 // ---- spread (gather) ----------------------------------------------------------------
-// One CTA (4 warps) = one 16 x 16 x 16 brick of the fine grid; warp w owns the 8 x 8 patch
-// of (x, y) columns (w & 1, w >> 1), each lane two columns (y and y + 4) with their 16 z
-// values in registers (32 accumulators).  The atoms of the 27 neighbouring bins are the
-// candidates; warp w scans the bins w, w+4, ... in order and contributes up to kTake atoms
-// whose stencil reaches the brick to each round (its own list segment: no CTA-wide
-// compaction, and the order -- segment 0, 1, 2, 3, each in scan order -- is fixed, so the
-// floating-point sums are reproducible).  Per round: stage the window tables of the listed
-// atoms in shared memory, then every warp adds the atoms that reach its patch:
-// a0/a1 = Tx[ix] * Ty[iy] once, then 32 DFMA against 8 LDS.128 of the zero-padded z table.
-constexpr int kTake = 16;               // atoms per warp per round
-constexpr int kChunk = 4 * kTake;       // table slots per round
+// One CTA (8 warps) = one 16 x 16 x 16 brick of the fine grid; warp w owns the 8 x 4 patch
+// of (x, y) columns (w & 1, w >> 1) with all 16 z values: 512 grid points per warp, held as
+// the accumulators of 4 x 2 FP64 tensor-core tiles (mma.sync.m8n8k4.f64, SASS DMMA).
+// The atoms of the 27 neighbouring bins are the candidates; warp w scans the bins w, w+8,
+// ... in order and contributes up to kTake atoms whose stencil reaches the brick to each
+// chunk (its own list segment: no CTA-wide compaction, and the order -- segment 0..7, each
+// in scan order -- is fixed, so the floating-point sums are reproducible).  The window
+// tables of a chunk are staged in shared memory RESOLVED TO THE BRICK: row (slot, axis)
+// holds the window value at each of the brick's 16 points of that axis (zero outside the
+// stencil).  Each warp lists the atoms that reach its patch (lane-parallel test, ballot)
+// and takes them four at a time: with A[x][k] = BX_k[x] * BY_k[y_t] and B[k][z] = BZ_k[z]
+//   C_t,u[x][z] += sum_{k<4} A_t[x][k] B_u[k][z]      (t = 4 y rows, u = 2 z halves)
+// i.e. 8 DMMA per 4 atoms fed by 5 shared-memory loads and 4 DMUL per lane -- the SIMT form
+// (16 DFMA against 16 broadcast z values per atom) was bound by shared-memory wavefronts.
+// Software pipeline, one barrier per round: while chunk k is accumulated, the tables of
+// chunk k+1 arrive by cp.async (double buffer) and the lists of chunk k+2 are filled
+// (triple buffer), so no global-memory latency sits between two barriers unhidden.
+constexpr int kSpreadWarps = 8;
+constexpr int kTake = 6;                        // atoms per warp per chunk
+constexpr int kChunk = kSpreadWarps * kTake;    // table slots per chunk (48)
+constexpr int kSlot = 3 * kBrick + 8;           // doubles per slot: X | Y | Z | pad; 448 B = 64 mod 128
+constexpr size_t kSpreadSmem = sizeof(double) * 2 * (kChunk + 1) * kSlot;  // +1: the all-zero slot
+
+__device__ __forceinline__ void cp_async8(double *dstShared, const double *srcGlobal) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dstShared)),
+               "l"(srcGlobal)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
 
 template <int W>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(256, 4)
     k_nufft_spread(GridGeom g, const int *__restrict__ binStart, const int4 *__restrict__ start,
                    const double *__restrict__ tab, double *__restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  double *sTz = reinterpret_cast<double *>(smemRaw);  // [kChunk][kZTab], zero padded, 16 B rows
-  double *sTx = sTz + kChunk * kZTab;                 // [kChunk][W]
-  double *sTy = sTx + kChunk * W;                     // [kChunk][W]
-  int *sX0 = reinterpret_cast<int *>(sTy + kChunk * W);
-  int *sY0 = sX0 + kChunk;
-  int *sZo = sY0 + kChunk;
-  int *sSrc = sZo + kChunk;
-  __shared__ int cnt[4];
+  double *sB = reinterpret_cast<double *>(smemRaw);  // [2][kChunk + 1][kSlot]
+  __shared__ int sX0[3][kChunk], sY0[3][kChunk], sZ0[3][kChunk], sSrc[3][kChunk];
+  __shared__ int cnt[3][kSpreadWarps];
+  __shared__ int hitList[kSpreadWarps][kChunk + 4];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned ltMask = (1u << lane) - 1u;
@@ -179,154 +200,193 @@ __global__ void __launch_bounds__(128, 4)
   const int by = (blockIdx.x / g.nb[2]) % g.nb[1];
   const int bx = blockIdx.x / (g.nb[2] * g.nb[1]);
   const int bx0 = bx * kBrick, by0 = by * kBrick, bz0 = bz * kBrick;
-  const int px0 = bx0 + 8 * (warp & 1), py0 = by0 + 8 * (warp >> 1);
-  const int gx = px0 + (lane & 7);
-  const int gyA = py0 + (lane >> 3), gyB = gyA + 4;
+  const int px = 8 * (warp & 1), py = 4 * (warp >> 1);  // patch origin inside the brick
+  const int px0 = bx0 + px, py0 = by0 + py;
   const int mx = g.n[0] - 1, my = g.n[1] - 1, mz = g.n[2] - 1;
+  const int fr = lane >> 2, fk = lane & 3;  // fragment row / column index, atom of the group
 
-  double acc0[kBrick], acc1[kBrick];
+  double acc[4][2][2];
 #pragma unroll
-  for (int j = 0; j < kBrick; ++j) acc0[j] = acc1[j] = 0.0;
-  for (int t = threadIdx.x; t < kChunk * kZTab; t += blockDim.x) sTz[t] = 0.0;
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+  // the all-zero slot of both table buffers pads the last group of four
+  if (threadIdx.x < 2 * kSlot)
+    sB[((size_t)(threadIdx.x / kSlot) * (kChunk + 1) + kChunk) * kSlot + threadIdx.x % kSlot] = 0.0;
 
-  // candidate cursor of this warp (all warp-uniform)
-  int curNbr = warp - 4, curPos = 0, curEnd = 0;
+  // Candidates = the atoms of the 27 neighbouring bins as one sequence of 32-atom batches
+  // (bin-major); warp w takes batches w, w+8, ... so that every warp contributes about the
+  // same number of atoms per chunk.
+  __shared__ int nbBeg[27], nbEnd[27], nbCum[28];
+  if (threadIdx.x < 27) {
+    const int nbr = threadIdx.x;
+    int cx = bx + nbr / 9 - 1, cy = by + (nbr / 3) % 3 - 1, cz = bz + nbr % 3 - 1;
+    cx += cx < 0 ? g.nb[0] : 0;
+    cx -= cx >= g.nb[0] ? g.nb[0] : 0;
+    cy += cy < 0 ? g.nb[1] : 0;
+    cy -= cy >= g.nb[1] ? g.nb[1] : 0;
+    cz += cz < 0 ? g.nb[2] : 0;
+    cz -= cz >= g.nb[2] ? g.nb[2] : 0;
+    const int bin = (cx * g.nb[1] + cy) * g.nb[2] + cz;
+    nbBeg[nbr] = binStart[bin];
+    nbEnd[nbr] = binStart[bin + 1];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int i = 0; i < 27; ++i) {
+      nbCum[i] = c;
+      c += (nbEnd[i] - nbBeg[i] + 31) >> 5;
+    }
+    nbCum[27] = c;
+  }
+  __syncthreads();
+  const int nBatches = nbCum[27];
+  int bid = warp, bi = 0;        // next batch of this warp, its bin (warp-uniform)
   unsigned pendMask = 0u;
   int pendBase = 0;
-  int pstX = 0, pstY = 0, pZo = 0;  // this lane's candidate of the pending batch
+  int pstX = 0, pstY = 0, pstZ = 0;  // this lane's candidate of the pending batch
+  // the following batch, already requested from global memory (consumed one round later)
+  int4 nxt = make_int4(0, 0, 0, 0);
+  int nxtBase = -1, nxtValid = 0;
+  auto prefetch = [&]() {
+    nxtBase = -1;
+    if (bid < nBatches) {
+      while (bid >= nbCum[bi + 1]) ++bi;
+      nxtBase = nbBeg[bi] + 32 * (bid - nbCum[bi]);
+      nxtValid = nxtBase + lane < nbEnd[bi];
+      if (nxtValid) nxt = start[nxtBase + lane];
+      bid += kSpreadWarps;
+    }
+  };
+  prefetch();
 
-  for (;;) {
-    // ---- fill: up to kTake relevant atoms of this warp's bins ----
+  // up to kTake relevant atoms of this warp's batches into list buffer lb
+  auto fill = [&](int lb) {
     int nw = 0;
     while (nw < kTake) {
       if (pendMask == 0u) {
-        while (curPos >= curEnd && curNbr + 4 < 27) {
-          curNbr += 4;
-          int cx = bx + curNbr / 9 - 1, cy = by + (curNbr / 3) % 3 - 1, cz = bz + curNbr % 3 - 1;
-          cx += cx < 0 ? g.nb[0] : 0;
-          cx -= cx >= g.nb[0] ? g.nb[0] : 0;
-          cy += cy < 0 ? g.nb[1] : 0;
-          cy -= cy >= g.nb[1] ? g.nb[1] : 0;
-          cz += cz < 0 ? g.nb[2] : 0;
-          cz -= cz >= g.nb[2] ? g.nb[2] : 0;
-          const int bin = (cx * g.nb[1] + cy) * g.nb[2] + cz;
-          curPos = binStart[bin];
-          curEnd = binStart[bin + 1];
-        }
-        if (curPos >= curEnd) break;  // exhausted
-        const int s = curPos + lane;
+        if (nxtBase < 0) break;  // exhausted
         bool rel = false;
-        if (s < curEnd) {
-          const int4 st = start[s];
+        if (nxtValid) {
           // offset of the brick's first point inside the stencil, unwrapped to
-          // [-(kBrick-1), n-kBrick]: brick point j has stencil index o + j, so the stencil
+          // [-(kBrick-1), n-kBrick]: brick point p has stencil index o + p, so the stencil
           // reaches the brick iff o < W (n >= 64 > W + kBrick keeps this unambiguous)
-          const int ox = ((bx0 - st.x + (kBrick - 1)) & mx) - (kBrick - 1);
-          const int oy = ((by0 - st.y + (kBrick - 1)) & my) - (kBrick - 1);
-          const int oz = ((bz0 - st.z + (kBrick - 1)) & mz) - (kBrick - 1);
+          const int ox = ((bx0 - nxt.x + (kBrick - 1)) & mx) - (kBrick - 1);
+          const int oy = ((by0 - nxt.y + (kBrick - 1)) & my) - (kBrick - 1);
+          const int oz = ((bz0 - nxt.z + (kBrick - 1)) & mz) - (kBrick - 1);
           rel = ox < W && oy < W && oz < W;
-          pstX = st.x;
-          pstY = st.y;
-          pZo = oz + kZPad;  // index of the brick's first z point in the padded table
+          pstX = nxt.x;
+          pstY = nxt.y;
+          pstZ = nxt.z;
         }
         pendMask = __ballot_sync(0xffffffffu, rel);
-        pendBase = curPos;
-        curPos += 32;
+        pendBase = nxtBase;
+        prefetch();
         if (pendMask == 0u) continue;
       }
       const int take = min(__popc(pendMask), kTake - nw);
       const int myRank = __popc(pendMask & ltMask);
       if (((pendMask >> lane) & 1u) && myRank < take) {
         const int pos = warp * kTake + nw + myRank;
-        sX0[pos] = pstX;
-        sY0[pos] = pstY;
-        sZo[pos] = pZo;
-        sSrc[pos] = pendBase + lane;
+        sX0[lb][pos] = pstX;
+        sY0[lb][pos] = pstY;
+        sZ0[lb][pos] = pstZ;
+        sSrc[lb][pos] = pendBase + lane;
       }
       for (int t = 0; t < take; ++t) pendMask &= pendMask - 1u;  // drop the taken bits
       nw += take;
     }
-    if (lane == 0) cnt[warp] = nw;
-    __syncthreads();
-    const int c0 = cnt[0], c1 = cnt[1], c2 = cnt[2], c3 = cnt[3];
-    if (c0 + c1 + c2 + c3 == 0) break;
-    // ---- stage the tables of the listed atoms ----
-    for (int t = threadIdx.x; t < kChunk * 3 * W; t += blockDim.x) {
-      const int r = t / (3 * W), e = t - r * 3 * W;
-      const int seg = r / kTake;
-      const int n = seg == 0 ? c0 : (seg == 1 ? c1 : (seg == 2 ? c2 : c3));
-      if ((r - seg * kTake) < n) {
-        const int d = e / W, j = e - d * W;
-        const double v = tab[(size_t)sSrc[r] * 3 * W + e];
-        if (d == 0)
-          sTx[r * W + j] = v;
-        else if (d == 1)
-          sTy[r * W + j] = v;
-        else
-          sTz[r * kZTab + kZPad + j] = v;
-      }
-    }
-    __syncthreads();
-    // ---- accumulate: lanes 0-15 test segment 2h, lanes 16-31 segment 2h+1 against the patch ----
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      const int seg = 2 * h + (lane >> 4);
-      const int n = seg == 0 ? c0 : (seg == 1 ? c1 : (seg == 2 ? c2 : c3));
-      const int slot = seg * kTake + (lane & 15);
-      bool hit = false;
-      if ((lane & 15) < n) {
-        const int ox = ((px0 - sX0[slot] + 7) & mx) - 7;  // patch is 8 wide: [-7, n-8]
-        const int oy = ((py0 - sY0[slot] + 7) & my) - 7;
-        hit = ox < W && oy < W;
-      }
-      unsigned m = __ballot_sync(0xffffffffu, hit);
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1u;
-        const int r = (2 * h + (b >> 4)) * kTake + (b & 15);
-        const int ix = (gx - sX0[r]) & mx;
-        const int y0 = sY0[r];
-        const int iyA = (gyA - y0) & my, iyB = (gyB - y0) & my;
-        const double tx = ix < W ? sTx[r * W + ix] : 0.0;
-        const double a0 = iyA < W ? tx * sTy[r * W + iyA] : 0.0;
-        const double a1 = iyB < W ? tx * sTy[r * W + iyB] : 0.0;
-        const int zo = sZo[r];
-        const double *tz = sTz + r * kZTab + zo;
-        if (zo & 1) {
-          const double t0 = tz[0];
-          acc0[0] = fma(a0, t0, acc0[0]);
-          acc1[0] = fma(a1, t0, acc1[0]);
+    if (lane == 0) cnt[lb][warp] = nw;
+  };
+
+  // thread = one (slot, axis) row: the 16 brick-resolved window values, by cp.async
+  auto stage = [&](int lb, int tb) {
+    if (threadIdx.x < kChunk * 3) {
+      const int r = threadIdx.x / 3, d = threadIdx.x - 3 * r;
+      if ((r % kTake) < cnt[lb][r / kTake]) {
+        const int x0 = d == 0 ? sX0[lb][r] : (d == 1 ? sY0[lb][r] : sZ0[lb][r]);
+        const int b0 = d == 0 ? bx0 : (d == 1 ? by0 : bz0);
+        const int m = d == 0 ? mx : (d == 1 ? my : mz);
+        const int o = ((b0 - x0 + (kBrick - 1)) & m) - (kBrick - 1);  // stencil index of point 0
+        double *dst = sB + ((size_t)tb * (kChunk + 1) + r) * kSlot + d * kBrick;
+        const double *src = tab + ((size_t)sSrc[lb][r] * 3 + d) * W;
 #pragma unroll
-          for (int j = 1; j < kBrick - 1; j += 2) {
-            const double2 t = *reinterpret_cast<const double2 *>(tz + j);
-            acc0[j] = fma(a0, t.x, acc0[j]);
-            acc1[j] = fma(a1, t.x, acc1[j]);
-            acc0[j + 1] = fma(a0, t.y, acc0[j + 1]);
-            acc1[j + 1] = fma(a1, t.y, acc1[j + 1]);
-          }
-          const double tl = tz[kBrick - 1];
-          acc0[kBrick - 1] = fma(a0, tl, acc0[kBrick - 1]);
-          acc1[kBrick - 1] = fma(a1, tl, acc1[kBrick - 1]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < kBrick; j += 2) {
-            const double2 t = *reinterpret_cast<const double2 *>(tz + j);
-            acc0[j] = fma(a0, t.x, acc0[j]);
-            acc1[j] = fma(a1, t.x, acc1[j]);
-            acc0[j + 1] = fma(a0, t.y, acc0[j + 1]);
-            acc1[j + 1] = fma(a1, t.y, acc1[j + 1]);
-          }
+        for (int pp = 0; pp < kBrick; ++pp) {
+          const int p = (pp + lane) & (kBrick - 1);  // rotated per lane: rows sit 128 B apart
+          const int j = p + o;
+          if ((unsigned)j < (unsigned)W)
+            cp_async8(dst + p, src + j);
+          else
+            dst[p] = 0.0;
         }
       }
     }
-    __syncthreads();  // lists and tables are rewritten by the next round
-  }
-  double *outA = grid + ((size_t)gx * g.n[1] + gyA) * g.n[2] + bz0;
-  double *outB = grid + ((size_t)gx * g.n[1] + gyB) * g.n[2] + bz0;
+  };
+
+  // this warp's hits of the chunk, four at a time through the FP64 tensor cores
+  auto accumulate = [&](int lb, int tb) {
+    const double *tbl = sB + (size_t)tb * (kChunk + 1) * kSlot;
+    int nHit = 0;
 #pragma unroll
-  for (int j = 0; j < kBrick; j += 2) {
-    *reinterpret_cast<double2 *>(outA + j) = make_double2(acc0[j], acc0[j + 1]);
-    *reinterpret_cast<double2 *>(outB + j) = make_double2(acc1[j], acc1[j + 1]);
+    for (int h = 0; h < (kChunk + 31) / 32; ++h) {
+      const int slot = 32 * h + lane;
+      bool hit = false;
+      if (slot < kChunk && (slot % kTake) < cnt[lb][slot / kTake]) {
+        const int ox = ((px0 - sX0[lb][slot] + 7) & mx) - 7;  // patch: 8 wide, 4 high
+        const int oy = ((py0 - sY0[lb][slot] + 3) & my) - 3;
+        hit = ox < W && oy < W;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) hitList[warp][nHit + __popc(m & ltMask)] = slot;
+      nHit += __popc(m);
+    }
+    if (lane < 4) hitList[warp][nHit + lane] = kChunk;  // pad with the all-zero slot
+    __syncwarp();
+    for (int g4 = 0; g4 < nHit; g4 += 4) {
+      const double *row = tbl + hitList[warp][g4 + fk] * kSlot;
+      const double ax = row[px + fr];
+      const double2 y01 = *reinterpret_cast<const double2 *>(row + kBrick + py);
+      const double2 y23 = *reinterpret_cast<const double2 *>(row + kBrick + py + 2);
+      const double b0 = row[2 * kBrick + fr], b1 = row[2 * kBrick + 8 + fr];
+      const double a0 = ax * y01.x, a1 = ax * y01.y, a2 = ax * y23.x, a3 = ax * y23.y;
+      dmma_m8n8k4(acc[0][0][0], acc[0][0][1], a0, b0);
+      dmma_m8n8k4(acc[0][1][0], acc[0][1][1], a0, b1);
+      dmma_m8n8k4(acc[1][0][0], acc[1][0][1], a1, b0);
+      dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1, b1);
+      dmma_m8n8k4(acc[2][0][0], acc[2][0][1], a2, b0);
+      dmma_m8n8k4(acc[2][1][0], acc[2][1][1], a2, b1);
+      dmma_m8n8k4(acc[3][0][0], acc[3][0][1], a3, b0);
+      dmma_m8n8k4(acc[3][1][0], acc[3][1][1], a3, b1);
+    }
+    __syncwarp();
+  };
+
+  fill(0);
+  __syncthreads();
+  stage(0, 0);
+  fill(1);
+  cp_async_wait_all();
+  __syncthreads();
+  for (int k = 0;; ++k) {
+    const int lb = k % 3;
+    int total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kSpreadWarps; ++w2) total += cnt[lb][w2];
+    if (total == 0) break;
+    stage((k + 1) % 3, (k + 1) & 1);
+    accumulate(lb, k & 1);
+    fill((k + 2) % 3);
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  // C fragment: row = x = lane >> 2, columns z = 8u + 2 (lane & 3) + {0, 1}; tile t = y row
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    double *out = grid + ((size_t)(px0 + fr) * g.n[1] + (py0 + t)) * g.n[2] + bz0 + 2 * fk;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      *reinterpret_cast<double2 *>(out + 8 * u) = make_double2(acc[t][u][0], acc[t][u][1]);
   }
 }
 
@@ -875,7 +935,7 @@ int pick_cb(int n, int C) {
 
 template <typename K>
 int set_smem(Nufft *nf, K kernel, size_t bytes) {
-  if (bytes > 48 * 1024)
+  if (bytes > 32 * 1024)  // static + dynamic above 48 KB needs the opt-in
     NCK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }
@@ -911,17 +971,16 @@ int nufft_type1(Nufft *nf, cudaStream_t st, const NufftGrid &g, const double L[3
   nf->binnedW = g.w;
   // spread
   {
-    const size_t smem = sizeof(double) * ((size_t)kChunk * (2 * g.w + kZTab)) + sizeof(int) * 4 * kChunk;
     const int nBricks = gg.nb[0] * gg.nb[1] * gg.nb[2];
     if (g.w == 12) {
-      if ((rc = set_smem(nf, k_nufft_spread<12>, smem))) return rc;
-      k_nufft_spread<12><<<nBricks, 128, smem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
+      if ((rc = set_smem(nf, k_nufft_spread<12>, kSpreadSmem))) return rc;
+      k_nufft_spread<12><<<nBricks, 256, kSpreadSmem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
     } else if (g.w == 14) {
-      if ((rc = set_smem(nf, k_nufft_spread<14>, smem))) return rc;
-      k_nufft_spread<14><<<nBricks, 128, smem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
+      if ((rc = set_smem(nf, k_nufft_spread<14>, kSpreadSmem))) return rc;
+      k_nufft_spread<14><<<nBricks, 256, kSpreadSmem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
     } else {
-      if ((rc = set_smem(nf, k_nufft_spread<16>, smem))) return rc;
-      k_nufft_spread<16><<<nBricks, 128, smem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
+      if ((rc = set_smem(nf, k_nufft_spread<16>, kSpreadSmem))) return rc;
+      k_nufft_spread<16><<<nBricks, 256, kSpreadSmem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
     }
   }
   // pruned FFT: z, y, x
