@@ -9,6 +9,9 @@
  *
  *   gomc_probe_<ENS> golden <in.conf> <out.bin> [nMoves] [seed]
  *       full Simulation construction; every function of the hot path.
+ *   gomc_probe_<ENS> slab <in.conf> <out.bin> <nSel> <seed> [coords]
+ *       light initialisation; BoxInter over the full box and BoxReciprocalSums on nSel
+ *       k-vectors spread over the whole list (full-size parity pins, tests/golden/full_*).
  *   gomc_probe_<ENS> time <in.conf> <out.bin> <kFraction> <reps> [force]
  *       light initialisation (no full structure-factor build, no virial) and
  *       wall-clock timing of BoxInter + BoxReciprocalSums(k-slab) +
@@ -644,12 +647,13 @@ int run_golden(int argc, char **argv) {
 // (src/Simulation.cpp:19-40) and System::Init (src/System.cpp:106-160) except
 // the two O(N*nk) start-up sweeps (BoxReciprocalSetup inside Ewald::Init and
 // SystemTotal's virial), which a bounded timing run cannot afford.
-int run_time(int argc, char **argv) {
-  const char *conf = argv[2];
-  const char *outPath = argv[3];
-  int kFrac = argc > 4 ? atoi(argv[4]) : 1;
-  int reps = argc > 5 ? atoi(argv[5]) : 3;
-  bool doForce = argc > 6 && std::string(argv[6]) == "force";
+struct LightSim {
+  StaticVals *sv;
+  System *sys;
+  bool ewaldOn;
+};
+
+LightSim light_init(const char *conf) {
   static Setup set;
   set.Init(conf, NULL);
   ulong startStep = 0;
@@ -718,6 +722,21 @@ int run_time(int argc, char **argv) {
       ew.SetRecipRef(b);
     }
   }
+  LightSim ls = {sv, sysp, ewaldOn};
+  return ls;
+}
+
+int run_time(int argc, char **argv) {
+  const char *conf = argv[2];
+  const char *outPath = argv[3];
+  int kFrac = argc > 4 ? atoi(argv[4]) : 1;
+  int reps = argc > 5 ? atoi(argv[5]) : 3;
+  bool doForce = argc > 6 && std::string(argv[6]) == "force";
+  LightSim ls = light_init(conf);
+  StaticVals *sv = ls.sv;
+  System &sys = *ls.sys;
+  const bool ewaldOn = ls.ewaldOn;
+  Ewald &ew = *sys.calcEwald;
   Dump out(outPath);
   out.i32("threads", omp_get_max_threads());
   dump_static(out, *sv, sys);
@@ -788,6 +807,87 @@ int run_time(int argc, char **argv) {
   return 0;
 }
 
+
+// Full-size parity pin: BoxInter over the whole box and the structure factor on a chosen
+// subset of the k list (the selected k-vectors are moved to the front of the Ref arrays and
+// imageSizeRef shortened, so Ewald::BoxReciprocalSums itself produces the values).
+//   gomc_probe_<ENS> slab <in.conf> <out.bin> <nSel> <seed>
+int run_slab(int argc, char **argv) {
+  const char *conf = argv[2];
+  const char *outPath = argv[3];
+  int nSel = argc > 4 ? atoi(argv[4]) : 256;
+  unsigned seed = argc > 5 ? (unsigned)atoi(argv[5]) : 7u;
+  LightSim ls = light_init(conf);
+  StaticVals *sv = ls.sv;
+  System &sys = *ls.sys;
+  const bool ewaldOn = ls.ewaldOn;
+  Ewald &ew = *sys.calcEwald;
+  Dump out(outPath);
+  out.i32("threads", omp_get_max_threads());
+  const uint b = 0;
+  const uint nAtoms = sys.coordinates.Count();
+  out.i32("nAtoms", (int)nAtoms);
+  XYZ ax = sys.boxDimRef.axis.Get(b);
+  double a3[3] = {ax.x, ax.y, ax.z};
+  out.f64("box0.axis", a3, 3);
+  // inputs as parsed: checksums (and the coordinates themselves for small boxes)
+  double cs[6] = {0, 0, 0, 0, 0, 0};
+  for (uint i = 0; i < nAtoms; ++i) {
+    cs[0] += sys.coordinates.x[i];
+    cs[1] += sys.coordinates.y[i];
+    cs[2] += sys.coordinates.z[i];
+    cs[3] += sys.coordinates.x[i] * (double)(i % 97 + 1);
+    cs[4] += sys.coordinates.y[i] * (double)(i % 89 + 1);
+    cs[5] += sys.coordinates.z[i] * (double)(i % 83 + 1);
+  }
+  out.f64("coords.checksum", cs, 6);
+  if (argc > 6 && std::string(argv[6]) == "coords") out.xyz("coords", sys.coordinates);
+  SystemPotential pot =
+      sys.calcEnergy.BoxInter(SystemPotential(), sys.coordinates, sys.boxDimRef, b);
+  out.f64("BoxInter.inter", pot.boxEnergy[b].inter);
+  out.f64("BoxInter.real", pot.boxEnergy[b].real);
+  if (ewaldOn) {
+    const uint nk = ew.imageSizeRef[b];
+    out.i32("box0.nk", (int)nk);
+    out.i32("box0.kmax", (int)ew.kmax[b]);
+    // selection: evenly spaced through the list (every x slab, every column range) plus
+    // random picks and both ends
+    std::vector<int> sel;
+    std::mt19937_64 rng(seed);
+    nSel = std::min<int>(nSel, (int)nk);
+    for (int i = 0; i < nSel / 2; ++i) sel.push_back((int)((uint64_t)i * nk / (nSel / 2)));
+    sel.push_back((int)nk - 1);
+    while ((int)sel.size() < nSel) sel.push_back((int)(rng() % nk));
+    std::sort(sel.begin(), sel.end());
+    sel.erase(std::unique(sel.begin(), sel.end()), sel.end());
+    nSel = (int)sel.size();
+    std::vector<double> kx(nSel), ky(nSel), kz(nSel), pf(nSel);
+    for (int i = 0; i < nSel; ++i) {
+      kx[i] = ew.kxRef[b][sel[i]];
+      ky[i] = ew.kyRef[b][sel[i]];
+      kz[i] = ew.kzRef[b][sel[i]];
+      pf[i] = ew.prefactRef[b][sel[i]];
+    }
+    for (int i = 0; i < nSel; ++i) {
+      ew.kxRef[b][i] = kx[i];
+      ew.kyRef[b][i] = ky[i];
+      ew.kzRef[b][i] = kz[i];
+      ew.prefactRef[b][i] = pf[i];
+    }
+    ew.imageSizeRef[b] = nSel;
+    ew.BoxReciprocalSums(b, sys.coordinates);
+    out.i32("slab.index", sel);
+    out.f64("slab.kx", kx);
+    out.f64("slab.ky", ky);
+    out.f64("slab.kz", kz);
+    out.f64("slab.prefact", pf);
+    out.f64("slab.sumRnew", ew.sumRnew[b], nSel);
+    out.f64("slab.sumInew", ew.sumInew[b], nSel);
+  }
+  (void)sv;
+  return 0;
+}
+
 } // namespace
 
 int main(int argc, char **argv) {
@@ -801,6 +901,7 @@ int main(int argc, char **argv) {
   std::string mode = argv[1];
   if (mode == "golden") return run_golden(argc, argv);
   if (mode == "time") return run_time(argc, argv);
+  if (mode == "slab") return run_slab(argc, argv);
   fprintf(stderr, "unknown mode %s\n", argv[1]);
   return 1;
 }
