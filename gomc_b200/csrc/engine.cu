@@ -572,7 +572,7 @@ int recip_enumerate_nonorth(const gomcb200_engine *e, int b, const double ax[3],
 }
 
 int recip_enumerate(const gomcb200_engine *e, int b, const double ax[3], KSet *ks,
-                    std::vector<RowRec> *rowsOut) {
+                    std::vector<RowRec> *rowsOut, double volume = 0.0) {
   if (e->box[b].nonOrth) {
     if (rowsOut) rowsOut->clear();
     return recip_enumerate_nonorth(e, b, ax, ks);
@@ -583,7 +583,9 @@ int recip_enumerate(const gomcb200_engine *e, int b, const double ax[3], KSet *k
   const double alpsqr4 = 1.0 / (4.0 * (alpha * alpha));
   double cv[3];
   for (int d = 0; d < 3; ++d) cv[d] = (1.0 / ax[d]) * (2.0 * M_PI);
-  const double vol = (ax[0] * ax[1] * ax[2]) / (4.0 * M_PI);
+  // boxAxes.volume[box]: the product of the axes, except after BoxDimensions::SetVolume
+  // (a volume trial), where the caller passes the stored value (src/Ewald.cpp:857)
+  const double vol = (volume > 0.0 ? volume : ax[0] * ax[1] * ax[2]) / (4.0 * M_PI);
   int nmax[3];
   for (int d = 0; d < 3; ++d) nmax[d] = int(recip_rcut * ax[d] / (2.0 * M_PI)) + 1;
   if (ks) {
@@ -2259,17 +2261,22 @@ int gomcb200_recip_count(gomcb200_engine *e, int box, const double axis[3], doub
 
 int gomcb200_recip_init(gomcb200_engine *e, int box, const double axis[3], int *imageSize,
                         int *kmax) {
-  if (!e || box < 0 || box >= e->nBoxes || !axis || !e->haveFF)
+  return gomcb200_recip_init_volume(e, box, axis, 0.0, imageSize, kmax);
+}
+
+int gomcb200_recip_init_volume(gomcb200_engine *e, int box, const double axis[3], double volume,
+                               int *imageSize, int *kmax) {
+  if (!e || box < 0 || box >= e->nBoxes || !axis || !e->haveFF || !(volume >= 0.0))
     return fail(GOMCB200_EINVAL, "bad arguments");
   CK(cudaSetDevice(e->device));
   BoxState &bx = e->box[box];
   KSet &ks = bx.kset[bx.cur];
   std::vector<RowRec> rows;
-  int n = recip_enumerate(e, box, axis, &ks, &rows);
+  int n = recip_enumerate(e, box, axis, &ks, &rows, volume);
   ks.planValid = false;
   if (n < 0) {  // cannot happen for an orthogonal box; keep the direct kernel usable
     rows.clear();
-    n = recip_enumerate(e, box, axis, &ks, nullptr);
+    n = recip_enumerate(e, box, axis, &ks, nullptr, volume);
   }
   if (e->imageTotal > 0 && n > e->imageTotal)
     return fail(GOMCB200_EKMAX,

@@ -75,6 +75,7 @@ _SIGS = {
     "gomcb200_get_forces": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int]),
     "gomcb200_init_ewald": (C.c_int, [_vp, C.c_int, _dp]),
     "gomcb200_recip_init": (C.c_int, [_vp, C.c_int, _dp, _ip, _ip]),
+    "gomcb200_recip_init_volume": (C.c_int, [_vp, C.c_int, _dp, C.c_double, _ip, _ip]),
     "gomcb200_recip_count": (C.c_int, [_vp, C.c_int, _dp, C.c_double, _ip]),
     "gomcb200_get_kvectors": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int]),
     "gomcb200_box_reciprocal_setup": (C.c_int, [_vp, C.c_int, _dp]),
@@ -382,10 +383,11 @@ class Engine:
         r, pr = _d(np.atleast_1d(recip_rcut))
         self._ck(self.L.gomcb200_init_ewald(self.h, int(image_total), pr))
 
-    def recip_init(self, box, axis):
+    def recip_init(self, box, axis, volume=0.0):
         a, pa = _d(axis)
         n, kmax = C.c_int(), C.c_int()
-        self._ck(self.L.gomcb200_recip_init(self.h, box, pa, C.byref(n), C.byref(kmax)))
+        self._ck(self.L.gomcb200_recip_init_volume(self.h, box, pa, float(volume), C.byref(n),
+                                                   C.byref(kmax)))
         return n.value, kmax.value
 
     def recip_count(self, box, axis, excess=1.0):

@@ -231,10 +231,11 @@ public:
     }
     check(gomcb200_init_ewald(eng_.get(), imageTotal, recipRcut_.data()), "InitEwaldVariablesCUDA");
   }
-  virtual void RecipInit(int box, const XYZ &axis) {  // src/Ewald.cpp:644 -> :847
+  // volume = boxAxes.volume[box] of a volume trial's newDim (0: product of the axes)
+  virtual void RecipInit(int box, const XYZ &axis, double volume = 0.0) {  // src/Ewald.cpp:644 -> :847
     double a[3] = {axis.x, axis.y, axis.z};
     int n = 0, kmax = 0;
-    check(gomcb200_recip_init(eng_.get(), box, a, &n, &kmax), "RecipInit");
+    check(gomcb200_recip_init_volume(eng_.get(), box, a, volume, &n, &kmax), "RecipInit");
   }
   virtual void BoxReciprocalSetup(int box, const XYZView &molCoords) {  // :193
     eng_.SetCoordinates(molCoords);
@@ -426,7 +427,7 @@ class NoEwald : public Ewald {
 public:
   using Ewald::Ewald;
   void AllocMem(const std::vector<XYZ> &, double) override {}
-  void RecipInit(int, const XYZ &) override {}
+  void RecipInit(int, const XYZ &, double = 0.0) override {}
   void BoxReciprocalSetup(int, const XYZView &) override {}
   void BoxReciprocalSums(int, const XYZView &) override {}
   double BoxReciprocal(int, bool) const override { return 0.0; }

@@ -348,7 +348,7 @@ def make_mixture(n_a=150, n_b=100, seed=5, L=26.0, r_cut=8.0, vdw_kind=VDW_STD,
 # GOMC input writers (consumed by oracle/_ref/gomc_probe_*)
 
 def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
-                      cached_fourier=False, run_steps=0, pressure_calc=False):
+                      cached_fourier=False, run_steps=0, pressure_calc=False, npt=False):
     os.makedirs(out_dir, exist_ok=True)
     ff = sys.ff
     # ---- parameter file (Mie / "EXOTIC" style, epsilon in K) --------------
@@ -437,7 +437,9 @@ PressureCalc {'true 1000' if pressure_calc else 'false'}
 RunSteps {max(run_steps, 10)}
 EqSteps 5
 AdjSteps 5
-DisFreq {0.40 if multiparticle else 0.60}
+{'Pressure 1.01325' if npt else ''}
+{'VolFreq 0.02' if npt else ''}
+DisFreq {(0.40 if multiparticle else 0.60) - (0.02 if npt else 0.0)}
 RotFreq {0.40 if multiparticle and any(len(k.atom_names) > 1 for k in sys.mol_kinds) else (0.40 if not multiparticle else 0.0)}
 {('MultiParticleFreq ' + ('0.20' if any(len(k.atom_names) > 1 for k in sys.mol_kinds) else '0.60')) if multiparticle else ''}
 CellBasisVector1 0 {float(CV[0][0])!r} {float(CV[0][1])!r} {float(CV[0][2])!r}

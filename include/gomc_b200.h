@@ -212,6 +212,14 @@ int gomcb200_init_ewald(gomcb200_engine *e, int imageTotal,
  * axes into the NEW k set (kx[box]...); returns imageSize[box] and kmax. */
 int gomcb200_recip_init(gomcb200_engine *e, int box, const double axis[3],
                         int *imageSize, int *kmax);
+/* The same for the dimensions of a volume trial (VolumeTransfer::CalcEn,
+ * src/moves/VolumeTransfer.h:160-189: RecipInit(box, newDim)).  volume =
+ * newDim.volume[box]: BoxDimensions::SetVolume (src/BoxDimensions.cpp:214-226) stores
+ * oldVolume + delta and cbrt-scales the axes, and RecipInitOrth's prefactor divides by
+ * that stored value (src/Ewald.cpp:857), which differs from the product of the axes in
+ * the last bit.  volume == 0: the product (gomcb200_recip_init). */
+int gomcb200_recip_init_volume(gomcb200_engine *e, int box, const double axis[3],
+                               double volume, int *imageSize, int *kmax);
 /* Ewald::RecipCountInit, src/Ewald.cpp:968-1018 (count only; excess = the
  * ensemble head-room factor 1.0 / 1.25 / 1.5). */
 int gomcb200_recip_count(gomcb200_engine *e, int box, const double axis[3],

@@ -1301,7 +1301,7 @@ int orc_recip_init_orth(const orc_params *p, double *kx, double *ky,
   cv[0] = (1.0 / p->axis[0]) * (2.0 * M_PI);
   cv[1] = (1.0 / p->axis[1]) * (2.0 * M_PI);
   cv[2] = (1.0 / p->axis[2]) * (2.0 * M_PI);
-  double volume = p->axis[0] * p->axis[1] * p->axis[2];
+  double volume = p->volume > 0.0 ? p->volume : p->axis[0] * p->axis[1] * p->axis[2];
   double vol = volume / (4.0 * M_PI);
   double rr2 = p->recip_rcut * p->recip_rcut;
   int nkx_max = (int)(p->recip_rcut * p->axis[0] / (2.0 * M_PI)) + 1;

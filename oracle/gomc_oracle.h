@@ -63,6 +63,11 @@ typedef struct {
    * axis[] then holds the cell edge lengths.  nonOrth == 0: ignored. */
   int nonOrth;
   double cellBasis[9], cellBasisInv[9];
+  /* BoxDimensions::volume[box] when it is not the product of the axes: after
+   * BoxDimensions::SetVolume (src/BoxDimensions.cpp:214-226, every volume trial) the
+   * stored volume is oldVolume + delta and the axes are cbrt-scaled, and
+   * RecipInitOrth's prefactor divides by THAT volume (src/Ewald.cpp:857).  0: product. */
+  double volume;
 } orc_params;
 
 /* ---- cell list (src/CellList.cpp:138-285, src/CellList.h:88-101) ---------- */

@@ -59,7 +59,31 @@ CASES = {
 }
 
 
+def make_npt():
+    """NPT volume trials (one accepted, one rejected) through the reference's own
+    VolumeTransfer object: tests/golden/npt_spce343.npz (probe mode `volume`)."""
+    probe = os.path.join(ROOT, "oracle", "_ref", "gomc_probe_NPT")
+    if not os.path.exists(probe):
+        subprocess.check_call(["make", "-s", "-f", "oracle/ref_build.mk", "ENS_LIST=NPT", "-j8"],
+                              cwd=ROOT)
+    s = synth.make_spce(343, r_cut=8.0, r_cut_coulomb=8.0)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_gomc_inputs(s, d, npt=True)
+        log = subprocess.run([probe, "volume", "in.conf", "dump.bin", "260.0", "-340.0"],
+                             cwd=d, env=env, capture_output=True, text=True)
+        if log.returncode != 0:
+            print(log.stdout[-3000:], log.stderr[-2000:])
+            raise SystemExit("NPT probe failed")
+        dump = po.read_dump(os.path.join(d, "dump.bin"))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "npt_spce343.npz"), **dump)
+    print(f"npt_spce343: {s.n_atoms} atoms, {len(dump)} arrays, nk {int(dump['box0.nk'][0])} -> "
+          f"{int(dump['trial0.nk'][0])} (accepted), {int(dump['trial1.nk'][0])} (rejected)")
+
+
 def main():
+    if sys.argv[1:] == ["npt"]:
+        return make_npt()
     probe = os.path.join(ROOT, "oracle", "_ref", "gomc_probe_NVT")
     if not os.path.exists(probe):
         subprocess.check_call(["make", "-s", "-f", "oracle/ref_build.mk", "ENS_LIST=NVT", "-j8"],

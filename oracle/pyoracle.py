@@ -31,7 +31,7 @@ class OrcParams(C.Structure):
                 ("rMin", _dp), ("expConst", _dp), ("rMaxSq", _dp),
                 ("isMartini", C.c_int), ("diElectric_1", C.c_double),
                 ("nonOrth", C.c_int), ("cellBasis", C.c_double * 9),
-                ("cellBasisInv", C.c_double * 9)]
+                ("cellBasisInv", C.c_double * 9), ("volume", C.c_double)]
 
 
 def build(force=False):
@@ -87,7 +87,7 @@ class Oracle:
     def __init__(self, *, vdw_kind, ewald, electrostatic, kind_count, r_cut, r_cut_low,
                  r_switch, r_cut_coulomb, alpha, recip_rcut, axis, sigma_sq, epsilon_cn, n,
                  r_min=None, exp_const=None, r_max_sq=None, is_martini=0, dielectric=1.0,
-                 cell_basis=None, cell_basis_inv=None):
+                 cell_basis=None, cell_basis_inv=None, volume=0.0):
         self.L = lib()
         self._keep = [_d(sigma_sq), _d(epsilon_cn), _d(n)]
         if r_min is not None:
@@ -103,6 +103,7 @@ class Oracle:
             p.rMin, p.expConst, p.rMaxSq = (k[1] for k in self._keep[3:6])
         p.isMartini = int(is_martini)
         p.diElectric_1 = 1.0 / float(dielectric)
+        p.volume = float(volume)   # BoxDimensions::volume after SetVolume; 0: product of the axes
         p.nonOrth = 0
         if cell_basis is not None:
             p.nonOrth = 1

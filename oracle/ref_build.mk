@@ -42,8 +42,9 @@ $(OUT)/obj_$(1)/%.o: $(REF)/%.cpp $(OUT)/include/GOMC_Config.h
 $(OUT)/obj_$(1)/ref_probe.o: oracle/ref_probe.cpp $(OUT)/include/GOMC_Config.h
 	@mkdir -p $$(dir $$@)
 	$(CXX) $(CXXFLAGS) -DENSEMBLE=$(ENSNUM_$(1)) $(INC) -c $$< -o $$@
+# (VolumeTransfer.h defines PrintAcceptKind out of line: the probe's copy is identical)
 $(OUT)/gomc_probe_$(1): $$(OBJ_$(1)) $(OUT)/obj_$(1)/ref_probe.o
-	$(CXX) $(CXXFLAGS) $$^ -o $$@
+	$(CXX) $(CXXFLAGS) -Wl,--allow-multiple-definition $$^ -o $$@
 endef
 $(foreach e,NVT GEMC GCMC NPT,$(eval $(call ENS_RULES,$(e))))
 

@@ -53,6 +53,9 @@
 #include "TrialMol.h"
 #include "MultiParticle.h"
 #include "MultiParticleBrownianMotion.h"
+#if ENSEMBLE == NPT || ENSEMBLE == GEMC
+#include "VolumeTransfer.h"
+#endif
 #undef private
 #undef protected
 
@@ -888,6 +891,120 @@ int run_slab(int argc, char **argv) {
   return 0;
 }
 
+#if ENSEMBLE == NPT
+// Volume trials of the NPT ensemble driven through the reference's own VolumeTransfer
+// object (src/moves/VolumeTransfer.h): Prep and Transform with a chosen volume change,
+// the real CalcEn (GridBox, RecipInit(newDim), BoxReciprocalSetup, BoxInter,
+// BoxReciprocal(box, true)), then the accept branch (UpdateRecip + UpdateRecipVec, :255-260)
+// for the first trial and the reject branch (:263-269) for the second.  After each, a
+// single-molecule MolReciprocal / MoleculeInter shows which state the Ewald object is in.
+//   gomc_probe_NPT volume <in.conf> <out.bin> <delta1> <delta2>
+int run_volume(int argc, char **argv) {
+  const char *conf = argv[2];
+  const char *outPath = argv[3];
+  const double deltas[2] = {argc > 4 ? atof(argv[4]) : 150.0, argc > 5 ? atof(argv[5]) : -220.0};
+  Simulation sim(conf);
+  System &sys = *sim.system;
+  StaticVals &sv = *sim.staticValues;
+  Molecules &mols = sv.mol;
+  Ewald &ew = *sys.calcEwald;
+  CalculateEnergy &ce = sys.calcEnergy;
+  VolumeTransfer *vt = static_cast<VolumeTransfer *>(sys.moves[mv::VOL_TRANSFER]);
+  Dump out(outPath);
+  out.i32("threads", omp_get_max_threads());
+  dump_static(out, sv, sys);
+  const uint b = 0;
+  dump_kvectors(out, ew, b, true);
+  out.f64("box0.sysPotRef.recip", sys.potential.boxEnergy[b].recip);
+  out.f64("box0.sysPotRef.inter", sys.potential.boxEnergy[b].inter);
+  out.f64("box0.sysPotRef.real", sys.potential.boxEnergy[b].real);
+  std::vector<uint> molsInBox;
+  for (MoleculeLookup::box_iterator it = sys.molLookupRef.BoxBegin(b);
+       it != sys.molLookupRef.BoxEnd(b); ++it)
+    molsInBox.push_back(*it);
+  // one fixed single-molecule displacement evaluated in whatever state is current
+  auto probe_move = [&](const std::string &tag, uint m) {
+    uint len = mols.GetKind(m).NumAtoms(), st = mols.MolStart(m);
+    XYZArray newPos(len);
+    XYZ ax = sys.boxDimRef.axis.Get(b);
+    for (uint a = 0; a < len; ++a) {
+      XYZ p = sys.coordinates.Get(st + a);
+      p.x += 0.37; p.y -= 0.21; p.z += 0.13;
+      newPos.Set(a, p);
+    }
+    sys.boxDimRef.WrapPBC(newPos, b);
+    out.xyz(tag + ".newPos", newPos);
+    out.i32(tag + ".mol", (int)m);
+    double recip = ew.MolReciprocal(newPos, m, b);
+    out.f64(tag + ".MolReciprocal", recip);
+    sys.cellList.RemoveMol(m, b, sys.coordinates);
+    Intermolecular iLJ, iReal;
+    bool ov = ce.MoleculeInter(iLJ, iReal, newPos, m, b);
+    sys.cellList.AddMol(m, b, sys.coordinates);
+    out.f64(tag + ".dLJ", iLJ.energy);
+    out.f64(tag + ".dReal", iReal.energy);
+    out.i32(tag + ".overlap", (int)ov);
+    out.f64(tag + ".sysPotRef.recip", sys.potential.boxEnergy[b].recip);
+  };
+  probe_move("state0", molsInBox[molsInBox.size() / 3]);
+  for (int t = 0; t < 2; ++t) {
+    const std::string tag = std::string("trial") + std::to_string(t);
+    // ---- Prep (:72-97) with box 0, Transform (:115-133) with a chosen delta ----
+    vt->box = b;
+    vt->newDim = sys.boxDimRef;
+    sys.coordinates.CopyRange(vt->newMolsPos, 0, 0, sys.coordinates.Count());
+    sys.com.CopyRange(vt->newCOMs, 0, 0, sys.com.Count());
+    XYZ scale;
+    uint state = sys.boxDimRef.ShiftVolume(vt->newDim, scale, b, deltas[t]);
+    if (state != mv::fail_state::NO_FAIL) return 3;
+    sys.coordinates.TranslateOneBox(vt->newMolsPos, vt->newCOMs, sys.com, vt->newDim, b, scale);
+    XYZ nax = vt->newDim.axis.Get(b);
+    double a3[3] = {nax.x, nax.y, nax.z};
+    out.f64(tag + ".delta", deltas[t]);
+    out.f64(tag + ".newAxis", a3, 3);
+    out.f64(tag + ".newVolume", vt->newDim.volume[b]);
+    out.xyz(tag + ".newCoords", vt->newMolsPos);
+    out.xyz(tag + ".newCOM", vt->newCOMs);
+    // ---- the reference's CalcEn (:139-198) ----
+    vt->CalcEn();
+    const Energy &en = vt->sysPotNew.boxEnergy[b];
+    out.f64(tag + ".inter", en.inter);
+    out.f64(tag + ".real", en.real);
+    out.f64(tag + ".recip", en.recip);
+    out.f64(tag + ".tailCorrection", en.tailCorrection);
+    out.f64(tag + ".total", vt->sysPotNew.Total());
+    out.f64(tag + ".coeff", vt->GetCoeff());
+    uint nkNew = ew.imageSize[b];
+    out.i32(tag + ".nk", (int)nkNew);
+    out.f64(tag + ".kx", ew.kx[b], nkNew);
+    out.f64(tag + ".ky", ew.ky[b], nkNew);
+    out.f64(tag + ".kz", ew.kz[b], nkNew);
+    out.f64(tag + ".hsqr", ew.hsqr[b], nkNew);
+    out.f64(tag + ".prefact", ew.prefact[b], nkNew);
+    out.f64(tag + ".sumRnew", ew.sumRnew[b], nkNew);
+    out.f64(tag + ".sumInew", ew.sumInew[b], nkNew);
+    if (t == 0) {
+      // ---- accept branch of VolumeTransfer::Accept (:243-260) ----
+      sys.potential = vt->sysPotNew;
+      swap(sys.coordinates, vt->newMolsPos);
+      swap(sys.com, vt->newCOMs);
+      sys.boxDimRef = vt->newDim;
+      ew.UpdateRecip(b);
+      ew.UpdateRecipVec(b);
+      out.i32(tag + ".accepted", 1);
+      out.f64(tag + ".after.BoxReciprocal", ew.BoxReciprocal(b, false));
+    } else {
+      // ---- reject branch (:263-269) ----
+      sys.cellList.GridBox(sys.boxDimRef, sys.coordinates, sys.molLookupRef, b);
+      ew.exgMolCache();
+      out.i32(tag + ".accepted", 0);
+    }
+    probe_move(tag + ".after", molsInBox[(molsInBox.size() * (t + 2)) / 5]);
+  }
+  return 0;
+}
+#endif
+
 } // namespace
 
 int main(int argc, char **argv) {
@@ -902,6 +1019,9 @@ int main(int argc, char **argv) {
   if (mode == "golden") return run_golden(argc, argv);
   if (mode == "time") return run_time(argc, argv);
   if (mode == "slab") return run_slab(argc, argv);
+#if ENSEMBLE == NPT
+  if (mode == "volume") return run_volume(argc, argv);
+#endif
   fprintf(stderr, "unknown mode %s\n", argv[1]);
   return 1;
 }

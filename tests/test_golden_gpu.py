@@ -12,7 +12,9 @@ from tests.helpers import rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+# (full_*: full-size slab pins, tests/test_full_size.py; npt_* / pentane_*: own test modules)
+GOLDEN = sorted(g for g in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(g).startswith(("full_", "npt_", "pentane_", "cached_")))
 
 
 def _xyz(d, key):
