@@ -99,6 +99,7 @@ struct KSet {
   int n = 0, kmax = 0;
   int nmax[3] = {0, 0, 0};
   double cv[3] = {0, 0, 0};
+  double L[3] = {0, 0, 0};  // box edges this k set was built for (non-uniform FFT grid mapping)
   // factorised-sum plan
   DevBuf<int4> rows, tiles;
   int nTiles = 0, maxRows = 0, nRowsPadded = 0;
@@ -286,11 +287,11 @@ BoxParams make_params(const gomcb200_engine *e, int b) {
   return p;
 }
 
-int check_box(const gomcb200_engine *e, int b, bool needAxes = true) {
+int check_box(const gomcb200_engine *e, int b, bool needAxes = true, bool needTopo = true) {
   if (!e) return fail(GOMCB200_EINVAL, "null engine");
   if (b < 0 || b >= e->nBoxes) return fail(GOMCB200_EINVAL, "box %d out of range", b);
   if (!e->haveFF) return fail(GOMCB200_EINVAL, "gomcb200_init_forcefield not called");
-  if (!e->haveTopo) return fail(GOMCB200_EINVAL, "gomcb200_init_topology not called");
+  if (needTopo && !e->haveTopo) return fail(GOMCB200_EINVAL, "gomcb200_init_topology not called");
   if (e->vdwKind == VDW_EXP6 && !e->haveExp6)
     return fail(GOMCB200_EINVAL, "Potential EXP6: gomcb200_init_exp6 not called");
   if (needAxes && !e->box[b].haveAxes)
@@ -589,7 +590,7 @@ int recip_enumerate(const gomcb200_engine *e, int b, const double ax[3], KSet *k
   int nmax[3];
   for (int d = 0; d < 3; ++d) nmax[d] = int(recip_rcut * ax[d] / (2.0 * M_PI)) + 1;
   if (ks) {
-    for (int d = 0; d < 3; ++d) { ks->nmax[d] = nmax[d]; ks->cv[d] = cv[d]; }
+    for (int d = 0; d < 3; ++d) { ks->nmax[d] = nmax[d]; ks->cv[d] = cv[d]; ks->L[d] = ax[d]; }
     ks->kmax = std::max(std::max(nmax[0], nmax[1]), std::max(nmax[1], nmax[2]));
   }
   // Same loop nest, order and floating-point expressions as the reference; for large
@@ -1024,7 +1025,7 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     // cheap enough to be replicated (every rank then holds the complete sums, which the
     // single-molecule deltas need); rank 0 alone reports the energy.
     CK(e->part.reserve((size_t)2 * nkStride + 64));
-    rc = gbn::nufft_type1(e->nufft, e->stream, ks.ng, bx.axis, bx.packed.p, nAt, ks.rows.p,
+    rc = gbn::nufft_type1(e->nufft, e->stream, ks.ng, ks.L, bx.packed.p, nAt, ks.rows.p,
                           ks.nRowsPadded, e->part.p, e->part.p + nkStride, &e->launches);
     if (rc) return fail(GOMCB200_ECUDA, "nufft_type1: %s", gbn::nufft_last_error(e->nufft));
     nSlabs = 1;
@@ -1251,35 +1252,62 @@ int ensure_mirror(gomcb200_engine *e) {
   return 0;
 }
 
-// Stage {len, per atom: q, new xyz, old xyz} of one molecule into the pinned
-// area (at stageOffset) and queue its upload to molBuf.
-int stage_molbuf(gomcb200_engine *e, int molIndex, const double *nx, const double *ny,
-                 const double *nz, int mode, size_t stageOffset) {
-  const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+// Stage {len, per atom: qEff, new xyz, old xyz (mode 0) | lambda = 1 charge (swap modes)} into
+// the pinned area (at stageOffset) and queue its upload to molBuf.
+int stage_molbuf_raw(gomcb200_engine *e, int len, const double *qEff, const double *qTrue,
+                     const double *nx, const double *ny, const double *nz, const double *ox,
+                     const double *oy, const double *oz, int mode, size_t stageOffset) {
   size_t nd = 1 + 7 * (size_t)len;
   int rc = stage_reserve(e, stageOffset + nd * sizeof(double));
   if (rc) return rc;
-  if (mode == 0) {
-    rc = ensure_mirror(e);
-    if (rc) return rc;
-  }
   CK(e->molBuf.reserve(nd + 8));
   double *h = reinterpret_cast<double *>(reinterpret_cast<char *>(e->hStage) + stageOffset);
   h[0] = (double)len;
   for (int a = 0; a < len; ++a) {
     double *m = h + 1 + 7 * a;
-    m[0] = e->hChargeEff[s + a];  // Ewald terms see q * lambdaCoef
+    m[0] = qEff[a];  // Ewald terms see q * lambdaCoef
     m[1] = nx[a];
     m[2] = ny[a];
     m[3] = nz[a];
-    // old coordinates (host mirror); the swap modes carry the lambda = 1 charge there
-    // instead (SwapSelf uses it, src/Ewald.cpp:1375-1391)
-    m[4] = mode == 0 ? e->hx[s + a] : e->hCharge[s + a];
-    m[5] = mode == 0 ? e->hy[s + a] : 0.0;
-    m[6] = mode == 0 ? e->hz[s + a] : 0.0;
+    // old coordinates; the swap modes carry the lambda = 1 charge there instead (SwapSelf
+    // uses it, src/Ewald.cpp:1375-1391)
+    m[4] = mode == 0 ? ox[a] : qTrue[a];
+    m[5] = mode == 0 ? oy[a] : 0.0;
+    m[6] = mode == 0 ? oz[a] : 0.0;
   }
   CK(cudaMemcpyAsync(e->molBuf.p, h, nd * sizeof(double), cudaMemcpyHostToDevice,
                      e->stream));
+  return 0;
+}
+
+// the same for the resident molecule molIndex (old coordinates from the host mirror)
+int stage_molbuf(gomcb200_engine *e, int molIndex, const double *nx, const double *ny,
+                 const double *nz, int mode, size_t stageOffset) {
+  const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
+  if (mode == 0) {
+    int rc = ensure_mirror(e);
+    if (rc) return rc;
+  }
+  return stage_molbuf_raw(e, len, e->hChargeEff.data() + s, e->hCharge.data() + s, nx, ny, nz,
+                          mode == 0 ? e->hx.data() + s : nullptr,
+                          mode == 0 ? e->hy.data() + s : nullptr,
+                          mode == 0 ? e->hz.data() + s : nullptr, mode, stageOffset);
+}
+
+// k-space delta of the molecule staged in molBuf (k_mol_recip) on the Ref set; result[0]
+int launch_mol_recip(gomcb200_engine *e, int b, int len, int mode) {
+  BoxState &bx = e->box[b];
+  KSet &ks = bx.kset[1 - bx.cur];
+  const int nk = ks.n;
+  const int nBlocks = (nk + 255) / 256;
+  CK(e->blockA.reserve(nBlocks + 1024));
+  k_mol_recip<<<nBlocks, 256, 7 * len * sizeof(double), e->stream>>>(
+      nk, mode, e->molBuf.p, ks.kx.p, ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRref].p,
+      bx.sum[bx.iIref].p, bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p, e->blockA.p);
+  k_final_reduce<<<1, 1024, 0, e->stream>>>(nBlocks, 1, e->blockA.p, nullptr, nullptr,
+                                           nullptr, e->result.p);
+  e->launches += 2;
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -1298,15 +1326,8 @@ int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
   const int len = e->hMolStart[molIndex + 1] - e->hMolStart[molIndex];
   rc = stage_molbuf(e, molIndex, nx, ny, nz, mode, stageOffset);
   if (rc) return rc;
-  const int nBlocks = (nk + 255) / 256;
-  CK(e->blockA.reserve(nBlocks + 1024));
-  k_mol_recip<<<nBlocks, 256, 7 * len * sizeof(double), e->stream>>>(
-      nk, mode, e->molBuf.p, ks.kx.p, ks.ky.p, ks.kz.p, ks.prefact.p, bx.sum[bx.iRref].p,
-      bx.sum[bx.iIref].p, bx.sum[bx.iRnew].p, bx.sum[bx.iInew].p, e->blockA.p);
-  k_final_reduce<<<1, 1024, 0, e->stream>>>(nBlocks, 1, e->blockA.p, nullptr, nullptr,
-                                           nullptr, e->result.p);
-  e->launches += 2;
-  CK(cudaGetLastError());
+  rc = launch_mol_recip(e, b, len, mode);
+  if (rc) return rc;
   if (!sync) {  // caller synchronises once for several queued operations
     CK(cudaMemcpyAsync(e->hRes, e->result.p, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     return 0;
@@ -2538,7 +2559,7 @@ static int run_force_recip(gomcb200_engine *e, int box, const double *sumR, cons
       CK(cudaMemsetAsync(rfy, 0, bytes, e->stream));
       CK(cudaMemsetAsync(rfz, 0, bytes, e->stream));
     }
-    rc = gbn::nufft_type2_force(e->nufft, e->stream, ks.ng, bx.axis, bx.packed.p,
+    rc = gbn::nufft_type2_force(e->nufft, e->stream, ks.ng, ks.L, bx.packed.p,
                                 bx.chargedList.p, bx.nCharged, ks.rows.p, ks.nRowsPadded,
                                 ks.prefact.p, sumR, sumI, rfx, rfy, rfz, 0, &e->launches);
     if (rc) return fail(GOMCB200_ECUDA, "nufft_type2_force: %s", gbn::nufft_last_error(e->nufft));
@@ -2944,7 +2965,7 @@ int gomcb200_set_recip_ref(gomcb200_engine *e, int box) {
   }
   dst.hkx = src.hkx; dst.hky = src.hky; dst.hkz = src.hkz; dst.hhsqr = src.hhsqr;
   dst.hprefact = src.hprefact;
-  for (int d = 0; d < 3; ++d) { dst.nmax[d] = src.nmax[d]; dst.cv[d] = src.cv[d]; }
+  for (int d = 0; d < 3; ++d) { dst.nmax[d] = src.nmax[d]; dst.cv[d] = src.cv[d]; dst.L[d] = src.L[d]; }
   dst.kmax = src.kmax;
   rc = upload_kset(e, dst);
   if (rc) return rc;
@@ -3124,6 +3145,198 @@ int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
   if (REn) *REn = e->hRes[9];
   if (energyRecip) *energyRecip = recip;
   return 0;
+}
+
+
+// ---- literal drop-ins of the reciprocal seam: explicit charges / k list in ----------
+int gomcb200_set_kvectors(gomcb200_engine *e, int box, int n, const double *kx, const double *ky,
+                          const double *kz, const double *hsqr, const double *prefact) {
+  if (!e || box < 0 || box >= e->nBoxes || n < 0 || (n && (!kx || !ky || !kz || !hsqr || !prefact)))
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  if (e->imageTotal > 0 && n > e->imageTotal)
+    return fail(GOMCB200_EKMAX, "k list of %d entries exceeds imageTotal %d", n, e->imageTotal);
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[bx.cur];
+  ks.hkx.assign(kx, kx + n); ks.hky.assign(ky, ky + n); ks.hkz.assign(kz, kz + n);
+  ks.hhsqr.assign(hsqr, hsqr + n); ks.hprefact.assign(prefact, prefact + n);
+  ks.planValid = ks.mmaValid = ks.fmValid = ks.ngValid = false;
+  // Recover the integer structure of Ewald::RecipInitOrth's list (src/Ewald.cpp:865-896):
+  // entries are ordered by (a, b, c) with k = (a cvx, b cvy, c cvz); the first entry is
+  // (0, 0, 1), the first with ky != 0 is (0, 1, .), the first with kx != 0 is (1, ., .).
+  std::vector<RowRec> rows;
+  bool ok = !bx.nonOrth && n > 0 && kx[0] == 0.0 && ky[0] == 0.0 && kz[0] > 0.0;
+  double cv[3] = {0.0, 0.0, kz ? (n ? kz[0] : 0.0) : 0.0};
+  if (ok) {
+    for (int i = 0; i < n && (cv[0] == 0.0 || cv[1] == 0.0); ++i) {
+      if (cv[1] == 0.0 && kx[i] == 0.0 && ky[i] != 0.0) cv[1] = ky[i];
+      if (cv[0] == 0.0 && kx[i] != 0.0) cv[0] = kx[i];
+    }
+    ok = cv[0] > 0.0 && cv[1] > 0.0;
+  }
+  int nm[3] = {0, 0, 0};
+  if (ok) {
+    int pa = 0, pb = 0, pc = 0;
+    for (int i = 0; i < n && ok; ++i) {
+      const int a = (int)std::lround(kx[i] / cv[0]), b = (int)std::lround(ky[i] / cv[1]),
+                c = (int)std::lround(kz[i] / cv[2]);
+      // the list must be exactly the products the device regenerates
+      ok = kx[i] == cv[0] * a && ky[i] == cv[1] * b && kz[i] == cv[2] * c;
+      if (i == 0 || a != pa || b != pb) {
+        rows.push_back({a, b, c, i});
+      } else if (c != pc + 1) {
+        ok = false;
+      }
+      rows.back().cmax = c;  // last c of the row
+      pa = a; pb = b; pc = c;
+      nm[0] = std::max(nm[0], std::abs(a));
+      nm[1] = std::max(nm[1], std::abs(b));
+      nm[2] = std::max(nm[2], std::abs(c));
+    }
+    for (size_t r = 0; r < rows.size() && ok; ++r) {
+      const int first = rows[r].start;
+      const int cnt = (r + 1 < rows.size() ? rows[r + 1].start : n) - first;
+      const int c0 = (int)std::lround(kz[first] / cv[2]);
+      const bool origin = rows[r].a == 0 && rows[r].b == 0;
+      ok = origin ? (c0 == 1 && cnt == rows[r].cmax) : (c0 == -rows[r].cmax && cnt == 2 * rows[r].cmax + 1);
+    }
+  }
+  for (int d = 0; d < 3; ++d) {
+    ks.cv[d] = ok ? cv[d] : 0.0;
+    ks.nmax[d] = ok ? nm[d] : 0;
+    ks.L[d] = ok ? (2.0 * M_PI) / cv[d] : bx.axis[d];
+  }
+  ks.kmax = std::max(nm[0], std::max(nm[1], nm[2]));
+  int rc = upload_kset(e, ks, false);  // the host's own values, prefactor included
+  if (rc) return rc;
+  if (ok && !rows.empty()) {
+    rc = build_plan(e, ks, rows);
+    if (rc) return rc;
+    ks.ngValid = gbn::nufft_choose(ks.nmax, &ks.ng) == 0;
+  }
+  return 0;
+}
+
+int gomcb200_set_recip_sums(gomcb200_engine *e, int box, int which, const double *sumR,
+                            const double *sumI, int n) {
+  if (!e || box < 0 || box >= e->nBoxes || n < 0 || !sumR || !sumI)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  int rc = ensure_sums(e, bx, n);
+  if (rc) return rc;
+  const int ir = which == GOMCB200_SUM_NEW ? bx.iRnew : bx.iRref;
+  const int ii = which == GOMCB200_SUM_NEW ? bx.iInew : bx.iIref;
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(bx.sum[ir].p, sumR, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(bx.sum[ii].p, sumI, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int gomcb200_set_forces(gomcb200_engine *e, int which, const double *x, const double *y,
+                        const double *z, int first, int count) {
+  if (!e || !e->haveTopo || which < 0 || which > 4) return fail(GOMCB200_EINVAL, "bad arguments");
+  const int limit = (which == GOMCB200_ATOM_FORCE || which == GOMCB200_ATOM_FORCE_REC) ? e->nAtoms
+                                                                                       : e->nMols;
+  CK(cudaSetDevice(e->device));
+  return upload3(e, e->force[which][0], e->force[which][1], e->force[which][2], x, y, z, first,
+                 count, limit);
+}
+
+static int download_sums(gomcb200_engine *e, BoxState &bx, int n, double *sumR, double *sumI) {
+  if (sumR) CK(cudaMemcpy(sumR, bx.sum[bx.iRnew].p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  if (sumI) CK(cudaMemcpy(sumI, bx.sum[bx.iInew].p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int gomcb200_call_box_reciprocal_points(gomcb200_engine *e, int box, int newSet, int n,
+                                        const double *x, const double *y, const double *z,
+                                        const double *q, double *sumRnew, double *sumInew,
+                                        double *energyRecip) {
+  int rc = check_box(e, box, false, false);  // explicit charges: no topology needed
+  if (rc) return rc;
+  if (n < 0 || (n && (!x || !y || !z || !q))) return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  KSet &ks = bx.kset[newSet ? bx.cur : 1 - bx.cur];
+  // the charged points as the packed {x, y, z, q} array the structure-factor kernels read
+  rc = stage_reserve(e, sizeof(double4) * (size_t)(n + 1));
+  if (rc) return rc;
+  double4 *h = reinterpret_cast<double4 *>(e->hStage);
+  int m = 0;
+  double qmax = 0.0;
+  for (int i = 0; i < n; ++i) {
+    if (std::fabs(q[i]) < 0.000000001) continue;  // particleHasNoCharge, src/Ewald.cpp:107-111
+    h[m++] = make_double4(x[i], y[i], z[i], q[i]);
+    qmax = std::max(qmax, std::fabs(q[i]));
+  }
+  CK(bx.packed.reserve(m + 1));
+  if (m)
+    CK(cudaMemcpyAsync(bx.packed.p, h, sizeof(double4) * (size_t)m, cudaMemcpyHostToDevice,
+                       e->stream));
+  const int savedCharged = bx.nCharged;
+  const double savedQmax = bx.qMaxAbs;
+  bx.nCharged = m;
+  bx.qMaxAbs = std::max(qmax, 1e-300);
+  bx.packedDirty = false;
+  rc = run_recip_sums(e, box, ks);
+  bx.nCharged = savedCharged;
+  bx.qMaxAbs = savedQmax;
+  bx.packedDirty = true;  // the resident atoms are packed again by the next resident call
+  if (rc) return rc;
+  rc = fetch_result(e, 1);
+  if (rc) return rc;
+  if (energyRecip) *energyRecip = e->hRes[0];
+  return download_sums(e, bx, ks.n, sumRnew, sumInew);
+}
+
+int gomcb200_call_mol_reciprocal(gomcb200_engine *e, int box, int len, const double *q,
+                                 const double *oldX, const double *oldY, const double *oldZ,
+                                 const double *newX, const double *newY, const double *newZ,
+                                 double *sumRnew, double *sumInew, double *energyRecipNew) {
+  int rc = check_box(e, box, false, false);  // explicit charges: no topology needed
+  if (rc) return rc;
+  if (len < 1 || !q || !oldX || !oldY || !oldZ || !newX || !newY || !newZ || !energyRecipNew)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  const int nk = bx.kset[1 - bx.cur].n;
+  *energyRecipNew = 0.0;
+  if (nk == 0) return 0;
+  rc = ensure_sums(e, bx, nk);
+  if (rc) return rc;
+  rc = stage_molbuf_raw(e, len, q, q, newX, newY, newZ, oldX, oldY, oldZ, 0, 0);
+  if (rc) return rc;
+  rc = launch_mol_recip(e, box, len, 0);
+  if (rc) return rc;
+  rc = fetch_result(e, 1);
+  if (rc) return rc;
+  *energyRecipNew = e->hRes[0];
+  return download_sums(e, bx, nk, sumRnew, sumInew);
+}
+
+int gomcb200_call_swap_reciprocal(gomcb200_engine *e, int box, int len, const double *q,
+                                  const double *x, const double *y, const double *z, int insert,
+                                  double *sumRnew, double *sumInew, double *energyRecipNew) {
+  int rc = check_box(e, box, false, false);  // explicit charges: no topology needed
+  if (rc) return rc;
+  if (len < 1 || !q || !x || !y || !z || !energyRecipNew)
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  BoxState &bx = e->box[box];
+  const int nk = bx.kset[1 - bx.cur].n;
+  *energyRecipNew = 0.0;
+  if (nk == 0) return 0;
+  rc = ensure_sums(e, bx, nk);
+  if (rc) return rc;
+  rc = stage_molbuf_raw(e, len, q, q, x, y, z, nullptr, nullptr, nullptr, insert ? 1 : 2, 0);
+  if (rc) return rc;
+  rc = launch_mol_recip(e, box, len, insert ? 1 : 2);
+  if (rc) return rc;
+  rc = fetch_result(e, 1);
+  if (rc) return rc;
+  *energyRecipNew = e->hRes[0];
+  return download_sums(e, bx, nk, sumRnew, sumInew);
 }
 
 int gomcb200_set_shard(gomcb200_engine *e, int rank, int world) {

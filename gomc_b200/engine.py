@@ -95,6 +95,15 @@ _SIGS = {
     "gomcb200_call_box_force": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
                                          _dp, _dp, _dp, _dp, _dp, _dp]),
     "gomcb200_call_full_box_energy": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "gomcb200_set_kvectors": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]),
+    "gomcb200_call_box_reciprocal_points": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp,
+                                                      _dp, _dp, _dp, _dp, _dp]),
+    "gomcb200_call_mol_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp,
+                                               _dp, _dp, _dp, _dp, _dp]),
+    "gomcb200_call_swap_reciprocal": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp,
+                                                C.c_int, _dp, _dp, _dp]),
+    "gomcb200_set_recip_sums": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int]),
+    "gomcb200_set_forces": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int]),
     "gomcb200_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
     "gomcb200_mark_coords_changed": (C.c_int, [_vp]),
     "gomcb200_set_recip_algo": (C.c_int, [_vp, C.c_int]),
@@ -432,6 +441,44 @@ class Engine:
 
     def box_force_reciprocal(self, box=0):
         self._ck(self.L.gomcb200_box_force_reciprocal(self.h, box))
+
+    # ---- literal drop-ins of the reciprocal seam (host arrays in, host sums out) ----
+    def set_kvectors(self, box, kx, ky, kz, hsqr, prefact):
+        arrs = [_d(a) for a in (kx, ky, kz, hsqr, prefact)]
+        self._ck(self.L.gomcb200_set_kvectors(self.h, box, len(arrs[0][0]),
+                                              *[p for _, p in arrs]))
+
+    def call_box_reciprocal_points(self, box, new_set, x, y, z, q, nk):
+        (x, px), (y, py), (z, pz), (q, pq) = _d(x), _d(y), _d(z), _d(q)
+        r, i, e = np.zeros(nk), np.zeros(nk), C.c_double()
+        self._ck(self.L.gomcb200_call_box_reciprocal_points(
+            self.h, box, int(new_set), len(x), px, py, pz, pq, r.ctypes.data_as(_dp),
+            i.ctypes.data_as(_dp), C.byref(e)))
+        return e.value, r, i
+
+    def call_mol_reciprocal(self, box, q, old, new, nk):
+        arrs = [_d(a) for a in (q, *old, *new)]
+        r, i, e = np.zeros(nk), np.zeros(nk), C.c_double()
+        self._ck(self.L.gomcb200_call_mol_reciprocal(
+            self.h, box, len(arrs[0][0]), *[p for _, p in arrs], r.ctypes.data_as(_dp),
+            i.ctypes.data_as(_dp), C.byref(e)))
+        return e.value, r, i
+
+    def call_swap_reciprocal(self, box, q, xyz, insert, nk):
+        arrs = [_d(a) for a in (q, *xyz)]
+        r, i, e = np.zeros(nk), np.zeros(nk), C.c_double()
+        self._ck(self.L.gomcb200_call_swap_reciprocal(
+            self.h, box, len(arrs[0][0]), *[p for _, p in arrs], int(insert),
+            r.ctypes.data_as(_dp), i.ctypes.data_as(_dp), C.byref(e)))
+        return e.value, r, i
+
+    def set_recip_sums(self, box, which, sum_r, sum_i):
+        (r, pr), (i, pi) = _d(sum_r), _d(sum_i)
+        self._ck(self.L.gomcb200_set_recip_sums(self.h, box, which, pr, pi, len(r)))
+
+    def set_forces(self, which, x, y, z, first=0):
+        (x, px), (y, py), (z, pz) = _d(x), _d(y), _d(z)
+        self._ck(self.L.gomcb200_set_forces(self.h, which, px, py, pz, first, len(x)))
 
     def get_recip_sums(self, box, which, n):
         r, i = np.zeros(n), np.zeros(n)

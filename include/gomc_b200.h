@@ -386,6 +386,44 @@ int gomcb200_call_full_box_energy(gomcb200_engine *e, int box,
                                   const double *z, double *LJEn, double *REn,
                                   double *energyRecip);
 
+/* ---- literal drop-ins of the reciprocal seam ------------------------------
+ * The reference's Call*GPU functions of src/GPU/CalculateEwaldCUDAKernel.cuh take the
+ * k list, the box's point charges and the moved molecule as HOST arrays and return the
+ * sums to HOST arrays; these entry points keep exactly that convention, so the shim of
+ * integration/ (the reference's own symbols on top of this library) needs no knowledge of
+ * the topology.  sumRnew / sumInew may be NULL (no device -> host copy). */
+/* The k list Ewald::RecipInit built on the host (kx[box] ... prefact[box], imageSize[box])
+ * into the NEW k set: what CallBoxReciprocalSetupGPU receives (CalculateEwaldCUDAKernel.cuh:
+ * 27-33).  The integer (a, b, c) structure is recovered from the list; the prefactors are
+ * the host's. */
+int gomcb200_set_kvectors(gomcb200_engine *e, int box, int n, const double *kx,
+                          const double *ky, const double *kz, const double *hsqr,
+                          const double *prefact);
+/* CallBoxReciprocalSetupGPU (newSet = 1) / CallBoxReciprocalSumsGPU (newSet = 0) with the
+ * reference's arguments: n point charges q (already times lambdaCoef) at x, y, z. */
+int gomcb200_call_box_reciprocal_points(gomcb200_engine *e, int box, int newSet, int n,
+                                        const double *x, const double *y, const double *z,
+                                        const double *q, double *sumRnew, double *sumInew,
+                                        double *energyRecip);
+/* CallMolReciprocalGPU (CalculateEwaldCUDAKernel.cuh:40-44): old and new coordinates and
+ * the charges (times lambdaCoef) of the moved molecule. */
+int gomcb200_call_mol_reciprocal(gomcb200_engine *e, int box, int len, const double *q,
+                                 const double *oldX, const double *oldY, const double *oldZ,
+                                 const double *newX, const double *newY, const double *newZ,
+                                 double *sumRnew, double *sumInew, double *energyRecipNew);
+/* CallSwapReciprocalGPU (CalculateEwaldCUDAKernel.cuh:54-57). */
+int gomcb200_call_swap_reciprocal(gomcb200_engine *e, int box, int len, const double *q,
+                                  const double *x, const double *y, const double *z,
+                                  int insert, double *sumRnew, double *sumInew,
+                                  double *energyRecipNew);
+/* CallMolExchangeReciprocalGPU (CalculateEwaldCUDAKernel.cuh:45-48): host sums -> device. */
+int gomcb200_set_recip_sums(gomcb200_engine *e, int box, int which, const double *sumR,
+                            const double *sumI, int n);
+/* Host forces / torques -> the resident buffers (the molForceRef / molTorqueRef arguments of
+ * CallTranslateParticlesGPU / CallRotateParticlesGPU, TransformParticlesCUDAKernel.cuh:20-37). */
+int gomcb200_set_forces(gomcb200_engine *e, int which, const double *x, const double *y,
+                        const double *z, int first, int count);
+
 /* ---- multi-GPU sharding (one engine per GPU, one process per GPU) -------- */
 /* Rank `rank` of `world` evaluates its share of every full-box sweep:
  * a contiguous slab of cells for the pair path and a contiguous block of

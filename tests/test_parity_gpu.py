@@ -343,3 +343,55 @@ def test_int8_structure_factor_large_box():
         assert e.box_reciprocal_sums(0) == out[3][0]
     finally:
         e.close()
+
+
+def test_literal_reciprocal_dropins(case):
+    """The host-array forms of the reciprocal seam (what the reference's Call*GPU functions
+    receive: k list, point charges, the moved molecule's old/new coordinates) against the
+    resident-state entry points and the oracle."""
+    s, e, o = case
+    if not _ewald(s) or getattr(s, "cell_basis", None) is not None:
+        pytest.skip("orthogonal Ewald boxes")
+    kx, ky, kz, hs, pf, kmax = o.recip_init_orth()
+    nk = len(kx)
+    sR, sI = o.box_recip_sums(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge, kx, ky, kz)
+    scale = max(np.max(np.abs(sR)), np.max(np.abs(sI)))
+    # host k list in (new set), explicit charges in, sums out
+    e.set_kvectors(0, kx, ky, kz, hs, pf)
+    for a, b in zip(e.get_kvectors(0, eng.K_NEW | eng.K_DEVICE, nk), (kx, ky, kz, hs, pf)):
+        assert np.array_equal(a, b)
+    for algo in (0, 2, 5):
+        e.set_recip_algo(algo)
+        en, gR, gI = e.call_box_reciprocal_points(0, True, s.x, s.y, s.z, s.charge, nk)
+        assert np.max(np.abs(gR - sR)) <= TOL * scale and np.max(np.abs(gI - sI)) <= TOL * scale
+        assert abs(en - o.box_reciprocal(sR, sI, pf)) <= TOL * abs(en)
+    e.set_recip_algo(4)
+    e.set_recip_ref(0)
+    # a shuffled point order gives the same sums (only the summation order changes)
+    perm = np.random.default_rng(5).permutation(s.n_atoms)
+    en2, gR2, gI2 = e.call_box_reciprocal_points(0, False, s.x[perm], s.y[perm], s.z[perm],
+                                                 s.charge[perm], nk)
+    assert np.max(np.abs(gR2 - sR)) <= TOL * scale
+    # moved molecule by explicit coordinates == by index on the resident state
+    rng = np.random.default_rng(9)
+    m = int(rng.integers(s.n_mols))
+    sl = slice(s.mol_start[m], s.mol_start[m + 1])
+    nx, ny, nz = random_move(s, rng, m, 1.0)
+    e.box_reciprocal_sums(0)
+    e.update_recip(0)          # resident-atom sums as the reference state
+    want = e.mol_reciprocal(0, m, nx, ny, nz)
+    wR, wI = e.get_recip_sums(0, eng.SUM_NEW, nk)
+    en, gR, gI = e.call_mol_reciprocal(0, s.charge[sl], (s.x[sl], s.y[sl], s.z[sl]),
+                                       (nx, ny, nz), nk)
+    assert en == want and np.array_equal(gR, wR) and np.array_equal(gI, wI)
+    for insert in (1, 0):
+        want = e.swap_reciprocal(0, m, nx, ny, nz, insert)
+        en, gR, gI = e.call_swap_reciprocal(0, s.charge[sl], (nx, ny, nz), insert, nk)
+        assert en == want
+    # host sums -> device (CallMolExchangeReciprocalGPU)
+    e.set_recip_sums(0, eng.SUM_NEW, sR * 0.5, sI * 0.25)
+    bR, bI = e.get_recip_sums(0, eng.SUM_NEW, nk)
+    assert np.array_equal(bR, sR * 0.5) and np.array_equal(bI, sI * 0.25)
+    # restore the module's state
+    e.box_reciprocal_sums(0)
+    e.update_recip(0)
