@@ -27,6 +27,7 @@
 #include "recip_mma.cuh"
 #include "recip_i8.cuh"
 #include "force_mma.cuh"
+#include "pair2.cuh"
 #include "nufft.h"
 
 using namespace gb;
@@ -145,6 +146,11 @@ struct BoxState {
   DevBuf<int> sortedPos;  // global atom index -> position in the cell-sorted copy
   DevBuf<double> sx, sy, sz, sq;
   DevBuf<int2> skm;
+  DevBuf<int> maxCellPop;  // largest cell population of the current binning (device)
+  // erfc(alpha r)/r and Coulomb virial factor as piecewise polynomials in r^2 (pair2.cuh)
+  DevBuf<double> coulTab;
+  double tabAlpha = -1.0, tabRc2 = -1.0;
+  int tabN = 0, tabHi0 = 0;
   // reciprocal space
   KSet kset[2];  // index with cur / 1-cur
   int cur = 0;   // kset[cur] = "new" k set (kx[]), kset[1-cur] = Ref
@@ -203,6 +209,7 @@ struct gomcb200_engine {
   // 0 direct, 1 factorised SIMT, 2 factorised DMMA, 3 int8 tensor cores, 5 = non-uniform FFT,
   // 4 = automatic: the non-uniform FFT for orthogonal boxes, the direct kernels otherwise
   int recipAlgo = 4;
+  int pairAlgo = 1;  // 1: k_pair_box2 (pair2.cuh) for orthogonal boxes, 0: k_pair_box
   gbn::Nufft *nufft = nullptr;
   double recipAutoWork = 1e11;
   int shardRank = 0, shardWorld = 1;
@@ -343,12 +350,14 @@ int ensure_cells(gomcb200_engine *e, int b) {
   CK(bx.vals.reserve(n + 1));
   CK(bx.sortedAtoms.reserve(n + 1));
   CK(bx.cellStart.reserve(g.nCells + 2));
-  CK(bx.sx.reserve(n + 1));
-  CK(bx.sy.reserve(n + 1));
-  CK(bx.sz.reserve(n + 1));
-  CK(bx.sq.reserve(n + 1));
-  CK(bx.skm.reserve(n + 1));
+  CK(bx.sx.reserve(n + 2));
+  CK(bx.sy.reserve(n + 2));
+  CK(bx.sz.reserve(n + 2));
+  CK(bx.sq.reserve(n + 2));
+  CK(bx.skm.reserve(n + 2));
   CK(bx.sortedPos.reserve(e->nAtoms + 1));
+  CK(bx.maxCellPop.reserve(4));
+  CK(cudaMemsetAsync(bx.maxCellPop.p, 0, sizeof(int), e->stream));
   if (n > 0) {
     int blocks = (n + 255) / 256;
     k_cell_keys<<<blocks, 256, 0, e->stream>>>(g, n, bx.atomList.p, e->x.p, e->y.p,
@@ -370,7 +379,7 @@ int ensure_cells(gomcb200_engine *e, int b) {
     e->launches += 4;
   }
   k_cell_bounds<<<(g.nCells + 1 + 255) / 256, 256, 0, e->stream>>>(
-      g.nCells, n, bx.keysSorted.p, bx.cellStart.p);
+      g.nCells, n, bx.keysSorted.p, bx.cellStart.p, bx.maxCellPop.p);
   e->launches += 1;
   CK(cudaGetLastError());
   bx.cellsDirty = false;
@@ -384,13 +393,83 @@ int fetch_result(gomcb200_engine *e, int n) {
   return 0;
 }
 
+// ---- Coulomb real-space table of k_pair_box2 (pair2.cuh) -------------------
+// f(s) = erfc(alpha sqrt(s)) / sqrt(s) and g(s) = (f(s) + 2 alpha/sqrt(pi) exp(-alpha^2 s)) / s
+// (FFParticle::CalcCoulomb / CalcCoulombVir with Ewald on, src/FFParticle.cpp:400-446) on
+// s = r^2 in [2^eMin, 2^eMax): 32 intervals per octave, degree-7 interpolant at the Chebyshev
+// nodes of each interval, computed in long double and stored as monomial coefficients in
+// u in [-1, 1], coefficient-major.
+int ensure_coul_table(gomcb200_engine *e, int b) {
+  BoxState &bx = e->box[b];
+  const double alpha = e->alpha[b], rc = e->rCutCoulomb[b];
+  const double rc2 = rc * rc;
+  if (bx.tabN > 0 && bx.tabAlpha == alpha && bx.tabRc2 == rc2) return 0;
+  const int eMin = -2;  // r >= 0.5 A; closer pairs take the library path
+  int eMax = 1;
+  while (std::ldexp(1.0, eMax) <= rc2 * (1.0 + 1e-12)) ++eMax;
+  const int perOct = 1 << kCtBits, n = (eMax - eMin) * perOct;
+  std::vector<double> tab((size_t)2 * kCtWords * n);
+  const long double al = alpha, PI = 3.14159265358979323846264338327950288L;
+  const long double c2 = 2.0L * al / sqrtl(PI);
+  // Chebyshev polynomials T_k as monomial coefficients
+  long double T[kCtCoef][kCtCoef] = {};
+  T[0][0] = 1.0L;
+  T[1][1] = 1.0L;
+  for (int k = 2; k < kCtCoef; ++k)
+    for (int j = 0; j < kCtCoef; ++j)
+      T[k][j] = (j > 0 ? 2.0L * T[k - 1][j - 1] : 0.0L) - T[k - 2][j];
+  long double node[kCtCoef];
+  for (int j = 0; j < kCtCoef; ++j) node[j] = cosl(PI * (2 * j + 1) / (2.0L * kCtCoef));
+  for (int i = 0; i < n; ++i) {
+    const int oct = eMin + i / perOct, sub = i % perOct;
+    const long double s0 = ldexpl(1.0L + (long double)sub / perOct, oct);
+    const long double w = ldexpl(1.0L / perOct, oct);
+    long double fv[2][kCtCoef];
+    for (int j = 0; j < kCtCoef; ++j) {
+      const long double sv = s0 + w * (node[j] + 1.0L) * 0.5L, r = sqrtl(sv);
+      const long double f = erfcl(al * r) / r;
+      fv[0][j] = f;
+      fv[1][j] = (f + c2 * expl(-al * al * sv)) / sv;
+    }
+    for (int which = 0; which < 2; ++which) {
+      long double mono[kCtCoef] = {};
+      for (int k = 0; k < kCtCoef; ++k) {
+        long double a = 0.0L;
+        for (int j = 0; j < kCtCoef; ++j) {
+          // T_k(node_j) = cos(k (2j+1) pi / (2n))
+          a += fv[which][j] * cosl(PI * k * (2 * j + 1) / (2.0L * kCtCoef));
+        }
+        a *= (k == 0 ? 1.0L : 2.0L) / kCtCoef;
+        for (int j = 0; j <= k; ++j) mono[j] += a * T[k][j];
+      }
+      double *tw = tab.data() + (size_t)which * kCtWords * n;
+      for (int c = 0; c < 4; ++c) tw[(size_t)c * n + i] = (double)mono[c];
+      float *hi = reinterpret_cast<float *>(tw + (size_t)4 * n);  // (c4,c5)[n], (c6,c7)[n]
+      hi[2 * i] = (float)mono[4];
+      hi[2 * i + 1] = (float)mono[5];
+      hi[2 * n + 2 * i] = (float)mono[6];
+      hi[2 * n + 2 * i + 1] = (float)mono[7];
+    }
+  }
+  CK(bx.coulTab.reserve(tab.size()));
+  // the stream may still read the previous table
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(bx.coulTab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  bx.tabAlpha = alpha;
+  bx.tabRc2 = rc2;
+  bx.tabN = n;
+  bx.tabHi0 = (1023 + eMin) << kCtBits;
+  return 0;
+}
+
 // warps per CTA of the box sweep: the energy kernel fits 32 warps in the
 // register file (<= 64 regs/thread), the force kernel 20 (<= 102 regs/thread)
 constexpr int kWarpsEnergy = 32, kWarpsForce = 20, kWarpsVirial = 16;
 
 template <int FORCE>  // MODE_ENERGY, MODE_FORCE or MODE_VIRIAL
 void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int useSmem,
-                 int smemAtoms, size_t smemBytes, int grid, int cell0) {
+                 int smemAtoms, size_t smemBytes, int grid, int cell0,
+                 const int *gatePop = nullptr, int gateCap = 0) {
   BoxState &bx = e->box[b];
   constexpr int NW = FORCE == MODE_ENERGY ? kWarpsEnergy
                                           : (FORCE == MODE_VIRIAL ? kWarpsVirial : kWarpsForce);
@@ -404,7 +483,7 @@ void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int 
     k_pair_box<V, M, NW><<<grid, NW * 32, smemBytes, e->stream>>>(                  \
         p, bx.grid, slices, cell0, useSmem, smemAtoms, bx.cellStart.p, bx.sx.p, bx.sy.p,  \
         bx.sz.p, bx.sq.p, bx.skm.p, bx.sortedAtoms.p, e->blockA.p, e->blockB.p, fx, \
-        fy, fz);                                                                    \
+        fy, fz, gatePop, gateCap);                                                  \
   } while (0)
   // boxes with a fractional molecule run the instantiation that carries the soft-core branch
 #define LAUNCH(V)                                 \
@@ -427,6 +506,94 @@ void launch_pair(gomcb200_engine *e, int b, const BoxParams &p, int slices, int 
 #undef LAUNCH
 #undef LAUNCH_M
   e->launches += 1;
+}
+
+// k_pair_box2 (pair2.cuh): orthogonal boxes.  FAST (Ewald real-space terms from the table)
+// whenever the box has Ewald electrostatics and no fractional molecule.
+template <int MODE>
+int launch_pair2(gomcb200_engine *e, int b, const BoxParams &p, int slices, int grid, int cell0,
+                 int *capOut) {
+  BoxState &bx = e->box[b];
+  // warps per CTA (one CTA per SM): 80 / 96 / 128 registers per thread
+  constexpr int NW = MODE == MODE_ENERGY ? 24 : (MODE == MODE_VIRIAL ? 16 : 20);
+  const bool lam = bx.lambdaMol >= 0;
+  const bool fast = !lam && e->ewald && e->electrostatic;
+  int tabN = 0;
+  if (fast) {
+    int rc = ensure_coul_table(e, b);
+    if (rc) return rc;
+    tabN = bx.tabN;
+  }
+  // staging capacity: everything the SM's shared memory leaves (one CTA per SM)
+  const size_t fixed = pair2_smem_bytes(0, NW, MODE, tabN) + 6 * 1024 +
+                       (MODE == MODE_VIRIAL ? 8 * 1024 : 0);
+  if (e->smemOptin <= fixed + 56 * 256) return fail(GOMCB200_ECUDA, "shared memory too small");
+  int cap = (int)((e->smemOptin - fixed) / 56) & ~1;
+  // no more than the sweep can use: all neighbour cells of an average cell, with slack
+  const double avg = (double)bx.nAtoms / bx.grid.nCells;
+  const long long want = (long long)((MODE == MODE_FORCE ? 27.0 : 14.0) * (avg + 2.0) * 1.5) + 128;
+  if (MODE != MODE_FORCE || want <= cap) cap = (int)std::min<long long>(cap, want) & ~1;
+  cap = std::min(cap, 60000);
+  Pair2Args A;
+  A.p = p;
+  A.g = bx.grid;
+  A.slices = slices;
+  A.cell0 = cell0;
+  A.cap = cap;
+  A.gateCap = MODE == MODE_ENERGY ? cap / 2 : cap;  // energy passes re-stage the self range
+  // work items per CTA: aim at >= 8 per warp
+  const double nI = std::max(1.0, avg / slices);
+  A.nSeg = std::max(1, std::min(kP2MaxSeg, (int)std::ceil(8.0 * NW / nI)));
+  const double brs = p.boxRcutSq;
+  A.cutF = (float)(brs * (1.0 + 1e-4) + 1e-6);
+  A.tabN = tabN;
+  A.tabHi0 = bx.tabHi0;
+  A.tabF = bx.coulTab.p;
+  A.tabG = bx.coulTab.p ? bx.coulTab.p + (size_t)kCtWords * tabN : nullptr;
+  A.cellStart = bx.cellStart.p;
+  A.sx = bx.sx.p;
+  A.sy = bx.sy.p;
+  A.sz = bx.sz.p;
+  A.sq = bx.sq.p;
+  A.skm = bx.skm.p;
+  A.sortedAtoms = bx.sortedAtoms.p;
+  A.maxCellPop = bx.maxCellPop.p;
+  A.partLJ = e->blockA.p;
+  A.partReal = e->blockB.p;
+  A.fx = e->force[GOMCB200_ATOM_FORCE][0].p;
+  A.fy = e->force[GOMCB200_ATOM_FORCE][1].p;
+  A.fz = e->force[GOMCB200_ATOM_FORCE][2].p;
+  const size_t smemBytes = pair2_smem_bytes(cap, NW, MODE, tabN);
+#define LAUNCH2(V, M, F)                                                                   \
+  do {                                                                                     \
+    cudaFuncSetAttribute(k_pair_box2<V, M, NW, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         (int)smemBytes);                                                  \
+    k_pair_box2<V, M, NW, F><<<grid, NW * 32, smemBytes, e->stream>>>(A);                  \
+  } while (0)
+#define LAUNCH2V(V)                          \
+  do {                                       \
+    if (lam)                                 \
+      LAUNCH2(V, MODE | MODE_LAMBDA, false); \
+    else if (fast)                           \
+      LAUNCH2(V, MODE, true);                \
+    else                                     \
+      LAUNCH2(V, MODE, false);               \
+  } while (0)
+  if (e->vdwKind == VDW_SHIFT)
+    LAUNCH2V(VDW_SHIFT);
+  else if (e->vdwKind == VDW_SWITCH)
+    LAUNCH2V(VDW_SWITCH);
+  else if (e->vdwKind == VDW_EXP6)
+    LAUNCH2V(VDW_EXP6);
+  else if (e->vdwKind == VDW_MARTINI)
+    LAUNCH2V(VDW_MARTINI);
+  else
+    LAUNCH2V(VDW_STD);
+#undef LAUNCH2V
+#undef LAUNCH2
+  e->launches += 1;
+  *capOut = A.gateCap;
+  return 0;
 }
 
 // pair sweep; results (LJ, real) land in e->result[0..1]; mode MODE_VIRIAL: the six
@@ -462,8 +629,24 @@ int run_pair(gomcb200_engine *e, int b, int mode) {
     CK(cudaMemsetAsync(e->result.p, 0, 8 * sizeof(double), e->stream));
     return 0;
   }
+  // orthogonal boxes: k_pair_box2, with the first kernel queued behind it as the fallback
+  // for cells too full to stage (both test the same device-side population count)
+  const int *gate = nullptr;
+  int gateCap = 0;
+  if (e->pairAlgo == 1 && !bx.nonOrth) {
+    if (mode == MODE_VIRIAL)
+      rc = launch_pair2<MODE_VIRIAL>(e, b, p, slices, grid, cell0, &gateCap);
+    else if (force)
+      rc = launch_pair2<MODE_FORCE>(e, b, p, slices, grid, cell0, &gateCap);
+    else
+      rc = launch_pair2<MODE_ENERGY>(e, b, p, slices, grid, cell0, &gateCap);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    gate = bx.maxCellPop.p;
+  }
   if (mode == MODE_VIRIAL) {
-    launch_pair<MODE_VIRIAL>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
+    launch_pair<MODE_VIRIAL>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0, gate,
+                             gateCap);
     CK(cudaGetLastError());
     const double *a = e->blockA.p;
     k_final_reduce<<<1, 1024, 0, e->stream>>>(grid, 4, a, e->blockB.p, a + 2 * (size_t)grid,
@@ -478,9 +661,11 @@ int run_pair(gomcb200_engine *e, int b, int mode) {
   if (force) {
     // ResetForce (src/CalculateEnergy.cpp:1408-1428) is implicit: every atom
     // and molecule of the box is overwritten below.
-    launch_pair<MODE_FORCE>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
+    launch_pair<MODE_FORCE>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0, gate,
+                            gateCap);
   } else {
-    launch_pair<MODE_ENERGY>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0);
+    launch_pair<MODE_ENERGY>(e, b, p, slices, useSmem, smemAtoms, smemBytes, grid, cell0, gate,
+                             gateCap);
   }
   CK(cudaGetLastError());
   k_final_reduce<<<1, 1024, 0, e->stream>>>(grid, 2, e->blockA.p, e->blockB.p, nullptr,
@@ -3355,6 +3540,12 @@ int gomcb200_mark_coords_changed(gomcb200_engine *e) {
 int gomcb200_set_recip_algo(gomcb200_engine *e, int algo) {
   if (!e || algo < 0 || algo > 5) return fail(GOMCB200_EINVAL, "bad arguments");
   e->recipAlgo = algo;
+  return 0;
+}
+
+int gomcb200_set_pair_algo(gomcb200_engine *e, int algo) {
+  if (!e || algo < 0 || algo > 1) return fail(GOMCB200_EINVAL, "bad arguments");
+  e->pairAlgo = algo;
   return 0;
 }
 

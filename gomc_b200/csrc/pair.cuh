@@ -60,12 +60,9 @@ __global__ void k_cell_keys(CellGrid g, int n, const int *__restrict__ atomList,
   vals[t] = a;
 }
 
-// cellStart[c] = first sorted position whose key >= c (lower bound).
-__global__ void k_cell_bounds(int nCells, int n,
-                              const int *__restrict__ sortedKeys,
-                              int *cellStart) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > nCells) return;
+// cellStart[c] = first sorted position whose key >= c (lower bound); *maxPop (zeroed by the
+// caller) = largest cell population.
+__device__ __forceinline__ int cell_lower_bound(const int *__restrict__ sortedKeys, int n, int c) {
   int lo = 0, hi = n;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
@@ -74,7 +71,19 @@ __global__ void k_cell_bounds(int nCells, int n,
     else
       hi = mid;
   }
+  return lo;
+}
+__global__ void k_cell_bounds(int nCells, int n,
+                              const int *__restrict__ sortedKeys,
+                              int *cellStart, int *maxPop) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nCells) return;
+  int lo = cell_lower_bound(sortedKeys, n, c);
   cellStart[c] = lo;
+  if (c < nCells) {
+    int pop = cell_lower_bound(sortedKeys, n, c + 1) - lo;
+    if (pop > 0) atomicMax(maxPop, pop);
+  }
 }
 
 __global__ void k_gather_sorted(int n, const int *__restrict__ sortedAtoms,
@@ -402,7 +411,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1)
                const double *__restrict__ sq, const int2 *__restrict__ skm,
                const int *__restrict__ sortedAtoms, double *__restrict__ partLJ,
                double *__restrict__ partReal, double *__restrict__ fx,
-               double *__restrict__ fy, double *__restrict__ fz) {
+               double *__restrict__ fy, double *__restrict__ fz,
+               const int *__restrict__ gatePop, int gateCap) {
+  // launched behind k_pair_box2 (pair2.cuh) as its fallback: runs only when a cell is too
+  // full for that kernel's staging pass (the same test makes k_pair_box2 return at once)
+  if (gatePop && *gatePop + 2 <= gateCap) return;
   constexpr bool FORCE = (MODE & 3) == MODE_FORCE;
   constexpr bool VIRIAL = (MODE & 3) == MODE_VIRIAL;
   extern __shared__ __align__(16) unsigned char dynSmem[];

@@ -101,39 +101,7 @@ __global__ void __launch_bounds__(256)
   *dst = v;
 }
 
-// ---- PTX helpers -------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-// 1-D bulk copy global -> shared through the TMA unit (bytes % 16 == 0).
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes,
-                                         unsigned bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
+// ---- PTX helpers: mbarrier / bulk copy in common.cuh -----------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
   asm volatile(
       "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"

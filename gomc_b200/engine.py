@@ -107,6 +107,7 @@ _SIGS = {
     "gomcb200_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
     "gomcb200_mark_coords_changed": (C.c_int, [_vp]),
     "gomcb200_set_recip_algo": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_set_pair_algo": (C.c_int, [_vp, C.c_int]),
     "gomcb200_set_recip_auto_work": (C.c_int, [_vp, C.c_double]),
     "gomcb200_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gomcb200_enable_timing": (C.c_int, [_vp, C.c_int]),
@@ -537,6 +538,9 @@ class Engine:
 
     def set_recip_algo(self, algo):
         self._ck(self.L.gomcb200_set_recip_algo(self.h, int(algo)))
+
+    def set_pair_algo(self, algo):
+        self._ck(self.L.gomcb200_set_pair_algo(self.h, int(algo)))
 
     def set_recip_auto_work(self, work):
         self._ck(self.L.gomcb200_set_recip_auto_work(self.h, float(work)))

@@ -452,6 +452,11 @@ int gomcb200_mark_coords_changed(gomcb200_engine *e);
  * of the box reaches the work threshold below (1e11: boxes of ~3e5 atoms up,
  * where the INT8 kernel measured 2.6x faster). */
 int gomcb200_set_recip_algo(gomcb200_engine *e, int algo);
+/* pair-sweep kernel of BoxInter / BoxForce / VirialCalc on orthogonal boxes: 1 = default,
+ * k_pair_box2 (TMA-staged cells, FP32 candidate filter, tabulated Ewald real-space terms);
+ * 0 = the first kernel (FP64 candidate tests, library erfc), always used for triclinic
+ * boxes.  Both decide InRcut on the same FP64 r^2; energies agree to ~1e-13 relative. */
+int gomcb200_set_pair_algo(gomcb200_engine *e, int algo);
 /* work threshold (charged atoms x k-vectors) of algorithm 4 */
 int gomcb200_set_recip_auto_work(gomcb200_engine *e, double work);
 /* CUDA-event time (ms) of the kernels launched by the last call, and the

@@ -395,3 +395,77 @@ def test_literal_reciprocal_dropins(case):
     # restore the module's state
     e.box_reciprocal_sums(0)
     e.update_recip(0)
+
+
+# ---- the two pair-sweep kernels (gomcb200_set_pair_algo) ---------------------------------
+def _pair_outputs(e, s):
+    en = e.box_inter(0)
+    fe = e.box_force(0)
+    f = [np.array(c) for c in e.get_forces(eng.ATOM_FORCE)]
+    e.set_com(*s.com())
+    vir = np.concatenate(e.box_inter_virial(0))
+    return en, fe, f, vir
+
+
+@pytest.mark.parametrize("name", ["spce_small", "spce_mid", "argon", "mixture_shift",
+                                  "mixture_exp6", "mixture_martini"])
+def test_pair_kernels_agree(name):
+    """k_pair_box2 (TMA staging, FP32 filter, tabulated Ewald real-space terms) against the
+    first kernel on the same coordinates: the filter never decides InRcut, so the pair sets
+    are identical and energies / forces / virial agree to rounding (1e-12), far inside TOL."""
+    s = SMALL_SYSTEMS[name]()
+    e = eng.Engine.from_system(s)
+    try:
+        e.set_pair_algo(0)
+        a = _pair_outputs(e, s)
+        e.set_pair_algo(1)
+        b = _pair_outputs(e, s)
+        for k in (0, 1):
+            for x, y in zip(a[k], b[k]):
+                assert abs(x - y) <= 1e-12 * max(abs(x), 1.0), (name, k, x, y)
+        for c in range(3):
+            assert rel_err(b[2][c], a[2][c]) <= 1e-12
+        assert rel_err(b[3], a[3]) <= 1e-12
+        assert _pair_outputs(e, s)[0] == b[0]      # bit-reproducible
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("dense_cells,per_cell", [(3, 300), (1, 600)])
+def test_pair_sweep_dense_cells(dense_cells, per_cell):
+    """Uneven boxes: a few cells far above the average population.  300 atoms in three
+    neighbouring cells exceeds one staging pass of k_pair_box2 (several passes, the self range
+    re-staged); 600 atoms in one cell exceeds what it can stage at all, so the kernel queued
+    behind it as the fallback must take over (device-side gate, no host round trip)."""
+    s = synth.make_argon(4000)                       # L = 57.3, 5 cells of 11.5 A per axis
+    rng = np.random.default_rng(3)
+    cs = float(s.axis[0]) / 5.0
+    moved = rng.permutation(s.n_atoms)[:dense_cells * per_cell]
+    for c in range(dense_cells):
+        idx = moved[c * per_cell:(c + 1) * per_cell]
+        lo = np.array([1.0 + c, 2.0, 2.0]) * cs
+        # a jittered sub-lattice inside the cell keeps the pairs apart (r > 1 A)
+        g = int(np.ceil(per_cell ** (1 / 3)))
+        pts = np.stack(np.meshgrid(*[np.arange(g)] * 3, indexing="ij"), -1).reshape(-1, 3)
+        pts = (pts[:per_cell] + 0.5 + rng.uniform(-0.1, 0.1, (per_cell, 3))) * (cs / g)
+        s.x[idx], s.y[idx], s.z[idx] = (lo + pts).T
+    e = eng.Engine.from_system(s)
+    o = oracle_for(s)
+    try:
+        olj, ore, aF, mF = o.box_force(s.x, s.y, s.z, s.kind, s.mol, s.charge, box_atoms(s),
+                                       s.n_mols)
+        res = {}
+        for algo in (0, 1):
+            e.set_pair_algo(algo)
+            lj, _ = e.box_inter(0)
+            flj, _ = e.box_force(0)
+            f = [np.array(c) for c in e.get_forces(eng.ATOM_FORCE)]
+            assert abs(lj - olj) <= TOL * abs(olj)
+            assert abs(flj - olj) <= TOL * abs(olj)
+            for c in range(3):
+                assert rel_err(f[c], aF[c]) <= TOL
+            res[algo] = (lj, flj)
+        if dense_cells == 1:     # energy sweep fell back: the very same kernel ran
+            assert res[0][0] == res[1][0]
+    finally:
+        e.close()
