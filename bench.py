@@ -7,16 +7,20 @@ the synthetic SPC/E box BASELINE's target is quoted on (100 002 atoms,
 Rcut = RcutCoulomb = 10 A, Tolerance 1e-5 -> 102 978 k-vectors).
 
   python bench.py --gpus N --steps K --warmup W [--workload spce100k|spce10k|argon4k|electrolyte1m]
-                  [--recip-algo 2|3]    # force the FP64-MMA / INT8 structure-factor kernel
-                                        # (default: the engine's choice, INT8 from 1e11 atom x k terms)
+                  [--recip-algo 5|2|3]  # structure factor: non-uniform FFT (default) / FP64-DMMA /
+                                        # INT8 direct sums
+                  [--pair-algo 1|0]     # pair sweep: k_pair_box2 (default) / the first kernel
   python bench.py --impl reference ...   # the reference's own CPU path on the host cores
 
 One JSON line on stdout (rank 0).  `value` is timed with inputs resident in
 HBM (cell binning + packing of the coordinates included every step); `e2e`
 goes through the host-buffer C-ABI call (pinned host coordinates in, three
-doubles out, copies inside the timed region).  Multi-GPU (torchrun): cells and
-k rows are sharded, coordinates replicated, the three partial energies are
-all-reduced with NCCL; strong scaling (the box is fixed).
+doubles out, copies inside the timed region).  Multi-GPU (torchrun): cell slabs
+and FFT x-slabs are sharded, coordinates replicated; the engine's own NCCL
+communicator all-gathers the pruned FFT slabs and all-reduces the three
+energies on the engine's stream; strong scaling (the box is fixed).  Every
+line of the default workload also carries `cfg5`: the same step on the 1 M-atom
+electrolyte box at this N.
 """
 import argparse
 import ctypes as C
@@ -157,8 +161,9 @@ def cpu_baseline_port(s, budget_s=12.0):
         t_slab = time.perf_counter() - t0
     t_full = t_inter + (t_slab * nk / slab if slab else 0.0)
     return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"BoxInter on the full box ({t_inter:.2f} s) + BoxReciprocalSums on "
-                      f"{slab} of {nk} k-vectors ({t_slab:.2f} s), extrapolated linearly in k"}
+            "sample": f"ESTIMATED from a k-slab: BoxInter on the full box ({t_inter:.2f} s) + "
+                      f"BoxReciprocalSums on {slab} of {nk} k-vectors ({t_slab:.2f} s), "
+                      "extrapolated linearly in k"}
 
 
 def run_reference(args):
@@ -202,7 +207,7 @@ def run_reference(args):
         scale = nk_full / nk_slab if nk_slab else 0.0
         t_full = t_inter + (t_sums + t_rec) * scale
         kind, threads = "reference", int(dmp["threads"][0])
-        sample = (f"unmodified GOMC CPU build (oracle/_ref): BoxInter full box ({t_inter:.3f} s) "
+        sample = (f"ESTIMATED from a k-slab: unmodified GOMC CPU build (oracle/_ref): BoxInter full box ({t_inter:.3f} s) "
                   f"+ BoxReciprocalSums/BoxReciprocal on {nk_slab} of {nk_full} k-vectors "
                   f"({t_sums:.3f} s), extrapolated linearly in k; median of {reps} steps")
     else:
@@ -337,6 +342,62 @@ def small_box_extras(eng, device, flush, reps=200):
             "timing": "wall clock per call incl. H2D of the trial molecule and D2H of the scalars"}
 
 
+def share_unique_id(eng, rank, world, dist, torch):
+    """rank 0 makes the NCCL unique id of the engines' own communicator; the process group of
+    the launcher only carries its 128 bytes to the other ranks."""
+    if world == 1:
+        return None
+    t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def time_full_box(e, world, dist, torch, flush, px, py, pz, steps, host):
+    """`steps` timed evaluations.  Device time per step = CUDA events on the engine's stream
+    around the whole call (binning, both sweeps, the in-engine NCCL all-reduce); wall time is
+    taken next to it.  Returns (device ms, structure-factor stage ms, wall ms, energies)."""
+    out = [C.c_double(), C.c_double(), C.c_double()]
+    outp = [C.byref(o) for o in out]
+    dev, dom, wall = [], [], []
+    for _ in range(steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        if host:
+            rc = e.L.gomcb200_call_full_box_energy(e.h, 0, px, py, pz, *outp)
+        else:
+            e.L.gomcb200_mark_coords_changed(e.h)
+            rc = e.L.gomcb200_call_full_box_energy(e.h, 0, None, None, None, *outp)
+        if rc:
+            raise RuntimeError(e.L.gomcb200_last_error().decode())
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t0) * 1e3)
+        a, b = e.last_timing()
+        dev.append(a)
+        dom.append(b)
+    return np.array(dev), np.array(dom), np.array(wall), [o.value for o in out]
+
+
+def cfg5_record(eng, local, rank, world, dist, torch, flush, steps):
+    """The box north_star's multi-GPU target is quoted on (1 M-atom electrolyte, 1.05 M
+    k-vectors), same step, at this N: rides in every line so that the driver's scaling run
+    carries the curve."""
+    s = make_system("electrolyte1m")
+    e = eng.Engine.from_system(s, device=local)
+    e.set_comm(share_unique_id(eng, rank, world, dist, torch), rank, world)
+    e.enable_timing(True)
+    for _ in range(3):
+        time_full_box(e, world, dist, torch, flush, None, None, None, 1, False)
+    dev, dom, wall, en = time_full_box(e, world, dist, torch, flush, None, None, None, steps, False)
+    nk = e.nk
+    e.close()
+    return s, nk, float(np.mean(dev)), float(np.mean(wall)), float(np.mean(dom)), en
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,10 +407,12 @@ def main():
     ap.add_argument("--workload", default="spce100k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--recip-algo", type=int, default=None, choices=[2, 3],
-                    help="structure-factor kernel of the timed step: 2 = FP64 DMMA, 3 = INT8 "
-                         "tcgen05 byte-sliced; default = the engine's own choice (2 below 1e11 "
-                         "charged atoms x k-vectors, 3 from there on)")
+    ap.add_argument("--recip-algo", type=int, default=None, choices=[2, 3, 5],
+                    help="structure-factor algorithm of the timed step: 5 = non-uniform FFT "
+                         "(the engine's default for orthogonal boxes), 2 = FP64 DMMA direct "
+                         "sum, 3 = INT8 tcgen05 byte-sliced direct sum")
+    ap.add_argument("--pair-algo", type=int, default=None, choices=[0, 1],
+                    help="pair-sweep kernel: 1 = k_pair_box2 (default), 0 = the first kernel")
     ap.add_argument("--no-ref-gpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -372,56 +435,34 @@ def main():
 
     s = make_system(args.workload)
     e = eng.Engine.from_system(s, device=local)
-    e.set_shard(rank, world)
+    # the engine's own NCCL communicator: cells and FFT slabs sharded, the three energies
+    # all-reduced on the engine's stream (no collective in this script's timed region)
+    e.set_comm(share_unique_id(eng, rank, world, dist, torch), rank, world)
     e.enable_timing(True)
     nk = e.nk
     n_charged = int(np.count_nonzero(np.abs(s.charge) >= 1e-9))
-    if args.recip_algo is None:        # the rule of gomcb200_set_recip_algo(e, 4), the default
-        args.recip_algo = 3 if float(n_charged) * nk >= 1e11 else 2
-    else:
+    if args.recip_algo is not None:
         e.set_recip_algo(args.recip_algo)
+    if args.pair_algo is not None:
+        e.set_pair_algo(args.pair_algo)
+    recip_algo = args.recip_algo if args.recip_algo is not None else 5
+    ewald = bool(s.ff.ewald and s.ff.electrostatic)
 
     # pinned host coordinates for the e2e leg
     hx, hy, hz = (torch.from_numpy(a.copy()).pin_memory() for a in (s.x, s.y, s.z))
     dp = C.POINTER(C.c_double)
     px, py, pz = (C.cast(t.data_ptr(), dp) for t in (hx, hy, hz))
-    out = [C.c_double(), C.c_double(), C.c_double()]
-    outp = [C.byref(o) for o in out]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def step(host):
-        if host:
-            rc = e.L.gomcb200_call_full_box_energy(e.h, 0, px, py, pz, *outp)
-        else:
-            e.L.gomcb200_mark_coords_changed(e.h)
-            rc = e.L.gomcb200_call_full_box_energy(e.h, 0, None, None, None, *outp)
-        if rc:
-            raise RuntimeError(e.L.gomcb200_last_error().decode())
-        # the path's only exchange: three partial energies (NCCL all-reduce)
-        return shard.allreduce_energies([o.value for o in out], world, "cuda")
-
-    def timed(host, k):
-        tot, dom, wall = [], [], []
-        for _ in range(k):
-            flush.zero_()
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            en = step(host)
-            torch.cuda.synchronize()
-            wall.append((time.perf_counter() - t0) * 1e3)
-            a, b = e.last_timing()
-            tot.append(a)
-            dom.append(b)
-        return np.array(tot), np.array(dom), np.array(wall), en
+    def run(host, k):
+        return time_full_box(e, world, dist, torch, flush, px, py, pz, k, host)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        step(False)
-        step(True)
+        run(False, 1)
+        run(True, 1)
     torch.cuda.synchronize()
     # nvidia-smi needs ~1 s to deliver its first sample: keep the GPU under the same
     # load until it does, so that the clocks are those of the timed region
@@ -437,22 +478,38 @@ def main():
                 go = int(flag.item())
             if not go:
                 return
-            step(False)
+            run(False, 1)
 
     load_until_samples(1, 5.0)
     sampler.lines.clear()
     l0 = e.launch_count()
-    dev_ms, dom_ms, wall_ms, en_res = timed(False, args.steps)
+    dev_ms, dom_ms, wall_ms, en_res = run(False, args.steps)
     l1 = e.launch_count()
-    dev_ms_h, _, wall_ms_h, en_host = timed(True, args.steps)
+    dev_ms_h, _, wall_ms_h, en_host = run(True, args.steps)
     # a short timed region (sharded runs take tens of ms) can fall between two 100 ms
     # nvidia-smi samples: keep the same load running until three samples exist
     load_until_samples(3, 3.0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the dominant kernels timed alone (CUDA events on the engine's stream) ----------
+    # pair sweep: second call on unchanged coordinates = the sweep kernel + its final reduce
+    def alone(fn, k):
+        fn()
+        t = []
+        for _ in range(k):
+            flush.zero_()
+            torch.cuda.synchronize()
+            fn()
+            t.append(e.last_timing()[0])
+        return float(np.mean(t))
+    pair_ms = alone(lambda: e.box_inter(0), max(5, args.steps // 2))
+    recip_stage_ms = float(np.mean(dom_ms)) if ewald else 0.0
+
     # secondary metric of BASELINE.json: MultiParticle moves/s = the energy/force work of
     # MultiParticle::CalcEn (src/moves/MultiParticle.h:414-441): BoxReciprocalSums + BoxForce
     # + BoxReciprocal + BoxForceReciprocal + torque, coordinates resident (single GPU)
     mp_ms = mp_move_ms = None
-    if world == 1 and s.ff.ewald:
+    if world == 1 and ewald:
         def mp_step():
             e.L.gomcb200_mark_coords_changed(e.h)
             e.box_reciprocal_sums(0)
@@ -496,66 +553,118 @@ def main():
             mp_move(i)
             t_mv.append((time.perf_counter() - t0) * 1e3)
         mp_move_ms = float(np.mean(t_mv))
-    # INT8 tensor-core structure factor (recip algorithm 3; the engine picks it by itself only
-    # for >= 1e11 atom x k boxes): same step, same timing
-    i8 = None
-    if world == 1 and s.ff.ewald and args.recip_algo == 2:
-        e.set_recip_algo(3)
-        for _ in range(3):
-            step(False)
-        d3, m3, _, en3 = timed(False, max(5, args.steps // 2))
+    # the direct-sum structure-factor kernels of round 1 next to the default (same step)
+    direct = None
+    if world == 1 and ewald and recip_algo == 5 and not args.no_extras:
+        direct = {}
+        for algo, name in ((2, "fp64_dmma"), (3, "int8_tcgen05")):
+            e.set_recip_algo(algo)
+            for _ in range(2):
+                run(False, 1)
+            d3, m3, _, en3 = run(False, max(3, args.steps // 4))
+            direct[name] = {"ms_per_step": float(np.mean(d3)),
+                            "structure_factor_stage_ms": float(np.mean(m3)),
+                            "recip_rel_diff_vs_default": abs(en3[2] - en_res[2]) / abs(en_res[2])}
         e.set_recip_algo(4)
-        i8 = {"ms_per_step": float(np.mean(d3)), "structure_factor_stage_ms": float(np.mean(m3)),
-              "recip_rel_diff_vs_default": abs(en3[2] - en_res[2]) / abs(en_res[2]),
-              "what": "gomcb200_set_recip_algo(e, 3): tcgen05.mma kind::i8 + TMEM, byte-sliced "
-                      "fixed point (DESIGN.md 4.1b); the default only from 1e11 atom x k terms up"}
-    clocks = sampler.stop() if rank == 0 else None
+        direct["what"] = ("gomcb200_set_recip_algo 2 / 3: the N x nk direct sums on FP64 DMMA and on "
+                          "tcgen05 kind::i8 (DESIGN.md 4.1, 4.1b); the default is the non-uniform FFT")
     extras = None
     if world == 1 and args.workload == "spce100k" and not args.no_extras:
         extras = small_box_extras(eng, local, flush)
+    e.close()
+    cfg5 = None
+    if args.workload == "spce100k" and not args.no_extras:
+        s5, nk5, dev5, wall5, dom5, en5 = cfg5_record(eng, local, rank, world, dist, torch, flush,
+                                                      max(3, min(args.steps, 5)))
+        dev5, wall5 = (shard.max_over_ranks(v, world, "cuda") for v in (dev5, wall5))
+        cfg5 = {"workload": f"electrolyte1m: {s5.n_atoms} atoms, L={float(s5.axis[0])} A, "
+                            f"k-vectors={nk5} (BASELINE configs[4])",
+                "n_gpus": world, "ms_per_step": dev5, "value": 1e3 / dev5, "unit": UNIT,
+                "wall_ms_per_step": wall5, "structure_factor_stage_ms": dom5,
+                "energies": {"lj": en5[0], "real": en5[1], "recip": en5[2]},
+                "timing": "CUDA events on the engine stream, max over ranks; coordinates "
+                          "resident, re-binned every step"}
 
-    # resident: device time of the step (CUDA events on the engine's stream) for
-    # N = 1; with sharding the step ends with the all-reduce, so wall time between
-    # synchronisations is the honest number.  Max over ranks either way.
-    ms_res = float(np.mean(dev_ms if world == 1 else wall_ms))
-    ms_e2e = float(np.mean(wall_ms_h))
-    ms_dom = float(np.mean(dom_ms))
-    ms_res, ms_e2e, ms_dom = (shard.max_over_ranks(v, world, "cuda")
-                              for v in (ms_res, ms_e2e, ms_dom))
+    # One clock at every N: CUDA events on the engine's stream around the whole call (the
+    # all-reduce is on that stream), max over ranks.  Wall time between synchronisations is
+    # reported next to it.
+    ms_res = shard.max_over_ranks(float(np.mean(dev_ms)), world, "cuda")
+    ms_res_wall = shard.max_over_ranks(float(np.mean(wall_ms)), world, "cuda")
+    ms_e2e = shard.max_over_ranks(float(np.mean(wall_ms_h)), world, "cuda")
+    pair_ms = shard.max_over_ranks(pair_ms, world, "cuda")
+    recip_stage_ms = shard.max_over_ranks(recip_stage_ms, world, "cuda")
 
     if rank == 0:
         peak = fp64_peak()
-        peak_tf = peak.get("dfma_tflops")
-        flops = 4.0 * n_charged * nk / world      # 2 FMA per (charged atom, k)
-        ach = flops / (ms_dom * 1e-3) * 1e-12 if ms_dom > 0 else None
+        dfma_tf, dmma_tf = peak.get("dfma_tflops"), peak.get("dmma_tflops")
+        # pairs inside rc x ~60 flop + candidate tests x 11 flop
+        vol = float(np.prod(s.axis))
+        rho = s.n_atoms / vol
+        rc = max(s.ff.r_cut, s.ff.r_cut_coulomb)
+        p_in = 0.5 * s.n_atoms * (4.0 / 3.0) * np.pi * rc ** 3 * rho
+        cells = [max(int(a // rc), 3) for a in s.axis]
+        p_cand = 0.5 * 27.0 * (s.n_atoms / float(np.prod(cells))) * s.n_atoms
+        pair_flops = (60.0 * p_in + 11.0 * p_cand) / world
+        pair_ach = pair_flops / (pair_ms * 1e-3) * 1e-12
+        pair_bytes = 40.0 * s.n_atoms / world
         traffic = None
         tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tj):
-            traffic = json.load(open(tj)).get("k_recip_mma_dram_bytes")
+            traffic = json.load(open(tj)).get("k_pair_box2_dram_bytes")
+        peaks = {}
+        pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pj):
+            peaks = json.load(open(pj))
+        hbm_peak = peaks.get("hbm_gbs")   # driver-written copy bandwidth of this pool's B200s
+        sf_flops = 4.0 * n_charged * nk
         line = {
             "metric": METRIC, "value": 1e3 / ms_res, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res,
+            "wall_ms_per_step": ms_res_wall,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, s, nk, {
-                "parallelism": f"cells+k-rows sharded over {world} GPU(s), coordinates replicated",
-                "recip_algo": args.recip_algo}),
+                "parallelism": f"cell slabs + FFT x-slabs sharded over {world} GPU(s), coordinates "
+                               "replicated, NCCL inside the engine (all-gather of the pruned FFT "
+                               "slabs, all-reduce of 3 energies)",
+                "recip_algo": recip_algo, "pair_algo": 1 if args.pair_algo is None else args.pair_algo,
+                "timing": "CUDA events on the engine stream around the whole call, max over ranks"}),
             "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": 3 * 8 * s.n_atoms, "d2h_bytes_per_step": 24},
+                    "h2d_bytes_per_step": 3 * 8 * s.n_atoms, "d2h_bytes_per_step": 24,
+                    "timing": "wall clock around gomcb200_call_full_box_energy, pinned host "
+                              "coordinates in, three doubles out"},
             "gpu_launches": int(l1 - l0),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "structure-factor stage: k_phase_tables + k_recip_mma (DMMA) + k_recip_finish"
-                         if args.recip_algo == 2 else
-                         "structure-factor stage with --recip-algo 3: k_i8_tables + k_recip_i8 (tcgen05 kind::i8); "
-                         "achieved = FP64-equivalent flops, so frac against the DFMA peak is a speed ratio, not a utilisation",
-                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (ach / peak_tf) if (ach and peak_tf) else None,
+            # the dominant kernel of the step: the pair sweep (43 % of the device time)
+            "roofline": {"bound": "fp64",
+                         "kernel": "k_pair_box2<VDW_STD, MODE_ENERGY> (+ its 4 us final reduce): "
+                                   "BoxInter on unchanged coordinates, timed alone",
+                         "achieved": pair_ach, "peak": dfma_tf, "unit": "TFLOP/s",
+                         "frac": (pair_ach / dfma_tf) if dfma_tf else None,
                          "traffic": traffic,
-                         "algorithmic_flops_per_launch": flops,
-                         "kernel_ms": ms_dom,
+                         "algorithmic_flops_per_launch": pair_flops,
+                         "algorithmic": "SURVEY.md 8(d): 60 flop x pairs inside rc "
+                                        f"({p_in:.3g}) + 11 flop x candidate pairs ({p_cand:.3g})",
+                         "kernel_ms": pair_ms,
                          "peak_source": "tools/fp64_peak DFMA stream measured in this run "
-                                        "(MEASURED_PEAKS.json has no FP64 entry)",
-                         "dmma_peak": peak.get("dmma_tflops")},
+                                        "(MEASURED_PEAKS.json has no FP64 entry); the kernel is "
+                                        "bound by shared-memory wavefronts and issue slots, not "
+                                        "by the FP64 pipe (profiles/r2_pair2_ncu.txt)",
+                         "hbm": {"achieved_GBps": pair_bytes / (pair_ms * 1e-3) * 1e-9,
+                                 "peak_GBps": hbm_peak,
+                                 "algorithmic_bytes_per_launch": pair_bytes,
+                                 "note": "40 B/atom once: the pair path is not HBM-bound by "
+                                         "construction (SURVEY.md 8d)"}},
+            "structure_factor": None if not ewald else {
+                "stage_ms": recip_stage_ms,
+                "algorithm": {5: "non-uniform FFT (type 1): DMMA spread, pruned FP64 FFT",
+                              2: "direct sum, FP64 DMMA", 3: "direct sum, INT8 tcgen05"}[recip_algo],
+                "direct_sum_equivalent_TFLOPs": sf_flops / (recip_stage_ms * 1e-3) * 1e-12,
+                "direct_sum_flops": sf_flops,
+                "dfma_peak_TFLOPs": dfma_tf, "dmma_peak_TFLOPs": dmma_tf,
+                "note": "4 flop x charged atoms x k-vectors is the minimum of the DIRECT sum "
+                        "(SURVEY.md 8d); the FFT path does ~20x less arithmetic, so this figure "
+                        "is a speed ratio against that algorithm, not a pipe utilisation"},
             "multiparticle": (None if mp_ms is None else {
                 "value": 1e3 / mp_ms, "unit": "MP energy/force evaluations per s",
                 "ms_per_step": mp_ms,
@@ -564,8 +673,9 @@ def main():
                 "full_move_ms": mp_move_ms,
                 "full_move": "device trial transform + CalcEn on the trial set + GetCoeff + "
                              "reject, coordinates never leave the GPU"}),
-            "int8_tensor_core": i8,
+            "direct_sum_kernels": direct,
             "small_box": extras,
+            "cfg5": cfg5,
             "energies": {"lj": en_res[0], "real": en_res[1], "recip": en_res[2],
                          "host_path_identical": en_res == en_host},
         }
@@ -574,7 +684,6 @@ def main():
         if not args.no_ref_gpu and world == 1:
             line["reference_gpu_build"] = reference_gpu_build(s)
         print(json.dumps(line))
-    e.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

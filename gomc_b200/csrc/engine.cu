@@ -29,6 +29,7 @@
 #include "force_mma.cuh"
 #include "pair2.cuh"
 #include "nufft.h"
+#include "comm.h"
 
 using namespace gb;
 
@@ -210,6 +211,8 @@ struct gomcb200_engine {
   // 4 = automatic: the non-uniform FFT for orthogonal boxes, the direct kernels otherwise
   int recipAlgo = 4;
   int pairAlgo = 1;  // 1: k_pair_box2 (pair2.cuh) for orthogonal boxes, 0: k_pair_box
+  gbc::Comm *comm = nullptr;  // NCCL communicator of a sharded engine (gomcb200_set_comm)
+  DevBuf<double> energy3;     // LJ, real, recip of a full-box evaluation (all-reduced in place)
   gbn::Nufft *nufft = nullptr;
   double recipAutoWork = 1e11;
   int shardRank = 0, shardWorld = 1;
@@ -605,11 +608,15 @@ int run_pair(gomcb200_engine *e, int b, int mode) {
   BoxState &bx = e->box[b];
   BoxParams p = make_params(e, b);
   const int nCells = bx.grid.nCells;
-  int slices = (4 * e->numSMs + nCells - 1) / nCells;
-  slices = std::max(1, std::min(slices, 16));
   // multi-GPU: this rank owns cells [cell0, cell1) (x-major slab)
   const int cell0 = (int)(((long long)nCells * e->shardRank) / e->shardWorld);
   const int cell1 = (int)(((long long)nCells * (e->shardRank + 1)) / e->shardWorld);
+  // CTAs per cell: enough CTAs for the SMs this rank has to fill (a sharded rank owns few
+  // cells), but every slice re-stages the whole neighbourhood
+  const int owned = std::max(1, cell1 - cell0);
+  int slices = e->shardWorld > 1 ? (2 * e->numSMs + owned - 1) / owned
+                                 : (4 * e->numSMs + nCells - 1) / nCells;
+  slices = std::max(1, std::min(slices, 16));
   int grid = (cell1 - cell0) * slices;
   // shared-memory staging of the neighbour cells (40 B per atom)
   const int nWarps = mode == MODE_ENERGY ? kWarpsEnergy
@@ -1186,6 +1193,25 @@ int ensure_packed(gomcb200_engine *e, int b) {
 
 // Structure factor of box b on k set `ks` into sumRnew/sumInew; energy into
 // result[0].  (BoxReciprocalSetup: ks = new set; BoxReciprocalSums: Ref set.)
+int nufft_allgather_cb(void *ctx, void *buf, size_t bytesPerRank, cudaStream_t st) {
+  gomcb200_engine *e = static_cast<gomcb200_engine *>(ctx);
+  std::string err;
+  if (gbc::comm_allgather_inplace(e->comm, buf, bytesPerRank, st, err))
+    return fail(GOMCB200_ECUDA, "%s", err.c_str());
+  e->launches += 1;
+  return 0;
+}
+
+// sum of n doubles at buf over the ranks of the communicator (no-op without one)
+int allreduce_energies(gomcb200_engine *e, double *buf, int n) {
+  if (!e->comm || e->shardWorld <= 1) return 0;
+  std::string err;
+  if (gbc::comm_allreduce_sum(e->comm, buf, (size_t)n, e->stream, err))
+    return fail(GOMCB200_ECUDA, "%s", err.c_str());
+  e->launches += 1;
+  return 0;
+}
+
 int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
   BoxState &bx = e->box[b];
   const int nk = ks.n;
@@ -1210,8 +1236,12 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     // cheap enough to be replicated (every rank then holds the complete sums, which the
     // single-molecule deltas need); rank 0 alone reports the energy.
     CK(e->part.reserve((size_t)2 * nkStride + 64));
+    // With a communicator the spread and the first two FFT passes are sharded by x slabs and
+    // the pruned slabs all-gathered (nufft.h); without one (set_shard only) it is replicated.
+    gbn::NufftShard sh = {e->shardRank, e->shardWorld, nufft_allgather_cb, e};
     rc = gbn::nufft_type1(e->nufft, e->stream, ks.ng, ks.L, bx.packed.p, nAt, ks.rows.p,
-                          ks.nRowsPadded, e->part.p, e->part.p + nkStride, &e->launches);
+                          ks.nRowsPadded, e->part.p, e->part.p + nkStride, &e->launches,
+                          (e->comm && e->shardWorld > 1) ? &sh : nullptr);
     if (rc) return fail(GOMCB200_ECUDA, "nufft_type1: %s", gbn::nufft_last_error(e->nufft));
     nSlabs = 1;
     nufftDone = true;
@@ -1757,6 +1787,7 @@ int gomcb200_destroy(gomcb200_engine *e) {
   if (e->hStage) cudaFreeHost(e->hStage);
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   gbn::nufft_destroy(e->nufft);
+  gbc::comm_destroy(e->comm);
   cudaStreamDestroy(e->stream);
   delete e;
   return 0;
@@ -2139,6 +2170,8 @@ int gomcb200_box_inter(gomcb200_engine *e, int box, double *LJEn, double *REn) {
   CK(cudaSetDevice(e->device));
   timing_begin(e);
   rc = run_pair(e, box, false);
+  if (rc) return rc;
+  rc = allreduce_energies(e, e->result.p, 2);
   if (rc) return rc;
   rc = fetch_result(e, 2);
   if (rc) return rc;
@@ -2541,6 +2574,8 @@ static int recip_sums_common(gomcb200_engine *e, int box, bool newSet, double *e
   BoxState &bx = e->box[box];
   timing_begin(e);
   rc = run_recip_sums(e, box, bx.kset[newSet ? bx.cur : 1 - bx.cur]);
+  if (rc) return rc;
+  rc = allreduce_energies(e, e->result.p, 1);
   if (rc) return rc;
   rc = fetch_result(e, 1);
   if (rc) return rc;
@@ -3310,22 +3345,30 @@ int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
     if (rc) return rc;
   }
   timing_begin(e);
+  CK(e->energy3.reserve(4));
   rc = run_pair(e, box, false);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(e->hRes + 8, e->result.p, 2 * sizeof(double), cudaMemcpyDeviceToHost,
+  CK(cudaMemcpyAsync(e->energy3.p, e->result.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice,
                      e->stream));
   BoxState &bx = e->box[box];
-  double recip = 0.0;
-  if (e->ewald && e->electrostatic) {
+  const bool recipOn = e->ewald && e->electrostatic;
+  if (recipOn) {
     rc = run_recip_sums(e, box, bx.kset[1 - bx.cur]);
     if (rc) return rc;
-    rc = fetch_result(e, 1);
-    if (rc) return rc;
-    recip = e->hRes[0];
+    CK(cudaMemcpyAsync(e->energy3.p + 2, e->result.p, sizeof(double), cudaMemcpyDeviceToDevice,
+                       e->stream));
   } else {
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemsetAsync(e->energy3.p + 2, 0, sizeof(double), e->stream));
   }
-  timing_end(e, e->ewald && e->electrostatic);
+  // sharded engine with a communicator: the path's only reduction, three doubles, on the
+  // engine's stream; every rank returns the complete energies
+  rc = allreduce_energies(e, e->energy3.p, 3);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->hRes + 8, e->energy3.p, 3 * sizeof(double), cudaMemcpyDeviceToHost,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const double recip = e->hRes[10];
+  timing_end(e, recipOn);
   if (LJEn) *LJEn = e->hRes[8];
   if (REn) *REn = e->hRes[9];
   if (energyRecip) *energyRecip = recip;
@@ -3526,6 +3569,32 @@ int gomcb200_call_swap_reciprocal(gomcb200_engine *e, int box, int len, const do
 
 int gomcb200_set_shard(gomcb200_engine *e, int rank, int world) {
   if (!e || world < 1 || rank < 0 || rank >= world) return fail(GOMCB200_EINVAL, "bad arguments");
+  e->shardRank = rank;
+  e->shardWorld = world;
+  return 0;
+}
+
+int gomcb200_comm_unique_id(void *id128) {
+  if (!id128) return fail(GOMCB200_EINVAL, "bad arguments");
+  std::string err;
+  if (gbc::comm_unique_id(id128, err)) return fail(GOMCB200_ECUDA, "%s", err.c_str());
+  return 0;
+}
+
+int gomcb200_set_comm(gomcb200_engine *e, const void *id128, int rank, int world) {
+  if (!e || world < 1 || rank < 0 || rank >= world || (world > 1 && !id128))
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->comm) {
+    gbc::comm_destroy(e->comm);
+    e->comm = nullptr;
+  }
+  if (world > 1) {
+    std::string err;
+    e->comm = gbc::comm_create(id128, rank, world, err);
+    if (!e->comm) return fail(GOMCB200_ECUDA, "%s", err.c_str());
+  }
   e->shardRank = rank;
   e->shardWorld = world;
   return 0;

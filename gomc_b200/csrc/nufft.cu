@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <tuple>
@@ -106,16 +107,35 @@ __global__ void k_nufft_bounds(int nBins, int n, const int *__restrict__ sortedK
 // Window tables of the atoms in bin-sorted order.  One thread per (atom, axis, j):
 // tab[(s*3 + d)*W + j] = psi(x0_d + j - t_d), with q folded into the x table when
 // foldQ; start[s] = {x0, y0, z0, original index}.  dtab (type 2 only): d psi / dt.
+// binStart != nullptr: tables only for the atoms of the x-bin planes px0 .. px1 (cyclic: the
+// planes whose stencils can reach a rank's slab of bricks).  Atoms are sorted x-plane-major,
+// so these are one or two contiguous runs of the sorted order; their bounds are read from
+// binStart on the device and the (fixed-size) grid strides over them.
 template <int W>
 __global__ void k_nufft_tables(GridGeom g, int nAtoms, double beta,
                                const double4 *__restrict__ packed,
                                const int *__restrict__ sortedIdx, int foldQ,
                                int4 *__restrict__ start, double *__restrict__ tab,
-                               double *__restrict__ dtab) {
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int s = (int)(tid / (3 * W));
-  if (s >= nAtoms) return;
-  const int r = (int)(tid - (long long)s * 3 * W);
+                               double *__restrict__ dtab,
+                               const int *__restrict__ binStart, int px0, int px1) {
+  int lo1 = 0, len1 = nAtoms, lo2 = 0, len2 = 0;
+  if (binStart) {
+    const int perX = g.nb[1] * g.nb[2];
+    if (px0 <= px1) {
+      lo1 = binStart[px0 * perX];
+      len1 = binStart[(px1 + 1) * perX] - lo1;
+    } else {  // wraps: planes px0 .. nb-1 and 0 .. px1
+      lo1 = binStart[px0 * perX];
+      len1 = nAtoms - lo1;
+      len2 = binStart[(px1 + 1) * perX];
+    }
+  }
+  const long long total = (long long)(len1 + len2) * 3 * W;
+  for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < total;
+       tid += (long long)gridDim.x * blockDim.x) {
+  const int sl = (int)(tid / (3 * W));
+  const int s = sl < len1 ? lo1 + sl : lo2 + (sl - len1);
+  const int r = (int)(tid - (long long)sl * 3 * W);
   const int d = r / W, j = r - d * W;
   const int i = sortedIdx[s];
   const double4 a = packed[i];
@@ -141,6 +161,7 @@ __global__ void k_nufft_tables(GridGeom g, int nAtoms, double beta,
     int *st = reinterpret_cast<int *>(start + s);
     st[d] = x0;
     if (d == 0) st[3] = i;
+  }
   }
 }
 
@@ -187,7 +208,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 template <int W>
 __global__ void __launch_bounds__(256, 4)
     k_nufft_spread(GridGeom g, const int *__restrict__ binStart, const int4 *__restrict__ start,
-                   const double *__restrict__ tab, double *__restrict__ grid) {
+                   const double *__restrict__ tab, double *__restrict__ grid, int brick0) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   double *sB = reinterpret_cast<double *>(smemRaw);  // [2][kChunk + 1][kSlot]
   __shared__ int sX0[3][kChunk], sY0[3][kChunk], sZ0[3][kChunk], sSrc[3][kChunk];
@@ -196,9 +217,10 @@ __global__ void __launch_bounds__(256, 4)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned ltMask = (1u << lane) - 1u;
-  const int bz = blockIdx.x % g.nb[2];
-  const int by = (blockIdx.x / g.nb[2]) % g.nb[1];
-  const int bx = blockIdx.x / (g.nb[2] * g.nb[1]);
+  const int brick = (int)blockIdx.x + brick0;  // x-major; a rank's share is a slab of x
+  const int bz = brick % g.nb[2];
+  const int by = (brick / g.nb[2]) % g.nb[1];
+  const int bx = brick / (g.nb[2] * g.nb[1]);
   const int bx0 = bx * kBrick, by0 = by * kBrick, bz0 = bz * kBrick;
   const int px = 8 * (warp & 1), py = 4 * (warp >> 1);  // patch origin inside the brick
   const int px0 = bx0 + px, py0 = by0 + py;
@@ -883,15 +905,19 @@ GridGeom make_geom(const NufftGrid &g, const double L[3]) {
 template <int W>
 void launch_tables(const GridGeom &gg, int nAtoms, double beta, const double4 *packed,
                    const int *sortedIdx, int4 *start, double *tab, double *dtab,
-                   cudaStream_t st) {
+                   cudaStream_t st, const int *sortedKeys /* binStart */ = nullptr, int px0 = 0,
+                   int px1 = 0) {
   const long long total = (long long)nAtoms * 3 * W;
-  k_nufft_tables<W><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      gg, nAtoms, beta, packed, sortedIdx, 1, start, tab, dtab);
+  const long long blocks = std::min<long long>((total + 255) / 256, 148LL * 32);
+  k_nufft_tables<W><<<(unsigned)blocks, 256, 0, st>>>(
+      gg, nAtoms, beta, packed, sortedIdx, 1, start, tab, dtab, sortedKeys, px0, px1);
 }
 
 // bin the atoms and build their window tables (dtab too when wantD)
+// bx0 < bx1: tables only for the atoms that can reach the bricks bx0 .. bx1-1 along x
 int bin_atoms(Nufft *nf, cudaStream_t st, const NufftGrid &g, const GridGeom &gg,
-              const double4 *packed, int nAtoms, bool wantD, long long *launches) {
+              const double4 *packed, int nAtoms, bool wantD, long long *launches, int bx0 = 0,
+              int bx1 = 0) {
   const int nBins = gg.nb[0] * gg.nb[1] * gg.nb[2];
   NCK(nf->keys.reserve(nAtoms + 1));
   NCK(nf->keysSorted.reserve(nAtoms + 1));
@@ -914,12 +940,22 @@ int bin_atoms(Nufft *nf, cudaStream_t st, const NufftGrid &g, const GridGeom &gg
   k_nufft_bounds<<<(nBins + 1 + 255) / 256, 256, 0, st>>>(nBins, nAtoms, nf->keysSorted.p,
                                                          nf->binStart.p);
   double *dt = wantD ? nf->dtab.p : nullptr;
+  const int *sk = nullptr;
+  int px0 = 0, px1 = 0;
+  if (bx1 > bx0 && bx1 - bx0 + 2 < gg.nb[0]) {  // one bin of halo on either side, cyclic
+    sk = nf->binStart.p;
+    px0 = (bx0 - 1 + gg.nb[0]) % gg.nb[0];
+    px1 = bx1 % gg.nb[0];
+  }
   if (g.w == 12)
-    launch_tables<12>(gg, nAtoms, g.beta, packed, nf->sortedIdx.p, nf->start.p, nf->tab.p, dt, st);
+    launch_tables<12>(gg, nAtoms, g.beta, packed, nf->sortedIdx.p, nf->start.p, nf->tab.p, dt, st,
+                      sk, px0, px1);
   else if (g.w == 14)
-    launch_tables<14>(gg, nAtoms, g.beta, packed, nf->sortedIdx.p, nf->start.p, nf->tab.p, dt, st);
+    launch_tables<14>(gg, nAtoms, g.beta, packed, nf->sortedIdx.p, nf->start.p, nf->tab.p, dt, st,
+                      sk, px0, px1);
   else
-    launch_tables<16>(gg, nAtoms, g.beta, packed, nf->sortedIdx.p, nf->start.p, nf->tab.p, dt, st);
+    launch_tables<16>(gg, nAtoms, g.beta, packed, nf->sortedIdx.p, nf->start.p, nf->tab.p, dt, st,
+                      sk, px0, px1);
   NCK(cudaGetLastError());
   *launches += 5;
   return 0;
@@ -944,7 +980,7 @@ int set_smem(Nufft *nf, K kernel, size_t bytes) {
 
 int nufft_type1(Nufft *nf, cudaStream_t st, const NufftGrid &g, const double L[3],
                 const double4 *packed, int nAtoms, const int4 *rows, int nRows, double *outR,
-                double *outI, long long *launches) {
+                double *outI, long long *launches, const NufftShard *shard) {
   if (!nf) return -1;
   if (g.w != 12 && g.w != 14 && g.w != 16) {
     nf->err = "unsupported window width";
@@ -965,40 +1001,75 @@ int nufft_type1(Nufft *nf, cudaStream_t st, const NufftGrid &g, const double L[3
       (rc = get_twiddle(nf, n3, &tw3)) || (rc = get_deconv(nf, n1, g.w, g.beta, &dc0)) ||
       (rc = get_deconv(nf, n2, g.w, g.beta, &dc1)) || (rc = get_deconv(nf, n3, g.w, g.beta, &dc2)))
     return rc;
-  rc = bin_atoms(nf, st, g, gg, packed, nAtoms, false, launches);
+  // GOMCB200_NUFFT_TRACE=1: per-phase device times of this call on stderr (debugging aid)
+  static const bool trace = getenv("GOMCB200_NUFFT_TRACE") != nullptr;
+  cudaEvent_t tev[8];
+  int nTev = 0;
+  auto mark = [&]() {
+    if (!trace) return;
+    cudaEventCreate(&tev[nTev]);
+    cudaEventRecord(tev[nTev++], st);
+  };
+  mark();
+  // this rank's slab of bricks / planes along x (everything when not sharded)
+  int bx0 = 0, bx1 = gg.nb[0];
+  const bool sharded = shard && shard->world > 1 && shard->allgather &&
+                       gg.nb[0] % shard->world == 0;
+  if (sharded) {
+    const int per = gg.nb[0] / shard->world;
+    bx0 = shard->rank * per;
+    bx1 = bx0 + per;
+  }
+  const int x0 = bx0 * kBrick, nx = (bx1 - bx0) * kBrick;  // planes of the slab
+  rc = bin_atoms(nf, st, g, gg, packed, nAtoms, false, launches, sharded ? bx0 : 0,
+                 sharded ? bx1 : 0);
   if (rc) return rc;
-  nf->binnedAtoms = nAtoms;
+  nf->binnedAtoms = sharded ? -1 : nAtoms;  // sharded: the tables are partial
   nf->binnedW = g.w;
+  mark();
   // spread
   {
-    const int nBricks = gg.nb[0] * gg.nb[1] * gg.nb[2];
+    const int perX = gg.nb[1] * gg.nb[2];
+    const int nBricks = (bx1 - bx0) * perX, brick0 = bx0 * perX;
     if (g.w == 12) {
       if ((rc = set_smem(nf, k_nufft_spread<12>, kSpreadSmem))) return rc;
-      k_nufft_spread<12><<<nBricks, 256, kSpreadSmem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
+      k_nufft_spread<12><<<nBricks, 256, kSpreadSmem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p, brick0);
     } else if (g.w == 14) {
       if ((rc = set_smem(nf, k_nufft_spread<14>, kSpreadSmem))) return rc;
-      k_nufft_spread<14><<<nBricks, 256, kSpreadSmem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
+      k_nufft_spread<14><<<nBricks, 256, kSpreadSmem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p, brick0);
     } else {
       if ((rc = set_smem(nf, k_nufft_spread<16>, kSpreadSmem))) return rc;
-      k_nufft_spread<16><<<nBricks, 256, kSpreadSmem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p);
+      k_nufft_spread<16><<<nBricks, 256, kSpreadSmem, st>>>(gg, nf->binStart.p, nf->start.p, nf->tab.p, nf->grid.p, brick0);
     }
   }
-  // pruned FFT: z, y, x
+  mark();
+  // pruned FFT: z and y on the slab's planes, then x over everything
   {
     const int LP = std::max(1, std::min(16, (int)((96 * 1024 / sizeof(double2) - n3 / 2) / n3)));
-    const long long nPairs = (long long)n1 * n2 / 2;
+    const long long nPairs = (long long)nx * n2 / 2;
     const size_t smem = fft_smem(n3, LP);
     if ((rc = set_smem(nf, k_fft_z_fwd, smem))) return rc;
     k_fft_z_fwd<<<(unsigned)((nPairs + LP - 1) / LP), 256, smem, st>>>(
-        n1, n2, n3, ilog2(n3), C1, LP, nf->grid.p, tw3, nf->h1.p);
+        nx, n2, n3, ilog2(n3), C1, LP, nf->grid.p + (size_t)x0 * n2 * n3, tw3,
+        nf->h1.p + (size_t)x0 * n2 * C1);
   }
   {
     const int CB = pick_cb(n2, C1);
     const size_t smem = fft_smem(n2, CB);
     if ((rc = set_smem(nf, k_fft_mid, smem))) return rc;
-    k_fft_mid<<<n1 * ((C1 + CB - 1) / CB), 256, smem, st>>>(n2, ilog2(n2), C1, CB, NB, g.nmax[1],
-                                                           nf->h1.p, tw2, nf->h2.p);
+    k_fft_mid<<<nx * ((C1 + CB - 1) / CB), 256, smem, st>>>(
+        n2, ilog2(n2), C1, CB, NB, g.nmax[1], nf->h1.p + (size_t)x0 * n2 * C1, tw2,
+        nf->h2.p + (size_t)x0 * NB * C1);
   }
+  mark();
+  if (sharded) {
+    NCK(cudaGetLastError());
+    if (shard->allgather(shard->ctx, nf->h2.p, sizeof(double2) * (size_t)nx * NB * C1, st)) {
+      nf->err = "all-gather of the pruned slabs failed";
+      return -1;
+    }
+  }
+  mark();
   {
     const int CB = pick_cb(n1, C1);
     const size_t smem = fft_smem(n1, CB);
@@ -1010,6 +1081,19 @@ int nufft_type1(Nufft *nf, cudaStream_t st, const NufftGrid &g, const double L[3
                                                  nf->h3.p, dc0, dc1, dc2, outR, outI);
   NCK(cudaGetLastError());
   *launches += 5;
+  if (trace) {
+    mark();
+    cudaEventSynchronize(tev[nTev - 1]);
+    const char *names[] = {"bin+tables", "spread", "fft z,y", "all-gather", "fft x + finish"};
+    fprintf(stderr, "[nufft rank %d/%d]", shard ? shard->rank : 0, shard ? shard->world : 1);
+    for (int i = 0; i + 1 < nTev; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
+      fprintf(stderr, " %s %.3f", names[i], ms);
+    }
+    fprintf(stderr, "\n");
+    for (int i = 0; i < nTev; ++i) cudaEventDestroy(tev[i]);
+  }
   return 0;
 }
 

@@ -26,6 +26,19 @@ const char *nufft_last_error(const Nufft *);
 // widest window.  Returns 0, or -1 when the path does not apply (a mode range of zero).
 int nufft_choose(const int nmax[3], NufftGrid *g);
 
+// Multi-GPU type 1 (one engine per GPU, every rank holds all atoms): rank r spreads onto its
+// slab of x planes only (window tables only for the atoms that reach it), runs the z and y
+// passes of the pruned FFT on that slab, the ranks all-gather the pruned slabs
+// (n1 x (2 nmax_y + 1) x (nmax_z + 1) complex: 5.8 MB for the 100k-atom box instead of a
+// 16.8 MB grid), and the x pass + deconvolution run replicated, so every rank ends with the
+// complete sums.  allgather(ctx, buf, bytesPerRank, stream): in place, rank r's share at
+// buf + r * bytesPerRank.  Applies when world divides the bricks along x.
+struct NufftShard {
+  int rank, world;
+  int (*allgather)(void *ctx, void *buf, size_t bytesPerRank, cudaStream_t stream);
+  void *ctx;
+};
+
 // Type 1.  packed[i] = {x, y, z, q} of the nAtoms charged atoms, L = box axes.
 // rows[nRows] = {a, b, cmax, first}: entries first.. of the reference's k list hold
 // c = -cmax..cmax (1..cmax for a = b = 0); rows with cmax < 0 are padding.
@@ -33,7 +46,7 @@ int nufft_choose(const int nmax[3], NufftGrid *g);
 // Returns 0 on success (kernels queued on `stream`); *launches is incremented.
 int nufft_type1(Nufft *, cudaStream_t stream, const NufftGrid &g, const double L[3],
                 const double4 *packed, int nAtoms, const int4 *rows, int nRows, double *outR,
-                double *outI, long long *launches);
+                double *outI, long long *launches, const NufftShard *shard = nullptr);
 
 // Type 2.  Reciprocal force of the same atoms from the sums:
 //   F_i = sum_k 2 q_i prefact_k (sin(k.r_i) R_k - cos(k.r_i) I_k) k   (src/Ewald.cpp:1540-1552)

@@ -108,6 +108,8 @@ _SIGS = {
     "gomcb200_mark_coords_changed": (C.c_int, [_vp]),
     "gomcb200_set_recip_algo": (C.c_int, [_vp, C.c_int]),
     "gomcb200_set_pair_algo": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_comm_unique_id": (C.c_int, [_vp]),
+    "gomcb200_set_comm": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "gomcb200_set_recip_auto_work": (C.c_int, [_vp, C.c_double]),
     "gomcb200_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gomcb200_enable_timing": (C.c_int, [_vp, C.c_int]),
@@ -115,6 +117,15 @@ _SIGS = {
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
 _lib = None
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id for Engine.set_comm (create on one rank, share with all)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    if L.gomcb200_comm_unique_id(buf):
+        raise RuntimeError(L.gomcb200_last_error().decode())
+    return buf.raw
 
 
 def load_library():
@@ -532,6 +543,11 @@ class Engine:
     # ---- misc --------------------------------------------------------------
     def set_shard(self, rank, world):
         self._ck(self.L.gomcb200_set_shard(self.h, int(rank), int(world)))
+
+    def set_comm(self, unique_id, rank, world):
+        """unique_id: the 128 bytes of comm_unique_id() of rank 0 (None for world == 1)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+        self._ck(self.L.gomcb200_set_comm(self.h, buf, int(rank), int(world)))
 
     def mark_coords_changed(self):
         self._ck(self.L.gomcb200_mark_coords_changed(self.h))

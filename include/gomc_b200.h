@@ -437,6 +437,21 @@ int gomcb200_set_forces(gomcb200_engine *e, int which, const double *x, const do
  * return GOMCB200_EINVAL while world > 1.  world == 1 restores the single-GPU
  * behaviour. */
 int gomcb200_set_shard(gomcb200_engine *e, int rank, int world);
+/* The collective inside the engine.  gomcb200_comm_unique_id fills 128 bytes (an NCCL unique
+ * id; call it on one rank and hand the bytes to the others by any means -- MPI, a socket,
+ * shared memory, or plain memory between the threads of one process).  gomcb200_set_comm
+ * makes the engine rank `rank` of a `world`-rank NCCL communicator (libnccl.so.2, bound at run
+ * time) and implies gomcb200_set_shard(rank, world).  From then on box_inter,
+ * box_reciprocal_setup/_sums and call_full_box_energy all-reduce their energies on the
+ * engine's stream before the one device-to-host copy, so every rank returns the COMPLETE
+ * values, and the structure factor runs as the slab-sharded non-uniform FFT (the pruned
+ * slabs are all-gathered; every rank ends with the complete sumRnew/sumInew).  One engine
+ * per GPU, one host thread per engine: the ranks may be processes (torchrun, MPI) or the
+ * threads of ONE process -- GOMC is a single process (src/Main.cpp:318-326) and reaches all
+ * GPUs of a box this way (gomc_b200/host/multi_gpu_test.cpp).  world == 1 drops the
+ * communicator. */
+int gomcb200_comm_unique_id(void *id128);
+int gomcb200_set_comm(gomcb200_engine *e, const void *id128, int rank, int world);
 /* Tell the engine that resident coordinates are to be treated as changed
  * (forces cell re-binning and re-packing on the next sweep), as after a
  * device-side MultiParticle transform. */
