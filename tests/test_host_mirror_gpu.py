@@ -136,3 +136,47 @@ def test_host_mirror_move_sequence(tmp_path, name):
     assert abs(g["inter_after_reject"] - r["recomputed"]["inter"]) <= 1e-12 * abs(g["inter"])
     lj2, re2 = o.box_inter(x, y, z, s.kind, s.mol, s.charge, box_atoms(s))
     assert abs(r["recomputed"]["inter"] - lj2) <= TOL * abs(lj2)
+
+
+MGPU = os.path.join(ROOT, "gomc_b200", "host", "multi_gpu_test")
+
+
+def _n_gpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        return sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+    except OSError:
+        return 0
+
+
+@pytest.mark.parametrize("name,world", [("spce", 2), ("spce", 4), ("argon", 2)])
+def test_one_process_many_gpus(tmp_path, name, world):
+    """ONE C++ process, one engine + host thread per GPU, gomcb200_set_comm: the collective
+    lives inside the engine (NCCL on the engine streams), so a single-process host such as
+    GOMC reaches every GPU through include/gomc_b200.h.  Every rank must return the complete
+    energies, equal to the single-GPU ones (1e-12: the partial sums associate differently)
+    and to the oracle (TOL).  Needs `world` GPUs on the box (gpurun --gpus N)."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    assert os.path.exists(MGPU), "run __graft_entry__.build()"
+    # 4 096 molecules -> 128-point fine grid: 8 bricks along x, divisible by 2 and 4 ranks
+    s = synth.make_spce(4096, r_cut=9.0) if name == "spce" else synth.make_argon(4000)
+    p = tmp_path / "sys.bin"
+    _write(p, s, [])
+    r = subprocess.run([MGPU, str(p), str(world)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    o = oracle_for(s)
+    olj, ore = o.box_inter(s.x, s.y, s.z, s.kind, s.mol, s.charge, box_atoms(s))
+    orc = 0.0
+    if s.ff.ewald:
+        kx, ky, kz, hs, pf, _ = o.recip_init_orth()
+        sR, sI = o.box_recip_sums(box_mols(s), s.mol_start, s.x, s.y, s.z, s.charge, kx, ky, kz)
+        orc = o.box_reciprocal(sR, sI, pf)
+    ref = (olj, ore, orc)
+    for c in range(3):
+        assert abs(res["single"][c] - ref[c]) <= TOL * max(abs(ref[c]), 1e-300)
+    for rank in res["ranks"]:
+        for c in range(3):
+            assert abs(rank[c] - res["single"][c]) <= 1e-12 * max(abs(res["single"][c]), 1.0)
+            assert abs(rank[c] - ref[c]) <= TOL * max(abs(ref[c]), 1e-300)
