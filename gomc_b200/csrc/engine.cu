@@ -2445,6 +2445,66 @@ int gomcb200_particle_inter(gomcb200_engine *e, int box, int molIndex, int partI
   return 0;
 }
 
+int gomcb200_particle_nonbonded(gomcb200_engine *e, int box, int kindI, double chargeI,
+                                int nPartners, const int *partnerKind,
+                                const double *partnerCharge, const double *px, const double *py,
+                                const double *pz, int trials, const double *tx, const double *ty,
+                                const double *tz, double *inter) {
+  int rc = check_box(e, box, true, false);
+  if (rc) return rc;
+  if (kindI < 0 || kindI >= e->kindCount || nPartners < 0 || trials < 0 || !inter ||
+      (nPartners && (!partnerKind || !partnerCharge || !px || !py || !pz)) ||
+      (trials && (!tx || !ty || !tz)))
+    return fail(GOMCB200_EINVAL, "bad arguments");
+  if (trials == 0 || nPartners == 0) return 0;
+  for (int k = 0; k < nPartners; ++k)
+    if (partnerKind[k] < 0 || partnerKind[k] >= e->kindCount)
+      return fail(GOMCB200_EINVAL, "partner kind out of range");
+  CK(cudaSetDevice(e->device));
+  const size_t nd = 4 * (size_t)nPartners + 3 * (size_t)trials;
+  const size_t bytes = nd * sizeof(double) + (size_t)nPartners * sizeof(int);
+  rc = stage_reserve(e, bytes + 64);
+  if (rc) return rc;
+  double *h = reinterpret_cast<double *>(e->hStage);
+  std::memcpy(h, px, sizeof(double) * nPartners);
+  std::memcpy(h + nPartners, py, sizeof(double) * nPartners);
+  std::memcpy(h + 2 * (size_t)nPartners, pz, sizeof(double) * nPartners);
+  std::memcpy(h + 3 * (size_t)nPartners, partnerCharge, sizeof(double) * nPartners);
+  double *ht = h + 4 * (size_t)nPartners;
+  std::memcpy(ht, tx, sizeof(double) * trials);
+  std::memcpy(ht + trials, ty, sizeof(double) * trials);
+  std::memcpy(ht + 2 * (size_t)trials, tz, sizeof(double) * trials);
+  std::memcpy(h + nd, partnerKind, sizeof(int) * nPartners);
+  CK(e->molBuf.reserve(nd + (size_t)nPartners + 8));
+  CK(e->probeOut.reserve((size_t)trials + 8));
+  CK(cudaMemcpyAsync(e->molBuf.p, h, bytes, cudaMemcpyHostToDevice, e->stream));
+  const BoxParams p = make_params(e, box);
+  const int *dk = reinterpret_cast<const int *>(e->molBuf.p + nd);
+  const int blocks = (trials + 63) / 64;
+#define PNB(V)                                                                              \
+  k_particle_nonbonded<V><<<blocks, 64, 0, e->stream>>>(p, kindI, chargeI, nPartners, dk, \
+                                                        e->molBuf.p, trials, e->probeOut.p)
+  if (e->vdwKind == VDW_SHIFT)
+    PNB(VDW_SHIFT);
+  else if (e->vdwKind == VDW_SWITCH)
+    PNB(VDW_SWITCH);
+  else if (e->vdwKind == VDW_EXP6)
+    PNB(VDW_EXP6);
+  else if (e->vdwKind == VDW_MARTINI)
+    PNB(VDW_MARTINI);
+  else
+    PNB(VDW_STD);
+#undef PNB
+  e->launches += 1;
+  CK(cudaGetLastError());
+  std::vector<double> out(trials);
+  CK(cudaMemcpyAsync(out.data(), e->probeOut.p, sizeof(double) * trials, cudaMemcpyDeviceToHost,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (int t = 0; t < trials; ++t) inter[t] += out[t];
+  return 0;
+}
+
 int gomcb200_calculate_torque(gomcb200_engine *e, int box) {
   int rc = check_box(e, box);
   if (rc) return rc;

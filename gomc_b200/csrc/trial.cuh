@@ -224,4 +224,32 @@ __global__ void k_accept_mol(const __grid_constant__ AcceptArgs a, double *x, do
   }
 }
 
+// CalculateEnergy::ParticleNonbonded, src/CalculateEnergy.cpp:689-725: one thread per trial
+// position, partners in the caller's (sortedNB) order.  buf = {px, py, pz, q}[nPartners] then
+// {tx, ty, tz}[trials]; kinds in pk.  out[t] = the increment of inter[t].
+template <int VDW>
+__global__ void k_particle_nonbonded(BoxParams p, int kindI, double qI, int nPartners,
+                                     const int *__restrict__ pk,
+                                     const double *__restrict__ buf, int trials,
+                                     double *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= trials) return;
+  const double *tr = buf + 4 * (size_t)nPartners;
+  const double tx = tr[t], ty = tr[trials + t], tz = tr[2 * trials + t];
+  double en = 0.0;
+  for (int k = 0; k < nPartners; ++k) {
+    double dx = tx - buf[k], dy = ty - buf[nPartners + k], dz = tz - buf[2 * nPartners + k];
+    min_image_vec(p, dx, dy, dz);
+    const double r2 = dist_sq(dx, dy, dz);
+    if (!(p.boxRcutSq > r2)) continue;  // BoxDimensions::InRcut, strict
+    en += calc_en<VDW>(p, r2, kindI + pk[k] * p.kindCount);
+    if (p.electrostatic) {
+      const double qq = qI * buf[3 * nPartners + k] * kQQFact;
+      // FFParticle::CalcCoulombAdd_1_4, NB = true (src/FFParticle.cpp:281-292)
+      if (qq != 0.0 && !(p.rCutSq < r2)) en += qq / sqrt(r2);
+    }
+  }
+  out[t] = en;
+}
+
 }  // namespace gb

@@ -108,6 +108,8 @@ _SIGS = {
     "gomcb200_mark_coords_changed": (C.c_int, [_vp]),
     "gomcb200_set_recip_algo": (C.c_int, [_vp, C.c_int]),
     "gomcb200_set_pair_algo": (C.c_int, [_vp, C.c_int]),
+    "gomcb200_particle_nonbonded": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_int, _ip,
+                                              _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp]),
     "gomcb200_comm_unique_id": (C.c_int, [_vp]),
     "gomcb200_set_comm": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "gomcb200_set_recip_auto_work": (C.c_int, [_vp, C.c_double]),
@@ -390,6 +392,17 @@ class Engine:
 
     def calculate_torque(self, box=0):
         self._ck(self.L.gomcb200_calculate_torque(self.h, box))
+
+    def particle_nonbonded(self, box, kind_i, q_i, partner_kind, partner_charge, px, py, pz,
+                           tx, ty, tz):
+        pk = np.ascontiguousarray(partner_kind, dtype=np.int32)
+        (pq, ppq), (px, ppx), (py, ppy), (pz, ppz) = _d(partner_charge), _d(px), _d(py), _d(pz)
+        (tx, ptx), (ty, pty), (tz, ptz) = _d(tx), _d(ty), _d(tz)
+        inter = np.zeros(len(tx))
+        self._ck(self.L.gomcb200_particle_nonbonded(
+            self.h, box, int(kind_i), float(q_i), len(pk), pk.ctypes.data_as(_ip), ppq, ppx, ppy,
+            ppz, len(tx), ptx, pty, ptz, inter.ctypes.data_as(_dp)))
+        return inter
 
     def get_forces(self, which, first=0, count=None):
         limit = self.n_atoms if which in (ATOM_FORCE, ATOM_FORCE_REC) else self.n_mols

@@ -197,6 +197,20 @@ public:
           "ParticleInter");
     for (int t = 0; t < trials; ++t) overlap[t] |= (ov[t] != 0);
   }
+  // src/CalculateEnergy.cpp:689-725.  The reference walks kind.sortedNB(partIndex) and tests
+  // trialMol.AtomExists(partner); here the caller hands in that filtered partner list (kinds,
+  // charges and trialMol.GetCoords() of the partners) in the same order.
+  void ParticleNonbonded(double *inter, int kindOfPart, double chargeOfPart,
+                         const std::vector<int> &partnerKind,
+                         const std::vector<double> &partnerCharge, const XYZView &partnerCoords,
+                         const XYZView &trialPos, int box, int trials) const {
+    check(gomcb200_particle_nonbonded(eng_.get(), box, kindOfPart, chargeOfPart,
+                                      (int)partnerKind.size(), partnerKind.data(),
+                                      partnerCharge.data(), partnerCoords.x, partnerCoords.y,
+                                      partnerCoords.z, trials, trialPos.x, trialPos.y, trialPos.z,
+                                      inter),
+          "ParticleNonbonded");
+  }
   // src/CalculateEnergy.cpp:1365-1406 (uses the resident force buffers and COM)
   void CalculateTorque(double *tx, double *ty, double *tz, int first, int count, int box) {
     check(gomcb200_calculate_torque(eng_.get(), box), "CalculateTorque");

@@ -32,6 +32,7 @@ class MolKind:
     masses: list
     bonds: list = field(default_factory=list)    # (i, j) local indices
     angles: list = field(default_factory=list)   # (i, j, k)
+    dihedrals: list = field(default_factory=list)  # (i, j, k, l)
     local_xyz: np.ndarray | None = None           # rigid template, (natoms, 3)
 
 
@@ -54,6 +55,8 @@ class ForceField:
     dielectric: float = 15.0       # Martini only (src/ConfigSetup.cpp:1684-1686 default)
     bond_params: list = field(default_factory=list)   # (t1, t2, b0)
     angle_params: list = field(default_factory=list)  # (t1, t2, t3, theta0)
+    angle_k: float = 999999999999.0                   # rigid unless a flexible kind sets it
+    dihedral_params: list = field(default_factory=list)  # (t1, t2, t3, t4, Kchi, n, delta)
 
     # ---- derived exactly as the reference derives them -------------------
     @property
@@ -344,6 +347,36 @@ def make_mixture(n_a=150, n_b=100, seed=5, L=26.0, r_cut=8.0, vdw_kind=VDW_STD,
                      jitter=0.2)
 
 
+def make_pentane(n_mols=150, L=34.0, seed=31, r_cut=10.0, charged=False, ewald=True):
+    """Config 3's molecule: TraPPE-UA n-pentane (CH3 eps/k 98 K sigma 3.75 A, CH2 46 K
+    3.95 A, bond 1.54 A, angle 114 deg; parameters as in the reference's
+    test/input/Systems/PEN_HEX/Base force-field file), five united atoms, flexible
+    angles and dihedrals -- the multi-site chain CBMC grows, with one intramolecular
+    non-bonded pair (sites 0 and 4, four bonds apart) under Exclude 1-4.  `charged` puts
+    partial charges on the sites (net zero) so that the Ewald deltas are not the degenerate
+    zero of the all-neutral alkane."""
+    q = [0.25, -0.15, -0.2, -0.15, 0.25] if charged else [0.0] * 5
+    ff = ForceField(["CH3", "CH2"], np.array([98.0, 46.0]), np.array([3.75, 3.95]),
+                    np.array([12.0, 12.0]), r_cut=r_cut, r_cut_coulomb=r_cut, tolerance=1e-5,
+                    ewald=ewald, electrostatic=True,
+                    bond_params=[("CH3", "CH2", 1.54), ("CH2", "CH2", 1.54)],
+                    angle_params=[("CH3", "CH2", "CH2", 114.0), ("CH2", "CH2", "CH2", 114.0)],
+                    angle_k=31250.0,
+                    dihedral_params=[("CH3", "CH2", "CH2", "CH2", kc, n_, dl) for kc, n_, dl in
+                                     ((2156.3, 0, 90.0), (-355.03, 1, 180.0), (68.19, 2, 0.0),
+                                      (-791.32, 3, 180.0))])
+    # all-trans zig-zag in the xy plane
+    th = math.radians(114.0)
+    dx, dy = 1.54 * math.sin(th / 2), 1.54 * math.cos(th / 2)
+    tmpl = np.array([[i * dx, (i % 2) * dy, 0.0] for i in range(5)])
+    mk = MolKind("PEN", ["C1", "C2", "C3", "C4", "C5"], ["CH3", "CH2", "CH2", "CH2", "CH3"], q,
+                 [15.035, 14.027, 14.027, 14.027, 15.035],
+                 bonds=[(0, 1), (1, 2), (2, 3), (3, 4)], angles=[(0, 1, 2), (1, 2, 3), (2, 3, 4)],
+                 dihedrals=[(0, 1, 2, 3), (1, 2, 3, 4)], local_xyz=tmpl)
+    return _assemble(f"pentane{n_mols}{'q' if charged else ''}", ff, [mk], [n_mols], L, seed,
+                     jitter=0.2)
+
+
 # --------------------------------------------------------------------------
 # GOMC input writers (consumed by oracle/_ref/gomc_probe_*)
 
@@ -359,14 +392,17 @@ def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
             f.write(f"{t1}\t{t2}\t999999999999\t{b0}\n")
         f.write("\nANGLES\n")
         for t1, t2, t3, th in ff.angle_params:
-            f.write(f"{t1}\t{t2}\t{t3}\t999999999999\t{th}\n")
+            f.write(f"{t1}\t{t2}\t{t3}\t{ff.angle_k!r}\t{th}\n")
         if ff.is_martini:   # CHARMM units: -eps in kcal/mol, Rmin/2 (src/FFSetup.cpp:265-279)
             f.write("\nDIHEDRALS\n\nNONBONDED\n")
             for t, e, s, n in zip(ff.type_names, ff.epsilon, ff.sigma, ff.n):
                 f.write(f"{t}\t0.0\t{-float(e) / KCAL_PER_MOL_TO_K!r}\t"
                         f"{float(s) / RIJ_OVER_2_TO_SIG!r}\n")
         else:
-            f.write("\nDIHEDRALS\n\nNONBONDED_MIE\n")
+            f.write("\nDIHEDRALS\n")
+            for t1, t2, t3, t4, kc, nn_, dl in ff.dihedral_params:
+                f.write(f"{t1}\t{t2}\t{t3}\t{t4}\t{kc!r}\t{int(nn_)}\t{dl!r}\n")
+            f.write("\nNONBONDED_MIE\n")
             for t, e, s, n in zip(ff.type_names, ff.epsilon, ff.sigma, ff.n):
                 f.write(f"{t}\t{float(e)!r}\t{float(s)!r}\t{float(n)!r}\n")
         f.write("\nEND\n")
@@ -384,12 +420,13 @@ def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
                 (a + 1) % 100000, mk.atom_names[la], mk.name, "A",
                 (m + 1) % 10000, sys.x[a], sys.y[a], sys.z[a], 1.0, 0.0))
         f.write("END\n")
-    bonds, angles = [], []
+    bonds, angles, dihedrals = [], [], []
     for m in range(sys.n_mols):
         mk = sys.mol_kinds[int(sys.mol_kind[m])]
         s = int(sys.mol_start[m]) + 1
         bonds.extend((s + i, s + j) for i, j in mk.bonds)
         angles.extend((s + i, s + j, s + k) for i, j, k in mk.angles)
+        dihedrals.extend((s + i, s + j, s + k, s + l) for i, j, k, l in mk.dihedrals)
     with open(os.path.join(out_dir, "box0.psf"), "w") as f:
         f.write("PSF\n\n       1 !NTITLE\n REMARKS synthetic system written by gomc_b200.synth\n\n")
         f.write("%8d !NATOM\n" % n)
@@ -406,7 +443,10 @@ def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
         f.write("\n%8d !NTHETA: angles\n" % len(angles))
         for i in range(0, len(angles), 3):
             f.write("".join("%8d%8d%8d" % t for t in angles[i:i + 3]) + "\n")
-        f.write("\n%8d !NPHI: dihedrals\n\n\n%8d !NIMPHI: impropers\n\n\n" % (0, 0))
+        f.write("\n%8d !NPHI: dihedrals\n" % len(dihedrals))
+        for i in range(0, len(dihedrals), 2):
+            f.write("".join("%8d%8d%8d%8d" % t for t in dihedrals[i:i + 2]) + "\n")
+        f.write("\n\n%8d !NIMPHI: impropers\n\n\n" % 0)
         f.write("%8d !NDON: donors\n\n\n%8d !NACC: acceptors\n\n\n" % (0, 0))
     # ---- in.conf ---------------------------------------------------------
     L = sys.axis

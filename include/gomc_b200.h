@@ -194,6 +194,18 @@ int gomcb200_particle_inter(gomcb200_engine *e, int box, int molIndex,
                             int partIndex, int trials, const double *tx,
                             const double *ty, const double *tz, double *en,
                             double *real, int *overlap);
+/* CalculateEnergy::ParticleNonbonded, src/CalculateEnergy.cpp:689-725 (called next to
+ * ParticleInter by every CBMC growth step, e.g. src/cbmc/DCSingle.cpp:48,86): the 1-N
+ * intramolecular non-bonded energy (FFParticle::CalcEn + CalcCoulombAdd_1_4 with NB = true)
+ * of `trials` trial positions of one site of kind kindI / charge chargeI against the partner
+ * sites that already exist in the trial molecule -- the caller walks kind.sortedNB(partIndex)
+ * and keeps the entries with TrialMol::AtomExists, in that order.  inter[] is incremented. */
+int gomcb200_particle_nonbonded(gomcb200_engine *e, int box, int kindI, double chargeI,
+                                int nPartners, const int *partnerKind,
+                                const double *partnerCharge, const double *px,
+                                const double *py, const double *pz, int trials,
+                                const double *tx, const double *ty, const double *tz,
+                                double *inter);
 /* CalculateEnergy::CalculateTorque, src/CalculateEnergy.cpp:1365-1406, from
  * the resident ATOM_FORCE + ATOM_FORCE_REC buffers and COM. */
 int gomcb200_calculate_torque(gomcb200_engine *e, int box);

@@ -1203,6 +1203,32 @@ int orc_particle_inter(const orc_params *p, int nAtomsTotal, const double *x,
   return 0;
 }
 
+/* CalculateEnergy::ParticleNonbonded, src/CalculateEnergy.cpp:689-725: the partners are the
+ * entries of kind.sortedNB(partIndex) whose site already exists in the trial molecule, in
+ * that order (the caller filters); Coulomb part = FFParticle::CalcCoulombAdd_1_4 with
+ * NB = true (src/FFParticle.cpp:281-292; the same text in every FF class). */
+int orc_particle_nonbonded(const orc_params *p, int kindI, double qI, int nPartners,
+                           const int *partnerKind, const double *partnerCharge,
+                           const double *px, const double *py, const double *pz, int trials,
+                           const double *tx, const double *ty, const double *tz,
+                           double *inter) {
+  double boxRcutSq = box_rcut(p) * box_rcut(p);
+  double rCutSq = p->rCut * p->rCut;
+  for (int k = 0; k < nPartners; ++k) {
+    for (int t = 0; t < trials; ++t) {
+      double distSq, d[3];
+      if (in_rcut(p, boxRcutSq, tx[t], ty[t], tz[t], px[k], py[k], pz[k], &distSq, d)) {
+        inter[t] += orc_calc_en(p, distSq, kindI, partnerKind[k]);
+        if (p->electrostatic) {
+          double qi_qj_fact = qI * partnerCharge[k] * ORC_QQFACT;
+          if (qi_qj_fact != 0.0 && !(rCutSq < distSq)) inter[t] += qi_qj_fact / sqrt(distSq);
+        }
+      }
+    }
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------------ */
 /* Torque                                                                    */
 

@@ -123,6 +123,14 @@ int orc_particle_inter(const orc_params *p, int nAtomsTotal, const double *x,
                        const double *ty, const double *tz, double *en,
                        double *real, int *overlap);
 
+/* CalculateEnergy::ParticleNonbonded, src/CalculateEnergy.cpp:689-725 (1-N intramolecular
+ * non-bonded energy of CBMC trial positions against the already-built partner sites). */
+int orc_particle_nonbonded(const orc_params *p, int kindI, double qI, int nPartners,
+                           const int *partnerKind, const double *partnerCharge,
+                           const double *px, const double *py, const double *pz, int trials,
+                           const double *tx, const double *ty, const double *tz,
+                           double *inter);
+
 /* CalculateEnergy::CalculateTorque, src/CalculateEnergy.cpp:1365-1406. */
 int orc_calculate_torque(const orc_params *p, int nBoxMols, const int *boxMols,
                          const int *molStart, const double *x, const double *y,

@@ -42,6 +42,12 @@ CASES = {
         216, r_cut=6.0, cell_vectors=synth.triclinic_cell(20.494)), 6, 7),
     "mixture_martini_ewald": (lambda: synth.make_mixture(vdw_kind=synth.VDW_SWITCH, r_switch=6.0,
                                                          martini=True, ewald=True, seed=4, n_b_exp=12.0), 4, 5),
+    # BASELINE configs[2]'s molecule: TraPPE-UA n-pentane (five united atoms, flexible), the
+    # all-neutral alkane (reciprocal deltas = the degenerate zero) and a variant with partial
+    # charges; the probe also grows the last site CBMC-style (ParticleInter +
+    # ParticleNonbonded on the same trial positions)
+    "pentane150": (lambda: synth.make_pentane(150), 6, 5),
+    "pentane150q": (lambda: synth.make_pentane(150, charged=True), 6, 5),
     # one fractional molecule (free-energy / NeMTMC state): soft-core LJ, with and without
     # soft-core Coulomb.  Extra probe arguments:
     #   pick, lambdaVDW, lambdaCoulomb, sc_alpha, sc_sigma, sc_power, sc_coul

@@ -329,6 +329,17 @@ class Oracle:
                                   ov.ctypes.data_as(_ip))
         return en, re, ov.astype(bool)
 
+    def particle_nonbonded(self, kind_i, q_i, partner_kind, partner_charge, px, py, pz,
+                           tx, ty, tz):
+        (pk, ppk), (pq, ppq) = _i(partner_kind), _d(partner_charge)
+        (px, ppx), (py, ppy), (pz, ppz) = _d(px), _d(py), _d(pz)
+        (tx, ptx), (ty, pty), (tz, ptz) = _d(tx), _d(ty), _d(tz)
+        inter = np.zeros(len(tx))
+        self.L.orc_particle_nonbonded(self.pp, int(kind_i), C.c_double(q_i), len(pk), ppk, ppq,
+                                      ppx, ppy, ppz, len(tx), ptx, pty, ptz,
+                                      inter.ctypes.data_as(_dp))
+        return inter
+
     def calculate_torque(self, box_mols, mol_start, x, y, z, com, aF, rF, n_mols):
         (bm, pbm), (ms, pms) = _i(box_mols), _i(mol_start)
         arrs = [_d(a) for a in (x, y, z, *com, *aF, *rF)]

@@ -452,6 +452,48 @@ int run_golden(int argc, char **argv) {
       out.f64(bname("ParticleInter.en", b), en);
       out.f64(bname("ParticleInter.real", b), re);
       out.i32(bname("ParticleInter.overlap", b), ovi);
+      // ---- CBMC growth of the LAST site of a chain molecule (DCSingle / DCLinkNoDih call
+      // ParticleInter and ParticleNonbonded back to back on the same trial positions):
+      // sites 0 .. len-2 of molecule m exist, the last one is tried at `trials2` positions
+      // one bond length from its neighbour
+      if (len >= 5) {
+        const uint part = len - 1, trials2 = 10;
+        cbmc::TrialMol grow(mols.GetKind(m), sys.boxDimRef, b);
+        for (uint a = 0; a + 1 < len; ++a) grow.AddAtom(a, sys.coordinates.Get(start + a));
+        XYZArray tp2(trials2);
+        XYZ anchor = sys.coordinates.Get(start + len - 2);
+        for (uint t = 0; t < trials2; ++t) {
+          XYZ d(U(rng), U(rng), U(rng));
+          d *= 1.54 / d.Length();
+          if (t == 0)   // fold the chain back: close to site 0, inside its cut-off for sure
+            d = (sys.boxDimRef.MinImage(sys.coordinates.Get(start) - anchor, b)) * 0.45;
+          tp2.Set(t, sys.boxDimRef.WrapPBC(anchor + d, b));
+        }
+        std::vector<double> nb(trials2, 0.0), en2(trials2, 0.0), re2(trials2, 0.0);
+        bool *ov2 = new bool[trials2];
+        for (uint t = 0; t < trials2; ++t) ov2[t] = false;
+        ce.ParticleNonbonded(nb.data(), grow, tp2, part, b, trials2);
+        sys.cellList.RemoveMol(m, b, sys.coordinates);
+        ce.ParticleInter(en2.data(), re2.data(), tp2, ov2, part, m, b, trials2);
+        sys.cellList.AddMol(m, b, sys.coordinates);
+        std::vector<int> ovi2(trials2);
+        for (uint t = 0; t < trials2; ++t) ovi2[t] = ov2[t];
+        delete[] ov2;
+        {  // the partner list ParticleNonbonded walks: sortedNB(part) filtered by AtomExists
+          std::vector<int> partners;
+          const MoleculeKind &mkd = mols.GetKind(m);
+          for (const uint *pp = mkd.sortedNB.Begin(part); pp != mkd.sortedNB.End(part); ++pp)
+            if (grow.AtomExists(*pp)) partners.push_back((int)*pp);
+          out.i32(bname("grow.partners", b), partners);
+        }
+        out.i32(bname("grow.mol", b), (int)m);
+        out.i32(bname("grow.part", b), (int)part);
+        out.xyz(bname("grow.trialPos", b), tp2);
+        out.f64(bname("grow.ParticleNonbonded", b), nb);
+        out.f64(bname("grow.ParticleInter.en", b), en2);
+        out.f64(bname("grow.ParticleInter.real", b), re2);
+        out.i32(bname("grow.ParticleInter.overlap", b), ovi2);
+      }
     }
 
     // ---- MultiParticle move: trial transform, CalcEn, acceptance weight ----

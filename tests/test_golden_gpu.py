@@ -319,3 +319,28 @@ def test_reciprocal_force_and_torque(gold):
         assert rel_err(gR[i], d[f"box0.BoxForceReciprocal.atomForceRec.{c}"]) <= TOL
         assert rel_err(gM[i], d[f"box0.BoxForceReciprocal.molForceRec.{c}"]) <= TOL
         assert rel_err(gT[i], d[f"box0.CalculateTorque.molTorque.{c}"]) <= TOL
+
+
+def test_cbmc_growth_step(gold):
+    """CBMC growth of the last site of a chain molecule (pentane fixtures): ParticleInter on a
+    batch of trial positions of site `part` and ParticleNonbonded against the sites that are
+    already built (src/CalculateEnergy.cpp:689-785), against the reference's dumps."""
+    d, e = gold
+    if "box0.grow.part" not in d:
+        pytest.skip("no chain molecule")
+    ms = d["molStart"]
+    kind, q = d["particleKind"], d["particleCharge"]
+    x, y, z = _xyz(d, "coords")
+    m, part = int(d["box0.grow.mol"][0]), int(d["box0.grow.part"][0])
+    partners = d["box0.grow.partners"].astype(int) + int(ms[m])
+    a = int(ms[m]) + part
+    tp = _xyz(d, "box0.grow.trialPos")
+    nb = e.particle_nonbonded(0, kind[a], q[a], kind[partners], q[partners], x[partners],
+                              y[partners], z[partners], *tp)
+    assert rel_err(nb, d["box0.grow.ParticleNonbonded"]) <= TOL
+    # the call increments: a second call on the same buffer doubles it
+    en, re, ov = e.particle_inter(0, m, part, *tp)
+    assert np.array_equal(ov.astype(np.int32), d["box0.grow.ParticleInter.overlap"])
+    assert rel_err(en, d["box0.grow.ParticleInter.en"]) <= TOL
+    if np.any(d["box0.grow.ParticleInter.real"] != 0):
+        assert rel_err(re, d["box0.grow.ParticleInter.real"]) <= TOL
