@@ -381,7 +381,11 @@ def make_pentane(n_mols=150, L=34.0, seed=31, r_cut=10.0, charged=False, ewald=T
 # GOMC input writers (consumed by oracle/_ref/gomc_probe_*)
 
 def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
-                      cached_fourier=False, run_steps=0, pressure_calc=False, npt=False):
+                      cached_fourier=False, run_steps=0, pressure_calc=False, npt=False,
+                      second: System | None = None, gemc_freqs=None):
+    """second: the system of box 1 (GEMC two-box input; same force field and molecule kinds);
+    gemc_freqs: {"DisFreq": ..., "RotFreq": ..., "SwapFreq": ..., "RegrowthFreq": ...,
+    "VolFreq": ...} for that case."""
     os.makedirs(out_dir, exist_ok=True)
     ff = sys.ff
     # ---- parameter file (Mie / "EXOTIC" style, epsilon in K) --------------
@@ -406,51 +410,68 @@ def write_gomc_inputs(sys: System, out_dir: str, multiparticle=True,
             for t, e, s, n in zip(ff.type_names, ff.epsilon, ff.sigma, ff.n):
                 f.write(f"{t}\t{float(e)!r}\t{float(s)!r}\t{float(n)!r}\n")
         f.write("\nEND\n")
-    # ---- PDB + PSF -------------------------------------------------------
-    n = sys.n_atoms
-    with open(os.path.join(out_dir, "box0.pdb"), "w") as f:
-        if sys.cell_vectors is None:   # (triclinic cells come from in.conf only)
-            f.write("CRYST1%9.3f%9.3f%9.3f  90.00  90.00  90.00 P 1           1\n"
-                    % tuple(sys.axis))
-        for a in range(n):
-            m = int(sys.mol[a])
-            mk = sys.mol_kinds[int(sys.mol_kind[m])]
-            la = a - int(sys.mol_start[m])
-            f.write("ATOM  %5d %-4s %-4s%1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n" % (
-                (a + 1) % 100000, mk.atom_names[la], mk.name, "A",
-                (m + 1) % 10000, sys.x[a], sys.y[a], sys.z[a], 1.0, 0.0))
-        f.write("END\n")
-    bonds, angles, dihedrals = [], [], []
-    for m in range(sys.n_mols):
-        mk = sys.mol_kinds[int(sys.mol_kind[m])]
-        s = int(sys.mol_start[m]) + 1
-        bonds.extend((s + i, s + j) for i, j in mk.bonds)
-        angles.extend((s + i, s + j, s + k) for i, j, k in mk.angles)
-        dihedrals.extend((s + i, s + j, s + k, s + l) for i, j, k, l in mk.dihedrals)
-    with open(os.path.join(out_dir, "box0.psf"), "w") as f:
-        f.write("PSF\n\n       1 !NTITLE\n REMARKS synthetic system written by gomc_b200.synth\n\n")
-        f.write("%8d !NATOM\n" % n)
-        for a in range(n):
-            m = int(sys.mol[a])
-            mk = sys.mol_kinds[int(sys.mol_kind[m])]
-            la = a - int(sys.mol_start[m])
-            f.write("%8d %-4s %-4d %-4s %-4s %-4s %10.6f %13.4f %11d\n" % (
-                a + 1, "S", m + 1, mk.name, mk.atom_names[la], mk.atom_types[la],
-                mk.charges[la], mk.masses[la], 0))
-        f.write("\n%8d !NBOND: bonds\n" % len(bonds))
-        for i in range(0, len(bonds), 4):
-            f.write("".join("%8d%8d" % b for b in bonds[i:i + 4]) + "\n")
-        f.write("\n%8d !NTHETA: angles\n" % len(angles))
-        for i in range(0, len(angles), 3):
-            f.write("".join("%8d%8d%8d" % t for t in angles[i:i + 3]) + "\n")
-        f.write("\n%8d !NPHI: dihedrals\n" % len(dihedrals))
-        for i in range(0, len(dihedrals), 2):
-            f.write("".join("%8d%8d%8d%8d" % t for t in dihedrals[i:i + 2]) + "\n")
-        f.write("\n\n%8d !NIMPHI: impropers\n\n\n" % 0)
-        f.write("%8d !NDON: donors\n\n\n%8d !NACC: acceptors\n\n\n" % (0, 0))
+    # ---- PDB + PSF (one pair per box) --------------------------------------
+    for bi, bs in enumerate([sys] + ([second] if second is not None else [])):
+        n = bs.n_atoms
+        with open(os.path.join(out_dir, f"box{bi}.pdb"), "w") as f:
+            if bs.cell_vectors is None:   # (triclinic cells come from in.conf only)
+                f.write("CRYST1%9.3f%9.3f%9.3f  90.00  90.00  90.00 P 1           1\n"
+                        % tuple(bs.axis))
+            for a in range(n):
+                m = int(bs.mol[a])
+                mk = bs.mol_kinds[int(bs.mol_kind[m])]
+                la = a - int(bs.mol_start[m])
+                f.write("ATOM  %5d %-4s %-4s%1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f\n" % (
+                    (a + 1) % 100000, mk.atom_names[la], mk.name, "A",
+                    (m + 1) % 10000, bs.x[a], bs.y[a], bs.z[a], 1.0, 0.0))
+            f.write("END\n")
+        bonds, angles, dihedrals = [], [], []
+        for m in range(bs.n_mols):
+            mk = bs.mol_kinds[int(bs.mol_kind[m])]
+            s = int(bs.mol_start[m]) + 1
+            bonds.extend((s + i, s + j) for i, j in mk.bonds)
+            angles.extend((s + i, s + j, s + k) for i, j, k in mk.angles)
+            dihedrals.extend((s + i, s + j, s + k, s + l) for i, j, k, l in mk.dihedrals)
+        with open(os.path.join(out_dir, f"box{bi}.psf"), "w") as f:
+            f.write("PSF\n\n       1 !NTITLE\n REMARKS synthetic system written by gomc_b200.synth\n\n")
+            f.write("%8d !NATOM\n" % n)
+            for a in range(n):
+                m = int(bs.mol[a])
+                mk = bs.mol_kinds[int(bs.mol_kind[m])]
+                la = a - int(bs.mol_start[m])
+                f.write("%8d %-4s %-4d %-4s %-4s %-4s %10.6f %13.4f %11d\n" % (
+                    a + 1, "S", m + 1, mk.name, mk.atom_names[la], mk.atom_types[la],
+                    mk.charges[la], mk.masses[la], 0))
+            f.write("\n%8d !NBOND: bonds\n" % len(bonds))
+            for i in range(0, len(bonds), 4):
+                f.write("".join("%8d%8d" % b for b in bonds[i:i + 4]) + "\n")
+            f.write("\n%8d !NTHETA: angles\n" % len(angles))
+            for i in range(0, len(angles), 3):
+                f.write("".join("%8d%8d%8d" % t for t in angles[i:i + 3]) + "\n")
+            f.write("\n%8d !NPHI: dihedrals\n" % len(dihedrals))
+            for i in range(0, len(dihedrals), 2):
+                f.write("".join("%8d%8d%8d%8d" % t for t in dihedrals[i:i + 2]) + "\n")
+            f.write("\n\n%8d !NIMPHI: impropers\n\n\n" % 0)
+            f.write("%8d !NDON: donors\n\n\n%8d !NACC: acceptors\n\n\n" % (0, 0))
+
     # ---- in.conf ---------------------------------------------------------
     L = sys.axis
     CV = sys.cell_vectors if sys.cell_vectors is not None else np.diag(L)
+    multi_site = any(len(k.atom_names) > 1 for k in sys.mol_kinds)
+    if second is not None:
+        fr = gemc_freqs or {"DisFreq": 0.5, "RotFreq": 0.2, "RegrowthFreq": 0.1, "SwapFreq": 0.2}
+        move_lines = "\n".join(f"{k} {v}" for k, v in fr.items())
+        L1 = second.axis
+        box1_cell = (f"CellBasisVector1 1 {float(L1[0])!r} 0.0 0.0\n"
+                     f"CellBasisVector2 1 0.0 {float(L1[1])!r} 0.0\n"
+                     f"CellBasisVector3 1 0.0 0.0 {float(L1[2])!r}")
+    else:
+        box1_cell = ""
+        dis = (0.40 if multiparticle else 0.60) - (0.02 if npt else 0.0)
+        rot = 0.40 if multiparticle and multi_site else (0.40 if not multiparticle else 0.0)
+        move_lines = f"DisFreq {dis}\nRotFreq {rot}"
+        if multiparticle:
+            move_lines += "\nMultiParticleFreq " + ("0.20" if multi_site else "0.60")
     conf = f"""ExpertMode True
 Restart false
 PRNG INTSEED
@@ -460,6 +481,9 @@ Random_Seed 123
 Parameters par.inp
 Coordinates 0 box0.pdb
 Structure 0 box0.psf
+{'Coordinates 1 box1.pdb' if second is not None else ''}
+{'Structure 1 box1.psf' if second is not None else ''}
+{'GEMC NVT' if second is not None else ''}
 Temperature 298.0
 Potential {_POT_NAME[ff.vdw_kind]}
 {('Rswitch ' + repr(float(ff.r_switch))) if ff.vdw_kind == VDW_SWITCH else ''}
@@ -473,18 +497,18 @@ CachedFourier {'true' if cached_fourier else 'false'}
 Tolerance {ff.tolerance!r}
 1-4scaling false
 RcutCoulomb 0 {float(ff.r_cut_coulomb)!r}
+{('RcutCoulomb 1 ' + repr(float(ff.r_cut_coulomb))) if second is not None else ''}
 PressureCalc {'true 1000' if pressure_calc else 'false'}
 RunSteps {max(run_steps, 10)}
 EqSteps 5
 AdjSteps 5
 {'Pressure 1.01325' if npt else ''}
 {'VolFreq 0.02' if npt else ''}
-DisFreq {(0.40 if multiparticle else 0.60) - (0.02 if npt else 0.0)}
-RotFreq {0.40 if multiparticle and any(len(k.atom_names) > 1 for k in sys.mol_kinds) else (0.40 if not multiparticle else 0.0)}
-{('MultiParticleFreq ' + ('0.20' if any(len(k.atom_names) > 1 for k in sys.mol_kinds) else '0.60')) if multiparticle else ''}
+{move_lines}
 CellBasisVector1 0 {float(CV[0][0])!r} {float(CV[0][1])!r} {float(CV[0][2])!r}
 CellBasisVector2 0 {float(CV[1][0])!r} {float(CV[1][1])!r} {float(CV[1][2])!r}
 CellBasisVector3 0 {float(CV[2][0])!r} {float(CV[2][1])!r} {float(CV[2][2])!r}
+{box1_cell}
 CBMC_First 10
 CBMC_Nth 8
 CBMC_Ang 50

@@ -51,21 +51,37 @@ def run(exe, workdir, threads=1, env_extra=None):
     return r.returncode, r.stdout + r.stderr, time.time() - t0
 
 
-def compare(mols=343, steps=10000, mp=False, ens="NVT", rcut=8.0, tol=1e-9, env_extra=None):
+def compare(mols=343, steps=10000, mp=False, ens="NVT", rcut=8.0, tol=1e-9, env_extra=None,
+            charged=True):
+    """ens "GEMC": BASELINE configs[2] in small -- TraPPE-UA n-pentane, a liquid and a vapour
+    box, translate / rotate / CBMC regrowth / CBMC molecule swaps (MoleculeTransfer:
+    SwapDestRecip, SwapSourceRecip, SwapCorrection x2, SwapSelf through the engine)."""
     cpu = os.path.join(ROOT, "oracle", "_ref", f"GOMC_CPU_{ens}")
     b200 = os.path.join(ROOT, "oracle", "_ref", f"GOMC_B200_{ens}")
     for exe in (cpu, b200):
         if not os.path.exists(exe):
-            raise FileNotFoundError(exe + " (make -f integration/Makefile)")
-    s = synth.make_spce(mols, r_cut=rcut, r_cut_coulomb=rcut)
-    out = {"system": f"SPC/E {mols} molecules, Rcut {rcut}", "steps": steps, "ensemble": ens,
-           "moves": "translate 0.4 / rotate 0.4 / MultiParticle 0.2" if mp
-                    else "translate 0.6 / rotate 0.4"}
+            raise FileNotFoundError(exe + f" (make -f integration/Makefile ENS={ens})")
+    second = None
+    if ens == "GEMC":
+        s = synth.make_pentane(mols, L=round((mols / 0.0038) ** (1 / 3), 3), charged=charged,
+                               r_cut=rcut)
+        second = synth.make_pentane(max(mols // 5, 8), L=50.0, seed=77, charged=charged,
+                                    r_cut=rcut)
+        out = {"system": f"TraPPE-UA n-pentane{' (partial charges)' if charged else ''}: "
+                         f"{s.n_mols} molecules in box 0 (L {float(s.axis[0])}), {second.n_mols} "
+                         f"in box 1 (L 50), Rcut {rcut}",
+               "steps": steps, "ensemble": "GEMC-NVT",
+               "moves": "translate 0.5 / rotate 0.2 / CBMC regrowth 0.1 / CBMC swap 0.2"}
+    else:
+        s = synth.make_spce(mols, r_cut=rcut, r_cut_coulomb=rcut)
+        out = {"system": f"SPC/E {mols} molecules, Rcut {rcut}", "steps": steps, "ensemble": ens,
+               "moves": "translate 0.4 / rotate 0.4 / MultiParticle 0.2" if mp
+                        else "translate 0.6 / rotate 0.4"}
     logs = {}
     with tempfile.TemporaryDirectory() as d:
         for tag, exe in (("cpu", cpu), ("b200", b200)):
             wd = os.path.join(d, tag)
-            synth.write_gomc_inputs(s, wd, multiparticle=mp, run_steps=steps)
+            synth.write_gomc_inputs(s, wd, multiparticle=mp, run_steps=steps, second=second)
             conf = open(os.path.join(wd, "in.conf")).read()
             conf = conf.replace("RestartFreq false 1000", f"RestartFreq true {steps}")
             open(os.path.join(wd, "in.conf"), "w").write(conf)
@@ -74,7 +90,9 @@ def compare(mols=343, steps=10000, mp=False, ens="NVT", rcut=8.0, tol=1e-9, env_
                 raise RuntimeError(f"{tag} run failed:\n{log[-3000:]}")
             logs[tag] = log
             out[tag + "_seconds"] = round(secs, 2)
-            out[tag + "_pdb"] = open(os.path.join(wd, "out_BOX_0_restart.pdb"), "rb").read()
+            out[tag + "_pdb"] = b"".join(
+                open(os.path.join(wd, f"out_BOX_{b}_restart.pdb"), "rb").read()
+                for b in range(2 if second is not None else 1))
     sc, cc = parse(logs["cpu"])
     sb, cb = parse(logs["b200"])
     out["steps_printed"] = len(sc)
@@ -103,9 +121,11 @@ if __name__ == "__main__":
     ap.add_argument("--mols", type=int, default=343)
     ap.add_argument("--steps", type=int, default=10000)
     ap.add_argument("--mp", action="store_true")
+    ap.add_argument("--ens", default="NVT", choices=["NVT", "GEMC"])
+    ap.add_argument("--cpu-only", action="store_true", help="smoke-run the CPU executable only")
     ap.add_argument("--json", default=None)
     a = ap.parse_args()
-    res = compare(a.mols, a.steps, a.mp)
+    res = compare(a.mols, a.steps, a.mp, ens=a.ens)
     print(json.dumps(res, indent=1))
     if a.json:
         json.dump(res, open(a.json, "w"), indent=1)

@@ -17,8 +17,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _need():
-    for exe in ("GOMC_CPU_NVT", "GOMC_B200_NVT"):
+def _need(ens="NVT"):
+    for exe in (f"GOMC_CPU_{ens}", f"GOMC_B200_{ens}"):
         if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", exe)):
             pytest.skip(f"oracle/_ref/{exe} not built (make -f integration/Makefile)")
 
@@ -39,3 +39,18 @@ def test_nvt_multiparticle_trajectory():
     print(r)
     assert r["steps_printed"] >= 1500
     assert r["first_divergent_step"] is None or r["first_divergent_step"] > 200, r
+
+
+def test_gemc_pentane_cbmc_swaps():
+    """BASELINE configs[2] in small: GEMC-NVT of TraPPE-UA n-pentane (with partial charges so
+    that the reciprocal deltas are not identically zero), liquid + vapour box, translate /
+    rotate / CBMC regrowth / CBMC molecule transfer.  Every accepted swap goes through
+    SwapDestRecip + SwapSourceRecip + SwapCorrection x2 + SwapSelf + UpdateRecip on both boxes
+    of the engine, with molecules changing box."""
+    _need("GEMC")
+    r = run_parity.compare(mols=120, steps=3000, ens="GEMC", rcut=10.0)
+    print(r)
+    assert r["steps_printed"] >= 2 * 3000          # both boxes, every step
+    assert r["first_divergent_step"] is None, r
+    assert r["counters_identical"], r
+    assert r["pdb_identical"], r
