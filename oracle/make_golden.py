@@ -65,6 +65,29 @@ CASES = {
 }
 
 
+def make_cached():
+    """CachedFourier true (EwaldCached, BASELINE configs[1]): the same systems and probe
+    sequence as spce100_rc7 / spce343_rc8 through the reference's CACHED reciprocal class --
+    MolReciprocal as ref - cached + new with RestoreMol on rejection, SwapDest/SourceRecip
+    handing the cached rows over, MultiParticle with backupMolCache / exgMolCache.  The probe
+    skips what EwaldCached refuses (MolExchangeReciprocal, ChangeLambdaRecip, ChangeRecip)."""
+    probe = os.path.join(ROOT, "oracle", "_ref", "gomc_probe_NVT")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for name in ("spce100_rc7", "spce343_rc8"):
+        make, n_moves, seed = CASES[name][:3]
+        s = make()
+        with tempfile.TemporaryDirectory() as d:
+            synth.write_gomc_inputs(s, d, cached_fourier=True)
+            log = subprocess.run([probe, "golden", "in.conf", "dump.bin", str(n_moves), str(seed)],
+                                 cwd=d, env=env, capture_output=True, text=True)
+            if log.returncode != 0 or "Cache Ewald Fourier                Active" not in log.stdout:
+                print(log.stdout[-3000:], log.stderr[-2000:])
+                raise SystemExit(f"cached probe failed on {name}")
+            dump = po.read_dump(os.path.join(d, "dump.bin"))
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cached_" + name + ".npz"), **dump)
+        print(f"cached_{name}: {s.n_atoms} atoms, {len(dump)} arrays")
+
+
 def make_npt():
     """NPT volume trials (one accepted, one rejected) through the reference's own
     VolumeTransfer object: tests/golden/npt_spce343.npz (probe mode `volume`)."""
@@ -90,6 +113,8 @@ def make_npt():
 def main():
     if sys.argv[1:] == ["npt"]:
         return make_npt()
+    if sys.argv[1:] == ["cached"]:
+        return make_cached()
     probe = os.path.join(ROOT, "oracle", "_ref", "gomc_probe_NVT")
     if not os.path.exists(probe):
         subprocess.check_call(["make", "-s", "-f", "oracle/ref_build.mk", "ENS_LIST=NVT", "-j8"],

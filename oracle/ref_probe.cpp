@@ -416,11 +416,14 @@ int run_golden(int argc, char **argv) {
         out.f64(bname("SwapDestRecip", b), dDest);
         out.f64(bname("SwapDestRecip.sumRnew", b), ew.sumRnew[b],
                 ew.imageSizeRef[b]);
-        ew.RestoreMol(m);
+        // source right after destination, as MoleculeTransfer::CalcEn calls them
+        // (src/moves/MoleculeTransfer.h:127-129): the cached class hands the molecule's
+        // old cos/sin rows from one to the other; the rejection (RestoreMol) comes after
         double dSrc = ew.SwapSourceRecip(oldMol, b, m);
         out.f64(bname("SwapSourceRecip", b), dSrc);
         out.f64(bname("SwapSourceRecip.sumInew", b), ew.sumInew[b],
                 ew.imageSizeRef[b]);
+        ew.RestoreMol(m);
         out.f64(bname("SwapCorrection.new", b), ew.SwapCorrection(newMol));
         out.f64(bname("SwapCorrection.old", b), ew.SwapCorrection(oldMol));
         out.f64(bname("SwapSelf", b), ew.SwapSelf(newMol));
@@ -614,7 +617,8 @@ int run_golden(int argc, char **argv) {
 
     // ---- MEMC / NeMTMC / free-energy reciprocal deltas (own RNG stream so
     // that the entries above keep their values) ------------------------------
-    if (ff.ewald && molsInBox.size() > 3) {
+    // (EwaldCached refuses these moves outright, src/EwaldCached.cpp:392-440)
+    if (ff.ewald && molsInBox.size() > 3 && dynamic_cast<EwaldCached *>(&ew) == NULL) {
       std::mt19937_64 rng2(seed * 7919ULL + 17ULL * b + 1ULL);
       std::uniform_real_distribution<double> U2(-1.0, 1.0);
       uint pick[4];

@@ -21,9 +21,8 @@ def _xyz(d, key):
     return [d[f"{key}.{c}"] for c in "xyz"]
 
 
-@pytest.fixture(scope="module", params=GOLDEN, ids=[os.path.basename(g)[:-4] for g in GOLDEN])
-def gold(request):
-    d = dict(np.load(request.param))
+def engine_from_dump(d):
+    """An engine initialised the way GOMC initialises its GPU state, from a probe dump."""
     e = eng.Engine(1)
     e.init_forcefield(d["ff.sigmaSq"], d["ff.epsilon_cn"], d["ff.n"], int(d["ff.vdwKind"][0]),
                       int(d["ff.kindCount"][0]), float(d["ff.rCut"][0]), d["ff.rCutCoulomb"][:1],
@@ -48,6 +47,13 @@ def gold(request):
     e.nk = 0
     if d["ff.ewald"][0]:
         e.nk = e.setup_ewald(d["box0.axis"], d["ff.recip_rcut"][:1])
+    return e
+
+
+@pytest.fixture(scope="module", params=GOLDEN, ids=[os.path.basename(g)[:-4] for g in GOLDEN])
+def gold(request):
+    d = dict(np.load(request.param))
+    e = engine_from_dump(d)
     yield d, e
     e.close()
 
