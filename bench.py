@@ -394,8 +394,29 @@ def cfg5_record(eng, local, rank, world, dist, torch, flush, steps):
         time_full_box(e, world, dist, torch, flush, None, None, None, 1, False)
     dev, dom, wall, en = time_full_box(e, world, dist, torch, flush, None, None, None, steps, False)
     nk = e.nk
+    # E2 on the same box: the energy/force work of one MultiParticle trial
+    e.set_com(*s.com())
+
+    def mp_step():
+        e.L.gomcb200_mark_coords_changed(e.h)
+        e.box_reciprocal_sums(0)
+        e.box_force(0)
+        e.box_force_reciprocal(0)
+        e.calculate_torque(0)
+        e.get_forces(eng.MOL_TORQUE, 0, 1)
+    mp_step()
+    t_mp = []
+    for _ in range(3):
+        flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        mp_step()
+        t_mp.append((time.perf_counter() - t0) * 1e3)
     e.close()
-    return s, nk, float(np.mean(dev)), float(np.mean(wall)), float(np.mean(dom)), en
+    return s, nk, float(np.mean(dev)), float(np.mean(wall)), float(np.mean(dom)), en, \
+        float(np.mean(t_mp))
 
 
 def main():
@@ -509,7 +530,7 @@ def main():
     # MultiParticle::CalcEn (src/moves/MultiParticle.h:414-441): BoxReciprocalSums + BoxForce
     # + BoxReciprocal + BoxForceReciprocal + torque, coordinates resident (single GPU)
     mp_ms = mp_move_ms = None
-    if world == 1 and ewald:
+    if ewald and s.n_mols > 0:
         def mp_step():
             e.L.gomcb200_mark_coords_changed(e.h)
             e.box_reciprocal_sums(0)
@@ -523,10 +544,12 @@ def main():
         for _ in range(max(5, args.steps // 2)):
             flush.zero_()
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             t0 = time.perf_counter()
             mp_step()
             t_mp.append((time.perf_counter() - t0) * 1e3)
-        mp_ms = float(np.mean(t_mp))
+        mp_ms = shard.max_over_ranks(float(np.mean(t_mp)), world, "cuda")
         # whole MultiParticle move on the device: trial transform (Philox), CalcEn on the
         # trial set, acceptance weight, reject (pointer exchange back)
         e.set_com(*s.com())
@@ -549,10 +572,12 @@ def main():
         for i in range(max(5, args.steps // 2)):
             flush.zero_()
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             t0 = time.perf_counter()
             mp_move(i)
             t_mv.append((time.perf_counter() - t0) * 1e3)
-        mp_move_ms = float(np.mean(t_mv))
+        mp_move_ms = shard.max_over_ranks(float(np.mean(t_mv)), world, "cuda")
     # the direct-sum structure-factor kernels of round 1 next to the default (same step)
     direct = None
     if world == 1 and ewald and recip_algo == 5 and not args.no_extras:
@@ -574,13 +599,14 @@ def main():
     e.close()
     cfg5 = None
     if args.workload == "spce100k" and not args.no_extras:
-        s5, nk5, dev5, wall5, dom5, en5 = cfg5_record(eng, local, rank, world, dist, torch, flush,
-                                                      max(3, min(args.steps, 5)))
-        dev5, wall5 = (shard.max_over_ranks(v, world, "cuda") for v in (dev5, wall5))
+        s5, nk5, dev5, wall5, dom5, en5, mp5 = cfg5_record(eng, local, rank, world, dist, torch,
+                                                           flush, max(3, min(args.steps, 5)))
+        dev5, wall5, mp5 = (shard.max_over_ranks(v, world, "cuda") for v in (dev5, wall5, mp5))
         cfg5 = {"workload": f"electrolyte1m: {s5.n_atoms} atoms, L={float(s5.axis[0])} A, "
                             f"k-vectors={nk5} (BASELINE configs[4])",
                 "n_gpus": world, "ms_per_step": dev5, "value": 1e3 / dev5, "unit": UNIT,
                 "wall_ms_per_step": wall5, "structure_factor_stage_ms": dom5,
+                "multiparticle_ms_per_step": mp5,
                 "energies": {"lj": en5[0], "real": en5[1], "recip": en5[2]},
                 "timing": "CUDA events on the engine stream, max over ranks; coordinates "
                           "resident, re-binned every step"}
@@ -669,7 +695,9 @@ def main():
                 "value": 1e3 / mp_ms, "unit": "MP energy/force evaluations per s",
                 "ms_per_step": mp_ms,
                 "step": "BoxReciprocalSums + BoxForce + BoxReciprocal + BoxForceReciprocal + "
-                        "CalculateTorque (MultiParticle::CalcEn), wall clock incl. launches",
+                        "CalculateTorque (MultiParticle::CalcEn), wall clock incl. launches, max "
+                        "over ranks; N > 1: cell-slab BoxForce + all-reduce of the atom forces, "
+                        "slab-sharded structure factor, reciprocal force replicated",
                 "full_move_ms": mp_move_ms,
                 "full_move": "device trial transform + CalcEn on the trial set + GetCoeff + "
                              "reject, coordinates never leave the GPU"}),

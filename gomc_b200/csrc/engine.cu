@@ -148,6 +148,7 @@ struct BoxState {
   DevBuf<double> sx, sy, sz, sq;
   DevBuf<int2> skm;
   DevBuf<int> maxCellPop;  // largest cell population of the current binning (device)
+  bool sumsComplete = true;  // sharded engine: every rank holds all of sumRnew/sumInew
   // erfc(alpha r)/r and Coulomb virial factor as piecewise polynomials in r^2 (pair2.cuh)
   DevBuf<double> coulTab;
   double tabAlpha = -1.0, tabRc2 = -1.0;
@@ -312,8 +313,10 @@ int check_box(const gomcb200_engine *e, int b, bool needAxes = true, bool needTo
 // Entry points that read or update the whole structure factor, or the forces of every atom,
 // are only valid on an unsharded engine: with gomcb200_set_shard(world > 1) the sums of
 // k-vectors owned by other ranks are zero and forces exist only for this rank's cell slab.
-int check_unsharded(const gomcb200_engine *e, const char *what) {
-  if (e && e->shardWorld > 1)
+// withComm: the entry point is also valid on a sharded engine that owns a communicator
+// (gomcb200_set_comm): there the forces are all-reduced and every rank holds complete sums.
+int check_unsharded(const gomcb200_engine *e, const char *what, bool withComm = false) {
+  if (e && e->shardWorld > 1 && !(withComm && e->comm))
     return fail(GOMCB200_EINVAL,
                 "%s is not available on a sharded engine (gomcb200_set_shard world %d): "
                 "only the full-box sweeps are sharded",
@@ -599,6 +602,8 @@ int launch_pair2(gomcb200_engine *e, int b, const BoxParams &p, int slices, int 
   return 0;
 }
 
+int allreduce_energies(gomcb200_engine *e, double *buf, int n);
+
 // pair sweep; results (LJ, real) land in e->result[0..1]; mode MODE_VIRIAL: the six
 // tensor sums (LJ 11/22/33, Coulomb 11/22/33 without qqFact) in e->result[0..5]
 int run_pair(gomcb200_engine *e, int b, int mode) {
@@ -640,6 +645,17 @@ int run_pair(gomcb200_engine *e, int b, int mode) {
   // for cells too full to stage (both test the same device-side population count)
   const int *gate = nullptr;
   int gateCap = 0;
+  const bool reduceForces = force && e->comm && e->shardWorld > 1;
+  if (reduceForces) {
+    // this rank writes the atoms of its cell slab (complete forces: full shell); the rest
+    // stays zero and the three arrays are summed over the ranks below
+    if (e->nBoxes > 1)
+      return fail(GOMCB200_EINVAL, "sharded BoxForce supports single-box engines (the force "
+                                   "arrays are summed over the ranks as a whole)");
+    for (int c = 0; c < 3; ++c)
+      CK(cudaMemsetAsync(e->force[GOMCB200_ATOM_FORCE][c].p, 0,
+                         sizeof(double) * (size_t)e->nAtoms, e->stream));
+  }
   if (e->pairAlgo == 1 && !bx.nonOrth) {
     if (mode == MODE_VIRIAL)
       rc = launch_pair2<MODE_VIRIAL>(e, b, p, slices, grid, cell0, &gateCap);
@@ -678,6 +694,11 @@ int run_pair(gomcb200_engine *e, int b, int mode) {
   k_final_reduce<<<1, 1024, 0, e->stream>>>(grid, 2, e->blockA.p, e->blockB.p, nullptr,
                                            nullptr, e->result.p);
   e->launches += 1;
+  if (reduceForces)
+    for (int c = 0; c < 3; ++c) {
+      rc = allreduce_energies(e, e->force[GOMCB200_ATOM_FORCE][c].p, e->nAtoms);
+      if (rc) return rc;
+    }
   if (force && bx.nMols > 0) {
     k_mol_force<<<(bx.nMols + 255) / 256, 256, 0, e->stream>>>(
         bx.nMols, bx.molList.p, e->molStart.p, e->force[GOMCB200_ATOM_FORCE][0].p,
@@ -1450,6 +1471,7 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
   CK(cudaGetLastError());
   if (nufftDone && e->shardWorld > 1 && e->shardRank != 0)  // replicated: counted once
     CK(cudaMemsetAsync(e->result.p, 0, sizeof(double), e->stream));
+  bx.sumsComplete = e->shardWorld == 1 || nufftDone;
   return 0;
 }
 
@@ -2184,11 +2206,13 @@ int gomcb200_box_inter(gomcb200_engine *e, int box, double *LJEn, double *REn) {
 int gomcb200_box_force(gomcb200_engine *e, int box, double *LJEn, double *REn) {
   int rc = check_box(e, box);
   if (rc) return rc;
-  rc = check_unsharded(e, "gomcb200_box_force");
+  rc = check_unsharded(e, "gomcb200_box_force", true);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   timing_begin(e);
   rc = run_pair(e, box, true);
+  if (rc) return rc;
+  rc = allreduce_energies(e, e->result.p, 2);
   if (rc) return rc;
   rc = fetch_result(e, 2);
   if (rc) return rc;
@@ -2508,7 +2532,7 @@ int gomcb200_particle_nonbonded(gomcb200_engine *e, int box, int kindI, double c
 int gomcb200_calculate_torque(gomcb200_engine *e, int box) {
   int rc = check_box(e, box);
   if (rc) return rc;
-  rc = check_unsharded(e, "gomcb200_calculate_torque");
+  rc = check_unsharded(e, "gomcb200_calculate_torque", true);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   BoxState &bx = e->box[box];
@@ -2915,10 +2939,14 @@ static int run_force_recip(gomcb200_engine *e, int box, const double *sumR, cons
 int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
   int rc = check_box(e, box);
   if (rc) return rc;
-  rc = check_unsharded(e, "gomcb200_box_force_reciprocal");
+  rc = check_unsharded(e, "gomcb200_box_force_reciprocal", true);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   BoxState &bx = e->box[box];
+  if (e->shardWorld > 1 && !bx.sumsComplete)
+    return fail(GOMCB200_EINVAL,
+                "gomcb200_box_force_reciprocal on a sharded engine needs the complete structure "
+                "factor on every rank (the non-uniform FFT path of BoxReciprocalSums)");
   KSet &ks = bx.kset[1 - bx.cur];
   rc = ensure_sums(e, bx, ks.n);
   if (rc) return rc;
@@ -3090,7 +3118,7 @@ int gomcb200_mp_coeff(gomcb200_engine *e, int box, int moveType, double max, dou
                       double *wRatio) {
   int rc = check_box(e, box);
   if (rc) return rc;
-  rc = check_unsharded(e, "gomcb200_mp_coeff");
+  rc = check_unsharded(e, "gomcb200_mp_coeff", true);
   if (rc) return rc;
   if (!wRatio || moveType < 0 || moveType > 1) return fail(GOMCB200_EINVAL, "bad arguments");
   if (!e->trialActive)
@@ -3125,7 +3153,7 @@ int gomcb200_bm_coeff(gomcb200_engine *e, int box, int moveType, double max, dou
                       double *wRatio) {
   int rc = check_box(e, box);
   if (rc) return rc;
-  rc = check_unsharded(e, "gomcb200_bm_coeff");
+  rc = check_unsharded(e, "gomcb200_bm_coeff", true);
   if (rc) return rc;
   if (!wRatio || moveType < 0 || moveType > 1) return fail(GOMCB200_EINVAL, "bad arguments");
   if (!e->trialActive)

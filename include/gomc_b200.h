@@ -457,7 +457,11 @@ int gomcb200_set_shard(gomcb200_engine *e, int rank, int world);
  * box_reciprocal_setup/_sums and call_full_box_energy all-reduce their energies on the
  * engine's stream before the one device-to-host copy, so every rank returns the COMPLETE
  * values, and the structure factor runs as the slab-sharded non-uniform FFT (the pruned
- * slabs are all-gathered; every rank ends with the complete sumRnew/sumInew).  One engine
+ * slabs are all-gathered; every rank ends with the complete sumRnew/sumInew).  The
+ * MultiParticle path runs sharded too (single-box engines): box_force computes the forces of
+ * this rank's cell slab and all-reduces the atom force arrays, box_force_reciprocal /
+ * calculate_torque / mp_transform / mp_coeff then run replicated on the complete data, so
+ * every rank takes the same accept/reject decision without exchanging coordinates.  One engine
  * per GPU, one host thread per engine: the ranks may be processes (torchrun, MPI) or the
  * threads of ONE process -- GOMC is a single process (src/Main.cpp:318-326) and reaches all
  * GPUs of a box this way (gomc_b200/host/multi_gpu_test.cpp).  world == 1 drops the
