@@ -31,6 +31,19 @@
 #include "nufft.h"
 #include "comm.h"
 
+// NVTX ranges under the reference's own profiling event names (src/GOMCEventsProfileDef.h:
+// 105-132), so that an Nsight timeline of GOMC on this engine reads like one of GOMC built
+// with GOMC_NVTX_ENABLED.  nvtx3 is header-only; without a profiler attached a range costs a
+// few nanoseconds.
+#include <nvtx3/nvToolsExt.h>
+namespace {
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define GB_RANGE(name) NvtxRange gbNvtxRange_(name)
+
 using namespace gb;
 
 namespace {
@@ -2187,6 +2200,7 @@ int gomcb200_set_molecule_coords(gomcb200_engine *e, int molIndex, const double 
 
 // ---- pair path --------------------------------------------------------------
 int gomcb200_box_inter(gomcb200_engine *e, int box, double *LJEn, double *REn) {
+  GB_RANGE("energy_box_inter");
   int rc = check_box(e, box);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
@@ -2204,6 +2218,7 @@ int gomcb200_box_inter(gomcb200_engine *e, int box, double *LJEn, double *REn) {
 }
 
 int gomcb200_box_force(gomcb200_engine *e, int box, double *LJEn, double *REn) {
+  GB_RANGE("energy_box_force");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_box_force", true);
@@ -2225,6 +2240,7 @@ int gomcb200_box_force(gomcb200_engine *e, int box, double *LJEn, double *REn) {
 int gomcb200_molecule_inter(gomcb200_engine *e, int box, int molIndex, const double *newX,
                             const double *newY, const double *newZ, double *dLJ,
                             double *dReal, int *overlap) {
+  GB_RANGE("energy_molecule_inter");
   int rc = check_box(e, box);
   if (rc) return rc;
   if (molIndex < 0 || molIndex >= e->nMols || !newX || !newY || !newZ)
@@ -2271,6 +2287,7 @@ int gomcb200_molecule_inter(gomcb200_engine *e, int box, int molIndex, const dou
 int gomcb200_molecule_trial(gomcb200_engine *e, int box, int molIndex, const double *newX,
                             const double *newY, const double *newZ, double *dLJ, double *dReal,
                             int *overlap, double *energyRecipNew) {
+  GB_RANGE("energy_molecule_inter");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_molecule_trial");
@@ -2334,6 +2351,7 @@ int gomcb200_molecule_trial(gomcb200_engine *e, int box, int molIndex, const dou
 int gomcb200_swap_correction(gomcb200_engine *e, int box, int molIndex, const double *x,
                              const double *y, const double *z, double *correction,
                              double *self) {
+  GB_RANGE("ewald_molecule_swap_correction_energy");
   int rc = check_box(e, box);
   if (rc) return rc;
   if (molIndex < 0 || molIndex >= e->nMols || !x || !y || !z)
@@ -2397,6 +2415,7 @@ int gomcb200_change_self_correction(gomcb200_engine *e, int box, int molIndex, d
 int gomcb200_swap_trial(gomcb200_engine *e, int box, int molIndex, const double *x,
                         const double *y, const double *z, int insert, double *energyRecipNew,
                         double *correction, double *self) {
+  GB_RANGE("ewald_molecule_swap_recip_energy");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_swap_trial");
@@ -2442,6 +2461,7 @@ int gomcb200_swap_trial(gomcb200_engine *e, int box, int molIndex, const double 
 int gomcb200_particle_inter(gomcb200_engine *e, int box, int molIndex, int partIndex,
                             int trials, const double *tx, const double *ty, const double *tz,
                             double *en, double *real, int *overlap) {
+  GB_RANGE("energy_CBMC_inter");
   int rc = check_box(e, box);
   if (rc) return rc;
   if (molIndex < 0 || molIndex >= e->nMols || trials < 0 || !tx || !ty || !tz)
@@ -2474,6 +2494,7 @@ int gomcb200_particle_nonbonded(gomcb200_engine *e, int box, int kindI, double c
                                 const double *partnerCharge, const double *px, const double *py,
                                 const double *pz, int trials, const double *tx, const double *ty,
                                 const double *tz, double *inter) {
+  GB_RANGE("energy_CBMC_intra_nonbonded");
   int rc = check_box(e, box, true, false);
   if (rc) return rc;
   if (kindI < 0 || kindI >= e->kindCount || nPartners < 0 || trials < 0 || !inter ||
@@ -2530,6 +2551,7 @@ int gomcb200_particle_nonbonded(gomcb200_engine *e, int box, int kindI, double c
 }
 
 int gomcb200_calculate_torque(gomcb200_engine *e, int box) {
+  GB_RANGE("energy_box_torque");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_calculate_torque", true);
@@ -2584,11 +2606,13 @@ int gomcb200_recip_count(gomcb200_engine *e, int box, const double axis[3], doub
 
 int gomcb200_recip_init(gomcb200_engine *e, int box, const double axis[3], int *imageSize,
                         int *kmax) {
+  GB_RANGE("ewald_box_recip_initialization");
   return gomcb200_recip_init_volume(e, box, axis, 0.0, imageSize, kmax);
 }
 
 int gomcb200_recip_init_volume(gomcb200_engine *e, int box, const double axis[3], double volume,
                                int *imageSize, int *kmax) {
+  GB_RANGE("ewald_box_recip_initialization");
   if (!e || box < 0 || box >= e->nBoxes || !axis || !e->haveFF || !(volume >= 0.0))
     return fail(GOMCB200_EINVAL, "bad arguments");
   CK(cudaSetDevice(e->device));
@@ -2669,14 +2693,17 @@ static int recip_sums_common(gomcb200_engine *e, int box, bool newSet, double *e
 }
 
 int gomcb200_box_reciprocal_setup(gomcb200_engine *e, int box, double *energyRecip) {
+  GB_RANGE("ewald_box_recip_setup");
   return recip_sums_common(e, box, true, energyRecip);
 }
 
 int gomcb200_box_reciprocal_sums(gomcb200_engine *e, int box, double *energyRecip) {
+  GB_RANGE("ewald_box_recip_energy");
   return recip_sums_common(e, box, false, energyRecip);
 }
 
 int gomcb200_box_reciprocal(gomcb200_engine *e, int box, int isNewVolume, double *energyRecip) {
+  GB_RANGE("ewald_box_recip_energy");
   int rc = check_box(e, box);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
@@ -2704,6 +2731,7 @@ int gomcb200_box_reciprocal(gomcb200_engine *e, int box, int isNewVolume, double
 
 int gomcb200_mol_reciprocal(gomcb200_engine *e, int box, int molIndex, const double *newX,
                             const double *newY, const double *newZ, double *energyRecipNew) {
+  GB_RANGE("ewald_molecule_recip_energy");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_mol_reciprocal");
@@ -2717,6 +2745,7 @@ int gomcb200_mol_reciprocal(gomcb200_engine *e, int box, int molIndex, const dou
 int gomcb200_swap_reciprocal(gomcb200_engine *e, int box, int molIndex, const double *x,
                              const double *y, const double *z, int insert,
                              double *energyRecipNew) {
+  GB_RANGE("ewald_molecule_swap_recip_energy");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_swap_reciprocal");
@@ -2730,6 +2759,7 @@ int gomcb200_swap_reciprocal(gomcb200_engine *e, int box, int molIndex, const do
 int gomcb200_mol_exchange_reciprocal(gomcb200_engine *e, int box, int n, const double *w,
                                      const double *x, const double *y, const double *z,
                                      int firstCall, double scale, double *energyRecipNew) {
+  GB_RANGE("ewald_molecule_MEMC_recip_energy");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_mol_exchange_reciprocal");
@@ -2775,6 +2805,7 @@ int gomcb200_mol_exchange_reciprocal(gomcb200_engine *e, int box, int n, const d
 int gomcb200_change_lambda_mol_reciprocal(gomcb200_engine *e, int box, int molIndex,
                                           const double *x, const double *y, const double *z,
                                           double lambdaCoef, double *energyRecipNew) {
+  GB_RANGE("ewald_molecule_NEMTMC_recip_energy");
   if (!e || !e->haveTopo || molIndex < 0 || molIndex >= e->nMols || !x || !y || !z)
     return fail(GOMCB200_EINVAL, "bad arguments");
   const int s = e->hMolStart[molIndex], len = e->hMolStart[molIndex + 1] - s;
@@ -2792,6 +2823,7 @@ int gomcb200_change_lambda_mol_reciprocal(gomcb200_engine *e, int box, int molIn
 
 int gomcb200_change_recip(gomcb200_engine *e, int box, int molIndex, int nStates,
                           const double *lambdaCoul, int iState, double *energyRecip) {
+  GB_RANGE("ewald_molecule_NEMTMC_recip_energy");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_change_recip");
@@ -2937,6 +2969,7 @@ static int run_force_recip(gomcb200_engine *e, int box, const double *sumR, cons
 }
 
 int gomcb200_box_force_reciprocal(gomcb200_engine *e, int box) {
+  GB_RANGE("ewald_box_recip_force");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_box_force_reciprocal", true);
@@ -2988,6 +3021,7 @@ static int mp_transform_impl(gomcb200_engine *e, int box, int brownian, int move
 int gomcb200_mp_transform(gomcb200_engine *e, int box, int moveType, double max,
                           double lambdaBETA, unsigned long long step, unsigned int key,
                           unsigned long long seed, const signed char *isMoleculeInvolved) {
+  GB_RANGE("transform_multiParticle_move");
   return mp_transform_impl(e, box, 0, moveType, max, lambdaBETA, step, key, seed,
                            isMoleculeInvolved);
 }
@@ -2995,6 +3029,7 @@ int gomcb200_mp_transform(gomcb200_engine *e, int box, int moveType, double max,
 int gomcb200_bm_transform(gomcb200_engine *e, int box, int moveType, double max, double BETA,
                           unsigned long long step, unsigned int key, unsigned long long seed,
                           const signed char *isMoleculeInvolved) {
+  GB_RANGE("transform_multiParticleBM_move");
   return mp_transform_impl(e, box, 1, moveType, max, BETA, step, key, seed,
                            isMoleculeInvolved);
 }
@@ -3185,6 +3220,7 @@ int gomcb200_bm_coeff(gomcb200_engine *e, int box, int moveType, double max, dou
 
 // ---- virial -----------------------------------------------------------------
 int gomcb200_box_inter_virial(gomcb200_engine *e, int box, double vT[3], double rT[3]) {
+  GB_RANGE("energy_box_virial");
   int rc = check_box(e, box);
   if (rc) return rc;
   if (!vT || !rT) return fail(GOMCB200_EINVAL, "bad arguments");
@@ -3201,6 +3237,7 @@ int gomcb200_box_inter_virial(gomcb200_engine *e, int box, double vT[3], double 
 }
 
 int gomcb200_virial_reciprocal(gomcb200_engine *e, int box, double wT[3]) {
+  GB_RANGE("ewald_box_recip_virial");
   int rc = check_box(e, box);
   if (rc) return rc;
   rc = check_unsharded(e, "gomcb200_virial_reciprocal");
@@ -3356,6 +3393,7 @@ int gomcb200_update_recip_vec(gomcb200_engine *e, int box) {
 }
 
 int gomcb200_box_self_correction(gomcb200_engine *e, int box, double *self, double *correction) {
+  GB_RANGE("ewald_box_self_energy");
   int rc = check_box(e, box);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
@@ -3388,6 +3426,7 @@ int gomcb200_box_self_correction(gomcb200_engine *e, int box, double *self, doub
 // ---- literal drop-ins --------------------------------------------------------
 int gomcb200_call_box_inter(gomcb200_engine *e, int box, const double *x, const double *y,
                             const double *z, const double axis[3], double *REn, double *LJEn) {
+  GB_RANGE("energy_box_inter");
   int rc = 0;
   if (axis) rc = gomcb200_set_box_axes(e, box, axis);
   if (rc) return rc;
@@ -3407,6 +3446,7 @@ int gomcb200_call_box_force(gomcb200_engine *e, int box, const double *x, const 
                             const double *z, const double axis[3], double *REn, double *LJEn,
                             double *aForcex, double *aForcey, double *aForcez,
                             double *mForcex, double *mForcey, double *mForcez) {
+  GB_RANGE("energy_box_force");
   int rc = 0;
   if (axis) rc = gomcb200_set_box_axes(e, box, axis);
   if (rc) return rc;
@@ -3425,6 +3465,7 @@ int gomcb200_call_box_force(gomcb200_engine *e, int box, const double *x, const 
 int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
                                   const double *y, const double *z, double *LJEn, double *REn,
                                   double *energyRecip) {
+  GB_RANGE("energy_system_total(inter,recip)");
   int rc = check_box(e, box);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));

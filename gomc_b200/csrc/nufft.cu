@@ -833,7 +833,9 @@ int nufft_choose(const int nmax[3], NufftGrid *g) {
   }
   // window width for ~1e-13: measured one point wider than the aliasing estimate
   // ln(1/eps) / (pi sqrt(1 - 1/sigma))
-  int w = (int)std::ceil(std::log(1e13) / (M_PI * std::sqrt(1.0 - 1.0 / sigmaMin))) + 1;
+  double eps = 1e-13;
+  if (const char *ev = getenv("GOMCB200_NUFFT_EPS")) eps = std::max(1e-14, std::min(1e-6, atof(ev)));
+  int w = (int)std::ceil(std::log(1.0 / eps) / (M_PI * std::sqrt(1.0 - 1.0 / sigmaMin))) + 1;
   w = std::min(kMaxW, std::max(12, (w + 1) & ~1));
   g->w = w;
   g->beta = 0.97 * M_PI * w * (1.0 - 1.0 / (2.0 * sigmaMin));

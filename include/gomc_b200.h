@@ -475,13 +475,15 @@ int gomcb200_mark_coords_changed(gomcb200_engine *e);
 
 /* ---- tuning / introspection (tests and bench only) ---------------------- */
 /* algorithm for the structure-factor build (the sums behind BoxReciprocalSetup/
- * BoxReciprocalSums, src/Ewald.cpp:213-330): 0 = direct sincos per (atom,k)
- * (reference algorithm), 1 = factorised per-axis phases on the FP64 CUDA
- * cores, 2 = the same factorisation on the FP64 MMA path (DMMA), 3 = byte-
- * sliced fixed point on the INT8 tensor cores (tcgen05 + TMEM; agrees with 2
- * to < 1e-11 relative), 4 = default: 2, or 3 once charged atoms x k-vectors
- * of the box reaches the work threshold below (1e11: boxes of ~3e5 atoms up,
- * where the INT8 kernel measured 2.6x faster). */
+ * BoxReciprocalSums, src/Ewald.cpp:213-330) and the reciprocal force:
+ *   4 = default: 5 where it applies (orthogonal box), else 2, else 0 (triclinic cell);
+ *   5 = non-uniform FFT (spread on the FP64 tensor path + pruned FFT; agrees with the direct
+ *       sums to ~1e-13 of max |S|, energy ~1e-15 relative);
+ *   0 = direct sincos per (atom,k) (the reference's algorithm);
+ *   1 = factorised per-axis phases on the FP64 CUDA cores;
+ *   2 = the same factorisation on the FP64 MMA path (DMMA);
+ *   3 = byte-sliced fixed point on the INT8 tensor cores (tcgen05 + TMEM; agrees with 2 to
+ *       < 1e-11 relative). */
 int gomcb200_set_recip_algo(gomcb200_engine *e, int algo);
 /* pair-sweep kernel of BoxInter / BoxForce / VirialCalc on orthogonal boxes: 1 = default,
  * k_pair_box2 (TMA-staged cells, FP32 candidate filter, tabulated Ewald real-space terms);
