@@ -524,7 +524,18 @@ def main():
             t.append(e.last_timing()[0])
         return float(np.mean(t))
     pair_ms = alone(lambda: e.box_inter(0), max(5, args.steps // 2))
-    recip_stage_ms = float(np.mean(dom_ms)) if ewald else 0.0
+    # structure-factor stage alone (inside the step it runs on a second stream next to the
+    # pair sweep): BoxReciprocalSums on re-packed coordinates, events around the stage
+    recip_stage_ms = 0.0
+    if ewald:
+        t = []
+        for _ in range(max(5, args.steps // 2)):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e.mark_coords_changed()
+            e.box_reciprocal_sums(0)
+            t.append(e.last_timing()[1])
+        recip_stage_ms = float(np.mean(t))
 
     # secondary metric of BASELINE.json: MultiParticle moves/s = the energy/force work of
     # MultiParticle::CalcEn (src/moves/MultiParticle.h:414-441): BoxReciprocalSums + BoxForce

@@ -248,6 +248,12 @@ struct gomcb200_engine {
   bool timing = false;
   cudaEvent_t ev[8];
   float lastTotalMs = 0, lastDominantMs = 0;
+  // second stream of the full-box evaluation: the structure factor (and, sharded, its
+  // all-gather) runs next to the cell binning and the pair sweep; scratch of its own
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  DevBuf<double> blockA2, result2;
+  bool overlap = true;
 };
 
 namespace {
@@ -397,7 +403,7 @@ int ensure_cells(gomcb200_engine *e, int b) {
                                                   bx.skm.p, bx.sortedPos.p);
     e->launches += 4;
   }
-  k_cell_bounds<<<(g.nCells + 1 + 255) / 256, 256, 0, e->stream>>>(
+  k_cell_bounds<<<(n + 1 + 255) / 256, 256, 0, e->stream>>>(
       g.nCells, n, bx.keysSorted.p, bx.cellStart.p, bx.maxCellPop.p);
   e->launches += 1;
   CK(cudaGetLastError());
@@ -629,12 +635,22 @@ int run_pair(gomcb200_engine *e, int b, int mode) {
   // multi-GPU: this rank owns cells [cell0, cell1) (x-major slab)
   const int cell0 = (int)(((long long)nCells * e->shardRank) / e->shardWorld);
   const int cell1 = (int)(((long long)nCells * (e->shardRank + 1)) / e->shardWorld);
-  // CTAs per cell: enough CTAs for the SMs this rank has to fill (a sharded rank owns few
-  // cells), but every slice re-stages the whole neighbourhood
+  // CTAs per cell ("slices" of a cell's i-atoms): every slice re-stages the whole
+  // neighbourhood (~8 % of a full cell's work), and CTAs run in waves of one per SM; take the
+  // slice count with the least  waves x (staging + work / slices)
   const int owned = std::max(1, cell1 - cell0);
-  int slices = e->shardWorld > 1 ? (2 * e->numSMs + owned - 1) / owned
-                                 : (4 * e->numSMs + nCells - 1) / nCells;
-  slices = std::max(1, std::min(slices, 16));
+  int slices = 1;
+  {
+    double best = 1e300;
+    for (int sl = 1; sl <= 16; ++sl) {
+      const double waves = std::ceil((double)owned * sl / e->numSMs);
+      const double cost = waves * (0.08 + 1.0 / sl);
+      if (cost < best - 1e-12) {
+        best = cost;
+        slices = sl;
+      }
+    }
+  }
   int grid = (cell1 - cell0) * slices;
   // shared-memory staging of the neighbour cells (40 B per atom)
   const int nWarps = mode == MODE_ENERGY ? kWarpsEnergy
@@ -1807,6 +1823,11 @@ int gomcb200_create(gomcb200_engine **out, int device, int nBoxes) {
   CK(cudaMemset(e->ticket.p, 0, 4 * sizeof(unsigned)));
   CK(e->trialPart.reserve(3 * 2 * kTrialMaxAtoms * kProbeSplit + 8));
   for (auto &ev : e->ev) CK(cudaEventCreate(&ev));
+  CK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
+  CK(e->result2.reserve(64));
+  if (const char *ev = getenv("GOMCB200_OVERLAP")) e->overlap = atoi(ev) != 0;
   e->nufft = gbn::nufft_create();
   *out = e;
   return 0;
@@ -1823,6 +1844,9 @@ int gomcb200_destroy(gomcb200_engine *e) {
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   gbn::nufft_destroy(e->nufft);
   gbc::comm_destroy(e->comm);
+  if (e->evFork) cudaEventDestroy(e->evFork);
+  if (e->evJoin) cudaEventDestroy(e->evJoin);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
   cudaStreamDestroy(e->stream);
   delete e;
   return 0;
@@ -3475,13 +3499,37 @@ int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
   }
   timing_begin(e);
   CK(e->energy3.reserve(4));
+  BoxState &bx = e->box[box];
+  const bool recipOn = e->ewald && e->electrostatic;
+  const bool fork = recipOn && e->overlap;
+  if (fork) {
+    // structure factor on the second stream, behind the coordinates that are on the first:
+    // its small set-up kernels, and on a sharded engine the all-gather of the FFT slabs, run
+    // under the cell binning and the pair sweep.  The stream and scratch members are
+    // exchanged for the duration of the call so that every helper below queues there.
+    CK(cudaEventRecord(e->evFork, e->stream));
+    CK(cudaStreamWaitEvent(e->stream2, e->evFork, 0));
+    std::swap(e->stream, e->stream2);
+    std::swap(e->blockA, e->blockA2);
+    std::swap(e->result, e->result2);
+    rc = run_recip_sums(e, box, bx.kset[1 - bx.cur]);
+    cudaError_t ce = cudaSuccess;
+    if (!rc) ce = cudaEventRecord(e->evJoin, e->stream);
+    std::swap(e->stream, e->stream2);
+    std::swap(e->blockA, e->blockA2);
+    std::swap(e->result, e->result2);
+    if (rc) return rc;
+    CK(ce);
+  }
   rc = run_pair(e, box, false);
   if (rc) return rc;
   CK(cudaMemcpyAsync(e->energy3.p, e->result.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice,
                      e->stream));
-  BoxState &bx = e->box[box];
-  const bool recipOn = e->ewald && e->electrostatic;
-  if (recipOn) {
+  if (fork) {
+    CK(cudaStreamWaitEvent(e->stream, e->evJoin, 0));
+    CK(cudaMemcpyAsync(e->energy3.p + 2, e->result2.p, sizeof(double), cudaMemcpyDeviceToDevice,
+                       e->stream));
+  } else if (recipOn) {
     rc = run_recip_sums(e, box, bx.kset[1 - bx.cur]);
     if (rc) return rc;
     CK(cudaMemcpyAsync(e->energy3.p + 2, e->result.p, sizeof(double), cudaMemcpyDeviceToDevice,

@@ -89,19 +89,15 @@ __global__ void k_nufft_keys(GridGeom g, int nAtoms, const double4 *__restrict__
   vals[i] = i;
 }
 
+// binStart[c] = first sorted position whose key >= c: one thread per sorted position (and one
+// past the end) fills the entries of the bins in (key[t-1], key[t]].
 __global__ void k_nufft_bounds(int nBins, int n, const int *__restrict__ sortedKeys,
                                int *__restrict__ binStart) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > nBins) return;
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (sortedKeys[mid] < c)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  binStart[c] = lo;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n) return;
+  const int prev = t == 0 ? -1 : sortedKeys[t - 1];
+  const int cur = t == n ? nBins : sortedKeys[t];
+  for (int c = prev + 1; c <= cur; ++c) binStart[c] = t;
 }
 
 // Window tables of the atoms in bin-sorted order.  One thread per (atom, axis, j):
@@ -939,8 +935,8 @@ int bin_atoms(Nufft *nf, cudaStream_t st, const NufftGrid &g, const GridGeom &gg
   NCK(nf->cubTemp.reserve(tmp + 16));
   NCK(cub::DeviceRadixSort::SortPairs(nf->cubTemp.p, tmp, nf->keys.p, nf->keysSorted.p,
                                       nf->vals.p, nf->sortedIdx.p, nAtoms, 0, bits, st));
-  k_nufft_bounds<<<(nBins + 1 + 255) / 256, 256, 0, st>>>(nBins, nAtoms, nf->keysSorted.p,
-                                                         nf->binStart.p);
+  k_nufft_bounds<<<(nAtoms + 1 + 255) / 256, 256, 0, st>>>(nBins, nAtoms, nf->keysSorted.p,
+                                                          nf->binStart.p);
   double *dt = wantD ? nf->dtab.p : nullptr;
   const int *sk = nullptr;
   int px0 = 0, px1 = 0;

@@ -61,28 +61,22 @@ __global__ void k_cell_keys(CellGrid g, int n, const int *__restrict__ atomList,
 }
 
 // cellStart[c] = first sorted position whose key >= c (lower bound); *maxPop (zeroed by the
-// caller) = largest cell population.
-__device__ __forceinline__ int cell_lower_bound(const int *__restrict__ sortedKeys, int n, int c) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (sortedKeys[mid] < c)
-      lo = mid + 1;
-    else
-      hi = mid;
-  }
-  return lo;
-}
+// caller) = largest cell population.  One thread per sorted position t (and one past the end):
+// it fills cellStart for every cell in (key[t-1], key[t]] -- no search, one coalesced pass --
+// and, where a cell ends, reports its population.
 __global__ void k_cell_bounds(int nCells, int n,
                               const int *__restrict__ sortedKeys,
                               int *cellStart, int *maxPop) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > nCells) return;
-  int lo = cell_lower_bound(sortedKeys, n, c);
-  cellStart[c] = lo;
-  if (c < nCells) {
-    int pop = cell_lower_bound(sortedKeys, n, c + 1) - lo;
-    if (pop > 0) atomicMax(maxPop, pop);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n) return;
+  const int prev = t == 0 ? -1 : sortedKeys[t - 1];
+  const int cur = t == n ? nCells : sortedKeys[t];
+  for (int c = prev + 1; c <= cur; ++c) cellStart[c] = t;
+  if (t > 0 && cur != prev) {
+    // the run of key `prev` ends at t; its start is the first position of that key
+    int lo = t - 1;
+    while (lo > 0 && sortedKeys[lo - 1] == prev) --lo;
+    atomicMax(maxPop, t - lo);
   }
 }
 
