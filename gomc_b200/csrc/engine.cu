@@ -69,6 +69,9 @@ int fail(int code, const char *fmt, ...) {
   } while (0)
 
 // Owning device buffer: freed when the engine (or the KSet / BoxState holding it) goes away.
+// bumped by every (re)allocation or release of a DevBuf: invalidates captured CUDA graphs
+std::atomic<long long> g_devBufGeneration{0};
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -93,6 +96,7 @@ struct DevBuf {
   ~DevBuf() { release(); }
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
+    ++g_devBufGeneration;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -102,6 +106,7 @@ struct DevBuf {
     return e;
   }
   void release() {
+    if (p) ++g_devBufGeneration;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -254,6 +259,17 @@ struct gomcb200_engine {
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   DevBuf<double> blockA2, result2;
   bool overlap = true;
+  // the whole full-box evaluation as a CUDA graph (both streams, the collectives included):
+  // captured once the state it bakes in has been identical for a few calls, replayed while
+  // it stays so (StepKey), dropped and re-captured otherwise
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<unsigned char> key;
+    long long launches = 0;
+    int warm = 0;
+    bool sumsComplete = true;
+  } stepGraph[2];
+  bool useGraph = true, capturing = false;
 };
 
 namespace {
@@ -261,6 +277,7 @@ namespace {
 BoxParams make_params(const gomcb200_engine *e, int b) {
   const BoxState &bx = e->box[b];
   BoxParams p;
+  std::memset(&p, 0, sizeof(p));  // padding included: the struct is compared bytewise (step_key)
   for (int d = 0; d < 3; ++d) {
     p.ax[d] = bx.axis[d];
     p.half[d] = bx.axis[d] * 0.5;  // BoxDimensions halfAx
@@ -1278,7 +1295,7 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
   }
   const int nAt = bx.nCharged;
   int nSlabs = 1;
-  if (e->timing) cudaEventRecord(e->ev[2], e->stream);
+  if (e->timing && !e->capturing) cudaEventRecord(e->ev[2], e->stream);
   bool i8Done = false, nufftDone = false;
   const bool wantI8 = e->recipAlgo == 3;
   if ((e->recipAlgo == 4 || e->recipAlgo == 5) && ks.planValid && ks.ngValid && nAt > 0) {
@@ -1490,7 +1507,7 @@ int run_recip_sums(gomcb200_engine *e, int b, KSet &ks) {
     }
   }
   CK(cudaGetLastError());
-  if (e->timing) cudaEventRecord(e->ev[3], e->stream);
+  if (e->timing && !e->capturing) cudaEventRecord(e->ev[3], e->stream);
   k_recip_finish<<<nBlocks, 256, 0, e->stream>>>(nk, nkStride, nSlabs, e->part.p,
                                                 ks.prefact.p, bx.sum[bx.iRnew].p,
                                                 bx.sum[bx.iInew].p, e->blockA.p);
@@ -1779,6 +1796,74 @@ void timing_end(gomcb200_engine *e, bool recip) {
   if (recip) cudaEventElapsedTime(&e->lastDominantMs, e->ev[2], e->ev[3]);
 }
 
+// Everything one full-box evaluation queues (both streams, the collectives, the D2H copy of
+// the three energies into hRes[8..10]) -- the unit that is captured as a CUDA graph.
+int enqueue_full_box(gomcb200_engine *e, int box, bool recipOn) {
+  BoxState &bx = e->box[box];
+  int rc = 0;
+  const bool fork = recipOn && e->overlap;
+  if (fork) {
+    // structure factor on the second stream, behind the coordinates that are on the first:
+    // its small set-up kernels, and on a sharded engine the all-gather of the FFT slabs, run
+    // under the cell binning and the pair sweep.  The stream and scratch members are
+    // exchanged for the duration of the call so that every helper below queues there.
+    CK(cudaEventRecord(e->evFork, e->stream));
+    CK(cudaStreamWaitEvent(e->stream2, e->evFork, 0));
+    std::swap(e->stream, e->stream2);
+    std::swap(e->blockA, e->blockA2);
+    std::swap(e->result, e->result2);
+    rc = run_recip_sums(e, box, bx.kset[1 - bx.cur]);
+    cudaError_t ce = cudaSuccess;
+    if (!rc) ce = cudaEventRecord(e->evJoin, e->stream);
+    std::swap(e->stream, e->stream2);
+    std::swap(e->blockA, e->blockA2);
+    std::swap(e->result, e->result2);
+    if (rc) return rc;
+    CK(ce);
+  }
+  rc = run_pair(e, box, false);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->energy3.p, e->result.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice,
+                     e->stream));
+  if (fork) {
+    CK(cudaStreamWaitEvent(e->stream, e->evJoin, 0));
+    CK(cudaMemcpyAsync(e->energy3.p + 2, e->result2.p, sizeof(double), cudaMemcpyDeviceToDevice,
+                       e->stream));
+  } else if (recipOn) {
+    rc = run_recip_sums(e, box, bx.kset[1 - bx.cur]);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(e->energy3.p + 2, e->result.p, sizeof(double), cudaMemcpyDeviceToDevice,
+                       e->stream));
+  } else {
+    CK(cudaMemsetAsync(e->energy3.p + 2, 0, sizeof(double), e->stream));
+  }
+  // sharded engine with a communicator: the path's only reduction, three doubles, on the
+  // engine's stream; every rank returns the complete energies
+  rc = allreduce_energies(e, e->energy3.p, 3);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(e->hRes + 8, e->energy3.p, 3 * sizeof(double), cudaMemcpyDeviceToHost,
+                     e->stream));
+  return 0;
+}
+
+// What a captured step bakes in besides the (stable) buffer addresses: if any of it differs,
+// the graph is dropped and the step re-captured.
+void step_key(gomcb200_engine *e, int box, std::vector<unsigned char> &key) {
+  BoxState &bx = e->box[box];
+  const BoxParams p = make_params(e, box);
+  const KSet &ks = bx.kset[1 - bx.cur];
+  const long long ints[] = {box, bx.nAtoms, bx.nMols, bx.nCharged, bx.cur, bx.iRnew, bx.iInew,
+                            ks.n, (long long)(size_t)ks.kx.p, (long long)(size_t)ks.prefact.p,
+                            e->recipAlgo, e->pairAlgo, e->shardRank, e->shardWorld,
+                            (long long)(size_t)e->comm, e->overlap, e->timing, bx.nonOrth,
+                            ks.planValid, ks.ngValid, ks.mmaValid,
+                            g_devBufGeneration.load(), gbn::nufft_alloc_generation()};
+  key.resize(sizeof(p) + sizeof(ints) + sizeof(bx.axis));
+  std::memcpy(key.data(), &p, sizeof(p));
+  std::memcpy(key.data() + sizeof(p), ints, sizeof(ints));
+  std::memcpy(key.data() + sizeof(p) + sizeof(ints), bx.axis, sizeof(bx.axis));
+}
+
 }  // namespace
 
 // =============================================================================
@@ -1828,6 +1913,7 @@ int gomcb200_create(gomcb200_engine **out, int device, int nBoxes) {
   CK(cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming));
   CK(e->result2.reserve(64));
   if (const char *ev = getenv("GOMCB200_OVERLAP")) e->overlap = atoi(ev) != 0;
+  if (const char *ev = getenv("GOMCB200_GRAPH")) e->useGraph = atoi(ev) != 0;
   e->nufft = gbn::nufft_create();
   *out = e;
   return 0;
@@ -1844,6 +1930,8 @@ int gomcb200_destroy(gomcb200_engine *e) {
   for (auto &ev : e->ev) cudaEventDestroy(ev);
   gbn::nufft_destroy(e->nufft);
   gbc::comm_destroy(e->comm);
+  for (auto &g : e->stepGraph)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   if (e->evFork) cudaEventDestroy(e->evFork);
   if (e->evJoin) cudaEventDestroy(e->evJoin);
   if (e->stream2) cudaStreamDestroy(e->stream2);
@@ -3501,48 +3589,74 @@ int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
   CK(e->energy3.reserve(4));
   BoxState &bx = e->box[box];
   const bool recipOn = e->ewald && e->electrostatic;
-  const bool fork = recipOn && e->overlap;
-  if (fork) {
-    // structure factor on the second stream, behind the coordinates that are on the first:
-    // its small set-up kernels, and on a sharded engine the all-gather of the FFT slabs, run
-    // under the cell binning and the pair sweep.  The stream and scratch members are
-    // exchanged for the duration of the call so that every helper below queues there.
-    CK(cudaEventRecord(e->evFork, e->stream));
-    CK(cudaStreamWaitEvent(e->stream2, e->evFork, 0));
-    std::swap(e->stream, e->stream2);
-    std::swap(e->blockA, e->blockA2);
-    std::swap(e->result, e->result2);
-    rc = run_recip_sums(e, box, bx.kset[1 - bx.cur]);
-    cudaError_t ce = cudaSuccess;
-    if (!rc) ce = cudaEventRecord(e->evJoin, e->stream);
-    std::swap(e->stream, e->stream2);
-    std::swap(e->blockA, e->blockA2);
-    std::swap(e->result, e->result2);
-    if (rc) return rc;
-    CK(ce);
+  // CUDA graph of the step: only the "coordinates changed" case (re-bin, re-pack), the one
+  // every MC evaluation is
+  gomcb200_engine::StepGraph &sg = e->stepGraph[box];
+  bool done = false;
+  // (not on a sharded engine: a graph replay of the engine's collectives next to a launcher's
+  // own communicator stalled an 8-rank run; the plain path is what was validated there)
+  if (e->useGraph && !e->comm && bx.cellsDirty && bx.packedDirty) {
+    std::vector<unsigned char> key;
+    step_key(e, box, key);
+    if (sg.exec && key == sg.key) {
+      CK(cudaGraphLaunch(sg.exec, e->stream));
+      bx.cellsDirty = bx.packedDirty = false;
+      bx.sumsComplete = sg.sumsComplete;
+      e->launches += sg.launches;
+      done = true;
+    } else {
+      if (sg.exec) {
+        cudaGraphExecDestroy(sg.exec);
+        sg.exec = nullptr;
+      }
+      sg.warm = key == sg.key ? sg.warm + 1 : 0;
+      sg.key = key;
+      if (sg.warm >= 2) {  // buffers and tables have settled: capture this call
+        const long long l0 = e->launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        e->capturing = true;
+        rc = enqueue_full_box(e, box, recipOn);
+        e->capturing = false;
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+        if (!rc && ce == cudaSuccess && graph &&
+            cudaGraphInstantiate(&sg.exec, graph, 0) == cudaSuccess) {
+          sg.launches = e->launches - l0;
+          sg.sumsComplete = bx.sumsComplete;
+          std::vector<unsigned char> after;
+          step_key(e, box, after);
+          if (after == key) {  // nothing was (re)allocated while capturing
+            cudaGraphDestroy(graph);
+            graph = nullptr;
+            CK(cudaGraphLaunch(sg.exec, e->stream));
+            done = true;
+            if (getenv("GOMCB200_GRAPH_VERBOSE"))
+              fprintf(stderr, "[gomc_b200] box %d: step captured as a CUDA graph (%lld launches)\n",
+                      box, sg.launches);
+          } else {
+            cudaGraphExecDestroy(sg.exec);
+            sg.exec = nullptr;
+          }
+        }
+        if (!done) {  // not capturable here: run the plain path from now on
+          if (graph) cudaGraphDestroy(graph);
+          const cudaError_t why = cudaGetLastError();
+          if (getenv("GOMCB200_GRAPH_VERBOSE"))
+            fprintf(stderr, "[gomc_b200] box %d: graph capture failed (rc %d, end %s, last %s)\n",
+                    box, rc, cudaGetErrorString(ce), cudaGetErrorString(why));
+          e->useGraph = false;
+          sg.exec = nullptr;
+          e->launches = l0;
+          bx.cellsDirty = bx.packedDirty = true;
+          rc = 0;
+        }
+      }
+    }
   }
-  rc = run_pair(e, box, false);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(e->energy3.p, e->result.p, 2 * sizeof(double), cudaMemcpyDeviceToDevice,
-                     e->stream));
-  if (fork) {
-    CK(cudaStreamWaitEvent(e->stream, e->evJoin, 0));
-    CK(cudaMemcpyAsync(e->energy3.p + 2, e->result2.p, sizeof(double), cudaMemcpyDeviceToDevice,
-                       e->stream));
-  } else if (recipOn) {
-    rc = run_recip_sums(e, box, bx.kset[1 - bx.cur]);
+  if (!done) {
+    rc = enqueue_full_box(e, box, recipOn);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(e->energy3.p + 2, e->result.p, sizeof(double), cudaMemcpyDeviceToDevice,
-                       e->stream));
-  } else {
-    CK(cudaMemsetAsync(e->energy3.p + 2, 0, sizeof(double), e->stream));
   }
-  // sharded engine with a communicator: the path's only reduction, three doubles, on the
-  // engine's stream; every rank returns the complete energies
-  rc = allreduce_energies(e, e->energy3.p, 3);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(e->hRes + 8, e->energy3.p, 3 * sizeof(double), cudaMemcpyDeviceToHost,
-                     e->stream));
   CK(cudaStreamSynchronize(e->stream));
   const double recip = e->hRes[10];
   timing_end(e, recipOn);

@@ -42,12 +42,17 @@ namespace {
 constexpr int kBrick = 16;     // bin edge in grid points (>= w/2 + 1)
 constexpr int kMaxW = 16;
 
+// bumped by every (re)allocation: a caller that captured CUDA graphs over these buffers
+// compares it to know that its pointers are still the ones in the graph
+long long g_allocGeneration = 0;
+
 template <typename T>
 struct Buf {
   T *p = nullptr;
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
+    ++g_allocGeneration;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -815,6 +820,8 @@ struct Nufft {
 Nufft *nufft_create() { return new Nufft(); }
 void nufft_destroy(Nufft *p) { delete p; }
 const char *nufft_last_error(const Nufft *p) { return p ? p->err.c_str() : ""; }
+
+long long nufft_alloc_generation() { return g_allocGeneration; }
 
 int nufft_choose(const int nmax[3], NufftGrid *g) {
   double sigmaMin = 1e30;

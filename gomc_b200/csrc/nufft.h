@@ -22,6 +22,9 @@ Nufft *nufft_create();
 void nufft_destroy(Nufft *);
 const char *nufft_last_error(const Nufft *);
 
+// Counter bumped by every (re)allocation inside this module (all engines of the process).
+long long nufft_alloc_generation();
+
 // Grid for modes |a| <= nmax[0], |b| <= nmax[1], |c| <= nmax[2] at the accuracy of the
 // widest window.  Returns 0, or -1 when the path does not apply (a mode range of zero).
 int nufft_choose(const int nmax[3], NufftGrid *g);
