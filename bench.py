@@ -394,6 +394,15 @@ def cfg5_record(eng, local, rank, world, dist, torch, flush, steps):
         time_full_box(e, world, dist, torch, flush, None, None, None, 1, False)
     dev, dom, wall, en = time_full_box(e, world, dist, torch, flush, None, None, None, steps, False)
     nk = e.nk
+    # the structure-factor stage alone (inside the step it shares the GPU with the pair sweep)
+    t = []
+    for _ in range(3):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e.mark_coords_changed()
+        e.box_reciprocal_sums(0)
+        t.append(e.last_timing()[1])
+    dom = np.array(t)
     # E2 on the same box: the energy/force work of one MultiParticle trial
     e.set_com(*s.com())
 

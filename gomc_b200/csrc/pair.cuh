@@ -73,9 +73,16 @@ __global__ void k_cell_bounds(int nCells, int n,
   const int cur = t == n ? nCells : sortedKeys[t];
   for (int c = prev + 1; c <= cur; ++c) cellStart[c] = t;
   if (t > 0 && cur != prev) {
-    // the run of key `prev` ends at t; its start is the first position of that key
-    int lo = t - 1;
-    while (lo > 0 && sortedKeys[lo - 1] == prev) --lo;
+    // the run of key `prev` ends at t; its start = lower bound of that key (binary search,
+    // only the ~nCells threads that sit on a run end do it)
+    int lo = 0, hi = t - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sortedKeys[mid] < prev)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
     atomicMax(maxPop, t - lo);
   }
 }
