@@ -1,5 +1,8 @@
 // Structure factor on the INT8 tensor cores (tcgen05.mma kind::i8) -- recip algorithm 3,
-// opt-in (gomcb200_set_recip_algo), exact to a stated bound instead of FP64 round-off.
+// selected with gomcb200_set_recip_algo(e, 3) (the default path is the non-uniform FFT of
+// nufft.cu; this direct sum stays as an independent implementation the parity tests
+// cross-check at full size), exact to a stated bound (energy ~1e-12 relative) instead of
+// FP64 round-off.
 //
 // Same real GEMM as recip_mma.cuh -- C[2*row+{r,i}][2*c+{cz,sz}] = sum_atoms A * B with
 // A = (q/qs) X^a Y^b and B = Z^c -- but every operand is bounded by 1 in magnitude, so each is
