@@ -469,3 +469,39 @@ def test_pair_sweep_dense_cells(dense_cells, per_cell):
             assert res[0][0] == res[1][0]
     finally:
         e.close()
+
+
+def test_full_box_energy_graph_replays():
+    """gomcb200_call_full_box_energy runs on two streams and, from the fourth call on identical
+    inputs, as a replayed CUDA graph.  Every call -- warm-up, capture, replays, and the calls
+    after something the graph bakes in has changed (reference/new sum buffers exchanged by
+    UpdateRecip, another structure-factor algorithm, a fractional molecule) -- must return what
+    the separate entry points return on the same coordinates."""
+    s = SMALL_SYSTEMS["spce_mid"]()
+    e = eng.Engine.from_system(s)
+    rng = np.random.default_rng(21)
+    try:
+        def check(tag):
+            x = np.mod(s.x + rng.uniform(-0.05, 0.05, s.n_atoms), s.axis[0])
+            y = np.mod(s.y + rng.uniform(-0.05, 0.05, s.n_atoms), s.axis[1])
+            z = np.mod(s.z + rng.uniform(-0.05, 0.05, s.n_atoms), s.axis[2])
+            lj, re, rc = e.call_full_box_energy(0, x, y, z)
+            lj2, re2 = e.box_inter(0)
+            rc2 = e.box_reciprocal_sums(0)
+            for a, b in ((lj, lj2), (re, re2), (rc, rc2)):
+                assert abs(a - b) <= 1e-12 * max(abs(b), 1.0), (tag, a, b)
+        for i in range(7):                 # plain, plain, plain, capture, replay ...
+            check(("replay", i))
+        e.update_recip(0)                  # new <-> ref sums exchanged: other buffers
+        for i in range(5):
+            check(("after update_recip", i))
+        e.set_recip_algo(2)                # direct sum instead of the FFT
+        for i in range(5):
+            check(("algo 2", i))
+        e.set_recip_algo(4)
+        e.init_softcore(0.5, 3.0, 2, 1)
+        e.update_lambda(0, 5, int(s.mol_kind[5]), 0.6, 0.4)   # fractional molecule
+        for i in range(5):
+            check(("lambda", i))
+    finally:
+        e.close()
