@@ -12,8 +12,10 @@ namespace gbn {
 struct NufftGrid {
   int n[3];     // fine grid points per axis (powers of two, >= 64)
   int nmax[3];  // largest |mode| per axis (Ewald kmax per axis)
-  int w;        // window width in grid points (even, <= 16)
+  int w;        // window width in grid points (even, <= 16): type 2 (forces), ~1e-13
   double beta;  // exponential-of-semicircle shape parameter
+  int w1;       // width of the type-1 transform (structure factor / energy), ~1e-11 of
+  double beta1; // max |S|: two points narrower where the oversampling allows it
 };
 
 struct Nufft;  // scratch buffers + cached tables; one per engine
