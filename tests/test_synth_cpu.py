@@ -57,3 +57,32 @@ def test_sizes_of_baseline_configs():
         L = round((n_mol / 0.0334) ** (1 / 3), 3)
         recip_rcut = -2.0 * math.log(1e-5) / 10.0
         assert int(recip_rcut * L / (2 * math.pi)) + 1 == kmax_expected
+
+
+def test_pentane_generator_and_two_box_writer(tmp_path):
+    """TraPPE-UA n-pentane (BASELINE configs[2]) and the GEMC two-box input files the
+    GOMC-on-engine runner feeds to the reference executables."""
+    import numpy as np
+    s = synth.make_pentane(64, L=30.0, charged=True)
+    assert s.n_atoms == 5 * 64 and abs(float(np.sum(s.charge))) < 1e-12
+    m = 7
+    sl = slice(s.mol_start[m], s.mol_start[m + 1])
+    r = np.stack([s.x[sl], s.y[sl], s.z[sl]], 1)
+    d = r[1:] - r[:-1]
+    d -= s.axis * np.round(d / s.axis)
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.54, atol=2e-3)      # rounded to 1e-3 A
+    cosang = [-(d[i] @ d[i + 1]) / 1.54 ** 2 for i in range(3)]
+    assert np.allclose(np.degrees(np.arccos(cosang)), 114.0, atol=0.3)
+    v = synth.make_pentane(8, L=40.0, seed=77, charged=True)
+    synth.write_gomc_inputs(s, str(tmp_path), multiparticle=False, run_steps=100, second=v)
+    conf = (tmp_path / "in.conf").read_text()
+    for needle in ("GEMC NVT", "Coordinates 1 box1.pdb", "Structure 1 box1.psf", "SwapFreq",
+                   "RegrowthFreq", "CellBasisVector1 1 40.0", "RcutCoulomb 1"):
+        assert needle in conf, needle
+    psf = (tmp_path / "box1.psf").read_text()
+    assert "%8d !NATOM" % 40 in psf and "%8d !NPHI" % 16 in psf
+    par = (tmp_path / "par.inp").read_text()
+    assert "CH3\tCH2\tCH2\tCH2" in par
+    # single-box output is unchanged by the two-box support
+    synth.write_gomc_inputs(s, str(tmp_path / "one"))
+    assert "GEMC" not in (tmp_path / "one" / "in.conf").read_text()
