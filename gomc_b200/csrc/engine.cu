@@ -1621,9 +1621,12 @@ int run_mol_recip(gomcb200_engine *e, int b, int molIndex, const double *nx,
   return 0;
 }
 
+// sync = false: the caller itself synchronises the stream before it returns to the user
+// (whose buffers must stay untouched only that long), so the kernels can be queued behind
+// the copies at once.
 int upload3(gomcb200_engine *e, DevBuf<double> &dx, DevBuf<double> &dy, DevBuf<double> &dz,
             const double *x, const double *y, const double *z, int first, int count,
-            int limit) {
+            int limit, bool sync = true) {
   if (first < 0 || count < 0 || first + count > limit)
     return fail(GOMCB200_EINVAL, "range [%d,%d) outside [0,%d)", first, first + count, limit);
   if (count == 0) return 0;
@@ -1631,7 +1634,7 @@ int upload3(gomcb200_engine *e, DevBuf<double> &dx, DevBuf<double> &dy, DevBuf<d
   CK(cudaMemcpyAsync(dx.p + first, x, bytes, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemcpyAsync(dy.p + first, y, bytes, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemcpyAsync(dz.p + first, z, bytes, cudaMemcpyHostToDevice, e->stream));
-  CK(cudaStreamSynchronize(e->stream));  // caller may reuse pageable buffers
+  if (sync) CK(cudaStreamSynchronize(e->stream));  // caller may reuse pageable buffers
   return 0;
 }
 
@@ -2207,11 +2210,11 @@ int gomcb200_set_box_cell_basis(gomcb200_engine *e, int box, const double cellBa
   return 0;
 }
 
-int gomcb200_set_coords(gomcb200_engine *e, const double *x, const double *y, const double *z,
-                        int first, int count) {
+static int set_coords_impl(gomcb200_engine *e, const double *x, const double *y, const double *z,
+                           int first, int count, bool sync) {
   if (!e || !e->haveTopo) return fail(GOMCB200_EINVAL, "topology not initialised");
   CK(cudaSetDevice(e->device));
-  int rc = upload3(e, e->x, e->y, e->z, x, y, z, first, count, e->nAtoms);
+  int rc = upload3(e, e->x, e->y, e->z, x, y, z, first, count, e->nAtoms, sync);
   if (rc) return rc;
   if (count > 4096) {
     e->mirrorValid = false;  // refreshed lazily by the next single-molecule call
@@ -2222,6 +2225,11 @@ int gomcb200_set_coords(gomcb200_engine *e, const double *x, const double *y, co
   }
   mark_coords_dirty(e);
   return 0;
+}
+
+int gomcb200_set_coords(gomcb200_engine *e, const double *x, const double *y, const double *z,
+                        int first, int count) {
+  return set_coords_impl(e, x, y, z, first, count, true);
 }
 
 int gomcb200_get_coords(gomcb200_engine *e, double *x, double *y, double *z, int first,
@@ -3574,15 +3582,16 @@ int gomcb200_call_box_force(gomcb200_engine *e, int box, const double *x, const 
   return rc;
 }
 
-int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
-                                  const double *y, const double *z, double *LJEn, double *REn,
-                                  double *energyRecip) {
-  GB_RANGE("energy_system_total(inter,recip)");
+static int full_box_energy_impl(gomcb200_engine *e, int box, const double *x, const double *y,
+                                const double *z, double *LJEn, double *REn,
+                                double *energyRecip) {
   int rc = check_box(e, box);
   if (rc) return rc;
   CK(cudaSetDevice(e->device));
   if (x) {
-    rc = gomcb200_set_coords(e, x, y, z, 0, e->nAtoms);
+    // no host wait between the upload and the kernels: this call synchronises before it
+    // returns, which is as long as the caller's buffers have to stay as they are
+    rc = set_coords_impl(e, x, y, z, 0, e->nAtoms, false);
     if (rc) return rc;
   }
   timing_begin(e);
@@ -3664,6 +3673,17 @@ int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
   if (REn) *REn = e->hRes[9];
   if (energyRecip) *energyRecip = recip;
   return 0;
+}
+
+int gomcb200_call_full_box_energy(gomcb200_engine *e, int box, const double *x,
+                                  const double *y, const double *z, double *LJEn, double *REn,
+                                  double *energyRecip) {
+  GB_RANGE("energy_system_total(inter,recip)");
+  const int rc = full_box_energy_impl(e, box, x, y, z, LJEn, REn, energyRecip);
+  // the coordinate upload is asynchronous: on an early error return it may still be reading
+  // the caller's buffers
+  if (rc && e && x && e->stream) cudaStreamSynchronize(e->stream);
+  return rc;
 }
 
 
