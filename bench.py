@@ -669,12 +669,14 @@ def main():
             "wall_ms_per_step": ms_res_wall,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.workload, s, nk, {
+            # identical to the reference arm's `config` (the driver compares the two)
+            "config": workload_config(args.workload, s, nk),
+            "engine": {
                 "parallelism": f"cell slabs + FFT x-slabs sharded over {world} GPU(s), coordinates "
                                "replicated, NCCL inside the engine (all-gather of the pruned FFT "
                                "slabs, all-reduce of 3 energies)",
                 "recip_algo": recip_algo, "pair_algo": 1 if args.pair_algo is None else args.pair_algo,
-                "timing": "CUDA events on the engine stream around the whole call, max over ranks"}),
+                "timing": "CUDA events on the engine stream around the whole call, max over ranks"},
             "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": 3 * 8 * s.n_atoms, "d2h_bytes_per_step": 24,
                     "timing": "wall clock around gomcb200_call_full_box_energy, pinned host "
