@@ -166,6 +166,44 @@ def cpu_baseline_port(s, budget_s=12.0):
                       "extrapolated linearly in k"}
 
 
+def reference_cpu_sample(s, reps=5):
+    """The reference's own CPU implementation of the step on the host cores (the unmodified
+    GOMC CPU build, oracle/_ref/gomc_probe_NVT, OpenMP over all cores) on a bounded sample:
+    BoxInter over the full box + BoxReciprocalSums / BoxReciprocal on a k-slab sized for ~1.5 s,
+    extrapolated linearly in the number of k-vectors.  None when the probe is not built."""
+    probe = os.path.join(ROOT, "oracle", "_ref", "gomc_probe_NVT")
+    if not os.path.exists(probe):
+        return None
+    from gomc_b200 import synth
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    nk_est = 0
+    if s.ff.ewald:
+        nk_est = len(po.Oracle.from_system(s).recip_init_orth()[0])
+    k_frac = max(1, int(nk_est * s.n_atoms * 40e-9 / cores / 1.5)) if nk_est else 1
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_gomc_inputs(s, d)
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+        r = subprocess.run([probe, "time", "in.conf", "dump.bin", str(k_frac), str(reps)],
+                           cwd=d, env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            return {"error": "reference probe failed: " + r.stderr[-200:]}
+        dmp = po.read_dump(os.path.join(d, "dump.bin"))
+    nk_full, nk_slab = int(dmp["time.nkFull"][0]), int(dmp["time.nkSlab"][0])
+    t_inter = float(np.median(dmp["time.BoxInter"]))
+    t_sums = float(np.median(dmp["time.BoxReciprocalSums.slab"])) if nk_full else 0.0
+    t_rec = float(np.median(dmp["time.BoxReciprocal.slab"])) if nk_full else 0.0
+    scale = nk_full / nk_slab if nk_slab else 0.0
+    t_full = t_inter + (t_sums + t_rec) * scale
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": int(dmp["threads"][0]),
+            "kind": "reference",
+            "sample": f"ESTIMATED from a k-slab: unmodified GOMC CPU build (oracle/_ref): BoxInter "
+                      f"full box ({t_inter:.3f} s) + BoxReciprocalSums/BoxReciprocal on {nk_slab} "
+                      f"of {nk_full} k-vectors ({t_sums:.3f} s), extrapolated linearly in k; "
+                      f"median of {reps} steps",
+            "nk": nk_full}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation on the host cores
     (oracle/_ref probe when it was built, else the C port)."""
@@ -173,50 +211,26 @@ def run_reference(args):
     if rank != 0:
         return 0
     s = make_system(args.workload)
-    cores = os.cpu_count() or 1
-    probe = os.path.join(ROOT, "oracle", "_ref", "gomc_probe_NVT")
-    from gomc_b200 import synth
     from oracle import pyoracle as po
     nk_est = 0
     if s.ff.ewald:
-        o = po.Oracle.from_system(s)
-        nk_est = len(o.recip_init_orth()[0])
+        nk_est = len(po.Oracle.from_system(s).recip_init_orth()[0])
     steps, warm = args.steps, args.warmup
     line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, s, nk_est)}
-    if os.path.exists(probe):
-        # bounded sample: k-slab sized for ~1.5 s per step on this host
-        k_frac = max(1, int(nk_est * s.n_atoms * 40e-9 / cores / 1.5)) if nk_est else 1
-        reps = max(1, min(steps, 8))
-        with tempfile.TemporaryDirectory() as d:
-            synth.write_gomc_inputs(s, d)
-            env = dict(os.environ, OMP_NUM_THREADS=str(cores))
-            r = subprocess.run([probe, "time", "in.conf", "dump.bin", str(k_frac), str(reps)],
-                               cwd=d, env=env, capture_output=True, text=True)
-            if r.returncode != 0:
-                line["unavailable"] = "reference probe failed: " + r.stderr[-200:]
-                print(json.dumps(line))
-                return 0
-            dmp = po.read_dump(os.path.join(d, "dump.bin"))
-        nk_full, nk_slab = int(dmp["time.nkFull"][0]), int(dmp["time.nkSlab"][0])
-        t_inter = float(np.median(dmp["time.BoxInter"]))
-        t_sums = float(np.median(dmp["time.BoxReciprocalSums.slab"])) if nk_full else 0.0
-        t_rec = float(np.median(dmp["time.BoxReciprocal.slab"])) if nk_full else 0.0
-        scale = nk_full / nk_slab if nk_slab else 0.0
-        t_full = t_inter + (t_sums + t_rec) * scale
-        kind, threads = "reference", int(dmp["threads"][0])
-        sample = (f"ESTIMATED from a k-slab: unmodified GOMC CPU build (oracle/_ref): BoxInter full box ({t_inter:.3f} s) "
-                  f"+ BoxReciprocalSums/BoxReciprocal on {nk_slab} of {nk_full} k-vectors "
-                  f"({t_sums:.3f} s), extrapolated linearly in k; median of {reps} steps")
-    else:
+    cb = reference_cpu_sample(s, reps=max(1, min(steps, 8)))
+    if cb is not None and "error" in cb:
+        line["unavailable"] = cb["error"]
+        print(json.dumps(line))
+        return 0
+    if cb is None:
         cb = cpu_baseline_port(s, budget_s=8.0)
-        t_full, kind, threads, sample = 1.0 / cb["value"], "port", cb["cores"], cb["sample"]
-    val = 1.0 / t_full
-    line.update({"value": val, "ms_per_step": 1e3 * t_full,
-                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
-                                  "sample": sample},
+    cb.pop("nk", None)
+    val = cb["value"]
+    line.update({"value": val, "ms_per_step": 1e3 / val,
+                 "cpu_baseline": cb,
                  "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0,
                          "d2h_bytes_per_step": 0},
                  "gpu_launches": 0})
@@ -730,7 +744,13 @@ def main():
                          "host_path_identical": en_res == en_host},
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_port(s)
+            # the same estimator as `--impl reference` (the unmodified reference on the host
+            # cores); the C port only where the reference probe is not built
+            cb = reference_cpu_sample(s, reps=3)
+            if cb is None or "error" in cb:
+                cb = cpu_baseline_port(s)
+            cb.pop("nk", None)
+            line["cpu_baseline"] = cb
         if not args.no_ref_gpu and world == 1:
             line["reference_gpu_build"] = reference_gpu_build(s)
         print(json.dumps(line))
